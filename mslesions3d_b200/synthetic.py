@@ -1,0 +1,116 @@
+"""In-memory synthetic lesion volumes (the benchmark's input spec).
+
+Restates the distribution of the reference's dataset generator without the
+NIfTI round trip (generate_artificial_dataset.py:63-105): uniform noise, then
+``randint(lo, hi) + 1`` axis-aligned cubes of side ``randint(smin, smax)`` at
++0.4 intensity, clipped to [0, 1]; followed by the non-zero z-score
+normalisation the data module applies (datasets.py:403).  Ground-truth boxes use
+the reference's convention ``[min_idx, max_idx] / dims`` in array-axis order with
+an inclusive max index (utils.py:472,500).
+
+Host-side numpy only: this is data preparation, outside the accelerated path.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+try:  # connected components are only needed when cubes touch
+    from scipy.ndimage import label as _cc_label
+except Exception:  # pragma: no cover
+    _cc_label = None
+
+
+def default_object_size(image_size: Sequence[int]) -> Tuple[int, int]:
+    """Object-size range scaled with the volume."""
+    s = int(image_size[0])
+    if tuple(image_size) == (160, 192, 160):
+        return 6, 14
+    return max(2, round(6 * s / 64)), max(3, round(14 * s / 64))
+
+
+def generate_volume(idx: int, image_size: Sequence[int] = (64, 64, 64), num_objects=(1, 5),
+                    object_size=None, random_seed: int = 0, noise: bool = True):
+    """One raw volume + mask + cube list, cf. generate_artificial_dataset.py:63-87.
+
+    Returns (data float64 (D,H,W) in [0,1], mask uint8, cubes [(corner3, side)]).
+    """
+    if object_size is None:
+        object_size = default_object_size(image_size)
+    smin, smax = sorted(int(v) for v in object_size)
+    rng_seed = random_seed + idx
+    np.random.seed(rng_seed)
+    data = np.random.rand(*image_size) if noise else np.zeros(tuple(image_size))
+    mask = np.zeros(tuple(image_size), dtype=np.uint8)
+    n_objects = np.random.randint(*num_objects)
+    cubes = []
+    for _ in range(n_objects + 1):
+        side = np.random.randint(smin, smax)
+        _cls = np.random.randint(0, 1)  # keeps the RNG stream aligned with the generator (n_classes=1)
+        corner = [np.random.randint(0, image_size[a] - side) for a in range(3)]
+        sl = tuple(slice(c, c + side) for c in corner)
+        data[sl] = data[sl] + 0.4 if noise else 1.0
+        data = data.clip(0, 1)
+        mask[sl] = 1
+        cubes.append((tuple(corner), side))
+    return data, mask, cubes
+
+
+def normalize_nonzero(x: np.ndarray) -> np.ndarray:
+    """MONAI ``NormalizeIntensity(nonzero=True)`` semantics (datasets.py:403)."""
+    nz = x != 0
+    if not nz.any():
+        return x.astype(np.float32)
+    sel = x[nz]
+    mean, std = sel.mean(), sel.std()
+    out = x.astype(np.float64).copy()
+    out[nz] = (sel - mean) / (std if std != 0 else 1.0)
+    return out.astype(np.float32)
+
+
+def boxes_from_mask(mask: np.ndarray) -> np.ndarray:
+    """GT boxes [min_idx, max_idx]/dims per connected component (utils.py:446-472,500)."""
+    dims = np.asarray(mask.shape, dtype=np.float64)
+    if _cc_label is None:
+        raise RuntimeError("scipy is required for connected-component GT extraction")
+    lab, n = _cc_label(mask)
+    out = []
+    for k in range(1, n + 1):
+        pos = np.argwhere(lab == k)
+        lo, hi = pos.min(0), pos.max(0)
+        if np.any(hi == lo):
+            continue  # zero-extent boxes are filtered upstream (utils.py:475-481)
+        out.append(np.concatenate([lo / dims, hi / dims]))
+    return np.asarray(out, dtype=np.float32).reshape(-1, 6)
+
+
+def make_batch(batch_size: int, channels: int = 1, image_size: Sequence[int] = (64, 64, 64),
+               first_idx: int = 0, random_seed: int = 0, num_objects=(1, 5), object_size=None,
+               with_boxes: bool = False):
+    """Batch of normalised volumes (N, C, D, H, W) fp32 (+ GT boxes / labels lists).
+
+    Extra channels reuse the same cubes with fresh noise from ``seed + idx + 10**6 * c``
+    (the reference's data modules are single-sequence).
+    """
+    vols = np.empty((batch_size, channels) + tuple(image_size), dtype=np.float32)
+    boxes: List[np.ndarray] = []
+    labels: List[np.ndarray] = []
+    for b in range(batch_size):
+        idx = first_idx + b
+        data, mask, cubes = generate_volume(idx, image_size, num_objects, object_size, random_seed)
+        vols[b, 0] = normalize_nonzero(data)
+        for c in range(1, channels):
+            rs = np.random.RandomState(random_seed + idx + 10 ** 6 * c)
+            extra = rs.rand(*image_size)
+            for corner, side in cubes:
+                sl = tuple(slice(k, k + side) for k in corner)
+                extra[sl] = extra[sl] + 0.4
+            vols[b, c] = normalize_nonzero(extra.clip(0, 1))
+        if with_boxes:
+            bx = boxes_from_mask(mask)
+            boxes.append(bx)
+            labels.append(np.ones((bx.shape[0],), dtype=np.int64))
+    if with_boxes:
+        return vols, boxes, labels
+    return vols

@@ -1,0 +1,471 @@
+"""CPU oracle for the SSD3D hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A restatement, in plain torch-CPU fp32 ops, of the reference's algorithm for the
+path BASELINE.json names.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` leg may import it; the
+product package ``mslesions3d_b200`` never does.
+
+Parity pin: the reference ships no tests or golden vectors of its own (SURVEY.md
+section 8c), so this oracle is pinned against outputs of the UNMODIFIED reference
+run in the build container (``tests/golden/make_golden.py`` -> committed
+``tests/golden/*.pt``; ``tests/test_oracle_golden.py`` replays them anywhere, and
+``tests/test_oracle_vs_reference.py`` re-runs the live comparison when
+``/root/reference`` is mounted).
+
+Every function cites the reference lines (relative to ``lesions3d/``) it follows.
+Each arithmetic step is one separately-rounded fp32 torch op in the reference's
+order, so on the same torch build the results are bit-identical to the reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# channel / repeat / stride plan of the 3-D MobileNet (mobilenet.py:13-20)
+MOBILENET_PLAN = ((64, 1, 2), (128, 2, 2), (256, 2, 2), (512, 6, 2), (1024, 2, 1))
+STEM_CHANNELS = 32
+DEFAULT_ASPECT_RATIOS = {3: [1.0], 5: [1.0], 7: [1]}  # ssd3d.py:25
+BOXES_PER_LOCATION = 2  # hard-coded, ssd3d.py:213
+BN_EPS = 1e-5
+
+
+# --------------------------------------------------------------------------- #
+# architecture bookkeeping
+# --------------------------------------------------------------------------- #
+def backbone_layers(in_channels: int, cube: bool, last_layer: int, width_mult: float = 1.0):
+    """Layer list of the truncated backbone (ssd3d.py:56-75, mobilenet.py:26-41).
+
+    Returns a list of dicts: index 0 is the stem (dense 3^3 conv), the others are
+    depthwise-separable blocks.  ``stride`` is a 3-tuple.
+    """
+    c_in = int(STEM_CHANNELS * width_mult)
+    first = (2, 2, 2) if cube else (1, 2, 2)
+    layers = [dict(kind="stem", cin=in_channels, cout=c_in, stride=first)]
+    for c, n, s in MOBILENET_PLAN:
+        if len(layers) - 1 == last_layer:
+            break
+        c_out = int(c * width_mult)
+        for i in range(n):
+            if len(layers) - 1 == last_layer:
+                break
+            st = s if i == 0 else 1
+            layers.append(dict(kind="block", cin=c_in, cout=c_out, stride=(st, st, st)))
+            c_in = c_out
+    return layers
+
+
+def conv_out_dim(d: int, stride: int) -> int:
+    # 3-wide kernel, padding 1: floor((d + 2 - 3) / s) + 1
+    return (d + 2 - 3) // stride + 1
+
+
+def feature_map_dims(input_size: Sequence[int], layers) -> List[Tuple[int, int, int]]:
+    """Spatial size after every layer (what get_feature_map_infos measures, ssd3d.py:102-110)."""
+    dims = []
+    cur = tuple(int(v) for v in input_size)
+    for L in layers:
+        cur = tuple(conv_out_dim(cur[a], L["stride"][a]) for a in range(3))
+        dims.append(cur)
+    return dims
+
+
+def default_scales(aspect_ratios: Dict[int, list], input_size, min_object_size=6, max_object_size=14):
+    """ssd3d.py:228-232 -- float64 linspace over input_size[0] only."""
+    keys = list(aspect_ratios.keys())
+    vals = np.linspace(min_object_size / input_size[0], max_object_size / input_size[0], len(keys))
+    return {k: v for k, v in zip(keys, vals)}
+
+
+def prior_boxes(input_size, aspect_ratios=None, scales=None, in_channels=1,
+                min_object_size=6, max_object_size=14) -> torch.Tensor:
+    """Default boxes in centre-size form, (P, 6) fp32 (ssd3d.py:286-342).
+
+    Note the axis quirk kept from ssd3d.py:304-309: coordinate 0 follows array
+    axis 1, coordinate 1 follows array axis 0.
+    """
+    if not aspect_ratios:
+        aspect_ratios = DEFAULT_ASPECT_RATIOS
+    if not scales:
+        scales = default_scales(aspect_ratios, input_size, min_object_size, max_object_size)
+    cube = input_size[0] == input_size[1] == input_size[2]
+    layers = backbone_layers(in_channels, cube, max(aspect_ratios.keys()))
+    dims = feature_map_dims(input_size, layers)
+    rows = []
+    for f in aspect_ratios.keys():
+        d0, d1, d2 = dims[f]
+        s = scales[f]
+        for i in range(d0):
+            cy = (i + 0.5) / d0
+            for j in range(d1):
+                cx = (j + 0.5) / d1
+                for k in range(d2):
+                    cz = (k + 0.5) / d2
+                    for ratio in aspect_ratios[f]:
+                        rows.append([cx, cy, cz, s, s, s])
+                        if ratio == 1.0:
+                            for div in range(1, BOXES_PER_LOCATION):
+                                extra = s + s / div
+                                rows.append([cx, cy, cz, extra, extra, extra])
+    out = torch.tensor(np.asarray(rows, dtype=np.float64), dtype=torch.float32)
+    return out.clamp_(0, 1)
+
+
+def prior_boxes_fast(input_size, aspect_ratios=None, scales=None, in_channels=1,
+                     min_object_size=6, max_object_size=14) -> torch.Tensor:
+    """Vectorised float64 equivalent of :func:`prior_boxes` for multi-million-prior configs."""
+    if not aspect_ratios:
+        aspect_ratios = DEFAULT_ASPECT_RATIOS
+    if not scales:
+        scales = default_scales(aspect_ratios, input_size, min_object_size, max_object_size)
+    cube = input_size[0] == input_size[1] == input_size[2]
+    layers = backbone_layers(in_channels, cube, max(aspect_ratios.keys()))
+    dims = feature_map_dims(input_size, layers)
+    chunks = []
+    for f in aspect_ratios.keys():
+        d0, d1, d2 = dims[f]
+        s = float(scales[f])
+        cy = (np.arange(d0, dtype=np.float64) + 0.5) / d0
+        cx = (np.arange(d1, dtype=np.float64) + 0.5) / d1
+        cz = (np.arange(d2, dtype=np.float64) + 0.5) / d2
+        CY, CX, CZ = np.meshgrid(cy, cx, cz, indexing="ij")
+        sizes = []
+        for ratio in aspect_ratios[f]:
+            sizes.append(s)
+            if ratio == 1.0:
+                for div in range(1, BOXES_PER_LOCATION):
+                    sizes.append(s + s / div)
+        per = np.empty((d0, d1, d2, len(sizes), 6), dtype=np.float64)
+        per[..., 0] = CX[..., None]
+        per[..., 1] = CY[..., None]
+        per[..., 2] = CZ[..., None]
+        per[..., 3:] = np.asarray(sizes)[None, None, None, :, None]
+        chunks.append(per.reshape(-1, 6))
+    out = torch.tensor(np.concatenate(chunks, 0), dtype=torch.float32)
+    return out.clamp_(0, 1)
+
+
+# --------------------------------------------------------------------------- #
+# network forward (mobilenet.py:26-49, ssd3d.py:86-100,143-169,248-263)
+# --------------------------------------------------------------------------- #
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _bn_relu(x, sd, prefix, emulate_bf16):
+    w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+    rm, rv = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
+    if not emulate_bf16:
+        return F.relu(F.batch_norm(x, rm, rv, w, b, False, 0.0, BN_EPS))
+    # product-path numerics: fp32 scale/shift epilogue, ReLU, round to bf16 storage
+    scale = w.float() / torch.sqrt(rv.float() + BN_EPS)
+    shift = b.float() - rm.float() * scale
+    y = x * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+    return _bf16(F.relu(y))
+
+
+def forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, aspect_ratios=None,
+            n_classes: int = 2, emulate_bf16: bool = False, return_features: bool = False):
+    """``LSSD3D.forward`` in eval mode -> (locs (N,P,6), scores (N,P,n_classes)).
+
+    ``emulate_bf16=True`` additionally rounds the input, the conv weights and every
+    stored activation to bf16 (the product path's storage precision) while
+    accumulating in fp32 -- used for the tight GPU-vs-oracle comparison.
+    """
+    if not aspect_ratios:
+        aspect_ratios = DEFAULT_ASPECT_RATIOS
+    q = _bf16 if emulate_bf16 else (lambda t: t)
+    cube = image.shape[2] == image.shape[3] == image.shape[4]
+    layers = backbone_layers(image.shape[1], cube, max(aspect_ratios.keys()))
+    x = q(image.float())
+    feats = {}
+    for i, L in enumerate(layers):
+        p = "base.features.%d" % i
+        if L["kind"] == "stem":
+            x = F.conv3d(x, q(sd[p + ".0.weight"].float()), None, L["stride"], 1)
+            x = _bn_relu(x, sd, p + ".1", emulate_bf16)
+        else:
+            x = F.conv3d(x, q(sd[p + ".conv1.weight"].float()), None, L["stride"], 1, 1, L["cin"])
+            x = _bn_relu(x, sd, p + ".bn1", emulate_bf16)
+            x = F.conv3d(x, q(sd[p + ".conv2.weight"].float()), None, 1, 0)
+            x = _bn_relu(x, sd, p + ".bn2", emulate_bf16)
+        if i in aspect_ratios:
+            feats[i] = x
+    n = image.shape[0]
+    locs, scores = [], []
+    for hi, f in enumerate(aspect_ratios.keys()):
+        lw, lb = sd["pred_convs.loc_convs.%d.weight" % hi], sd["pred_convs.loc_convs.%d.bias" % hi]
+        cw, cb = sd["pred_convs.cl_convs.%d.weight" % hi], sd["pred_convs.cl_convs.%d.bias" % hi]
+        l = F.conv3d(feats[f], q(lw.float()), lb.float(), 1, 1)
+        c = F.conv3d(feats[f], q(cw.float()), cb.float(), 1, 1)
+        locs.append(l.permute(0, 2, 3, 4, 1).reshape(n, -1, 6))
+        scores.append(c.permute(0, 2, 3, 4, 1).reshape(n, -1, n_classes))
+    out = (torch.cat(locs, 1), torch.cat(scores, 1))
+    if return_features:
+        return out + (feats,)
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# box geometry (utils.py:42-149)
+# --------------------------------------------------------------------------- #
+def cxcycz_to_xyz(c: torch.Tensor) -> torch.Tensor:
+    """utils.py:50-51."""
+    half = c[:, 3:] / 2
+    return torch.cat([c[:, :3] - half, c[:, :3] + half], 1)
+
+
+def xyz_to_cxcycz(b: torch.Tensor) -> torch.Tensor:
+    """utils.py:101-102."""
+    return torch.cat([(b[:, 3:] + b[:, :3]) / 2, b[:, 3:] - b[:, :3]], 1)
+
+
+def gcxgcygcz_to_cxcycz(g: torch.Tensor, priors: torch.Tensor) -> torch.Tensor:
+    """utils.py:67-68 -- (g*p_wh)/10 + p_c ; exp(g/5)*p_wh."""
+    return torch.cat([g[:, :3] * priors[:, 3:] / 10 + priors[:, :3],
+                      torch.exp(g[:, 3:] / 5) * priors[:, 3:]], 1)
+
+
+def cxcycz_to_gcxgcygcz(c: torch.Tensor, priors: torch.Tensor) -> torch.Tensor:
+    """utils.py:88-89."""
+    return torch.cat([(c[:, :3] - priors[:, :3]) / (priors[:, 3:] / 10),
+                      torch.log(c[:, 3:] / priors[:, 3:]) * 5], 1)
+
+
+def find_intersection3d(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """utils.py:119-122."""
+    lo = torch.max(a[:, None, :3], b[None, :, :3])
+    hi = torch.min(a[:, None, 3:], b[None, :, 3:])
+    d = torch.clamp(hi - lo, min=0)
+    return d[:, :, 0] * d[:, :, 1] * d[:, :, 2]
+
+
+def find_jaccard_overlap3d(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """utils.py:135-149 -- inter / ((vol_a + vol_b) - inter), every op rounded separately."""
+    inter = find_intersection3d(a, b)
+    va = (a[:, 3] - a[:, 0]) * (a[:, 4] - a[:, 1]) * (a[:, 5] - a[:, 2])
+    vb = (b[:, 3] - b[:, 0]) * (b[:, 4] - b[:, 1]) * (b[:, 5] - b[:, 2])
+    union = va[:, None] + vb[None, :] - inter
+    return inter / union
+
+
+def iou_rows_chunked(boxes: torch.Tensor, i0: int, i1: int) -> torch.Tensor:
+    return find_jaccard_overlap3d(boxes[i0:i1], boxes)
+
+
+# --------------------------------------------------------------------------- #
+# detection (ssd3d.py:344-460)
+# --------------------------------------------------------------------------- #
+def greedy_nms(boxes_sorted: torch.Tensor, max_overlap: float, row_chunk: int = 2048) -> torch.Tensor:
+    """ssd3d.py:407-426 -- returns the boolean keep mask over score-sorted boxes.
+
+    The reference materialises the full n x n IoU; here rows are produced in
+    chunks (identical values) so that n ~ 1e5 stays within memory.
+    """
+    n = boxes_sorted.shape[0]
+    suppress = np.zeros(n, dtype=bool)
+    for c0 in range(0, n, row_chunk):
+        c1 = min(n, c0 + row_chunk)
+        over = (iou_rows_chunked(boxes_sorted, c0, c1) > max_overlap).numpy()
+        for r in range(c0, c1):
+            if suppress[r]:
+                continue
+            suppress |= over[r - c0]
+            suppress[r] = False
+    return torch.from_numpy(~suppress)
+
+
+def detect_objects(predicted_locs, predicted_scores, priors_cxcycz, min_score, max_overlap, top_k,
+                   stable: bool = True, return_indices: bool = False):
+    """``LSSD3D.detect_objects`` (ssd3d.py:344-460).
+
+    ``stable=True`` fixes the tie rule the reference leaves unspecified (SURVEY.md
+    M8): equal scores keep ascending prior index.  With tie-free scores this is
+    exactly the reference.  With ``return_indices`` a fourth list carries, per
+    image, the prior index of every returned detection (-1 for the placeholder).
+    """
+    n_img, n_priors, n_classes = predicted_scores.shape
+    assert n_priors == priors_cxcycz.shape[0] == predicted_locs.shape[1]
+    probs = F.softmax(predicted_scores, dim=2)
+    out_b, out_l, out_s, out_i = [], [], [], []
+    for i in range(n_img):
+        decoded = cxcycz_to_xyz(gcxgcygcz_to_cxcycz(predicted_locs[i], priors_cxcycz))
+        ib, il, isc, ii = [], [], [], []
+        for c in range(1, n_classes):
+            cs = probs[i][:, c]
+            above = cs > min_score
+            n_above = int(above.sum())
+            if n_above == 0:
+                continue
+            idx = torch.nonzero(above).flatten()
+            cs = cs[above]
+            cb = decoded[above]
+            cs, order = cs.sort(dim=0, descending=True, stable=stable)
+            cb = cb[order]
+            idx = idx[order]
+            n_keep = min(10 * top_k, n_above)
+            cs, cb, idx = cs[:n_keep], cb[:n_keep], idx[:n_keep]
+            keep = greedy_nms(cb, max_overlap)
+            ib.append(cb[keep])
+            il.append(torch.full((int(keep.sum()),), c, dtype=torch.long))
+            isc.append(cs[keep])
+            ii.append(idx[keep])
+        if not ib:
+            ib.append(torch.tensor([[0., 0., 0., 1., 1., 1.]]))
+            il.append(torch.zeros(1, dtype=torch.long))
+            isc.append(torch.zeros(1))
+            ii.append(torch.full((1,), -1, dtype=torch.long))
+        ib, il, isc, ii = torch.cat(ib, 0), torch.cat(il, 0), torch.cat(isc, 0), torch.cat(ii, 0)
+        if isc.shape[0] > top_k:
+            isc, order = isc.sort(dim=0, descending=True, stable=stable)
+            isc = isc[:top_k]
+            ib = ib[order][:top_k]
+            il = il[order][:top_k]
+            ii = ii[order][:top_k]
+        out_b.append(ib)
+        out_l.append(il)
+        out_s.append(isc)
+        out_i.append(ii)
+    if return_indices:
+        return out_b, out_l, out_s, out_i
+    return out_b, out_l, out_s
+
+
+# --------------------------------------------------------------------------- #
+# prior <-> ground-truth matching and MultiBox loss (ssd3d.py:741-941)
+# --------------------------------------------------------------------------- #
+def parse_threshold(threshold):
+    """ssd3d.py:762-773 -> (mode, t0, t1)."""
+    if isinstance(threshold, list):
+        if len(threshold) == 1:
+            return "hard", float(threshold[0]), float(threshold[0])
+        assert len(threshold) == 2
+        return "soft", float(threshold[0]), float(threshold[1])
+    if isinstance(threshold, float):
+        return "hard", threshold, threshold
+    raise Exception("Type error. Expected float or list of floats for threshold")
+
+
+def match_image(boxes: torch.Tensor, labels: torch.Tensor, priors_cxcycz: torch.Tensor, threshold,
+                chunk: int = 100):
+    """One image of ssd3d.py:786-888 -> (true_classes (P,), true_locs (P,6), overlap (P,), obj (P,), prior_for_obj)."""
+    mode, t0, t1 = parse_threshold(threshold)
+    priors_xyz = cxcycz_to_xyz(priors_cxcycz)
+    n_obj = boxes.shape[0]
+    ov_parts, obj_parts, pfo_parts = [], [], []
+    for s in range(0, n_obj, chunk):
+        part = find_jaccard_overlap3d(boxes[s:s + chunk], priors_xyz)
+        ov, ob = part.max(dim=0)
+        _, pf = part.max(dim=1)
+        ov_parts.append(ov.view(1, -1))
+        obj_parts.append((ob + s).view(1, -1))
+        pfo_parts.append(pf)
+    prior_for_obj = torch.cat(pfo_parts)
+    ov_all = torch.cat(ov_parts)
+    obj_all = torch.cat(obj_parts)
+    overlap, which = ov_all.max(dim=0)
+    obj = obj_all.gather(0, which.view(1, -1)).view(-1)
+    obj[prior_for_obj] = torch.arange(n_obj)          # ssd3d.py:865 (duplicates: last writer wins)
+    overlap[prior_for_obj] = 1.0                      # ssd3d.py:868
+    lab = labels[obj]
+    if mode == "hard":
+        lab[overlap < t0] = 0
+    else:
+        lab[overlap < t0] = 0
+        lab[(overlap >= t0) & (overlap < t1)] = -1
+    true_locs = cxcycz_to_gcxgcygcz(xyz_to_cxcycz(boxes[obj]), priors_cxcycz)
+    return lab, true_locs, overlap, obj, prior_for_obj
+
+
+def multibox_loss(predicted_locs, predicted_scores, boxes: List[torch.Tensor], labels: List[torch.Tensor],
+                  priors_cxcycz, threshold=0.5, neg_pos_ratio=3, hard_negative_mining=False,
+                  return_targets=False):
+    """``MultiBoxLoss.forward`` (ssd3d.py:775-941) -> (conf_loss, loc_loss).
+
+    Default follows the shipped code: confidence loss summed over ALL non-ignored
+    priors / n_positives (ssd3d.py:933).  ``hard_negative_mining=True`` is the
+    variant of the commented-out lines ssd3d.py:926-932.
+    """
+    n_img, n_priors, n_classes = predicted_scores.shape
+    true_locs = torch.zeros((n_img, n_priors, 6), dtype=torch.float)
+    true_classes = torch.zeros((n_img, n_priors), dtype=torch.long)
+    for i in range(n_img):
+        if boxes[i].shape[0] == 0:
+            continue
+        lab, tl, _, _, _ = match_image(boxes[i], labels[i], priors_cxcycz, threshold)
+        true_classes[i] = lab
+        true_locs[i] = tl
+    pos = true_classes > 0
+    loc_loss = (predicted_locs[pos] - true_locs[pos]).abs().mean()
+    n_pos = pos.sum(dim=1)
+    tc = true_classes.view(-1).clone()
+    tc[tc == -1] = 0
+    ce = F.cross_entropy(predicted_scores.view(-1, n_classes), tc, reduction="none").view(n_img, n_priors)
+    ce = ce.clone()
+    ce[true_classes < 0] = 0
+    ce_pos = ce[pos]
+    ce_neg = ce.clone()
+    ce_neg[pos] = 0.0
+    if hard_negative_mining:
+        ce_neg, _ = ce_neg.sort(dim=1, descending=True)
+        ranks = torch.arange(n_priors).unsqueeze(0).expand_as(ce_neg)
+        hard = ranks < (neg_pos_ratio * n_pos).unsqueeze(1)
+        conf_loss = (ce_neg[hard].sum() + ce_pos.sum()) / n_pos.sum().float()
+    else:
+        conf_loss = (ce_neg.sum() + ce_pos.sum()) / n_pos.sum().float()
+    if torch.isnan(loc_loss):
+        raise Exception("Loss is NaN")
+    if return_targets:
+        return conf_loss, loc_loss, true_classes, true_locs
+    return conf_loss, loc_loss
+
+
+# --------------------------------------------------------------------------- #
+# weights
+# --------------------------------------------------------------------------- #
+def random_state_dict(in_channels=1, aspect_ratios=None, n_classes=2, seed=0, randomize_bn=True):
+    """Random-init weights with the reference's 103 state-dict keys/shapes.
+
+    Conv weights ~ kaiming-uniform-like U(-b, b) with b = sqrt(6/fan_in); BN
+    running stats randomised so that folding is exercised.
+    """
+    if not aspect_ratios:
+        aspect_ratios = DEFAULT_ASPECT_RATIOS
+    g = torch.Generator().manual_seed(seed)
+    layers = backbone_layers(in_channels, True, max(aspect_ratios.keys()))
+    sd = {}
+
+    def conv_w(co, ci, k):
+        bound = math.sqrt(6.0 / (ci * k ** 3))
+        return (torch.rand((co, ci, k, k, k), generator=g) * 2 - 1) * bound
+
+    def bn(prefix, c):
+        sd[prefix + ".weight"] = 1.0 + 0.2 * (torch.rand(c, generator=g) - 0.5) if randomize_bn else torch.ones(c)
+        sd[prefix + ".bias"] = 0.1 * torch.randn(c, generator=g) if randomize_bn else torch.zeros(c)
+        sd[prefix + ".running_mean"] = 0.1 * torch.randn(c, generator=g) if randomize_bn else torch.zeros(c)
+        sd[prefix + ".running_var"] = 0.5 + torch.rand(c, generator=g) if randomize_bn else torch.ones(c)
+        sd[prefix + ".num_batches_tracked"] = torch.tensor(0)
+
+    first_pred = min(aspect_ratios.keys())
+    sd["rescale_factors"] = torch.full((1, layers[first_pred]["cout"], 1, 1, 1), 20.0)
+    for i, L in enumerate(layers):
+        p = "base.features.%d" % i
+        if L["kind"] == "stem":
+            sd[p + ".0.weight"] = conv_w(L["cout"], L["cin"], 3)
+            bn(p + ".1", L["cout"])
+        else:
+            sd[p + ".conv1.weight"] = conv_w(L["cin"], 1, 3)
+            bn(p + ".bn1", L["cin"])
+            sd[p + ".conv2.weight"] = conv_w(L["cout"], L["cin"], 1)
+            bn(p + ".bn2", L["cout"])
+    for hi, f in enumerate(aspect_ratios.keys()):
+        c = layers[f]["cout"]
+        nb = len(aspect_ratios[f]) + BOXES_PER_LOCATION - 1
+        sd["pred_convs.loc_convs.%d.weight" % hi] = conv_w(nb * 6, c, 3)
+        sd["pred_convs.loc_convs.%d.bias" % hi] = 0.05 * torch.randn(nb * 6, generator=g)
+        sd["pred_convs.cl_convs.%d.weight" % hi] = conv_w(nb * n_classes, c, 3)
+        sd["pred_convs.cl_convs.%d.bias" % hi] = 0.05 * torch.randn(nb * n_classes, generator=g)
+    return sd

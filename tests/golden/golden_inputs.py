@@ -1,0 +1,93 @@
+"""Seeded inputs shared by ``make_golden.py`` (reference side, build container) and the
+tests that replay the golden outputs (any machine).  Everything here is deterministic
+CPU RNG (numpy MT19937 / torch CPU generator), so inputs are regenerated, not stored.
+"""
+import numpy as np
+import torch
+
+from oracle import ssd3d_oracle as O
+from mslesions3d_b200 import synthetic
+
+PRIOR_CASES = {
+    "cube64": dict(channels=1, size=(64, 64, 64)),
+    "cube96": dict(channels=1, size=(96, 96, 96)),
+    "cube128": dict(channels=2, size=(128, 128, 128)),
+    "noncube": dict(channels=2, size=(32, 64, 48)),
+    "odd40": dict(channels=1, size=(40, 40, 40)),
+    "layer0": dict(channels=2, size=(16, 32, 32), aspect_ratios={0: [1.], 3: [1.]}),
+}
+
+FORWARD_CASES = {
+    "c1_64": dict(channels=1, size=(64, 64, 64), batch=1, seed=0),
+    "c2_48": dict(channels=2, size=(48, 48, 48), batch=2, seed=1),
+    "noncube": dict(channels=2, size=(32, 64, 48), batch=2, seed=2),
+    "odd40": dict(channels=1, size=(40, 40, 40), batch=1, seed=3),
+    "layer0": dict(channels=2, size=(16, 32, 32), batch=1, seed=4, aspect_ratios={0: [1.], 3: [1.]}),
+}
+
+DETECT_CASES = {
+    "default": dict(channels=1, size=(64, 64, 64), batch=3, seed=10, min_score=0.5, max_overlap=0.5, top_k=100),
+    "all_topk50": dict(channels=1, size=(64, 64, 64), batch=2, seed=11, min_score=0.0, max_overlap=0.5, top_k=50),
+    "loose": dict(channels=1, size=(64, 64, 64), batch=2, seed=12, min_score=0.3, max_overlap=0.3, top_k=200),
+    "empty": dict(channels=1, size=(64, 64, 64), batch=2, seed=13, min_score=0.9999999, max_overlap=0.5, top_k=100),
+    "three_class": dict(channels=1, size=(64, 64, 64), batch=2, seed=14, min_score=0.4, max_overlap=0.45,
+                        top_k=60, n_classes=3),
+    "cube96": dict(channels=1, size=(96, 96, 96), batch=1, seed=15, min_score=0.2, max_overlap=0.5, top_k=300),
+}
+
+MATCH_CASES = {
+    "hard05": dict(channels=1, size=(64, 64, 64), seed=20, threshold=0.5, n_obj=[3, 1, 6, 0]),
+    "soft": dict(channels=1, size=(64, 64, 64), seed=21, threshold=[0.1, 0.2], n_obj=[2, 5, 4, 3]),
+    "hardlist": dict(channels=1, size=(64, 64, 64), seed=22, threshold=[0.3], n_obj=[1, 2]),
+    "chunked": dict(channels=1, size=(64, 64, 64), seed=23, threshold=[0.1, 0.2], n_obj=[230, 100, 7]),
+    "three_class": dict(channels=1, size=(96, 96, 96), seed=24, threshold=[0.1, 0.2], n_obj=[4, 9], n_classes=3),
+}
+
+
+def checksum(t: torch.Tensor) -> float:
+    return float(t.double().sum())
+
+
+def forward_inputs(case):
+    """(state_dict, image) for a FORWARD case."""
+    sd = O.random_state_dict(case["channels"], case.get("aspect_ratios"), case.get("n_classes", 2),
+                             seed=100 + case["seed"])
+    x = synthetic.make_batch(case["batch"], case["channels"], case["size"], first_idx=7 * case["seed"])
+    return sd, torch.from_numpy(x)
+
+
+def detect_inputs(case, n_priors):
+    """(predicted_locs (N,P,6), predicted_scores (N,P,C)) with tie-free class probabilities."""
+    g = torch.Generator().manual_seed(case["seed"])
+    n, c = case["batch"], case.get("n_classes", 2)
+    locs = torch.randn(n, n_priors, 6, generator=g) * 0.7
+    scores = torch.randn(n, n_priors, c, generator=g) * 1.5
+    # nudge exact duplicates so that the (unstable) reference sort has a unique answer
+    probs = torch.softmax(scores, 2)
+    for i in range(n):
+        for k in range(1, c):
+            col = probs[i, :, k]
+            if torch.unique(col).numel() != col.numel():
+                raise AssertionError("tie in golden scores; change the seed of case %r" % (case,))
+    return locs, scores
+
+
+def random_gt_boxes(g, n_obj, lo=0.06, hi=0.30):
+    side = lo + (hi - lo) * torch.rand(n_obj, 1, generator=g)
+    side = side.expand(n_obj, 3) * (0.8 + 0.4 * torch.rand(n_obj, 3, generator=g))
+    corner = torch.rand(n_obj, 3, generator=g) * (1.0 - side)
+    return torch.cat([corner, corner + side], 1).float()
+
+
+def match_inputs(case, n_priors):
+    """(predicted_locs, predicted_scores, boxes list, labels list) for a MATCH case."""
+    g = torch.Generator().manual_seed(case["seed"])
+    n = len(case["n_obj"])
+    c = case.get("n_classes", 2)
+    locs = torch.randn(n, n_priors, 6, generator=g) * 0.5
+    scores = torch.randn(n, n_priors, c, generator=g)
+    boxes, labels = [], []
+    for k in case["n_obj"]:
+        boxes.append(random_gt_boxes(g, k))
+        labels.append(torch.randint(1, c, (k,), generator=g))
+    return locs, scores, boxes, labels

@@ -1,0 +1,101 @@
+"""The CPU oracle replayed against golden outputs of the UNMODIFIED reference
+(tests/golden/*.pt, produced by tests/golden/make_golden.py).  Runs anywhere."""
+import pytest
+import torch
+
+from oracle import ssd3d_oracle as O
+from tests.conftest import load_golden
+from tests.golden import golden_inputs as GI
+
+torch.set_num_threads(1)
+
+
+@pytest.mark.parametrize("name", list(GI.PRIOR_CASES))
+def test_priors_match_reference(name):
+    case, gold = GI.PRIOR_CASES[name], load_golden("priors.pt")[name]
+    p = O.prior_boxes(case["size"], case.get("aspect_ratios"), in_channels=case["channels"])
+    assert p.shape[0] == gold["n"]
+    assert torch.equal(p[:4], gold["first"]) and torch.equal(p[-4:], gold["last"])
+    assert float(p.double().sum()) == gold["sum64"]
+    assert torch.equal(p.double().sum(0), gold["colsum64"])
+    if gold["full"] is not None:
+        assert torch.equal(p, gold["full"])
+    assert torch.equal(p, O.prior_boxes_fast(case["size"], case.get("aspect_ratios"), in_channels=case["channels"]))
+
+
+def test_prior_known_answers():
+    # SURVEY.md section 8a row F6 (64^3 probe of the reference)
+    p = O.prior_boxes((64, 64, 64))
+    assert p.shape == (1168, 6)
+    assert p[0].tolist() == [.0625, .0625, .0625, .09375, .09375, .09375]
+    assert p[1].tolist() == [.0625, .0625, .0625, .1875, .1875, .1875]
+    assert p[-1].tolist() == [.75, .75, .75, .4375, .4375, .4375]
+    assert float(p.sum()) == 2289.75
+    assert O.prior_boxes((96, 96, 96)).shape[0] == 3942
+    assert O.prior_boxes_fast((128, 128, 128), in_channels=2).shape[0] == 9344
+    assert O.prior_boxes_fast((160, 192, 160), in_channels=2).shape[0] == 43800
+    assert O.prior_boxes_fast((160, 192, 160), {0: [1.], 3: [1.], 5: [1.], 7: [1.]}, in_channels=2).shape[0] == 2501400
+
+
+@pytest.mark.parametrize("name", list(GI.FORWARD_CASES))
+def test_forward_matches_reference(name):
+    case, gold = GI.FORWARD_CASES[name], load_golden("forward.pt")[name]
+    sd, x = GI.forward_inputs(case)
+    assert GI.checksum(x) == gold["x_sum"], "synthetic input drifted from the golden run"
+    assert GI.checksum(torch.cat([v.flatten().float() for v in sd.values()])) == gold["w_sum"]
+    assert set(sd.keys()) == set(gold["keys"])
+    with torch.no_grad():
+        locs, scores = O.forward(sd, x, case.get("aspect_ratios"), case.get("n_classes", 2))
+    # same torch ops in the same order; only conv algorithm selection may differ by batch shape
+    torch.testing.assert_close(locs, gold["locs"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(scores, gold["scores"], rtol=1e-5, atol=1e-5)
+
+
+def test_box_functions_match_reference():
+    g = load_golden("boxes.pt")
+    a, b, gc = g["a"], g["b"], g["gc"]
+    pri = O.xyz_to_cxcycz(b)
+    assert torch.equal(O.find_intersection3d(a, b), g["inter"])
+    assert torch.equal(O.find_jaccard_overlap3d(a, b), g["iou"])
+    assert torch.equal(O.xyz_to_cxcycz(a), g["cxcycz"])
+    assert torch.equal(O.cxcycz_to_xyz(pri), g["xyz"])
+    assert torch.equal(O.gcxgcygcz_to_cxcycz(gc, pri), g["decoded"])
+    assert torch.equal(O.cxcycz_to_gcxgcygcz(O.xyz_to_cxcycz(b.flip(0)), pri), g["encoded"])
+
+
+@pytest.mark.parametrize("name", list(GI.DETECT_CASES))
+def test_detect_matches_reference(name):
+    case, gold = GI.DETECT_CASES[name], load_golden("detect.pt")[name]
+    priors = O.prior_boxes(case["size"], in_channels=case["channels"])
+    locs, scores = GI.detect_inputs(case, priors.shape[0])
+    assert GI.checksum(torch.cat([locs.flatten(), scores.flatten()])) == gold["in_sum"]
+    b, l, s, idx = O.detect_objects(locs, scores, priors, case["min_score"], case["max_overlap"], case["top_k"],
+                                    return_indices=True)
+    for i in range(case["batch"]):
+        assert torch.equal(l[i], gold["labels"][i])
+        assert torch.equal(s[i], gold["scores"][i])
+        assert torch.equal(b[i], gold["boxes"][i])
+        assert idx[i].shape == l[i].shape
+
+
+@pytest.mark.parametrize("name", list(GI.MATCH_CASES))
+def test_multibox_loss_matches_reference(name):
+    case, gold = GI.MATCH_CASES[name], load_golden("match.pt")[name]
+    priors = O.prior_boxes(case["size"], in_channels=case["channels"])
+    locs, scores, boxes, labels = GI.match_inputs(case, priors.shape[0])
+    conf, loc, tc, tl = O.multibox_loss(locs, scores, boxes, labels, priors, case["threshold"], return_targets=True)
+    assert torch.equal(tc.clamp(min=0), gold["tc"])
+    assert int((tc > 0).sum()) == gold["n_pos"]
+    assert torch.equal(tl[tc > 0], gold["true_locs_pos"])
+    assert torch.equal(conf, gold["conf_loss"])
+    assert torch.equal(loc, gold["loc_loss"])
+
+
+def test_bf16_emulation_is_close_to_fp32():
+    case = GI.FORWARD_CASES["c2_48"]
+    sd, x = GI.forward_inputs(case)
+    with torch.no_grad():
+        l32, s32 = O.forward(sd, x)
+        l16, s16 = O.forward(sd, x, emulate_bf16=True)
+    assert (l32 - l16).abs().max() < 0.15 and (s32 - s16).abs().max() < 0.15
+    assert (l32 - l16).abs().mean() < 0.02
