@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the SSD3D hot path: volumes/sec for forward + decode + NMS (= ``LSSD3D.predict_step``).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): SSD3D-MobileNet inference on synthetic 2-channel 128^3 cube-lesion
+volumes (generate_artificial_dataset.py distribution), batch 8 per GPU, bf16 activations, random-init
+weights with randomised BN statistics.  One step = one predict_step over one batch.  With N > 1 every rank
+runs the same per-GPU batch (independent volumes, no data-path collective): weak scaling.
+
+The single JSON line printed by rank 0 carries
+  value        whole-job volumes/s with the input batches already resident in HBM (device-timed, max over ranks)
+  e2e          the same through the public API from PINNED HOST buffers: H2D of the batch and D2H of the
+               detections inside the timed region
+  roofline     the dominant kernel timed alone with CUDA events, algorithmic bytes / time vs the measured
+               HBM peak of MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (a restatement of the reference's torch-CPU path) on a bounded sample of the
+               same workload, best thread count
+``--impl reference`` times that CPU path alone (rank 0 only) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "SSD3D volumes/sec (fwd+decode+NMS)"
+UNIT = "volumes/s"
+WORKLOAD = "SSD3D-MobileNet inference, 2ch 128^3 synthetic cube-lesion volumes, batch 8 per GPU, bf16"
+CHANNELS, SIZE, BATCH = 2, (128, 128, 128), 8
+MIN_SCORE, MAX_OVERLAP, TOP_K = 0.5, 0.5, 100
+N_ROTATE = 4   # distinct resident input batches: 4 x 67 MB > 126 MB of L2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------
+def make_inputs(n_batches: int, rank: int):
+    """Host fp32 batches (n_batches, BATCH, C, D, H, W) of normalised synthetic volumes."""
+    from mslesions3d_b200 import synthetic
+    out = []
+    for b in range(n_batches):
+        out.append(synthetic.make_batch(BATCH, CHANNELS, SIZE, first_idx=(rank * n_batches + b) * BATCH))
+    return out
+
+
+def cpu_reference_run(volumes, threads: int, repeats: int = 1):
+    """The reference's CPU path (oracle restatement, fp32 torch-CPU ops): forward + detect_objects per volume.
+    Returns seconds per volume."""
+    from oracle import ssd3d_oracle as O
+    torch.set_num_threads(threads)
+    sd = O.random_state_dict(CHANNELS, seed=0)
+    priors = O.prior_boxes_fast(SIZE, in_channels=CHANNELS)
+    x = torch.from_numpy(volumes)
+    with torch.no_grad():
+        O.forward(sd, x[:1])  # warm-up (thread pool, mkldnn primitives)
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            for i in range(x.shape[0]):
+                locs, scores = O.forward(sd, x[i:i + 1])
+                O.detect_objects(locs, scores, priors, MIN_SCORE, MAX_OVERLAP, TOP_K)
+        dt = time.perf_counter() - t0
+    return dt / (repeats * x.shape[0])
+
+
+def best_cpu_baseline(sample_volumes):
+    """Sweep thread counts (oversubscription can be far slower than 1 thread) and keep the best."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({t for t in (1, 2, 4, 8, 16, 32, 64, ncpu) if t <= ncpu})
+    best = None
+    t_start = time.perf_counter()
+    for t in cands:
+        if time.perf_counter() - t_start > 40:
+            break
+        spv = cpu_reference_run(sample_volumes, t)
+        if best is None or spv < best[0]:
+            best = (spv, t)
+    return best
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from mslesions3d_b200 import synthetic
+    sample = synthetic.make_batch(2, CHANNELS, SIZE)
+    spv_probe, threads = best_cpu_baseline(sample[:1])
+    torch.set_num_threads(threads)
+    for _ in range(args.warmup):
+        cpu_reference_run(sample[:1], threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_run(sample, threads)
+    dt = time.perf_counter() - t0
+    vps = args.steps * sample.shape[0] / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": "2 volumes (bounded sample of the batch-8 workload), batch 1 each, "
+                   "fp32 torch-CPU forward + detect_objects"},
+        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "2 volumes per step x %d steps, oracle port of the reference's torch-CPU path, "
+                                   "best of thread sweep (host has %d cpus)" % (args.steps, os.cpu_count() or 1)},
+        "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from mslesions3d_b200 import _lib, ops
+    from mslesions3d_b200.ssd3d import LSSD3D
+    from oracle import ssd3d_oracle as O  # weights only (random_state_dict); never on the timed path
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- model + inputs -------------------------------------------------------------------------
+    sd = O.random_state_dict(CHANNELS, seed=0)
+    model = LSSD3D(n_classes=2, input_channels=CHANNELS, input_size=SIZE, min_score=MIN_SCORE,
+                   max_overlap=MAX_OVERLAP, top_k=TOP_K)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    host_f32 = make_inputs(N_ROTATE, rank)
+    host_bf16 = [torch.from_numpy(h).to(torch.bfloat16).pin_memory() for h in host_f32]
+    dev_bf16 = [h.to(dev) for h in host_bf16]
+    in_bytes = host_bf16[0].numel() * 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    d2h_bytes = [0]
+
+    def step_resident(i):
+        with torch.no_grad():
+            model.predict_step({"img": dev_bf16[i % N_ROTATE]}, i)
+
+    def step_e2e(i):
+        with torch.no_grad():
+            b, l, s = model.predict_step({"img": host_bf16[i % N_ROTATE]}, i)
+            hb = [t.cpu() for t in b]
+            hl = [t.cpu() for t in l]
+            hs = [t.cpu() for t in s]
+        d2h_bytes[0] = sum(t.numel() * t.element_size() for t in hb + hl + hs) + 4 * (BATCH + 2)
+
+    # ---- resident-input throughput (value) --------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.LAUNCHES[0] = 0
+    ms = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES[0]
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * BATCH * args.steps / (ms / 1000.0)
+
+    # ---- end to end from pinned host memory --------------------------------------------------------
+    for i in range(args.warmup):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * BATCH * args.steps / (ms_e2e / 1000.0)
+
+    # ---- dominant kernel alone: roofline ------------------------------------------------------------
+    peak, peak_src = load_peaks()
+    stem = model.base.features[0]
+    w, scale, shift = stem._pack()
+    sd_stride = 2
+    evs = []
+    for i in range(3):
+        ops.stem_conv_bn_relu(dev_bf16[i % N_ROTATE], w, scale, shift, sd_stride)
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.stem_conv_bn_relu(dev_bf16[i % N_ROTATE], w, scale, shift, sd_stride)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    vox_out = BATCH * (SIZE[0] // 2) * (SIZE[1] // 2) * (SIZE[2] // 2)
+    algo_bytes = in_bytes + vox_out * 32 * 2 + 27 * CHANNELS * 32 * 4
+    achieved = algo_bytes / (k_ms / 1000.0) / 1e9
+    roofline = {"kernel": "stem_conv_kernel<bf16,2> (dense 3x3x3 conv 2->32 + BN + ReLU)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms, "peak_source": peak_src}
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        spv, threads = best_cpu_baseline(host_f32[0][:1])
+        spv = min(spv, cpu_reference_run(host_f32[0][:2], threads))
+        cpu = {"value": 1.0 / spv, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "2 volumes of the same 2ch 128^3 workload, batch 1, fp32 torch-CPU oracle port "
+                         "(forward + detect_objects), best of a thread sweep on %d host cpus" % (os.cpu_count() or 1)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
+                       "l2": "inputs rotate over %d resident batches (%d MB) > 126 MB L2" %
+                             (N_ROTATE, N_ROTATE * in_bytes // 2 ** 20),
+                       "min_score": MIN_SCORE, "max_overlap": MAX_OVERLAP, "top_k": TOP_K, "priors": 9344},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

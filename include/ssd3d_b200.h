@@ -1,0 +1,164 @@
+/*
+ * ssd3d_b200.h -- C ABI of libssd3d_b200.so: the sm_100a kernels behind the SSD3D detector hot path.
+ *
+ * The reference (Medical-Image-Analysis-Laboratory/MSLesions3D, lesions3d/) has no FFI of its own: the
+ * path is a chain of torch calls.  Each entry point below replaces one such call site (cited as
+ * file:line, relative to lesions3d/); the Python host in mslesions3d_b200/ binds them with ctypes and
+ * keeps the reference's class/function surface.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; nothing here allocates or frees;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value: 0 on success, a cudaError_t (> 0) from the launch, or an SSD3D_ERR_* code (>= 10001);
+ *   - activations are channels-last-3d (N, D, H, W, C) bf16; conv accumulation is fp32;
+ *   - `nan_flag` (may be NULL) is a device int32 that kernels OR bits into instead of the reference's
+ *     host-synchronising `isnan().sum() > 0` checks (mobilenet.py:46, ssd3d.py:95,258-261):
+ *     bit 0 = backbone activation, bit 1 = locs, bit 2 = class scores.
+ */
+#ifndef SSD3D_B200_H_
+#define SSD3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSD3D_OK 0
+#define SSD3D_ERR_ARG 10001
+#define SSD3D_ERR_TMA 10002
+#define SSD3D_ERR_UNSUPPORTED 10003
+
+#define SSD3D_NAN_BACKBONE 1
+#define SSD3D_NAN_LOCS 2
+#define SSD3D_NAN_SCORES 4
+
+/* Library / build identification ("ssd3d_b200 sm_100a <n>"). */
+const char* ssd3d_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backbone (mobilenet.py:26-49, ssd3d.py:47-100)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Stem: dense Conv3d(Cin->Cout=32, k3, pad 1, stride (sd,2,2), no bias) + BN(eval, as scale/shift) + ReLU.
+ * Replaces mobilenet.py:28-30 as instantiated at ssd3d.py:61.
+ *   x      (N, Cin, D, H, W) NCDHW, fp32 (x_is_bf16 = 0) or bf16 (x_is_bf16 = 1); Cin in 1..4
+ *   w      (27*Cin, 32) fp32, row = tap*Cin + cin, tap = (kd*3+kh)*3+kw   (values already bf16-rounded)
+ *   scale, shift (32) fp32:  y = relu(conv * scale + shift)
+ *   y      (N, Do, Ho, Wo, 32) bf16, Do = (D-1)/sd+1, Ho = (H-1)/2+1, Wo = (W-1)/2+1 */
+int ssd3d_stem_conv_bn_relu(const void* x, int x_is_bf16, const float* w, const float* scale, const float* shift,
+                            void* y, int N, int Cin, int D, int H, int W, int stride_d, void* stream);
+
+/* Depthwise Conv3d(C, C, k3, pad 1, stride s in {1,2}, groups=C, no bias) + BN + ReLU.
+ * Replaces mobilenet.py:38,44 (Block.conv1/bn1).
+ *   x (N, D, H, W, C) bf16;  w (27, C) bf16, row = tap;  scale, shift (C) fp32;  C % 8 == 0
+ *   y (N, Do, Ho, Wo, C) bf16 with Xo = (X-1)/s+1 */
+int ssd3d_dwconv3d_bn_relu(const void* x, const void* w, const float* scale, const float* shift, void* y, int N,
+                           int C, int D, int H, int W, int stride, void* stream);
+
+/* Pointwise Conv3d(Cin->Cout, k1, no bias) + BN + ReLU as a tcgen05/TMEM GEMM with TMA-fed operands.
+ * Replaces mobilenet.py:40,45 (Block.conv2/bn2) and the NaN check at mobilenet.py:46.
+ *   x (M, Cin) bf16 (M = N*D*H*W rows of a channels-last activation);  w (Cout, Cin) bf16
+ *   scale, shift (Cout) fp32;  y (M, Cout) bf16;  Cin % 32 == 0, Cout % 16 == 0 */
+int ssd3d_pwconv_bn_relu(const void* x, const void* w, const float* scale, const float* shift, void* y,
+                         int64_t M, int Cin, int Cout, int* nan_flag, void* stream);
+
+/* SSD head for one feature map: loc conv and class conv (both k3, pad 1, with bias) fused into ONE
+ * tcgen05 implicit GEMM whose epilogue writes straight into the concatenated outputs.
+ * Replaces ssd3d.py:131-132,152-167 (two Conv3d + permute/contiguous/view + cat) and ssd3d.py:258-261.
+ *   x      (N, D, H, W, C) bf16, C % 32 == 0
+ *   w      (NPAD, 27*C) bf16, K index = tap*C + c; rows [0, bpl*6) = loc conv out channels, rows
+ *          [bpl*6, bpl*(6+n_classes)) = class conv out channels, remaining rows zero; NPAD % 16 == 0
+ *   bias   (NPAD) fp32
+ *   locs   (N, P, 6) fp32, scores (N, P, n_classes) fp32; this layer writes priors
+ *          [prior_offset, prior_offset + D*H*W*bpl) of every image, prior = ((d*H+h)*W+w)*bpl + b */
+int ssd3d_head_conv(const void* x, const void* w, const float* bias, float* locs, float* scores, int N, int C,
+                    int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset,
+                    int* nan_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Box geometry (utils.py:42-149).  All fp32, every arithmetic step separately rounded (no FMA).
+ * ---------------------------------------------------------------------------------------------- */
+#define SSD3D_BOX_CXCYCZ_TO_XYZ 0         /* utils.py:50-51   */
+#define SSD3D_BOX_XYZ_TO_CXCYCZ 1         /* utils.py:101-102 */
+#define SSD3D_BOX_GCXGCYGCZ_TO_CXCYCZ 2   /* utils.py:67-68   (needs priors) */
+#define SSD3D_BOX_CXCYCZ_TO_GCXGCYGCZ 3   /* utils.py:88-89   (needs priors) */
+int ssd3d_box_transform(int mode, const float* in, const float* priors, float* out, int64_t n, void* stream);
+
+/* All-pairs intersection volume (want_iou = 0, utils.py:119-122) or Jaccard overlap (want_iou = 1,
+ * utils.py:135-149) of boxes a (n1,6) and b (n2,6) in boundary coordinates -> out (n1, n2). */
+int ssd3d_iou3d_pairwise(const float* a, const float* b, float* out, int64_t n1, int64_t n2, int want_iou,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Detection: softmax + decode + score filter + sort + greedy 3-D NMS + top-k  (ssd3d.py:344-460)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bytes of scratch the detect call needs for the given problem (device memory, 256-byte aligned). */
+int64_t ssd3d_detect_workspace_bytes(int N, int64_t P, int n_classes, int top_k);
+
+/* One call = LSSD3D.detect_objects for the whole batch, no host synchronisation inside.
+ *   locs (N,P,6), scores (N,P,n_classes) fp32 raw head outputs; priors (P,6) centre-size fp32
+ *   min_score, max_overlap: thresholds already rounded to fp32 (strict > in both, ssd3d.py:388,422)
+ *   Outputs, padded to top_k rows per image (rows >= out_count[i] are undefined):
+ *     out_boxes (N, top_k, 6) fp32 boundary coords, out_scores (N, top_k) fp32,
+ *     out_labels (N, top_k) int64, out_prior (N, top_k) int64 (prior index of each detection, -1 for
+ *     the placeholder), out_count (N) int32.
+ *   An image with no surviving box gets the reference's placeholder [0,0,0,1,1,1] / label 0 / score 0
+ *   (ssd3d.py:437-440) and count 1.
+ *   Tie rule for equal scores: ascending prior index (the stable order; the reference's sort is
+ *   unspecified there).
+ *   Limit of this version: candidates above min_score per (image, class) <= SSD3D_SORT_MAX; beyond it
+ *   the call sets bit 0 of *status (device int32, may be NULL) and truncates. */
+#define SSD3D_SORT_MAX 16384
+int ssd3d_detect_objects(const float* locs, const float* scores, const float* priors, int N, int64_t P,
+                         int n_classes, float min_score, float max_overlap, int top_k, float* out_boxes,
+                         float* out_scores, int64_t* out_labels, int64_t* out_prior, int32_t* out_count,
+                         void* workspace, int64_t workspace_bytes, int32_t* status, void* stream);
+
+/* Stage entry points (used by the stage-wise parity tests and by callers that want the pieces). */
+
+/* softmax over classes + decode to boundary coords: probs (N, P, n_classes), boxes (N, P, 6). */
+int ssd3d_decode_softmax(const float* locs, const float* scores, const float* priors, int N, int64_t P,
+                         int n_classes, float* probs, float* boxes_xyz, void* stream);
+
+/* Greedy NMS over n boxes ALREADY sorted by descending score: keep (n) uint8, 1 = kept
+ * (ssd3d.py:407-426).  mask_ws must hold n * ceil(n/64) uint64. */
+int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_overlap, uint8_t* keep, void* mask_ws,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training: prior <-> ground-truth matching and the MultiBox loss (ssd3d.py:741-941)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Matching + labelling + target encoding for a batch (ssd3d.py:786-888).
+ *   gt_boxes (T, 6) fp32 boundary coords, all images concatenated; gt_labels (T) int64;
+ *   gt_offsets (N+1) int32 prefix offsets (image i owns [gt_offsets[i], gt_offsets[i+1])), T = total
+ *   priors_cxcycz (P, 6); thresholds t0 <= t1 (hard mode: t0 == t1), fp32-rounded
+ *   true_classes (N, P) int64 in {-1, 0, 1..}; true_locs (N, P, 6) fp32
+ *   overlap (N,P) fp32 and object_for_prior (N,P) int32: per-prior best IoU / object after the
+ *   force-match; prior_for_object (T) int32: first-max prior of each object (ssd3d.py:811)
+ *   best_key_ws: T * 8 bytes of scratch.  Images with no object are all background with zero targets
+ *   (ssd3d.py:854-855).  Tie rules: first maximum (torch.max), last writer wins in the force-match. */
+int ssd3d_match_priors(const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets, int N,
+                       int64_t T, const float* priors_cxcycz, int64_t P, float t0, float t1,
+                       int64_t* true_classes, float* true_locs, float* overlap, int32_t* object_for_prior,
+                       int32_t* prior_for_object, void* best_key_ws, void* stream);
+
+/* MultiBox loss forward + analytic backward (ssd3d.py:891-941).
+ *   out_loss (2) fp32 = {conf_loss, loc_loss}; n_pos_out (1) int32
+ *   grad_locs (N,P,6), grad_scores (N,P,n_classes): d(conf_loss + alpha*loc_loss)/d input, may be NULL
+ *   hard_negative_mining = 0 reproduces the shipped loss (all negatives, ssd3d.py:933); = 1 the
+ *   commented variant (ssd3d.py:926-932) with neg_pos_ratio.
+ *   workspace: ssd3d_multibox_workspace_bytes(N, P). */
+int64_t ssd3d_multibox_workspace_bytes(int N, int64_t P);
+int ssd3d_multibox_loss(const float* locs, const float* scores, const int64_t* true_classes,
+                        const float* true_locs, int N, int64_t P, int n_classes, float alpha,
+                        int hard_negative_mining, int neg_pos_ratio, float* out_loss, int32_t* n_pos_out,
+                        float* grad_locs, float* grad_scores, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSD3D_B200_H_ */

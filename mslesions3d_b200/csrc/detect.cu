@@ -1,0 +1,474 @@
+// LSSD3D.detect_objects on the device (ssd3d.py:344-460), batched over images and classes, with no
+// host synchronisation inside:
+//   1. decode_filter : softmax over classes, decode offsets -> boundary boxes (utils.py:50-68), keep
+//                      candidates with score > min_score (warp-ballot compaction into per-(image,class) lists)
+//   2. sort_segments : per (image,class) bitonic sort of 64-bit keys {~orderable(score), prior index}
+//                      = descending score, ascending prior index on ties; truncate to 10*top_k
+//   3. nms_mask      : IoU > max_overlap bit matrix (64-bit words) over the sorted candidates
+//   4. nms_select    : greedy scan of the bit matrix (ssd3d.py:414-426), per-image merge of the classes,
+//                      final top-k cut (ssd3d.py:449-453), placeholder for empty images (ssd3d.py:437-440)
+#include "boxes.cuh"
+
+namespace ssd3d {
+
+// ------------------------------------------------------------------------------------------------
+// stage 1: softmax + decode (+ filter)
+// ------------------------------------------------------------------------------------------------
+// softmax of one prior's class scores: exp(x - max) * (1 / sum), classes summed in index order
+template <typename F>
+__device__ __forceinline__ void softmax_small(const float* s, int C, F&& emit) {
+  float m = s[0];
+  for (int k = 1; k < C; ++k) m = fmaxf(m, s[k]);
+  float sum = 0.f;
+  for (int k = 0; k < C; ++k) sum = __fadd_rn(sum, expf(__fsub_rn(s[k], m)));
+  const float inv = __fdiv_rn(1.0f, sum);
+  for (int k = 0; k < C; ++k) emit(k, __fmul_rn(expf(__fsub_rn(s[k], m)), inv));
+}
+
+__global__ void __launch_bounds__(256) decode_softmax_kernel(const float* __restrict__ locs,
+                                                             const float* __restrict__ scores,
+                                                             const float* __restrict__ priors, long long P, int C,
+                                                             float* __restrict__ probs, float* __restrict__ boxes) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int img = blockIdx.y;
+  if (p >= P) return;
+  const long long ip = (long long)img * P + p;
+  const Box6 xyz = cxcycz_to_xyz(gcxgcygcz_to_cxcycz(load_box(locs + ip * 6), load_box(priors + p * 6)));
+  store_box(boxes + ip * 6, xyz);
+  const float* s = scores + ip * C;
+  float* o = probs + ip * C;
+  softmax_small(s, C, [&](int k, float v) { o[k] = v; });
+}
+
+// cand layout: segment seg = img*(C-1) + (c-1) owns cand[seg*P .. seg*P + count[seg])
+__global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restrict__ locs,
+                                                            const float* __restrict__ scores,
+                                                            const float* __restrict__ priors, long long P, int C,
+                                                            float min_score, float* __restrict__ boxes,
+                                                            unsigned long long* __restrict__ cand,
+                                                            int* __restrict__ count) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int img = blockIdx.y;
+  const bool live = p < P;
+  const long long ip = (long long)img * P + (live ? p : 0);
+  if (live) {
+    const Box6 xyz = cxcycz_to_xyz(gcxgcygcz_to_cxcycz(load_box(locs + ip * 6), load_box(priors + p * 6)));
+    store_box(boxes + ip * 6, xyz);
+  }
+  const float* s = scores + ip * C;
+  const int lane = threadIdx.x & 31;
+  // every lane walks the classes together so that the ballots are warp-uniform
+  float m = s[0];
+  for (int k = 1; k < C; ++k) m = fmaxf(m, s[k]);
+  float sum = 0.f;
+  for (int k = 0; k < C; ++k) sum = __fadd_rn(sum, expf(__fsub_rn(s[k], m)));
+  const float inv = __fdiv_rn(1.0f, sum);
+  for (int c = 1; c < C; ++c) {
+    const float prob = __fmul_rn(expf(__fsub_rn(s[c], m)), inv);
+    const bool pass = live && (prob > min_score);
+    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+    if (ballot == 0u) continue;
+    const int seg = img * (C - 1) + (c - 1);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&count[seg], __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pass) {
+      const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+      const unsigned long long key =
+          ((unsigned long long)(~float_orderable(prob)) << 32) | (unsigned long long)(uint32_t)p;
+      cand[(long long)seg * P + slot] = key;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 2: per-segment sort (shared-memory bitonic network on 64-bit keys)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) sort_segments_kernel(unsigned long long* __restrict__ cand,
+                                                             const int* __restrict__ count, int* __restrict__ nkeep,
+                                                             const float* __restrict__ boxes, long long P, int C,
+                                                             int nmax, int sort_cap, float* __restrict__ sboxes,
+                                                             float* __restrict__ sscores, int* __restrict__ sprior,
+                                                             int* __restrict__ status) {
+  extern __shared__ unsigned long long keys[];
+  const int seg = blockIdx.x;
+  const int img = seg / (C - 1);
+  int n = count[seg];
+  if (n > sort_cap) {
+    if (threadIdx.x == 0 && status) atomicOr(status, 1);
+    n = sort_cap;
+  }
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  unsigned long long* src = cand + (long long)seg * P;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) keys[i] = (i < n) ? src[i] : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  const int nk = n < nmax ? n : nmax;
+  if (threadIdx.x == 0) nkeep[seg] = nk;
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+    const unsigned long long key = keys[i];
+    const uint32_t p = (uint32_t)(key & 0xffffffffull);
+    const long long o = (long long)seg * nmax + i;
+    sprior[o] = (int)p;
+    sscores[o] = float_from_orderable(~(uint32_t)(key >> 32));
+    store_box(sboxes + o * 6, load_box(boxes + ((long long)img * P + p) * 6));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 3: suppression bit matrix.  mask[seg][i][w] bit b  <=>  j = 64 w + b > i  and  IoU(i, j) > thr
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sboxes, const int* __restrict__ nkeep,
+                                                      int n_fixed, long long seg_stride_boxes, int words,
+                                                      long long seg_stride_mask, float thr,
+                                                      unsigned long long* __restrict__ mask) {
+  const int cb = blockIdx.x, rb = blockIdx.y, seg = blockIdx.z;
+  if (cb < rb) return;
+  const int n = nkeep ? nkeep[seg] : n_fixed;
+  if (rb * 64 >= n || cb * 64 >= n) return;
+  __shared__ float cbox[64][6];
+  __shared__ float cvol[64];
+  const float* base = sboxes + (long long)seg * seg_stride_boxes;
+  const int t = threadIdx.x;
+  const int cj = cb * 64 + t;
+  if (cj < n) {
+    const Box6 b = load_box(base + (long long)cj * 6);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cbox[t][k] = b.v[k];
+    cvol[t] = box_volume(b);
+  }
+  __syncthreads();
+  const int i = rb * 64 + t;
+  if (i >= n) return;
+  const Box6 a = load_box(base + (long long)i * 6);
+  const float va = box_volume(a);
+  const int jn = min(64, n - cb * 64);
+  unsigned long long bits = 0ull;
+  for (int b = 0; b < jn; ++b) {
+    const int j = cb * 64 + b;
+    Box6 o;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o.v[k] = cbox[b][k];
+    if (j > i && box_iou(a, va, o, cvol[b]) > thr) bits |= (1ull << b);
+  }
+  mask[(long long)seg * seg_stride_mask + (long long)i * words + cb] = bits;
+}
+
+// Greedy scan of one segment's bit matrix (rows are `row_stride` words apart).  `removed` is shared
+// scratch of ceil(n/64) 64-bit words, `keptw` receives the keep bits.  Only words cb >= rb of row i
+// were written by nms_mask_kernel, and only those are read.  Called by all threads of the block.
+__device__ void nms_scan(const unsigned long long* __restrict__ mask, int n, int row_stride,
+                         unsigned long long* removed, unsigned long long* keptw, unsigned long long* diag) {
+  const int words = (n + 63) >> 6;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0ull;
+  __syncthreads();
+  for (int k = 0; k < words; ++k) {
+    const int rows = min(64, n - k * 64);
+    if (threadIdx.x < 64) diag[threadIdx.x] = (threadIdx.x < rows) ? mask[(long long)(k * 64 + threadIdx.x) * row_stride + k] : 0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long cur = removed[k], kept = 0ull;
+      for (int b = 0; b < rows; ++b) {
+        if (!((cur >> b) & 1ull)) {
+          kept |= (1ull << b);
+          cur |= diag[b];
+        }
+      }
+      keptw[k] = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = keptw[k];
+    // OR the rows of this chunk's kept boxes into the later words
+    for (int w = k + 1 + (int)threadIdx.x; w < words; w += blockDim.x) {
+      unsigned long long acc = removed[w];
+      unsigned long long kk = kept;
+      while (kk) {
+        const int b = __ffsll((long long)kk) - 1;
+        kk &= kk - 1;
+        acc |= mask[(long long)(k * 64 + b) * row_stride + w];
+      }
+      removed[w] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 4: per image: scan every class, merge, top-k, write outputs
+// ------------------------------------------------------------------------------------------------
+// number of entries of the descending list s[0..n) that are > v (strict) or >= v
+__device__ __forceinline__ int count_greater(const float* s, int n, float v, bool or_equal) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const bool before = or_equal ? (s[mid] >= v) : (s[mid] > v);
+    if (before) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) nms_select_kernel(const unsigned long long* __restrict__ mask,
+                                                         const int* __restrict__ nkeep, int C, int nmax, int words_max,
+                                                         const float* __restrict__ sboxes,
+                                                         const float* __restrict__ sscores,
+                                                         const int* __restrict__ sprior, int* __restrict__ kept_pos,
+                                                         float* __restrict__ kept_score, int* __restrict__ kept_cnt,
+                                                         int top_k, float* __restrict__ out_boxes,
+                                                         float* __restrict__ out_scores, long long* __restrict__ out_labels,
+                                                         long long* __restrict__ out_prior, int* __restrict__ out_count) {
+  extern __shared__ unsigned long long sm[];
+  unsigned long long* removed = sm;
+  unsigned long long* keptw = sm + words_max;
+  unsigned long long* diag = sm + 2 * words_max;
+  __shared__ int s_total;
+  const int img = blockIdx.x;
+  const int nseg = C - 1;
+
+  // ---- greedy NMS per class; compact kept positions (in sorted order) ----
+  for (int c = 0; c < nseg; ++c) {
+    const int seg = img * nseg + c;
+    const int n = nkeep[seg];
+    const int words = (n + 63) >> 6;
+    int* kp = kept_pos + (long long)seg * nmax;
+    float* ks = kept_score + (long long)seg * nmax;
+    if (n > 0) {
+      nms_scan(mask + (long long)seg * nmax * words_max, n, words_max, removed, keptw, diag);
+      __syncthreads();
+      // exclusive prefix of the kept counts per word (kept in `removed`, which the scan is done with)
+      if (threadIdx.x == 0) {
+        int run = 0;
+        for (int w = 0; w < words; ++w) {
+          removed[w] = (unsigned long long)run;
+          run += __popcll(keptw[w]);
+        }
+        kept_cnt[seg] = run;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long kw = keptw[i >> 6];
+        if ((kw >> (i & 63)) & 1ull) {
+          const int pos = (int)removed[i >> 6] + __popcll(kw & ((1ull << (i & 63)) - 1ull));
+          kp[pos] = i;
+          ks[pos] = sscores[(long long)seg * nmax + i];
+        }
+      }
+    } else if (threadIdx.x == 0) {
+      kept_cnt[seg] = 0;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int c = 0; c < nseg; ++c) t += kept_cnt[img * nseg + c];
+    s_total = t;
+  }
+  __syncthreads();
+  const int total = s_total;
+  float* ob = out_boxes + (long long)img * top_k * 6;
+  float* os = out_scores + (long long)img * top_k;
+  long long* ol = out_labels + (long long)img * top_k;
+  long long* op = out_prior + (long long)img * top_k;
+
+  if (total == 0) {  // ssd3d.py:437-440
+    if (threadIdx.x == 0) {
+      ob[0] = 0.f; ob[1] = 0.f; ob[2] = 0.f; ob[3] = 1.f; ob[4] = 1.f; ob[5] = 1.f;
+      os[0] = 0.f;
+      ol[0] = 0;
+      op[0] = -1;
+      out_count[img] = 1;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) out_count[img] = total < top_k ? total : top_k;
+
+  // ---- merge classes.  total <= top_k: concatenation in class order (ssd3d.py:443-446).  Otherwise
+  // the stable descending sort of the concatenation (ssd3d.py:449-453): an entry's rank is its own
+  // position in its class list + entries of earlier classes with score >= its score + entries of later
+  // classes with score > its score. ----
+  int class_base = 0;
+  for (int c = 0; c < nseg; ++c) {
+    const int seg = img * nseg + c;
+    const int cnt = kept_cnt[seg];
+    const int* kp = kept_pos + (long long)seg * nmax;
+    const float* ks = kept_score + (long long)seg * nmax;
+    for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+      int rank;
+      if (total <= top_k) {
+        rank = class_base + r;
+      } else {
+        const float v = ks[r];
+        rank = r;
+        for (int c2 = 0; c2 < nseg; ++c2) {
+          if (c2 == c) continue;
+          const int seg2 = img * nseg + c2;
+          rank += count_greater(kept_score + (long long)seg2 * nmax, kept_cnt[seg2], v, c2 < c);
+        }
+      }
+      if (rank < top_k) {
+        const long long src = (long long)seg * nmax + kp[r];
+        store_box(ob + (long long)rank * 6, load_box(sboxes + src * 6));
+        os[rank] = sscores[src];
+        ol[rank] = (long long)(c + 1);
+        op[rank] = (long long)sprior[src];
+      }
+    }
+    class_base += cnt;
+  }
+}
+
+// standalone scan for ssd3d_nms3d_sorted
+__global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int words,
+                                                       uint8_t* __restrict__ keep) {
+  extern __shared__ unsigned long long sm[];
+  unsigned long long* removed = sm;
+  unsigned long long* keptw = sm + words;
+  unsigned long long* diag = sm + 2 * words;
+  nms_scan(mask, n, words, removed, keptw, diag);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) keep[i] = (uint8_t)((keptw[i >> 6] >> (i & 63)) & 1ull);
+}
+
+static inline long long align256(long long v) { return (v + 255) & ~255ll; }
+
+struct DetectLayout {
+  int S, nmax, words;
+  long long off_count, off_nkeep, off_keptcnt, off_boxes, off_cand, off_sboxes, off_sscores, off_sprior, off_mask,
+      off_keptpos, off_keptscore, total;
+};
+
+static DetectLayout detect_layout(int N, long long P, int C, int top_k) {
+  DetectLayout L;
+  L.S = N * (C - 1);
+  long long nm = 10ll * (long long)top_k;
+  if (nm > P) nm = P;
+  if (nm > SSD3D_SORT_MAX) nm = SSD3D_SORT_MAX;
+  if (nm < 1) nm = 1;
+  L.nmax = (int)nm;
+  L.words = (L.nmax + 63) / 64;
+  long long o = 0;
+  L.off_count = o; o += align256(4ll * L.S);
+  L.off_nkeep = o; o += align256(4ll * L.S);
+  L.off_keptcnt = o; o += align256(4ll * L.S);
+  L.off_boxes = o; o += align256(4ll * N * P * 6);
+  L.off_cand = o; o += align256(8ll * L.S * P);
+  L.off_sboxes = o; o += align256(4ll * L.S * L.nmax * 6);
+  L.off_sscores = o; o += align256(4ll * L.S * L.nmax);
+  L.off_sprior = o; o += align256(4ll * L.S * L.nmax);
+  L.off_mask = o; o += align256(8ll * L.S * L.nmax * L.words);
+  L.off_keptpos = o; o += align256(4ll * L.S * L.nmax);
+  L.off_keptscore = o; o += align256(4ll * L.S * L.nmax);
+  L.total = o;
+  return L;
+}
+
+}  // namespace ssd3d
+
+using namespace ssd3d;
+
+extern "C" int64_t ssd3d_detect_workspace_bytes(int N, int64_t P, int n_classes, int top_k) {
+  if (N <= 0 || P <= 0 || n_classes < 2 || top_k <= 0) return 0;
+  return detect_layout(N, P, n_classes, top_k).total;
+}
+
+extern "C" int ssd3d_decode_softmax(const float* locs, const float* scores, const float* priors, int N, int64_t P,
+                                    int n_classes, float* probs, float* boxes_xyz, void* stream) {
+  if (!locs || !scores || !priors || !probs || !boxes_xyz || N <= 0 || P <= 0 || n_classes < 1) return SSD3D_ERR_ARG;
+  dim3 grid((unsigned)((P + 255) / 256), (unsigned)N);
+  decode_softmax_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(locs, scores, priors, P, n_classes, probs,
+                                                                            boxes_xyz);
+  SSD3D_CHECK_LAUNCH();
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_overlap, uint8_t* keep, void* mask_ws,
+                                  void* stream) {
+  if (!boxes_xyz || !keep || !mask_ws || n <= 0 || n > 131072) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int words = (int)((n + 63) / 64);
+  dim3 grid((unsigned)words, (unsigned)words, 1);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(boxes_xyz, nullptr, (int)n, 0, words, 0, max_overlap,
+                                       static_cast<unsigned long long*>(mask_ws));
+  SSD3D_CHECK_LAUNCH();
+  const size_t smem = (size_t)(2 * words + 64) * 8;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  nms_scan_kernel<<<1, 256, smem, st>>>(static_cast<const unsigned long long*>(mask_ws), (int)n, words, keep);
+  SSD3D_CHECK_LAUNCH();
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, const float* priors, int N, int64_t P,
+                                    int n_classes, float min_score, float max_overlap, int top_k, float* out_boxes,
+                                    float* out_scores, int64_t* out_labels, int64_t* out_prior, int32_t* out_count,
+                                    void* workspace, int64_t workspace_bytes, int32_t* status, void* stream) {
+  if (!locs || !scores || !priors || !out_boxes || !out_scores || !out_labels || !out_prior || !out_count || !workspace)
+    return SSD3D_ERR_ARG;
+  if (N <= 0 || P <= 0 || n_classes < 2 || top_k <= 0 || P > 0x7fffffffll) return SSD3D_ERR_ARG;
+  const DetectLayout L = detect_layout(N, P, n_classes, top_k);
+  if (workspace_bytes < L.total) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* count = reinterpret_cast<int*>(ws + L.off_count);
+  int* nkeep = reinterpret_cast<int*>(ws + L.off_nkeep);
+  int* keptcnt = reinterpret_cast<int*>(ws + L.off_keptcnt);
+  float* boxes = reinterpret_cast<float*>(ws + L.off_boxes);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + L.off_cand);
+  float* sboxes = reinterpret_cast<float*>(ws + L.off_sboxes);
+  float* sscores = reinterpret_cast<float*>(ws + L.off_sscores);
+  int* sprior = reinterpret_cast<int*>(ws + L.off_sprior);
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + L.off_mask);
+  int* keptpos = reinterpret_cast<int*>(ws + L.off_keptpos);
+  float* keptscore = reinterpret_cast<float*>(ws + L.off_keptscore);
+
+  cudaError_t e = cudaMemsetAsync(count, 0, (size_t)(L.off_boxes - L.off_count), st);
+  if (e != cudaSuccess) return (int)e;
+  if (status) {
+    e = cudaMemsetAsync(status, 0, 4, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  {
+    dim3 grid((unsigned)((P + 255) / 256), (unsigned)N);
+    decode_filter_kernel<<<grid, 256, 0, st>>>(locs, scores, priors, P, n_classes, min_score, boxes, cand, count);
+    SSD3D_CHECK_LAUNCH();
+  }
+  {
+    int cap = 1;
+    while (cap < P && cap < SSD3D_SORT_MAX) cap <<= 1;
+    const size_t smem = (size_t)cap * 8;
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(sort_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    sort_segments_kernel<<<L.S, 1024, smem, st>>>(cand, count, nkeep, boxes, P, n_classes, L.nmax, cap, sboxes, sscores,
+                                                  sprior, status);
+    SSD3D_CHECK_LAUNCH();
+  }
+  {
+    dim3 grid((unsigned)L.words, (unsigned)L.words, (unsigned)L.S);
+    nms_mask_kernel<<<grid, 64, 0, st>>>(sboxes, nkeep, 0, (long long)L.nmax * 6, L.words, (long long)L.nmax * L.words,
+                                         max_overlap, mask);
+    SSD3D_CHECK_LAUNCH();
+  }
+  {
+    const size_t smem = (size_t)(2 * L.words + 64) * 8;
+    nms_select_kernel<<<N, 256, smem, st>>>(mask, nkeep, n_classes, L.nmax, L.words, sboxes, sscores, sprior, keptpos,
+                                            keptscore, keptcnt, top_k, out_boxes, out_scores,
+                                            reinterpret_cast<long long*>(out_labels),
+                                            reinterpret_cast<long long*>(out_prior), out_count);
+    SSD3D_CHECK_LAUNCH();
+  }
+  return SSD3D_OK;
+}

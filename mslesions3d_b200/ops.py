@@ -1,0 +1,338 @@
+"""Tensor-level wrappers over the C ABI: argument checking, output allocation (torch's caching
+allocator), launch on torch's current stream.  PyTorch is plumbing here -- device memory and streams;
+all arithmetic happens in ``libssd3d_b200.so``.  CPU tensors are an error, never a fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+# kernels launched by this process through the library (bench.py reports it as ``gpu_launches``)
+LAUNCHES = [0]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ssd3d_b200 ops need CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def f32(v: float) -> float:
+    """Round a Python float to fp32 the way torch does when comparing it with a float32 tensor."""
+    return float(np.float32(v))
+
+
+def conv_out(d: int, s: int) -> int:
+    return (d - 1) // s + 1
+
+
+# ----------------------------------------------------------------------------------------------
+# activations: logical (N, C, D, H, W) tensors stored channels-last-3d in bf16
+# ----------------------------------------------------------------------------------------------
+def to_channels_last_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Bring a 5-D activation to the kernels' storage format (a no-op for tensors produced by the ops)."""
+    if x.dim() != 5:
+        raise RuntimeError("expected a 5-D (N, C, D, H, W) tensor, got %s" % (tuple(x.shape),))
+    if x.dtype != BF16:
+        x = x.to(BF16)
+    if not x.is_contiguous(memory_format=torch.channels_last_3d):
+        x = x.contiguous(memory_format=torch.channels_last_3d)
+    return x
+
+
+def _alloc_ndhwc(n, c, d, h, w, device) -> torch.Tensor:
+    # physical (N, D, H, W, C), returned as its logical NCDHW view
+    return torch.empty((n, d, h, w, c), dtype=BF16, device=device).permute(0, 4, 1, 2, 3)
+
+
+def stem_conv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                      stride_d: int) -> torch.Tensor:
+    """x (N,Cin,D,H,W) contiguous fp32|bf16 -> (N,32,Do,Ho,Wo) channels-last bf16.  mobilenet.py:28-30."""
+    _need_cuda(x, w_packed, scale, shift)
+    if x.dim() != 5:
+        raise RuntimeError("expected (N, C, D, H, W) input")
+    if x.dtype not in (torch.float32, BF16):
+        x = x.float()
+    x = x.contiguous()
+    n, cin, d, h, w = x.shape
+    y = _alloc_ndhwc(n, 32, conv_out(d, stride_d), conv_out(h, 2), conv_out(w, 2), x.device)
+    rc = _lib.load().ssd3d_stem_conv_bn_relu(x.data_ptr(), int(x.dtype == BF16), w_packed.data_ptr(), scale.data_ptr(),
+                                             shift.data_ptr(), y.data_ptr(), n, cin, d, h, w, stride_d, _stream())
+    _lib.check(rc, "ssd3d_stem_conv_bn_relu")
+    LAUNCHES[0] += 1
+    return y
+
+
+def dwconv3d_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                     stride: int) -> torch.Tensor:
+    """Depthwise 3x3x3 + BN + ReLU on a channels-last bf16 activation.  mobilenet.py:38,44."""
+    _need_cuda(x, w_packed, scale, shift)
+    x = to_channels_last_bf16(x)
+    n, c, d, h, w = x.shape
+    y = _alloc_ndhwc(n, c, conv_out(d, stride), conv_out(h, stride), conv_out(w, stride), x.device)
+    rc = _lib.load().ssd3d_dwconv3d_bn_relu(x.data_ptr(), w_packed.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                            y.data_ptr(), n, c, d, h, w, stride, _stream())
+    _lib.check(rc, "ssd3d_dwconv3d_bn_relu")
+    LAUNCHES[0] += 1
+    return y
+
+
+def pwconv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
+                   nan_flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Pointwise conv + BN + ReLU (tcgen05 GEMM).  w_packed (Cout, Cin) bf16.  mobilenet.py:40,45."""
+    _need_cuda(x, w_packed, scale, shift, nan_flag)
+    x = to_channels_last_bf16(x)
+    n, c, d, h, w = x.shape
+    cout = w_packed.shape[0]
+    y = _alloc_ndhwc(n, cout, d, h, w, x.device)
+    rc = _lib.load().ssd3d_pwconv_bn_relu(x.data_ptr(), w_packed.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                          y.data_ptr(), n * d * h * w, c, cout, _ptr(nan_flag), _stream())
+    _lib.check(rc, "ssd3d_pwconv_bn_relu")
+    LAUNCHES[0] += 1
+    return y
+
+
+def head_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, locs: torch.Tensor, scores: torch.Tensor,
+              bpl: int, n_classes: int, prior_offset: int, nan_flag: Optional[torch.Tensor] = None) -> None:
+    """Fused loc+class 3x3x3 head of one feature map, written into locs (N,P,6) / scores (N,P,n_classes)."""
+    _need_cuda(x, w_packed, bias, locs, scores, nan_flag)
+    x = to_channels_last_bf16(x)
+    n, c, d, h, w = x.shape
+    rc = _lib.load().ssd3d_head_conv(x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), locs.data_ptr(),
+                                     scores.data_ptr(), n, c, d, h, w, bpl, n_classes, w_packed.shape[0],
+                                     locs.shape[1], prior_offset, _ptr(nan_flag), _stream())
+    _lib.check(rc, "ssd3d_head_conv")
+    LAUNCHES[0] += 1
+
+
+# ----------------------------------------------------------------------------------------------
+# weight packing (host-side layout work, done once per state_dict)
+# ----------------------------------------------------------------------------------------------
+def fold_bn(bn: torch.nn.BatchNorm3d) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm as y = x*scale + shift (fp32)."""
+    w = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(bn.running_mean)
+    b = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(bn.running_mean)
+    scale = w / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = b - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
+    """(32, Cin, 3,3,3) -> (27*Cin, 32) fp32 with bf16-rounded values; row = tap*Cin + cin."""
+    co, ci = w.shape[0], w.shape[1]
+    p = w.detach().to(BF16).float().permute(2, 3, 4, 1, 0).reshape(27 * ci, co)
+    return p.contiguous()
+
+
+def pack_dw_weight(w: torch.Tensor) -> torch.Tensor:
+    """(C, 1, 3,3,3) -> (27, C) bf16."""
+    c = w.shape[0]
+    return w.detach().reshape(c, 27).t().contiguous().to(BF16)
+
+
+def pack_pw_weight(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, 1,1,1) -> (Cout, Cin) bf16."""
+    return w.detach().reshape(w.shape[0], w.shape[1]).contiguous().to(BF16)
+
+
+def pack_head_weight(loc_w, loc_b, cl_w, cl_b) -> Tuple[torch.Tensor, torch.Tensor]:
+    """loc (bpl*6, C,3,3,3) and class (bpl*n_classes, C,3,3,3) convs -> (NPAD, 27*C) bf16 + (NPAD) fp32 bias."""
+    c = loc_w.shape[1]
+    rows = loc_w.shape[0] + cl_w.shape[0]
+    npad = ((rows + 15) // 16) * 16
+    w = torch.zeros((npad, 27 * c), dtype=torch.float32, device=loc_w.device)
+    w[:loc_w.shape[0]] = loc_w.detach().float().permute(0, 2, 3, 4, 1).reshape(loc_w.shape[0], 27 * c)
+    w[loc_w.shape[0]:rows] = cl_w.detach().float().permute(0, 2, 3, 4, 1).reshape(cl_w.shape[0], 27 * c)
+    b = torch.zeros((npad,), dtype=torch.float32, device=loc_w.device)
+    b[:loc_w.shape[0]] = loc_b.detach().float()
+    b[loc_w.shape[0]:rows] = cl_b.detach().float()
+    return w.to(BF16).contiguous(), b.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# box geometry (utils.py:42-149)
+# ----------------------------------------------------------------------------------------------
+def _boxes(t: torch.Tensor, what: str) -> torch.Tensor:
+    _need_cuda(t)
+    if t.dim() != 2 or t.shape[1] != 6:
+        raise RuntimeError("%s must be (n, 6), got %s" % (what, tuple(t.shape)))
+    return t.float().contiguous()
+
+
+def box_transform(mode: int, boxes: torch.Tensor, priors: Optional[torch.Tensor] = None) -> torch.Tensor:
+    boxes = _boxes(boxes, "boxes")
+    if priors is not None:
+        priors = _boxes(priors, "priors")
+        if priors.shape[0] != boxes.shape[0]:
+            raise RuntimeError("boxes and priors must have the same length")
+    out = torch.empty_like(boxes)
+    rc = _lib.load().ssd3d_box_transform(mode, boxes.data_ptr(), _ptr(priors), out.data_ptr(), boxes.shape[0], _stream())
+    _lib.check(rc, "ssd3d_box_transform")
+    LAUNCHES[0] += 1
+    return out
+
+
+def iou3d_pairwise(a: torch.Tensor, b: torch.Tensor, want_iou: bool = True) -> torch.Tensor:
+    a, b = _boxes(a, "set_1"), _boxes(b, "set_2")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    rc = _lib.load().ssd3d_iou3d_pairwise(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.shape[0], b.shape[0],
+                                          int(want_iou), _stream())
+    _lib.check(rc, "ssd3d_iou3d_pairwise")
+    LAUNCHES[0] += 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# detection
+# ----------------------------------------------------------------------------------------------
+def decode_softmax(locs: torch.Tensor, scores: torch.Tensor, priors: torch.Tensor):
+    """-> (probs (N,P,C), boxes_xyz (N,P,6)); ssd3d.py:363,373-374."""
+    _need_cuda(locs, scores, priors)
+    locs, scores, priors = locs.float().contiguous(), scores.float().contiguous(), priors.float().contiguous()
+    n, p, c = scores.shape
+    probs = torch.empty_like(scores)
+    boxes = torch.empty_like(locs)
+    rc = _lib.load().ssd3d_decode_softmax(locs.data_ptr(), scores.data_ptr(), priors.data_ptr(), n, p, c,
+                                          probs.data_ptr(), boxes.data_ptr(), _stream())
+    _lib.check(rc, "ssd3d_decode_softmax")
+    LAUNCHES[0] += 1
+    return probs, boxes
+
+
+def nms3d_sorted(boxes_xyz: torch.Tensor, max_overlap: float) -> torch.Tensor:
+    """Greedy NMS over score-sorted boxes -> bool keep mask (ssd3d.py:407-426)."""
+    boxes_xyz = _boxes(boxes_xyz, "boxes")
+    n = boxes_xyz.shape[0]
+    keep = torch.empty((n,), dtype=torch.uint8, device=boxes_xyz.device)
+    if n == 0:
+        return keep.bool()
+    words = (n + 63) // 64
+    ws = torch.empty((n * words,), dtype=torch.int64, device=boxes_xyz.device)
+    rc = _lib.load().ssd3d_nms3d_sorted(boxes_xyz.data_ptr(), n, f32(max_overlap), keep.data_ptr(), ws.data_ptr(),
+                                        _stream())
+    _lib.check(rc, "ssd3d_nms3d_sorted")
+    LAUNCHES[0] += 2
+    return keep.bool()
+
+
+class DetectOutput:
+    """Padded device-side result of one detect call (rows >= count[i] are undefined)."""
+    __slots__ = ("boxes", "scores", "labels", "prior", "count", "status")
+
+    def __init__(self, boxes, scores, labels, prior, count, status):
+        self.boxes, self.scores, self.labels, self.prior, self.count, self.status = (boxes, scores, labels, prior,
+                                                                                   count, status)
+
+
+def detect_objects_padded(locs: torch.Tensor, scores: torch.Tensor, priors: torch.Tensor, min_score: float,
+                          max_overlap: float, top_k: int, workspace: Optional[torch.Tensor] = None) -> DetectOutput:
+    """The whole of ``detect_objects`` on the device, no host sync; see include/ssd3d_b200.h."""
+    _need_cuda(locs, scores, priors)
+    locs, scores, priors = locs.float().contiguous(), scores.float().contiguous(), priors.float().contiguous()
+    n, p, c = scores.shape
+    if locs.shape[0] != n or locs.shape[1] != p or priors.shape[0] != p:
+        raise AssertionError("prior / prediction count mismatch")  # ssd3d.py:370
+    dev = locs.device
+    top_k = int(top_k)
+    lib = _lib.load()
+    need = lib.ssd3d_detect_workspace_bytes(n, p, c, top_k)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
+    out_boxes = torch.empty((n, top_k, 6), dtype=torch.float32, device=dev)
+    out_scores = torch.empty((n, top_k), dtype=torch.float32, device=dev)
+    out_labels = torch.empty((n, top_k), dtype=torch.int64, device=dev)
+    out_prior = torch.empty((n, top_k), dtype=torch.int64, device=dev)
+    out_count = torch.empty((n,), dtype=torch.int32, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    rc = lib.ssd3d_detect_objects(locs.data_ptr(), scores.data_ptr(), priors.data_ptr(), n, p, c, f32(min_score),
+                                  f32(max_overlap), top_k, out_boxes.data_ptr(), out_scores.data_ptr(),
+                                  out_labels.data_ptr(), out_prior.data_ptr(), out_count.data_ptr(),
+                                  workspace.data_ptr(), workspace.numel(), status.data_ptr(), _stream())
+    _lib.check(rc, "ssd3d_detect_objects")
+    LAUNCHES[0] += 4
+    return DetectOutput(out_boxes, out_scores, out_labels, out_prior, out_count, status)
+
+
+def detect_lists(out: DetectOutput, return_prior: bool = False):
+    """Turn the padded result into the reference's three Python lists (one D2H read of the counts)."""
+    host = torch.cat([out.count, out.status]).cpu()
+    if int(host[-1]) & 1:
+        raise RuntimeError("detect_objects: more than %d candidates above min_score for one (image, class); "
+                           "raise min_score (limit of this version)" % _lib.SORT_MAX)
+    counts = host[:-1].tolist()
+    b = [out.boxes[i, :k] for i, k in enumerate(counts)]
+    l = [out.labels[i, :k] for i, k in enumerate(counts)]
+    s = [out.scores[i, :k] for i, k in enumerate(counts)]
+    if return_prior:
+        return b, l, s, [out.prior[i, :k] for i, k in enumerate(counts)]
+    return b, l, s
+
+
+# ----------------------------------------------------------------------------------------------
+# matching + loss
+# ----------------------------------------------------------------------------------------------
+def match_priors(boxes: Sequence[torch.Tensor], labels: Sequence[torch.Tensor], priors_cxcycz: torch.Tensor,
+                 t0: float, t1: float):
+    """-> dict(true_classes (N,P) int64, true_locs (N,P,6), overlap, object_for_prior, prior_for_object)."""
+    _need_cuda(priors_cxcycz, *boxes, *labels)
+    dev = priors_cxcycz.device
+    n = len(boxes)
+    p = priors_cxcycz.shape[0]
+    counts = [int(b.shape[0]) for b in boxes]
+    offsets = torch.tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), device=dev)
+    total = int(sum(counts))
+    if total:
+        gt_boxes = torch.cat([b.reshape(-1, 6).float() for b in boxes]).contiguous()
+        gt_labels = torch.cat([l.reshape(-1).long() for l in labels]).contiguous()
+    else:
+        gt_boxes = gt_labels = None
+    tc = torch.empty((n, p), dtype=torch.int64, device=dev)
+    tl = torch.empty((n, p, 6), dtype=torch.float32, device=dev)
+    ov = torch.empty((n, p), dtype=torch.float32, device=dev)
+    ofp = torch.empty((n, p), dtype=torch.int32, device=dev)
+    pfo = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
+    ws = torch.empty((max(total, 1),), dtype=torch.int64, device=dev)
+    pri = priors_cxcycz.float().contiguous()
+    rc = _lib.load().ssd3d_match_priors(_ptr(gt_boxes), _ptr(gt_labels), offsets.data_ptr(), n, total, pri.data_ptr(),
+                                        p, f32(t0), f32(t1), tc.data_ptr(), tl.data_ptr(), ov.data_ptr(),
+                                        ofp.data_ptr(), pfo.data_ptr(), ws.data_ptr(), _stream())
+    _lib.check(rc, "ssd3d_match_priors")
+    LAUNCHES[0] += 2
+    return dict(true_classes=tc, true_locs=tl, overlap=ov, object_for_prior=ofp, prior_for_object=pfo[:total])
+
+
+def multibox_loss(locs: torch.Tensor, scores: torch.Tensor, true_classes: torch.Tensor, true_locs: torch.Tensor,
+                  alpha: float = 1.0, hard_negative_mining: bool = False, neg_pos_ratio: int = 3,
+                  want_grads: bool = True):
+    """-> (loss (2,) = [conf, loc], n_pos (1,) int32, grad_locs | None, grad_scores | None)."""
+    _need_cuda(locs, scores, true_classes, true_locs)
+    locs, scores = locs.float().contiguous(), scores.float().contiguous()
+    n, p, c = scores.shape
+    dev = locs.device
+    lib = _lib.load()
+    ws = torch.empty((lib.ssd3d_multibox_workspace_bytes(n, p),), dtype=torch.uint8, device=dev)
+    out = torch.empty((2,), dtype=torch.float32, device=dev)
+    n_pos = torch.empty((1,), dtype=torch.int32, device=dev)
+    gl = torch.empty_like(locs) if want_grads else None
+    gs = torch.empty_like(scores) if want_grads else None
+    rc = lib.ssd3d_multibox_loss(locs.data_ptr(), scores.data_ptr(), true_classes.contiguous().data_ptr(),
+                                 true_locs.contiguous().data_ptr(), n, p, c, float(alpha), int(hard_negative_mining),
+                                 int(neg_pos_ratio), out.data_ptr(), n_pos.data_ptr(), _ptr(gl), _ptr(gs),
+                                 ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_multibox_loss")
+    LAUNCHES[0] += 3
+    return out, n_pos, gl, gs

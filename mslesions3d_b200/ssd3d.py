@@ -1,0 +1,520 @@
+"""SSD3D detector with the reference's class / method surface (``lesions3d/ssd3d.py``), running on
+hand-written sm_100a kernels (``libssd3d_b200.so``).
+
+Drop-in points kept verbatim: ``LSSD3D`` constructor kwargs (ssd3d.py:177-200), ``forward`` ->
+``(locs (N,P,6), classes_scores (N,P,n_classes))``, ``detect_objects`` -> three lists of per-image
+tensors, ``create_prior_boxes``, ``predict_step``, ``init``, ``configure_optimizers``,
+``load_from_checkpoint``; ``MobileNetBase``, ``PredictionConvolutions``, ``MultiBoxLoss`` with their
+signatures; parameter names / ``state_dict`` keys (103 tensors incl. the unused ``rescale_factors``).
+``SSD3D`` is an alias of ``LSSD3D`` (the name BASELINE.json uses).
+
+What differs from the reference by design:
+  * all arithmetic is in CUDA kernels; activations are channels-last-3d bf16 with fp32 accumulation;
+  * the reference's per-layer ``isnan().sum() > 0`` host syncs are one device flag, read once;
+  * ``detect_objects`` runs fully on the device and reads back only the per-image counts;
+  * equal scores are ordered by ascending prior index (the reference's sort leaves ties unspecified);
+  * no CPU path: CPU tensors handed to the kernels raise.
+"""
+from __future__ import annotations
+
+import inspect
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .mobilenet import MOBILENET_CONFIGS, Block, conv_bn
+from .utils import *  # noqa: F401,F403  (the reference does `from utils import *`)
+from .utils import cxcycz_to_xyz
+
+try:  # the reference derives from pytorch_lightning.LightningModule; it is optional here
+    import pytorch_lightning as pl  # type: ignore
+    _LightningBase = pl.LightningModule
+    _HAVE_PL = True
+except Exception:  # pragma: no cover - PL is absent in the build image
+    _HAVE_PL = False
+
+    class _LightningBase(nn.Module):
+        """The small part of ``LightningModule`` the SSD3D path touches."""
+
+        def __init__(self):
+            super().__init__()
+            self.hparams = {}
+            self.current_epoch = 0
+            self.global_step = 0
+
+        def save_hyperparameters(self, *args, **kwargs):
+            frame = inspect.currentframe().f_back
+            names = inspect.signature(type(self).__init__).parameters
+            self.hparams = {k: frame.f_locals[k] for k in names if k != "self" and k in frame.f_locals}
+
+        def log(self, *args, **kwargs):
+            pass
+
+        def lr_schedulers(self):
+            return None
+
+        @property
+        def device(self):
+            for p in self.parameters():
+                return p.device
+            return torch.device("cpu")
+
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
+            """Read a PyTorch-Lightning checkpoint dict (``state_dict`` + ``hyper_parameters``), predict.py:257."""
+            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+            hp = dict(ckpt.get("hyper_parameters", {}))
+            hp.update(kwargs)
+            allowed = inspect.signature(cls.__init__).parameters
+            model = cls(**{k: v for k, v in hp.items() if k in allowed})
+            model.load_state_dict(ckpt["state_dict"], strict=strict)
+            return model
+
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")   # ssd3d.py:23
+
+ASPECT_RATIOS = {3: [1.], 5: [1.], 7: [1]}   # ssd3d.py:25
+
+
+class MobileNetBase(nn.Module):
+    """Truncated 3-D MobileNet-v1 feature extractor (ssd3d.py:47-110)."""
+
+    def __init__(self, config="mobilenet", in_channels=1, width_mult=1., cube=False, aspect_ratios=None):
+        super(MobileNetBase, self).__init__()
+        if aspect_ratios is None:
+            aspect_ratios = ASPECT_RATIOS
+        self.aspect_ratios = aspect_ratios
+        self.in_channels = in_channels
+        self.config = MOBILENET_CONFIGS[config]
+        input_channel = int(self.config[0] * width_mult)
+        cfg = self.config[1:]
+        first_stride = (1, 2, 2) if not cube else (2, 2, 2)
+        features = [conv_bn(in_channels, input_channel, first_stride)]
+        last = max(self.aspect_ratios.keys())
+        for c, n, s in cfg:
+            if len(features) - 1 == last:   # truncate the network after the last prediction layer
+                break
+            output_channel = int(c * width_mult)
+            for i in range(n):
+                if len(features) - 1 == last:
+                    break
+                stride = s if i == 0 else 1
+                features.append(Block(input_channel, output_channel, stride))
+                input_channel = output_channel
+        self.features = nn.Sequential(*features)
+        self._nan_flag: Optional[torch.Tensor] = None
+
+    def init(self):
+        for c in self.children():
+            if isinstance(c, nn.Conv3d):
+                nn.init.kaiming_uniform_(c.weight)
+                nn.init.constant_(c.bias, 0.)
+
+    def nan_flag(self, dev) -> torch.Tensor:
+        """Device int32 the kernels OR NaN bits into (replaces the syncs at mobilenet.py:46, ssd3d.py:95)."""
+        if self._nan_flag is None or self._nan_flag.device != dev:
+            self._nan_flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+            for f in self.features:
+                if isinstance(f, Block):
+                    f.nan_flag = self._nan_flag
+        return self._nan_flag
+
+    def forward(self, image, check_nan: bool = True):
+        flag = self.nan_flag(image.device)
+        out = image
+        wanted = list(self.aspect_ratios.keys())
+        out_features = {}
+        for i, feat in enumerate(self.features):
+            out = feat(out)
+            if i in wanted:
+                out_features[i] = out
+        if check_nan and int(flag.item()) & _lib.NAN_BACKBONE:
+            flag.zero_()
+            print("Yesssss this NaN error again in the base network")
+            raise Exception("Yesssss this NaN error again in the base network")   # ssd3d.py:95-98
+        return out_features
+
+    def get_feature_map_infos(self, input_size, device=None):
+        """Spatial size and channel count after every layer (ssd3d.py:102-110), computed from the layer
+        parameters instead of a dummy forward."""
+        cur = tuple(int(v) for v in input_size)
+        dims, chans = {}, []
+        for i, l in enumerate(self.features):
+            conv = l[0] if isinstance(l, nn.Sequential) else l.conv1
+            st = conv.stride if isinstance(conv.stride, tuple) else (conv.stride,) * 3
+            cur = tuple(ops.conv_out(cur[a], st[a]) for a in range(3))
+            dims[i] = cur
+            chans.append(l[0].out_channels if isinstance(l, nn.Sequential) else l.conv2.out_channels)
+        return dims, chans
+
+
+class PredictionConvolutions(nn.Module):
+    """Localisation and class prediction convolutions over the selected feature maps (ssd3d.py:113-169).
+    Both 3x3x3 convs of a feature map run as one tcgen05 implicit GEMM."""
+
+    def __init__(self, n_classes, width_mult, aspect_ratios, features_n_channels, boxes_per_location=2):
+        super(PredictionConvolutions, self).__init__()
+        self.n_classes = n_classes
+        self.aspect_ratios = aspect_ratios
+        n_boxes = {feat: len(aspect_ratios[feat]) + boxes_per_location - 1 for feat in aspect_ratios}
+        self.n_boxes = n_boxes
+        loc_convs, cl_convs = [], []
+        for f in aspect_ratios:
+            f_n_channels = int(features_n_channels[f] * width_mult)   # width_mult applied twice, as ssd3d.py:130
+            loc_convs.append(nn.Conv3d(f_n_channels, n_boxes[f] * 6, kernel_size=3, padding=1))
+            cl_convs.append(nn.Conv3d(f_n_channels, n_boxes[f] * n_classes, kernel_size=3, padding=1))
+        self.loc_convs = nn.ModuleList(loc_convs)
+        self.cl_convs = nn.ModuleList(cl_convs)
+        self._packed = None
+        self._packed_key = None
+
+    def init(self):
+        for c in self.children():
+            if isinstance(c, nn.Conv3d):
+                nn.init.kaiming_uniform_(c.weight)
+                nn.init.constant_(c.bias, 0.)
+
+    def _pack(self):
+        tensors = []
+        for lc, cc in zip(self.loc_convs, self.cl_convs):
+            tensors += [lc.weight, lc.bias, cc.weight, cc.bias]
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if self._packed is None or key != self._packed_key:
+            self._packed = [ops.pack_head_weight(lc.weight, lc.bias, cc.weight, cc.bias)
+                            for lc, cc in zip(self.loc_convs, self.cl_convs)]
+            self._packed_key = key
+        return self._packed
+
+    def forward(self, feats, nan_flag: Optional[torch.Tensor] = None, out=None):
+        if self.training:
+            raise NotImplementedError("PredictionConvolutions: training-mode forward/backward is not built in this "
+                                      "version of the B200 path; call .eval()")
+        feat_keys = list(feats.keys())
+        first = feats[min(feat_keys)]
+        batch_size = first.size(0)
+        packed = self._pack()
+        counts = []
+        for i, key in enumerate(feat_keys):
+            _, _, d, h, w = feats[key].shape
+            counts.append(d * h * w * self.n_boxes[list(self.aspect_ratios.keys())[i]])
+        total = int(sum(counts))
+        if out is None:
+            locs = torch.empty((batch_size, total, 6), dtype=torch.float32, device=first.device)
+            classes_scores = torch.empty((batch_size, total, self.n_classes), dtype=torch.float32, device=first.device)
+        else:
+            locs, classes_scores = out
+        off = 0
+        for i, key in enumerate(feat_keys):
+            w, b = packed[i]
+            bpl = self.n_boxes[list(self.aspect_ratios.keys())[i]]
+            ops.head_conv(feats[key], w, b, locs, classes_scores, bpl, self.n_classes, off, nan_flag)
+            off += counts[i]
+        return locs, classes_scores
+
+
+class LSSD3D(_LightningBase):
+    """The SSD 3D network - the base MobileNet network and the prediction convolutions (ssd3d.py:172-738)."""
+
+    def __init__(self,
+                 n_classes,
+                 input_channels=3,
+                 input_size=(64, 64, 64),
+                 threshold=0.5,  # threshold for box matching in MultiBoxLoss
+                 alpha=1.,
+                 lr=1.3e-5,
+                 base_network_config="mobilenet",
+                 width_mult=1.,
+                 min_score=0.5,
+                 max_overlap=0.5,  # for box matching
+                 min_overlap=0.5,  # for evaluation metrics
+                 top_k=100,
+                 scheduler="CosineAnnealingLR",
+                 use_wandb=False,
+                 batch_size=8,
+                 compute_metric_every_n_epochs=1,
+                 comments="",
+                 aspect_ratios={},
+                 min_object_size=6,
+                 max_object_size=14,
+                 scales={},
+                 boxes_per_location=2
+                 ):
+        super(LSSD3D, self).__init__()
+        if aspect_ratios == {}:
+            aspect_ratios = ASPECT_RATIOS
+        self.save_hyperparameters()
+        self.base_network_config = base_network_config
+        self.cube = input_size[0] == input_size[1] == input_size[2]
+        self.input_size = input_size
+        self.input_channels = input_channels
+        self.width_mult = width_mult
+        self.aspect_ratios = aspect_ratios
+        self.boxes_per_location = 2   # the kwarg is ignored, as in ssd3d.py:213
+
+        self.n_classes = n_classes
+        self._make_base_and_prediction_layers()
+        self.lr = lr
+        self.min_score = min_score
+        self.max_overlap = max_overlap
+        self.min_overlap = min_overlap
+        self.top_k = top_k
+        self.scheduler = scheduler
+        self.use_wandb = use_wandb
+        self.batch_size = batch_size
+        self.compute_metric_every_n_epochs = compute_metric_every_n_epochs
+        self.comments = comments
+
+        if scales == {}:
+            self.scales = {layer: scale for layer, scale in zip(self.aspect_ratios.keys(),
+                                                                np.linspace(min_object_size / input_size[0],
+                                                                            max_object_size / input_size[0],
+                                                                            len(self.aspect_ratios)))}
+        else:
+            self.scales = scales
+
+        features_n_channels = self.base.get_feature_map_infos(self.input_size)[1]
+        n_channel_rescale = int(features_n_channels[min(self.aspect_ratios.keys())] * self.width_mult)
+        # kept for checkpoint compatibility; unused in forward exactly as in the reference (ssd3d.py:240-254)
+        self.rescale_factors = nn.Parameter(torch.FloatTensor(1, n_channel_rescale, 1, 1, 1))
+        nn.init.constant_(self.rescale_factors, 20)
+
+        self.priors_cxcycz = self.create_prior_boxes()
+        self.loss_fn = MultiBoxLoss(self.priors_cxcycz, threshold=threshold, alpha=alpha)
+        self.defer_nan_check = False
+        self._detect_ws = None
+
+    # ------------------------------------------------------------------------------------------
+    def _make_base_and_prediction_layers(self):
+        if 'mobilenet' in self.base_network_config:
+            self.base = MobileNetBase(config=self.base_network_config, in_channels=self.input_channels,
+                                      width_mult=self.width_mult, cube=self.cube, aspect_ratios=self.aspect_ratios)
+            features_n_channels = self.base.get_feature_map_infos(self.input_size)[1]
+            # The reference measures the shapes with a dummy forward of torch.randn(...) here
+            # (ssd3d.py:102-103,270); drawing the same numbers keeps the global RNG stream -- and hence the
+            # default initialisation of the head convs that follow -- identical for a given manual_seed.
+            torch.randn((1, self.input_channels, *self.input_size))
+            self.pred_convs = PredictionConvolutions(self.n_classes, width_mult=self.width_mult,
+                                                     aspect_ratios=self.aspect_ratios,
+                                                     features_n_channels=features_n_channels,
+                                                     boxes_per_location=self.boxes_per_location)
+        elif 'convnet' in self.base_network_config:
+            # the reference's branch is itself broken (self.boxes.per_location, ssd3d.py:281) and needs MONAI
+            raise NotImplementedError("the 'convnet' base network is outside the accelerated SSD3D-MobileNet path")
+        else:
+            raise Exception(
+                f"Unknown base network name. Expected 'mobilenet' or 'convnet' but got {self.base_network_config}")
+
+    def create_prior_boxes(self, per_feature_map=False):
+        """Prior (default) boxes in centre-size coordinates, (P, 6) fp32 (ssd3d.py:286-342).
+
+        Same float64 arithmetic per box as the reference's Python triple loop, vectorised; note the axis
+        quirk kept from ssd3d.py:304-309 (cx follows array axis 1, cy axis 0)."""
+        features = list(self.aspect_ratios.keys())
+        fmd = self.base.get_feature_map_infos(self.input_size)[0]
+        chunks, per_map = [], {}
+        for fmap in features:
+            d0, d1, d2 = fmd[fmap]
+            s = float(self.scales[fmap])
+            cy = (np.arange(d0, dtype=np.float64) + 0.5) / d0
+            cx = (np.arange(d1, dtype=np.float64) + 0.5) / d1
+            cz = (np.arange(d2, dtype=np.float64) + 0.5) / d2
+            CY, CX, CZ = np.meshgrid(cy, cx, cz, indexing="ij")
+            sizes = []
+            for ratio in self.aspect_ratios[fmap]:
+                sizes.append(s)
+                if ratio == 1.:
+                    for div in list(range(1, self.boxes_per_location)):
+                        sizes.append(s + s / div)
+            per = np.empty((d0, d1, d2, len(sizes), 6), dtype=np.float64)
+            per[..., 0] = CX[..., None]
+            per[..., 1] = CY[..., None]
+            per[..., 2] = CZ[..., None]
+            per[..., 3:] = np.asarray(sizes, dtype=np.float64)[None, None, None, :, None]
+            chunks.append(per.reshape(-1, 6))
+            per_map[fmap] = per.reshape(-1, 6).tolist() if per_feature_map else None
+        if per_feature_map:
+            return per_map
+        prior_boxes = torch.tensor(np.concatenate(chunks, 0), dtype=torch.float32).to(device)
+        prior_boxes.clamp_(0, 1)
+        return prior_boxes
+
+    # ------------------------------------------------------------------------------------------
+    def _priors_on(self, dev) -> torch.Tensor:
+        if self.priors_cxcycz.device != dev:
+            self.priors_cxcycz = self.priors_cxcycz.to(dev)
+            self.loss_fn.set_priors(self.priors_cxcycz)
+        return self.priors_cxcycz
+
+    def _raise_on_nan(self, flag: torch.Tensor):
+        bits = int(flag.item())
+        if bits:
+            flag.zero_()
+        if bits & _lib.NAN_BACKBONE:
+            print("Yesssss this NaN error again in the base network")
+            raise Exception("Yesssss this NaN error again in the base network")
+        if bits & _lib.NAN_SCORES:
+            raise Exception("Oh no not this NaN error again... (forward SSD), CLASSES_SCORES is nan!")
+        if bits & _lib.NAN_LOCS:
+            raise Exception("Oh no not this NaN error again... (forward SSD), LOCS is nan!")
+
+    def forward(self, image):
+        """image (N, Cin, D, H, W) -> locs (N,P,6), classes_scores (N,P,n_classes) fp32 (ssd3d.py:248-263)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("LSSD3D.forward needs the model on a CUDA device; there is no CPU path")
+        if image.device != dev:
+            image = image.to(dev, non_blocking=True)
+        flag = self.base.nan_flag(dev)
+        feats = self.base(image, check_nan=False)
+        locs, classes_scores = self.pred_convs(feats, flag)
+        if not self.defer_nan_check:
+            self._raise_on_nan(flag)
+        return locs, classes_scores
+
+    def detect_objects(self, predicted_locs, predicted_scores, min_score, max_overlap, top_k, return_prior=False):
+        """Decode + per-class NMS + top-k (ssd3d.py:344-460) -> lists of per-image boxes, labels, scores."""
+        priors = self._priors_on(predicted_locs.device)
+        out = ops.detect_objects_padded(predicted_locs, predicted_scores, priors, min_score, max_overlap, top_k)
+        return ops.detect_lists(out, return_prior=return_prior)
+
+    def init(self):
+        print("[INFO] Initializing model weights")
+        self.base.init()
+        self.pred_convs.init()
+
+    def predict_step(self, batch, batch_idx: int = 0, dataloader_idx: int = None):
+        """forward + detect_objects with a single host sync for the whole batch (ssd3d.py:692-702)."""
+        prev = self.defer_nan_check
+        self.defer_nan_check = True
+        try:
+            predicted_locs, predicted_scores = self(batch["img"])
+        finally:
+            self.defer_nan_check = prev
+        priors = self._priors_on(predicted_locs.device)
+        out = ops.detect_objects_padded(predicted_locs, predicted_scores, priors, self.min_score, self.max_overlap,
+                                        self.top_k)
+        flag = self.base.nan_flag(predicted_locs.device)
+        host = torch.cat([out.count, out.status, flag]).cpu()   # the one device->host read of the step
+        if int(host[-1]):
+            self._raise_on_nan(flag)
+        if int(host[-2]) & 1:
+            raise RuntimeError("detect_objects: more than %d candidates above min_score for one (image, class)"
+                               % _lib.SORT_MAX)
+        counts = host[:-2].tolist()
+        det_boxes = [out.boxes[i, :k] for i, k in enumerate(counts)]
+        det_label = [out.labels[i, :k] for i, k in enumerate(counts)]
+        det_scores = [out.scores[i, :k] for i, k in enumerate(counts)]
+        return det_boxes, det_label, det_scores
+
+    def training_step(self, batch):
+        """forward + MultiBox loss (ssd3d.py:467-531).  The loss (matching, hard/soft labelling, CE + L1 and
+        their gradients w.r.t. the head outputs) runs on the device; the network forward in train mode
+        (batch-stat BN) and the convolution backward are not built yet, so this raises from forward()."""
+        images, gt_boxes, gt_labels = batch["img"], batch['boxes'], batch["labels"]
+        dev = self.device
+        gt_boxes = [b.to(dev) for b in gt_boxes]
+        gt_labels = [l.to(dev) for l in gt_labels]
+        predicted_locs, predicted_scores = self(images)
+        conf_loss, loc_loss = self.loss_fn(predicted_locs, predicted_scores, gt_boxes, gt_labels)
+        loss = conf_loss + self.loss_fn.alpha * loc_loss
+        logs = {"train_total_loss": loss, "train_conf_loss": conf_loss, "train_loc_loss": loc_loss}
+        sch = self.lr_schedulers()
+        if sch is not None:
+            sch.step()
+        return {'loss': loss, "log": logs}
+
+    def configure_optimizers(self):
+        """Adam, weight decay 5e-4, biases at twice the learning rate, cosine schedule (ssd3d.py:704-722)."""
+        biases, not_biases = list(), list()
+        for param_name, param in self.named_parameters():
+            if param.requires_grad:
+                if param_name.endswith('.bias'):
+                    biases.append(param)
+                else:
+                    not_biases.append(param)
+        params = [{'params': biases, 'lr': 2 * self.lr}, {'params': not_biases}]
+        optimizer = torch.optim.Adam(params=params, lr=self.lr, weight_decay=0.0005)
+        if self.scheduler != "none":
+            scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=40)
+            return [optimizer], [scheduler]
+        return optimizer
+
+
+SSD3D = LSSD3D
+
+
+class _MultiBoxLossFn(torch.autograd.Function):
+    """conf / loc losses with the analytic gradient computed by the loss kernel in the same pass."""
+
+    @staticmethod
+    def forward(ctx, locs, scores, true_classes, true_locs, hnm, ratio):
+        out, n_pos, g_locs, g_scores = ops.multibox_loss(locs, scores, true_classes, true_locs, alpha=1.0,
+                                                         hard_negative_mining=hnm, neg_pos_ratio=ratio,
+                                                         want_grads=True)
+        ctx.save_for_backward(g_locs, g_scores)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_conf, g_loc):
+        g_locs, g_scores = ctx.saved_tensors
+        return g_locs * g_loc, g_scores * g_conf, None, None, None, None
+
+
+class MultiBoxLoss(nn.Module):
+    """The MultiBox loss: L1 localisation loss over positive priors + cross-entropy confidence loss over
+    all non-ignored priors, normalised by the number of positives (ssd3d.py:741-941).
+
+    ``hard_negative_mining=True`` (not in the reference's signature) switches to the variant the
+    reference ships commented out (ssd3d.py:926-932): per image only the ``neg_pos_ratio * n_positives``
+    hardest negatives count."""
+
+    def __init__(self, priors_cxcycz, threshold=0.5, neg_pos_ratio=3, alpha=1., hard_negative_mining=False):
+        super(MultiBoxLoss, self).__init__()
+        self.threshold = threshold
+        self.neg_pos_ratio = neg_pos_ratio
+        self.alpha = alpha
+        self.hard_negative_mining = hard_negative_mining
+        if type(self.threshold) == list:
+            if len(self.threshold) == 1:
+                self.thresholding_mode = "hard"
+                self.threshold = self.threshold[0]
+            else:
+                self.thresholding_mode = "soft"
+                assert (len(self.threshold) == 2)
+        elif type(self.threshold) == float:
+            self.thresholding_mode = "hard"
+        else:
+            raise Exception(
+                "Type error. Expected float or list of floats for threshold but got {type(self.threshold))}")
+        self.set_priors(priors_cxcycz)
+
+    def set_priors(self, priors_cxcycz):
+        self.priors_cxcycz = priors_cxcycz
+        # centre-size -> boundary is +-(w/2): exact in fp32 on any device, so the CPU build container can
+        # construct the module; the kernels recompute it from priors_cxcycz anyway
+        half = priors_cxcycz[:, 3:] / 2
+        self.priors_xyz = torch.cat([priors_cxcycz[:, :3] - half, priors_cxcycz[:, :3] + half], 1)
+
+    def match(self, boxes, labels):
+        """Prior <-> object matching, labelling and target encoding for a batch (ssd3d.py:786-888)."""
+        if self.thresholding_mode == "hard":
+            t0 = t1 = self.threshold
+        else:
+            t0, t1 = self.threshold
+        dev = boxes[0].device if len(boxes) else self.priors_cxcycz.device
+        if self.priors_cxcycz.device != dev:
+            self.set_priors(self.priors_cxcycz.to(dev))
+        return ops.match_priors(boxes, labels, self.priors_cxcycz, t0, t1)
+
+    def forward(self, predicted_locs, predicted_scores, boxes, labels):
+        n_priors = self.priors_cxcycz.size(0)
+        assert n_priors == predicted_locs.size(1) == predicted_scores.size(1)
+        m = self.match(boxes, labels)
+        conf_loss, loc_loss = _MultiBoxLossFn.apply(predicted_locs, predicted_scores, m["true_classes"],
+                                                    m["true_locs"], self.hard_negative_mining, self.neg_pos_ratio)
+        if torch.isnan(loc_loss):   # no positive prior at all (ssd3d.py:938-940, without the breakpoint)
+            raise Exception("Loss is NaN")
+        return conf_loss, loc_loss

@@ -289,10 +289,21 @@ def detect_objects(predicted_locs, predicted_scores, priors_cxcycz, min_score, m
     """
     n_img, n_priors, n_classes = predicted_scores.shape
     assert n_priors == priors_cxcycz.shape[0] == predicted_locs.shape[1]
-    probs = F.softmax(predicted_scores, dim=2)
+    probs = F.softmax(predicted_scores, dim=2)                                   # ssd3d.py:363
+    decoded = torch.stack([cxcycz_to_xyz(gcxgcygcz_to_cxcycz(predicted_locs[i], priors_cxcycz))
+                           for i in range(n_img)])                               # ssd3d.py:373-374
+    return detect_from_decoded(probs, decoded, min_score, max_overlap, top_k, stable, return_indices)
+
+
+def detect_from_decoded(probs, decoded, min_score, max_overlap, top_k, stable: bool = True,
+                        return_indices: bool = False):
+    """The integer-exact part of ``detect_objects`` (ssd3d.py:376-453): filter, sort, truncate,
+    greedy NMS, per-image concatenation and top-k, on GIVEN class probabilities (N,P,C) and decoded
+    boundary boxes (N,P,6).  The stage-wise parity tests feed it the device's own softmax/decode
+    output, so that exp() implementation differences cannot leak into the index comparison."""
+    n_img, n_priors, n_classes = probs.shape
     out_b, out_l, out_s, out_i = [], [], [], []
     for i in range(n_img):
-        decoded = cxcycz_to_xyz(gcxgcygcz_to_cxcycz(predicted_locs[i], priors_cxcycz))
         ib, il, isc, ii = [], [], [], []
         for c in range(1, n_classes):
             cs = probs[i][:, c]
@@ -302,7 +313,7 @@ def detect_objects(predicted_locs, predicted_scores, priors_cxcycz, min_score, m
                 continue
             idx = torch.nonzero(above).flatten()
             cs = cs[above]
-            cb = decoded[above]
+            cb = decoded[i][above]
             cs, order = cs.sort(dim=0, descending=True, stable=stable)
             cb = cb[order]
             idx = idx[order]

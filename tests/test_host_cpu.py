@@ -1,0 +1,167 @@
+"""CPU-only checks (no GPU, no compute through the library): the C-ABI library builds/loads and exports every
+symbol ``include/ssd3d_b200.h`` declares with matching arity; the host-side mirror of the reference's classes
+(constructor, state_dict keys, priors, hyper-parameters, checkpoints, weight packing layouts) behaves."""
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ssd3d_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "ssd3d_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*)\s+(ssd3d_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mslesions3d_b200 import build, _lib
+    build.build(verbose=False)
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from mslesions3d_b200 import _lib
+    declared = _header_functions()
+    assert len(declared) >= 14
+    assert set(declared) == set(_lib.SIGNATURES), "header and ctypes table disagree"
+    for name, n_args in declared.items():
+        assert hasattr(lib, name), "libssd3d_b200.so does not export %s" % name
+        assert len(_lib.SIGNATURES[name][1]) == n_args, "%s: header has %d params" % (name, n_args)
+    assert lib.ssd3d_version().decode().startswith("ssd3d_b200 sm_100a")
+
+
+def test_library_is_sm100a_tcgen05_code():
+    import shutil
+    import subprocess
+    from mslesions3d_b200 import _lib
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    elf = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and "sm_90" not in elf and "sm_80" not in elf
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, "%s missing from the GEMM SASS" % mnemonic
+
+
+def test_workspace_size_queries_need_no_gpu(lib):
+    assert lib.ssd3d_detect_workspace_bytes(8, 9344, 2, 100) > 8 * 9344 * 24
+    assert lib.ssd3d_detect_workspace_bytes(0, 9344, 2, 100) == 0
+    assert lib.ssd3d_multibox_workspace_bytes(16, 3942) > 16 * 3942 * 5
+
+
+def test_argument_errors_are_reported_without_a_gpu(lib):
+    from mslesions3d_b200 import _lib
+    assert lib.ssd3d_dwconv3d_bn_relu(None, None, None, None, None, 1, 32, 4, 4, 4, 1, None) == _lib.SSD3D_ERR_ARG
+    assert lib.ssd3d_pwconv_bn_relu(1, 1, 1, 1, 1, 128, 33, 64, None, None) == _lib.SSD3D_ERR_ARG
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        _lib.check(_lib.SSD3D_ERR_ARG, "x")
+
+
+def test_model_surface_matches_reference_names():
+    from mslesions3d_b200.ssd3d import LSSD3D, SSD3D, MultiBoxLoss, MobileNetBase, PredictionConvolutions
+    assert SSD3D is LSSD3D
+    torch.manual_seed(0)
+    m = LSSD3D(n_classes=2, input_channels=1, input_size=(64, 64, 64))
+    sd = m.state_dict()
+    ref = O.random_state_dict(1)
+    assert set(sd.keys()) == set(ref.keys()) and len(sd) == 103
+    assert all(sd[k].shape == ref[k].shape for k in ref)
+    assert sum(p.numel() for p in m.parameters()) == 949936
+    assert torch.equal(m.priors_cxcycz.cpu(), O.prior_boxes((64, 64, 64)))
+    assert float(m.rescale_factors.mean()) == 20.0
+    assert m.hparams["input_size"] == (64, 64, 64) and m.boxes_per_location == 2
+    assert isinstance(m.base, MobileNetBase) and isinstance(m.pred_convs, PredictionConvolutions)
+    assert isinstance(m.loss_fn, MultiBoxLoss) and m.loss_fn.thresholding_mode == "hard"
+    opt, sch = m.configure_optimizers()
+    assert opt[0].param_groups[0]["lr"] == 2 * m.lr and opt[0].param_groups[1]["weight_decay"] == 0.0005
+    for case in (dict(channels=2, size=(32, 64, 48)), dict(channels=2, size=(16, 32, 32),
+                                                           aspect_ratios={0: [1.], 3: [1.]})):
+        mm = LSSD3D(n_classes=2, input_channels=case["channels"], input_size=case["size"],
+                    aspect_ratios=case.get("aspect_ratios", {}))
+        assert torch.equal(mm.priors_cxcycz.cpu(), O.prior_boxes(case["size"], case.get("aspect_ratios"),
+                                                                 in_channels=case["channels"]))
+    with pytest.raises(Exception, match="Type error"):
+        MultiBoxLoss(m.priors_cxcycz, threshold=1)
+
+
+def test_no_cpu_path_and_train_mode_is_loud():
+    from mslesions3d_b200.ssd3d import LSSD3D
+    from mslesions3d_b200 import ops
+    m = LSSD3D(n_classes=2, input_channels=1, input_size=(32, 32, 32)).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 1, 32, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.iou3d_pairwise(torch.zeros(2, 6), torch.zeros(2, 6))
+
+
+def test_checkpoint_round_trip(tmp_path):
+    from mslesions3d_b200.ssd3d import LSSD3D
+    m = LSSD3D(n_classes=3, input_channels=2, input_size=(32, 32, 32), top_k=7)
+    path = os.path.join(tmp_path, "m.ckpt")
+    torch.save({"state_dict": m.state_dict(), "hyper_parameters": dict(m.hparams)}, path)   # PL checkpoint layout
+    m2 = LSSD3D.load_from_checkpoint(path, min_score=0.25)
+    assert m2.n_classes == 3 and m2.top_k == 7 and m2.min_score == 0.25
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+def test_weight_packing_layouts():
+    """The packed matrices reproduce the convs as plain matmuls (layout check, CPU)."""
+    from mslesions3d_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    # head: (NPAD, 27*C) with K index tap*C + c
+    c, bpl, ncls = 8, 2, 3
+    x = torch.randn(1, c, 4, 5, 6, generator=g)
+    lw, lb = torch.randn(bpl * 6, c, 3, 3, 3, generator=g), torch.randn(bpl * 6, generator=g)
+    cw, cb = torch.randn(bpl * ncls, c, 3, 3, 3, generator=g), torch.randn(bpl * ncls, generator=g)
+    wp, bp = ops.pack_head_weight(lw, lb, cw, cb)
+    assert wp.shape == (32, 27 * c) and wp.dtype == torch.bfloat16
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    cols = []
+    for kd in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                cols.append(xp[0, :, kd:kd + 4, kh:kh + 5, kw:kw + 6].permute(1, 2, 3, 0).reshape(-1, c))
+    a = torch.cat(cols, 1)                                           # (voxels, 27*C), tap-major
+    out = a @ wp.float().t() + bp
+    want_l = F.conv3d(x, lw.to(torch.bfloat16).float(), lb, 1, 1).permute(0, 2, 3, 4, 1).reshape(-1, bpl * 6)
+    want_c = F.conv3d(x, cw.to(torch.bfloat16).float(), cb, 1, 1).permute(0, 2, 3, 4, 1).reshape(-1, bpl * ncls)
+    torch.testing.assert_close(out[:, :bpl * 6], want_l, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out[:, bpl * 6:bpl * (6 + ncls)], want_c, rtol=1e-4, atol=1e-4)
+    assert float(out[:, bpl * (6 + ncls):].abs().max()) == 0.0
+    # stem: (27*Cin, 32), row = tap*Cin + cin
+    w = torch.randn(32, 2, 3, 3, 3, generator=g)
+    ps = ops.pack_stem_weight(w)
+    assert ps.shape == (54, 32)
+    assert float(ps[(1 * 9 + 2 * 3 + 0) * 2 + 1, 5]) == float(w[5, 1, 1, 2, 0].to(torch.bfloat16))
+    # depthwise: (27, C)
+    wd = torch.randn(16, 1, 3, 3, 3, generator=g)
+    pd = ops.pack_dw_weight(wd)
+    assert pd.shape == (27, 16) and float(pd[2 * 9 + 0 * 3 + 1, 7]) == float(wd[7, 0, 2, 0, 1].to(torch.bfloat16))
+    # BN fold
+    bn = torch.nn.BatchNorm3d(4).eval()
+    bn.running_mean.normal_(generator=g), bn.running_var.uniform_(0.5, 1.5, generator=g)
+    bn.weight.data.normal_(generator=g), bn.bias.data.normal_(generator=g)
+    s, b = ops.fold_bn(bn)
+    xx = torch.randn(2, 4, 3, 3, 3, generator=g)
+    torch.testing.assert_close(xx * s.view(1, -1, 1, 1, 1) + b.view(1, -1, 1, 1, 1), bn(xx), rtol=1e-5, atol=1e-5)
+
+
+def test_synthetic_volumes_follow_the_generator_spec():
+    from mslesions3d_b200 import synthetic
+    vols, boxes, labels = synthetic.make_batch(2, 2, (32, 32, 32), with_boxes=True, object_size=(4, 9))
+    assert vols.shape == (2, 2, 32, 32, 32) and vols.dtype.name == "float32"
+    assert abs(float(vols[0, 0].mean())) < 1e-3 and abs(float(vols[0, 0].std()) - 1) < 1e-2   # z-scored
+    assert all(b.shape[1] == 6 and (b[:, 3:] > b[:, :3]).all() for b in boxes)
+    v2 = synthetic.make_batch(2, 2, (32, 32, 32), object_size=(4, 9))
+    assert (vols == v2).all()
