@@ -297,7 +297,7 @@ def main():
     vox_out = BATCH * (SIZE[0] // 2) * (SIZE[1] // 2) * (SIZE[2] // 2)
     algo_bytes = in_bytes + vox_out * 32 * 2 + 27 * CHANNELS * 32 * 4
     achieved = algo_bytes / (k_ms / 1000.0) / 1e9
-    roofline = {"kernel": "stem_conv_kernel<bf16,2> (dense 3x3x3 conv 2->32 + BN + ReLU)", "bound": "hbm",
+    roofline = {"kernel": "stem_tc_kernel<bf16,2> (dense 3x3x3 conv 2->32 + BN + ReLU, tcgen05 implicit GEMM)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms, "peak_source": peak_src}
 

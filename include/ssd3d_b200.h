@@ -42,12 +42,19 @@ const char* ssd3d_version(void);
 
 /* Stem: dense Conv3d(Cin->Cout=32, k3, pad 1, stride (sd,2,2), no bias) + BN(eval, as scale/shift) + ReLU.
  * Replaces mobilenet.py:28-30 as instantiated at ssd3d.py:61.
- *   x      (N, Cin, D, H, W) NCDHW, fp32 (x_is_bf16 = 0) or bf16 (x_is_bf16 = 1); Cin in 1..4
- *   w      (27*Cin, 32) fp32, row = tap*Cin + cin, tap = (kd*3+kh)*3+kw   (values already bf16-rounded)
+ *   x      (N, Cin, D, H, W) NCDHW, fp32 (x_is_bf16 = 0, rounded to bf16 on load) or bf16; Cin in 1..4
+ *   w      (32, KPAD) bf16, KPAD = 64 (Cin <= 2) or 128: the conv weight flattened as (Cout, Cin*27)
+ *          -- PyTorch's own (Cout, Cin, 3,3,3) order -- zero padded along K
  *   scale, shift (32) fp32:  y = relu(conv * scale + shift)
- *   y      (N, Do, Ho, Wo, 32) bf16, Do = (D-1)/sd+1, Ho = (H-1)/2+1, Wo = (W-1)/2+1 */
-int ssd3d_stem_conv_bn_relu(const void* x, int x_is_bf16, const float* w, const float* scale, const float* shift,
+ *   y      (N, Do, Ho, Wo, 32) bf16, Do = (D-1)/sd+1, Ho = (H-1)/2+1, Wo = (W-1)/2+1
+ * Runs as a tcgen05 implicit GEMM fed by a 4-D TMA halo load when the row pitch W*elemsize is a multiple
+ * of 16 bytes (ssd3d_stem_tc_supported), otherwise on the CUDA-core kernel (.._simt, same contract). */
+int ssd3d_stem_conv_bn_relu(const void* x, int x_is_bf16, const void* w, const float* scale, const float* shift,
                             void* y, int N, int Cin, int D, int H, int W, int stride_d, void* stream);
+int ssd3d_stem_conv_bn_relu_simt(const void* x, int x_is_bf16, const void* w, const float* scale,
+                                 const float* shift, void* y, int N, int Cin, int D, int H, int W, int stride_d,
+                                 void* stream);
+int ssd3d_stem_tc_supported(int x_is_bf16, int Cin, int W);
 
 /* Depthwise Conv3d(C, C, k3, pad 1, stride s in {1,2}, groups=C, no bias) + BN + ReLU.
  * Replaces mobilenet.py:38,44 (Block.conv1/bn1).

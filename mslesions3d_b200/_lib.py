@@ -26,6 +26,8 @@ P = c_void_p  # every device pointer / stream crosses the ABI as a plain address
 SIGNATURES = {
     "ssd3d_version": (c_char_p, []),
     "ssd3d_stem_conv_bn_relu": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "ssd3d_stem_conv_bn_relu_simt": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "ssd3d_stem_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ssd3d_dwconv3d_bn_relu": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "ssd3d_pwconv_bn_relu": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, P, P]),
     "ssd3d_head_conv": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,

@@ -124,13 +124,20 @@ template <> __device__ __forceinline__ float load_in<__nv_bfloat16>(const __nv_b
 }
 
 template <typename T, int CIN>
-__global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ shift,
                                                         __nv_bfloat16* __restrict__ y, int N, int D, int H, int W,
                                                         int Do, int Ho, int Wo, int sd, long long total_pairs) {
+  // w is (32, KPAD) bf16 with k = ci*27 + tap (PyTorch's flattened (Cin,3,3,3)); shared copy is
+  // [tap*CIN + ci][32] fp32 so that one tap's 32 output-channel weights are contiguous
+  constexpr int KPAD = (27 * CIN <= 64) ? 64 : 128;
   __shared__ __align__(16) float ws[27 * CIN * 32];
-  for (int i = threadIdx.x; i < 27 * CIN * 32; i += blockDim.x) ws[i] = w[i];
+  for (int i = threadIdx.x; i < 27 * CIN * 32; i += blockDim.x) {
+    const int c = i & 31, kk = i >> 5;
+    const int tap = kk / CIN, ci = kk - tap * CIN;
+    ws[i] = __bfloat162float(w[c * KPAD + ci * 27 + tap]);
+  }
   __syncthreads();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total_pairs) return;
@@ -209,8 +216,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x,
 }
 
 template <typename T>
-static int launch_stem(const void* x, const float* w, const float* scale, const float* shift, void* y, int N, int Cin,
-                       int D, int H, int W, int sd, cudaStream_t st) {
+static int launch_stem(const void* x, const __nv_bfloat16* w, const float* scale, const float* shift, void* y, int N,
+                       int Cin, int D, int H, int W, int sd, cudaStream_t st) {
   const int Do = (D - 1) / sd + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = (long long)N * Do * Ho * ((Wo + 1) / 2);
   const unsigned blocks = (unsigned)((total + 127) / 128);
@@ -229,14 +236,15 @@ static int launch_stem(const void* x, const float* w, const float* scale, const 
 
 }  // namespace ssd3d
 
-extern "C" int ssd3d_stem_conv_bn_relu(const void* x, int x_is_bf16, const float* w, const float* scale,
-                                       const float* shift, void* y, int N, int Cin, int D, int H, int W, int stride_d,
-                                       void* stream) {
+extern "C" int ssd3d_stem_conv_bn_relu_simt(const void* x, int x_is_bf16, const void* w, const float* scale,
+                                            const float* shift, void* y, int N, int Cin, int D, int H, int W,
+                                            int stride_d, void* stream) {
   if (!x || !w || !scale || !shift || !y || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
   if (stride_d != 1 && stride_d != 2) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (x_is_bf16) return ssd3d::launch_stem<__nv_bfloat16>(x, w, scale, shift, y, N, Cin, D, H, W, stride_d, st);
-  return ssd3d::launch_stem<float>(x, w, scale, shift, y, N, Cin, D, H, W, stride_d, st);
+  const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
+  if (x_is_bf16) return ssd3d::launch_stem<__nv_bfloat16>(x, wp, scale, shift, y, N, Cin, D, H, W, stride_d, st);
+  return ssd3d::launch_stem<float>(x, wp, scale, shift, y, N, Cin, D, H, W, stride_d, st);
 }
 
 extern "C" int ssd3d_dwconv3d_bn_relu(const void* x, const void* w, const float* scale, const float* shift, void* y,

@@ -166,42 +166,66 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   mask[(long long)seg * seg_stride_mask + (long long)i * words + cb] = bits;
 }
 
-// Greedy scan of one segment's bit matrix (rows are `row_stride` words apart).  `removed` is shared
-// scratch of ceil(n/64) 64-bit words, `keptw` receives the keep bits.  Only words cb >= rb of row i
-// were written by nms_mask_kernel, and only those are read.  Called by all threads of the block.
-__device__ void nms_scan(const unsigned long long* __restrict__ mask, int n, int row_stride,
-                         unsigned long long* removed, unsigned long long* keptw, unsigned long long* diag) {
+// Greedy scan of one segment's bit matrix M (rows `stride` words apart; shared or global memory).
+// `removed` is scratch of ceil(n/64) words, `keptw` receives the keep bits.  Only words w >= i/64 of row
+// i exist (nms_mask_kernel skips the lower triangle) and only those are read.  All threads call it.
+//
+// The 64 boxes of a chunk are resolved by ONE thread on register-resident diagonal words (a fully
+// unrolled chain of bit tests, ~5 dependent ALU ops per box); the rows of the boxes it keeps are then
+// OR-ed into the later words by the whole block.
+__device__ __forceinline__ void nms_scan_core(const unsigned long long* M, int n, int stride,
+                                              unsigned long long* removed, unsigned long long* keptw) {
   const int words = (n + 63) >> 6;
   for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0ull;
   __syncthreads();
   for (int k = 0; k < words; ++k) {
     const int rows = min(64, n - k * 64);
-    if (threadIdx.x < 64) diag[threadIdx.x] = (threadIdx.x < rows) ? mask[(long long)(k * 64 + threadIdx.x) * row_stride + k] : 0ull;
-    __syncthreads();
     if (threadIdx.x == 0) {
+      unsigned long long d[64];
+#pragma unroll
+      for (int b = 0; b < 64; ++b) d[b] = (b < rows) ? M[(long long)(k * 64 + b) * stride + k] : 0ull;
       unsigned long long cur = removed[k], kept = 0ull;
-      for (int b = 0; b < rows; ++b) {
-        if (!((cur >> b) & 1ull)) {
-          kept |= (1ull << b);
-          cur |= diag[b];
-        }
+      if (rows < 64) cur |= (~0ull) << rows;   // rows past the end are never kept
+#pragma unroll
+      for (int b = 0; b < 64; ++b) {
+        const bool fr = ((cur >> b) & 1ull) == 0ull;
+        kept |= fr ? (1ull << b) : 0ull;
+        cur |= fr ? d[b] : 0ull;
       }
       keptw[k] = kept;
     }
     __syncthreads();
     const unsigned long long kept = keptw[k];
-    // OR the rows of this chunk's kept boxes into the later words
-    for (int w = k + 1 + (int)threadIdx.x; w < words; w += blockDim.x) {
-      unsigned long long acc = removed[w];
-      unsigned long long kk = kept;
-      while (kk) {
-        const int b = __ffsll((long long)kk) - 1;
-        kk &= kk - 1;
-        acc |= mask[(long long)(k * 64 + b) * row_stride + w];
+    if (kept != 0ull) {
+      for (int w = k + 1 + (int)threadIdx.x; w < words; w += blockDim.x) {
+        unsigned long long acc = removed[w];
+        const unsigned long long* col = M + (long long)(k * 64) * stride + w;
+#pragma unroll 16
+        for (int b = 0; b < 64; ++b)
+          if ((kept >> b) & 1ull) acc |= col[(long long)b * stride];
+        removed[w] = acc;
       }
-      removed[w] = acc;
     }
     __syncthreads();
+  }
+}
+
+// Stage the upper-triangular words of the bit matrix in shared memory when they fit (the default
+// 10*top_k = 1000 candidates need 125 KB), so that the serial chain runs at shared-memory latency.
+__device__ void nms_scan(const unsigned long long* __restrict__ mask, int n, int row_stride,
+                         unsigned long long* removed, unsigned long long* keptw, unsigned long long* stage,
+                         long long stage_words) {
+  const int words = (n + 63) >> 6;
+  if ((long long)n * words <= stage_words) {
+    const int total = n * words;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int i = e / words, w = e - i * words;
+      if (w >= (i >> 6)) stage[e] = mask[(long long)i * row_stride + w];
+    }
+    __syncthreads();
+    nms_scan_core(stage, n, words, removed, keptw);
+  } else {
+    nms_scan_core(mask, n, row_stride, removed, keptw);
   }
 }
 
@@ -221,7 +245,7 @@ __device__ __forceinline__ int count_greater(const float* s, int n, float v, boo
 
 __global__ void __launch_bounds__(256) nms_select_kernel(const unsigned long long* __restrict__ mask,
                                                          const int* __restrict__ nkeep, int C, int nmax, int words_max,
-                                                         const float* __restrict__ sboxes,
+                                                         long long stage_words, const float* __restrict__ sboxes,
                                                          const float* __restrict__ sscores,
                                                          const int* __restrict__ sprior, int* __restrict__ kept_pos,
                                                          float* __restrict__ kept_score, int* __restrict__ kept_cnt,
@@ -231,7 +255,7 @@ __global__ void __launch_bounds__(256) nms_select_kernel(const unsigned long lon
   extern __shared__ unsigned long long sm[];
   unsigned long long* removed = sm;
   unsigned long long* keptw = sm + words_max;
-  unsigned long long* diag = sm + 2 * words_max;
+  unsigned long long* stage = sm + 2 * words_max;
   __shared__ int s_total;
   const int img = blockIdx.x;
   const int nseg = C - 1;
@@ -244,7 +268,7 @@ __global__ void __launch_bounds__(256) nms_select_kernel(const unsigned long lon
     int* kp = kept_pos + (long long)seg * nmax;
     float* ks = kept_score + (long long)seg * nmax;
     if (n > 0) {
-      nms_scan(mask + (long long)seg * nmax * words_max, n, words_max, removed, keptw, diag);
+      nms_scan(mask + (long long)seg * nmax * words_max, n, words_max, removed, keptw, stage, stage_words);
       __syncthreads();
       // exclusive prefix of the kept counts per word (kept in `removed`, which the scan is done with)
       if (threadIdx.x == 0) {
@@ -330,16 +354,23 @@ __global__ void __launch_bounds__(256) nms_select_kernel(const unsigned long lon
 
 // standalone scan for ssd3d_nms3d_sorted
 __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int words,
-                                                       uint8_t* __restrict__ keep) {
+                                                       long long stage_words, uint8_t* __restrict__ keep) {
   extern __shared__ unsigned long long sm[];
   unsigned long long* removed = sm;
   unsigned long long* keptw = sm + words;
-  unsigned long long* diag = sm + 2 * words;
-  nms_scan(mask, n, words, removed, keptw, diag);
+  unsigned long long* stage = sm + 2 * words;
+  nms_scan(mask, n, words, removed, keptw, stage, stage_words);
   for (int i = threadIdx.x; i < n; i += blockDim.x) keep[i] = (uint8_t)((keptw[i >> 6] >> (i & 63)) & 1ull);
 }
 
 static inline long long align256(long long v) { return (v + 255) & ~255ll; }
+
+// shared-memory words available for staging the bit matrix of up to n_max candidates (<= ~200 KB)
+static inline long long nms_stage_words(int words, long long n_max) {
+  const long long budget = (200ll * 1024) / 8 - 2ll * words;
+  const long long want = n_max * (long long)words;
+  return want < budget ? want : (budget > 0 ? budget : 0);
+}
 
 struct DetectLayout {
   int S, nmax, words;
@@ -400,12 +431,14 @@ extern "C" int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_o
   nms_mask_kernel<<<grid, 64, 0, st>>>(boxes_xyz, nullptr, (int)n, 0, words, 0, max_overlap,
                                        static_cast<unsigned long long*>(mask_ws));
   SSD3D_CHECK_LAUNCH();
-  const size_t smem = (size_t)(2 * words + 64) * 8;
+  const long long stage_words = nms_stage_words(words, n);
+  const size_t smem = (size_t)(2 * words + stage_words) * 8;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  nms_scan_kernel<<<1, 256, smem, st>>>(static_cast<const unsigned long long*>(mask_ws), (int)n, words, keep);
+  nms_scan_kernel<<<1, 256, smem, st>>>(static_cast<const unsigned long long*>(mask_ws), (int)n, words, stage_words,
+                                        keep);
   SSD3D_CHECK_LAUNCH();
   return SSD3D_OK;
 }
@@ -463,8 +496,13 @@ extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, cons
     SSD3D_CHECK_LAUNCH();
   }
   {
-    const size_t smem = (size_t)(2 * L.words + 64) * 8;
-    nms_select_kernel<<<N, 256, smem, st>>>(mask, nkeep, n_classes, L.nmax, L.words, sboxes, sscores, sprior, keptpos,
+    const long long stage_words = nms_stage_words(L.words, L.nmax);
+    const size_t smem = (size_t)(2 * L.words + stage_words) * 8;
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+    }
+    nms_select_kernel<<<N, 256, smem, st>>>(mask, nkeep, n_classes, L.nmax, L.words, stage_words, sboxes, sscores, sprior, keptpos,
                                             keptscore, keptcnt, top_k, out_boxes, out_scores,
                                             reinterpret_cast<long long*>(out_labels),
                                             reinterpret_cast<long long*>(out_prior), out_count);

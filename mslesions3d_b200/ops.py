@@ -60,8 +60,9 @@ def _alloc_ndhwc(n, c, d, h, w, device) -> torch.Tensor:
 
 
 def stem_conv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
-                      stride_d: int) -> torch.Tensor:
-    """x (N,Cin,D,H,W) contiguous fp32|bf16 -> (N,32,Do,Ho,Wo) channels-last bf16.  mobilenet.py:28-30."""
+                      stride_d: int, force_simt: bool = False) -> torch.Tensor:
+    """x (N,Cin,D,H,W) contiguous fp32|bf16 -> (N,32,Do,Ho,Wo) channels-last bf16.  mobilenet.py:28-30.
+    tcgen05 implicit GEMM when TMA can address the rows, CUDA-core kernel otherwise (or when forced)."""
     _need_cuda(x, w_packed, scale, shift)
     if x.dim() != 5:
         raise RuntimeError("expected (N, C, D, H, W) input")
@@ -70,8 +71,10 @@ def stem_conv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tens
     x = x.contiguous()
     n, cin, d, h, w = x.shape
     y = _alloc_ndhwc(n, 32, conv_out(d, stride_d), conv_out(h, 2), conv_out(w, 2), x.device)
-    rc = _lib.load().ssd3d_stem_conv_bn_relu(x.data_ptr(), int(x.dtype == BF16), w_packed.data_ptr(), scale.data_ptr(),
-                                             shift.data_ptr(), y.data_ptr(), n, cin, d, h, w, stride_d, _stream())
+    lib = _lib.load()
+    fn = lib.ssd3d_stem_conv_bn_relu_simt if force_simt else lib.ssd3d_stem_conv_bn_relu
+    rc = fn(x.data_ptr(), int(x.dtype == BF16), w_packed.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
+            n, cin, d, h, w, stride_d, _stream())
     _lib.check(rc, "ssd3d_stem_conv_bn_relu")
     LAUNCHES[0] += 1
     return y
@@ -132,9 +135,12 @@ def fold_bn(bn: torch.nn.BatchNorm3d) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
-    """(32, Cin, 3,3,3) -> (27*Cin, 32) fp32 with bf16-rounded values; row = tap*Cin + cin."""
+    """(32, Cin, 3,3,3) -> (32, KPAD) bf16: the weight flattened in its own (Cin,3,3,3) order, K zero-padded
+    to 64 (Cin <= 2) or 128."""
     co, ci = w.shape[0], w.shape[1]
-    p = w.detach().to(BF16).float().permute(2, 3, 4, 1, 0).reshape(27 * ci, co)
+    kpad = 64 if 27 * ci <= 64 else 128
+    p = torch.zeros((co, kpad), dtype=BF16, device=w.device)
+    p[:, :27 * ci] = w.detach().reshape(co, 27 * ci).to(BF16)
     return p.contiguous()
 
 

@@ -60,6 +60,11 @@ def rand_bn(c, g):
     (2, (17, 19, 23), 2, torch.float32, 2),
     (1, (40, 40, 40), 2, torch.bfloat16, 3),
     (3, (9, 16, 31), 1, torch.float32, 1),
+    (2, (128, 128, 128), 2, torch.bfloat16, 1),    # the benchmark shape: tcgen05 path, 64-wide tiles
+    (1, (96, 96, 96), 2, torch.float32, 1),        # fp32 TMA tile, 16-wide tiles
+    (4, (16, 32, 24), 1, torch.float32, 2),        # K = 108 -> two k-blocks
+    (3, (24, 24, 24), 2, torch.bfloat16, 1),
+    (2, (6, 8, 8), 2, torch.bfloat16, 3),          # tile larger than the volume
 ])
 def test_stem_conv(cin, size, sd, dtype, batch):
     ops = _ops()
@@ -69,9 +74,11 @@ def test_stem_conv(cin, size, sd, dtype, batch):
     scale, shift = rand_bn(32, g)
     want = F.conv3d(bf16r(x), bf16r(w), None, (sd, 2, 2), 1)
     want = bf16r(F.relu(want * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)))
-    got = ops.stem_conv_bn_relu(x.to(dtype).cuda(), ops.pack_stem_weight(w.cuda()), scale.cuda(), shift.cuda(), sd)
-    assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last_3d)
-    assert_bf16_close(got, want, "stem")
+    for force_simt in (False, True):     # default = tcgen05 implicit GEMM when TMA can address the rows
+        got = ops.stem_conv_bn_relu(x.to(dtype).cuda(), ops.pack_stem_weight(w.cuda()), scale.cuda(), shift.cuda(), sd,
+                                    force_simt=force_simt)
+        assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last_3d)
+        assert_bf16_close(got, want, "stem simt" if force_simt else "stem")
 
 
 @pytest.mark.parametrize("c,size,stride,batch", [

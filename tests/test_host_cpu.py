@@ -139,11 +139,13 @@ def test_weight_packing_layouts():
     torch.testing.assert_close(out[:, :bpl * 6], want_l, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(out[:, bpl * 6:bpl * (6 + ncls)], want_c, rtol=1e-4, atol=1e-4)
     assert float(out[:, bpl * (6 + ncls):].abs().max()) == 0.0
-    # stem: (27*Cin, 32), row = tap*Cin + cin
+    # stem: (32, KPAD) bf16, k = cin*27 + tap, zero padded
     w = torch.randn(32, 2, 3, 3, 3, generator=g)
     ps = ops.pack_stem_weight(w)
-    assert ps.shape == (54, 32)
-    assert float(ps[(1 * 9 + 2 * 3 + 0) * 2 + 1, 5]) == float(w[5, 1, 1, 2, 0].to(torch.bfloat16))
+    assert ps.shape == (32, 64) and ps.dtype == torch.bfloat16
+    assert float(ps[5, 1 * 27 + 1 * 9 + 2 * 3 + 0]) == float(w[5, 1, 1, 2, 0].to(torch.bfloat16))
+    assert float(ps[:, 54:].abs().max()) == 0.0
+    assert ops.pack_stem_weight(torch.randn(32, 3, 3, 3, 3)).shape == (32, 128)
     # depthwise: (27, C)
     wd = torch.randn(16, 1, 3, 3, 3, generator=g)
     pd = ops.pack_dw_weight(wd)
