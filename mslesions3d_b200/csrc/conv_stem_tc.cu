@@ -52,16 +52,17 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
   constexpr int KPAD = (KREAL <= 64) ? 64 : 128;
   constexpr int KB = KPAD / 64;
   constexpr int NREG = KPAD / 2;          // packed bf16 pairs per A row
+  constexpr int PADL = 16 / (int)sizeof(TIn);   // left halo rounded up to 16 bytes (1 column is needed)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // KB x (128 rows x 128 B)
   uint8_t* sB = sA + KB * 16384;                        // KB x (32 rows x 128 B)
-  uint8_t* sX = sB + KB * 4096;                         // input halo tile [CIN][TDI][THI][TWI] of TIn
+  uint8_t* ctl = sB + KB * 4096;                        // mbarriers + TMEM slot (128 B)
+  uint8_t* sX = ctl + 128;                              // input halo tile [CIN][TDI][THI][TWI] of TIn
   const int tile_elems = CIN * p.TDI * p.THI * p.TWI;
-  uint8_t* tail = sX + (((size_t)tile_elems * sizeof(TIn) + 15) & ~(size_t)15);
-  uint64_t* bar_in = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* bar_in = reinterpret_cast<uint64_t*>(ctl);
   uint64_t* bar_mma = bar_in + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_in + 2);
 
@@ -74,13 +75,16 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
   const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
   const int n = t;
 
-  if (tid == 0) {
+  // barrier init and TMA issue live in warp 1, so that warp 0 reaches the .sync.aligned TMEM
+  // allocation fully converged (a lane still inside a divergent branch makes it an illegal instruction)
+  if (tid == 32) {
     tma_prefetch_desc(&tmX);
     mbar_init(bar_in, 1);
     mbar_init(bar_mma, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
+    __syncwarp();
     tmem_alloc(tmem_slot, 32);
     tmem_relinquish();
   }
@@ -89,9 +93,11 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (tid == 0) {
+  if (tid == 32) {
     mbar_arrive_expect_tx(bar_in, (uint32_t)(tile_elems * sizeof(TIn)));
-    tma_load_4d(sX, &tmX, bar_in, 2 * w0 - 1, 2 * h0 - 1, p.sd * d0 - 1, n * CIN);
+    // TMA needs the box start to be 16-byte aligned along the innermost dimension (a start at column
+    // 2*w0 - 1 is an illegal instruction): fetch from 2*w0 - PADL, PADL = 16 bytes of elements
+    tma_load_4d(sX, &tmX, bar_in, 2 * w0 - PADL, 2 * h0 - 1, p.sd * d0 - 1, n * CIN);
   }
 
   // weights -> swizzled B operand while the TMA is in flight: 32 rows x (KPAD/8) 16-byte chunks
@@ -120,16 +126,17 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
         const int g = (ci * 3 + kd) * 3 + kh;
-        const TIn* src = xt + ((ci * p.TDI + (p.sd * dl + kd)) * p.THI + (2 * hl + kh)) * p.TWI + 2 * wl;
+        // taps kw = 0..2 sit at tile columns 2*wl + PADL - 1 .. 2*wl + PADL + 1
+        const TIn* src = xt + ((ci * p.TDI + (p.sd * dl + kd)) * p.THI + (2 * hl + kh)) * p.TWI + 2 * wl + PADL;
         uint32_t e0, e1, e2;
         if constexpr (sizeof(TIn) == 2) {
-          const uint32_t a = *reinterpret_cast<const uint32_t*>(src);
-          const uint32_t b = *reinterpret_cast<const uint32_t*>(src + 2);
-          e0 = a & 0xffffu; e1 = a >> 16; e2 = b & 0xffffu;
+          const uint32_t a = *reinterpret_cast<const uint32_t*>(src - 2);   // columns -2, -1
+          const uint32_t b = *reinterpret_cast<const uint32_t*>(src);       // columns  0, +1
+          e0 = a >> 16; e1 = b & 0xffffu; e2 = b >> 16;
         } else {
-          const float2 a = *reinterpret_cast<const float2*>(src);
-          const float b = reinterpret_cast<const float*>(src)[2];
-          e0 = bf16_bits(a.x); e1 = bf16_bits(a.y); e2 = bf16_bits(b);
+          const float a = reinterpret_cast<const float*>(src)[-1];
+          const float2 b = *reinterpret_cast<const float2*>(src);
+          e0 = bf16_bits(a); e1 = bf16_bits(b.x); e2 = bf16_bits(b.y);
         }
         const int k0 = g * 3;
         regs[(k0 + 0) >> 1] |= e0 << (16 * ((k0 + 0) & 1));
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
   fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
   __syncthreads();
 
-  if (tid == 0) {
+  if (tid == 32) {
     tc_fence_after();
     const uint32_t idesc = umma_idesc_bf16(128, 32);
 #pragma unroll
@@ -161,6 +168,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
   }
   __syncwarp();
   mbar_wait(bar_mma, 0);
+  __syncwarp();                 // tcgen05.ld is .sync.aligned: reconverge after the per-thread poll loop
   tc_fence_after();
 
   // ---- epilogue: TMEM lane = tile row = this thread's voxel ----
@@ -192,6 +200,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, 32);
   }
@@ -218,11 +227,12 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
     cuuint32_t box[4] = {(cuuint32_t)p.TWI, (cuuint32_t)p.THI, (cuuint32_t)p.TDI, (cuuint32_t)CIN};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&tm, dt, 4, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return SSD3D_ERR_TMA;
   }
   const size_t tile_bytes = ((size_t)CIN * p.TDI * p.THI * p.TWI * sizeof(TIn) + 15) & ~(size_t)15;
-  const size_t smem = 1024 + (size_t)KB * (16384 + 4096) + tile_bytes + 64;
+  const size_t smem = 1024 + (size_t)KB * (16384 + 4096) + 128 + tile_bytes + 256;
   cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<TIn, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const unsigned grid = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_d * p.N);
@@ -259,8 +269,10 @@ static int stem_tc(const void* x, int x_is_bf16, const void* w_tc, const float* 
   p.TH = p2ceil(p.Ho) < rest ? p2ceil(p.Ho) : rest;
   rest /= p.TH;
   p.TD = rest;                                 // whatever remains goes to D (rows past Do are masked)
-  const int align = x_is_bf16 ? 8 : 4;
-  p.TWI = ((2 * p.TW + 1 + align - 1) / align) * align;
+  const int padl = x_is_bf16 ? 8 : 4;          // 16 bytes of elements on the left (see the kernel)
+  p.TWI = 2 * p.TW + padl;                      // columns 2*w0 - padl .. 2*w0 + 2*TW - 1: a multiple of 16 bytes
+  // every tile's first column 2*k*TW - padl must stay 16-byte aligned
+  if (p.Wo > p.TW && ((2 * p.TW * (x_is_bf16 ? 2 : 4)) % 16) != 0) return SSD3D_ERR_UNSUPPORTED;
   p.THI = 2 * p.TH + 1;
   p.TDI = stride_d * (p.TD - 1) + 3;
   if (p.TWI > 256 || p.THI > 256 || p.TDI > 256) return SSD3D_ERR_UNSUPPORTED;

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
     mbar_wait(tmem_full, 0);
+    __syncwarp();               // tcgen05.ld is .sync.aligned: reconverge after the per-thread poll loop
     tc_fence_after();
     const int row = warp * 32 + lane;                  // tile row == TMEM lane
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);

