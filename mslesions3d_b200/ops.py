@@ -245,8 +245,12 @@ class DetectOutput:
 
 
 def detect_objects_padded(locs: torch.Tensor, scores: torch.Tensor, priors: torch.Tensor, min_score: float,
-                          max_overlap: float, top_k: int, workspace: Optional[torch.Tensor] = None) -> DetectOutput:
-    """The whole of ``detect_objects`` on the device, no host sync; see include/ssd3d_b200.h."""
+                          max_overlap: float, top_k: int, workspace: Optional[torch.Tensor] = None,
+                          out_count: Optional[torch.Tensor] = None,
+                          status: Optional[torch.Tensor] = None) -> DetectOutput:
+    """The whole of ``detect_objects`` on the device, no host sync; see include/ssd3d_b200.h.
+    ``out_count`` (N,) / ``status`` (1,) int32 may be supplied (e.g. slices of one buffer that is read back
+    with a single copy)."""
     _need_cuda(locs, scores, priors)
     locs, scores, priors = locs.float().contiguous(), scores.float().contiguous(), priors.float().contiguous()
     n, p, c = scores.shape
@@ -262,8 +266,10 @@ def detect_objects_padded(locs: torch.Tensor, scores: torch.Tensor, priors: torc
     out_scores = torch.empty((n, top_k), dtype=torch.float32, device=dev)
     out_labels = torch.empty((n, top_k), dtype=torch.int64, device=dev)
     out_prior = torch.empty((n, top_k), dtype=torch.int64, device=dev)
-    out_count = torch.empty((n,), dtype=torch.int32, device=dev)
-    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    if out_count is None:
+        out_count = torch.empty((n,), dtype=torch.int32, device=dev)
+    if status is None:
+        status = torch.empty((1,), dtype=torch.int32, device=dev)
     rc = lib.ssd3d_detect_objects(locs.data_ptr(), scores.data_ptr(), priors.data_ptr(), n, p, c, f32(min_score),
                                   f32(max_overlap), top_k, out_boxes.data_ptr(), out_scores.data_ptr(),
                                   out_labels.data_ptr(), out_prior.data_ptr(), out_count.data_ptr(),

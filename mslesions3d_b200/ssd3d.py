@@ -215,6 +215,77 @@ class PredictionConvolutions(nn.Module):
         return locs, classes_scores
 
 
+class _InferencePlan:
+    """forward + detect_objects for one input signature, captured once into a CUDA graph.
+
+    The network is 19 small kernels (~20 us each at the benchmark size) plus 4 detection kernels: launched
+    one by one from Python the step is host-bound, so the whole sequence is recorded on first use and
+    replayed with a single launch.  Inputs are copied into a static buffer; outputs live in static buffers
+    whose per-image counts, the detect status word and the NaN flag are packed in one int32 vector that is
+    read back with a single device->host copy."""
+
+    def __init__(self, model: "LSSD3D", shape, dtype, min_score, max_overlap, top_k):
+        dev = model.device
+        n = shape[0]
+        self.key = None
+        self.inp = torch.empty(shape, dtype=dtype, device=dev)
+        self.meta = torch.zeros((n + 2,), dtype=torch.int32, device=dev)
+        self.host_meta = torch.zeros((n + 2,), dtype=torch.int32).pin_memory()
+        self.args = (min_score, max_overlap, top_k)
+        self.n = n
+        self.out = None
+        self.graph = None
+        self.ready = torch.cuda.Event()      # input buffer may be overwritten / outputs were consumed
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            self.inp.zero_()
+            for _ in range(2):                # warm-up: lazy module loading, function attributes, packing
+                self._run(model)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        before = ops.LAUNCHES[0]
+        with torch.no_grad(), torch.cuda.graph(graph):
+            self._run(model)
+        self.n_kernels = ops.LAUNCHES[0] - before      # library kernels inside one replay
+        self.graph = graph
+
+    def _run(self, model: "LSSD3D"):
+        dev = self.inp.device
+        flag = model.base.nan_flag(dev)
+        flag.zero_()
+        feats = model.base(self.inp, check_nan=False)
+        locs, scores = model.pred_convs(feats, flag)
+        ms, mo, k = self.args
+        self.out = ops.detect_objects_padded(locs, scores, model._priors_on(dev), ms, mo, k,
+                                             out_count=self.meta[:self.n], status=self.meta[self.n:self.n + 1])
+        self.meta[self.n + 1:].copy_(flag)
+        self.locs, self.scores = locs, scores
+
+    def launch(self, image: torch.Tensor):
+        """Copy the batch in (H2D or D2D, asynchronous) and replay the graph on the current stream."""
+        self.inp.copy_(image, non_blocking=True)
+        self.graph.replay()
+        ops.LAUNCHES[0] += self.n_kernels
+        self.host_meta.copy_(self.meta, non_blocking=True)
+
+    def results(self, model: "LSSD3D"):
+        """Wait for the replay, check the flags, return fresh per-image tensors (the static buffers are
+        reused by the next replay)."""
+        torch.cuda.current_stream().synchronize()
+        meta = self.host_meta.tolist()
+        if meta[-1]:
+            model._raise_on_nan_bits(meta[-1])
+        if meta[-2] & 1:
+            raise RuntimeError("detect_objects: more than %d candidates above min_score for one (image, class)"
+                               % _lib.SORT_MAX)
+        counts = meta[:self.n]
+        boxes, labels, scores = self.out.boxes.clone(), self.out.labels.clone(), self.out.scores.clone()
+        return ([boxes[i, :k] for i, k in enumerate(counts)], [labels[i, :k] for i, k in enumerate(counts)],
+                [scores[i, :k] for i, k in enumerate(counts)])
+
+
 class LSSD3D(_LightningBase):
     """The SSD 3D network - the base MobileNet network and the prediction convolutions (ssd3d.py:172-738)."""
 
@@ -284,7 +355,8 @@ class LSSD3D(_LightningBase):
         self.priors_cxcycz = self.create_prior_boxes()
         self.loss_fn = MultiBoxLoss(self.priors_cxcycz, threshold=threshold, alpha=alpha)
         self.defer_nan_check = False
-        self._detect_ws = None
+        self.use_cuda_graph = True     # predict_step replays a captured forward+detect graph
+        self._plans = {}
 
     # ------------------------------------------------------------------------------------------
     def _make_base_and_prediction_layers(self):
@@ -352,6 +424,10 @@ class LSSD3D(_LightningBase):
         bits = int(flag.item())
         if bits:
             flag.zero_()
+        self._raise_on_nan_bits(bits)
+
+    @staticmethod
+    def _raise_on_nan_bits(bits: int):
         if bits & _lib.NAN_BACKBONE:
             print("Yesssss this NaN error again in the base network")
             raise Exception("Yesssss this NaN error again in the base network")
@@ -385,12 +461,100 @@ class LSSD3D(_LightningBase):
         self.base.init()
         self.pred_convs.init()
 
+    # ------------------------------------------------------------------------------------------
+    def _state_version(self):
+        """Cheap fingerprint of everything a captured plan depends on besides the input signature: in-place
+        updates of any parameter / buffer bump its version counter; moves and dtype changes go through
+        ``_apply`` which drops the plans."""
+        ts = self.__dict__.get("_state_tensors")
+        if ts is None:
+            ts = list(self.parameters()) + list(self.buffers())
+            self.__dict__["_state_tensors"] = ts
+        return sum(t._version for t in ts)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.get("_plans", {}).clear()
+        self.__dict__["_state_tensors"] = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__.get("_plans", {}).clear()
+        self.__dict__["_state_tensors"] = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def _plan_for(self, image: torch.Tensor, slot: int = 0) -> _InferencePlan:
+        if self.training:
+            raise NotImplementedError("predict_step needs eval(): the training-mode forward is not built yet")
+        dtype = image.dtype if image.dtype in (torch.float32, torch.bfloat16) else torch.float32
+        key = (tuple(image.shape), dtype, str(self.device), float(self.min_score), float(self.max_overlap),
+               int(self.top_k), slot)
+        ver = self._state_version()
+        plan = self._plans.get(key)
+        if plan is None or plan.key != ver:
+            if len(self._plans) > 8:
+                self._plans.clear()
+            plan = _InferencePlan(self, tuple(image.shape), dtype, self.min_score, self.max_overlap, self.top_k)
+            plan.key = ver
+            self._plans[key] = plan
+        return plan
+
     def predict_step(self, batch, batch_idx: int = 0, dataloader_idx: int = None):
-        """forward + detect_objects with a single host sync for the whole batch (ssd3d.py:692-702)."""
+        """forward + detect_objects (ssd3d.py:692-702): one CUDA-graph replay and a single host sync for the
+        whole batch.  ``batch["img"]`` may live on the host (pinned memory makes the copy asynchronous)."""
+        image = batch["img"]
+        if not self.use_cuda_graph:
+            return self._predict_step_eager(image)
+        if self.device.type != "cuda":
+            raise RuntimeError("LSSD3D.predict_step needs the model on a CUDA device; there is no CPU path")
+        plan = self._plan_for(image)
+        plan.launch(image if image.dtype == plan.inp.dtype else image.to(plan.inp.dtype))
+        return plan.results(self)
+
+    def predict_batches(self, batches):
+        """Generator over an iterable of batches (dicts with "img", as a DataLoader yields them) -> per-batch
+        (boxes, labels, scores).  What ``Trainer.predict(model, loader)`` does in the reference
+        (predict.py:262-263), software-pipelined: the host->device copy of batch i+1 runs on a copy stream
+        while the graph of batch i executes, using two input slots."""
+        if self.device.type != "cuda":
+            raise RuntimeError("LSSD3D.predict_batches needs the model on a CUDA device; there is no CPU path")
+        compute = torch.cuda.current_stream()
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(device=self.device)
+        pending = None          # (plan, copied-event)
+        slot = 0
+        for batch in batches:
+            image = batch["img"]
+            plan = self._plan_for(image, slot)
+            if image.dtype != plan.inp.dtype:
+                image = image.to(plan.inp.dtype)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(plan.ready)           # previous replay that read this slot is done
+                plan.inp.copy_(image, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(copy_stream)
+            if pending is not None:
+                yield self._finish(pending, compute)
+            pending = (plan, copied)
+            slot ^= 1
+        if pending is not None:
+            yield self._finish(pending, compute)
+
+    def _finish(self, pending, compute):
+        plan, copied = pending
+        compute.wait_event(copied)
+        plan.graph.replay()
+        ops.LAUNCHES[0] += plan.n_kernels
+        plan.host_meta.copy_(plan.meta, non_blocking=True)
+        res = plan.results(self)
+        plan.ready.record(compute)
+        return res
+
+    def _predict_step_eager(self, image):
         prev = self.defer_nan_check
         self.defer_nan_check = True
         try:
-            predicted_locs, predicted_scores = self(batch["img"])
+            predicted_locs, predicted_scores = self(image)
         finally:
             self.defer_nan_check = prev
         priors = self._priors_on(predicted_locs.device)

@@ -155,3 +155,33 @@ def test_lssd3d_predict_step_and_detect_api():
     wb, wl, ws = O.detect_from_decoded(*[t.cpu() for t in _ops().decode_softmax(locs, cls, m.priors_cxcycz)],
                                        _ops().f32(0.3), 0.5, 40)
     assert torch.equal(labels[0].cpu(), wl[0]) and torch.equal(scores[0].cpu(), ws[0])
+
+
+def test_predict_step_graph_equals_eager_and_streams():
+    from mslesions3d_b200.ssd3d import LSSD3D
+    from mslesions3d_b200 import synthetic
+    sd = O.random_state_dict(2, seed=5)
+    m = LSSD3D(n_classes=2, input_channels=2, input_size=(48, 48, 48), min_score=0.35, top_k=30)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    batches = [torch.from_numpy(synthetic.make_batch(2, 2, (48, 48, 48), first_idx=10 * k)) for k in range(5)]
+    with torch.no_grad():
+        m.use_cuda_graph = False
+        eager = [m.predict_step({"img": b.cuda()}, 0) for b in batches]
+        m.use_cuda_graph = True
+        graphed = [m.predict_step({"img": b.pin_memory()}, 0) for b in batches]      # host input, replayed graph
+        streamed = list(m.predict_batches({"img": b.pin_memory()} for b in batches))  # pipelined copies
+    assert len(streamed) == len(batches)
+    for e, g, s in zip(eager, graphed, streamed):
+        for k in range(3):
+            for i in range(2):
+                assert torch.equal(e[k][i], g[k][i]) and torch.equal(e[k][i], s[k][i])
+    # a new state_dict invalidates the captured plan
+    sd2 = O.random_state_dict(2, seed=6)
+    m.load_state_dict(sd2)
+    with torch.no_grad():
+        again = m.predict_step({"img": batches[0].cuda()}, 0)
+        m.use_cuda_graph = False
+        again_eager = m.predict_step({"img": batches[0].cuda()}, 0)
+    assert all(torch.equal(a, b) for a, b in zip(again[2], again_eager[2]))
+    assert not all(torch.equal(a, b) if a.shape == b.shape else False for a, b in zip(again[2], eager[0][2]))
