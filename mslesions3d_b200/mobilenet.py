@@ -75,14 +75,14 @@ class ConvBN(nn.Sequential):
             self._packed_key = key
         return self._packed
 
-    def forward(self, x):
+    def forward(self, x, out=None):
         _require_eval(self)
         conv = self[0]
         sd, sh, sw = _stride3(conv.stride)
         if conv.out_channels != 32 or (sh, sw) != (2, 2) or sd not in (1, 2):
             raise NotImplementedError("stem kernel is built for Cout=32 and stride (1|2, 2, 2), as ssd3d.py:60-61 uses it")
         w, scale, shift = self._pack()
-        return ops.stem_conv_bn_relu(x, w, scale, shift, sd)
+        return ops.stem_conv_bn_relu(x, w, scale, shift, sd, out=out)
 
 
 def conv_bn(inp, oup, stride):

@@ -60,7 +60,7 @@ def _alloc_ndhwc(n, c, d, h, w, device) -> torch.Tensor:
 
 
 def stem_conv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
-                      stride_d: int, force_simt: bool = False) -> torch.Tensor:
+                      stride_d: int, force_simt: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x (N,Cin,D,H,W) contiguous fp32|bf16 -> (N,32,Do,Ho,Wo) channels-last bf16.  mobilenet.py:28-30.
     tcgen05 implicit GEMM when TMA can address the rows, CUDA-core kernel otherwise (or when forced)."""
     _need_cuda(x, w_packed, scale, shift)
@@ -70,7 +70,8 @@ def stem_conv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tens
         x = x.float()
     x = x.contiguous()
     n, cin, d, h, w = x.shape
-    y = _alloc_ndhwc(n, 32, conv_out(d, stride_d), conv_out(h, 2), conv_out(w, 2), x.device)
+    y = out if out is not None else _alloc_ndhwc(n, 32, conv_out(d, stride_d), conv_out(h, 2), conv_out(w, 2),
+                                                 x.device)
     lib = _lib.load()
     fn = lib.ssd3d_stem_conv_bn_relu_simt if force_simt else lib.ssd3d_stem_conv_bn_relu
     rc = fn(x.data_ptr(), int(x.dtype == BF16), w_packed.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(),

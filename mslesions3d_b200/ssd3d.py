@@ -122,13 +122,15 @@ class MobileNetBase(nn.Module):
                     f.nan_flag = self._nan_flag
         return self._nan_flag
 
-    def forward(self, image, check_nan: bool = True):
-        flag = self.nan_flag(image.device)
+    def forward(self, image, check_nan: bool = True, stem_out=None):
+        """``stem_out``: the already-computed output of features[0] (the captured inference plan runs the
+        stem eagerly on the caller's tensor and replays the rest from a static buffer)."""
+        flag = self.nan_flag(image.device if stem_out is None else stem_out.device)
         out = image
         wanted = list(self.aspect_ratios.keys())
         out_features = {}
         for i, feat in enumerate(self.features):
-            out = feat(out)
+            out = stem_out if (i == 0 and stem_out is not None) else feat(out)
             if i in wanted:
                 out_features[i] = out
         if check_nan and int(flag.item()) & _lib.NAN_BACKBONE:
@@ -236,10 +238,12 @@ class _InferencePlan:
         self.out = None
         self.graph = None
         self.ready = torch.cuda.Event()      # input buffer may be overwritten / outputs were consumed
+        self.stem = model.base.features[0]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             self.inp.zero_()
+            self.stem_out = self.stem(self.inp)          # static buffer the captured graph reads
             for _ in range(2):                # warm-up: lazy module loading, function attributes, packing
                 self._run(model)
         torch.cuda.current_stream().wait_stream(side)
@@ -248,14 +252,23 @@ class _InferencePlan:
         before = ops.LAUNCHES[0]
         with torch.no_grad(), torch.cuda.graph(graph):
             self._run(model)
-        self.n_kernels = ops.LAUNCHES[0] - before      # library kernels inside one replay
+        self.n_kernels = ops.LAUNCHES[0] - before + 1  # library kernels per step (graph + the eager stem)
         self.graph = graph
+
+    def run_stem(self, image: torch.Tensor):
+        """The stem runs outside the graph so that a device-resident batch is consumed in place (no staging
+        copy of the largest tensor of the step); a host batch goes through the static input buffer."""
+        if image.is_cuda:
+            self.stem(image, out=self.stem_out)
+        else:
+            self.inp.copy_(image, non_blocking=True)
+            self.stem(self.inp, out=self.stem_out)
 
     def _run(self, model: "LSSD3D"):
         dev = self.inp.device
         flag = model.base.nan_flag(dev)
         flag.zero_()
-        feats = model.base(self.inp, check_nan=False)
+        feats = model.base(None, check_nan=False, stem_out=self.stem_out)
         locs, scores = model.pred_convs(feats, flag)
         ms, mo, k = self.args
         self.out = ops.detect_objects_padded(locs, scores, model._priors_on(dev), ms, mo, k,
@@ -264,8 +277,9 @@ class _InferencePlan:
         self.locs, self.scores = locs, scores
 
     def launch(self, image: torch.Tensor):
-        """Copy the batch in (H2D or D2D, asynchronous) and replay the graph on the current stream."""
-        self.inp.copy_(image, non_blocking=True)
+        """Stem on the batch (after an asynchronous H2D copy if it lives on the host), then replay the
+        captured rest of the step on the current stream."""
+        self.run_stem(image)
         self.graph.replay()
         ops.LAUNCHES[0] += self.n_kernels
         self.host_meta.copy_(self.meta, non_blocking=True)
@@ -543,6 +557,7 @@ class LSSD3D(_LightningBase):
     def _finish(self, pending, compute):
         plan, copied = pending
         compute.wait_event(copied)
+        plan.stem(plan.inp, out=plan.stem_out)
         plan.graph.replay()
         ops.LAUNCHES[0] += plan.n_kernels
         plan.host_meta.copy_(plan.meta, non_blocking=True)
