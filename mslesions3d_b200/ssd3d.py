@@ -237,7 +237,8 @@ class _InferencePlan:
         self.n = n
         self.out = None
         self.graph = None
-        self.ready = torch.cuda.Event()      # input buffer may be overwritten / outputs were consumed
+        self.done = torch.cuda.Event()       # graph + metadata read-back of the latest launch finished
+        self.cloned = torch.cuda.Event()     # results of the latest launch were copied out of the static buffers
         self.stem = model.base.features[0]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
@@ -276,18 +277,35 @@ class _InferencePlan:
         self.meta[self.n + 1:].copy_(flag)
         self.locs, self.scores = locs, scores
 
-    def launch(self, image: torch.Tensor):
-        """Stem on the batch (after an asynchronous H2D copy if it lives on the host), then replay the
-        captured rest of the step on the current stream."""
-        self.run_stem(image)
+    def launch(self, image: torch.Tensor, copy_stream=None):
+        """Queue one step on the current stream: stem on the batch (a host batch is first copied in, on
+        ``copy_stream`` if given, so that the copy overlaps the previous step), replay of the captured rest,
+        asynchronous read-back of the 4*(N+2) metadata bytes."""
+        compute = torch.cuda.current_stream()
+        compute.wait_event(self.cloned)          # static outputs of the previous use of this plan were consumed
+        if image.is_cuda:
+            self.stem(image, out=self.stem_out)
+        else:
+            if copy_stream is None:
+                self.inp.copy_(image, non_blocking=True)
+            else:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(self.done)    # the previous stem that read this buffer has run
+                    self.inp.copy_(image, non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record(copy_stream)
+                compute.wait_event(copied)
+            self.stem(self.inp, out=self.stem_out)
         self.graph.replay()
         ops.LAUNCHES[0] += self.n_kernels
         self.host_meta.copy_(self.meta, non_blocking=True)
+        self.done.record(compute)
 
-    def results(self, model: "LSSD3D"):
-        """Wait for the replay, check the flags, return fresh per-image tensors (the static buffers are
-        reused by the next replay)."""
-        torch.cuda.current_stream().synchronize()
+    def results(self, model: "LSSD3D", post_stream=None, to_host: bool = False):
+        """Wait for this plan's latest launch (not for later work on the stream), check the flags, and hand
+        out fresh per-image tensors: the static buffers are copied on ``post_stream`` (device clones, or
+        pinned-host copies when ``to_host``) so that the next steps already queued are not delayed."""
+        self.done.synchronize()
         meta = self.host_meta.tolist()
         if meta[-1]:
             model._raise_on_nan_bits(meta[-1])
@@ -295,7 +313,18 @@ class _InferencePlan:
             raise RuntimeError("detect_objects: more than %d candidates above min_score for one (image, class)"
                                % _lib.SORT_MAX)
         counts = meta[:self.n]
-        boxes, labels, scores = self.out.boxes.clone(), self.out.labels.clone(), self.out.scores.clone()
+        current = torch.cuda.current_stream()
+        stream = post_stream if post_stream is not None else current
+        with torch.cuda.stream(stream):
+            if to_host:
+                boxes = self.out.boxes.to("cpu", non_blocking=False)
+                labels = self.out.labels.to("cpu", non_blocking=False)
+                scores = self.out.scores.to("cpu", non_blocking=False)
+            else:
+                boxes, labels, scores = self.out.boxes.clone(), self.out.labels.clone(), self.out.scores.clone()
+            self.cloned.record(stream)
+        if not to_host and stream is not current:
+            current.wait_event(self.cloned)      # later work on the caller's stream sees complete tensors
         return ([boxes[i, :k] for i, k in enumerate(counts)], [labels[i, :k] for i, k in enumerate(counts)],
                 [scores[i, :k] for i, k in enumerate(counts)])
 
@@ -513,8 +542,9 @@ class LSSD3D(_LightningBase):
         return plan
 
     def predict_step(self, batch, batch_idx: int = 0, dataloader_idx: int = None):
-        """forward + detect_objects (ssd3d.py:692-702): one CUDA-graph replay and a single host sync for the
-        whole batch.  ``batch["img"]`` may live on the host (pinned memory makes the copy asynchronous)."""
+        """forward + detect_objects (ssd3d.py:692-702): eager stem + one CUDA-graph replay and a single host
+        sync for the whole batch.  ``batch["img"]`` may live on the host (pinned memory makes the copy
+        asynchronous)."""
         image = batch["img"]
         if not self.use_cuda_graph:
             return self._predict_step_eager(image)
@@ -524,46 +554,32 @@ class LSSD3D(_LightningBase):
         plan.launch(image if image.dtype == plan.inp.dtype else image.to(plan.inp.dtype))
         return plan.results(self)
 
-    def predict_batches(self, batches):
+    def predict_batches(self, batches, to_host: bool = False):
         """Generator over an iterable of batches (dicts with "img", as a DataLoader yields them) -> per-batch
         (boxes, labels, scores).  What ``Trainer.predict(model, loader)`` does in the reference
-        (predict.py:262-263), software-pipelined: the host->device copy of batch i+1 runs on a copy stream
-        while the graph of batch i executes, using two input slots."""
+        (predict.py:262-263), software-pipelined over two plan slots: batch i+1 is copied (copy stream) and
+        launched before the host waits for batch i, and batch i's results leave the static buffers on a
+        third stream.  ``to_host=True`` returns CPU tensors (one device->host copy per output)."""
         if self.device.type != "cuda":
             raise RuntimeError("LSSD3D.predict_batches needs the model on a CUDA device; there is no CPU path")
-        compute = torch.cuda.current_stream()
-        copy_stream = getattr(self, "_copy_stream", None)
-        if copy_stream is None:
-            copy_stream = self._copy_stream = torch.cuda.Stream(device=self.device)
-        pending = None          # (plan, copied-event)
+        if self.__dict__.get("_copy_stream") is None:
+            self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
+            self.__dict__["_post_stream"] = torch.cuda.Stream(device=self.device)
+        copy_stream, post_stream = self.__dict__["_copy_stream"], self.__dict__["_post_stream"]
+        prev = None
         slot = 0
         for batch in batches:
             image = batch["img"]
             plan = self._plan_for(image, slot)
             if image.dtype != plan.inp.dtype:
                 image = image.to(plan.inp.dtype)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(plan.ready)           # previous replay that read this slot is done
-                plan.inp.copy_(image, non_blocking=True)
-                copied = torch.cuda.Event()
-                copied.record(copy_stream)
-            if pending is not None:
-                yield self._finish(pending, compute)
-            pending = (plan, copied)
+            plan.launch(image, copy_stream)
+            if prev is not None:
+                yield prev.results(self, post_stream, to_host)
+            prev = plan
             slot ^= 1
-        if pending is not None:
-            yield self._finish(pending, compute)
-
-    def _finish(self, pending, compute):
-        plan, copied = pending
-        compute.wait_event(copied)
-        plan.stem(plan.inp, out=plan.stem_out)
-        plan.graph.replay()
-        ops.LAUNCHES[0] += plan.n_kernels
-        plan.host_meta.copy_(plan.meta, non_blocking=True)
-        res = plan.results(self)
-        plan.ready.record(compute)
-        return res
+        if prev is not None:
+            yield prev.results(self, post_stream, to_host)
 
     def _predict_step_eager(self, image):
         prev = self.defer_nan_check

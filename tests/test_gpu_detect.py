@@ -171,11 +171,15 @@ def test_predict_step_graph_equals_eager_and_streams():
         m.use_cuda_graph = True
         graphed = [m.predict_step({"img": b.pin_memory()}, 0) for b in batches]      # host input, replayed graph
         streamed = list(m.predict_batches({"img": b.pin_memory()} for b in batches))  # pipelined copies
-    assert len(streamed) == len(batches)
-    for e, g, s in zip(eager, graphed, streamed):
+        resident = list(m.predict_batches({"img": b.cuda()} for b in batches))        # device-resident inputs
+        hosted = list(m.predict_batches(({"img": b.pin_memory()} for b in batches), to_host=True))
+    assert len(streamed) == len(batches) == len(hosted) == len(resident)
+    assert not hosted[0][0][0].is_cuda and streamed[0][0][0].is_cuda
+    for e, g, s, r, h in zip(eager, graphed, streamed, resident, hosted):
         for k in range(3):
             for i in range(2):
                 assert torch.equal(e[k][i], g[k][i]) and torch.equal(e[k][i], s[k][i])
+                assert torch.equal(e[k][i], r[k][i]) and torch.equal(e[k][i].cpu(), h[k][i])
     # a new state_dict invalidates the captured plan
     sd2 = O.random_state_dict(2, seed=6)
     m.load_state_dict(sd2)
