@@ -78,10 +78,16 @@ int ssd3d_pwconv_bn_relu(const void* x, const void* w, const float* scale, const
  *          [bpl*6, bpl*(6+n_classes)) = class conv out channels, remaining rows zero; NPAD % 16 == 0
  *   bias   (NPAD) fp32
  *   locs   (N, P, 6) fp32, scores (N, P, n_classes) fp32; this layer writes priors
- *          [prior_offset, prior_offset + D*H*W*bpl) of every image, prior = ((d*H+h)*W+w)*bpl + b */
+ *          [prior_offset, prior_offset + D*H*W*bpl) of every image, prior = ((d*H+h)*W+w)*bpl + b
+ *   workspace: ssd3d_head_workspace_bytes(...) bytes (0 for large maps; small maps split K across CTAs and
+ *          reduce partial sums in a fixed order)
+ *   algo   0 = auto; 1 = per-tap TMA kernel (27 shifted 5-D boxes per chunk); 2 = halo-tile kernel (each
+ *          activation voxel loaded once per 64-channel chunk, taps = row-shifted smem descriptors; needs
+ *          C % 64 == 0 and NPAD <= 64) */
+int64_t ssd3d_head_workspace_bytes(int N, int C, int D, int H, int W, int NPAD);
 int ssd3d_head_conv(const void* x, const void* w, const float* bias, float* locs, float* scores, int N, int C,
                     int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset,
-                    int* nan_flag, void* stream);
+                    int* nan_flag, void* workspace, int64_t workspace_bytes, int algo, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Box geometry (utils.py:42-149).  All fp32, every arithmetic step separately rounded (no FMA).

@@ -30,8 +30,9 @@ SIGNATURES = {
     "ssd3d_stem_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ssd3d_dwconv3d_bn_relu": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "ssd3d_pwconv_bn_relu": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, P, P]),
+    "ssd3d_head_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "ssd3d_head_conv": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
-                                c_int64, P, P]),
+                                c_int64, P, P, c_int64, c_int, P]),
     "ssd3d_box_transform": (c_int, [c_int, P, P, P, c_int64, P]),
     "ssd3d_iou3d_pairwise": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
     "ssd3d_detect_workspace_bytes": (c_int64, [c_int, c_int64, c_int, c_int]),

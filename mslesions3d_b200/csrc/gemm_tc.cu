@@ -303,13 +303,24 @@ extern "C" int ssd3d_pwconv_bn_relu(const void* x, const void* w, const float* s
   return launch_gemm<32, false>(tmA, tmB, p, grid, st);
 }
 
+// conv_head_tc.cu: halo-tile kernel (one activation load per 64-channel chunk)
+int ssd3d_head_conv_halo(const void* x, const void* w, const float* bias, float* locs, float* scores, int N, int C,
+                         int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset,
+                         int* nan_flag, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+
 extern "C" int ssd3d_head_conv(const void* x, const void* w, const float* bias, float* locs, float* scores, int N,
                                int C, int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P,
-                               int64_t prior_offset, int* nan_flag, void* stream) {
+                               int64_t prior_offset, int* nan_flag, void* workspace, int64_t workspace_bytes,
+                               int algo, void* stream) {
   if (!x || !w || !bias || !locs || !scores || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
   if (C <= 0 || (C % 32) || bpl <= 0 || n_classes <= 0) return SSD3D_ERR_ARG;
   if (NPAD % 16 || NPAD > 256 || NPAD < bpl * (6 + n_classes)) return SSD3D_ERR_ARG;
   if (prior_offset < 0 || prior_offset + (int64_t)D * H * W * bpl > P) return SSD3D_ERR_ARG;
+  if (algo != 1) {
+    const int rc = ssd3d_head_conv_halo(x, w, bias, locs, scores, N, C, D, H, W, bpl, n_classes, NPAD, P, prior_offset,
+                                        nan_flag, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    if (rc != SSD3D_ERR_UNSUPPORTED || algo == 2) return rc;
+  }
   const int BK = (C % 64 == 0) ? 64 : 32;
   GemmParams p{};
   p.num_kb = 27 * (C / BK);

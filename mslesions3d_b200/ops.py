@@ -111,16 +111,22 @@ def pwconv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor,
 
 
 def head_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, locs: torch.Tensor, scores: torch.Tensor,
-              bpl: int, n_classes: int, prior_offset: int, nan_flag: Optional[torch.Tensor] = None) -> None:
-    """Fused loc+class 3x3x3 head of one feature map, written into locs (N,P,6) / scores (N,P,n_classes)."""
+              bpl: int, n_classes: int, prior_offset: int, nan_flag: Optional[torch.Tensor] = None,
+              algo: int = 0) -> None:
+    """Fused loc+class 3x3x3 head of one feature map, written into locs (N,P,6) / scores (N,P,n_classes).
+    algo: 0 auto, 1 per-tap TMA kernel, 2 halo-tile kernel."""
     _need_cuda(x, w_packed, bias, locs, scores, nan_flag)
     x = to_channels_last_bf16(x)
     n, c, d, h, w = x.shape
-    rc = _lib.load().ssd3d_head_conv(x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), locs.data_ptr(),
-                                     scores.data_ptr(), n, c, d, h, w, bpl, n_classes, w_packed.shape[0],
-                                     locs.shape[1], prior_offset, _ptr(nan_flag), _stream())
+    lib = _lib.load()
+    npad = w_packed.shape[0]
+    need = lib.ssd3d_head_workspace_bytes(n, c, d, h, w, npad) if algo != 1 else 0
+    ws = torch.empty((need,), dtype=torch.uint8, device=x.device) if need else None
+    rc = lib.ssd3d_head_conv(x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), locs.data_ptr(), scores.data_ptr(),
+                             n, c, d, h, w, bpl, n_classes, npad, locs.shape[1], prior_offset, _ptr(nan_flag),
+                             _ptr(ws), need, algo, _stream())
     _lib.check(rc, "ssd3d_head_conv")
-    LAUNCHES[0] += 1
+    LAUNCHES[0] += 2 if need else 1
 
 
 # ----------------------------------------------------------------------------------------------

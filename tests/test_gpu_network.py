@@ -149,9 +149,15 @@ def test_pointwise_nan_flag():
     (128, (5, 6, 10), 1, 3),       # NPAD = 32
     (32, (16, 12, 20), 1, 2),      # layer-0 head: BK = 32
     (512, (4, 4, 4), 8, 2),
+    (128, (16, 16, 16), 2, 2),     # several 4x8x8 tiles, J = 3 row blocks, no K split
+    (256, (8, 8, 8), 8, 2),        # K split across CTAs + ordered reduction
+    (64, (9, 7, 20), 1, 2),        # one chunk, ragged tiles
 ])
-def test_head_conv_tcgen05(c, size, batch, n_classes):
+@pytest.mark.parametrize("algo", [1, 2])
+def test_head_conv_tcgen05(c, size, batch, n_classes, algo):
     ops = _ops()
+    if algo == 2 and c % 64:
+        pytest.skip("halo-tile kernel needs C % 64 == 0 (the per-tap kernel covers C = 32)")
     g = torch.Generator().manual_seed(c + size[2] + n_classes)
     bpl = 2
     x = bf16r(torch.randn((batch, c) + size, generator=g))
@@ -168,7 +174,7 @@ def test_head_conv_tcgen05(c, size, batch, n_classes):
     scores = torch.full((batch, P, n_classes), -77.0, device="cuda")
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")
     wp, bp = ops.pack_head_weight(lw.cuda(), lb.cuda(), cw.cuda(), cb.cuda())
-    ops.head_conv(to_cl(x), wp, bp, locs, scores, bpl, n_classes, pad_front, flag)
+    ops.head_conv(to_cl(x), wp, bp, locs, scores, bpl, n_classes, pad_front, flag, algo=algo)
     locs, scores = locs.cpu(), scores.cpu()
     assert bool((locs[:, :pad_front] == -77).all()) and bool((locs[:, pad_front + here:] == -77).all())
     assert bool((scores[:, :pad_front] == -77).all()) and bool((scores[:, pad_front + here:] == -77).all())
