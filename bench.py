@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true",
+                    help="launch every kernel individually (no CUDA graph): for ncu launch lists, not for numbers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -245,6 +247,12 @@ def main():
     def run_resident(steps):
         """`steps` device-resident batches through LSSD3D.predict_batches (results stay on the device)."""
         batches = ({"img": dev_bf16[i % N_ROTATE]} for i in range(steps))
+        if args.eager:
+            model.use_cuda_graph = False
+            with torch.no_grad():
+                for b in batches:
+                    model.predict_step(b, 0)
+            return
         with torch.no_grad():
             for _ in model.predict_batches(batches):
                 pass

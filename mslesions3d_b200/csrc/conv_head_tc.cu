@@ -203,29 +203,41 @@ __global__ void __launch_bounds__(224, 1) head2_kernel(const __grid_constant__ C
   }
 }
 
-// out[voxel][col] = bias[col] + sum over splits (ascending) of partial[split][tile][m][col]
+// out[voxel][col] = bias[col] + sum over splits (ascending) of partial[split][tile][m][col].
+// One thread per (voxel, 4 columns): the S float4 loads are independent, the additions run in split order.
 __global__ void __launch_bounds__(256) head2_reduce_kernel(const Head2Params p) {
-  const long long total = (long long)p.N * p.D * p.H * p.W;
-  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= total) return;
-  long long r = v;
+  const int groups = p.NPAD >> 2;
+  const long long total = (long long)p.N * p.D * p.H * p.W * groups;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c0 = (int)(gid % groups) * 4;
+  long long r = gid / groups;
   const int w = (int)(r % p.W); r /= p.W;
   const int h = (int)(r % p.H); r /= p.H;
   const int d = (int)(r % p.D);
   const int n = (int)(r / p.D);
+  const int ncol = p.n_loc + p.n_cls;
+  if (c0 >= ncol) return;
   const int tile = ((n * p.tiles_d + d / p.TD) * p.tiles_h + h / p.TH) * p.tiles_w + w / p.TW;
   const int f = ((d % p.TD + 1) * p.HH + (h % p.TH + 1)) * p.HW + (w % p.TW + 1);
   const int m = f - p.f0;
+  const long long split_stride = (long long)p.tiles_total * (p.J * 128) * p.NPAD;
+  const float* src = p.partial + ((long long)tile * (p.J * 128) + m) * p.NPAD + c0;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < p.S; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + s * split_stride));
+    acc[0] = __fadd_rn(acc[0], v.x); acc[1] = __fadd_rn(acc[1], v.y);
+    acc[2] = __fadd_rn(acc[2], v.z); acc[3] = __fadd_rn(acc[3], v.w);
+  }
   const long long prior = p.prior_off + (((long long)d * p.H + h) * p.W + w) * p.bpl;
   float* lp = p.locs + ((long long)n * p.P + prior) * 6;
   float* sp = p.scores + ((long long)n * p.P + prior) * p.n_classes;
   bool bad_l = false, bad_s = false;
-  const int ncol = p.n_loc + p.n_cls;
-  for (int c = 0; c < ncol; ++c) {
-    float acc = 0.f;
-    for (int s = 0; s < p.S; ++s)
-      acc = __fadd_rn(acc, p.partial[(((long long)s * p.tiles_total + tile) * (p.J * 128) + m) * p.NPAD + c]);
-    const float val = __fadd_rn(acc, __ldg(p.bias + c));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int c = c0 + q;
+    if (c >= ncol) break;
+    const float val = __fadd_rn(acc[q], __ldg(p.bias + c));
     if (c < p.n_loc) { lp[c] = val; bad_l |= (val != val); }
     else { sp[c - p.n_loc] = val; bad_s |= (val != val); }
   }
@@ -340,7 +352,7 @@ int ssd3d_head_conv_halo(const void* x, const void* w, const float* bias, float*
   head2_kernel<<<grid, 224, smem, st>>>(tmX, tmW, p);
   SSD3D_CHECK_LAUNCH();
   if (p.S > 1) {
-    const long long total = (long long)N * D * H * W;
+    const long long total = (long long)N * D * H * W * (NPAD / 4);
     head2_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
     SSD3D_CHECK_LAUNCH();
   }

@@ -128,8 +128,24 @@ __global__ void __launch_bounds__(1024) sort_segments_kernel(unsigned long long*
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 3: suppression bit matrix.  mask[seg][i][w] bit b  <=>  j = 64 w + b > i  and  IoU(i, j) > thr
+// stage 3: suppression bit matrix over the score-sorted candidates.
+//   off-diagonal word (w > i/64): bit b  <=>  IoU(i, 64 w + b) > thr              (all of them later boxes)
+//   diagonal word    (w = i/64): bit b  <=>  64 w + b != i and IoU(i, 64 w + b) > thr   (both directions:
+//                                 IoU is exactly symmetric, so this word also lists the EARLIER neighbours)
+// Words w < i/64 are never written nor read.
 // ------------------------------------------------------------------------------------------------
+// fl(inter / uni) > thr without the IEEE divide in the common case: a multiply pre-test with a 2^-18
+// guard band (>> the 2^-23 rounding of the two products) decides all but near-threshold pairs; those,
+// and every degenerate union, take the exactly rounded division the reference performs (utils.py:149).
+__device__ __forceinline__ bool iou_exceeds(float inter, float uni, float thr) {
+  if (thr > 0.0f && uni > 1e-30f && uni < 1e30f) {
+    const float t = thr * uni;
+    if (inter > t * 1.000004f) return true;
+    if (inter < t * 0.999996f) return false;
+  }
+  return __fdiv_rn(inter, uni) > thr;
+}
+
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sboxes, const int* __restrict__ nkeep,
                                                       int n_fixed, long long seg_stride_boxes, int words,
                                                       long long seg_stride_mask, float thr,
@@ -157,53 +173,69 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   const int jn = min(64, n - cb * 64);
   unsigned long long bits = 0ull;
   for (int b = 0; b < jn; ++b) {
-    const int j = cb * 64 + b;
     Box6 o;
 #pragma unroll
     for (int k = 0; k < 6; ++k) o.v[k] = cbox[b][k];
-    if (j > i && box_iou(a, va, o, cvol[b]) > thr) bits |= (1ull << b);
+    const float inter = box_intersection(a, o);
+    const float uni = __fsub_rn(__fadd_rn(va, cvol[b]), inter);
+    if (iou_exceeds(inter, uni, thr)) bits |= (1ull << b);
   }
+  if (cb == rb) bits &= ~(1ull << t);       // a box does not suppress itself (ssd3d.py:425-426)
   mask[(long long)seg * seg_stride_mask + (long long)i * words + cb] = bits;
 }
 
 // Greedy scan of one segment's bit matrix M (rows `stride` words apart; shared or global memory).
-// `removed` is scratch of ceil(n/64) words, `keptw` receives the keep bits.  Only words w >= i/64 of row
-// i exist (nms_mask_kernel skips the lower triangle) and only those are read.  All threads call it.
+// `removed` is scratch of ceil(n/64) words, `keptw` receives the keep bits.  All threads call it.
 //
-// The 64 boxes of a chunk are resolved by ONE thread on register-resident diagonal words (a fully
-// unrolled chain of bit tests, ~5 dependent ALU ops per box); the rows of the boxes it keeps are then
-// OR-ed into the later words by the whole block.
+// Chunk k (64 boxes) is resolved by warp 0 in rounds instead of a 64-step serial chain: lane l owns boxes
+// l and l+32 with the masks of their EARLIER neighbours inside the chunk.  A box with a kept earlier
+// neighbour is removed; a box none of whose earlier neighbours is kept or still undecided is kept.  The
+// lowest undecided box is always decidable, so the loop ends, normally after a handful of rounds, with
+// exactly the greedy result of ssd3d.py:414-426.  The rows of the kept boxes are then OR-ed into the later
+// words, one warp per word, with redux.or across the 32 lanes.
 __device__ __forceinline__ void nms_scan_core(const unsigned long long* M, int n, int stride,
                                               unsigned long long* removed, unsigned long long* keptw) {
   const int words = (n + 63) >> 6;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0ull;
   __syncthreads();
   for (int k = 0; k < words; ++k) {
     const int rows = min(64, n - k * 64);
-    if (threadIdx.x == 0) {
-      unsigned long long d[64];
-#pragma unroll
-      for (int b = 0; b < 64; ++b) d[b] = (b < rows) ? M[(long long)(k * 64 + b) * stride + k] : 0ull;
-      unsigned long long cur = removed[k], kept = 0ull;
-      if (rows < 64) cur |= (~0ull) << rows;   // rows past the end are never kept
-#pragma unroll
-      for (int b = 0; b < 64; ++b) {
-        const bool fr = ((cur >> b) & 1ull) == 0ull;
-        kept |= fr ? (1ull << b) : 0ull;
-        cur |= fr ? d[b] : 0ull;
+    if (warp == 0) {
+      const unsigned long long r0 = (lane < rows) ? M[(long long)(k * 64 + lane) * stride + k] : 0ull;
+      const unsigned long long r1 = (lane + 32 < rows) ? M[(long long)(k * 64 + lane + 32) * stride + k] : 0ull;
+      const unsigned long long e0 = r0 & ((1ull << lane) - 1ull);
+      const unsigned long long e1 = r1 & ((1ull << (lane + 32)) - 1ull);
+      unsigned long long rem = removed[k];
+      if (rows < 64) rem |= (~0ull) << rows;            // rows past the end are never kept
+      unsigned long long und = ~rem, kept = 0ull;
+      while (und != 0ull) {
+        const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
+        const bool x0 = u0 && (e0 & kept) != 0ull, x1 = u1 && (e1 & kept) != 0ull;
+        const bool k0 = u0 && !x0 && (e0 & und) == 0ull, k1 = u1 && !x1 && (e1 & und) == 0ull;
+        const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+        const unsigned long long nx = (unsigned long long)__ballot_sync(0xffffffffu, x0) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, x1) << 32);
+        kept |= nk;
+        und &= ~(nk | nx);
       }
-      keptw[k] = kept;
+      if (lane == 0) keptw[k] = kept;
     }
     __syncthreads();
     const unsigned long long kept = keptw[k];
     if (kept != 0ull) {
-      for (int w = k + 1 + (int)threadIdx.x; w < words; w += blockDim.x) {
-        unsigned long long acc = removed[w];
-        const unsigned long long* col = M + (long long)(k * 64) * stride + w;
-#pragma unroll 16
-        for (int b = 0; b < 64; ++b)
-          if ((kept >> b) & 1ull) acc |= col[(long long)b * stride];
-        removed[w] = acc;
+      for (int w = k + 1 + warp; w < words; w += nwarps) {
+        unsigned int lo = 0u, hi = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int b = h * 32 + lane;
+          unsigned long long v = 0ull;
+          if ((kept >> b) & 1ull) v = M[(long long)(k * 64 + b) * stride + w];
+          lo |= __reduce_or_sync(0xffffffffu, (unsigned int)v);
+          hi |= __reduce_or_sync(0xffffffffu, (unsigned int)(v >> 32));
+        }
+        if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
       }
     }
     __syncthreads();

@@ -316,7 +316,11 @@ extern "C" int ssd3d_head_conv(const void* x, const void* w, const float* bias, 
   if (C <= 0 || (C % 32) || bpl <= 0 || n_classes <= 0) return SSD3D_ERR_ARG;
   if (NPAD % 16 || NPAD > 256 || NPAD < bpl * (6 + n_classes)) return SSD3D_ERR_ARG;
   if (prior_offset < 0 || prior_offset + (int64_t)D * H * W * bpl > P) return SSD3D_ERR_ARG;
-  if (algo != 1) {
+  // auto: the halo-tile kernel wins where it can split K across CTAs (small maps: 8^3 23.6 vs 49 us,
+  // 4^3 23.6 vs 88 us at batch 8); on large maps both are bound by the UMMA issue rate (~128 cycles per
+  // M=128 instruction whatever N) and the per-tap kernel issues fewer of them (no halo rows): 30.7 vs 43.9 us
+  const bool small_map = (long long)N * D * H * W < 128ll * 128;
+  if (algo == 2 || (algo == 0 && small_map)) {
     const int rc = ssd3d_head_conv_halo(x, w, bias, locs, scores, N, C, D, H, W, bpl, n_classes, NPAD, P, prior_offset,
                                         nan_flag, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (rc != SSD3D_ERR_UNSUPPORTED || algo == 2) return rc;
