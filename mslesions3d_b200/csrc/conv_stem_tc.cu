@@ -46,46 +46,56 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
   return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// NaN-propagating ReLU in one instruction (max.NaN returns NaN if either input is NaN: torch.relu semantics)
+__device__ __forceinline__ float relu_nan1(float v) {
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// Persistent CTA: loops over tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  Per tile
+//   TMA halo box (double buffered, prefetched two tiles ahead)  ->  gather into the swizzled A tile (double
+//   buffered)  ->  4*KB UMMAs into one of two 32-column TMEM accumulators (asynchronous)  ->  epilogue of the
+//   PREVIOUS tile (TMEM -> scale/shift/ReLU -> 64-byte store) while this tile's UMMAs run.
+// Weights (B operand), scale and shift are loaded once per CTA; 3 CTAs are resident per SM.
 template <typename TIn, int CIN>
-__global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const StemParams p) {
+__global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const StemParams p) {
   constexpr int KREAL = 27 * CIN;
   constexpr int KPAD = (KREAL <= 64) ? 64 : 128;
   constexpr int KB = KPAD / 64;
   constexpr int NREG = KPAD / 2;          // packed bf16 pairs per A row
   constexpr int PADL = 16 / (int)sizeof(TIn);   // left halo rounded up to 16 bytes (1 column is needed)
+  constexpr int NG = 9 * CIN;             // (ci, kd, kh) groups of 3 consecutive taps
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  uint8_t* sA = smem;                                   // KB x (128 rows x 128 B)
-  uint8_t* sB = sA + KB * 16384;                        // KB x (32 rows x 128 B)
+  uint8_t* sA = smem;                                   // 2 x KB x (128 rows x 128 B)
+  uint8_t* sB = sA + 2 * KB * 16384;                    // KB x (32 rows x 128 B)
   uint8_t* ctl = sB + KB * 4096;                        // mbarriers + TMEM slot (128 B)
-  uint8_t* sX = ctl + 128;                              // input halo tile [CIN][TDI][THI][TWI] of TIn
   const int tile_elems = CIN * p.TDI * p.THI * p.TWI;
-  uint64_t* bar_in = reinterpret_cast<uint64_t*>(ctl);
-  uint64_t* bar_mma = bar_in + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_in + 2);
+  const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(TIn));
+  const uint32_t tile_pitch = (tile_bytes + 127u) & ~127u;
+  uint8_t* sX = ctl + 128;                              // 2 x input halo tile [CIN][TDI][THI][TWI] of TIn
+  uint64_t* bar_in = reinterpret_cast<uint64_t*>(ctl);  // [2]
+  uint64_t* bar_mma = bar_in + 2;                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_in + 4);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-
-  int t = blockIdx.x;
-  const int w0 = (t % p.tiles_w) * p.TW; t /= p.tiles_w;
-  const int h0 = (t % p.tiles_h) * p.TH; t /= p.tiles_h;
-  const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
-  const int n = t;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.N;
 
   // barrier init and TMA issue live in warp 1, so that warp 0 reaches the .sync.aligned TMEM
   // allocation fully converged (a lane still inside a divergent branch makes it an illegal instruction)
   if (tid == 32) {
     tma_prefetch_desc(&tmX);
-    mbar_init(bar_in, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(&bar_in[0], 1); mbar_init(&bar_in[1], 1);
+    mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
     fence_barrier_init();
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc(tmem_slot, 32);
+    tmem_alloc(tmem_slot, 64);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -93,11 +103,21 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (tid == 32) {
-    mbar_arrive_expect_tx(bar_in, (uint32_t)(tile_elems * sizeof(TIn)));
+  auto issue_tma = [&](int tile, int buf) {   // called by tid 32 only
+    int t = tile;
+    const int w0 = (t % p.tiles_w) * p.TW; t /= p.tiles_w;
+    const int h0 = (t % p.tiles_h) * p.TH; t /= p.tiles_h;
+    const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
+    mbar_arrive_expect_tx(&bar_in[buf], tile_bytes);
     // TMA needs the box start to be 16-byte aligned along the innermost dimension (a start at column
     // 2*w0 - 1 is an illegal instruction): fetch from 2*w0 - PADL, PADL = 16 bytes of elements
-    tma_load_4d(sX, &tmX, bar_in, 2 * w0 - PADL, 2 * h0 - 1, p.sd * d0 - 1, n * CIN);
+    tma_load_4d(sX + (size_t)buf * tile_pitch, &tmX, &bar_in[buf], 2 * w0 - PADL, 2 * h0 - 1, p.sd * d0 - 1, t * CIN);
+  };
+
+  const int first = blockIdx.x;
+  if (tid == 32) {
+    if (first < total_tiles) issue_tma(first, 0);
+    if (first + (int)gridDim.x < total_tiles) issue_tma(first + gridDim.x, 1);
   }
 
   // weights -> swizzled B operand while the TMA is in flight: 32 rows x (KPAD/8) 16-byte chunks
@@ -106,95 +126,143 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.wt + row * KPAD + ch * 8));
     *reinterpret_cast<uint4*>(sB + (ch >> 3) * 4096 + sw128_offset(row, ch & 7)) = v;
   }
+  float sc[32], sh[32];
+#pragma unroll
+  for (int c = 0; c < 32; c += 4) {
+    *reinterpret_cast<float4*>(&sc[c]) = __ldg(reinterpret_cast<const float4*>(p.scale + c));
+    *reinterpret_cast<float4*>(&sh[c]) = __ldg(reinterpret_cast<const float4*>(p.shift + c));
+  }
 
-  // this thread's output voxel inside the tile (w fastest)
+  // this thread's output voxel inside a tile (w fastest) and its offset inside the halo tile
   const int wl = tid % p.TW;
   const int hl = (tid / p.TW) % p.TH;
   const int dl = tid / (p.TW * p.TH);
+  const int vox_off = ((p.sd * dl) * p.THI + 2 * hl) * p.TWI + 2 * wl + PADL;
+  const int plane = p.TDI * p.THI * p.TWI;
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 
-  mbar_wait(bar_in, 0);
-
-  // ---- gather the 27*CIN taps of this voxel into one K-major row (bf16 pairs in registers) ----
-  uint32_t regs[NREG];
+  auto epilogue = [&](int tile, int buf) {
+    uint32_t v0[16], v1[16];
+    __syncwarp();
+    tmem_ld_32x32b_x16(taddr + (uint32_t)(buf * 32), v0);
+    tmem_ld_32x32b_x16(taddr + (uint32_t)(buf * 32 + 16), v1);
+    tmem_ld_wait();
+    int t = tile;
+    const int wo = (t % p.tiles_w) * p.TW + wl; t /= p.tiles_w;
+    const int ho = (t % p.tiles_h) * p.TH + hl; t /= p.tiles_h;
+    const int dz = (t % p.tiles_d) * p.TD + dl; t /= p.tiles_d;
+    if (wo < p.Wo && ho < p.Ho && dz < p.Do) {
+      uint4* dst = reinterpret_cast<uint4*>(p.y + ((((long long)t * p.Do + dz) * p.Ho + ho) * p.Wo + wo) * 32);
 #pragma unroll
-  for (int i = 0; i < NREG; ++i) regs[i] = 0u;
-  const TIn* xt = reinterpret_cast<const TIn*>(sX);
+      for (int q = 0; q < 4; ++q) {
+        uint32_t o[4];
 #pragma unroll
-  for (int ci = 0; ci < CIN; ++ci) {
-#pragma unroll
-    for (int kd = 0; kd < 3; ++kd) {
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int g = (ci * 3 + kd) * 3 + kh;
-        // taps kw = 0..2 sit at tile columns 2*wl + PADL - 1 .. 2*wl + PADL + 1
-        const TIn* src = xt + ((ci * p.TDI + (p.sd * dl + kd)) * p.THI + (2 * hl + kh)) * p.TWI + 2 * wl + PADL;
-        uint32_t e0, e1, e2;
-        if constexpr (sizeof(TIn) == 2) {
-          const uint32_t a = *reinterpret_cast<const uint32_t*>(src - 2);   // columns -2, -1
-          const uint32_t b = *reinterpret_cast<const uint32_t*>(src);       // columns  0, +1
-          e0 = a >> 16; e1 = b & 0xffffu; e2 = b >> 16;
-        } else {
-          const float a = reinterpret_cast<const float*>(src)[-1];
-          const float2 b = *reinterpret_cast<const float2*>(src);
-          e0 = bf16_bits(a); e1 = bf16_bits(b.x); e2 = bf16_bits(b.y);
+        for (int h = 0; h < 4; ++h) {
+          const int c = q * 8 + h * 2;
+          const float a0 = __uint_as_float(c < 16 ? v0[c & 15] : v1[c & 15]);
+          const float a1 = __uint_as_float(c + 1 < 16 ? v0[(c + 1) & 15] : v1[(c + 1) & 15]);
+          o[h] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(a0, sc[c]), sh[c])),
+                             relu_nan1(__fadd_rn(__fmul_rn(a1, sc[c + 1]), sh[c + 1])));
         }
+        dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  };
+
+  int it = 0;
+  int prev_tile = -1;
+  for (int tile = first; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const uint32_t par = (uint32_t)((it >> 1) & 1);
+    mbar_wait(&bar_in[buf], par);
+
+    // ---- gather the 27*CIN taps of this voxel into one K-major row (bf16 pairs in registers) ----
+    uint32_t regs[NREG];
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) regs[i] = 0u;
+    const TIn* xt = reinterpret_cast<const TIn*>(sX + (size_t)buf * tile_pitch) + vox_off;
+    if constexpr (sizeof(TIn) == 2) {
+      // taps kw = 0..2 of group g sit at columns -1, 0, +1: words a = (col -2, col -1), b = (col 0, col +1).
+      // Two groups give three packed registers with two byte permutes.
+      uint32_t wa[NG], wb[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int ci = g / 9, kd = (g / 3) % 3, kh = g % 3;
+        const TIn* src = xt + ci * plane + (kd * p.THI + kh) * p.TWI;
+        wa[g] = *reinterpret_cast<const uint32_t*>(src - 2);
+        wb[g] = *reinterpret_cast<const uint32_t*>(src);
+      }
+#pragma unroll
+      for (int g = 0; g + 1 < NG; g += 2) {
+        const int r = (3 * g) >> 1;                           // 3g is even
+        regs[r] = __byte_perm(wa[g], wb[g], 0x5432);          // (e0, e1) of group g
+        regs[r + 1] = __byte_perm(wb[g], wa[g + 1], 0x7632);  // (e2 of g, e0 of g+1)
+        regs[r + 2] = wb[g + 1];                              // (e1, e2) of group g+1
+      }
+      if constexpr (NG & 1) {
+        const int g = NG - 1, r = (3 * g) >> 1;
+        regs[r] = __byte_perm(wa[g], wb[g], 0x5432);
+        regs[r + 1] = wb[g] >> 16;
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int ci = g / 9, kd = (g / 3) % 3, kh = g % 3;
+        const float* src = reinterpret_cast<const float*>(xt) + ci * plane + (kd * p.THI + kh) * p.TWI;
+        const float a = src[-1];
+        const float2 b = *reinterpret_cast<const float2*>(src);
+        const uint32_t e0 = bf16_bits(a), e1 = bf16_bits(b.x), e2 = bf16_bits(b.y);
         const int k0 = g * 3;
         regs[(k0 + 0) >> 1] |= e0 << (16 * ((k0 + 0) & 1));
         regs[(k0 + 1) >> 1] |= e1 << (16 * ((k0 + 1) & 1));
         regs[(k0 + 2) >> 1] |= e2 << (16 * ((k0 + 2) & 1));
       }
     }
-  }
+    // the A buffer of this parity was last read by the UMMAs of tile it-2: their completion was observed
+    // in the epilogue of tile it-2 (bar_mma wait), which every thread has passed
+    uint8_t* a_dst = sA + (size_t)buf * KB * 16384;
 #pragma unroll
-  for (int j = 0; j < KPAD / 8; ++j) {
-    *reinterpret_cast<uint4*>(sA + (j >> 3) * 16384 + sw128_offset(tid, j & 7)) =
-        make_uint4(regs[4 * j], regs[4 * j + 1], regs[4 * j + 2], regs[4 * j + 3]);
-  }
-  fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-  __syncthreads();
-
-  if (tid == 32) {
-    tc_fence_after();
-    const uint32_t idesc = umma_idesc_bf16(128, 32);
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb) {
-      const uint64_t da = umma_desc_k_sw128(smem_u32(sA + kb * 16384));
-      const uint64_t db = umma_desc_k_sw128(smem_u32(sB + kb * 4096));
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16_ss(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+    for (int j = 0; j < KPAD / 8; ++j) {
+      *reinterpret_cast<uint4*>(a_dst + (j >> 3) * 16384 + sw128_offset(tid, j & 7)) =
+          make_uint4(regs[4 * j], regs[4 * j + 1], regs[4 * j + 2], regs[4 * j + 3]);
     }
-    umma_commit(bar_mma);
-  }
-  __syncwarp();
-  mbar_wait(bar_mma, 0);
-  __syncwarp();                 // tcgen05.ld is .sync.aligned: reconverge after the per-thread poll loop
-  tc_fence_after();
+    fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncthreads();              // all rows written; everyone is also done reading sX[buf]
 
-  // ---- epilogue: TMEM lane = tile row = this thread's voxel ----
-  uint32_t v0[16], v1[16];
-  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-  tmem_ld_32x32b_x16(taddr, v0);
-  tmem_ld_32x32b_x16(taddr + 16, v1);
-  tmem_ld_wait();
-  const int wo = w0 + wl, ho = h0 + hl, dz = d0 + dl;
-  if (wo < p.Wo && ho < p.Ho && dz < p.Do) {
-    uint4* dst = reinterpret_cast<uint4*>(p.y + ((((long long)n * p.Do + dz) * p.Ho + ho) * p.Wo + wo) * 32);
+    if (tid == 32) {
+      // the halo buffer is free: prefetch the tile two iterations ahead
+      const int nxt = tile + 2 * (int)gridDim.x;
+      if (nxt < total_tiles) issue_tma(nxt, buf);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, 32);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t o[4];
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint64_t da = umma_desc_k_sw128(smem_u32(a_dst + kb * 16384));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(sB + kb * 4096));
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int c = q * 8 + h * 2;
-        const float a0 = __uint_as_float(c < 16 ? v0[c & 15] : v1[c & 15]);
-        const float a1 = __uint_as_float(c + 1 < 16 ? v0[(c + 1) & 15] : v1[(c + 1) & 15]);
-        const float2 sc = __ldg(reinterpret_cast<const float2*>(p.scale + c));
-        const float2 sh = __ldg(reinterpret_cast<const float2*>(p.shift + c));
-        o[h] = pack_bf16x2(relu_nan(__fadd_rn(__fmul_rn(a0, sc.x), sh.x)),
-                           relu_nan(__fadd_rn(__fmul_rn(a1, sc.y), sh.y)));
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + (uint32_t)(buf * 32), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                       (kb | k) != 0 ? 1u : 0u);
       }
-      dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+      umma_commit(&bar_mma[buf]);
     }
+    __syncwarp();
+
+    // ---- epilogue of the previous tile overlaps this tile's UMMAs ----
+    if (prev_tile >= 0) {
+      const int pb = (it - 1) & 1;
+      mbar_wait(&bar_mma[pb], (uint32_t)(((it - 1) >> 1) & 1));
+      tc_fence_after();
+      epilogue(prev_tile, pb);
+      tc_fence_before();
+    }
+    prev_tile = tile;
+  }
+  if (prev_tile >= 0) {
+    const int pb = (it - 1) & 1;
+    mbar_wait(&bar_mma[pb], (uint32_t)(((it - 1) >> 1) & 1));
+    tc_fence_after();
+    epilogue(prev_tile, pb);
   }
 
   tc_fence_before();
@@ -202,7 +270,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 32);
+    tmem_dealloc(tmem_base, 64);
   }
 }
 
@@ -231,11 +299,19 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return SSD3D_ERR_TMA;
   }
-  const size_t tile_bytes = ((size_t)CIN * p.TDI * p.THI * p.TWI * sizeof(TIn) + 15) & ~(size_t)15;
-  const size_t smem = 1024 + (size_t)KB * (16384 + 4096) + 128 + tile_bytes + 256;
+  const size_t tile_pitch = ((size_t)CIN * p.TDI * p.THI * p.TWI * sizeof(TIn) + 127) & ~(size_t)127;
+  const size_t smem = 1024 + (size_t)KB * (2 * 16384 + 4096) + 128 + 2 * tile_pitch + 128;
   cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<TIn, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const unsigned grid = (unsigned)(p.tiles_w * p.tiles_h * p.tiles_d * p.N);
+  // persistent grid: 3 CTAs per SM (smem ~53 KB, 64 TMEM columns each), never more CTAs than tiles
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
+  const unsigned grid = (unsigned)(tiles < 3ll * n_sm ? tiles : 3ll * n_sm);
   stem_tc_kernel<TIn, CIN><<<grid, 128, smem, st>>>(tm, p);
   SSD3D_CHECK_LAUNCH();
   return SSD3D_OK;
