@@ -210,11 +210,15 @@ class PredictionConvolutions(nn.Module):
             locs, classes_scores = out
         off = 0
         for i, key in enumerate(feat_keys):
-            w, b = packed[i]
-            bpl = self.n_boxes[list(self.aspect_ratios.keys())[i]]
-            ops.head_conv(feats[key], w, b, locs, classes_scores, bpl, self.n_classes, off, nan_flag)
+            self.run_head(i, feats[key], locs, classes_scores, off, nan_flag)
             off += counts[i]
         return locs, classes_scores
+
+    def run_head(self, i, feat, locs, classes_scores, prior_offset, nan_flag=None):
+        """Head ``i`` (i-th prediction layer) on its feature map, written at ``prior_offset``."""
+        w, b = self._pack()[i]
+        bpl = self.n_boxes[list(self.aspect_ratios.keys())[i]]
+        ops.head_conv(feat, w, b, locs, classes_scores, bpl, self.n_classes, prior_offset, nan_flag)
 
 
 class _InferencePlan:
@@ -240,6 +244,7 @@ class _InferencePlan:
         self.done = torch.cuda.Event()       # graph + metadata read-back of the latest launch finished
         self.cloned = torch.cuda.Event()     # results of the latest launch were copied out of the static buffers
         self.stem = model.base.features[0]
+        self.head_streams = [torch.cuda.Stream(device=dev) for _ in model.aspect_ratios]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
@@ -269,8 +274,30 @@ class _InferencePlan:
         dev = self.inp.device
         flag = model.base.nan_flag(dev)
         flag.zero_()
-        feats = model.base(None, check_nan=False, stem_out=self.stem_out)
-        locs, scores = model.pred_convs(feats, flag)
+        # Backbone on the main stream; every head forks onto its own stream as soon as its feature map
+        # exists, so the head GEMMs overlap the small tail layers (which leave most SMs idle) and join
+        # before detection.  Captured, these become parallel branches of the graph.
+        main = torch.cuda.current_stream()
+        base, pc = model.base, model.pred_convs
+        keys = list(model.aspect_ratios.keys())
+        dims, _ = base.get_feature_map_infos(tuple(self.inp.shape[2:]))
+        counts = [dims[k][0] * dims[k][1] * dims[k][2] * pc.n_boxes[k] for k in keys]
+        offs = [int(sum(counts[:j])) for j in range(len(keys))]
+        locs = torch.empty((self.n, int(sum(counts)), 6), dtype=torch.float32, device=dev)
+        scores = torch.empty((self.n, int(sum(counts)), pc.n_classes), dtype=torch.float32, device=dev)
+        out, keep_alive = self.stem_out, []
+        for i, feat in enumerate(base.features):
+            if i > 0:
+                out = feat(out)
+            if i in keys:
+                j = keys.index(i)
+                keep_alive.append(out)
+                hs = self.head_streams[j]
+                hs.wait_stream(main)
+                with torch.cuda.stream(hs):
+                    pc.run_head(j, out, locs, scores, offs[j], flag)
+        for hs in self.head_streams:
+            main.wait_stream(hs)
         ms, mo, k = self.args
         self.out = ops.detect_objects_padded(locs, scores, model._priors_on(dev), ms, mo, k,
                                              out_count=self.meta[:self.n], status=self.meta[self.n:self.n + 1])
