@@ -121,8 +121,11 @@ int64_t ssd3d_detect_workspace_bytes(int N, int64_t P, int n_classes, int top_k)
  *   (ssd3d.py:437-440) and count 1.
  *   Tie rule for equal scores: ascending prior index (the stable order; the reference's sort is
  *   unspecified there).
- *   Limit of this version: candidates above min_score per (image, class) <= SSD3D_SORT_MAX; beyond it
- *   the call sets bit 0 of *status (device int32, may be NULL) and truncates. */
+ *   Any number of candidates is accepted: lists longer than SSD3D_SORT_MAX are reduced to their best
+ *   10*top_k entries by a hierarchical block sort (exact).  Limit of this version: the NMS itself runs over
+ *   at most min(10*top_k, SSD3D_SORT_MAX) boxes, and with P > SSD3D_SORT_MAX it needs 10*top_k <=
+ *   SSD3D_SORT_MAX/2 (else SSD3D_ERR_UNSUPPORTED); bit 0 of *status (device int32, may be NULL) reports a
+ *   truncated list. */
 #define SSD3D_SORT_MAX 16384
 int ssd3d_detect_objects(const float* locs, const float* scores, const float* priors, int N, int64_t P,
                          int n_classes, float min_score, float max_overlap, int top_k, float* out_boxes,

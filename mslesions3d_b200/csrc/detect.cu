@@ -83,24 +83,16 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------------
 // stage 2: per-segment sort (shared-memory bitonic network on 64-bit keys)
+//
+// A block sorts at most SSD3D_SORT_MAX keys.  Longer candidate lists (the >1M-prior whole-brain config) are
+// reduced hierarchically: every 16384-key chunk is sorted by its own block which keeps the chunk's best
+// `nmax` keys, the survivors form the next level's list, until one chunk is left.  Keys are unique
+// ({~orderable(score), prior index}), so the result is exactly the first `nmax` entries of the full sort.
+// Empty slots hold the sentinel ~0, which sorts last and is dropped at the end.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) sort_segments_kernel(unsigned long long* __restrict__ cand,
-                                                             const int* __restrict__ count, int* __restrict__ nkeep,
-                                                             const float* __restrict__ boxes, long long P, int C,
-                                                             int nmax, int sort_cap, float* __restrict__ sboxes,
-                                                             float* __restrict__ sscores, int* __restrict__ sprior,
-                                                             int* __restrict__ status) {
-  extern __shared__ unsigned long long keys[];
-  const int seg = blockIdx.x;
-  const int img = seg / (C - 1);
-  int n = count[seg];
-  if (n > sort_cap) {
-    if (threadIdx.x == 0 && status) atomicOr(status, 1);
-    n = sort_cap;
-  }
+__device__ __forceinline__ int bitonic_sort_smem(unsigned long long* keys, const unsigned long long* src, int n) {
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
-  unsigned long long* src = cand + (long long)seg * P;
   for (int i = threadIdx.x; i < np2; i += blockDim.x) keys[i] = (i < n) ? src[i] : ~0ull;
   __syncthreads();
   for (int k = 2; k <= np2; k <<= 1) {
@@ -115,7 +107,53 @@ __global__ void __launch_bounds__(1024) sort_segments_kernel(unsigned long long*
       __syncthreads();
     }
   }
-  const int nk = n < nmax ? n : nmax;
+  return np2;
+}
+
+// one level of the hierarchical reduction: block (chunk, seg) -> best `nmax` keys of its chunk (or sentinels)
+__global__ void __launch_bounds__(1024) topk_reduce_kernel(const unsigned long long* __restrict__ src,
+                                                           long long src_stride, const int* __restrict__ count,
+                                                           int fixed_len, unsigned long long* __restrict__ dst,
+                                                           long long dst_stride, int nmax, int chunk_len) {
+  extern __shared__ unsigned long long keys[];
+  const int chunk = blockIdx.x, seg = blockIdx.y;
+  const long long len = count ? (long long)count[seg] : (long long)fixed_len;
+  const long long begin = (long long)chunk * chunk_len;
+  long long n = len - begin;
+  if (n > chunk_len) n = chunk_len;
+  unsigned long long* out = dst + (long long)seg * dst_stride + (long long)chunk * nmax;
+  if (n <= 0) {
+    for (int i = threadIdx.x; i < nmax; i += blockDim.x) out[i] = ~0ull;
+    return;
+  }
+  bitonic_sort_smem(keys, src + (long long)seg * src_stride + begin, (int)n);
+  for (int i = threadIdx.x; i < nmax; i += blockDim.x) out[i] = (i < n) ? keys[i] : ~0ull;
+}
+
+__global__ void __launch_bounds__(1024) sort_segments_kernel(const unsigned long long* __restrict__ cand,
+                                                             long long cand_stride, const int* __restrict__ count,
+                                                             int fixed_len, int* __restrict__ nkeep,
+                                                             const float* __restrict__ boxes, long long P, int C,
+                                                             int nmax, int sort_cap, float* __restrict__ sboxes,
+                                                             float* __restrict__ sscores, int* __restrict__ sprior,
+                                                             int* __restrict__ status) {
+  extern __shared__ unsigned long long keys[];
+  __shared__ int s_valid;
+  const int seg = blockIdx.x;
+  const int img = seg / (C - 1);
+  int n = count ? count[seg] : fixed_len;
+  if (n > sort_cap) {
+    if (threadIdx.x == 0 && status) atomicOr(status, 1);
+    n = sort_cap;
+  }
+  if (threadIdx.x == 0) s_valid = 0;
+  const int np2 = bitonic_sort_smem(keys, cand + (long long)seg * cand_stride, n);
+  // sentinels (empty slots of a reduced list) sort last: the valid prefix ends at the first one
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (keys[i] != ~0ull && (i + 1 == np2 || keys[i + 1] == ~0ull)) s_valid = i + 1;
+  __syncthreads();
+  const int nv = s_valid;
+  const int nk = nv < nmax ? nv : nmax;
   if (threadIdx.x == 0) nkeep[seg] = nk;
   for (int i = threadIdx.x; i < nk; i += blockDim.x) {
     const unsigned long long key = keys[i];
@@ -406,7 +444,7 @@ static inline long long nms_stage_words(int words, long long n_max) {
 
 struct DetectLayout {
   int S, nmax, words;
-  long long off_count, off_nkeep, off_keptcnt, off_boxes, off_cand, off_sboxes, off_sscores, off_sprior, off_mask,
+  long long off_count, off_nkeep, off_keptcnt, off_boxes, off_cand, off_cand2, cand2_stride, off_sboxes, off_sscores, off_sprior, off_mask,
       off_keptpos, off_keptscore, total;
 };
 
@@ -425,6 +463,9 @@ static DetectLayout detect_layout(int N, long long P, int C, int top_k) {
   L.off_keptcnt = o; o += align256(4ll * L.S);
   L.off_boxes = o; o += align256(4ll * N * P * 6);
   L.off_cand = o; o += align256(8ll * L.S * P);
+  // second key buffer for the hierarchical top-k (only when one block cannot hold all candidates)
+  L.cand2_stride = (P > SSD3D_SORT_MAX) ? ((P + SSD3D_SORT_MAX - 1) / SSD3D_SORT_MAX) * L.nmax : 0;
+  L.off_cand2 = o; o += align256(8ll * L.S * L.cand2_stride);
   L.off_sboxes = o; o += align256(4ll * L.S * L.nmax * 6);
   L.off_sscores = o; o += align256(4ll * L.S * L.nmax);
   L.off_sprior = o; o += align256(4ll * L.S * L.nmax);
@@ -516,10 +557,41 @@ extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, cons
     if (smem > 48 * 1024) {
       e = cudaFuncSetAttribute(sort_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(topk_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
     }
-    sort_segments_kernel<<<L.S, 1024, smem, st>>>(cand, count, nkeep, boxes, P, n_classes, L.nmax, cap, sboxes, sscores,
-                                                  sprior, status);
-    SSD3D_CHECK_LAUNCH();
+    if (P <= SSD3D_SORT_MAX) {
+      sort_segments_kernel<<<L.S, 1024, smem, st>>>(cand, P, count, 0, nkeep, boxes, P, n_classes, L.nmax, cap, sboxes,
+                                                    sscores, sprior, status);
+      SSD3D_CHECK_LAUNCH();
+    } else {
+      // hierarchical top-nmax: every level shrinks the list by SORT_MAX / nmax (>= 2)
+      if (L.nmax > SSD3D_SORT_MAX / 2) return SSD3D_ERR_UNSUPPORTED;
+      unsigned long long* cand2 = reinterpret_cast<unsigned long long*>(ws + L.off_cand2);
+      const unsigned long long* src = cand;
+      long long src_stride = P;
+      unsigned long long* dst = cand2;
+      long long dst_stride = L.cand2_stride;
+      const int* cnt = count;
+      long long len = P;
+      while (len > SSD3D_SORT_MAX) {
+        const long long chunks = (len + SSD3D_SORT_MAX - 1) / SSD3D_SORT_MAX;
+        dim3 grid((unsigned)chunks, (unsigned)L.S);
+        topk_reduce_kernel<<<grid, 1024, smem, st>>>(src, src_stride, cnt, (int)len, dst, dst_stride, L.nmax,
+                                                     SSD3D_SORT_MAX);
+        SSD3D_CHECK_LAUNCH();
+        len = chunks * L.nmax;
+        cnt = nullptr;
+        // ping-pong: the buffer just read becomes the next destination
+        unsigned long long* next_dst = (dst == cand2) ? cand : cand2;
+        const long long next_stride = (dst == cand2) ? P : L.cand2_stride;
+        src = dst; src_stride = dst_stride;
+        dst = next_dst; dst_stride = next_stride;
+      }
+      sort_segments_kernel<<<L.S, 1024, smem, st>>>(src, src_stride, nullptr, (int)len, nkeep, boxes, P, n_classes, L.nmax,
+                                                    cap, sboxes, sscores, sprior, status);
+      SSD3D_CHECK_LAUNCH();
+    }
   }
   {
     dim3 grid((unsigned)L.words, (unsigned)L.words, (unsigned)L.S);

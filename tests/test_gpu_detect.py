@@ -189,3 +189,44 @@ def test_predict_step_graph_equals_eager_and_streams():
         again_eager = m.predict_step({"img": batches[0].cuda()}, 0)
     assert all(torch.equal(a, b) for a, b in zip(again[2], again_eager[2]))
     assert not all(torch.equal(a, b) if a.shape == b.shape else False for a, b in zip(again[2], eager[0][2]))
+
+
+@pytest.mark.parametrize("P,n_classes,min_score,top_k", [(50000, 2, 0.5, 100), (50000, 3, 0.0, 300),
+                                                         (16385, 2, 0.2, 100), (300000, 2, 0.3, 100)])
+def test_detect_hierarchical_topk_many_candidates(P, n_classes, min_score, top_k):
+    """More candidates than one sort block holds (the whole-brain / layer-0 prior sets): the hierarchical
+    top-(10*top_k) reduction must give exactly the head of the full sort."""
+    g = torch.Generator().manual_seed(P + top_k)
+    c = torch.rand(P, 3, generator=g)
+    s = 0.02 + 0.05 * torch.rand(P, 1, generator=g)
+    priors = torch.cat([c, s.expand(P, 3)], 1)
+    locs = torch.randn(2, P, 6, generator=g) * 0.3
+    scores = torch.randn(2, P, n_classes, generator=g) * 2
+    _check_detect_stagewise(locs, scores, priors, min_score, 0.5, top_k)
+
+
+def test_whole_brain_layer0_config_end_to_end():
+    """BASELINE config 4 shape: 2ch 160x192x160, prediction layers 0/3/5/7 -> 2 501 400 priors, default
+    min_score / top_k.  Network vs the bf16-emulating oracle; detections exact on the device's decode."""
+    from mslesions3d_b200.ssd3d import LSSD3D
+    from mslesions3d_b200 import synthetic
+    ar = {0: [1.], 3: [1.], 5: [1.], 7: [1.]}
+    size = (160, 192, 160)
+    sd = O.random_state_dict(2, ar, seed=11)
+    m = LSSD3D(n_classes=2, input_channels=2, input_size=size, aspect_ratios=ar)
+    assert m.priors_cxcycz.shape[0] == 2501400
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = torch.from_numpy(synthetic.make_batch(1, 2, size))
+    with torch.no_grad():
+        locs, scores = m(x.cuda())
+        torch.set_num_threads(max(1, min(16, torch.get_num_threads())))
+        el, es = O.forward(sd, x, ar, emulate_bf16=True)
+    dl, ds = (locs.cpu() - el).abs(), (scores.cpu() - es).abs()
+    assert float(dl.max()) <= 0.06 and float(ds.max()) <= 0.06, (float(dl.max()), float(ds.max()))
+    assert float(dl.mean()) <= 6e-3 and float(ds.mean()) <= 6e-3
+    with torch.no_grad():
+        boxes, labels, sc, idx = m.detect_objects(locs, scores, 0.5, 0.5, 100, return_prior=True)
+    probs, dec = _ops().decode_softmax(locs, scores, m.priors_cxcycz)
+    wb, wl, ws, widx = O.detect_from_decoded(probs.cpu(), dec.cpu(), 0.5, 0.5, 100, return_indices=True)
+    assert torch.equal(idx[0].cpu(), widx[0]) and torch.equal(sc[0].cpu(), ws[0]) and torch.equal(boxes[0].cpu(), wb[0])
