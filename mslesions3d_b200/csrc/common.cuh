@@ -14,7 +14,51 @@
     if (e__ != cudaSuccess) return (int)e__;         \
   } while (0)
 
+#include <cstdlib>
+#include <utility>
+
 namespace ssd3d {
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: consecutive kernels of the step are launched with programmatic stream
+// serialization, so the next kernel's CTAs are scheduled (and run their prologue: barrier init, TMEM
+// allocation, constant loads) while the previous kernel drains.  pdl_wait() blocks until every
+// prerequisite grid has completed and its writes are visible: it must precede the first access to memory
+// another kernel produces or still reads.  pdl_launch_dependents() lets the next kernel start launching.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSD3D_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+#define SSD3D_LAUNCH_PDL(kernel, grid, block, smem, st, ...)                                 \
+  do {                                                                                       \
+    cudaError_t e__ = ssd3d::launch_pdl(kernel, grid, block, smem, st, __VA_ARGS__);         \
+    if (e__ != cudaSuccess) return (int)e__;                                                 \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // numerics

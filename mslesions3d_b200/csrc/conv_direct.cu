@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_kernel(const __nv_bfloat16* _
                                                        __nv_bfloat16* __restrict__ y, int N, int C, int D, int H, int W,
                                                        int Do, int Ho, int Wo, long long total) {
   constexpr int NI = (WT - 1) * S + 3;  // input columns needed by WT outputs
+  pdl_wait();
+  pdl_launch_dependents();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
   const int CV = C >> 3;
@@ -263,9 +265,11 @@ extern "C" int ssd3d_dwconv3d_bn_relu(const void* x, const void* w, const float*
   const long long total = (long long)N * Do * Ho * ((Wo + WT - 1) / WT) * (C / 8);
   const unsigned blocks = (unsigned)((total + 255) / 256);
   if (stride == 1)
-    ssd3d::dwconv3d_kernel<1, WT><<<blocks, 256, 0, st>>>(xp, wp, scale, shift, yp, N, C, D, H, W, Do, Ho, Wo, total);
+    SSD3D_LAUNCH_PDL((ssd3d::dwconv3d_kernel<1, WT>), dim3(blocks), dim3(256), 0, st, xp, wp, scale, shift, yp, N, C, D,
+                     H, W, Do, Ho, Wo, total);
   else
-    ssd3d::dwconv3d_kernel<2, WT><<<blocks, 256, 0, st>>>(xp, wp, scale, shift, yp, N, C, D, H, W, Do, Ho, Wo, total);
+    SSD3D_LAUNCH_PDL((ssd3d::dwconv3d_kernel<2, WT>), dim3(blocks), dim3(256), 0, st, xp, wp, scale, shift, yp, N, C, D,
+                     H, W, Do, Ho, Wo, total);
   SSD3D_CHECK_LAUNCH();
   return SSD3D_OK;
 }

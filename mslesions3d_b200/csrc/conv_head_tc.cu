@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(224, 1) head2_kernel(const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int R_BYTES = p.HD * p.HH * p.HW * 128;   // bytes one halo box delivers
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 4) {
     // ===================== activation producer: one 5-D box per 64-channel chunk =====================
@@ -206,6 +208,8 @@ __global__ void __launch_bounds__(224, 1) head2_kernel(const __grid_constant__ C
 // out[voxel][col] = bias[col] + sum over splits (ascending) of partial[split][tile][m][col].
 // One thread per (voxel, 4 columns): the S float4 loads are independent, the additions run in split order.
 __global__ void __launch_bounds__(256) head2_reduce_kernel(const Head2Params p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int groups = p.NPAD >> 2;
   const long long total = (long long)p.N * p.D * p.H * p.W * groups;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -349,12 +353,10 @@ int ssd3d_head_conv_halo(const void* x, const void* w, const float* bias, float*
   cudaError_t e = cudaFuncSetAttribute(head2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)p.tiles_total, (unsigned)p.S);
-  head2_kernel<<<grid, 224, smem, st>>>(tmX, tmW, p);
-  SSD3D_CHECK_LAUNCH();
+  SSD3D_LAUNCH_PDL(head2_kernel, grid, dim3(224), smem, st, tmX, tmW, p);
   if (p.S > 1) {
     const long long total = (long long)N * D * H * W * (NPAD / 4);
-    head2_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
-    SSD3D_CHECK_LAUNCH();
+    SSD3D_LAUNCH_PDL(head2_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);
   }
   return SSD3D_OK;
 }

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
   };
 
   const int first = blockIdx.x;
+  pdl_wait();                 // the input (and the output buffer's previous readers) belong to earlier work
+  pdl_launch_dependents();
   if (tid == 32) {
     if (first < total_tiles) issue_tma(first, 0);
     if (first + (int)gridDim.x < total_tiles) issue_tma(first + gridDim.x, 1);
@@ -312,8 +314,7 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
   }
   const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
   const unsigned grid = (unsigned)(tiles < 3ll * n_sm ? tiles : 3ll * n_sm);
-  stem_tc_kernel<TIn, CIN><<<grid, 128, smem, st>>>(tm, p);
-  SSD3D_CHECK_LAUNCH();
+  SSD3D_LAUNCH_PDL((stem_tc_kernel<TIn, CIN>), dim3(grid), dim3(128), smem, st, tm, p);
   return SSD3D_OK;
 }
 

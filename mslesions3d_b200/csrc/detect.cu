@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
                                                             float min_score, float* __restrict__ boxes,
                                                             unsigned long long* __restrict__ cand,
                                                             int* __restrict__ count) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int img = blockIdx.y;
   const bool live = p < P;
@@ -116,6 +118,8 @@ __global__ void __launch_bounds__(1024) topk_reduce_kernel(const unsigned long l
                                                            int fixed_len, unsigned long long* __restrict__ dst,
                                                            long long dst_stride, int nmax, int chunk_len) {
   extern __shared__ unsigned long long keys[];
+  pdl_wait();
+  pdl_launch_dependents();
   const int chunk = blockIdx.x, seg = blockIdx.y;
   const long long len = count ? (long long)count[seg] : (long long)fixed_len;
   const long long begin = (long long)chunk * chunk_len;
@@ -139,6 +143,8 @@ __global__ void __launch_bounds__(1024) sort_segments_kernel(const unsigned long
                                                              int* __restrict__ status) {
   extern __shared__ unsigned long long keys[];
   __shared__ int s_valid;
+  pdl_wait();
+  pdl_launch_dependents();
   const int seg = blockIdx.x;
   const int img = seg / (C - 1);
   int n = count ? count[seg] : fixed_len;
@@ -188,6 +194,8 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
                                                       int n_fixed, long long seg_stride_boxes, int words,
                                                       long long seg_stride_mask, float thr,
                                                       unsigned long long* __restrict__ mask) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int cb = blockIdx.x, rb = blockIdx.y, seg = blockIdx.z;
   if (cb < rb) return;
   const int n = nkeep ? nkeep[seg] : n_fixed;
@@ -327,6 +335,8 @@ __global__ void __launch_bounds__(256) nms_select_kernel(const unsigned long lon
   unsigned long long* keptw = sm + words_max;
   unsigned long long* stage = sm + 2 * words_max;
   __shared__ int s_total;
+  pdl_wait();
+  pdl_launch_dependents();
   const int img = blockIdx.x;
   const int nseg = C - 1;
 
@@ -547,8 +557,8 @@ extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, cons
   }
   {
     dim3 grid((unsigned)((P + 255) / 256), (unsigned)N);
-    decode_filter_kernel<<<grid, 256, 0, st>>>(locs, scores, priors, P, n_classes, min_score, boxes, cand, count);
-    SSD3D_CHECK_LAUNCH();
+    SSD3D_LAUNCH_PDL(decode_filter_kernel, grid, dim3(256), 0, st, locs, scores, priors, (long long)P, n_classes, min_score, boxes,
+                     cand, count);
   }
   {
     int cap = 1;
@@ -561,9 +571,8 @@ extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, cons
       if (e != cudaSuccess) return (int)e;
     }
     if (P <= SSD3D_SORT_MAX) {
-      sort_segments_kernel<<<L.S, 1024, smem, st>>>(cand, P, count, 0, nkeep, boxes, P, n_classes, L.nmax, cap, sboxes,
-                                                    sscores, sprior, status);
-      SSD3D_CHECK_LAUNCH();
+      SSD3D_LAUNCH_PDL(sort_segments_kernel, dim3(L.S), dim3(1024), smem, st, cand, (long long)P, count, 0, nkeep, boxes,
+                       (long long)P, n_classes, L.nmax, cap, sboxes, sscores, sprior, status);
     } else {
       // hierarchical top-nmax: every level shrinks the list by SORT_MAX / nmax (>= 2)
       if (L.nmax > SSD3D_SORT_MAX / 2) return SSD3D_ERR_UNSUPPORTED;
@@ -577,9 +586,8 @@ extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, cons
       while (len > SSD3D_SORT_MAX) {
         const long long chunks = (len + SSD3D_SORT_MAX - 1) / SSD3D_SORT_MAX;
         dim3 grid((unsigned)chunks, (unsigned)L.S);
-        topk_reduce_kernel<<<grid, 1024, smem, st>>>(src, src_stride, cnt, (int)len, dst, dst_stride, L.nmax,
-                                                     SSD3D_SORT_MAX);
-        SSD3D_CHECK_LAUNCH();
+        SSD3D_LAUNCH_PDL(topk_reduce_kernel, grid, dim3(1024), smem, st, src, src_stride, cnt, (int)len, dst, dst_stride,
+                         L.nmax, SSD3D_SORT_MAX);
         len = chunks * L.nmax;
         cnt = nullptr;
         // ping-pong: the buffer just read becomes the next destination
@@ -588,16 +596,14 @@ extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, cons
         src = dst; src_stride = dst_stride;
         dst = next_dst; dst_stride = next_stride;
       }
-      sort_segments_kernel<<<L.S, 1024, smem, st>>>(src, src_stride, nullptr, (int)len, nkeep, boxes, P, n_classes, L.nmax,
-                                                    cap, sboxes, sscores, sprior, status);
-      SSD3D_CHECK_LAUNCH();
+      SSD3D_LAUNCH_PDL(sort_segments_kernel, dim3(L.S), dim3(1024), smem, st, src, src_stride, (const int*)nullptr, (int)len,
+                       nkeep, boxes, (long long)P, n_classes, L.nmax, cap, sboxes, sscores, sprior, status);
     }
   }
   {
     dim3 grid((unsigned)L.words, (unsigned)L.words, (unsigned)L.S);
-    nms_mask_kernel<<<grid, 64, 0, st>>>(sboxes, nkeep, 0, (long long)L.nmax * 6, L.words, (long long)L.nmax * L.words,
-                                         max_overlap, mask);
-    SSD3D_CHECK_LAUNCH();
+    SSD3D_LAUNCH_PDL(nms_mask_kernel, grid, dim3(64), 0, st, sboxes, nkeep, 0, (long long)L.nmax * 6, L.words,
+                     (long long)L.nmax * L.words, max_overlap, mask);
   }
   {
     const long long stage_words = nms_stage_words(L.words, L.nmax);
@@ -606,11 +612,9 @@ extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, cons
       e = cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    nms_select_kernel<<<N, 256, smem, st>>>(mask, nkeep, n_classes, L.nmax, L.words, stage_words, sboxes, sscores, sprior, keptpos,
-                                            keptscore, keptcnt, top_k, out_boxes, out_scores,
-                                            reinterpret_cast<long long*>(out_labels),
-                                            reinterpret_cast<long long*>(out_prior), out_count);
-    SSD3D_CHECK_LAUNCH();
+    SSD3D_LAUNCH_PDL(nms_select_kernel, dim3(N), dim3(256), smem, st, mask, nkeep, n_classes, L.nmax, L.words, stage_words,
+                     sboxes, sscores, sprior, keptpos, keptscore, keptcnt, top_k, out_boxes, out_scores,
+                     reinterpret_cast<long long*>(out_labels), reinterpret_cast<long long*>(out_prior), out_count);
   }
   return SSD3D_OK;
 }

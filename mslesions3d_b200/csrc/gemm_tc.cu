@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // prologue above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   // ---- tile coordinates ----
   int m0 = 0, n0 = 0;                   // pointwise
@@ -250,8 +252,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   const size_t smem = gemm_smem_bytes(BK, p.BN, p.stages);
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BK, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  gemm_tc_kernel<BK, HEAD><<<grid, 192, smem, st>>>(tmA, tmB, p);
-  SSD3D_CHECK_LAUNCH();
+  SSD3D_LAUNCH_PDL((gemm_tc_kernel<BK, HEAD>), grid, dim3(192), smem, st, tmA, tmB, p);
   return SSD3D_OK;
 }
 
