@@ -174,6 +174,87 @@ int ssd3d_multibox_loss(const float* locs, const float* scores, const int64_t* t
                         float* grad_locs, float* grad_scores, void* workspace, int64_t workspace_bytes,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Training step of the network (LSSD3D.training_step, ssd3d.py:467-531): what torch autograd derives for
+ * the reference from nn.Conv3d / nn.BatchNorm3d / nn.ReLU (mobilenet.py:26-49, ssd3d.py:131-167) and
+ * torch.optim.Adam (ssd3d.py:704-722).  Activations and activation gradients: channels-last bf16;
+ * parameter gradients and optimizer state: fp32.  All reductions are two-stage and run-to-run reproducible.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Convolutions with an explicit epilogue y = conv * scale + shift, optional ReLU (relu = 0: identity).
+ * relu = 1 is exactly the *_bn_relu entry point; training-mode BatchNorm needs the raw conv output
+ * (scale = 1, shift = 0, relu = 0), and the pointwise data gradient dx = dz . W is the same GEMM with the
+ * transposed weight. */
+int ssd3d_stem_conv_affine(const void* x, int x_is_bf16, const void* w, const float* scale, const float* shift,
+                           void* y, int N, int Cin, int D, int H, int W, int stride_d, int relu, void* stream);
+int ssd3d_stem_conv_affine_simt(const void* x, int x_is_bf16, const void* w, const float* scale, const float* shift,
+                                void* y, int N, int Cin, int D, int H, int W, int stride_d, int relu, void* stream);
+int ssd3d_dwconv3d_affine(const void* x, const void* w, const float* scale, const float* shift, void* y, int N, int C,
+                          int D, int H, int W, int stride, int relu, void* stream);
+int ssd3d_pwconv_affine(const void* x, const void* w, const float* scale, const float* shift, void* y, int64_t M,
+                        int Cin, int Cout, int relu, int* nan_flag, void* stream);
+
+/* BatchNorm3d in training mode + ReLU on a raw conv output z (M, C) bf16 (mobilenet.py:29-30,39,41,44-45):
+ * batch mean / biased variance per channel -> scale = gamma/sqrt(var+eps), shift = beta - mean*scale
+ * (fp32, C each; also mean and invstd for the backward), running statistics updated in place with
+ * `momentum` and the unbiased variance (NULL to skip), a = relu(z*scale + shift) (NULL to skip).
+ * workspace: ssd3d_bn_workspace_bytes(C). */
+int64_t ssd3d_bn_workspace_bytes(int C);
+int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                       float* mean, float* invstd, void* a, int* nan_flag, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+/* Backward of the same unit: grad_a (M, C) bf16 = dL/da -> dgamma, dbeta (C) fp32 and dz (M, C) bf16
+ * (dz may alias grad_a).  The ReLU mask is recomputed from z with the forward's arithmetic. */
+int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, int C, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, float* dgamma, float* dbeta, void* dz, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* Weight gradients, dW = dz^T . im2col(x), split over rows and reduced in a fixed order.
+ * workspace: ssd3d_wgrad_workspace_bytes(M, n_out, K) with (n_out, K) = (Cout, Cin) pointwise,
+ * (16, 27*C) head, (32, 27*Cin) stem. */
+int64_t ssd3d_wgrad_workspace_bytes(int64_t M, int n_out, int K);
+/* pointwise: dz (M, Cout) bf16, x (M, Cin) bf16 -> dw (Cout, Cin) fp32.  Cin % 32 == 0, Cout % 64 == 0 */
+int ssd3d_pwconv_wgrad(const void* dz, const void* x, int64_t M, int Cin, int Cout, float* dw, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+/* stem: dz (N, Do, Ho, Wo, 32) bf16, x (N, Cin, D, H, W) fp32|bf16 -> dw (32, Cin, 3, 3, 3) fp32 */
+int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W, int stride_d,
+                     float* dw, void* workspace, int64_t workspace_bytes, void* stream);
+/* head: dO (N*D*H*W, 16) bf16 gradient rows (ssd3d_head_grad_pack), x (N, D, H, W, C) bf16
+ * -> dw_loc (n_loc, C, 3,3,3), dw_cls (n_cls, C, 3,3,3) fp32.  C % 64 == 0, n_loc + n_cls <= 16 */
+int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int D, int H, int W, int n_loc, int n_cls,
+                     float* dw_loc, float* dw_cls, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Head gradient rows of one feature map from d(loss)/d(locs (N,P,6)), d(loss)/d(scores (N,P,n_classes)):
+ * dO (N*D*H*W, 16) bf16 in the column order of the fused head GEMM ([loc | class | zero pad]), and the bias
+ * gradients dbias_loc (bpl*6), dbias_cls (bpl*n_classes) fp32 (column sums of the fp32 values).
+ * Needs bpl*(6+n_classes) <= 16.  workspace: ssd3d_head_grad_workspace_bytes(N, D, H, W). */
+int64_t ssd3d_head_grad_workspace_bytes(int N, int D, int H, int W);
+int ssd3d_head_grad_pack(const float* dlocs, const float* dscores, int N, int D, int H, int W, int bpl,
+                         int n_classes, int64_t P, int64_t prior_offset, void* dO, float* dbias_loc, float* dbias_cls,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+/* Head data gradient (transposed 3x3x3 conv): dx (N, D, H, W, C) bf16 = conv_transpose(dO, w) + addend
+ * (addend: the gradient arriving from the next backbone block, may be NULL, may alias dx).
+ * w: the packed head weight (16, 27*C) bf16 of ssd3d_head_conv.  C % 64 == 0 */
+int ssd3d_head_dgrad(const void* dO, const void* w, const void* addend, void* dx, int N, int C, int D, int H, int W,
+                     void* stream);
+
+/* Depthwise 3x3x3 backward: dz (N, Do, Ho, Wo, C) bf16, w (27, C) bf16, x (N, D, H, W, C) bf16
+ * -> dx (N, D, H, W, C) bf16;  dw (C, 1, 3, 3, 3) fp32.  workspace: ssd3d_dw_wgrad_workspace_bytes(C). */
+int ssd3d_dwconv3d_dgrad(const void* dz, const void* w, void* dx, int N, int C, int D, int H, int W, int stride,
+                         void* stream);
+int64_t ssd3d_dw_wgrad_workspace_bytes(int C);
+int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C, int D, int H, int W, int stride, float* dw,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* One Adam step over flat fp32 buffers with torch.optim.Adam's arithmetic (L2 weight decay added to the
+ * gradient, bias-corrected moments; ssd3d.py:716): elements [0, bias_start) use lr, [bias_start, n) use
+ * lr_bias (the reference's "biases at 2x lr" group, ssd3d.py:715).  grad is multiplied by grad_scale first
+ * (1/world_size after the NCCL sum).  step >= 1. */
+int ssd3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    int64_t bias_start, float lr, float lr_bias, float beta1, float beta2, float eps,
+                    float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,27 @@ SIGNATURES = {
     "ssd3d_multibox_workspace_bytes": (c_int64, [c_int, c_int64]),
     "ssd3d_multibox_loss": (c_int, [P, P, P, P, c_int, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P,
                                     c_int64, P]),
+    # ---- training step ----
+    "ssd3d_stem_conv_affine": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "ssd3d_stem_conv_affine_simt": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "ssd3d_dwconv3d_affine": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "ssd3d_pwconv_affine": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, P, P]),
+    "ssd3d_bn_workspace_bytes": (c_int64, [c_int]),
+    "ssd3d_bn_train_fwd": (c_int, [P, c_int64, c_int, P, P, c_float, c_float, P, P, P, P, P, P, P, P, P, c_int64, P]),
+    "ssd3d_bn_relu_bwd": (c_int, [P, P, c_int64, c_int, P, P, P, P, P, P, P, P, c_int64, P]),
+    "ssd3d_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "ssd3d_pwconv_wgrad": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P]),
+    "ssd3d_stem_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int64, P]),
+    "ssd3d_head_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int64, P]),
+    "ssd3d_head_grad_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "ssd3d_head_grad_pack": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, P, P, P, P,
+                                     c_int64, P]),
+    "ssd3d_head_dgrad": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "ssd3d_dwconv3d_dgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "ssd3d_dw_wgrad_workspace_bytes": (c_int64, [c_int]),
+    "ssd3d_dwconv3d_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int64, P]),
+    "ssd3d_adam_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, c_float,
+                                c_int, c_float, P]),
 }
 
 _lib = None

@@ -65,6 +65,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // ---------------------------------------------------------------------------------------------
 // torch.relu semantics: NaN propagates (fmaxf(NaN, 0) would return 0).  mobilenet.py:30,44-45
 __device__ __forceinline__ float relu_nan(float v) { return (v < 0.0f) ? 0.0f : v; }
+// Activation floor: 0 = ReLU, -inf = identity (raw conv output for training-mode BatchNorm).  NaN propagates.
+__device__ __forceinline__ float clamp_floor(float v, float floor) { return (v < floor) ? floor : v; }
+#define SSD3D_FLOOR(relu) ((relu) ? 0.0f : -__builtin_huge_valf())
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_kernel(const __nv_bfloat16* _
                                                        const float* __restrict__ scale,
                                                        const float* __restrict__ shift,
                                                        __nv_bfloat16* __restrict__ y, int N, int C, int D, int H, int W,
-                                                       int Do, int Ho, int Wo, long long total) {
+                                                       int Do, int Ho, int Wo, long long total, float floor) {
   constexpr int NI = (WT - 1) * S + 3;  // input columns needed by WT outputs
   pdl_wait();
   pdl_launch_dependents();
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3d_kernel(const __nv_bfloat16* _
     if (wo >= Wo) break;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = relu_nan(__fadd_rn(__fmul_rn(acc[ow][j], sc[j]), sh[j]));
+    for (int j = 0; j < 8; ++j) v[j] = clamp_floor(__fadd_rn(__fmul_rn(acc[ow][j], sc[j]), sh[j]), floor);
     uint4 o;
     o.x = pack_bf16x2(v[0], v[1]);
     o.y = pack_bf16x2(v[2], v[3]);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x,
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ shift,
                                                         __nv_bfloat16* __restrict__ y, int N, int D, int H, int W,
-                                                        int Do, int Ho, int Wo, int sd, long long total_pairs) {
+                                                        int Do, int Ho, int Wo, int sd, long long total_pairs, float floor) {
   // w is (32, KPAD) bf16 with k = ci*27 + tap (PyTorch's flattened (Cin,3,3,3)); shared copy is
   // [tap*CIN + ci][32] fp32 so that one tap's 32 output-channel weights are contiguous
   constexpr int KPAD = (27 * CIN <= 64) ? 64 : 128;
@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x,
       const int c = q * 8 + h * 2;
       const float s0 = __ldg(scale + c), s1 = __ldg(scale + c + 1);
       const float b0 = __ldg(shift + c), b1 = __ldg(shift + c + 1);
-      u0[h] = pack_bf16x2(relu_nan(__fadd_rn(__fmul_rn(acc0[c], s0), b0)),
-                          relu_nan(__fadd_rn(__fmul_rn(acc0[c + 1], s1), b1)));
-      u1[h] = pack_bf16x2(relu_nan(__fadd_rn(__fmul_rn(acc1[c], s0), b0)),
-                          relu_nan(__fadd_rn(__fmul_rn(acc1[c + 1], s1), b1)));
+      u0[h] = pack_bf16x2(clamp_floor(__fadd_rn(__fmul_rn(acc0[c], s0), b0), floor),
+                          clamp_floor(__fadd_rn(__fmul_rn(acc0[c + 1], s1), b1), floor));
+      u1[h] = pack_bf16x2(clamp_floor(__fadd_rn(__fmul_rn(acc1[c], s0), b0), floor),
+                          clamp_floor(__fadd_rn(__fmul_rn(acc1[c + 1], s1), b1), floor));
     }
     *reinterpret_cast<uint4*>(o + q * 8) = p0;
     if (second) *reinterpret_cast<uint4*>(o + 32 + q * 8) = p1;
@@ -219,17 +219,17 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const T* __restrict__ x,
 
 template <typename T>
 static int launch_stem(const void* x, const __nv_bfloat16* w, const float* scale, const float* shift, void* y, int N,
-                       int Cin, int D, int H, int W, int sd, cudaStream_t st) {
+                       int Cin, int D, int H, int W, int sd, float floor, cudaStream_t st) {
   const int Do = (D - 1) / sd + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = (long long)N * Do * Ho * ((Wo + 1) / 2);
   const unsigned blocks = (unsigned)((total + 127) / 128);
   const T* xp = static_cast<const T*>(x);
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   switch (Cin) {
-    case 1: stem_conv_kernel<T, 1><<<blocks, 128, 0, st>>>(xp, w, scale, shift, yp, N, D, H, W, Do, Ho, Wo, sd, total); break;
-    case 2: stem_conv_kernel<T, 2><<<blocks, 128, 0, st>>>(xp, w, scale, shift, yp, N, D, H, W, Do, Ho, Wo, sd, total); break;
-    case 3: stem_conv_kernel<T, 3><<<blocks, 128, 0, st>>>(xp, w, scale, shift, yp, N, D, H, W, Do, Ho, Wo, sd, total); break;
-    case 4: stem_conv_kernel<T, 4><<<blocks, 128, 0, st>>>(xp, w, scale, shift, yp, N, D, H, W, Do, Ho, Wo, sd, total); break;
+    case 1: stem_conv_kernel<T, 1><<<blocks, 128, 0, st>>>(xp, w, scale, shift, yp, N, D, H, W, Do, Ho, Wo, sd, total, floor); break;
+    case 2: stem_conv_kernel<T, 2><<<blocks, 128, 0, st>>>(xp, w, scale, shift, yp, N, D, H, W, Do, Ho, Wo, sd, total, floor); break;
+    case 3: stem_conv_kernel<T, 3><<<blocks, 128, 0, st>>>(xp, w, scale, shift, yp, N, D, H, W, Do, Ho, Wo, sd, total, floor); break;
+    case 4: stem_conv_kernel<T, 4><<<blocks, 128, 0, st>>>(xp, w, scale, shift, yp, N, D, H, W, Do, Ho, Wo, sd, total, floor); break;
     default: return SSD3D_ERR_UNSUPPORTED;
   }
   SSD3D_CHECK_LAUNCH();
@@ -238,19 +238,32 @@ static int launch_stem(const void* x, const __nv_bfloat16* w, const float* scale
 
 }  // namespace ssd3d
 
-extern "C" int ssd3d_stem_conv_bn_relu_simt(const void* x, int x_is_bf16, const void* w, const float* scale,
-                                            const float* shift, void* y, int N, int Cin, int D, int H, int W,
-                                            int stride_d, void* stream) {
+static int stem_simt(const void* x, int x_is_bf16, const void* w, const float* scale, const float* shift, void* y,
+                     int N, int Cin, int D, int H, int W, int stride_d, int relu, void* stream) {
   if (!x || !w || !scale || !shift || !y || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
   if (stride_d != 1 && stride_d != 2) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
-  if (x_is_bf16) return ssd3d::launch_stem<__nv_bfloat16>(x, wp, scale, shift, y, N, Cin, D, H, W, stride_d, st);
-  return ssd3d::launch_stem<float>(x, wp, scale, shift, y, N, Cin, D, H, W, stride_d, st);
+  const float floor = SSD3D_FLOOR(relu);
+  if (x_is_bf16)
+    return ssd3d::launch_stem<__nv_bfloat16>(x, wp, scale, shift, y, N, Cin, D, H, W, stride_d, floor, st);
+  return ssd3d::launch_stem<float>(x, wp, scale, shift, y, N, Cin, D, H, W, stride_d, floor, st);
 }
 
-extern "C" int ssd3d_dwconv3d_bn_relu(const void* x, const void* w, const float* scale, const float* shift, void* y,
-                                      int N, int C, int D, int H, int W, int stride, void* stream) {
+extern "C" int ssd3d_stem_conv_bn_relu_simt(const void* x, int x_is_bf16, const void* w, const float* scale,
+                                            const float* shift, void* y, int N, int Cin, int D, int H, int W,
+                                            int stride_d, void* stream) {
+  return stem_simt(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, 1, stream);
+}
+
+extern "C" int ssd3d_stem_conv_affine_simt(const void* x, int x_is_bf16, const void* w, const float* scale,
+                                           const float* shift, void* y, int N, int Cin, int D, int H, int W,
+                                           int stride_d, int relu, void* stream) {
+  return stem_simt(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, relu, stream);
+}
+
+extern "C" int ssd3d_dwconv3d_affine(const void* x, const void* w, const float* scale, const float* shift, void* y,
+                                     int N, int C, int D, int H, int W, int stride, int relu, void* stream) {
   if (!x || !w || !scale || !shift || !y || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
   if (C <= 0 || (C & 7)) return SSD3D_ERR_ARG;
   if (stride != 1 && stride != 2) return SSD3D_ERR_ARG;
@@ -259,6 +272,7 @@ extern "C" int ssd3d_dwconv3d_bn_relu(const void* x, const void* w, const float*
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  const float floor = SSD3D_FLOOR(relu);
   // WT = 4 outputs per thread and 2 resident blocks/SM measured best on B200 (WT = 2 or a tighter register
   // cap were 2-70 % slower on every layer of the benchmark network)
   constexpr int WT = 4;
@@ -266,10 +280,14 @@ extern "C" int ssd3d_dwconv3d_bn_relu(const void* x, const void* w, const float*
   const unsigned blocks = (unsigned)((total + 255) / 256);
   if (stride == 1)
     SSD3D_LAUNCH_PDL((ssd3d::dwconv3d_kernel<1, WT>), dim3(blocks), dim3(256), 0, st, xp, wp, scale, shift, yp, N, C, D,
-                     H, W, Do, Ho, Wo, total);
+                     H, W, Do, Ho, Wo, total, floor);
   else
     SSD3D_LAUNCH_PDL((ssd3d::dwconv3d_kernel<2, WT>), dim3(blocks), dim3(256), 0, st, xp, wp, scale, shift, yp, N, C, D,
-                     H, W, Do, Ho, Wo, total);
-  SSD3D_CHECK_LAUNCH();
+                     H, W, Do, Ho, Wo, total, floor);
   return SSD3D_OK;
+}
+
+extern "C" int ssd3d_dwconv3d_bn_relu(const void* x, const void* w, const float* scale, const float* shift, void* y,
+                                      int N, int C, int D, int H, int W, int stride, void* stream) {
+  return ssd3d_dwconv3d_affine(x, w, scale, shift, y, N, C, D, H, W, stride, 1, stream);
 }

@@ -26,6 +26,7 @@ struct StemParams {
   const float* scale;
   const float* shift;
   __nv_bfloat16* y;          // (N, Do, Ho, Wo, 32)
+  float floor;               // activation floor: 0 = ReLU, -inf = identity
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
@@ -47,9 +48,9 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
 }
 
 // NaN-propagating ReLU in one instruction (max.NaN returns NaN if either input is NaN: torch.relu semantics)
-__device__ __forceinline__ float relu_nan1(float v) {
+__device__ __forceinline__ float relu_nan1(float v, float floor) {
   float r;
-  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(floor));
   return r;
 }
 
@@ -163,8 +164,8 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
           const int c = q * 8 + h * 2;
           const float a0 = __uint_as_float(c < 16 ? v0[c & 15] : v1[c & 15]);
           const float a1 = __uint_as_float(c + 1 < 16 ? v0[(c + 1) & 15] : v1[(c + 1) & 15]);
-          o[h] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(a0, sc[c]), sh[c])),
-                             relu_nan1(__fadd_rn(__fmul_rn(a1, sc[c + 1]), sh[c + 1])));
+          o[h] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(a0, sc[c]), sh[c]), p.floor),
+                             relu_nan1(__fadd_rn(__fmul_rn(a1, sc[c + 1]), sh[c + 1]), p.floor));
         }
         dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -329,8 +330,9 @@ extern "C" int ssd3d_stem_tc_supported(int x_is_bf16, int Cin, int W) {
 }
 
 static int stem_tc(const void* x, int x_is_bf16, const void* w_tc, const float* scale, const float* shift, void* y,
-                   int N, int Cin, int D, int H, int W, int stride_d, cudaStream_t st) {
+                   int N, int Cin, int D, int H, int W, int stride_d, int relu, cudaStream_t st) {
   StemParams p{};
+  p.floor = SSD3D_FLOOR(relu);
   p.N = N; p.D = D; p.H = H; p.W = W; p.sd = stride_d;
   p.Do = (D - 1) / stride_d + 1; p.Ho = (H - 1) / 2 + 1; p.Wo = (W - 1) / 2 + 1;
   // output tile: widest W extent (<= 64) that wastes < 15 % of its columns, then H, then D
@@ -379,17 +381,27 @@ static int stem_tc(const void* x, int x_is_bf16, const void* w_tc, const float* 
 #undef STEM_CASE
 }
 
-extern "C" int ssd3d_stem_conv_bn_relu(const void* x, int x_is_bf16, const void* w, const float* scale,
-                                       const float* shift, void* y, int N, int Cin, int D, int H, int W, int stride_d,
-                                       void* stream) {
+extern "C" int ssd3d_stem_conv_affine_simt(const void* x, int x_is_bf16, const void* w, const float* scale,
+                                           const float* shift, void* y, int N, int Cin, int D, int H, int W,
+                                           int stride_d, int relu, void* stream);
+
+extern "C" int ssd3d_stem_conv_affine(const void* x, int x_is_bf16, const void* w, const float* scale,
+                                      const float* shift, void* y, int N, int Cin, int D, int H, int W, int stride_d,
+                                      int relu, void* stream) {
   if (!x || !w || !scale || !shift || !y || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
   if (stride_d != 1 && stride_d != 2) return SSD3D_ERR_ARG;
   if (Cin < 1 || Cin > 4) return SSD3D_ERR_UNSUPPORTED;
   if (ssd3d_stem_tc_supported(x_is_bf16, Cin, W)) {
-    const int rc = stem_tc(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d,
+    const int rc = stem_tc(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, relu,
                            static_cast<cudaStream_t>(stream));
     if (rc != SSD3D_ERR_UNSUPPORTED) return rc;
   }
   // rows that TMA cannot address (W * elemsize not a multiple of 16 bytes): CUDA-core kernel
-  return ssd3d_stem_conv_bn_relu_simt(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, stream);
+  return ssd3d_stem_conv_affine_simt(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, relu, stream);
+}
+
+extern "C" int ssd3d_stem_conv_bn_relu(const void* x, int x_is_bf16, const void* w, const float* scale,
+                                       const float* shift, void* y, int N, int Cin, int D, int H, int W, int stride_d,
+                                       void* stream) {
+  return ssd3d_stem_conv_affine(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, 1, stream);
 }

@@ -21,6 +21,7 @@ struct GemmParams {
   int stages;        // smem ring depth
   int tmem_cols;     // power of two >= max(32, BN)
   int* nan_flag;
+  float floor;       // activation floor of the pointwise epilogue: 0 = ReLU, -inf = identity
   // ---- pointwise ----
   long long M;
   int Cout;
@@ -176,10 +177,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           for (int j = 0; j < 16; j += 4) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + c + j));
             const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + c + j));
-            const float r0 = relu_nan(__fadd_rn(__fmul_rn(__uint_as_float(v[j + 0]), sc.x), sh.x));
-            const float r1 = relu_nan(__fadd_rn(__fmul_rn(__uint_as_float(v[j + 1]), sc.y), sh.y));
-            const float r2 = relu_nan(__fadd_rn(__fmul_rn(__uint_as_float(v[j + 2]), sc.z), sh.z));
-            const float r3 = relu_nan(__fadd_rn(__fmul_rn(__uint_as_float(v[j + 3]), sc.w), sh.w));
+            const float r0 = clamp_floor(__fadd_rn(__fmul_rn(__uint_as_float(v[j + 0]), sc.x), sh.x), p.floor);
+            const float r1 = clamp_floor(__fadd_rn(__fmul_rn(__uint_as_float(v[j + 1]), sc.y), sh.y), p.floor);
+            const float r2 = clamp_floor(__fadd_rn(__fmul_rn(__uint_as_float(v[j + 2]), sc.z), sh.z), p.floor);
+            const float r3 = clamp_floor(__fadd_rn(__fmul_rn(__uint_as_float(v[j + 3]), sc.w), sh.w), p.floor);
             bad |= (r0 != r0) | (r1 != r1) | (r2 != r2) | (r3 != r3);
             o[j / 2] = pack_bf16x2(r0, r1);
             o[j / 2 + 1] = pack_bf16x2(r2, r3);
@@ -260,8 +261,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 using namespace ssd3d;
 
-extern "C" int ssd3d_pwconv_bn_relu(const void* x, const void* w, const float* scale, const float* shift, void* y,
-                                    int64_t M, int Cin, int Cout, int* nan_flag, void* stream) {
+extern "C" int ssd3d_pwconv_affine(const void* x, const void* w, const float* scale, const float* shift, void* y,
+                                   int64_t M, int Cin, int Cout, int relu, int* nan_flag, void* stream) {
   if (!x || !w || !scale || !shift || !y || M <= 0) return SSD3D_ERR_ARG;
   if (Cin <= 0 || (Cin % 32) || Cout <= 0 || (Cout % 16)) return SSD3D_ERR_ARG;
   const int BK = (Cin % 64 == 0) ? 64 : 32;
@@ -278,6 +279,7 @@ extern "C" int ssd3d_pwconv_bn_relu(const void* x, const void* w, const float* s
   p.stages = p.num_kb < 4 ? p.num_kb : 4;
   p.tmem_cols = pow2_ceil(BN < 32 ? 32 : BN);
   p.nan_flag = nan_flag;
+  p.floor = SSD3D_FLOOR(relu);
   p.M = M;
   p.Cout = Cout;
   p.y = static_cast<__nv_bfloat16*>(y);
@@ -302,6 +304,11 @@ extern "C" int ssd3d_pwconv_bn_relu(const void* x, const void* w, const float* s
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (BK == 64) return launch_gemm<64, false>(tmA, tmB, p, grid, st);
   return launch_gemm<32, false>(tmA, tmB, p, grid, st);
+}
+
+extern "C" int ssd3d_pwconv_bn_relu(const void* x, const void* w, const float* scale, const float* shift, void* y,
+                                    int64_t M, int Cin, int Cout, int* nan_flag, void* stream) {
+  return ssd3d_pwconv_affine(x, w, scale, shift, y, M, Cin, Cout, 1, nan_flag, stream);
 }
 
 // conv_head_tc.cu: halo-tile kernel (one activation load per 64-channel chunk)

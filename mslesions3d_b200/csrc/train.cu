@@ -1,0 +1,989 @@
+// Training-step kernels of the SSD3D network (LSSD3D.training_step, ssd3d.py:467-531; the reference gets
+// them from torch autograd over nn.Conv3d / nn.BatchNorm3d / nn.ReLU, mobilenet.py:26-49, ssd3d.py:131-167):
+//   * train-mode BatchNorm: per-channel batch statistics of a raw conv output (two-stage, deterministic),
+//     running-stat update, normalise + ReLU; and its backward (ReLU mask recomputed from the saved raw
+//     output, dgamma / dbeta reductions, dz)
+//   * weight gradients of the pointwise, head (3x3x3) and stem (3x3x3, NCDHW input) convolutions as ONE
+//     split-M implicit GEMM   dW[n][k] = sum_m dz[m][n] * im2col(x)[m][k]   on mma.sync bf16 tensor cores
+//     (operands are channels-last, i.e. M-major: fragments come from ldmatrix.trans), fixed-order reduction
+//   * data gradient of the head convs (transposed 3x3x3 conv, 16 -> C channels) as an mma.sync implicit GEMM
+//   * depthwise 3x3x3 data and weight gradients (HBM-bound CUDA-core kernels, 16-byte channel vectors)
+//   * packing of d(loss)/d(locs, scores) into the head's (voxel, 16) bf16 gradient rows
+//   * fused Adam over the flat parameter / gradient buffers (ssd3d.py:704-722)
+// Activations and activation gradients are channels-last bf16; every reduction accumulates in fp32 (fp64
+// for the final cross-block sums) and is bit-reproducible run to run.
+#include "common.cuh"
+#include "../../include/ssd3d_b200.h"
+
+namespace ssd3d {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ uint4 ld_nc16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void unpack8f(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8f(const float (&v)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  return o;
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  *reinterpret_cast<float4*>(&f[0]) = __ldg(reinterpret_cast<const float4*>(p));
+  *reinterpret_cast<float4*>(&f[4]) = __ldg(reinterpret_cast<const float4*>(p + 4));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column reductions over a channels-last (M, C) bf16 matrix; thread = 8 channels x a strided set of rows.
+//   MODE 0 (BN forward) : s0 = sum z,  s1 = sum z^2
+//   MODE 1 (BN backward): dy = g * [z*scale+shift > 0], xhat = (z-mean)*invstd;  s0 = sum dy, s1 = sum dy*xhat
+// partial[(block*2 + {0,1}) * C + c]
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) colreduce_kernel(const bf16* __restrict__ z, const bf16* __restrict__ g,
+                                                        const float* __restrict__ scale,
+                                                        const float* __restrict__ shift,
+                                                        const float* __restrict__ mean,
+                                                        const float* __restrict__ invstd, long long M, int C,
+                                                        long long rows_per_block, float* __restrict__ partial) {
+  __shared__ float red[256 * 16];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int CV = C >> 3;
+  const int RP = blockDim.x / CV;
+  const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
+  const int c0 = cv << 3;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+  float sc[8], sh[8], mu[8], is[8];
+  if (MODE == 1) {
+    load8(scale + c0, sc); load8(shift + c0, sh); load8(mean + c0, mu); load8(invstd + c0, is);
+  }
+  const long long m_begin = (long long)blockIdx.x * rows_per_block;
+  const long long m_end = (m_begin + rows_per_block < M) ? m_begin + rows_per_block : M;
+  for (long long m = m_begin + r; m < m_end; m += RP) {
+    float zf[8];
+    unpack8f(ld_nc16(z + m * C + c0), zf);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s0[j] += zf[j]; s1[j] = fmaf(zf[j], zf[j], s1[j]); }
+    } else {
+      float gf[8];
+      unpack8f(ld_nc16(g + m * C + c0), gf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = __fadd_rn(__fmul_rn(zf[j], sc[j]), sh[j]);
+        const float dy = (pre > 0.f) ? gf[j] : 0.f;
+        const float xh = (zf[j] - mu[j]) * is[j];
+        s0[j] += dy;
+        s1[j] = fmaf(dy, xh, s1[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s0[j]; red[threadIdx.x * 16 + 8 + j] = s1[j]; }
+  __syncthreads();
+  if (r == 0) {
+    for (int rr = 1; rr < RP; ++rr) {
+      const float* src = red + (rr * CV + cv) * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s0[j] += src[j]; s1[j] += src[8 + j]; }
+    }
+    float* dst = partial + (size_t)blockIdx.x * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dst[c0 + j] = s0[j]; dst[C + c0 + j] = s1[j]; }
+  }
+}
+
+// BN forward finalize: batch mean / biased variance -> scale = gamma*invstd, shift = beta - mean*scale,
+// running statistics (momentum update with the unbiased variance, as nn.BatchNorm3d in train mode).
+__global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int B, int C, long long M,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                       float momentum, float* __restrict__ running_mean,
+                                       float* __restrict__ running_var, float* __restrict__ scale,
+                                       float* __restrict__ shift, float* __restrict__ mean,
+                                       float* __restrict__ invstd) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < B; ++b) {
+    s += (double)partial[(size_t)b * 2 * C + c];
+    q += (double)partial[(size_t)b * 2 * C + C + c];
+  }
+  const double mu = s / (double)M;
+  double var = q / (double)M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float istd = (float)(1.0 / sqrt(var + (double)eps));
+  const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+  const float sc = ga * istd;
+  scale[c] = sc;
+  shift[c] = be - (float)mu * sc;
+  mean[c] = (float)mu;
+  invstd[c] = istd;
+  if (running_mean && running_var) {
+    const double unbiased = (M > 1) ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mu);
+    running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+  }
+}
+
+// BN backward finalize: dbeta = sum dy, dgamma = sum dy*xhat (written into the parameter gradients).
+__global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int B, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < B; ++b) {
+    s += (double)partial[(size_t)b * 2 * C + c];
+    q += (double)partial[(size_t)b * 2 * C + C + c];
+  }
+  dbeta[c] = (float)s;
+  dgamma[c] = (float)q;
+}
+
+// a = relu(z*scale + shift)   (train-mode BN + ReLU on the raw conv output, mobilenet.py:29-30,44-45)
+__global__ void __launch_bounds__(256) bn_apply_relu_kernel(const bf16* __restrict__ z,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, bf16* __restrict__ a,
+                                                            long long total_vec, int CV, int* nan_flag) {
+  pdl_wait();
+  pdl_launch_dependents();
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % CV) << 3;
+    float zf[8], sc[8], sh[8], o[8];
+    unpack8f(ld_nc16(z + i * 8), zf);
+    load8(scale + c0, sc);
+    load8(shift + c0, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = relu_nan(__fadd_rn(__fmul_rn(zf[j], sc[j]), sh[j]));
+      bad |= (o[j] != o[j]);
+    }
+    *reinterpret_cast<uint4*>(a + i * 8) = pack8f(o);
+  }
+  if (bad && nan_flag) atomicOr(nan_flag, SSD3D_NAN_BACKBONE);
+}
+
+// dz = scale * (dy - dbeta/M - xhat * dgamma/M),  dy = g * [z*scale+shift > 0]      (dz may alias g)
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const bf16* __restrict__ z, const bf16* g,
+                                                                const float* __restrict__ scale,
+                                                                const float* __restrict__ shift,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd,
+                                                                const float* __restrict__ dgamma,
+                                                                const float* __restrict__ dbeta, float inv_m,
+                                                                bf16* dz, long long total_vec, int CV) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % CV) << 3;
+    float zf[8], gf[8], sc[8], sh[8], mu[8], is[8], dg[8], db[8], o[8];
+    unpack8f(ld_nc16(z + i * 8), zf);
+    unpack8f(*reinterpret_cast<const uint4*>(g + i * 8), gf);
+    load8(scale + c0, sc); load8(shift + c0, sh); load8(mean + c0, mu); load8(invstd + c0, is);
+    load8(dgamma + c0, dg); load8(dbeta + c0, db);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float pre = __fadd_rn(__fmul_rn(zf[j], sc[j]), sh[j]);
+      const float dy = (pre > 0.f) ? gf[j] : 0.f;
+      const float xh = (zf[j] - mu[j]) * is[j];
+      o[j] = sc[j] * (dy - db[j] * inv_m - xh * (dg[j] * inv_m));
+    }
+    *reinterpret_cast<uint4*>(dz + i * 8) = pack8f(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mma.sync helpers (bf16 x bf16 -> fp32, m16n8k16)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient as a split-M implicit GEMM:  dW[n][k] = sum_m dz[m][n] * X[m][k]
+//   MODE 0 pointwise : X[m][k] = x[m*C + k], zero for k >= C                        (K = Cin rounded up to 64)
+//   MODE 1 head 3^3  : k = tap*C + c, X = x[voxel(m) + (tap offsets - 1)][c], zero outside the map
+//   MODE 2 stem 3^3  : k = ci*27 + tap, X = bf16(x_ncdhw[n][ci][sd*do+kd-1][2*ho+kh-1][2*wo+kw-1])
+// CTA: 128 threads, output tile NT (n) x 64 (k), rows [split*rows_per_split, ...) in chunks of 64.
+// Both operands sit in smem as [m][n] / [m][k] (M-major); A (= dz^T) and B fragments are ldmatrix.trans.
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  const bf16* dz;
+  int ldz;
+  long long M;
+  int K;                      // padded to a multiple of 64
+  const void* x;
+  int x_is_bf16;              // stem only
+  int C;                      // pointwise: Cin (row pitch); head: channels
+  int N, D, H, W;             // head: feature map; stem: input volume
+  int Do, Ho, Wo, sd, Cin;    // stem
+  long long rows_per_split;
+  int n_pad;                  // rows of one partial slab (multiple of NT)
+  float* partial;             // [splits][n_pad][K]
+};
+
+template <int NT, int MODE>
+__global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
+  constexpr int ZP = NT + 8;          // padded row pitch (elements): conflict-free ldmatrix
+  constexpr int XP = 72;
+  constexpr int ZCH = NT / 8;         // 16-byte chunks per dz row
+  constexpr int ZPT = (64 * ZCH + 127) / 128;
+  __shared__ __align__(16) bf16 sZ[64 * ZP];
+  __shared__ __align__(16) bf16 sX[64 * XP];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k0 = blockIdx.x * 64;
+  const int n0 = blockIdx.y * NT;
+  const long long m_begin = (long long)blockIdx.z * p.rows_per_split;
+  const long long m_end = (m_begin + p.rows_per_split < p.M) ? m_begin + p.rows_per_split : p.M;
+
+  // ---- per-thread constants of the X gather ----
+  const int xcc = tid & 7;            // 16-byte chunk (8 k values) inside the 64-wide k tile
+  const int xrow0 = tid >> 3;         // rows xrow0 + 16*i, i = 0..3
+  int tap_d = 0, tap_h = 0, tap_w = 0, cbase = 0;       // MODE 1
+  int e_off[8];                                          // MODE 2: per element (ci, tap) -> offset, or -1
+  int e_kd[8], e_kh[8], e_kw[8];
+  if (MODE == 1) {
+    const int tap = k0 / p.C;
+    cbase = k0 - tap * p.C + xcc * 8;
+    tap_d = tap / 9 - 1; tap_h = (tap / 3) % 3 - 1; tap_w = tap % 3 - 1;
+  }
+  if (MODE == 2) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + xcc * 8 + e;
+      const int ci = k / 27, tap = k - ci * 27;
+      e_off[e] = (ci < p.Cin) ? ci : -1;
+      e_kd[e] = tap / 9 - 1; e_kh[e] = (tap / 3) % 3 - 1; e_kw[e] = tap % 3 - 1;
+    }
+  }
+
+  uint4 zr[ZPT], xr[4];
+  auto load_tiles = [&](long long m0) {
+#pragma unroll
+    for (int i = 0; i < ZPT; ++i) {
+      const int q = tid + i * 128;
+      const int row = q / ZCH, cc = q % ZCH;
+      const long long m = m0 + row;
+      zr[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (q < 64 * ZCH && m < m_end) zr[i] = ld_nc16(p.dz + m * p.ldz + n0 + cc * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long m = m0 + xrow0 + 16 * i;
+      xr[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (m >= m_end) continue;
+      if (MODE == 0) {
+        if (k0 + xcc * 8 < p.C) xr[i] = ld_nc16(static_cast<const bf16*>(p.x) + m * p.C + k0 + xcc * 8);
+      } else if (MODE == 1) {
+        long long t = m;
+        const int w = (int)(t % p.W) + tap_w; t /= p.W;
+        const int h = (int)(t % p.H) + tap_h; t /= p.H;
+        const int d = (int)(t % p.D) + tap_d; t /= p.D;
+        if ((unsigned)w < (unsigned)p.W && (unsigned)h < (unsigned)p.H && (unsigned)d < (unsigned)p.D)
+          xr[i] = ld_nc16(static_cast<const bf16*>(p.x) + ((((long long)t * p.D + d) * p.H + h) * p.W + w) * p.C + cbase);
+      } else {
+        long long t = m;
+        const int wo = (int)(t % p.Wo); t /= p.Wo;
+        const int ho = (int)(t % p.Ho); t /= p.Ho;
+        const int dz_ = (int)(t % p.Do); t /= p.Do;
+        const long long plane = (long long)p.D * p.H * p.W;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[e] = 0.f;
+          const int d = dz_ * p.sd + e_kd[e], h = ho * 2 + e_kh[e], w = wo * 2 + e_kw[e];
+          if (e_off[e] >= 0 && (unsigned)d < (unsigned)p.D && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W) {
+            const long long idx = ((long long)t * p.Cin + e_off[e]) * plane + ((long long)d * p.H + h) * p.W + w;
+            v[e] = p.x_is_bf16 ? __bfloat162float(static_cast<const bf16*>(p.x)[idx])
+                               : __ldg(static_cast<const float*>(p.x) + idx);
+          }
+        }
+        xr[i] = pack8f(v);
+      }
+    }
+  };
+
+  float acc[NT / 16][2][4];
+#pragma unroll
+  for (int a = 0; a < NT / 16; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+  const uint32_t sZ_u = smem_u32(sZ), sX_u = smem_u32(sX);
+  const int lq = lane >> 3, lr = lane & 7;
+  if (m_begin < m_end) load_tiles(m_begin);
+  for (long long m0 = m_begin; m0 < m_end; m0 += 64) {
+    __syncthreads();                       // the previous chunk's fragments have been read
+#pragma unroll
+    for (int i = 0; i < ZPT; ++i) {
+      const int q = tid + i * 128;
+      if (q < 64 * ZCH) *reinterpret_cast<uint4*>(&sZ[(q / ZCH) * ZP + (q % ZCH) * 8]) = zr[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(&sX[(xrow0 + 16 * i) * XP + xcc * 8]) = xr[i];
+    __syncthreads();
+    if (m0 + 64 < m_end) load_tiles(m0 + 64);   // global loads of the next chunk fly during the MMAs
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int kk = ks * 16;
+      uint32_t bfr[4];
+      // B (k16 x 2 n8 tiles): matrices {rows kk..+7 | kk+8..+15} x {cols w*16 | w*16+8}
+      ldsm_x4_t(sX_u + (uint32_t)(((kk + (lq & 1) * 8 + lr) * XP + warp * 16 + (lq >> 1) * 8) * 2), bfr);
+#pragma unroll
+      for (int a = 0; a < NT / 16; ++a) {
+        uint32_t afr[4];
+        // A = dz^T (16 n x k16): matrices {n 0-7 | 8-15} x {rows kk..+7 | kk+8..+15}, transposed on load
+        ldsm_x4_t(sZ_u + (uint32_t)(((kk + (lq >> 1) * 8 + lr) * ZP + a * 16 + (lq & 1) * 8) * 2), afr);
+        mma_bf16(acc[a][0], afr, bfr[0], bfr[1]);
+        mma_bf16(acc[a][1], afr, bfr[2], bfr[3]);
+      }
+    }
+  }
+  float* out = p.partial + ((size_t)blockIdx.z * p.n_pad + n0) * p.K + k0 + warp * 16;
+#pragma unroll
+  for (int a = 0; a < NT / 16; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int n = a * 16 + (lane >> 2), k = b * 8 + (lane & 3) * 2;
+      *reinterpret_cast<float2*>(out + (size_t)n * p.K + k) = make_float2(acc[a][b][0], acc[a][b][1]);
+      *reinterpret_cast<float2*>(out + (size_t)(n + 8) * p.K + k) = make_float2(acc[a][b][2], acc[a][b][3]);
+    }
+}
+
+// out[r*dst_ld + c] = sum over splits (ascending) of partial[s][r*src_ld + c],  c < cols
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int S,
+                                                           long long slab, int rows, int cols, int src_ld,
+                                                           int dst_ld, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += partial[(size_t)k * slab + (size_t)r * src_ld + c];
+  out[(size_t)r * dst_ld + c] = s;
+}
+
+// head: partial [S][16][27*C] (k = tap*C + c) -> loc (n_loc, C, 27) and class (n_cls, C, 27) conv weight grads
+__global__ void __launch_bounds__(256) head_wgrad_finalize_kernel(const float* __restrict__ partial, int S, int C,
+                                                                  int n_loc, int n_cls, float* __restrict__ dw_loc,
+                                                                  float* __restrict__ dw_cls) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long total = (long long)(n_loc + n_cls) * C * 27;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int tap = (int)(i % 27);
+  const int c = (int)((i / 27) % C);
+  const int n = (int)(i / (27ll * C));
+  const size_t slab = (size_t)16 * 27 * C;
+  float s = 0.f;
+  for (int k = 0; k < S; ++k) s += partial[k * slab + (size_t)n * 27 * C + (size_t)tap * C + c];
+  if (n < n_loc) dw_loc[((size_t)n * C + c) * 27 + tap] = s;
+  else dw_cls[((size_t)(n - n_loc) * C + c) * 27 + tap] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head gradient rows: dO[m][b*6+j] = dlocs[n][off + v*bpl + b][j], dO[m][bpl*6 + b*ncls + k] = dscores[...][k]
+// (the column order of the fused head GEMM, gemm_tc.cu), zero padded to 16 columns; bias gradients are
+// the column sums (second stage: sum_partials).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_grad_pack_kernel(const float* __restrict__ dlocs,
+                                                             const float* __restrict__ dscores, long long P,
+                                                             long long prior_off, long long V, int N, int bpl,
+                                                             int n_classes, bf16* __restrict__ dO,
+                                                             float* __restrict__ bias_partial) {
+  __shared__ float red[256][16];
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long M = (long long)N * V;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) {
+    const long long n = m / V, vox = m - n * V;
+    const float* lp = dlocs + (n * P + prior_off + vox * bpl) * 6;
+    const float* sp = dscores + (n * P + prior_off + vox * bpl) * n_classes;
+    const int nl = bpl * 6, nc = bpl * n_classes;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < nl) v[j] = lp[j];
+      else if (j < nl + nc) v[j] = sp[j - nl];
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+    uint4* dst = reinterpret_cast<uint4*>(dO + m * 16);
+    dst[0] = pack8f(lo);
+    dst[1] = pack8f(hi);
+  }
+  // block-level column sums of the fp32 values (bias gradient), fixed order
+#pragma unroll
+  for (int j = 0; j < 16; ++j) red[threadIdx.x][j] = v[j];
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float s = 0.f;
+    for (int t = 0; t < 256; ++t) s += red[t][threadIdx.x];
+    bias_partial[(size_t)blockIdx.x * 16 + threadIdx.x] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head data gradient: dx[m][c] = sum_tap sum_n dO[voxel(m) - (tap offsets - 1)][n] * w[n][tap*C + c]  (+ addend)
+// implicit GEMM, M x C output, K = 27 taps x 16; CTA = 64 rows x 64 channels, 4 warps (16 rows each).
+// ------------------------------------------------------------------------------------------------
+struct HeadDgradParams {
+  const bf16* dO;        // (M, 16)
+  const bf16* w;         // (16, 27*C)
+  const bf16* addend;    // (M, C) or null
+  bf16* dx;              // (M, C)
+  int N, D, H, W, C;
+  long long M;
+};
+
+__global__ void __launch_bounds__(128) head_dgrad_kernel(const HeadDgradParams p) {
+  constexpr int BP = 72, AP = 24;
+  extern __shared__ __align__(16) uint8_t hd_smem[];
+  bf16* sB = reinterpret_cast<bf16*>(hd_smem);                 // [27*16][BP]
+  bf16* sA = sB + 27 * 16 * BP;                                // [2][64][AP]
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long m0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  for (int q = tid; q < 27 * 16 * 8; q += 128) {
+    const int row = q >> 3, cc = q & 7;          // row = tap*16 + n
+    const int tap = row >> 4, n = row & 15;
+    *reinterpret_cast<uint4*>(&sB[row * BP + cc * 8]) =
+        ld_nc16(p.w + (size_t)n * 27 * p.C + (size_t)tap * p.C + c0 + cc * 8);
+  }
+  // gather role: row = tid/2, half = tid%2
+  const int arow = tid >> 1, ahalf = tid & 1;
+  const long long am = m0 + arow;
+  int aw = 0, ah = 0, ad = 0;
+  long long an = 0;
+  if (am < p.M) {
+    long long t = am;
+    aw = (int)(t % p.W); t /= p.W;
+    ah = (int)(t % p.H); t /= p.H;
+    ad = (int)(t % p.D); t /= p.D;
+    an = t;
+  }
+  float acc[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+  const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+  const int lq = lane >> 3, lr = lane & 7;
+  for (int tap = 0; tap < 27; ++tap) {
+    const int buf = tap & 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    {
+      const int d = ad - (tap / 9 - 1), h = ah - ((tap / 3) % 3 - 1), w = aw - (tap % 3 - 1);
+      if (am < p.M && (unsigned)d < (unsigned)p.D && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
+        v = ld_nc16(p.dO + ((((long long)an * p.D + d) * p.H + h) * p.W + w) * 16 + ahalf * 8);
+    }
+    *reinterpret_cast<uint4*>(&sA[(buf * 64 + arow) * AP + ahalf * 8]) = v;
+    __syncthreads();
+    uint32_t afr[4];
+    // A (16 rows x k16): matrices {rows 0-7 | 8-15} x {cols 0-7 | 8-15}
+    ldsm_x4(sA_u + (uint32_t)(((buf * 64 + warp * 16 + (lq & 1) * 8 + lr) * AP + (lq >> 1) * 8) * 2), afr);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      uint32_t bfr[4];
+      ldsm_x4_t(sB_u + (uint32_t)(((tap * 16 + (lq & 1) * 8 + lr) * BP + jj * 16 + (lq >> 1) * 8) * 2), bfr);
+      mma_bf16(acc[jj * 2], afr, bfr[0], bfr[1]);
+      mma_bf16(acc[jj * 2 + 1], afr, bfr[2], bfr[3]);
+    }
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const long long m = m0 + warp * 16 + (lane >> 2) + half * 8;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int c = c0 + a * 8 + (lane & 3) * 2;
+      float v0 = acc[a][half * 2], v1 = acc[a][half * 2 + 1];
+      if (p.addend) {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(p.addend + m * p.C + c);
+        v0 += bf16_lo(u);
+        v1 += bf16_hi(u);
+      }
+      *reinterpret_cast<uint32_t*>(p.dx + m * p.C + c) = pack_bf16x2(v0, v1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise 3x3x3 backward.  forward: y[o][c] = sum_k x[S*o + k - 1][c] * w[k][c]
+// ------------------------------------------------------------------------------------------------
+// data: dx[i][c] = sum_{k : (i + 1 - k) % S == 0} dz[(i + 1 - k)/S][c] * w[k][c];  thread = 8 channels x 1 voxel
+template <int S>
+__global__ void __launch_bounds__(256) dw_dgrad_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ w,
+                                                       bf16* __restrict__ dx, int N, int C, int D, int H, int W,
+                                                       int Do, int Ho, int Wo, long long total) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int CV = C >> 3;
+  const int cv = (int)(gid % CV);
+  long long r = gid / CV;
+  const int wi = (int)(r % W); r /= W;
+  const int hi = (int)(r % H); r /= H;
+  const int di = (int)(r % D);
+  const int n = (int)(r / D);
+  const int c0 = cv << 3;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd) {
+    const int td = di + 1 - kd;
+    if (td < 0 || (S == 2 && (td & 1))) continue;
+    const int od = td / S;
+    if (od >= Do) continue;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int th = hi + 1 - kh;
+      if (th < 0 || (S == 2 && (th & 1))) continue;
+      const int oh = th / S;
+      if (oh >= Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tw = wi + 1 - kw;
+        if (tw < 0 || (S == 2 && (tw & 1))) continue;
+        const int ow = tw / S;
+        if (ow >= Wo) continue;
+        float gf[8], wf[8];
+        unpack8f(ld_nc16(dz + ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * C + c0), gf);
+        unpack8f(ld_nc16(w + ((kd * 3 + kh) * 3 + kw) * C + c0), wf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(gf[j], wf[j], acc[j]);
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + gid * 8) = pack8f(acc);
+}
+
+// weight: dw[c][k] = sum_o dz[o][c] * x[S*o + k - 1][c].  thread = (8 channels, kd, voxel lane g): 9 taps x 8
+// channels of accumulators; block partial [C][27] after a fixed-order reduction over the voxel lanes.
+template <int S>
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x,
+                                                       int N, int C, int D, int H, int W, int Do, int Ho, int Wo,
+                                                       long long Mo, long long vox_per_block, int G,
+                                                       float* __restrict__ partial) {
+  __shared__ float red[256 * 8];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int CV = C >> 3;
+  const int cv = threadIdx.x % CV;
+  const int kd = (threadIdx.x / CV) % 3;
+  const int g = threadIdx.x / (CV * 3);
+  const int c0 = cv << 3;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const long long o_begin = (long long)blockIdx.x * vox_per_block;
+  const long long o_end = (o_begin + vox_per_block < Mo) ? o_begin + vox_per_block : Mo;
+  for (long long o = o_begin + g; o < o_end; o += G) {
+    long long t = o;
+    const int ow = (int)(t % Wo); t /= Wo;
+    const int oh = (int)(t % Ho); t /= Ho;
+    const int od = (int)(t % Do); t /= Do;
+    const int di = od * S + kd - 1;
+    if ((unsigned)di >= (unsigned)D) continue;
+    float gf[8];
+    unpack8f(ld_nc16(dz + o * C + c0), gf);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = oh * S + kh - 1;
+      if ((unsigned)hi >= (unsigned)H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = ow * S + kw - 1;
+        if ((unsigned)wi >= (unsigned)W) continue;
+        float xf[8];
+        unpack8f(ld_nc16(x + ((((long long)t * D + di) * H + hi) * W + wi) * C + c0), xf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[kh * 3 + kw][j] = fmaf(gf[j], xf[j], acc[kh * 3 + kw][j]);
+      }
+    }
+  }
+  float* dst = partial + (size_t)blockIdx.x * C * 27;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    if (G > 1) {
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = acc[t][j];
+      __syncthreads();
+      if (g == 0) {
+        for (int gg = 1; gg < G; ++gg) {
+          const float* src = red + (size_t)(gg * CV * 3 + kd * CV + cv) * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[t][j] += src[j];
+        }
+      }
+    }
+    if (g == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[(size_t)(c0 + j) * 27 + kd * 9 + t] = acc[t][j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics: L2 weight decay folded into the gradient, bias-corrected moments)
+// over flat buffers; elements >= bias_start use lr_bias (the reference's "biases at twice the lr" group).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n,
+                                                   long long bias_start, float lr, float lr_bias, float beta1,
+                                                   float beta2, float eps, float weight_decay, float bc1,
+                                                   float bc2_sqrt, float grad_scale) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    const float gi = g[i] * grad_scale + weight_decay * pi;
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float step = (i >= bias_start ? lr_bias : lr) / bc1;
+    p[i] = pi - step * (mi / denom);
+  }
+}
+
+static inline int grid_for(long long total, int block, int cap) {
+  long long b = (total + block - 1) / block;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace ssd3d
+
+using namespace ssd3d;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+static const int COLRED_MAX_BLOCKS = 592;   // 4 x 148 SMs
+
+static int colreduce_plan(long long M, int C, int* threads, long long* rows_per_block) {
+  const int CV = C / 8;
+  if (C <= 0 || (C & 7) || CV > 256) return -1;
+  const int RP = 256 / CV;
+  *threads = CV * RP;
+  long long B = (M + RP * 4 - 1) / (RP * 4);
+  if (B > COLRED_MAX_BLOCKS) B = COLRED_MAX_BLOCKS;
+  if (B < 1) B = 1;
+  long long rpb = (M + B - 1) / B;
+  *rows_per_block = rpb;
+  return (int)((M + rpb - 1) / rpb);
+}
+
+extern "C" int64_t ssd3d_bn_workspace_bytes(int C) { return (int64_t)COLRED_MAX_BLOCKS * 2 * C * 4; }
+
+extern "C" int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* gamma, const float* beta, float eps,
+                                  float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                                  float* mean, float* invstd, void* a, int* nan_flag, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  if (!z || !scale || !shift || !mean || !invstd || !workspace || M <= 0) return SSD3D_ERR_ARG;
+  int threads;
+  long long rpb;
+  const int B = colreduce_plan(M, C, &threads, &rpb);
+  if (B < 0 || workspace_bytes < (int64_t)B * 2 * C * 4) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  const bf16* zp = static_cast<const bf16*>(z);
+  SSD3D_LAUNCH_PDL(colreduce_kernel<0>, dim3(B), dim3(threads), 0, st, zp, (const bf16*)nullptr, (const float*)nullptr,
+                   (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (long long)M, C, rpb, partial);
+  SSD3D_LAUNCH_PDL(bn_finalize_fwd_kernel, dim3((C + 127) / 128), dim3(128), 0, st, (const float*)partial, B, C,
+                   (long long)M, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
+  if (a) {
+    const long long total_vec = (long long)M * (C / 8);
+    SSD3D_LAUNCH_PDL(bn_apply_relu_kernel, dim3(grid_for(total_vec, 256, 148 * 8)), dim3(256), 0, st, zp,
+                     (const float*)scale, (const float*)shift, static_cast<bf16*>(a), total_vec, C / 8, nan_flag);
+  }
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, int C, const float* scale,
+                                 const float* shift, const float* mean, const float* invstd, float* dgamma,
+                                 float* dbeta, void* dz, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!z || !grad_a || !scale || !shift || !mean || !invstd || !dgamma || !dbeta || !dz || !workspace || M <= 0)
+    return SSD3D_ERR_ARG;
+  int threads;
+  long long rpb;
+  const int B = colreduce_plan(M, C, &threads, &rpb);
+  if (B < 0 || workspace_bytes < (int64_t)B * 2 * C * 4) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  const bf16* zp = static_cast<const bf16*>(z);
+  const bf16* gp = static_cast<const bf16*>(grad_a);
+  SSD3D_LAUNCH_PDL(colreduce_kernel<1>, dim3(B), dim3(threads), 0, st, zp, gp, scale, shift, mean, invstd, (long long)M,
+                   C, rpb, partial);
+  SSD3D_LAUNCH_PDL(bn_finalize_bwd_kernel, dim3((C + 127) / 128), dim3(128), 0, st, (const float*)partial, B, C, dgamma,
+                   dbeta);
+  const long long total_vec = (long long)M * (C / 8);
+  SSD3D_LAUNCH_PDL(bn_relu_bwd_apply_kernel, dim3(grid_for(total_vec, 256, 148 * 8)), dim3(256), 0, st, zp, gp, scale,
+                   shift, mean, invstd, (const float*)dgamma, (const float*)dbeta, (float)(1.0 / (double)M),
+                   static_cast<bf16*>(dz), total_vec, C / 8);
+  return SSD3D_OK;
+}
+
+// ---- weight gradients ------------------------------------------------------------------------------
+static int wgrad_splits(long long M, int tiles) {
+  long long s = (592 + tiles - 1) / tiles;
+  const long long chunks = (M + 63) / 64;
+  if (s > chunks) s = chunks;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+extern "C" int64_t ssd3d_wgrad_workspace_bytes(int64_t M, int n_out, int K) {
+  const int kp = (K + 63) / 64 * 64;
+  const int np = n_out <= 16 ? 16 : (n_out <= 32 ? 32 : (n_out + 63) / 64 * 64);
+  const int nt = np <= 16 ? 16 : (np <= 32 ? 32 : 64);
+  const int S = wgrad_splits(M, (kp / 64) * (np / nt));
+  return (int64_t)S * np * kp * 4;
+}
+
+template <int NT, int MODE>
+static int run_wgrad(WgradParams& p, int n_out, cudaStream_t st, int* splits_out) {
+  const int tiles = (p.K / 64) * (p.n_pad / NT);
+  const int S = wgrad_splits(p.M, tiles);
+  long long rps = (p.M + S - 1) / S;
+  rps = (rps + 63) / 64 * 64;
+  p.rows_per_split = rps;
+  const int S2 = (int)((p.M + rps - 1) / rps);
+  dim3 grid((unsigned)(p.K / 64), (unsigned)(p.n_pad / NT), (unsigned)S2);
+  SSD3D_LAUNCH_PDL((wgrad_kernel<NT, MODE>), grid, dim3(128), 0, st, p);
+  *splits_out = S2;
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_pwconv_wgrad(const void* dz, const void* x, int64_t M, int Cin, int Cout, float* dw,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!dz || !x || !dw || !workspace || M <= 0) return SSD3D_ERR_ARG;
+  if (Cin <= 0 || (Cin % 32) || Cout <= 0 || (Cout % 64)) return SSD3D_ERR_ARG;
+  if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, Cout, Cin)) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WgradParams p{};
+  p.dz = static_cast<const bf16*>(dz); p.ldz = Cout; p.M = M;
+  p.K = (Cin + 63) / 64 * 64;
+  p.x = x; p.C = Cin; p.n_pad = Cout;
+  p.partial = static_cast<float*>(workspace);
+  int S = 0;
+  const int rc = run_wgrad<64, 0>(p, Cout, st, &S);
+  if (rc) return rc;
+  const long long total = (long long)Cout * Cin;
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+                   (const float*)p.partial, S, (long long)p.n_pad * p.K, Cout, Cin, p.K, Cin, dw);
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int D, int H, int W, int n_loc, int n_cls,
+                                float* dw_loc, float* dw_cls, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
+  if (!dO || !x || !dw_loc || !dw_cls || !workspace || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
+  if (C <= 0 || (C % 64) || n_loc + n_cls > 16 || n_loc <= 0 || n_cls <= 0) return SSD3D_ERR_UNSUPPORTED;
+  const long long M = (long long)N * D * H * W;
+  if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, 16, 27 * C)) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WgradParams p{};
+  p.dz = static_cast<const bf16*>(dO); p.ldz = 16; p.M = M;
+  p.K = 27 * C;
+  p.x = x; p.C = C; p.N = N; p.D = D; p.H = H; p.W = W; p.n_pad = 16;
+  p.partial = static_cast<float*>(workspace);
+  int S = 0;
+  const int rc = run_wgrad<16, 1>(p, 16, st, &S);
+  if (rc) return rc;
+  const long long total = (long long)(n_loc + n_cls) * C * 27;
+  SSD3D_LAUNCH_PDL(head_wgrad_finalize_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+                   (const float*)p.partial, S, C, n_loc, n_cls, dw_loc, dw_cls);
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W,
+                                int stride_d, float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!dz || !x || !dw || !workspace || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
+  if (Cin < 1 || Cin > 4 || (stride_d != 1 && stride_d != 2)) return SSD3D_ERR_UNSUPPORTED;
+  const int Do = (D - 1) / stride_d + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long M = (long long)N * Do * Ho * Wo;
+  const int K = (27 * Cin + 63) / 64 * 64;
+  if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, 32, K)) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WgradParams p{};
+  p.dz = static_cast<const bf16*>(dz); p.ldz = 32; p.M = M;
+  p.K = K;
+  p.x = x; p.x_is_bf16 = x_is_bf16; p.N = N; p.D = D; p.H = H; p.W = W;
+  p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.sd = stride_d; p.Cin = Cin; p.n_pad = 32;
+  p.partial = static_cast<float*>(workspace);
+  int S = 0;
+  const int rc = run_wgrad<32, 2>(p, 32, st, &S);
+  if (rc) return rc;
+  const long long total = 32ll * 27 * Cin;
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+                   (const float*)p.partial, S, (long long)p.n_pad * p.K, 32, 27 * Cin, p.K, 27 * Cin, dw);
+  return SSD3D_OK;
+}
+
+// ---- head gradient rows + bias gradient, head data gradient ---------------------------------------------
+extern "C" int64_t ssd3d_head_grad_workspace_bytes(int N, int D, int H, int W) {
+  const long long M = (long long)N * D * H * W;
+  return (int64_t)((M + 255) / 256) * 16 * 4;
+}
+
+extern "C" int ssd3d_head_grad_pack(const float* dlocs, const float* dscores, int N, int D, int H, int W, int bpl,
+                                    int n_classes, int64_t P, int64_t prior_offset, void* dO, float* dbias_loc,
+                                    float* dbias_cls, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!dlocs || !dscores || !dO || !dbias_loc || !dbias_cls || !workspace || N <= 0) return SSD3D_ERR_ARG;
+  if (bpl * (6 + n_classes) > 16) return SSD3D_ERR_UNSUPPORTED;
+  const long long V = (long long)D * H * W, M = (long long)N * V;
+  const int blocks = (int)((M + 255) / 256);
+  if (workspace_bytes < (int64_t)blocks * 16 * 4) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  SSD3D_LAUNCH_PDL(head_grad_pack_kernel, dim3(blocks), dim3(256), 0, st, dlocs, dscores, (long long)P,
+                   (long long)prior_offset, V, N, bpl, n_classes, static_cast<bf16*>(dO), partial);
+  // column sums: partial is [blocks][16] -> rows = 1, cols = 16 with slab = 16
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3(1), dim3(256), 0, st, (const float*)partial, blocks, 16ll, 1, bpl * 6, 16,
+                   bpl * 6, dbias_loc);
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3(1), dim3(256), 0, st, (const float*)(partial + bpl * 6), blocks, 16ll, 1,
+                   bpl * n_classes, 16, bpl * n_classes, dbias_cls);
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_head_dgrad(const void* dO, const void* w, const void* addend, void* dx, int N, int C, int D,
+                                int H, int W, void* stream) {
+  if (!dO || !w || !dx || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
+  if (C <= 0 || (C % 64)) return SSD3D_ERR_UNSUPPORTED;
+  HeadDgradParams p{};
+  p.dO = static_cast<const bf16*>(dO); p.w = static_cast<const bf16*>(w);
+  p.addend = static_cast<const bf16*>(addend); p.dx = static_cast<bf16*>(dx);
+  p.N = N; p.D = D; p.H = H; p.W = W; p.C = C; p.M = (long long)N * D * H * W;
+  const size_t smem = (size_t)(27 * 16 * 72 + 2 * 64 * 24) * 2;
+  cudaError_t e = cudaFuncSetAttribute(head_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)((p.M + 63) / 64), (unsigned)(C / 64));
+  SSD3D_LAUNCH_PDL(head_dgrad_kernel, grid, dim3(128), smem, static_cast<cudaStream_t>(stream), p);
+  return SSD3D_OK;
+}
+
+// ---- depthwise backward -------------------------------------------------------------------------------
+extern "C" int ssd3d_dwconv3d_dgrad(const void* dz, const void* w, void* dx, int N, int C, int D, int H, int W,
+                                    int stride, void* stream) {
+  if (!dz || !w || !dx || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
+  if (C <= 0 || (C & 7) || (stride != 1 && stride != 2)) return SSD3D_ERR_ARG;
+  const int Do = (D - 1) / stride + 1, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long total = (long long)N * D * H * W * (C / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bf16* gp = static_cast<const bf16*>(dz);
+  const bf16* wp = static_cast<const bf16*>(w);
+  if (stride == 1)
+    SSD3D_LAUNCH_PDL(dw_dgrad_kernel<1>, dim3(blocks), dim3(256), 0, st, gp, wp, static_cast<bf16*>(dx), N, C, D, H, W,
+                     Do, Ho, Wo, total);
+  else
+    SSD3D_LAUNCH_PDL(dw_dgrad_kernel<2>, dim3(blocks), dim3(256), 0, st, gp, wp, static_cast<bf16*>(dx), N, C, D, H, W,
+                     Do, Ho, Wo, total);
+  return SSD3D_OK;
+}
+
+static int dw_wgrad_plan(long long Mo, int C, int* threads, int* G, long long* vpb) {
+  const int CV = C / 8;
+  if (C <= 0 || (C & 7) || CV * 3 > 256) return -1;
+  *G = 256 / (CV * 3);
+  *threads = CV * 3 * (*G);
+  long long B = (Mo + (*G) * 8 - 1) / ((*G) * 8);
+  if (B > 592) B = 592;
+  if (B < 1) B = 1;
+  *vpb = (Mo + B - 1) / B;
+  return (int)((Mo + *vpb - 1) / *vpb);
+}
+
+extern "C" int64_t ssd3d_dw_wgrad_workspace_bytes(int C) { return (int64_t)592 * C * 27 * 4; }
+
+extern "C" int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C, int D, int H, int W, int stride,
+                                    float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!dz || !x || !dw || !workspace || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
+  if (stride != 1 && stride != 2) return SSD3D_ERR_ARG;
+  const int Do = (D - 1) / stride + 1, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long Mo = (long long)N * Do * Ho * Wo;
+  int threads, G;
+  long long vpb;
+  const int B = dw_wgrad_plan(Mo, C, &threads, &G, &vpb);
+  if (B < 0) return SSD3D_ERR_UNSUPPORTED;
+  if (workspace_bytes < (int64_t)B * C * 27 * 4) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  const bf16* gp = static_cast<const bf16*>(dz);
+  const bf16* xp = static_cast<const bf16*>(x);
+  if (stride == 1)
+    SSD3D_LAUNCH_PDL(dw_wgrad_kernel<1>, dim3(B), dim3(threads), 0, st, gp, xp, N, C, D, H, W, Do, Ho, Wo, Mo, vpb, G,
+                     partial);
+  else
+    SSD3D_LAUNCH_PDL(dw_wgrad_kernel<2>, dim3(B), dim3(threads), 0, st, gp, xp, N, C, D, H, W, Do, Ho, Wo, Mo, vpb, G,
+                     partial);
+  const long long total = (long long)C * 27;
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float*)partial,
+                   B, (long long)C * 27, C, 27, 27, 27, dw);
+  return SSD3D_OK;
+}
+
+// ---- optimizer ------------------------------------------------------------------------------------------
+extern "C" int ssd3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                               int64_t bias_start, float lr, float lr_bias, float beta1, float beta2, float eps,
+                               float weight_decay, int step, float grad_scale, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return SSD3D_ERR_ARG;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  SSD3D_LAUNCH_PDL(adam_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), param,
+                   grad, exp_avg, exp_avg_sq, (long long)n, (long long)bias_start, lr, lr_bias, beta1, beta2, eps,
+                   weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
+  return SSD3D_OK;
+}

@@ -355,3 +355,217 @@ def multibox_loss(locs: torch.Tensor, scores: torch.Tensor, true_classes: torch.
     _lib.check(rc, "ssd3d_multibox_loss")
     LAUNCHES[0] += 3
     return out, n_pos, gl, gs
+
+
+# ----------------------------------------------------------------------------------------------
+# training step: raw convolutions, train-mode BatchNorm, backward kernels, Adam
+# ----------------------------------------------------------------------------------------------
+_CONST = {}
+
+
+def _ones_zeros(n: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Identity epilogue vectors (scale = 1, shift = 0) for the raw-conv launches."""
+    key = (str(device), "oz")
+    cur = _CONST.get(key)
+    if cur is None or cur[0].numel() < n:
+        m = max(n, 1024)
+        cur = (torch.ones((m,), dtype=torch.float32, device=device), torch.zeros((m,), dtype=torch.float32, device=device))
+        _CONST[key] = cur
+    return cur
+
+
+def _workspace(nbytes: int, device, slot: str = "ws") -> torch.Tensor:
+    """Grow-only scratch buffer per (device, slot); kernels of one stream use it strictly in order."""
+    key = (str(device), slot)
+    cur = _CONST.get(key)
+    if cur is None or cur.numel() < nbytes:
+        cur = torch.empty((max(int(nbytes), 1 << 20),), dtype=torch.uint8, device=device)
+        _CONST[key] = cur
+    return cur
+
+
+def stem_conv_raw(x: torch.Tensor, w_packed: torch.Tensor, stride_d: int) -> torch.Tensor:
+    """Raw stem conv output (no BN, no ReLU), channels-last bf16."""
+    _need_cuda(x, w_packed)
+    if x.dtype not in (torch.float32, BF16):
+        x = x.float()
+    x = x.contiguous()
+    n, cin, d, h, w = x.shape
+    y = _alloc_ndhwc(n, 32, conv_out(d, stride_d), conv_out(h, 2), conv_out(w, 2), x.device)
+    one, zero = _ones_zeros(32, x.device)
+    rc = _lib.load().ssd3d_stem_conv_affine(x.data_ptr(), int(x.dtype == BF16), w_packed.data_ptr(), one.data_ptr(),
+                                            zero.data_ptr(), y.data_ptr(), n, cin, d, h, w, stride_d, 0, _stream())
+    _lib.check(rc, "ssd3d_stem_conv_affine")
+    LAUNCHES[0] += 1
+    return y
+
+
+def dwconv3d_raw(x: torch.Tensor, w_packed: torch.Tensor, stride: int) -> torch.Tensor:
+    _need_cuda(x, w_packed)
+    x = to_channels_last_bf16(x)
+    n, c, d, h, w = x.shape
+    y = _alloc_ndhwc(n, c, conv_out(d, stride), conv_out(h, stride), conv_out(w, stride), x.device)
+    one, zero = _ones_zeros(c, x.device)
+    rc = _lib.load().ssd3d_dwconv3d_affine(x.data_ptr(), w_packed.data_ptr(), one.data_ptr(), zero.data_ptr(),
+                                           y.data_ptr(), n, c, d, h, w, stride, 0, _stream())
+    _lib.check(rc, "ssd3d_dwconv3d_affine")
+    LAUNCHES[0] += 1
+    return y
+
+
+def pw_gemm_raw(x2d_rows: int, x: torch.Tensor, w_packed: torch.Tensor, out: torch.Tensor) -> None:
+    """out (M, Cout) bf16 = x (M, Cin) bf16 . w (Cout, Cin)^T -- the pointwise GEMM with an identity epilogue
+    (raw pointwise conv, and the pointwise data gradient with the transposed weight)."""
+    cout, cin = w_packed.shape
+    one, zero = _ones_zeros(cout, x.device)
+    rc = _lib.load().ssd3d_pwconv_affine(x.data_ptr(), w_packed.data_ptr(), one.data_ptr(), zero.data_ptr(),
+                                         out.data_ptr(), x2d_rows, cin, cout, 0, 0, _stream())
+    _lib.check(rc, "ssd3d_pwconv_affine")
+    LAUNCHES[0] += 1
+
+
+def pwconv_raw(x: torch.Tensor, w_packed: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x, w_packed)
+    x = to_channels_last_bf16(x)
+    n, c, d, h, w = x.shape
+    y = _alloc_ndhwc(n, w_packed.shape[0], d, h, w, x.device)
+    pw_gemm_raw(n * d * h * w, x, w_packed, y)
+    return y
+
+
+class BNState:
+    """What the backward of one conv -> BN -> ReLU unit needs from the forward."""
+    __slots__ = ("scale", "shift", "mean", "invstd")
+
+    def __init__(self, c, device):
+        buf = torch.empty((4, c), dtype=torch.float32, device=device)
+        self.scale, self.shift, self.mean, self.invstd = buf[0], buf[1], buf[2], buf[3]
+
+
+def bn_train_relu(z: torch.Tensor, bn: torch.nn.BatchNorm3d, nan_flag: Optional[torch.Tensor] = None):
+    """Training-mode BatchNorm3d + ReLU on a raw conv output (channels-last bf16) -> (a, BNState); updates the
+    module's running statistics and num_batches_tracked like nn.BatchNorm3d does."""
+    _need_cuda(z, nan_flag)
+    n, c, d, h, w = z.shape
+    m = n * d * h * w
+    st = BNState(c, z.device)
+    a = _alloc_ndhwc(n, c, d, h, w, z.device)
+    lib = _lib.load()
+    need = lib.ssd3d_bn_workspace_bytes(c)
+    ws = _workspace(need, z.device)
+    track = bn.track_running_stats and bn.running_mean is not None
+    momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+        if bn.momentum is None:
+            raise NotImplementedError("cumulative-average BatchNorm (momentum=None) is not used by the reference")
+    rc = lib.ssd3d_bn_train_fwd(z.data_ptr(), m, c, _ptr(bn.weight.detach() if bn.weight is not None else None),
+                                _ptr(bn.bias.detach() if bn.bias is not None else None), float(bn.eps), momentum,
+                                _ptr(bn.running_mean if track else None), _ptr(bn.running_var if track else None),
+                                st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+                                a.data_ptr(), _ptr(nan_flag), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_bn_train_fwd")
+    LAUNCHES[0] += 3
+    return a, st
+
+
+def bn_relu_backward(z: torch.Tensor, grad_a: torch.Tensor, st: BNState, dgamma: torch.Tensor, dbeta: torch.Tensor):
+    """-> dz, written over grad_a (both channels-last bf16); dgamma / dbeta (C) fp32 are filled."""
+    n, c, d, h, w = z.shape
+    lib = _lib.load()
+    ws = _workspace(lib.ssd3d_bn_workspace_bytes(c), z.device)
+    rc = lib.ssd3d_bn_relu_bwd(z.data_ptr(), grad_a.data_ptr(), n * d * h * w, c, st.scale.data_ptr(),
+                               st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), dgamma.data_ptr(),
+                               dbeta.data_ptr(), grad_a.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_bn_relu_bwd")
+    LAUNCHES[0] += 3
+    return grad_a
+
+
+def pwconv_wgrad(dz: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> None:
+    """dw (Cout, Cin, 1,1,1) fp32 <- dz (M, Cout)^T . x (M, Cin)."""
+    n, cin, d, h, w = x.shape
+    cout = dz.shape[1]
+    m = n * d * h * w
+    lib = _lib.load()
+    ws = _workspace(lib.ssd3d_wgrad_workspace_bytes(m, cout, cin), x.device)
+    rc = lib.ssd3d_pwconv_wgrad(dz.data_ptr(), x.data_ptr(), m, cin, cout, dw.data_ptr(), ws.data_ptr(), ws.numel(),
+                                _stream())
+    _lib.check(rc, "ssd3d_pwconv_wgrad")
+    LAUNCHES[0] += 2
+
+
+def stem_wgrad(dz: torch.Tensor, x: torch.Tensor, stride_d: int, dw: torch.Tensor) -> None:
+    n, cin, d, h, w = x.shape
+    do, ho, wo = conv_out(d, stride_d), conv_out(h, 2), conv_out(w, 2)
+    lib = _lib.load()
+    ws = _workspace(lib.ssd3d_wgrad_workspace_bytes(n * do * ho * wo, 32, 27 * cin), x.device)
+    rc = lib.ssd3d_stem_wgrad(dz.data_ptr(), x.data_ptr(), int(x.dtype == BF16), n, cin, d, h, w, stride_d,
+                              dw.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_stem_wgrad")
+    LAUNCHES[0] += 2
+
+
+def head_grad_pack(dlocs, dscores, n, d, h, w, bpl, n_classes, prior_offset, dbias_loc, dbias_cls) -> torch.Tensor:
+    """-> dO (N*D*H*W, 16) bf16 gradient rows of one head; fills the two bias gradients."""
+    lib = _lib.load()
+    dO = torch.empty((n * d * h * w, 16), dtype=BF16, device=dlocs.device)
+    ws = _workspace(lib.ssd3d_head_grad_workspace_bytes(n, d, h, w), dlocs.device)
+    rc = lib.ssd3d_head_grad_pack(dlocs.data_ptr(), dscores.data_ptr(), n, d, h, w, bpl, n_classes, dlocs.shape[1],
+                                  prior_offset, dO.data_ptr(), dbias_loc.data_ptr(), dbias_cls.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_head_grad_pack")
+    LAUNCHES[0] += 3
+    return dO
+
+
+def head_wgrad(dO: torch.Tensor, x: torch.Tensor, n_loc: int, n_cls: int, dw_loc: torch.Tensor, dw_cls: torch.Tensor):
+    n, c, d, h, w = x.shape
+    lib = _lib.load()
+    ws = _workspace(lib.ssd3d_wgrad_workspace_bytes(n * d * h * w, 16, 27 * c), x.device)
+    rc = lib.ssd3d_head_wgrad(dO.data_ptr(), x.data_ptr(), n, c, d, h, w, n_loc, n_cls, dw_loc.data_ptr(),
+                              dw_cls.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_head_wgrad")
+    LAUNCHES[0] += 2
+
+
+def head_dgrad(dO: torch.Tensor, w_packed: torch.Tensor, like: torch.Tensor, addend: Optional[torch.Tensor] = None):
+    """-> d(loss)/d(feature map) (channels-last bf16, shape of ``like``) [+ addend, written in place]."""
+    n, c, d, h, w = like.shape
+    out = addend if addend is not None else _alloc_ndhwc(n, c, d, h, w, like.device)
+    rc = _lib.load().ssd3d_head_dgrad(dO.data_ptr(), w_packed.data_ptr(), _ptr(addend), out.data_ptr(), n, c, d, h, w,
+                                      _stream())
+    _lib.check(rc, "ssd3d_head_dgrad")
+    LAUNCHES[0] += 1
+    return out
+
+
+def dwconv3d_dgrad(dz: torch.Tensor, w_packed: torch.Tensor, like: torch.Tensor, stride: int) -> torch.Tensor:
+    n, c, d, h, w = like.shape
+    dx = _alloc_ndhwc(n, c, d, h, w, like.device)
+    rc = _lib.load().ssd3d_dwconv3d_dgrad(dz.data_ptr(), w_packed.data_ptr(), dx.data_ptr(), n, c, d, h, w, stride,
+                                          _stream())
+    _lib.check(rc, "ssd3d_dwconv3d_dgrad")
+    LAUNCHES[0] += 1
+    return dx
+
+
+def dwconv3d_wgrad(dz: torch.Tensor, x: torch.Tensor, stride: int, dw: torch.Tensor) -> None:
+    n, c, d, h, w = x.shape
+    lib = _lib.load()
+    ws = _workspace(lib.ssd3d_dw_wgrad_workspace_bytes(c), x.device)
+    rc = lib.ssd3d_dwconv3d_wgrad(dz.data_ptr(), x.data_ptr(), n, c, d, h, w, stride, dw.data_ptr(), ws.data_ptr(),
+                                  ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_dwconv3d_wgrad")
+    LAUNCHES[0] += 2
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+              bias_start: int, lr: float, lr_bias: float, step: int, betas=(0.9, 0.999), eps: float = 1e-8,
+              weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    rc = _lib.load().ssd3d_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                     param.numel(), bias_start, lr, lr_bias, betas[0], betas[1], eps, weight_decay,
+                                     int(step), grad_scale, _stream())
+    _lib.check(rc, "ssd3d_adam_step")
+    LAUNCHES[0] += 1

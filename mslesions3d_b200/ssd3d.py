@@ -507,10 +507,21 @@ class LSSD3D(_LightningBase):
             raise Exception("Oh no not this NaN error again... (forward SSD), LOCS is nan!")
 
     def forward(self, image):
-        """image (N, Cin, D, H, W) -> locs (N,P,6), classes_scores (N,P,n_classes) fp32 (ssd3d.py:248-263)."""
+        """image (N, Cin, D, H, W) -> locs (N,P,6), classes_scores (N,P,n_classes) fp32 (ssd3d.py:248-263).
+        In training mode BatchNorm uses batch statistics (and updates its running ones) and the outputs carry
+        an autograd node whose backward runs the hand-written gradient kernels (training.py)."""
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("LSSD3D.forward needs the model on a CUDA device; there is no CPU path")
+        if self.training:
+            from . import training
+            if torch.is_grad_enabled():
+                locs, classes_scores = training.forward_train(self, image)
+            else:
+                locs, classes_scores = self.train_engine().forward(image)
+            if not self.defer_nan_check:
+                self._raise_on_nan(self.base.nan_flag(dev))
+            return locs, classes_scores
         if image.device != dev:
             image = image.to(dev, non_blocking=True)
         flag = self.base.nan_flag(dev)
@@ -554,7 +565,7 @@ class LSSD3D(_LightningBase):
 
     def _plan_for(self, image: torch.Tensor, slot: int = 0) -> _InferencePlan:
         if self.training:
-            raise NotImplementedError("predict_step needs eval(): the training-mode forward is not built yet")
+            raise RuntimeError("predict_step needs eval() mode (BatchNorm running statistics)")
         dtype = image.dtype if image.dtype in (torch.float32, torch.bfloat16) else torch.float32
         key = (tuple(image.shape), dtype, str(self.device), float(self.min_score), float(self.max_overlap),
                int(self.top_k), slot)
@@ -631,10 +642,41 @@ class LSSD3D(_LightningBase):
         det_scores = [out.scores[i, :k] for i, k in enumerate(counts)]
         return det_boxes, det_label, det_scores
 
+    def train_engine(self):
+        eng = self.__dict__.get("_train_engine")
+        if eng is None:
+            from .training import TrainEngine
+            eng = TrainEngine(self)
+            self.__dict__["_train_engine"] = eng
+        return eng
+
+    def invalidate_packed(self):
+        """Drop every packed-weight cache and captured plan (the fused optimizer updates parameters through
+        raw pointers, which does not bump their version counters)."""
+        for mod in self.modules():
+            if getattr(mod, "_packed", None) is not None:
+                mod._packed = None
+        self.__dict__.get("_plans", {}).clear()
+
+    def fit_step(self, batch, world_size: int = None, allreduce=None):
+        """forward + MultiBox loss + backward + (gradient all-reduce) + Adam in one call, everything on the
+        device (training.py).  With torch.distributed initialised the flat gradient buffer is summed over
+        ranks with one NCCL all-reduce and averaged inside the Adam kernel (DDP semantics).
+        Returns the (2,) device tensor [conf_loss, loc_loss]."""
+        from . import training
+        import torch.distributed as dist
+        if world_size is None:
+            world_size = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if allreduce is None and world_size > 1:
+            allreduce = dist.all_reduce
+        if not self.training:
+            raise RuntimeError("fit_step needs train() mode")
+        return training.fit_step(self, batch, world_size, allreduce)
+
     def training_step(self, batch):
-        """forward + MultiBox loss (ssd3d.py:467-531).  The loss (matching, hard/soft labelling, CE + L1 and
-        their gradients w.r.t. the head outputs) runs on the device; the network forward in train mode
-        (batch-stat BN) and the convolution backward are not built yet, so this raises from forward()."""
+        """forward + MultiBox loss (ssd3d.py:467-531): matching, hard/soft labelling, CE + L1 and their
+        gradients w.r.t. the head outputs run in the loss kernels; ``loss.backward()`` continues through the
+        network's hand-written backward (training.py) and fills ``p.grad`` for every parameter."""
         images, gt_boxes, gt_labels = batch["img"], batch['boxes'], batch["labels"]
         dev = self.device
         gt_boxes = [b.to(dev) for b in gt_boxes]

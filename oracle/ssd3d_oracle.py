@@ -480,3 +480,136 @@ def random_state_dict(in_channels=1, aspect_ratios=None, n_classes=2, seed=0, ra
         sd["pred_convs.cl_convs.%d.weight" % hi] = conv_w(nb * n_classes, c, 3)
         sd["pred_convs.cl_convs.%d.bias" % hi] = 0.05 * torch.randn(nb * n_classes, generator=g)
     return sd
+
+
+# --------------------------------------------------------------------------- #
+# training step (ssd3d.py:467-531, 704-722): train-mode forward, loss, autograd, Adam
+# --------------------------------------------------------------------------- #
+BN_MOMENTUM = 0.1  # nn.BatchNorm3d default, mobilenet.py:29,39,41
+
+
+def _ste_bf16(t: torch.Tensor) -> torch.Tensor:
+    """bf16 storage rounding that is transparent to autograd (straight-through)."""
+    return t + (_bf16(t.detach()) - t.detach())
+
+
+class _RoundGradBF16(torch.autograd.Function):
+    """Identity whose backward rounds the gradient to bf16: marks the places where the product path stores an
+    activation gradient (after each BN/ReLU backward and after each data-gradient kernel)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+def _rg(t: torch.Tensor) -> torch.Tensor:
+    return _RoundGradBF16.apply(t)
+
+
+def _bn_relu_train(x, params, running, prefix, emulate_bf16):
+    """nn.BatchNorm3d in training mode + ReLU (mobilenet.py:29-30,39,41,44-45): batch statistics, running
+    statistics updated in ``running`` (momentum 0.1, unbiased variance)."""
+    if emulate_bf16:
+        x = _rg(_ste_bf16(x))  # the raw conv output (and later its gradient) is stored in bf16
+    y = F.batch_norm(x, running[prefix + ".running_mean"], running[prefix + ".running_var"],
+                     params[prefix + ".weight"], params[prefix + ".bias"], True, BN_MOMENTUM, BN_EPS)
+    running[prefix + ".num_batches_tracked"] = running[prefix + ".num_batches_tracked"] + 1
+    y = F.relu(y)
+    return _rg(_ste_bf16(y)) if emulate_bf16 else y
+
+
+def forward_train(params: Dict[str, torch.Tensor], running: Dict[str, torch.Tensor], image: torch.Tensor,
+                  aspect_ratios=None, n_classes: int = 2, emulate_bf16: bool = False):
+    """``LSSD3D.forward`` in train mode.  ``params`` holds the learnable tensors (they may require grad),
+    ``running`` the BN buffers, UPDATED IN PLACE like the module's.  -> (locs, scores)."""
+    if not aspect_ratios:
+        aspect_ratios = DEFAULT_ASPECT_RATIOS
+    q = _ste_bf16 if emulate_bf16 else (lambda t: t)
+    cube = image.shape[2] == image.shape[3] == image.shape[4]
+    layers = backbone_layers(image.shape[1], cube, max(aspect_ratios.keys()))
+    x = _bf16(image.float()) if emulate_bf16 else image.float()
+    feats = {}
+    for i, L in enumerate(layers):
+        p = "base.features.%d" % i
+        rgi = _rg if emulate_bf16 else (lambda t: t)   # a data-gradient kernel's output is bf16
+        if L["kind"] == "stem":
+            x = F.conv3d(x, q(params[p + ".0.weight"]), None, L["stride"], 1)
+            x = _bn_relu_train(x, params, running, p + ".1", emulate_bf16)
+        else:
+            x = F.conv3d(rgi(x), q(params[p + ".conv1.weight"]), None, L["stride"], 1, 1, L["cin"])
+            x = _bn_relu_train(x, params, running, p + ".bn1", emulate_bf16)
+            x = F.conv3d(rgi(x), q(params[p + ".conv2.weight"]), None, 1, 0)
+            x = _bn_relu_train(x, params, running, p + ".bn2", emulate_bf16)
+        if i in aspect_ratios:
+            feats[i] = x
+    rgo = _rg if emulate_bf16 else (lambda t: t)       # head gradient rows are packed to bf16
+    n = image.shape[0]
+    locs, scores = [], []
+    for hi, f in enumerate(aspect_ratios.keys()):
+        l = rgo(F.conv3d(feats[f], q(params["pred_convs.loc_convs.%d.weight" % hi]), None, 1, 1)) \
+            + params["pred_convs.loc_convs.%d.bias" % hi].view(1, -1, 1, 1, 1)
+        c = rgo(F.conv3d(feats[f], q(params["pred_convs.cl_convs.%d.weight" % hi]), None, 1, 1)) \
+            + params["pred_convs.cl_convs.%d.bias" % hi].view(1, -1, 1, 1, 1)
+        locs.append(l.permute(0, 2, 3, 4, 1).reshape(n, -1, 6))
+        scores.append(c.permute(0, 2, 3, 4, 1).reshape(n, -1, n_classes))
+    return torch.cat(locs, 1), torch.cat(scores, 1)
+
+
+def split_state_dict(sd: Dict[str, torch.Tensor]):
+    """-> (params requiring grad, BN buffers), both fresh fp32 clones.  ``rescale_factors`` is a parameter of
+    the reference that never receives a gradient."""
+    params, running = {}, {}
+    for k, v in sd.items():
+        if k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"):
+            running[k] = v.clone()
+        else:
+            params[k] = v.clone().float().requires_grad_(True)
+    return params, running
+
+
+def train_step_grads(sd, image, boxes, labels, priors_cxcycz, threshold=0.5, alpha=1.0, aspect_ratios=None,
+                     n_classes=2, emulate_bf16=False):
+    """One ``training_step`` + backward of the reference (ssd3d.py:467-494): train-mode forward, MultiBox
+    loss, ``(conf + alpha*loc).backward()``.
+    -> dict(conf, loc, locs, scores, grads {name: tensor | None}, running {BN buffers after the step})."""
+    params, running = split_state_dict(sd)
+    locs, scores = forward_train(params, running, image, aspect_ratios, n_classes, emulate_bf16)
+    conf, loc = multibox_loss(locs, scores, boxes, labels, priors_cxcycz, threshold)
+    (conf + alpha * loc).backward()
+    return dict(conf=conf.detach(), loc=loc.detach(), locs=locs.detach(), scores=scores.detach(),
+                grads={k: (v.grad.clone() if v.grad is not None else None) for k, v in params.items()},
+                running=running, params=params)
+
+
+def make_optimizer(params: Dict[str, torch.Tensor], lr: float):
+    """``configure_optimizers`` (ssd3d.py:704-722): Adam, biases at 2x lr, weight decay 5e-4, cosine schedule
+    (T_max 40) stepped once per batch."""
+    biases = [p for n, p in params.items() if n.endswith(".bias")]
+    others = [p for n, p in params.items() if not n.endswith(".bias")]
+    opt = torch.optim.Adam([{"params": biases, "lr": 2 * lr}, {"params": others}], lr=lr, weight_decay=0.0005)
+    sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=40)
+    return opt, sch
+
+
+def fit_steps(sd, batches, priors_cxcycz, threshold, lr, alpha=1.0, aspect_ratios=None, n_classes=2):
+    """A few optimisation steps the way pytorch-lightning drives the reference: per batch zero_grad,
+    training_step (which steps the scheduler, ssd3d.py:525-527), backward, optimizer.step.
+    -> (state dict after the steps, list of (conf, loc))."""
+    params, running = split_state_dict(sd)
+    opt, sch = make_optimizer(params, lr)
+    losses = []
+    for image, boxes, labels in batches:
+        opt.zero_grad(set_to_none=True)
+        locs, scores = forward_train(params, running, image, aspect_ratios, n_classes)
+        conf, loc = multibox_loss(locs, scores, boxes, labels, priors_cxcycz, threshold)
+        sch.step()
+        (conf + alpha * loc).backward()
+        opt.step()
+        losses.append((float(conf), float(loc)))
+    out = {k: v.detach().clone() for k, v in params.items()}
+    out.update({k: v.clone() for k, v in running.items()})
+    return out, losses
