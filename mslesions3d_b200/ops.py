@@ -310,7 +310,6 @@ def match_priors(boxes: Sequence[torch.Tensor], labels: Sequence[torch.Tensor], 
     _need_cuda(priors_cxcycz, *boxes, *labels)
     dev = priors_cxcycz.device
     n = len(boxes)
-    p = priors_cxcycz.shape[0]
     counts = [int(b.shape[0]) for b in boxes]
     offsets = torch.tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), device=dev)
     total = int(sum(counts))
@@ -319,6 +318,16 @@ def match_priors(boxes: Sequence[torch.Tensor], labels: Sequence[torch.Tensor], 
         gt_labels = torch.cat([l.reshape(-1).long() for l in labels]).contiguous()
     else:
         gt_boxes = gt_labels = None
+    return match_priors_packed(gt_boxes, gt_labels, offsets, n, total, priors_cxcycz, t0, t1)
+
+
+def match_priors_packed(gt_boxes: Optional[torch.Tensor], gt_labels: Optional[torch.Tensor], offsets: torch.Tensor,
+                        n: int, total: int, priors_cxcycz: torch.Tensor, t0: float, t1: float):
+    """Same, on already concatenated ground truth: gt_boxes (>= total, 6) fp32, gt_labels (>= total) int64,
+    offsets (n+1) int32 on the device.  ``total`` may be a CAPACITY larger than offsets[-1] (static buffers of a
+    captured training step): rows past offsets[-1] are never read."""
+    dev = priors_cxcycz.device
+    p = priors_cxcycz.shape[0]
     tc = torch.empty((n, p), dtype=torch.int64, device=dev)
     tl = torch.empty((n, p, 6), dtype=torch.float32, device=dev)
     ov = torch.empty((n, p), dtype=torch.float32, device=dev)

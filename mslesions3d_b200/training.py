@@ -89,6 +89,7 @@ class TrainEngine:
         self.model = model
         self.flat: Optional[FlatParams] = None
         self.tape = None
+        self.plans = {}
 
     # ------------------------------------------------------------------------------------------
     def flatten(self) -> FlatParams:
@@ -241,13 +242,127 @@ def cosine_lr(base_lr: float, step: int, t_max: int = 40, eta_min: float = 0.0) 
     return eta_min + (base_lr - eta_min) * (1.0 + math.cos(math.pi * step / t_max)) / 2.0
 
 
+class _TrainPlan:
+    """forward + matching + loss + backward of one step for one input signature, captured into a CUDA graph
+    (the eager step is host-bound: ~180 launches).  Inputs are staged into static buffers: the image batch,
+    the concatenated ground-truth boxes / labels (capacity ``tmax`` rows) and the per-image offsets.  The
+    gradient all-reduce and the Adam launch stay outside the graph (host scalars: step count, learning rate)."""
+
+    def __init__(self, model, images: torch.Tensor, tmax: int):
+        eng = model.train_engine()
+        self.flat = eng.flatten()
+        dev = model.device
+        n = images.shape[0]
+        self.n, self.tmax = n, tmax
+        self.image = torch.empty(tuple(images.shape), dtype=images.dtype, device=dev)
+        self.gt_boxes = torch.zeros((tmax, 6), dtype=torch.float32, device=dev)
+        self.gt_labels = torch.zeros((tmax,), dtype=torch.int64, device=dev)
+        self.offsets = torch.zeros((n + 1,), dtype=torch.int32, device=dev)
+        self.loss = None
+        self.n_kernels = 0
+        self.graph = None
+
+    def load(self, images, gt_boxes, gt_labels):
+        self.image.copy_(images, non_blocking=True)
+        counts = [int(b.shape[0]) for b in gt_boxes]
+        total = sum(counts)
+        if total > self.tmax:
+            raise RuntimeError("more ground-truth boxes (%d) than the captured plan holds (%d)" % (total, self.tmax))
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        # a fresh pageable tensor per step: the copy is staged before copy_ returns, so the host may run
+        # steps ahead of the device without rewriting memory an earlier copy still has to read
+        self.offsets.copy_(torch.tensor(offs, dtype=torch.int32))
+        if total:
+            self.gt_boxes[:total].copy_(torch.cat([b.reshape(-1, 6) for b in gt_boxes]).float(), non_blocking=True)
+            self.gt_labels[:total].copy_(torch.cat([l.reshape(-1) for l in gt_labels]).long(), non_blocking=True)
+
+    def _run(self, model):
+        eng = model.train_engine()
+        lf = model.loss_fn
+        t0, t1 = (lf.threshold, lf.threshold) if lf.thresholding_mode == "hard" else lf.threshold
+        locs, scores = eng.forward(self.image)
+        m = ops.match_priors_packed(self.gt_boxes, self.gt_labels, self.offsets, self.n, self.tmax,
+                                    model._priors_on(model.device), t0, t1)
+        out, n_pos, g_locs, g_scores = ops.multibox_loss(locs, scores, m["true_classes"], m["true_locs"],
+                                                         alpha=float(lf.alpha),
+                                                         hard_negative_mining=lf.hard_negative_mining,
+                                                         neg_pos_ratio=lf.neg_pos_ratio, want_grads=True)
+        grads = _Grads(((n, p) for n, p in model.named_parameters() if p.requires_grad and n != "rescale_factors"),
+                       self.flat)
+        eng.backward(g_locs, g_scores, grads)
+        self.loss = out
+
+    def capture(self, model):
+        """Warm up (lazy module loading, workspaces) and record.  The warm-up steps run for real, so the
+        BatchNorm buffers they touch are restored afterwards; parameters are not modified by this part."""
+        buffers = {k: v.clone() for k, v in model.named_buffers()}
+        side = torch.cuda.Stream(device=model.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):
+                self._run(model)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for k, v in model.named_buffers():
+                v.copy_(buffers[k])
+        model.invalidate_packed()      # the weight packing must be recorded too: it runs again on every replay
+        graph = torch.cuda.CUDAGraph()
+        before = ops.LAUNCHES[0]
+        with torch.no_grad(), torch.cuda.graph(graph):
+            self._run(model)
+        self.n_kernels = ops.LAUNCHES[0] - before
+        ops.LAUNCHES[0] = before
+        self.graph = graph
+
+
+def _optimizer_step(model, flat, world_size, allreduce):
+    if allreduce is not None:
+        allreduce(flat.grad)
+    flat.step += 1
+    lr = float(model.lr)
+    if model.scheduler != "none":
+        # the reference steps the scheduler inside training_step, i.e. before the optimizer step of the
+        # same batch (ssd3d.py:525-527): optimizer step k (1-based) runs at the k-th scheduled rate
+        lr = cosine_lr(lr, flat.step)
+    ops.adam_step(flat.param, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.bias_start, lr, 2.0 * lr, flat.step,
+                  weight_decay=0.0005, grad_scale=1.0 / float(world_size))
+    model.invalidate_packed()
+
+
 def fit_step(model, batch, world_size: int = 1, allreduce=None):
     """One fused optimisation step: forward, MultiBox loss + its gradient, backward into the flat gradient
-    buffer, (all-reduce), fused Adam.  Returns a (2,) device tensor [conf_loss, loc_loss] -- no host sync."""
+    buffer, (all-reduce), fused Adam.  Returns a (2,) device tensor [conf_loss, loc_loss] -- no host sync.
+    With ``model.use_cuda_graph`` the forward..backward part is one CUDA-graph replay per step."""
     eng = model.train_engine()
     flat = eng.flatten()
     dev = model.device
     images, gt_boxes, gt_labels = batch["img"], batch["boxes"], batch["labels"]
+    if images.dtype not in (torch.float32, torch.bfloat16):
+        images = images.float()
+    if model.use_cuda_graph:
+        total = sum(int(b.shape[0]) for b in gt_boxes)
+        key = (tuple(images.shape), images.dtype)
+        plan = eng.plans.get(key)
+        if plan is None or plan.tmax < total:
+            tmax = 64
+            while tmax < total:
+                tmax *= 2
+            plan = _TrainPlan(model, images, tmax)
+            plan.load(images, gt_boxes, gt_labels)
+            model.invalidate_packed()
+            plan.capture(model)
+            eng.plans.clear()
+            eng.plans[key] = plan
+        else:
+            plan.load(images, gt_boxes, gt_labels)
+        plan.graph.replay()
+        ops.LAUNCHES[0] += plan.n_kernels
+        with torch.no_grad():
+            _optimizer_step(model, flat, world_size, allreduce)
+            return plan.loss.clone()
     gt_boxes = [b.to(dev) for b in gt_boxes]
     gt_labels = [l.to(dev) for l in gt_labels]
     with torch.no_grad():
@@ -260,15 +375,5 @@ def fit_step(model, batch, world_size: int = 1, allreduce=None):
         grads = _Grads(((n, p) for n, p in model.named_parameters() if p.requires_grad and n != "rescale_factors"),
                        flat)
         eng.backward(g_locs, g_scores, grads)
-        if allreduce is not None:
-            allreduce(flat.grad)
-        flat.step += 1
-        lr = float(model.lr)
-        if model.scheduler != "none":
-            # the reference steps the scheduler inside training_step, i.e. before the optimizer step of the
-            # same batch (ssd3d.py:525-527): optimizer step k (1-based) runs at the k-th scheduled rate
-            lr = cosine_lr(lr, flat.step)
-        ops.adam_step(flat.param, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.bias_start, lr, 2.0 * lr, flat.step,
-                      weight_decay=0.0005, grad_scale=1.0 / float(world_size))
-        model.invalidate_packed()
+        _optimizer_step(model, flat, world_size, allreduce)
     return out
