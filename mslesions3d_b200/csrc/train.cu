@@ -106,23 +106,42 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const bf16* __restrict__
   }
 }
 
+// Cross-block sums of the column partials: 32 channels x 8 block lanes per CTA, fp64, combined in a fixed order.
+__device__ __forceinline__ void colpartials_sum(const float* __restrict__ partial, int B, int C, int c, int lane,
+                                                double (&red)[8][32][2], double& s, double& q) {
+  double ls = 0.0, lq = 0.0;
+  if (c < C) {
+    for (int b = lane; b < B; b += 8) {
+      ls += (double)partial[(size_t)b * 2 * C + c];
+      lq += (double)partial[(size_t)b * 2 * C + C + c];
+    }
+  }
+  red[lane][threadIdx.x & 31][0] = ls;
+  red[lane][threadIdx.x & 31][1] = lq;
+  __syncthreads();
+  s = 0.0; q = 0.0;
+  if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) { s += red[l][threadIdx.x & 31][0]; q += red[l][threadIdx.x & 31][1]; }
+  }
+}
+
 // BN forward finalize: batch mean / biased variance -> scale = gamma*invstd, shift = beta - mean*scale,
 // running statistics (momentum update with the unbiased variance, as nn.BatchNorm3d in train mode).
-__global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int B, int C, long long M,
-                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                       float momentum, float* __restrict__ running_mean,
-                                       float* __restrict__ running_var, float* __restrict__ scale,
-                                       float* __restrict__ shift, float* __restrict__ mean,
-                                       float* __restrict__ invstd) {
+__global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __restrict__ partial, int B, int C,
+                                                              long long M, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps,
+                                                              float momentum, float* __restrict__ running_mean,
+                                                              float* __restrict__ running_var,
+                                                              float* __restrict__ scale, float* __restrict__ shift,
+                                                              float* __restrict__ mean, float* __restrict__ invstd) {
+  __shared__ double red[8][32][2];
   pdl_wait();
   pdl_launch_dependents();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < B; ++b) {
-    s += (double)partial[(size_t)b * 2 * C + c];
-    q += (double)partial[(size_t)b * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
+  double s, q;
+  colpartials_sum(partial, B, C, c, lane, red, s, q);
+  if (lane != 0 || c >= C) return;
   const double mu = s / (double)M;
   double var = q / (double)M - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -141,17 +160,15 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int B,
 }
 
 // BN backward finalize: dbeta = sum dy, dgamma = sum dy*xhat (written into the parameter gradients).
-__global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int B, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(256) bn_finalize_bwd_kernel(const float* __restrict__ partial, int B, int C,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double red[8][32][2];
   pdl_wait();
   pdl_launch_dependents();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < B; ++b) {
-    s += (double)partial[(size_t)b * 2 * C + c];
-    q += (double)partial[(size_t)b * 2 * C + C + c];
-  }
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
+  double s, q;
+  colpartials_sum(partial, B, C, c, lane, red, s, q);
+  if (lane != 0 || c >= C) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)q;
 }
@@ -253,25 +270,29 @@ struct WgradParams {
   float* partial;             // [splits][n_pad][K]
 };
 
-template <int NT, int MODE>
+template <int NT, int MODE, int KT>
 __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
   constexpr int ZP = NT + 8;          // padded row pitch (elements): conflict-free ldmatrix
-  constexpr int XP = 72;
+  constexpr int XP = KT + 8;
   constexpr int ZCH = NT / 8;         // 16-byte chunks per dz row
   constexpr int ZPT = (64 * ZCH + 127) / 128;
+  constexpr int XCH = KT / 8;         // 16-byte chunks per X row (8 or 4)
+  constexpr int XPT = 64 * XCH / 128; // chunks per thread (4 or 2)
+  constexpr int XRS = 128 / XCH;      // row step between a thread's chunks (16 or 32)
+  constexpr int NB = KT / 32;         // n8 tiles per warp along k (2 or 1)
   __shared__ __align__(16) bf16 sZ[64 * ZP];
   __shared__ __align__(16) bf16 sX[64 * XP];
   pdl_wait();
   pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int k0 = blockIdx.x * 64;
+  const int k0 = blockIdx.x * KT;
   const int n0 = blockIdx.y * NT;
   const long long m_begin = (long long)blockIdx.z * p.rows_per_split;
   const long long m_end = (m_begin + p.rows_per_split < p.M) ? m_begin + p.rows_per_split : p.M;
 
   // ---- per-thread constants of the X gather ----
-  const int xcc = tid & 7;            // 16-byte chunk (8 k values) inside the 64-wide k tile
-  const int xrow0 = tid >> 3;         // rows xrow0 + 16*i, i = 0..3
+  const int xcc = tid % XCH;          // 16-byte chunk (8 k values) inside the KT-wide k tile
+  const int xrow0 = tid / XCH;        // rows xrow0 + XRS*i, i < XPT
   int tap_d = 0, tap_h = 0, tap_w = 0, cbase = 0;       // MODE 1
   int e_off[8];                                          // MODE 2: per element (ci, tap) -> offset, or -1
   int e_kd[8], e_kh[8], e_kw[8];
@@ -290,7 +311,7 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
     }
   }
 
-  uint4 zr[ZPT], xr[4];
+  uint4 zr[ZPT], xr[XPT];
   auto load_tiles = [&](long long m0) {
 #pragma unroll
     for (int i = 0; i < ZPT; ++i) {
@@ -301,8 +322,8 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
       if (q < 64 * ZCH && m < m_end) zr[i] = ld_nc16(p.dz + m * p.ldz + n0 + cc * 8);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const long long m = m0 + xrow0 + 16 * i;
+    for (int i = 0; i < XPT; ++i) {
+      const long long m = m0 + xrow0 + XRS * i;
       xr[i] = make_uint4(0u, 0u, 0u, 0u);
       if (m >= m_end) continue;
       if (MODE == 0) {
@@ -336,11 +357,11 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
     }
   };
 
-  float acc[NT / 16][2][4];
+  float acc[NT / 16][NB][4];
 #pragma unroll
   for (int a = 0; a < NT / 16; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < NB; ++b)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
@@ -355,67 +376,91 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
       if (q < 64 * ZCH) *reinterpret_cast<uint4*>(&sZ[(q / ZCH) * ZP + (q % ZCH) * 8]) = zr[i];
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(&sX[(xrow0 + 16 * i) * XP + xcc * 8]) = xr[i];
+    for (int i = 0; i < XPT; ++i) *reinterpret_cast<uint4*>(&sX[(xrow0 + XRS * i) * XP + xcc * 8]) = xr[i];
     __syncthreads();
     if (m0 + 64 < m_end) load_tiles(m0 + 64);   // global loads of the next chunk fly during the MMAs
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       const int kk = ks * 16;
       uint32_t bfr[4];
-      // B (k16 x 2 n8 tiles): matrices {rows kk..+7 | kk+8..+15} x {cols w*16 | w*16+8}
-      ldsm_x4_t(sX_u + (uint32_t)(((kk + (lq & 1) * 8 + lr) * XP + warp * 16 + (lq >> 1) * 8) * 2), bfr);
+      // B (k16 x NB n8 tiles): matrices {rows kk..+7 | kk+8..+15} x {cols w*8*NB (| +8)}; with NB = 1 the
+      // upper two matrices re-read the first tile (their registers are unused)
+      ldsm_x4_t(sX_u + (uint32_t)(((kk + (lq & 1) * 8 + lr) * XP + warp * 8 * NB + (NB == 2 ? (lq >> 1) * 8 : 0)) * 2),
+                bfr);
 #pragma unroll
       for (int a = 0; a < NT / 16; ++a) {
         uint32_t afr[4];
         // A = dz^T (16 n x k16): matrices {n 0-7 | 8-15} x {rows kk..+7 | kk+8..+15}, transposed on load
         ldsm_x4_t(sZ_u + (uint32_t)(((kk + (lq >> 1) * 8 + lr) * ZP + a * 16 + (lq & 1) * 8) * 2), afr);
         mma_bf16(acc[a][0], afr, bfr[0], bfr[1]);
-        mma_bf16(acc[a][1], afr, bfr[2], bfr[3]);
+        if (NB == 2) mma_bf16(acc[a][NB - 1], afr, bfr[2], bfr[3]);
       }
     }
   }
-  float* out = p.partial + ((size_t)blockIdx.z * p.n_pad + n0) * p.K + k0 + warp * 16;
+  float* out = p.partial + ((size_t)blockIdx.z * p.n_pad + n0) * p.K + k0 + warp * 8 * NB;
 #pragma unroll
   for (int a = 0; a < NT / 16; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NB; ++b) {
       const int n = a * 16 + (lane >> 2), k = b * 8 + (lane & 3) * 2;
       *reinterpret_cast<float2*>(out + (size_t)n * p.K + k) = make_float2(acc[a][b][0], acc[a][b][1]);
       *reinterpret_cast<float2*>(out + (size_t)(n + 8) * p.K + k) = make_float2(acc[a][b][2], acc[a][b][3]);
     }
 }
 
-// out[r*dst_ld + c] = sum over splits (ascending) of partial[s][r*src_ld + c],  c < cols
+// out[r*dst_ld + c] = sum over splits of partial[s][r*src_ld + c],  c < cols.  32 outputs x 8 split lanes per
+// CTA; lane l adds splits l, l+8, ... in order and the 8 lane sums are combined in order: fixed for a given S.
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int S,
                                                            long long slab, int rows, int cols, int src_ld,
                                                            int dst_ld, float* __restrict__ out) {
+  __shared__ float red[8][32];
   pdl_wait();
   pdl_launch_dependents();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)rows * cols) return;
-  const int r = (int)(i / cols), c = (int)(i % cols);
+  const int ox = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + ox;
+  const bool valid = i < (long long)rows * cols;
+  const int r = valid ? (int)(i / cols) : 0, c = valid ? (int)(i % cols) : 0;
   float s = 0.f;
-  for (int k = 0; k < S; ++k) s += partial[(size_t)k * slab + (size_t)r * src_ld + c];
-  out[(size_t)r * dst_ld + c] = s;
+  if (valid)
+    for (int k = lane; k < S; k += 8) s += partial[(size_t)k * slab + (size_t)r * src_ld + c];
+  red[lane][ox] = s;
+  __syncthreads();
+  if (lane == 0 && valid) {
+    float t = red[0][ox];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) t += red[l][ox];
+    out[(size_t)r * dst_ld + c] = t;
+  }
 }
 
 // head: partial [S][16][27*C] (k = tap*C + c) -> loc (n_loc, C, 27) and class (n_cls, C, 27) conv weight grads
 __global__ void __launch_bounds__(256) head_wgrad_finalize_kernel(const float* __restrict__ partial, int S, int C,
                                                                   int n_loc, int n_cls, float* __restrict__ dw_loc,
                                                                   float* __restrict__ dw_cls) {
+  __shared__ float red[8][32];
   pdl_wait();
   pdl_launch_dependents();
+  // thread ox walks the SOURCE order (n, tap, c) so that the partial reads are coalesced
+  const int ox = threadIdx.x & 31, lane = threadIdx.x >> 5;
   const long long total = (long long)(n_loc + n_cls) * C * 27;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int tap = (int)(i % 27);
-  const int c = (int)((i / 27) % C);
-  const int n = (int)(i / (27ll * C));
+  const long long i = (long long)blockIdx.x * 32 + ox;
+  const bool valid = i < total;
   const size_t slab = (size_t)16 * 27 * C;
   float s = 0.f;
-  for (int k = 0; k < S; ++k) s += partial[k * slab + (size_t)n * 27 * C + (size_t)tap * C + c];
-  if (n < n_loc) dw_loc[((size_t)n * C + c) * 27 + tap] = s;
-  else dw_cls[((size_t)(n - n_loc) * C + c) * 27 + tap] = s;
+  if (valid)
+    for (int k = lane; k < S; k += 8) s += partial[k * slab + (size_t)i];
+  red[lane][ox] = s;
+  __syncthreads();
+  if (lane == 0 && valid) {
+    float t = red[0][ox];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) t += red[l][ox];
+    const int c = (int)(i % C);
+    const int tap = (int)((i / C) % 27);
+    const int n = (int)(i / (27ll * C));
+    if (n < n_loc) dw_loc[((size_t)n * C + c) * 27 + tap] = t;
+    else dw_cls[((size_t)(n - n_loc) * C + c) * 27 + tap] = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -741,7 +786,7 @@ extern "C" int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* 
   const bf16* zp = static_cast<const bf16*>(z);
   SSD3D_LAUNCH_PDL(colreduce_kernel<0>, dim3(B), dim3(threads), 0, st, zp, (const bf16*)nullptr, (const float*)nullptr,
                    (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (long long)M, C, rpb, partial);
-  SSD3D_LAUNCH_PDL(bn_finalize_fwd_kernel, dim3((C + 127) / 128), dim3(128), 0, st, (const float*)partial, B, C,
+  SSD3D_LAUNCH_PDL(bn_finalize_fwd_kernel, dim3((C + 31) / 32), dim3(256), 0, st, (const float*)partial, B, C,
                    (long long)M, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
   if (a) {
     const long long total_vec = (long long)M * (C / 8);
@@ -766,7 +811,7 @@ extern "C" int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, i
   const bf16* gp = static_cast<const bf16*>(grad_a);
   SSD3D_LAUNCH_PDL(colreduce_kernel<1>, dim3(B), dim3(threads), 0, st, zp, gp, scale, shift, mean, invstd, (long long)M,
                    C, rpb, partial);
-  SSD3D_LAUNCH_PDL(bn_finalize_bwd_kernel, dim3((C + 127) / 128), dim3(128), 0, st, (const float*)partial, B, C, dgamma,
+  SSD3D_LAUNCH_PDL(bn_finalize_bwd_kernel, dim3((C + 31) / 32), dim3(256), 0, st, (const float*)partial, B, C, dgamma,
                    dbeta);
   const long long total_vec = (long long)M * (C / 8);
   SSD3D_LAUNCH_PDL(bn_relu_bwd_apply_kernel, dim3(grid_for(total_vec, 256, 148 * 8)), dim3(256), 0, st, zp, gp, scale,
@@ -792,16 +837,16 @@ extern "C" int64_t ssd3d_wgrad_workspace_bytes(int64_t M, int n_out, int K) {
   return (int64_t)S * np * kp * 4;
 }
 
-template <int NT, int MODE>
+template <int NT, int MODE, int KT>
 static int run_wgrad(WgradParams& p, int n_out, cudaStream_t st, int* splits_out) {
-  const int tiles = (p.K / 64) * (p.n_pad / NT);
+  const int tiles = (p.K / KT) * (p.n_pad / NT);
   const int S = wgrad_splits(p.M, tiles);
   long long rps = (p.M + S - 1) / S;
   rps = (rps + 63) / 64 * 64;
   p.rows_per_split = rps;
   const int S2 = (int)((p.M + rps - 1) / rps);
-  dim3 grid((unsigned)(p.K / 64), (unsigned)(p.n_pad / NT), (unsigned)S2);
-  SSD3D_LAUNCH_PDL((wgrad_kernel<NT, MODE>), grid, dim3(128), 0, st, p);
+  dim3 grid((unsigned)(p.K / KT), (unsigned)(p.n_pad / NT), (unsigned)S2);
+  SSD3D_LAUNCH_PDL((wgrad_kernel<NT, MODE, KT>), grid, dim3(128), 0, st, p);
   *splits_out = S2;
   return SSD3D_OK;
 }
@@ -818,10 +863,10 @@ extern "C" int ssd3d_pwconv_wgrad(const void* dz, const void* x, int64_t M, int 
   p.x = x; p.C = Cin; p.n_pad = Cout;
   p.partial = static_cast<float*>(workspace);
   int S = 0;
-  const int rc = run_wgrad<64, 0>(p, Cout, st, &S);
+  const int rc = run_wgrad<64, 0, 64>(p, Cout, st, &S);
   if (rc) return rc;
   const long long total = (long long)Cout * Cin;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, st,
                    (const float*)p.partial, S, (long long)p.n_pad * p.K, Cout, Cin, p.K, Cin, dw);
   return SSD3D_OK;
 }
@@ -840,10 +885,10 @@ extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int
   p.x = x; p.C = C; p.N = N; p.D = D; p.H = H; p.W = W; p.n_pad = 16;
   p.partial = static_cast<float*>(workspace);
   int S = 0;
-  const int rc = run_wgrad<16, 1>(p, 16, st, &S);
+  const int rc = run_wgrad<16, 1, 64>(p, 16, st, &S);
   if (rc) return rc;
   const long long total = (long long)(n_loc + n_cls) * C * 27;
-  SSD3D_LAUNCH_PDL(head_wgrad_finalize_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+  SSD3D_LAUNCH_PDL(head_wgrad_finalize_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, st,
                    (const float*)p.partial, S, C, n_loc, n_cls, dw_loc, dw_cls);
   return SSD3D_OK;
 }
@@ -854,8 +899,8 @@ extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, in
   if (Cin < 1 || Cin > 4 || (stride_d != 1 && stride_d != 2)) return SSD3D_ERR_UNSUPPORTED;
   const int Do = (D - 1) / stride_d + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long M = (long long)N * Do * Ho * Wo;
-  const int K = (27 * Cin + 63) / 64 * 64;
-  if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, 32, K)) return SSD3D_ERR_ARG;
+  const int K = (27 * Cin <= 32) ? 32 : (27 * Cin + 63) / 64 * 64;     // one 32-wide k tile for Cin = 1
+  if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, 32, 27 * Cin)) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   WgradParams p{};
   p.dz = static_cast<const bf16*>(dz); p.ldz = 32; p.M = M;
@@ -864,10 +909,10 @@ extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, in
   p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.sd = stride_d; p.Cin = Cin; p.n_pad = 32;
   p.partial = static_cast<float*>(workspace);
   int S = 0;
-  const int rc = run_wgrad<32, 2>(p, 32, st, &S);
+  const int rc = (K == 32) ? run_wgrad<32, 2, 32>(p, 32, st, &S) : run_wgrad<32, 2, 64>(p, 32, st, &S);
   if (rc) return rc;
   const long long total = 32ll * 27 * Cin;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st,
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, st,
                    (const float*)p.partial, S, (long long)p.n_pad * p.K, 32, 27 * Cin, p.K, 27 * Cin, dw);
   return SSD3D_OK;
 }
@@ -970,7 +1015,7 @@ extern "C" int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C,
     SSD3D_LAUNCH_PDL(dw_wgrad_kernel<2>, dim3(B), dim3(threads), 0, st, gp, xp, N, C, D, H, W, Do, Ho, Wo, Mo, vpb, G,
                      partial);
   const long long total = (long long)C * 27;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float*)partial,
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, st, (const float*)partial,
                    B, (long long)C * 27, C, 27, 27, 27, dw);
   return SSD3D_OK;
 }
