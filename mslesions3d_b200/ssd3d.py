@@ -18,6 +18,7 @@ What differs from the reference by design:
 from __future__ import annotations
 
 import inspect
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -121,6 +122,16 @@ class MobileNetBase(nn.Module):
                 if isinstance(f, Block):
                     f.nan_flag = self._nan_flag
         return self._nan_flag
+
+    def use_nan_flag(self, flag: torch.Tensor) -> torch.Tensor:
+        """Route the blocks' NaN bits into ``flag`` (a captured inference plan owns its word); returns the
+        previous one."""
+        prev = self._nan_flag
+        self._nan_flag = flag
+        for f in self.features:
+            if isinstance(f, Block):
+                f.nan_flag = flag
+        return prev
 
     def forward(self, image, check_nan: bool = True, stem_out=None):
         """``stem_out``: the already-computed output of features[0] (the captured inference plan runs the
@@ -244,7 +255,14 @@ class _InferencePlan:
         self.done = torch.cuda.Event()       # graph + metadata read-back of the latest launch finished
         self.cloned = torch.cuda.Event()     # results of the latest launch were copied out of the static buffers
         self.stem = model.base.features[0]
-        self.head_streams = [torch.cuda.Stream(device=dev) for _ in model.aspect_ratios]
+        self.flag = torch.zeros((1,), dtype=torch.int32, device=dev)   # this plan's own NaN word: plans may overlap
+        self.stream = torch.cuda.Stream(device=dev)                     # compute stream of the streaming API
+        # Later stages run at higher stream priority (recorded into the graph's kernel nodes): when two batches
+        # are in flight, the latency-bound tail of the older one (small maps, heads, sort/NMS: a few CTAs each)
+        # takes SM slots as soon as CTAs of the younger batch's big layers retire, instead of queueing behind them.
+        self.head_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in model.aspect_ratios]
+        self.tail_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.tail_from = model.tail_from   # backbone layers >= this index run on the high-priority stream
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
@@ -272,7 +290,15 @@ class _InferencePlan:
 
     def _run(self, model: "LSSD3D"):
         dev = self.inp.device
-        flag = model.base.nan_flag(dev)
+        model.base.nan_flag(dev)
+        prev_flag = model.base.use_nan_flag(self.flag)
+        try:
+            self._run_with_flag(model, self.flag)
+        finally:
+            model.base.use_nan_flag(prev_flag)
+
+    def _run_with_flag(self, model: "LSSD3D", flag: torch.Tensor):
+        dev = self.inp.device
         flag.zero_()
         # Backbone on the main stream; every head forks onto its own stream as soon as its feature map
         # exists, so the head GEMMs overlap the small tail layers (which leave most SMs idle) and join
@@ -286,28 +312,48 @@ class _InferencePlan:
         locs = torch.empty((self.n, int(sum(counts)), 6), dtype=torch.float32, device=dev)
         scores = torch.empty((self.n, int(sum(counts)), pc.n_classes), dtype=torch.float32, device=dev)
         out, keep_alive = self.stem_out, []
+        cur = main
+        tail = self.tail_stream
         for i, feat in enumerate(base.features):
-            if i > 0:
-                out = feat(out)
-            if i in keys:
-                j = keys.index(i)
-                keep_alive.append(out)
-                hs = self.head_streams[j]
-                hs.wait_stream(main)
-                with torch.cuda.stream(hs):
-                    pc.run_head(j, out, locs, scores, offs[j], flag)
-        for hs in self.head_streams:
-            main.wait_stream(hs)
+            if i == self.tail_from and cur is main:
+                tail.wait_stream(main)
+                cur = tail
+            with torch.cuda.stream(cur):
+                if i > 0:
+                    out = feat(out)
+                if i in keys:
+                    j = keys.index(i)
+                    keep_alive.append(out)
+                    hs = self.head_streams[j]
+                    hs.wait_stream(cur)
+                    with torch.cuda.stream(hs):
+                        pc.run_head(j, out, locs, scores, offs[j], flag)
+        if cur is main:
+            tail.wait_stream(main)
         ms, mo, k = self.args
-        self.out = ops.detect_objects_padded(locs, scores, model._priors_on(dev), ms, mo, k,
-                                             out_count=self.meta[:self.n], status=self.meta[self.n:self.n + 1])
-        self.meta[self.n + 1:].copy_(flag)
+        with torch.cuda.stream(tail):
+            for hs in self.head_streams:
+                tail.wait_stream(hs)
+            self.out = ops.detect_objects_padded(locs, scores, model._priors_on(dev), ms, mo, k,
+                                                 out_count=self.meta[:self.n], status=self.meta[self.n:self.n + 1])
+            self.meta[self.n + 1:].copy_(flag)
+        main.wait_stream(tail)
         self.locs, self.scores = locs, scores
 
-    def launch(self, image: torch.Tensor, copy_stream=None):
-        """Queue one step on the current stream: stem on the batch (a host batch is first copied in, on
-        ``copy_stream`` if given, so that the copy overlaps the previous step), replay of the captured rest,
-        asynchronous read-back of the 4*(N+2) metadata bytes."""
+    def launch(self, image: torch.Tensor, copy_stream=None, own_stream: bool = False):
+        """Queue one step: stem on the batch (a host batch is first copied in, on ``copy_stream`` if given, so
+        that the copy overlaps the previous step), replay of the captured rest, asynchronous read-back of the
+        4*(N+2) metadata bytes.  With ``own_stream`` the step runs on this plan's stream (after everything
+        already queued on the caller's stream), so that consecutive batches on different plan slots overlap:
+        the small tail layers of one batch leave most SMs idle for the big first layers of the next."""
+        if own_stream:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                self._launch(image, copy_stream)
+        else:
+            self._launch(image, copy_stream)
+
+    def _launch(self, image: torch.Tensor, copy_stream=None):
         compute = torch.cuda.current_stream()
         compute.wait_event(self.cloned)          # static outputs of the previous use of this plan were consumed
         if image.is_cuda:
@@ -426,6 +472,8 @@ class LSSD3D(_LightningBase):
         self.loss_fn = MultiBoxLoss(self.priors_cxcycz, threshold=threshold, alpha=alpha)
         self.defer_nan_check = False
         self.use_cuda_graph = True     # predict_step replays a captured forward+detect graph
+        self.pipeline_depth = int(os.environ.get("SSD3D_PIPELINE_DEPTH", "4"))   # batches in flight in predict_batches
+        self.tail_from = int(os.environ.get("SSD3D_TAIL_FROM", "3"))   # first backbone layer on the high-priority stream
         self._plans = {}
 
     # ------------------------------------------------------------------------------------------
@@ -572,7 +620,7 @@ class LSSD3D(_LightningBase):
         ver = self._state_version()
         plan = self._plans.get(key)
         if plan is None or plan.key != ver:
-            if len(self._plans) > 8:
+            if len(self._plans) > 16:
                 self._plans.clear()
             plan = _InferencePlan(self, tuple(image.shape), dtype, self.min_score, self.max_overlap, self.top_k)
             plan.key = ver
@@ -604,20 +652,21 @@ class LSSD3D(_LightningBase):
             self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
             self.__dict__["_post_stream"] = torch.cuda.Stream(device=self.device)
         copy_stream, post_stream = self.__dict__["_copy_stream"], self.__dict__["_post_stream"]
-        prev = None
+        depth = max(1, int(self.pipeline_depth))
+        inflight = []
         slot = 0
         for batch in batches:
             image = batch["img"]
+            if len(inflight) == depth:
+                yield inflight.pop(0).results(self, post_stream, to_host)
             plan = self._plan_for(image, slot)
             if image.dtype != plan.inp.dtype:
                 image = image.to(plan.inp.dtype)
-            plan.launch(image, copy_stream)
-            if prev is not None:
-                yield prev.results(self, post_stream, to_host)
-            prev = plan
-            slot ^= 1
-        if prev is not None:
-            yield prev.results(self, post_stream, to_host)
+            plan.launch(image, copy_stream, own_stream=True)
+            inflight.append(plan)
+            slot = (slot + 1) % depth
+        while inflight:
+            yield inflight.pop(0).results(self, post_stream, to_host)
 
     def _predict_step_eager(self, image):
         prev = self.defer_nan_check

@@ -61,3 +61,54 @@ def test_gloo_world_size_2():
     assert ret[0][1] == ["vol0", "vol1", "vol2", "vol3", "vol4"]   # global order on rank 0
     assert ret[0][2] == [(1, 6), (2, 6), (3, 6), (4, 6), (5, 6)]
     assert ret[1][1] == []
+
+
+# ---------------------------------------------------------------------------------------------------
+# data-parallel training plumbing: flat parameter / gradient buffers and their all-reduce
+# ---------------------------------------------------------------------------------------------------
+def _train_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mslesions3d_b200.ssd3d import LSSD3D
+        from mslesions3d_b200.training import FlatParams, cosine_lr
+        torch.manual_seed(0)
+        model = LSSD3D(n_classes=2, input_channels=1, input_size=(64, 64, 64))
+        before = {k: v.clone() for k, v in model.named_parameters()}
+        flat = FlatParams(model)
+        # parameters are now views of the flat buffer, values unchanged, weights first and biases last
+        ok = all(torch.equal(before[k], p) for k, p in model.named_parameters())
+        names = list(flat.offsets)
+        first_bias = min(i for i, n in enumerate(names) if n.endswith(".bias"))
+        ok = ok and all(n.endswith(".bias") for n in names[first_bias:]) and flat.offsets[names[first_bias]] == flat.bias_start
+        ok = ok and "rescale_factors" not in flat.offsets and all(o % 8 == 0 for o in flat.offsets.values())
+        p = dict(model.named_parameters())["base.features.3.conv2.weight"]
+        flat.param[flat.offsets["base.features.3.conv2.weight"]] = 123.0
+        ok = ok and float(p.flatten()[0]) == 123.0
+        # every rank writes its own gradient; one all-reduce of the flat buffer sums them (fit_step's call)
+        for n, g in flat.views_grad.items():
+            g.fill_(float(rank + 1))
+        dist.all_reduce(flat.grad)
+        want = float(sum(r + 1 for r in range(world)))
+        ok = ok and all(bool((g == want).all()) for g in flat.views_grad.values())
+        ret[rank] = (ok, flat.numel, flat.bias_start, cosine_lr(1.0, 0), cosine_lr(1.0, 40), cosine_lr(1.0, 20))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_flat_gradient_allreduce():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret[0][0] and ret[1][0]
+    assert ret[0][1:3] == ret[1][1:3]                    # identical layout on every rank
+    assert ret[0][1] >= 949936 - 128 and ret[0][1] < 949936 + 8 * 103   # all trainable parameters + padding
+    assert ret[0][3] == 1.0 and abs(ret[0][4]) < 1e-12 and abs(ret[0][5] - 0.5) < 1e-12
