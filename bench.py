@@ -268,6 +268,9 @@ def main():
         d2h_bytes[0] = BATCH * TOP_K * (24 + 8 + 4) + 4 * (BATCH + 2)
 
     # ---- resident-input throughput (value) --------------------------------------------------------
+    # Build (capture) the inference plan of every pipeline slot first: that is one-off setup, not a step.
+    depth = int(model.pipeline_depth)
+    run_resident(depth)
     run_resident(args.warmup)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -279,6 +282,7 @@ def main():
     value = world * BATCH * args.steps / (ms / 1000.0)
 
     # ---- end to end from pinned host memory --------------------------------------------------------
+    run_e2e(depth)
     run_e2e(args.warmup)
     ms_e2e = timed(lambda i: run_e2e(args.steps) if i == 0 else None, args.steps)
     e2e_value = world * BATCH * args.steps / (ms_e2e / 1000.0)
@@ -324,7 +328,9 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                        "l2": "inputs rotate over %d resident batches (%d MB) > 126 MB L2" %
                              (N_ROTATE, N_ROTATE * in_bytes // 2 ** 20),
-                       "min_score": MIN_SCORE, "max_overlap": MAX_OVERLAP, "top_k": TOP_K, "priors": 9344},
+                       "min_score": MIN_SCORE, "max_overlap": MAX_OVERLAP, "top_k": TOP_K, "priors": 9344,
+                       "pipeline": "%d batches in flight (LSSD3D.predict_batches: one captured plan per slot, own "
+                                   "stream each; a step = one batch through stem + graph replay + result read-back)" % depth},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,

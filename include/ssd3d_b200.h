@@ -191,6 +191,11 @@ int ssd3d_stem_conv_affine_simt(const void* x, int x_is_bf16, const void* w, con
                                 void* y, int N, int Cin, int D, int H, int W, int stride_d, int relu, void* stream);
 int ssd3d_dwconv3d_affine(const void* x, const void* w, const float* scale, const float* shift, void* y, int N, int C,
                           int D, int H, int W, int stride, int relu, void* stream);
+/* The depthwise entry points pick the TMA halo-tile kernel (conv_dw_tma.cu: one 5-D cp.async.bulk.tensor per
+ * 32-channel tile, double buffered, persistent CTAs) for maps with Wo >= 8 and C % 32 == 0, else the direct
+ * kernel (16-byte loads through L1); .._direct forces the latter (same contract; parity tests cover both). */
+int ssd3d_dwconv3d_affine_direct(const void* x, const void* w, const float* scale, const float* shift, void* y, int N,
+                                 int C, int D, int H, int W, int stride, int relu, void* stream);
 int ssd3d_pwconv_affine(const void* x, const void* w, const float* scale, const float* shift, void* y, int64_t M,
                         int Cin, int Cout, int relu, int* nan_flag, void* stream);
 

@@ -262,11 +262,42 @@ extern "C" int ssd3d_stem_conv_affine_simt(const void* x, int x_is_bf16, const v
   return stem_simt(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, relu, stream);
 }
 
+// conv_dw_tma.cu: TMA halo-tile kernel for the large maps
+int ssd3d_dwconv3d_tma(const void* x, const void* w, const float* scale, const float* shift, void* y, int N, int C,
+                       int D, int H, int W, int stride, float floor, cudaStream_t st);
+
+static int dwconv3d_direct(const void* x, const void* w, const float* scale, const float* shift, void* y, int N,
+                           int C, int D, int H, int W, int stride, int relu, void* stream);
+
 extern "C" int ssd3d_dwconv3d_affine(const void* x, const void* w, const float* scale, const float* shift, void* y,
                                      int N, int C, int D, int H, int W, int stride, int relu, void* stream) {
   if (!x || !w || !scale || !shift || !y || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
   if (C <= 0 || (C & 7)) return SSD3D_ERR_ARG;
   if (stride != 1 && stride != 2) return SSD3D_ERR_ARG;
+  static int use_tma = -1;
+  if (use_tma < 0) {
+    const char* e = getenv("SSD3D_DW_TMA");
+    use_tma = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_tma) {
+    const int rc = ssd3d_dwconv3d_tma(x, w, scale, shift, y, N, C, D, H, W, stride, SSD3D_FLOOR(relu),
+                                      static_cast<cudaStream_t>(stream));
+    if (rc != SSD3D_ERR_UNSUPPORTED) return rc;
+  }
+  return dwconv3d_direct(x, w, scale, shift, y, N, C, D, H, W, stride, relu, stream);
+}
+
+extern "C" int ssd3d_dwconv3d_affine_direct(const void* x, const void* w, const float* scale, const float* shift,
+                                            void* y, int N, int C, int D, int H, int W, int stride, int relu,
+                                            void* stream) {
+  if (!x || !w || !scale || !shift || !y || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
+  if (C <= 0 || (C & 7)) return SSD3D_ERR_ARG;
+  if (stride != 1 && stride != 2) return SSD3D_ERR_ARG;
+  return dwconv3d_direct(x, w, scale, shift, y, N, C, D, H, W, stride, relu, stream);
+}
+
+static int dwconv3d_direct(const void* x, const void* w, const float* scale, const float* shift, void* y, int N,
+                           int C, int D, int H, int W, int stride, int relu, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Do = (D - 1) / stride + 1, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);

@@ -82,14 +82,20 @@ def stem_conv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tens
 
 
 def dwconv3d_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
-                     stride: int) -> torch.Tensor:
-    """Depthwise 3x3x3 + BN + ReLU on a channels-last bf16 activation.  mobilenet.py:38,44."""
+                     stride: int, force_direct: bool = False) -> torch.Tensor:
+    """Depthwise 3x3x3 + BN + ReLU on a channels-last bf16 activation.  mobilenet.py:38,44.
+    TMA halo-tile kernel on large maps, direct kernel otherwise (or when forced)."""
     _need_cuda(x, w_packed, scale, shift)
     x = to_channels_last_bf16(x)
     n, c, d, h, w = x.shape
     y = _alloc_ndhwc(n, c, conv_out(d, stride), conv_out(h, stride), conv_out(w, stride), x.device)
-    rc = _lib.load().ssd3d_dwconv3d_bn_relu(x.data_ptr(), w_packed.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                            y.data_ptr(), n, c, d, h, w, stride, _stream())
+    lib = _lib.load()
+    if force_direct:
+        rc = lib.ssd3d_dwconv3d_affine_direct(x.data_ptr(), w_packed.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                              y.data_ptr(), n, c, d, h, w, stride, 1, _stream())
+    else:
+        rc = lib.ssd3d_dwconv3d_bn_relu(x.data_ptr(), w_packed.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                        y.data_ptr(), n, c, d, h, w, stride, _stream())
     _lib.check(rc, "ssd3d_dwconv3d_bn_relu")
     LAUNCHES[0] += 1
     return y

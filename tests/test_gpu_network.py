@@ -91,6 +91,14 @@ def test_stem_conv(cin, size, sd, dtype, batch):
     (512, (2, 2, 2), 1, 2),
     (512, (3, 3, 3), 1, 1),
     (40, (6, 5, 9), 1, 1),
+    # maps large enough for the TMA halo-tile kernel (Wo >= 8): full and ragged tiles, several channel chunks
+    (32, (32, 32, 32), 2, 2),
+    (32, (17, 19, 21), 2, 1),
+    (64, (16, 16, 16), 2, 3),
+    (128, (8, 16, 12), 1, 2),
+    (128, (9, 10, 11), 1, 1),
+    (96, (7, 9, 17), 2, 2),
+    (32, (64, 64, 64), 2, 1),
 ])
 def test_depthwise_conv(c, size, stride, batch):
     ops = _ops()
@@ -102,6 +110,11 @@ def test_depthwise_conv(c, size, stride, batch):
     want = bf16r(F.relu(want * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)))
     got = ops.dwconv3d_bn_relu(to_cl(x), ops.pack_dw_weight(w.cuda()), scale.cuda(), shift.cuda(), stride)
     assert_bf16_close(got, want, "depthwise")
+    direct = ops.dwconv3d_bn_relu(to_cl(x), ops.pack_dw_weight(w.cuda()), scale.cuda(), shift.cuda(), stride,
+                                  force_direct=True)
+    assert_bf16_close(direct, want, "depthwise (direct kernel)")
+    # both kernels accumulate the 27 taps in the same order in fp32: identical bits
+    assert torch.equal(got, direct)
 
 
 @pytest.mark.parametrize("cin,cout,size,batch", [
