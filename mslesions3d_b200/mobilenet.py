@@ -8,8 +8,9 @@ only: ``forward`` packs their tensors once (bf16, channels-last, BN folded to sc
 the CUDA kernels; activations travel between modules as logical (N,C,D,H,W) tensors stored
 channels-last-3d in bf16.
 
-Inference (``eval()``) only in this version: training-mode BatchNorm (batch statistics) and the
-convolution backward kernels are not built yet, and asking for them raises instead of falling back.
+Called stand-alone these modules run in ``eval()`` mode only (and raise otherwise instead of falling back):
+the training-mode forward (batch-statistic BatchNorm) and the backward kernels are driven by
+``training.TrainEngine`` through ``LSSD3D``, which owns the tape of saved activations.
 """
 from __future__ import annotations
 
@@ -44,8 +45,8 @@ def _bn_tensors(bn):
 def _require_eval(mod: nn.Module):
     if mod.training:
         raise NotImplementedError(
-            "%s: training-mode forward (BatchNorm batch statistics + conv backward) is not built in this version of "
-            "the B200 path; call .eval()" % type(mod).__name__)
+            "%s: stand-alone training-mode forward is not supported; train through LSSD3D (training_step / fit_step), "
+            "or call .eval()" % type(mod).__name__)
 
 
 def _stride3(stride):

@@ -203,8 +203,8 @@ class PredictionConvolutions(nn.Module):
 
     def forward(self, feats, nan_flag: Optional[torch.Tensor] = None, out=None):
         if self.training:
-            raise NotImplementedError("PredictionConvolutions: training-mode forward/backward is not built in this "
-                                      "version of the B200 path; call .eval()")
+            raise NotImplementedError("PredictionConvolutions: stand-alone training-mode forward is not supported; "
+                                      "train through LSSD3D (training_step / fit_step), or call .eval()")
         feat_keys = list(feats.keys())
         first = feats[min(feat_keys)]
         batch_size = first.size(0)
