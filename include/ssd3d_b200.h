@@ -260,6 +260,26 @@ int ssd3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
                     int64_t bias_start, float lr, float lr_bias, float beta1, float beta2, float eps,
                     float weight_decay, int step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Detection metrics of ONE class (utils.py:155-230 compute_metrics_per_class + the cumulative precision /
+ * recall / 11-point AP of utils.py:296-318), called from training_step / validation_step (ssd3d.py:499-518,
+ * 563-584) and predict.py:279-281.  No host synchronisation.
+ *   det_boxes (nd,6) boundary coords, det_scores (nd), det_images (nd) int32: image index of each detection
+ *   true_boxes (nt,6), true_difficulties (nt) uint8, true_images (nt) int32
+ *   recall_thresholds (n_thresholds <= 16) fp32 (the reference: torch.arange(0, 1.1, .1))
+ * Outputs, detections in descending score order (equal scores: ascending input index):
+ *   sorted_scores (nd), sort_index (nd) int32 (input index of each sorted position),
+ *   true_positives / false_positives (nd) fp32 in {0,1}, detected (nt) uint8, true_volumes (nt) fp32,
+ *   cum_precision / cum_recall (nd), out_stats (4 + n_thresholds) = {AP, recall, precision, F1, precision at
+ *   every threshold}.   workspace: ssd3d_map_workspace_bytes(nd, nt).  nd >= 1. */
+int64_t ssd3d_map_workspace_bytes(int64_t nd, int64_t nt);
+int ssd3d_map_class(const float* det_boxes, const float* det_scores, const int32_t* det_images, int64_t nd,
+                    const float* true_boxes, const uint8_t* true_difficulties, const int32_t* true_images, int64_t nt,
+                    float min_overlap, const float* recall_thresholds, int n_thresholds, float* sorted_scores,
+                    int32_t* sort_index, float* true_positives, float* false_positives, uint8_t* detected,
+                    float* true_volumes, float* cum_precision, float* cum_recall, float* out_stats, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,9 @@ SIGNATURES = {
     "ssd3d_dwconv3d_dgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "ssd3d_dw_wgrad_workspace_bytes": (c_int64, [c_int]),
     "ssd3d_dwconv3d_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int64, P]),
+    "ssd3d_map_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "ssd3d_map_class": (c_int, [P, P, P, c_int64, P, P, P, c_int64, c_float, P, c_int, P, P, P, P, P, P, P, P, P, P,
+                                c_int64, P]),
     "ssd3d_adam_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, c_float,
                                 c_int, c_float, P]),
 }

@@ -25,7 +25,8 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
                 "--expt-relaxed-constexpr", "--expt-extended-lambda"]
 # integer-exact kernels: never let the compiler contract a*b+c (boxes.cuh already uses *_rn intrinsics)
-PER_FILE_FLAGS = {"detect.cu": ["-fmad=false"], "match_loss.cu": ["-fmad=false"], "box_ops.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"detect.cu": ["-fmad=false"], "match_loss.cu": ["-fmad=false"], "box_ops.cu": ["-fmad=false"],
+                  "metrics.cu": ["-fmad=false"]}
 
 
 def _nvcc() -> str:

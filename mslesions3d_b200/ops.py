@@ -584,3 +584,45 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, ex
                                      int(step), grad_scale, _stream())
     _lib.check(rc, "ssd3d_adam_step")
     LAUNCHES[0] += 1
+
+
+# ----------------------------------------------------------------------------------------------
+# detection metrics (utils.py:155-396)
+# ----------------------------------------------------------------------------------------------
+def map_class(det_boxes: torch.Tensor, det_scores: torch.Tensor, det_images: torch.Tensor, true_boxes: torch.Tensor,
+              true_difficulties: torch.Tensor, true_images: torch.Tensor, min_overlap: float,
+              recall_thresholds: torch.Tensor):
+    """Metrics of one class on the device (no host sync) -> dict of tensors; see include/ssd3d_b200.h."""
+    _need_cuda(det_boxes, det_scores, det_images)
+    dev = det_boxes.device
+    nd, nt = int(det_boxes.shape[0]), int(true_boxes.shape[0])
+    if nd == 0:
+        raise RuntimeError("map_class needs at least one detection")
+    db = det_boxes.float().contiguous()
+    ds = det_scores.float().contiguous()
+    di = det_images.to(torch.int32).contiguous()
+    tb = true_boxes.to(dev).float().contiguous()
+    td = true_difficulties.to(dev).to(torch.uint8).contiguous()
+    ti = true_images.to(dev).to(torch.int32).contiguous()
+    thr = recall_thresholds.to(dev).float().contiguous()
+    k = int(thr.numel())
+    out = dict(sorted_scores=torch.empty((nd,), dtype=torch.float32, device=dev),
+               sort_index=torch.empty((nd,), dtype=torch.int32, device=dev),
+               tp=torch.empty((nd,), dtype=torch.float32, device=dev),
+               fp=torch.empty((nd,), dtype=torch.float32, device=dev),
+               detected=torch.empty((nt,), dtype=torch.uint8, device=dev),
+               volumes=torch.empty((nt,), dtype=torch.float32, device=dev),
+               cum_precision=torch.empty((nd,), dtype=torch.float32, device=dev),
+               cum_recall=torch.empty((nd,), dtype=torch.float32, device=dev),
+               stats=torch.empty((4 + k,), dtype=torch.float32, device=dev))
+    lib = _lib.load()
+    ws = torch.empty((lib.ssd3d_map_workspace_bytes(nd, nt),), dtype=torch.uint8, device=dev)
+    rc = lib.ssd3d_map_class(db.data_ptr(), ds.data_ptr(), di.data_ptr(), nd, _ptr(tb if nt else None),
+                             _ptr(td if nt else None), _ptr(ti if nt else None), nt, f32(min_overlap), thr.data_ptr(), k,
+                             out["sorted_scores"].data_ptr(), out["sort_index"].data_ptr(), out["tp"].data_ptr(),
+                             out["fp"].data_ptr(), _ptr(out["detected"] if nt else None),
+                             _ptr(out["volumes"] if nt else None), out["cum_precision"].data_ptr(),
+                             out["cum_recall"].data_ptr(), out["stats"].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_map_class")
+    LAUNCHES[0] += 5 if nt else 4
+    return out

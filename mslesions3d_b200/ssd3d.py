@@ -734,10 +734,58 @@ class LSSD3D(_LightningBase):
         conf_loss, loc_loss = self.loss_fn(predicted_locs, predicted_scores, gt_boxes, gt_labels)
         loss = conf_loss + self.loss_fn.alpha * loc_loss
         logs = {"train_total_loss": loss, "train_conf_loss": conf_loss, "train_loc_loss": loc_loss}
+        # mAP every 2n epochs (ssd3d.py:497-518)
+        if self.current_epoch % (self.compute_metric_every_n_epochs * 2) == 0:
+            logs.update(self._detection_metrics(predicted_locs, predicted_scores, gt_boxes, gt_labels))
         sch = self.lr_schedulers()
         if sch is not None:
             sch.step()
         return {'loss': loss, "log": logs}
+
+    def _detection_metrics(self, predicted_locs, predicted_scores, gt_boxes, gt_labels, wrap_map50: bool = False):
+        """detect_objects + calculate_mAP at IoU 0.1 and 0.5 (ssd3d.py:499-518,563-584), all on the device."""
+        from .utils import calculate_mAP
+        with torch.no_grad():
+            det_boxes, det_labels, det_scores = self.detect_objects(predicted_locs.detach(), predicted_scores.detach(),
+                                                                    self.min_score, self.max_overlap, self.top_k)
+            if predicted_locs.size(1) <= 500:          # the reference only computes mAP with more than 500 priors
+                raise NotImplementedError
+            gt_difficulties = [torch.zeros((lbls.size(0),), dtype=torch.bool, device=lbls.device) for lbls in gt_labels]
+            metrics_10 = calculate_mAP(det_boxes, det_labels, det_scores, gt_boxes, gt_labels, gt_difficulties,
+                                       min_overlap=0.1, return_detail=True)
+            metrics_50 = calculate_mAP(det_boxes, det_labels, det_scores, gt_boxes, gt_labels, gt_difficulties,
+                                       min_overlap=0.5, return_detail=True)
+            if wrap_map50:
+                metrics_50["mAP"] = torch.FloatTensor([metrics_50["mAP"]])   # ssd3d.py:580
+        return {"metrics_10": metrics_10, "metrics_50": metrics_50}
+
+    def validation_step(self, batch, batch_idx=0):
+        """forward + MultiBox loss (+ mAP every n epochs) on a validation batch (ssd3d.py:533-586);
+        ``batch["seg"]`` = [gt_boxes, gt_labels]."""
+        import warnings
+        images, (gt_boxes, gt_labels) = batch["img"], batch['seg']
+        dev = self.device
+        gt_boxes = [b.to(dev) for b in gt_boxes]
+        gt_labels = [l.to(dev) for l in gt_labels]
+        predicted_locs, predicted_scores = self(images)
+        subjects = batch.get("subject", list(range(len(gt_boxes))))
+        for i, subj_boxes in enumerate(gt_boxes):
+            sb = subj_boxes.detach().cpu()
+            for axis in (0, 1, 2):
+                negatives = int((sb[:, axis + 3] < sb[:, axis]).sum())
+                zeros = int((sb[:, axis + 3] == sb[:, axis]).sum())
+                if negatives > 0:
+                    warnings.warn(f"Given boxes has invalid values (subject {subjects[i]}). The box size must "
+                                  f"be non-negative but got {negatives} boxes with negative sizes.")
+                if zeros > 0:
+                    warnings.warn(f"Given boxes has invalid values (subject {subjects[i]}). The box size must "
+                                  f"be non-zero but got {zeros} boxes with size of zero.")
+        conf_loss, loc_loss = self.loss_fn(predicted_locs, predicted_scores, gt_boxes, gt_labels)
+        loss = conf_loss + self.loss_fn.alpha * loc_loss
+        logs = {"val_total_loss": loss, "val_conf_loss": conf_loss, "val_loc_loss": loc_loss}
+        if self.current_epoch % self.compute_metric_every_n_epochs == 0:
+            logs.update(self._detection_metrics(predicted_locs, predicted_scores, gt_boxes, gt_labels, wrap_map50=True))
+        return {'val_loss': loss, "log": logs}
 
     def configure_optimizers(self):
         """Adam, weight decay 5e-4, biases at twice the learning rate, cosine schedule (ssd3d.py:704-722)."""

@@ -613,3 +613,81 @@ def fit_steps(sd, batches, priors_cxcycz, threshold, lr, alpha=1.0, aspect_ratio
     out = {k: v.detach().clone() for k, v in params.items()}
     out.update({k: v.clone() for k, v in running.items()})
     return out, losses
+
+
+# --------------------------------------------------------------------------- #
+# detection metrics (utils.py:155-396)
+# --------------------------------------------------------------------------- #
+def metrics_per_class(det_images, det_boxes, det_scores, true_images, true_boxes, true_difficulties, min_overlap,
+                      stable: bool = True):
+    """``compute_metrics_per_class`` (utils.py:155-230): walk the detections of one class in descending score
+    order; a detection is a true positive when its best-overlapping object of the same image (first maximum)
+    exceeds ``min_overlap`` (strict), is not difficult and has not been claimed by an earlier detection.
+    -> (tp, fp, detected, sorted_scores, sort_index)."""
+    n_det = det_boxes.shape[0]
+    detected = torch.zeros(true_boxes.shape[0], dtype=torch.uint8)
+    det_scores, order = torch.sort(det_scores, dim=0, descending=True, stable=stable)
+    det_images, det_boxes = det_images[order], det_boxes[order]
+    tp, fp = torch.zeros(n_det), torch.zeros(n_det)
+    all_idx = torch.arange(true_boxes.shape[0])
+    for d in range(n_det):
+        same = true_images == det_images[d]
+        cand = true_boxes[same]
+        if cand.shape[0] == 0:
+            fp[d] = 1
+            continue
+        ov = find_jaccard_overlap3d(det_boxes[d:d + 1], cand).squeeze(0)
+        best, ind = torch.max(ov, dim=0)
+        orig = all_idx[same][ind]
+        if best.item() > min_overlap:
+            if true_difficulties[same][ind] == 0:
+                if detected[orig] == 0:
+                    tp[d] = 1
+                    detected[orig] = 1
+                else:
+                    fp[d] = 1
+        else:
+            fp[d] = 1
+    return tp, fp, detected, det_scores, order
+
+
+def average_precision_11pt(tp, fp, n_easy):
+    """utils.py:296-318 -> (AP, cumulative precision, cumulative recall, precision at the 11 thresholds)."""
+    ctp, cfp = torch.cumsum(tp, 0), torch.cumsum(fp, 0)
+    prec = ctp / (ctp + cfp + 1e-10)
+    rec = ctp / n_easy
+    thr = torch.arange(start=0, end=1.1, step=.1).tolist()
+    p11 = torch.zeros(len(thr))
+    for i, t in enumerate(thr):
+        above = rec >= t
+        p11[i] = prec[above].max() if above.any() else 0.
+    return p11.mean(), prec, rec, p11
+
+
+def calculate_map(det_boxes, det_labels, det_scores, true_boxes, true_labels, true_difficulties, min_overlap=0.5,
+                  n_classes=2, stable: bool = True):
+    """``calculate_mAP`` (utils.py:233-396) for ``n_classes`` (the reference hard-codes 2 via its label map).
+    -> dict(mAP, per class c: AP, tp, fp, detected, sorted_scores, precision, recall, f1, volumes)."""
+    t_img = torch.cat([torch.full((l.shape[0],), i, dtype=torch.long) for i, l in enumerate(true_labels)])
+    t_box, t_lab, t_dif = torch.cat(true_boxes), torch.cat(true_labels), torch.cat(true_difficulties)
+    d_img = torch.cat([torch.full((l.shape[0],), i, dtype=torch.long) for i, l in enumerate(det_labels)])
+    d_box, d_lab, d_sc = torch.cat(det_boxes), torch.cat(det_labels), torch.cat(det_scores)
+    aps = torch.zeros(n_classes - 1)
+    out = {}
+    for c in range(1, n_classes):
+        st, sd_ = t_lab == c, d_lab == c
+        if int(sd_.sum()) == 0:
+            continue
+        tp, fp, detected, scores, order = metrics_per_class(d_img[sd_], d_box[sd_], d_sc[sd_], t_img[st], t_box[st],
+                                                            t_dif[st], min_overlap, stable)
+        n_easy = int(t_dif[st].logical_not().sum())
+        ap, prec, rec, p11 = average_precision_11pt(tp, fp, n_easy)
+        aps[c - 1] = ap
+        fn = 1 - detected
+        r = tp.sum() / (tp.sum() + fn.sum())
+        p = tp.sum() / (tp.sum() + fp.sum())
+        vols = torch.tensor([float((b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2])) for b in t_box[st]])
+        out[c] = dict(AP=ap, tp=tp, fp=fp, detected=detected, sorted_scores=scores, order=order, recall=r, precision=p,
+                      f1=(2 * p * r) / (p + r), cum_precision=prec, cum_recall=rec, p11=p11, volumes=vols)
+    out["mAP"] = aps.mean().item()
+    return out

@@ -91,3 +91,49 @@ def match_inputs(case, n_priors):
         boxes.append(random_gt_boxes(g, k))
         labels.append(torch.randint(1, c, (k,), generator=g))
     return locs, scores, boxes, labels
+
+
+MAP_CASES = {
+    "typical": dict(seed=40, n_obj=[3, 0, 5, 2, 1], n_det=[12, 4, 20, 7, 9], min_overlap=0.1),
+    "strict": dict(seed=41, n_obj=[6, 6, 6], n_det=[30, 25, 40], min_overlap=0.5),
+    "no_objects": dict(seed=42, n_obj=[0, 0], n_det=[5, 3], min_overlap=0.5),
+    "crowded": dict(seed=43, n_obj=[40, 35], n_det=[100, 100], min_overlap=0.1),
+}
+
+
+def map_inputs(case):
+    """(det_boxes, det_labels, det_scores, true_boxes, true_labels, true_difficulties): lists of per-image
+    tensors; detections are jittered copies of the objects plus random boxes, scores tie-free."""
+    g = torch.Generator().manual_seed(case["seed"])
+    tb, tl, td, db, dl, ds = [], [], [], [], [], []
+    for n_obj, n_det in zip(case["n_obj"], case["n_det"]):
+        t = random_gt_boxes(g, n_obj)
+        reps = []
+        while sum(r.shape[0] for r in reps) < n_det:          # several detections per object, then clutter
+            reps.append(t if (n_obj and len(reps) < 2) else random_gt_boxes(g, max(1, n_det // 3)))
+        d = torch.cat(reps)[:n_det]
+        d = d + 0.03 * torch.randn(d.shape, generator=g)
+        d = torch.cat([torch.minimum(d[:, :3], d[:, 3:] - 0.01), d[:, 3:]], 1).float()
+        tb.append(t)
+        tl.append(torch.ones(n_obj, dtype=torch.long))
+        td.append(torch.zeros(n_obj, dtype=torch.bool))
+        db.append(d)
+        dl.append(torch.ones(n_det, dtype=torch.long))
+        ds.append(torch.rand(n_det, generator=g))
+    allsc = torch.cat(ds)
+    assert torch.unique(allsc).numel() == allsc.numel(), "tie in golden scores"
+    return db, dl, ds, tb, tl, td
+
+
+TRAIN_CASES = {
+    "c1_64_b2": dict(channels=1, size=(64, 64, 64), batch=2, seed=50, threshold=[0.1, 0.2]),
+    "c2_48_b3": dict(channels=2, size=(48, 48, 48), batch=3, seed=51, threshold=0.5),
+}
+
+
+def train_inputs(case):
+    """(state_dict, image, gt boxes list, gt labels list) for a TRAIN case (synthetic cube volumes + their boxes)."""
+    sd = O.random_state_dict(case["channels"], seed=200 + case["seed"])
+    x, b, l = synthetic.make_batch(case["batch"], case["channels"], case["size"], first_idx=3 * case["seed"],
+                                   with_boxes=True)
+    return sd, torch.from_numpy(x), [torch.from_numpy(v) for v in b], [torch.from_numpy(v) for v in l]

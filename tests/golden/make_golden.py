@@ -24,8 +24,8 @@ sys.path.insert(0, ROOT)
 
 from oracle import ssd3d_oracle as O  # noqa: E402
 from oracle.ref_shim import load_reference  # noqa: E402
-from tests.golden.golden_inputs import (FORWARD_CASES, DETECT_CASES, MATCH_CASES, PRIOR_CASES,  # noqa: E402
-                                        forward_inputs, detect_inputs, match_inputs, checksum)
+from tests.golden.golden_inputs import (FORWARD_CASES, DETECT_CASES, MATCH_CASES, PRIOR_CASES, MAP_CASES,  # noqa: E402
+                                        forward_inputs, detect_inputs, match_inputs, map_inputs, checksum)
 
 
 def build_reference_model(ssd3d, case, **over):
@@ -109,6 +109,42 @@ def main():
                          true_locs_pos=rec["true_locs_pos"], n_pos=rec["n_pos"])
         print("match", name, float(conf), float(loc), rec["n_pos"])
     torch.save(out, os.path.join(HERE, "match.pt"))
+
+    # ---- calculate_mAP ------------------------------------------------------------------
+    out = {}
+    for name, case in MAP_CASES.items():
+        db, dl, ds, tb, tl, td = map_inputs(case)
+        r = utils.calculate_mAP(db, dl, ds, tb, tl, td, min_overlap=case["min_overlap"], return_detail=True)
+        simple = utils.calculate_mAP(db, dl, ds, tb, tl, td, min_overlap=case["min_overlap"])
+        out[name] = dict(detail={k: (v.clone() if torch.is_tensor(v) else v) for k, v in r.items()}, simple=simple,
+                         in_sum=checksum(torch.cat([torch.cat(db).flatten(), torch.cat(ds)])))
+        print("mAP", name, r["mAP"], r["n_true_boxes"])
+    torch.save(out, os.path.join(HERE, "map.pt"))
+
+    # ---- training step (train-mode forward, MultiBox loss, backward) ---------------------------
+    from tests.golden.golden_inputs import TRAIN_CASES, train_inputs
+    out = {}
+    for name, case in TRAIN_CASES.items():
+        sd, x, boxes, labels = train_inputs(case)
+        m = build_reference_model(ssd3d, case, threshold=case["threshold"])
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        locs, scores = m(x)
+        conf, loc = m.loss_fn(locs, scores, boxes, labels)
+        (conf + m.loss_fn.alpha * loc).backward()
+        grads = {}
+        for k, p in m.named_parameters():
+            if p.grad is None:
+                grads[k] = None
+            else:
+                gflat = p.grad.flatten()
+                grads[k] = dict(norm=float(gflat.double().norm()), sum=float(gflat.double().sum()),
+                                head=gflat[:8].clone(), tail=gflat[-8:].clone())
+        buffers = {k: v.clone() for k, v in m.named_buffers() if v.numel() <= 64 or "features.0." in k}
+        out[name] = dict(conf=conf.detach().clone(), loc=loc.detach().clone(), grads=grads, buffers=buffers,
+                         locs_sum=checksum(locs.detach()), x_sum=checksum(x))
+        print("train", name, float(conf), float(loc))
+    torch.save(out, os.path.join(HERE, "train.pt"))
 
     # ---- box utility functions ----------------------------------------------------
     g = torch.Generator().manual_seed(1234)

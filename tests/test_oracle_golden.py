@@ -99,3 +99,50 @@ def test_bf16_emulation_is_close_to_fp32():
         l16, s16 = O.forward(sd, x, emulate_bf16=True)
     assert (l32 - l16).abs().max() < 0.15 and (s32 - s16).abs().max() < 0.15
     assert (l32 - l16).abs().mean() < 0.02
+
+
+@pytest.mark.parametrize("name", list(GI.MAP_CASES))
+def test_map_matches_reference(name):
+    case, gold = GI.MAP_CASES[name], load_golden("map.pt")[name]
+    db, dl, ds, tb, tl, td = GI.map_inputs(case)
+    assert GI.checksum(torch.cat([torch.cat(db).flatten(), torch.cat(ds)])) == gold["in_sum"]
+    o = O.calculate_map(db, dl, ds, tb, tl, td, case["min_overlap"])
+    d = gold["detail"]
+    assert o["mAP"] == d["mAP"] == gold["simple"][1]
+    if sum(case["n_det"]) and 1 in o:
+        assert torch.equal(o[1]["tp"], d["TP"]) and torch.equal(o[1]["fp"], d["FP"])
+        assert torch.equal(o[1]["sorted_scores"], d["sorted_det_scores"][1])
+        assert float(o[1]["AP"]) == d["APs"]
+        for a, b in ((o[1]["recall"], d["recall"]), (o[1]["precision"], d["precision"]), (o[1]["f1"], d["f1_score"])):
+            assert float(a) == float(b) or (float(a) != float(a) and float(b) != float(b))   # NaN when 0/0
+        assert int(o[1]["detected"].numel()) == d["n_true_boxes"]
+        assert torch.equal(o[1]["volumes"][o[1]["detected"] == 1], d["found_boxes_volumes_per_class"])
+        assert torch.equal(o[1]["volumes"][o[1]["detected"] == 0], d["not_found_boxes_volumes_per_class"])
+
+
+@pytest.mark.parametrize("name", list(GI.TRAIN_CASES))
+def test_train_step_matches_reference(name):
+    """Train-mode forward + MultiBox loss + autograd backward of the oracle vs the unmodified reference."""
+    case, gold = GI.TRAIN_CASES[name], load_golden("train.pt")[name]
+    sd, x, boxes, labels = GI.train_inputs(case)
+    assert GI.checksum(x) == gold["x_sum"]
+    pri = O.prior_boxes(case["size"], in_channels=case["channels"])
+    r = O.train_step_grads(sd, x, boxes, labels, pri, case["threshold"])
+    torch.testing.assert_close(r["conf"], gold["conf"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(r["loc"], gold["loc"], rtol=1e-5, atol=1e-5)
+    assert abs(GI.checksum(r["locs"]) - gold["locs_sum"]) <= 1e-3 * max(1.0, abs(gold["locs_sum"]))
+    for k, g in gold["grads"].items():
+        got = r["grads"][k]
+        if g is None:
+            assert got is None, k
+            continue
+        flat = got.flatten()
+        assert abs(float(flat.double().norm()) - g["norm"]) <= 2e-3 * g["norm"] + 1e-7, k
+        torch.testing.assert_close(flat[:8], g["head"], rtol=5e-3, atol=1e-5 * max(1.0, g["norm"]), msg=k)
+        torch.testing.assert_close(flat[-8:], g["tail"], rtol=5e-3, atol=1e-5 * max(1.0, g["norm"]), msg=k)
+    for k, v in gold["buffers"].items():
+        got = r["running"][k]
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == int(v)
+        else:
+            torch.testing.assert_close(got, v, rtol=1e-4, atol=1e-5, msg=k)
