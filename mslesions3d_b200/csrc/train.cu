@@ -106,14 +106,19 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const bf16* __restrict__
   }
 }
 
-// Cross-block sums of the column partials: 32 channels x 8 block lanes per CTA, fp64, combined in a fixed order.
+// Cross-block sums of the column partials: 32 channels x 32 block lanes per CTA (1024 threads), fp64, combined in
+// a fixed order.  The loads of a lane are independent (unrolled): the loop is L2-latency bound otherwise.
+constexpr int FIN_LANES = 32;
 __device__ __forceinline__ void colpartials_sum(const float* __restrict__ partial, int B, int C, int c, int lane,
-                                                double (&red)[8][32][2], double& s, double& q) {
+                                                double (&red)[FIN_LANES][32][2], double& s, double& q) {
   double ls = 0.0, lq = 0.0;
   if (c < C) {
-    for (int b = lane; b < B; b += 8) {
-      ls += (double)partial[(size_t)b * 2 * C + c];
-      lq += (double)partial[(size_t)b * 2 * C + C + c];
+#pragma unroll 4
+    for (int b = lane; b < B; b += FIN_LANES) {
+      const float a0 = partial[(size_t)b * 2 * C + c];
+      const float a1 = partial[(size_t)b * 2 * C + C + c];
+      ls += (double)a0;
+      lq += (double)a1;
     }
   }
   red[lane][threadIdx.x & 31][0] = ls;
@@ -122,20 +127,20 @@ __device__ __forceinline__ void colpartials_sum(const float* __restrict__ partia
   s = 0.0; q = 0.0;
   if (lane == 0) {
 #pragma unroll
-    for (int l = 0; l < 8; ++l) { s += red[l][threadIdx.x & 31][0]; q += red[l][threadIdx.x & 31][1]; }
+    for (int l = 0; l < FIN_LANES; ++l) { s += red[l][threadIdx.x & 31][0]; q += red[l][threadIdx.x & 31][1]; }
   }
 }
 
 // BN forward finalize: batch mean / biased variance -> scale = gamma*invstd, shift = beta - mean*scale,
 // running statistics (momentum update with the unbiased variance, as nn.BatchNorm3d in train mode).
-__global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __restrict__ partial, int B, int C,
+__global__ void __launch_bounds__(1024) bn_finalize_fwd_kernel(const float* __restrict__ partial, int B, int C,
                                                               long long M, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps,
                                                               float momentum, float* __restrict__ running_mean,
                                                               float* __restrict__ running_var,
                                                               float* __restrict__ scale, float* __restrict__ shift,
                                                               float* __restrict__ mean, float* __restrict__ invstd) {
-  __shared__ double red[8][32][2];
+  __shared__ double red[FIN_LANES][32][2];
   pdl_wait();
   pdl_launch_dependents();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
@@ -160,9 +165,9 @@ __global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __res
 }
 
 // BN backward finalize: dbeta = sum dy, dgamma = sum dy*xhat (written into the parameter gradients).
-__global__ void __launch_bounds__(256) bn_finalize_bwd_kernel(const float* __restrict__ partial, int B, int C,
+__global__ void __launch_bounds__(1024) bn_finalize_bwd_kernel(const float* __restrict__ partial, int B, int C,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ double red[8][32][2];
+  __shared__ double red[FIN_LANES][32][2];
   pdl_wait();
   pdl_launch_dependents();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
@@ -408,12 +413,12 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
     }
 }
 
-// out[r*dst_ld + c] = sum over splits of partial[s][r*src_ld + c],  c < cols.  32 outputs x 8 split lanes per
-// CTA; lane l adds splits l, l+8, ... in order and the 8 lane sums are combined in order: fixed for a given S.
-__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int S,
+// out[r*dst_ld + c] = sum over splits of partial[s][r*src_ld + c],  c < cols.  32 outputs x 32 split lanes per
+// CTA; lane l adds splits l, l+32, ... in order and the 32 lane sums are combined in order: fixed for a given S.
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restrict__ partial, int S,
                                                            long long slab, int rows, int cols, int src_ld,
                                                            int dst_ld, float* __restrict__ out) {
-  __shared__ float red[8][32];
+  __shared__ float red[FIN_LANES][32];
   pdl_wait();
   pdl_launch_dependents();
   const int ox = threadIdx.x & 31, lane = threadIdx.x >> 5;
@@ -421,23 +426,25 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
   const bool valid = i < (long long)rows * cols;
   const int r = valid ? (int)(i / cols) : 0, c = valid ? (int)(i % cols) : 0;
   float s = 0.f;
-  if (valid)
-    for (int k = lane; k < S; k += 8) s += partial[(size_t)k * slab + (size_t)r * src_ld + c];
+  if (valid) {
+#pragma unroll 4
+    for (int k = lane; k < S; k += FIN_LANES) s += partial[(size_t)k * slab + (size_t)r * src_ld + c];
+  }
   red[lane][ox] = s;
   __syncthreads();
   if (lane == 0 && valid) {
     float t = red[0][ox];
 #pragma unroll
-    for (int l = 1; l < 8; ++l) t += red[l][ox];
+    for (int l = 1; l < FIN_LANES; ++l) t += red[l][ox];
     out[(size_t)r * dst_ld + c] = t;
   }
 }
 
 // head: partial [S][16][27*C] (k = tap*C + c) -> loc (n_loc, C, 27) and class (n_cls, C, 27) conv weight grads
-__global__ void __launch_bounds__(256) head_wgrad_finalize_kernel(const float* __restrict__ partial, int S, int C,
+__global__ void __launch_bounds__(1024) head_wgrad_finalize_kernel(const float* __restrict__ partial, int S, int C,
                                                                   int n_loc, int n_cls, float* __restrict__ dw_loc,
                                                                   float* __restrict__ dw_cls) {
-  __shared__ float red[8][32];
+  __shared__ float red[FIN_LANES][32];
   pdl_wait();
   pdl_launch_dependents();
   // thread ox walks the SOURCE order (n, tap, c) so that the partial reads are coalesced
@@ -447,14 +454,16 @@ __global__ void __launch_bounds__(256) head_wgrad_finalize_kernel(const float* _
   const bool valid = i < total;
   const size_t slab = (size_t)16 * 27 * C;
   float s = 0.f;
-  if (valid)
-    for (int k = lane; k < S; k += 8) s += partial[k * slab + (size_t)i];
+  if (valid) {
+#pragma unroll 4
+    for (int k = lane; k < S; k += FIN_LANES) s += partial[k * slab + (size_t)i];
+  }
   red[lane][ox] = s;
   __syncthreads();
   if (lane == 0 && valid) {
     float t = red[0][ox];
 #pragma unroll
-    for (int l = 1; l < 8; ++l) t += red[l][ox];
+    for (int l = 1; l < FIN_LANES; ++l) t += red[l][ox];
     const int c = (int)(i % C);
     const int tap = (int)((i / C) % 27);
     const int n = (int)(i / (27ll * C));
@@ -786,7 +795,7 @@ extern "C" int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* 
   const bf16* zp = static_cast<const bf16*>(z);
   SSD3D_LAUNCH_PDL(colreduce_kernel<0>, dim3(B), dim3(threads), 0, st, zp, (const bf16*)nullptr, (const float*)nullptr,
                    (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (long long)M, C, rpb, partial);
-  SSD3D_LAUNCH_PDL(bn_finalize_fwd_kernel, dim3((C + 31) / 32), dim3(256), 0, st, (const float*)partial, B, C,
+  SSD3D_LAUNCH_PDL(bn_finalize_fwd_kernel, dim3((C + 31) / 32), dim3(1024), 0, st, (const float*)partial, B, C,
                    (long long)M, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
   if (a) {
     const long long total_vec = (long long)M * (C / 8);
@@ -811,7 +820,7 @@ extern "C" int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, i
   const bf16* gp = static_cast<const bf16*>(grad_a);
   SSD3D_LAUNCH_PDL(colreduce_kernel<1>, dim3(B), dim3(threads), 0, st, zp, gp, scale, shift, mean, invstd, (long long)M,
                    C, rpb, partial);
-  SSD3D_LAUNCH_PDL(bn_finalize_bwd_kernel, dim3((C + 31) / 32), dim3(256), 0, st, (const float*)partial, B, C, dgamma,
+  SSD3D_LAUNCH_PDL(bn_finalize_bwd_kernel, dim3((C + 31) / 32), dim3(1024), 0, st, (const float*)partial, B, C, dgamma,
                    dbeta);
   const long long total_vec = (long long)M * (C / 8);
   SSD3D_LAUNCH_PDL(bn_relu_bwd_apply_kernel, dim3(grid_for(total_vec, 256, 148 * 8)), dim3(256), 0, st, zp, gp, scale,
@@ -866,7 +875,7 @@ extern "C" int ssd3d_pwconv_wgrad(const void* dz, const void* x, int64_t M, int 
   const int rc = run_wgrad<64, 0, 64>(p, Cout, st, &S);
   if (rc) return rc;
   const long long total = (long long)Cout * Cin;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, st,
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st,
                    (const float*)p.partial, S, (long long)p.n_pad * p.K, Cout, Cin, p.K, Cin, dw);
   return SSD3D_OK;
 }
@@ -888,7 +897,7 @@ extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int
   const int rc = run_wgrad<16, 1, 64>(p, 16, st, &S);
   if (rc) return rc;
   const long long total = (long long)(n_loc + n_cls) * C * 27;
-  SSD3D_LAUNCH_PDL(head_wgrad_finalize_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, st,
+  SSD3D_LAUNCH_PDL(head_wgrad_finalize_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st,
                    (const float*)p.partial, S, C, n_loc, n_cls, dw_loc, dw_cls);
   return SSD3D_OK;
 }
@@ -912,7 +921,7 @@ extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, in
   const int rc = (K == 32) ? run_wgrad<32, 2, 32>(p, 32, st, &S) : run_wgrad<32, 2, 64>(p, 32, st, &S);
   if (rc) return rc;
   const long long total = 32ll * 27 * Cin;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, st,
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st,
                    (const float*)p.partial, S, (long long)p.n_pad * p.K, 32, 27 * Cin, p.K, 27 * Cin, dw);
   return SSD3D_OK;
 }
@@ -936,9 +945,9 @@ extern "C" int ssd3d_head_grad_pack(const float* dlocs, const float* dscores, in
   SSD3D_LAUNCH_PDL(head_grad_pack_kernel, dim3(blocks), dim3(256), 0, st, dlocs, dscores, (long long)P,
                    (long long)prior_offset, V, N, bpl, n_classes, static_cast<bf16*>(dO), partial);
   // column sums: partial is [blocks][16] -> rows = 1, cols = 16 with slab = 16
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3(1), dim3(256), 0, st, (const float*)partial, blocks, 16ll, 1, bpl * 6, 16,
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3(1), dim3(1024), 0, st, (const float*)partial, blocks, 16ll, 1, bpl * 6, 16,
                    bpl * 6, dbias_loc);
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3(1), dim3(256), 0, st, (const float*)(partial + bpl * 6), blocks, 16ll, 1,
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3(1), dim3(1024), 0, st, (const float*)(partial + bpl * 6), blocks, 16ll, 1,
                    bpl * n_classes, 16, bpl * n_classes, dbias_cls);
   return SSD3D_OK;
 }
@@ -1015,7 +1024,7 @@ extern "C" int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C,
     SSD3D_LAUNCH_PDL(dw_wgrad_kernel<2>, dim3(B), dim3(threads), 0, st, gp, xp, N, C, D, H, W, Do, Ho, Wo, Mo, vpb, G,
                      partial);
   const long long total = (long long)C * 27;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, st, (const float*)partial,
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st, (const float*)partial,
                    B, (long long)C * 27, C, 27, 27, 27, dw);
   return SSD3D_OK;
 }

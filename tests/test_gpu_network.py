@@ -127,6 +127,14 @@ def test_depthwise_conv(c, size, stride, batch):
     (512, 512, (4, 4, 4), 8),      # 8 k-blocks through a 4-deep ring
     (512, 1024, (3, 3, 3), 1),
     (96, 48, (5, 5, 5), 1),        # BK = 32, three k-blocks, Cout % 16 == 0 only
+    # enough tiles for the persistent kernel (gemm_pw.cu): several tiles per CTA, ragged last tile, 1-8 k-blocks
+    (32, 64, (40, 40, 40), 1),
+    (64, 128, (32, 32, 32), 1),
+    (64, 128, (31, 33, 17), 2),
+    (128, 128, (16, 16, 16), 8),
+    (256, 256, (24, 24, 24), 1),
+    (512, 512, (16, 16, 16), 2),
+    (128, 32, (30, 30, 30), 1),
 ])
 def test_pointwise_conv_tcgen05(cin, cout, size, batch):
     ops = _ops()
