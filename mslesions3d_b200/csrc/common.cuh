@@ -38,6 +38,24 @@ inline bool pdl_enabled() {
   return v != 0;
 }
 
+// SMs a persistent kernel spreads over: all of them minus SSD3D_RESERVE_SMS (default 0).  Persistent CTAs hold
+// their SM for the whole kernel, so leaving a few SMs free lets the latency-bound kernels of OTHER in-flight
+// batches (sort / NMS / small heads: a handful of CTAs) start immediately instead of waiting for a slot.
+inline int persistent_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    const char* e = getenv("SSD3D_RESERVE_SMS");
+    int r = e ? atoi(e) : 0;
+    if (r < 0) r = 0;
+    if (r > sms / 2) r = sms / 2;
+    n = sms - r;
+  }
+  return n;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args&&... args) {

@@ -208,12 +208,7 @@ static int launch_dw_tma(const void* x, DwTmaParams& p, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(dw_tma_kernel<S, WT, TD, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)T::SMEM);
   if (e != cudaSuccess) return (int)e;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = persistent_sms();
   // persistent grid: one CTA per SM (the register-resident weights need 1 x 256 threads x ~200 registers),
   // rounded down to a multiple of the channel chunks so that every CTA keeps one chunk
   long long grid = n_sm;

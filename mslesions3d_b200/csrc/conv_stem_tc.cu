@@ -307,12 +307,7 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
   cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<TIn, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   // persistent grid: 3 CTAs per SM (smem ~53 KB, 64 TMEM columns each), never more CTAs than tiles
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = persistent_sms();
   const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
   const unsigned grid = (unsigned)(tiles < 3ll * n_sm ? tiles : 3ll * n_sm);
   SSD3D_LAUNCH_PDL((stem_tc_kernel<TIn, CIN>), dim3(grid), dim3(128), smem, st, tm, p);

@@ -200,12 +200,7 @@ using namespace ssd3d;
 // Returns SSD3D_ERR_UNSUPPORTED when the problem has too few tiles to be worth a persistent grid.
 int ssd3d_pwconv_persistent(const void* x, const void* w, const float* scale, const float* shift, void* y, int64_t M,
                             int Cin, int Cout, float floor, int* nan_flag, cudaStream_t st) {
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-  }
+  const int n_sm = persistent_sms();
   const int BK = (Cin % 64 == 0) ? 64 : 32;
   if (Cout % 64 || Cout > 1024) return SSD3D_ERR_UNSUPPORTED;
   const int BN = 64;                                  // one 128-byte swizzle atom per output row

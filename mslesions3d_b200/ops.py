@@ -18,7 +18,9 @@ LAUNCHES = [0]
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # raw handle of torch's current stream on the current device (torch.cuda.current_stream() costs ~14 us of
+    # host time per call, which matters when a pipelined inference step is ~250 us)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _need_cuda(*tensors: torch.Tensor) -> None:
@@ -260,7 +262,7 @@ class DetectOutput:
 def detect_objects_padded(locs: torch.Tensor, scores: torch.Tensor, priors: torch.Tensor, min_score: float,
                           max_overlap: float, top_k: int, workspace: Optional[torch.Tensor] = None,
                           out_count: Optional[torch.Tensor] = None,
-                          status: Optional[torch.Tensor] = None) -> DetectOutput:
+                          status: Optional[torch.Tensor] = None, out=None) -> DetectOutput:
     """The whole of ``detect_objects`` on the device, no host sync; see include/ssd3d_b200.h.
     ``out_count`` (N,) / ``status`` (1,) int32 may be supplied (e.g. slices of one buffer that is read back
     with a single copy)."""
@@ -275,10 +277,13 @@ def detect_objects_padded(locs: torch.Tensor, scores: torch.Tensor, priors: torc
     need = lib.ssd3d_detect_workspace_bytes(n, p, c, top_k)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty((need,), dtype=torch.uint8, device=dev)
-    out_boxes = torch.empty((n, top_k, 6), dtype=torch.float32, device=dev)
-    out_scores = torch.empty((n, top_k), dtype=torch.float32, device=dev)
-    out_labels = torch.empty((n, top_k), dtype=torch.int64, device=dev)
-    out_prior = torch.empty((n, top_k), dtype=torch.int64, device=dev)
+    if out is not None:          # caller-provided (boxes, scores, labels, prior), e.g. views of one packed buffer
+        out_boxes, out_scores, out_labels, out_prior = out
+    else:
+        out_boxes = torch.empty((n, top_k, 6), dtype=torch.float32, device=dev)
+        out_scores = torch.empty((n, top_k), dtype=torch.float32, device=dev)
+        out_labels = torch.empty((n, top_k), dtype=torch.int64, device=dev)
+        out_prior = torch.empty((n, top_k), dtype=torch.int64, device=dev)
     if out_count is None:
         out_count = torch.empty((n,), dtype=torch.int32, device=dev)
     if status is None:

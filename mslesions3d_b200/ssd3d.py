@@ -18,6 +18,7 @@ What differs from the reference by design:
 from __future__ import annotations
 
 import inspect
+import operator
 import os
 from typing import Dict, List, Optional
 
@@ -76,6 +77,7 @@ except Exception:  # pragma: no cover - PL is absent in the build image
 
 
 device = torch.device("cuda" if torch.cuda.is_available() else "cpu")   # ssd3d.py:23
+_VERSION_OF = operator.attrgetter("_version")
 
 ASPECT_RATIOS = {3: [1.], 5: [1.], 7: [1]}   # ssd3d.py:25
 
@@ -254,6 +256,7 @@ class _InferencePlan:
         self.graph = None
         self.done = torch.cuda.Event()       # graph + metadata read-back of the latest launch finished
         self.cloned = torch.cuda.Event()     # results of the latest launch were copied out of the static buffers
+        self.copied = torch.cuda.Event()     # the latest host batch has arrived in the static input buffer
         self.stem = model.base.features[0]
         self.flag = torch.zeros((1,), dtype=torch.int32, device=dev)   # this plan's own NaN word: plans may overlap
         self.stream = torch.cuda.Stream(device=dev)                     # compute stream of the streaming API
@@ -331,30 +334,49 @@ class _InferencePlan:
         if cur is main:
             tail.wait_stream(main)
         ms, mo, k = self.args
+        k = int(k)
+        # one packed result buffer (labels | prior | boxes | scores) so that handing results out is ONE copy
+        nk = self.n * k
+        self.outbuf = torch.empty((nk * (8 + 8 + 24 + 4),), dtype=torch.uint8, device=dev)
+        self.out_views = self._views(self.outbuf, k)
         with torch.cuda.stream(tail):
             for hs in self.head_streams:
                 tail.wait_stream(hs)
+            b_, s_, l_, p_ = self.out_views
             self.out = ops.detect_objects_padded(locs, scores, model._priors_on(dev), ms, mo, k,
-                                                 out_count=self.meta[:self.n], status=self.meta[self.n:self.n + 1])
+                                                 out_count=self.meta[:self.n], status=self.meta[self.n:self.n + 1],
+                                                 out=(b_, s_, l_, p_))
             self.meta[self.n + 1:].copy_(flag)
         main.wait_stream(tail)
         self.locs, self.scores = locs, scores
 
-    def launch(self, image: torch.Tensor, copy_stream=None, own_stream: bool = False):
+    def _views(self, buf: torch.Tensor, k: int):
+        """(boxes (N,K,6) f32, scores (N,K) f32, labels (N,K) i64, prior (N,K) i64) views of a packed buffer."""
+        nk = self.n * k
+        labels = buf[:nk * 8].view(torch.int64).view(self.n, k)
+        prior = buf[nk * 8:nk * 16].view(torch.int64).view(self.n, k)
+        boxes = buf[nk * 16:nk * 40].view(torch.float32).view(self.n, k, 6)
+        scores = buf[nk * 40:nk * 44].view(torch.float32).view(self.n, k)
+        return boxes, scores, labels, prior
+
+    def launch(self, image: torch.Tensor, copy_stream=None, own_stream: bool = False, caller_stream=None):
         """Queue one step: stem on the batch (a host batch is first copied in, on ``copy_stream`` if given, so
         that the copy overlaps the previous step), replay of the captured rest, asynchronous read-back of the
         4*(N+2) metadata bytes.  With ``own_stream`` the step runs on this plan's stream (after everything
         already queued on the caller's stream), so that consecutive batches on different plan slots overlap:
         the small tail layers of one batch leave most SMs idle for the big first layers of the next."""
         if own_stream:
-            self.stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.stream):
-                self._launch(image, copy_stream)
+            caller = caller_stream if caller_stream is not None else torch.cuda.current_stream()
+            self.stream.wait_stream(caller)
+            torch.cuda.set_stream(self.stream)       # (the context manager costs several current_stream() calls)
+            try:
+                self._launch(image, copy_stream, self.stream)
+            finally:
+                torch.cuda.set_stream(caller)
         else:
-            self._launch(image, copy_stream)
+            self._launch(image, copy_stream, caller_stream if caller_stream is not None else torch.cuda.current_stream())
 
-    def _launch(self, image: torch.Tensor, copy_stream=None):
-        compute = torch.cuda.current_stream()
+    def _launch(self, image: torch.Tensor, copy_stream, compute):
         compute.wait_event(self.cloned)          # static outputs of the previous use of this plan were consumed
         if image.is_cuda:
             self.stem(image, out=self.stem_out)
@@ -362,19 +384,21 @@ class _InferencePlan:
             if copy_stream is None:
                 self.inp.copy_(image, non_blocking=True)
             else:
-                with torch.cuda.stream(copy_stream):
+                torch.cuda.set_stream(copy_stream)
+                try:
                     copy_stream.wait_event(self.done)    # the previous stem that read this buffer has run
                     self.inp.copy_(image, non_blocking=True)
-                    copied = torch.cuda.Event()
-                    copied.record(copy_stream)
-                compute.wait_event(copied)
+                    self.copied.record(copy_stream)
+                finally:
+                    torch.cuda.set_stream(compute)
+                compute.wait_event(self.copied)
             self.stem(self.inp, out=self.stem_out)
         self.graph.replay()
         ops.LAUNCHES[0] += self.n_kernels
         self.host_meta.copy_(self.meta, non_blocking=True)
         self.done.record(compute)
 
-    def results(self, model: "LSSD3D", post_stream=None, to_host: bool = False):
+    def results(self, model: "LSSD3D", post_stream=None, to_host: bool = False, caller_stream=None):
         """Wait for this plan's latest launch (not for later work on the stream), check the flags, and hand
         out fresh per-image tensors: the static buffers are copied on ``post_stream`` (device clones, or
         pinned-host copies when ``to_host``) so that the next steps already queued are not delayed."""
@@ -386,18 +410,19 @@ class _InferencePlan:
             raise RuntimeError("detect_objects: more than %d candidates above min_score for one (image, class)"
                                % _lib.SORT_MAX)
         counts = meta[:self.n]
-        current = torch.cuda.current_stream()
+        current = caller_stream if caller_stream is not None else torch.cuda.current_stream()
         stream = post_stream if post_stream is not None else current
-        with torch.cuda.stream(stream):
-            if to_host:
-                boxes = self.out.boxes.to("cpu", non_blocking=False)
-                labels = self.out.labels.to("cpu", non_blocking=False)
-                scores = self.out.scores.to("cpu", non_blocking=False)
-            else:
-                boxes, labels, scores = self.out.boxes.clone(), self.out.labels.clone(), self.out.scores.clone()
+        if stream is not current:
+            torch.cuda.set_stream(stream)
+        try:
+            buf = self.outbuf.to("cpu", non_blocking=False) if to_host else self.outbuf.clone()
             self.cloned.record(stream)
+        finally:
+            if stream is not current:
+                torch.cuda.set_stream(current)
         if not to_host and stream is not current:
             current.wait_event(self.cloned)      # later work on the caller's stream sees complete tensors
+        boxes, scores, labels, _ = self._views(buf, int(self.args[2]))
         return ([boxes[i, :k] for i, k in enumerate(counts)], [labels[i, :k] for i, k in enumerate(counts)],
                 [scores[i, :k] for i, k in enumerate(counts)])
 
@@ -472,7 +497,7 @@ class LSSD3D(_LightningBase):
         self.loss_fn = MultiBoxLoss(self.priors_cxcycz, threshold=threshold, alpha=alpha)
         self.defer_nan_check = False
         self.use_cuda_graph = True     # predict_step replays a captured forward+detect graph
-        self.pipeline_depth = int(os.environ.get("SSD3D_PIPELINE_DEPTH", "4"))   # batches in flight in predict_batches
+        self.pipeline_depth = int(os.environ.get("SSD3D_PIPELINE_DEPTH", "6"))   # batches in flight in predict_batches
         self.tail_from = int(os.environ.get("SSD3D_TAIL_FROM", "3"))   # first backbone layer on the high-priority stream
         self._plans = {}
 
@@ -599,7 +624,7 @@ class LSSD3D(_LightningBase):
         if ts is None:
             ts = list(self.parameters()) + list(self.buffers())
             self.__dict__["_state_tensors"] = ts
-        return sum(t._version for t in ts)
+        return sum(map(_VERSION_OF, ts))
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.get("_plans", {}).clear()
@@ -652,21 +677,22 @@ class LSSD3D(_LightningBase):
             self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
             self.__dict__["_post_stream"] = torch.cuda.Stream(device=self.device)
         copy_stream, post_stream = self.__dict__["_copy_stream"], self.__dict__["_post_stream"]
+        caller = torch.cuda.current_stream()
         depth = max(1, int(self.pipeline_depth))
         inflight = []
         slot = 0
         for batch in batches:
             image = batch["img"]
             if len(inflight) == depth:
-                yield inflight.pop(0).results(self, post_stream, to_host)
+                yield inflight.pop(0).results(self, post_stream, to_host, caller)
             plan = self._plan_for(image, slot)
             if image.dtype != plan.inp.dtype:
                 image = image.to(plan.inp.dtype)
-            plan.launch(image, copy_stream, own_stream=True)
+            plan.launch(image, copy_stream, own_stream=True, caller_stream=caller)
             inflight.append(plan)
             slot = (slot + 1) % depth
         while inflight:
-            yield inflight.pop(0).results(self, post_stream, to_host)
+            yield inflight.pop(0).results(self, post_stream, to_host, caller)
 
     def _predict_step_eager(self, image):
         prev = self.defer_nan_check
