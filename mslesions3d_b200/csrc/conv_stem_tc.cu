@@ -60,7 +60,8 @@ __device__ __forceinline__ float relu_nan1(float v, float floor) {
 //   PREVIOUS tile (TMEM -> scale/shift/ReLU -> 64-byte store) while this tile's UMMAs run.
 // Weights (B operand), scale and shift are loaded once per CTA; 3 CTAs are resident per SM.
 template <typename TIn, int CIN>
-__global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__ CUtensorMap tmX, const StemParams p) {
+__global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                         const __grid_constant__ CUtensorMap tmY, const StemParams p) {
   constexpr int KREAL = 27 * CIN;
   constexpr int KPAD = (KREAL <= 64) ? 64 : 128;
   constexpr int KB = KPAD / 64;
@@ -73,11 +74,14 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // 2 x KB x (128 rows x 128 B)
   uint8_t* sB = sA + 2 * KB * 16384;                    // KB x (32 rows x 128 B)
-  uint8_t* ctl = sB + KB * 4096;                        // mbarriers + TMEM slot (128 B)
+  uint8_t* ctl = sB + KB * 4096;                        // mbarriers + TMEM slot (128 B), then scale/shift (256 B)
   const int tile_elems = CIN * p.TDI * p.THI * p.TWI;
   const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(TIn));
   const uint32_t tile_pitch = (tile_bytes + 127u) & ~127u;
-  uint8_t* sX = ctl + 128;                              // 2 x input halo tile [CIN][TDI][THI][TWI] of TIn
+  float* s_sc = reinterpret_cast<float*>(ctl + 128);    // BN scale[32], shift[32]: shared, not 64 registers per
+  float* s_sh = s_sc + 32;                              // thread, so that a 4th CTA fits on the SM
+  uint8_t* sOut = ctl + 384 + 640;                      // 128 rows x 64 B output staging tile (1024-aligned), 64B-swizzled
+  uint8_t* sX = sOut + 8192;                            // 2 x input halo tile [CIN][TDI][THI][TWI] of TIn
   uint64_t* bar_in = reinterpret_cast<uint64_t*>(ctl);  // [2]
   uint64_t* bar_mma = bar_in + 2;                       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_in + 4);
@@ -90,6 +94,7 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
   // allocation fully converged (a lane still inside a divergent branch makes it an illegal instruction)
   if (tid == 32) {
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
     mbar_init(&bar_in[0], 1); mbar_init(&bar_in[1], 1);
     mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1);
     fence_barrier_init();
@@ -129,12 +134,8 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.wt + row * KPAD + ch * 8));
     *reinterpret_cast<uint4*>(sB + (ch >> 3) * 4096 + sw128_offset(row, ch & 7)) = v;
   }
-  float sc[32], sh[32];
-#pragma unroll
-  for (int c = 0; c < 32; c += 4) {
-    *reinterpret_cast<float4*>(&sc[c]) = __ldg(reinterpret_cast<const float4*>(p.scale + c));
-    *reinterpret_cast<float4*>(&sh[c]) = __ldg(reinterpret_cast<const float4*>(p.shift + c));
-  }
+  if (tid < 32) { s_sc[tid] = __ldg(p.scale + tid); s_sh[tid] = __ldg(p.shift + tid); }
+  __syncthreads();
 
   // this thread's output voxel inside a tile (w fastest) and its offset inside the halo tile
   const int wl = tid % p.TW;
@@ -150,25 +151,45 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
     tmem_ld_32x32b_x16(taddr + (uint32_t)(buf * 32), v0);
     tmem_ld_32x32b_x16(taddr + (uint32_t)(buf * 32 + 16), v1);
     tmem_ld_wait();
-    int t = tile;
-    const int wo = (t % p.tiles_w) * p.TW + wl; t /= p.tiles_w;
-    const int ho = (t % p.tiles_h) * p.TH + hl; t /= p.tiles_h;
-    const int dz = (t % p.tiles_d) * p.TD + dl; t /= p.tiles_d;
-    if (wo < p.Wo && ho < p.Ho && dz < p.Do) {
-      uint4* dst = reinterpret_cast<uint4*>(p.y + ((((long long)t * p.Do + dz) * p.Ho + ho) * p.Wo + wo) * 32);
+    // BN + activation, then the tile leaves through ONE TMA store: a thread owns a 64-byte row, so direct 16-byte
+    // stores would touch 32 different rows per warp instruction (half-used sectors, 4 instructions per row)
+    uint4 o4[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t o[4];
+    for (int q = 0; q < 4; ++q) {
+      uint32_t o[4];
+      float sc[8], sh[8];
+      *reinterpret_cast<float4*>(&sc[0]) = *reinterpret_cast<const float4*>(s_sc + q * 8);
+      *reinterpret_cast<float4*>(&sc[4]) = *reinterpret_cast<const float4*>(s_sc + q * 8 + 4);
+      *reinterpret_cast<float4*>(&sh[0]) = *reinterpret_cast<const float4*>(s_sh + q * 8);
+      *reinterpret_cast<float4*>(&sh[4]) = *reinterpret_cast<const float4*>(s_sh + q * 8 + 4);
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int c = q * 8 + h * 2;
-          const float a0 = __uint_as_float(c < 16 ? v0[c & 15] : v1[c & 15]);
-          const float a1 = __uint_as_float(c + 1 < 16 ? v0[(c + 1) & 15] : v1[(c + 1) & 15]);
-          o[h] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(a0, sc[c]), sh[c]), p.floor),
-                             relu_nan1(__fadd_rn(__fmul_rn(a1, sc[c + 1]), sh[c + 1]), p.floor));
-        }
-        dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+      for (int h = 0; h < 4; ++h) {
+        const int c = q * 8 + h * 2;
+        const float a0 = __uint_as_float(c < 16 ? v0[c & 15] : v1[c & 15]);
+        const float a1 = __uint_as_float(c + 1 < 16 ? v0[(c + 1) & 15] : v1[(c + 1) & 15]);
+        o[h] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(a0, sc[h * 2]), sh[h * 2]), p.floor),
+                           relu_nan1(__fadd_rn(__fmul_rn(a1, sc[h * 2 + 1]), sh[h * 2 + 1]), p.floor));
       }
+      o4[q] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read sOut
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q)      // 64-byte swizzle: 16-byte chunk ^= (row >> 1) & 3
+      *reinterpret_cast<uint4*>(sOut + tid * 64 + ((q ^ ((tid >> 1) & 3)) << 4)) = o4[q];
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 32) {
+      int t = tile;
+      const int w0 = (t % p.tiles_w) * p.TW; t /= p.tiles_w;
+      const int h0 = (t % p.tiles_h) * p.TH; t /= p.tiles_h;
+      const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
+      asm volatile(
+          "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+              reinterpret_cast<uint64_t>(&tmY)),
+          "r"(smem_u32(sOut)), "r"(0), "r"(w0), "r"(h0), "r"(d0), "r"(t)
+          : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   };
 
@@ -268,6 +289,7 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
     epilogue(prev_tile, pb);
   }
 
+  if (tid == 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every output tile has landed
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -303,14 +325,23 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
     if (r != CUDA_SUCCESS) return SSD3D_ERR_TMA;
   }
   const size_t tile_pitch = ((size_t)CIN * p.TDI * p.THI * p.TWI * sizeof(TIn) + 127) & ~(size_t)127;
-  const size_t smem = 1024 + (size_t)KB * (2 * 16384 + 4096) + 128 + 2 * tile_pitch + 128;
+  const size_t smem = 1024 + (size_t)KB * (2 * 16384 + 4096) + 1024 + 8192 + 2 * tile_pitch + 128;
+  CUtensorMap tmY;
+  {
+    const uint64_t dims[5] = {32ull, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.Do, (uint64_t)p.N};
+    const uint64_t strides[4] = {64ull, (uint64_t)p.Wo * 64, (uint64_t)p.Ho * p.Wo * 64, (uint64_t)p.Do * p.Ho * p.Wo * 64};
+    const uint32_t box[5] = {32u, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TD, 1u};
+    if (make_tma_bf16(&tmY, p.y, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return SSD3D_ERR_TMA;
+  }
   cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<TIn, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  // persistent grid: 3 CTAs per SM (smem ~53 KB, 64 TMEM columns each), never more CTAs than tiles
+  // persistent grid: up to 4 CTAs per SM (smem ~54 KB, 64 TMEM columns, <= 128 registers each), never more CTAs
+  // than tiles
   const int n_sm = persistent_sms();
   const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
-  const unsigned grid = (unsigned)(tiles < 3ll * n_sm ? tiles : 3ll * n_sm);
-  SSD3D_LAUNCH_PDL((stem_tc_kernel<TIn, CIN>), dim3(grid), dim3(128), smem, st, tm, p);
+  const long long per_sm = (smem + 1024) * 4 <= 227 * 1024 ? 4 : ((smem + 1024) * 3 <= 227 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1));
+  const unsigned grid = (unsigned)(tiles < per_sm * n_sm ? tiles : per_sm * n_sm);
+  SSD3D_LAUNCH_PDL((stem_tc_kernel<TIn, CIN>), dim3(grid), dim3(128), smem, st, tm, tmY, p);
   return SSD3D_OK;
 }
 
