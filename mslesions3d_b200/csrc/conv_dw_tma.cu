@@ -189,6 +189,176 @@ __global__ void __launch_bounds__(256, 1) dw_tma_kernel(const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Depthwise WEIGHT gradient with the same tiling: dw[c][tap] = sum_o dz[o][c] * x[S*o + tap - 1][c].
+// Roles swapped w.r.t. the forward kernel: the 27 x 4 accumulators live in registers for the whole kernel, the
+// 4-channel dz vector of each output is the multiplier.  At the end the threads of a CTA that own the same
+// channels are reduced (warp shuffles, then shared memory, fixed order) into one (32 channels x 27) block of the
+// CTA's partial slab; ssd3d_dwconv3d_wgrad sums the slabs.
+// ------------------------------------------------------------------------------------------------
+template <int S, int WT, int TD, int TH, int TW>
+__global__ void __launch_bounds__(256, 1) dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm,
+                                                              const DwTmaParams p, const __nv_bfloat16* __restrict__ dz,
+                                                              float* __restrict__ partial) {
+  using T = DwTile<S, WT, TD, TH, TW>;
+  constexpr int NI = (WT - 1) * S + 3;
+  extern __shared__ uint8_t dw_raw[];
+  const uint32_t raw = smem_u32(dw_raw);
+  uint8_t* smem = dw_raw + ((128u - (raw & 127u)) & 127u);
+  uint8_t* tiles = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * T::PITCH);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
+  const int chunk = blockIdx.x % p.chunks;
+  const int cbase = chunk * DW_CB;
+  const int first = blockIdx.x / p.chunks;
+  const int step = gridDim.x / p.chunks;
+  auto decode = [&](int tile, int& ow0, int& oh0, int& od0, int& n) {
+    int t = tile;
+    ow0 = (t % p.tiles_w) * TW; t /= p.tiles_w;
+    oh0 = (t % p.tiles_h) * TH; t /= p.tiles_h;
+    od0 = (t % p.tiles_d) * TD;
+    n = t / p.tiles_d;
+  };
+  auto issue = [&](int tile, int buf) {
+    int ow0, oh0, od0, n;
+    decode(tile, ow0, oh0, od0, n);
+    mbar_arrive_expect_tx(&full[buf], (uint32_t)T::BYTES);
+    tma_load_5d(tiles + (size_t)buf * T::PITCH, &tm, &full[buf], cbase, ow0 * S - 1, oh0 * S - 1, od0 * S - 1, n);
+  };
+  if (tid == 0 && first < p.spatial_tiles) issue(first, 0);
+  const int cv = tid & 7;
+  const int c0 = cbase + cv * 4;
+  f32x2 acc[27][2];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) { acc[t][0] = 0ull; acc[t][1] = 0ull; }
+
+  int it = 0;
+  for (int tile = first; tile < p.spatial_tiles; tile += step, ++it) {
+    const int buf = it & 1;
+    const int next = tile + step;
+    if (tid == 0 && next < p.spatial_tiles) issue(next, buf ^ 1);
+    int ow0, oh0, od0, n;
+    decode(tile, ow0, oh0, od0, n);
+    mbar_wait(&full[buf], (uint32_t)((it >> 1) & 1));
+    const uint8_t* in = tiles + (size_t)buf * T::PITCH;
+#pragma unroll 1
+    for (int item = tid; item < T::ITEMS; item += 256) {
+      int r = item >> 3;
+      const int h = r % TH; r /= TH;
+      const int wq = r % T::WQ;
+      const int d = r / T::WQ;
+      const int od = od0 + d, oh = oh0 + h, owb = ow0 + wq * WT;
+      if (od >= p.Do || oh >= p.Ho || owb >= p.Wo) continue;
+      const __nv_bfloat16* grow = dz + ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo) * p.C + c0;
+      f32x2 g[WT][2];
+#pragma unroll
+      for (int ow = 0; ow < WT; ++ow) {
+        uint2 u = make_uint2(0u, 0u);
+        if (owb + ow < p.Wo) u = __ldg(reinterpret_cast<const uint2*>(grow + (long long)(owb + ow) * p.C));
+        g[ow][0] = bf16x2_to_f32x2(u.x);
+        g[ow][1] = bf16x2_to_f32x2(u.y);
+      }
+      const uint8_t* base = in + ((size_t)(((d * S) * T::THI + h * S) * T::TWI + wq * WT * S) * DW_CB + cv * 4) * 2;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint8_t* row = base + (size_t)((kd * T::THI + kh) * T::TWI) * DW_CB * 2;
+          f32x2 x[NI][2];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            const uint2 u = *reinterpret_cast<const uint2*>(row + i * DW_CB * 2);
+            x[i][0] = bf16x2_to_f32x2(u.x);
+            x[i][1] = bf16x2_to_f32x2(u.y);
+          }
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int t = (kd * 3 + kh) * 3 + kw;
+#pragma unroll
+            for (int ow = 0; ow < WT; ++ow) {
+              ffma2(acc[t][0], x[ow * S + kw][0], g[ow][0]);
+              ffma2(acc[t][1], x[ow * S + kw][1], g[ow][1]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- reduce over the threads that own the same 4 channels: lanes l, l^8, l^16, l^24 of a warp, then the 8 warps ----
+  float* red = reinterpret_cast<float*>(tiles);      // [8 warps][8 cv][108]: 27.6 KB of the (now idle) tile buffers
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+#pragma unroll
+    for (int hsel = 0; hsel < 2; ++hsel) {
+      float a, b;
+      unpack_f32x2(acc[t][hsel], a, b);
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      b += __shfl_xor_sync(0xffffffffu, b, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      b += __shfl_xor_sync(0xffffffffu, b, 16);
+      if (lane < 8) {
+        red[(warp * 8 + cv) * 108 + t * 4 + hsel * 2] = a;
+        red[(warp * 8 + cv) * 108 + t * 4 + hsel * 2 + 1] = b;
+      }
+    }
+  }
+  __syncthreads();
+  // partial slab [C][27] of this CTA's spatial index; this CTA fills rows cbase .. cbase+31
+  float* dst = partial + (size_t)(blockIdx.x / p.chunks) * p.C * 27;
+  for (int i = tid; i < 32 * 27; i += 256) {
+    const int ch = i / 27, t = i % 27;         // ch = cv*4 + j
+    const int cvv = ch >> 2, j = ch & 3;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[(w * 8 + cvv) * 108 + t * 4 + j];
+    dst[(size_t)(cbase + ch) * 27 + t] = s;
+  }
+}
+
+template <int S, int WT, int TD, int TH, int TW>
+static int launch_dw_wgrad_tma(const void* x, DwTmaParams& p, const __nv_bfloat16* dz, float* partial, int max_slabs,
+                               int* slabs_out, cudaStream_t st) {
+  using T = DwTile<S, WT, TD, TH, TW>;
+  p.tiles_w = (p.Wo + TW - 1) / TW;
+  p.tiles_h = (p.Ho + TH - 1) / TH;
+  p.tiles_d = (p.Do + TD - 1) / TD;
+  p.chunks = p.C / DW_CB;
+  const long long spatial = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
+  if (spatial * p.chunks > 0x3fffffffll) return SSD3D_ERR_UNSUPPORTED;
+  p.spatial_tiles = (int)spatial;
+  CUtensorMap tm;
+  const uint64_t dims[5] = {(uint64_t)p.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.N};
+  const uint64_t strides[4] = {(uint64_t)p.C * 2, (uint64_t)p.W * p.C * 2, (uint64_t)p.H * p.W * p.C * 2,
+                               (uint64_t)p.D * p.H * p.W * p.C * 2};
+  const uint32_t box[5] = {(uint32_t)DW_CB, (uint32_t)T::TWI, (uint32_t)T::THI, (uint32_t)T::TDI, 1u};
+  if (make_tma_bf16(&tm, x, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return SSD3D_ERR_TMA;
+  size_t smem = T::SMEM;
+  if (smem < 128 + 8 * 8 * 108 * 4 + 64) smem = 128 + 8 * 8 * 108 * 4 + 64;
+  cudaError_t e = cudaFuncSetAttribute(dw_wgrad_tma_kernel<S, WT, TD, TH, TW>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int n_sm = persistent_sms();
+  long long grid = n_sm;
+  if (grid > spatial * p.chunks) grid = spatial * p.chunks;
+  grid = grid / p.chunks * p.chunks;
+  if (grid < p.chunks) grid = p.chunks;
+  if (grid / p.chunks > max_slabs) return SSD3D_ERR_UNSUPPORTED;
+  *slabs_out = (int)(grid / p.chunks);
+  SSD3D_LAUNCH_PDL((dw_wgrad_tma_kernel<S, WT, TD, TH, TW>), dim3((unsigned)grid), dim3(256), smem, st, tm, p, dz, partial);
+  return SSD3D_OK;
+}
+
 template <int S, int WT, int TD, int TH, int TW>
 static int launch_dw_tma(const void* x, DwTmaParams& p, cudaStream_t st) {
   using T = DwTile<S, WT, TD, TH, TW>;
@@ -235,4 +405,18 @@ int ssd3d_dwconv3d_tma(const void* x, const void* w, const float* scale, const f
   p.scale = scale; p.shift = shift; p.y = static_cast<__nv_bfloat16*>(y); p.floor = floor;
   if (stride == 2) return launch_dw_tma<2, 2, 4, 4, 8>(x, p, st);
   return launch_dw_tma<1, 4, 4, 8, 8>(x, p, st);
+}
+
+// Weight gradient through the same tiles; fills `slabs` partial slabs of (C, 27) floats in `partial`
+// (capacity max_slabs) that the caller sums.  SSD3D_ERR_UNSUPPORTED -> use the direct kernel.
+int ssd3d_dwconv3d_wgrad_tma(const void* dz, const void* x, int N, int C, int D, int H, int W, int stride,
+                             float* partial, int max_slabs, int* slabs, cudaStream_t st) {
+  const int Do = (D - 1) / stride + 1, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  if (C % DW_CB || Wo < 8 || Ho < 4 || Do < 4) return SSD3D_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return SSD3D_ERR_UNSUPPORTED;
+  DwTmaParams p{};
+  p.N = N; p.C = C; p.D = D; p.H = H; p.W = W; p.Do = Do; p.Ho = Ho; p.Wo = Wo;
+  const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(dz);
+  if (stride == 2) return launch_dw_wgrad_tma<2, 2, 4, 4, 8>(x, p, g, partial, max_slabs, slabs, st);
+  return launch_dw_wgrad_tma<1, 4, 4, 8, 8>(x, p, g, partial, max_slabs, slabs, st);
 }

@@ -628,22 +628,22 @@ __global__ void __launch_bounds__(256) dw_dgrad_kernel(const bf16* __restrict__ 
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-  for (int kd = 0; kd < 3; ++kd) {
+  // only taps with (i + 1 - k) divisible by S reach an output: for S = 2 that is k = parity, parity + 2
+  // (1 or 2 taps per axis, 3.4 of 27 on average) -- walk exactly those
+  const int pd = (S == 2) ? ((di + 1) & 1) : 0, ph = (S == 2) ? ((hi + 1) & 1) : 0, pw = (S == 2) ? ((wi + 1) & 1) : 0;
+  for (int kd = pd; kd < 3; kd += S) {
     const int td = di + 1 - kd;
-    if (td < 0 || (S == 2 && (td & 1))) continue;
+    if (td < 0) continue;
     const int od = td / S;
     if (od >= Do) continue;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
+    for (int kh = ph; kh < 3; kh += S) {
       const int th = hi + 1 - kh;
-      if (th < 0 || (S == 2 && (th & 1))) continue;
+      if (th < 0) continue;
       const int oh = th / S;
       if (oh >= Ho) continue;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
+      for (int kw = pw; kw < 3; kw += S) {
         const int tw = wi + 1 - kw;
-        if (tw < 0 || (S == 2 && (tw & 1))) continue;
+        if (tw < 0) continue;
         const int ow = tw / S;
         if (ow >= Wo) continue;
         float gf[8], wf[8];
@@ -1002,12 +1002,30 @@ static int dw_wgrad_plan(long long Mo, int C, int* threads, int* G, long long* v
 
 extern "C" int64_t ssd3d_dw_wgrad_workspace_bytes(int C) { return (int64_t)592 * C * 27 * 4; }
 
+// conv_dw_tma.cu
+int ssd3d_dwconv3d_wgrad_tma(const void* dz, const void* x, int N, int C, int D, int H, int W, int stride,
+                             float* partial, int max_slabs, int* slabs, cudaStream_t st);
+
 extern "C" int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C, int D, int H, int W, int stride,
                                     float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!dz || !x || !dw || !workspace || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
   if (stride != 1 && stride != 2) return SSD3D_ERR_ARG;
   const int Do = (D - 1) / stride + 1, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   const long long Mo = (long long)N * Do * Ho * Wo;
+  if (C > 0 && workspace_bytes >= ssd3d_dw_wgrad_workspace_bytes(C)) {
+    // large maps: TMA halo tiles, register-resident accumulators (conv_dw_tma.cu)
+    int slabs = 0;
+    const int rc = ssd3d_dwconv3d_wgrad_tma(dz, x, N, C, D, H, W, stride, static_cast<float*>(workspace), 592, &slabs,
+                                            static_cast<cudaStream_t>(stream));
+    if (rc == SSD3D_OK) {
+      const long long total = (long long)C * 27;
+      SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0,
+                       static_cast<cudaStream_t>(stream), (const float*)workspace, slabs, (long long)C * 27, C, 27, 27,
+                       27, dw);
+      return SSD3D_OK;
+    }
+    if (rc != SSD3D_ERR_UNSUPPORTED) return rc;
+  }
   int threads, G;
   long long vpb;
   const int B = dw_wgrad_plan(Mo, C, &threads, &G, &vpb);

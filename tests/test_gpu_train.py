@@ -142,7 +142,10 @@ def test_pointwise_raw_dgrad_wgrad(cin, cout, n, size):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("c,n,size,stride", [(32, 2, (12, 12, 12), 2), (64, 1, (9, 7, 11), 2), (128, 2, (6, 6, 6), 1),
                                              (256, 1, (5, 4, 3), 2), (512, 2, (2, 2, 2), 1), (128, 1, (7, 8, 9), 1),
-                                             (32, 1, (24, 24, 24), 2)])
+                                             (32, 1, (24, 24, 24), 2),
+                                             # large enough for the TMA halo-tile forward / weight-gradient kernels
+                                             (32, 2, (32, 32, 32), 2), (64, 1, (24, 20, 28), 2), (128, 1, (16, 16, 16), 1),
+                                             (32, 1, (19, 21, 17), 2), (96, 2, (9, 12, 10), 1)])
 def test_depthwise_raw_dgrad_wgrad(c, n, size, stride):
     ops = _ops()
     g = torch.Generator().manual_seed(c + stride)
