@@ -306,49 +306,45 @@ def main():
     stem = model.base.features[0]
     w, scale, shift = stem._pack()
     sd_stride = 2
-    evs = []
-    for i in range(3):
-        ops.stem_conv_bn_relu(dev_bf16[i % N_ROTATE], w, scale, shift, sd_stride)
-    torch.cuda.synchronize()
-    for i in range(args.steps):
+    def kernel_ms(fn, n_launch):
+        """Average duration of n_launch back-to-back launches (one event pair around all of them, so the
+        per-launch event/launch overhead is not attributed to the kernel); inputs rotate over > L2 bytes."""
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        ops.stem_conv_bn_relu(dev_bf16[i % N_ROTATE], w, scale, shift, sd_stride)
+        for i in range(n_launch):
+            fn(i)
         b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n_launch
+
+    stem_out = ops.stem_conv_bn_relu(dev_bf16[0], w, scale, shift, sd_stride)
+    n_launch = max(20, args.steps)
+    k_ms = kernel_ms(lambda i: ops.stem_conv_bn_relu(dev_bf16[i % N_ROTATE], w, scale, shift, sd_stride, out=stem_out),
+                     n_launch)
     vox_out = BATCH * (SIZE[0] // 2) * (SIZE[1] // 2) * (SIZE[2] // 2)
     algo_bytes = in_bytes + vox_out * 32 * 2 + 27 * CHANNELS * 32 * 4
     achieved = algo_bytes / (k_ms / 1000.0) / 1e9
     roofline = {"kernel": "stem_tc_kernel<bf16,2> (dense 3x3x3 conv 2->32 + BN + ReLU, tcgen05 implicit GEMM)", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic("r01_ncu_full_prof_stem_r01.json"),
-                "traffic_source": "profiles/r01_ncu_full_prof_stem_r01.json (ncu --set full, dram read+write per launch; "
-                                  "most of the 134 MB output is still in the 126 MB L2 when the kernel ends)",
+                "traffic": ncu_traffic("r01_ncu_full_stem_final.json"),
+                "traffic_source": "profiles/r01_ncu_full_stem_final.json (ncu --set full, dram read+write per launch; "
+                                  "part of the 134 MB output is still in the 126 MB L2 when the kernel ends)",
+                "timing": "%d back-to-back launches between one CUDA event pair, inputs rotating over 268 MB" % n_launch,
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms, "peak_source": peak_src}
 
     # second HBM-bound kernel the north star names: the first depthwise conv (32 ch, stride 2, 64^3 -> 32^3)
     blk = model.base.features[1]
     wd, s1, b1 = blk._pack()[:3]
-    f0 = ops.stem_conv_bn_relu(dev_bf16[0], w, scale, shift, sd_stride)
+    f0 = stem_out
     f0s = [f0, f0.clone()]      # 2 x 134 MB > L2
-    for i in range(3):
-        ops.dwconv3d_bn_relu(f0s[i % 2], wd, s1, b1, 2)
-    torch.cuda.synchronize()
-    evs = []
-    for i in range(args.steps):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ops.dwconv3d_bn_relu(f0s[i % 2], wd, s1, b1, 2)
-        b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    dw_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    dw_ms = kernel_ms(lambda i: ops.dwconv3d_bn_relu(f0s[i % 2], wd, s1, b1, 2), n_launch)
     dw_bytes = f0.numel() * 2 + (f0.numel() // 8) * 2 + 54 * 32
     roofline_dw = {"kernel": "dw_tma_kernel<2,2,4,4,8> (depthwise 3x3x3, 32 ch, stride 2 + BN + ReLU, TMA halo tiles)",
                    "bound": "hbm", "achieved": dw_bytes / (dw_ms / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
-                   "frac": dw_bytes / (dw_ms / 1000.0) / 1e9 / peak, "traffic": None,
+                   "frac": dw_bytes / (dw_ms / 1000.0) / 1e9 / peak, "traffic": ncu_traffic("r01_ncu_full_dw_final.json"),
                    "algorithmic_bytes_per_launch": dw_bytes, "kernel_ms": dw_ms}
     del f0s, f0
 

@@ -4,8 +4,10 @@ Same flags and the same ``predict_example(...)`` signature.  The reference reads
 MONAI/nibabel (absent here, and data loading is outside the accelerated path): this entry point accepts
 either a ``.npy``/``.pt`` stack of volumes at ``--dataset_path`` or, by default, generates the synthetic
 cube volumes of ``generate_artificial_dataset.py`` in memory.  Checkpoints are the reference's
-PyTorch-Lightning ``.ckpt`` files (``state_dict`` + ``hyper_parameters``).  Detections are written as
-``predictions.json`` (per subject: boxes in fractional boundary coordinates, labels, scores).
+PyTorch-Lightning ``.ckpt`` files (``state_dict`` + ``hyper_parameters``).  Outputs follow the reference's
+(predict.py:155-232,85-150,279-281): per subject ``sub-{id}_preds.csv`` / ``.json`` and the box-outline volume
+(``.npy`` instead of NIfTI), ``aa_metrics_per_subject_(min_IoU=0.5|0.1).json`` from the device-side
+``calculate_mAP``, plus one ``predictions.json`` with every subject's boxes / labels / scores.
 """
 from __future__ import annotations
 
@@ -58,6 +60,91 @@ def load_volumes(dataset_path, n_subjects, channels, size, percentage=1.0):
     return vols[:n]
 
 
+def box_outline_segmentation(det_boxes, det_labels, det_scores, img_shape, min_score):
+    """The reference's prediction volume (predict.py:181-216): box j's outline is painted with the value j+1 into
+    an array of the image's shape; boxes below ``min_score`` or with label 0 (the "nothing found" placeholder,
+    ssd3d.py:437-440) are skipped.  -> (volume, scores_map [(label_id, score)], infos {label_id: (fractional box,
+    voxel box, label, score)})."""
+    seg = np.zeros(tuple(img_shape))
+    scores_map, infos = [], {}
+    shape2 = torch.tensor(list(img_shape) * 2, dtype=torch.float32)
+    for j in range(det_boxes.shape[0]):
+        score = float(det_scores[j])
+        scores_map.append((j + 1, score))
+        if score < min_score:
+            continue
+        label = int(det_labels[j])
+        if label == 0:
+            continue
+        frac = [float(v) for v in det_boxes[j].tolist()]
+        box = (torch.clip(det_boxes[j].float().cpu(), 0, 1) * shape2).numpy().astype(int).tolist()
+        x0, y0, z0, x1, y1, z1 = box
+        x0, y0, z0 = max(x0, 0), max(y0, 0), max(z0, 0)
+        x1, y1, z1 = min(x1 + 1, img_shape[0] - 1), min(y1 + 1, img_shape[1] - 1), min(z1 + 1, img_shape[2] - 1)
+        seg[x0, y0:y1, z0:z1] = j + 1
+        seg[x1, y0:y1, z0:z1] = j + 1
+        seg[x0:x1, y0, z0:z1] = j + 1
+        seg[x0:x1, y1, z0:z1] = j + 1
+        seg[x0:x1, y0:y1, z0] = j + 1
+        seg[x0:x1, y0:y1, z1] = j + 1
+        seg[x0:x1, y1, z1] = j + 1
+        seg[x1, y0:y1, z1] = j + 1
+        seg[x1, y1, z0:z1] = j + 1
+        seg[x1, y1, z1] = j + 1
+        infos[j + 1] = (frac, box, label, score)
+    return seg, scores_map, infos
+
+
+def save_predictions_example(subjects, img_shape, det_locs, det_labels, det_scores, min_score=0.5,
+                             output_dir=r"./predictions", save_images=True):
+    """Per subject ``sub-{id}_preds.csv`` (label_id, score), ``sub-{id}_preds.json`` (the reference's ``all_infos``)
+    and the box-outline volume (predict.py:155-232).  The reference writes the volume as NIfTI through nibabel,
+    which is absent here: it is saved as ``sub-{id}_preds.npy``."""
+    if not pexists(output_dir):
+        os.makedirs(output_dir)
+    for i, subj in enumerate(subjects):
+        seg, scores_map, infos = box_outline_segmentation(det_locs[i].cpu(), det_labels[i].cpu(), det_scores[i].cpu(),
+                                                          img_shape, min_score)
+        if save_images:
+            np.save(pjoin(output_dir, f"sub-{subj}_preds.npy"), seg.astype(np.uint16))
+        with open(pjoin(output_dir, f"sub-{subj}_preds.csv"), "w") as f:
+            f.write(",label_id,score\n")
+            for r, (lid, sc) in enumerate(scores_map):
+                f.write("%d,%d,%r\n" % (r, lid, sc))
+        with open(pjoin(output_dir, f"sub-{subj}_preds.json"), "w") as f:
+            json.dump(infos, f)
+
+
+def compute_subjects_mAP(model, subjects, det, gt_boxes, gt_labels, output_dir=r"./predictions", min_iou=0.5):
+    """Per-subject detection metrics with the device-side ``calculate_mAP`` (predict.py:85-150), written to
+    ``aa_metrics_per_subject_(min_IoU=...).json`` like the reference."""
+    from .utils import calculate_mAP
+
+    def convert(v):
+        if torch.is_tensor(v):
+            return v.cpu().item() if v.numel() == 1 else v.cpu().tolist()
+        return v
+
+    det_locs, det_labels, det_scores = det
+    all_metrics = {}
+    for i, subj in enumerate(subjects):
+        gb = torch.as_tensor(gt_boxes[i]).to(device).reshape(-1, 6).float()
+        gl = torch.as_tensor(gt_labels[i]).to(device).long()
+        out = calculate_mAP([det_locs[i]], [det_labels[i]], [det_scores[i]], [gb], [gl],
+                            [torch.zeros((gl.shape[0],), dtype=torch.bool, device=device)], min_overlap=min_iou,
+                            return_detail=True)
+        metrics = {}
+        for key, value in out.items():
+            if isinstance(value, dict):
+                metrics[key] = {str(k): convert(v) for k, v in value.items()}
+            else:
+                metrics[key] = convert(value)
+        all_metrics[str(subj)] = metrics
+    with open(pjoin(output_dir, f"aa_metrics_per_subject_(min_IoU={min_iou}).json"), "w") as f:
+        json.dump(all_metrics, f, indent=4)
+    return all_metrics
+
+
 def predict_example(model_path, output_dir, dataset_path, dataset_name, n_classes=1, subject=None, percentage=1.,
                     predict_subset="train", min_score=0.5, top_k=10, num_workers=8, save_images=True, model_name=None,
                     batch_size=8, n_subjects=16, model=None):
@@ -74,22 +161,39 @@ def predict_example(model_path, output_dir, dataset_path, dataset_name, n_classe
     model.top_k = top_k
     model.min_score = min_score
 
-    vols = load_volumes(dataset_path, n_subjects, model.input_channels, tuple(model.input_size), percentage)
+    gt_boxes = gt_labels = None
+    if dataset_path and os.path.isfile(dataset_path):
+        vols = load_volumes(dataset_path, n_subjects, model.input_channels, tuple(model.input_size), percentage)
+    else:   # synthetic cube volumes come with their ground-truth boxes (generate_artificial_dataset.py)
+        n = max(1, int(round(n_subjects * percentage)))
+        vols, gt_boxes, gt_labels = synthetic.make_batch(n, model.input_channels, tuple(model.input_size),
+                                                         with_boxes=True)
+    subjects = list(range(vols.shape[0]))
     if subject is not None:
-        vols = vols[int(subject):int(subject) + 1]
+        k = int(subject)
+        vols, subjects = vols[k:k + 1], subjects[k:k + 1]
+        if gt_boxes is not None:
+            gt_boxes, gt_labels = gt_boxes[k:k + 1], gt_labels[k:k + 1]
     det_locs, det_labels, det_scores = [], [], []
     with torch.no_grad():
-        for s in range(0, vols.shape[0], batch_size):
-            batch = {"img": torch.from_numpy(vols[s:s + batch_size]).pin_memory()}
-            locs, labels, scores = model.predict_step(batch, s // batch_size)
+        batches = ({"img": torch.from_numpy(vols[s:s + batch_size]).pin_memory()}
+                   for s in range(0, vols.shape[0], batch_size))
+        for locs, labels, scores in model.predict_batches(batches):      # Trainer.predict of the reference
             det_locs += locs
             det_labels += labels
             det_scores += scores
-    results = {str(i): {"boxes": det_locs[i].cpu().tolist(), "labels": det_labels[i].cpu().tolist(),
-                        "scores": det_scores[i].cpu().tolist()} for i in range(len(det_locs))}
-    if save_images and output_dir is not None:
-        with open(pjoin(output_dir, "predictions.json"), "w") as f:
-            json.dump(results, f)
+    results = {str(subjects[i]): {"boxes": det_locs[i].cpu().tolist(), "labels": det_labels[i].cpu().tolist(),
+                                  "scores": det_scores[i].cpu().tolist()} for i in range(len(det_locs))}
+    if output_dir is not None:
+        if save_images:
+            with open(pjoin(output_dir, "predictions.json"), "w") as f:
+                json.dump(results, f)
+        save_predictions_example(subjects, tuple(vols.shape[2:]), det_locs, det_labels, det_scores, min_score,
+                                 output_dir, bool(save_images))
+        if gt_boxes is not None:
+            for iou in (0.5, 0.1):    # predict.py:279-281
+                compute_subjects_mAP(model, subjects, (det_locs, det_labels, det_scores), gt_boxes, gt_labels,
+                                     output_dir=output_dir, min_iou=iou)
     return results
 
 

@@ -230,3 +230,37 @@ def test_whole_brain_layer0_config_end_to_end():
     probs, dec = _ops().decode_softmax(locs, scores, m.priors_cxcycz)
     wb, wl, ws, widx = O.detect_from_decoded(probs.cpu(), dec.cpu(), 0.5, 0.5, 100, return_indices=True)
     assert torch.equal(idx[0].cpu(), widx[0]) and torch.equal(sc[0].cpu(), ws[0]) and torch.equal(boxes[0].cpu(), wb[0])
+
+
+def test_predict_entry_point_writes_reference_style_outputs(tmp_path):
+    """predict.py:235-281 -- checkpoint in, per-subject csv/json/volume + per-subject mAP json out."""
+    import json
+    import os
+    from mslesions3d_b200 import predict
+    from mslesions3d_b200.ssd3d import LSSD3D
+    sd = O.random_state_dict(1, seed=9)
+    ckpt = tmp_path / "model.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": dict(n_classes=2, input_channels=1, input_size=(64, 64, 64))}, ckpt)
+    res = predict.predict_example(str(ckpt), str(tmp_path / "out"), dataset_path="", dataset_name="synthetic", n_classes=1,
+                                  min_score=0.3, top_k=20, n_subjects=5, batch_size=2)
+    out_dir = tmp_path / "out" / "synthetic" / "train_set" / "min_score_0.3"
+    assert len(res) == 5
+    for i in range(5):
+        for ext in ("csv", "json", "npy"):
+            assert os.path.isfile(out_dir / ("sub-%d_preds.%s" % (i, ext)))
+        info = json.load(open(out_dir / ("sub-%d_preds.json" % i)))
+        n_det = len(res[str(i)]["boxes"])
+        assert 1 <= n_det <= 20 and len(info) <= n_det
+        for frac, box, label, score in info.values():
+            assert label == 1 and score >= 0.3 and len(frac) == 6 and all(0 <= v <= 64 for v in box)
+    for iou in (0.5, 0.1):
+        m = json.load(open(out_dir / ("aa_metrics_per_subject_(min_IoU=%s).json" % iou)))
+        assert set(m) == {str(i) for i in range(5)} and all("mAP" in v and "n_true_boxes" in v for v in m.values())
+    # the same detections as a direct predict_step on the same volumes
+    model = LSSD3D.load_from_checkpoint(str(ckpt), min_score=0.3).cuda().eval()
+    model.top_k = 20
+    from mslesions3d_b200 import synthetic
+    vols = synthetic.make_batch(5, 1, (64, 64, 64))
+    with torch.no_grad():
+        b, l, s = model.predict_step({"img": torch.from_numpy(vols[:2])}, 0)
+    assert torch.equal(torch.tensor(res["0"]["scores"]), s[0].cpu()) and torch.equal(torch.tensor(res["1"]["boxes"]), b[1].cpu())

@@ -167,3 +167,17 @@ def test_synthetic_volumes_follow_the_generator_spec():
     assert all(b.shape[1] == 6 and (b[:, 3:] > b[:, :3]).all() for b in boxes)
     v2 = synthetic.make_batch(2, 2, (32, 32, 32), object_size=(4, 9))
     assert (vols == v2).all()
+
+
+def test_box_outline_segmentation_known_answer():
+    """predict.py:181-216: a box paints its outline with its 1-based index; placeholder / low scores are skipped."""
+    import torch
+    from mslesions3d_b200.predict import box_outline_segmentation
+    boxes = torch.tensor([[0.25, 0.25, 0.25, 0.5, 0.5, 0.5], [0., 0., 0., 1., 1., 1.], [0.1, 0.1, 0.1, 0.2, 0.2, 0.2]])
+    labels = torch.tensor([1, 0, 1])
+    scores = torch.tensor([0.9, 0.8, 0.2])
+    seg, scores_map, infos = box_outline_segmentation(boxes, labels, scores, (16, 16, 16), 0.5)
+    assert [m[0] for m in scores_map] == [1, 2, 3] and list(infos) == [1]
+    assert infos[1][1] == [4, 4, 4, 8, 8, 8] and infos[1][2] == 1
+    assert seg.max() == 1 and seg[4, 4, 4] == 1 and seg[9, 9, 9] == 1 and seg[6, 6, 6] == 0 and seg[4, 6, 6] == 1
+    assert int((seg == 1).sum()) == 6 * 6 * 6 - 4 * 4 * 4      # the shell of the 6^3 block [4, 9]^3
