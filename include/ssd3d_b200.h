@@ -255,10 +255,14 @@ int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C, int D, int
 /* One Adam step over flat fp32 buffers with torch.optim.Adam's arithmetic (L2 weight decay added to the
  * gradient, bias-corrected moments; ssd3d.py:716): elements [0, bias_start) use lr, [bias_start, n) use
  * lr_bias (the reference's "biases at 2x lr" group, ssd3d.py:715).  grad is multiplied by grad_scale first
- * (1/world_size after the NCCL sum).  step >= 1. */
+ * (1/world_size after the NCCL sum).  step >= 1.
+ * status (2 int32, may be NULL): a step whose gradient holds a NaN / Inf (a batch without any positive prior
+ * makes the MultiBox loss 0/0; the reference raises "Loss is NaN", ssd3d.py:938-940) is SKIPPED -- parameters and
+ * moments untouched -- with status[0] = 1 for this call and status[1] incremented; status[1] must be zeroed once
+ * by the caller.  After an all-reduce every rank sees the same non-finite values, so all ranks skip together. */
 int ssd3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                     int64_t bias_start, float lr, float lr_bias, float beta1, float beta2, float eps,
-                    float weight_decay, int step, float grad_scale, void* stream);
+                    float weight_decay, int step, float grad_scale, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Detection metrics of ONE class (utils.py:155-230 compute_metrics_per_class + the cumulative precision /

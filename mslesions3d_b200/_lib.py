@@ -68,7 +68,7 @@ SIGNATURES = {
     "ssd3d_map_class": (c_int, [P, P, P, c_int64, P, P, P, c_int64, c_float, P, c_int, P, P, P, P, P, P, P, P, P, P,
                                 c_int64, P]),
     "ssd3d_adam_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, c_float,
-                                c_int, c_float, P]),
+                                c_int, c_float, P, P]),
 }
 
 _lib = None

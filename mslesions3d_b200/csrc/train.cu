@@ -730,13 +730,32 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ 
 // Adam (torch.optim.Adam semantics: L2 weight decay folded into the gradient, bias-corrected moments)
 // over flat buffers; elements >= bias_start use lr_bias (the reference's "biases at twice the lr" group).
 // ------------------------------------------------------------------------------------------------
+// status[0] |= 1 when any gradient element is NaN / Inf (a batch without a single positive prior makes the
+// MultiBox loss 0/0, ssd3d.py:938-940: the reference raises; a fused step cannot raise without a host sync, so it
+// must at least not poison the parameters)
+__global__ void __launch_bounds__(256) grad_nonfinite_kernel(const float* __restrict__ g, long long n,
+                                                             int* __restrict__ status) {
+  pdl_wait();
+  pdl_launch_dependents();
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = g[i];
+    bad |= !(fabsf(x) <= 3.0e38f);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(status, 1);
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
                                                    long long bias_start, float lr, float lr_bias, float beta1,
                                                    float beta2, float eps, float weight_decay, float bc1,
-                                                   float bc2_sqrt, float grad_scale) {
+                                                   float bc2_sqrt, float grad_scale, int* __restrict__ status) {
   pdl_wait();
   pdl_launch_dependents();
+  if (status && (status[0] & 1)) {       // non-finite gradient: leave parameters and moments untouched
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(status + 1, 1);
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float pi = p[i];
     const float gi = g[i] * grad_scale + weight_decay * pi;
@@ -1050,12 +1069,18 @@ extern "C" int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C,
 // ---- optimizer ------------------------------------------------------------------------------------------
 extern "C" int ssd3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                                int64_t bias_start, float lr, float lr_bias, float beta1, float beta2, float eps,
-                               float weight_decay, int step, float grad_scale, void* stream) {
+                               float weight_decay, int step, float grad_scale, int32_t* status, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return SSD3D_ERR_ARG;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  SSD3D_LAUNCH_PDL(adam_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), param,
-                   grad, exp_avg, exp_avg_sq, (long long)n, (long long)bias_start, lr, lr_bias, beta1, beta2, eps,
-                   weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (status) {
+    cudaError_t e = cudaMemsetAsync(status, 0, 4, st);
+    if (e != cudaSuccess) return (int)e;
+    SSD3D_LAUNCH_PDL(grad_nonfinite_kernel, dim3(grid_for(n, 256, 148 * 4)), dim3(256), 0, st, grad, (long long)n, status);
+  }
+  SSD3D_LAUNCH_PDL(adam_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq,
+                   (long long)n, (long long)bias_start, lr, lr_bias, beta1, beta2, eps, weight_decay, (float)bc1,
+                   (float)sqrt(bc2), grad_scale, status);
   return SSD3D_OK;
 }

@@ -582,13 +582,14 @@ def dwconv3d_wgrad(dz: torch.Tensor, x: torch.Tensor, stride: int, dw: torch.Ten
 
 def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
               bias_start: int, lr: float, lr_bias: float, step: int, betas=(0.9, 0.999), eps: float = 1e-8,
-              weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
-    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+              weight_decay: float = 0.0, grad_scale: float = 1.0, status: Optional[torch.Tensor] = None) -> None:
+    """``status`` (2,) int32: steps with a non-finite gradient are skipped and counted (see the header)."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, status)
     rc = _lib.load().ssd3d_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                      param.numel(), bias_start, lr, lr_bias, betas[0], betas[1], eps, weight_decay,
-                                     int(step), grad_scale, _stream())
+                                     int(step), grad_scale, _ptr(status), _stream())
     _lib.check(rc, "ssd3d_adam_step")
-    LAUNCHES[0] += 1
+    LAUNCHES[0] += 2 if status is not None else 1
 
 
 # ----------------------------------------------------------------------------------------------

@@ -748,6 +748,15 @@ class LSSD3D(_LightningBase):
             raise RuntimeError("fit_step needs train() mode")
         return training.fit_step(self, batch, world_size, allreduce)
 
+    def fit_skipped_steps(self) -> int:
+        """Number of fit_step calls whose gradient was NaN / Inf (e.g. a batch without one positive prior: the
+        reference raises "Loss is NaN", ssd3d.py:938-940) and whose update was therefore skipped on the device.
+        Reading it synchronises with the device."""
+        eng = self.__dict__.get("_train_engine")
+        if eng is None or eng.flat is None:
+            return 0
+        return int(eng.flat.status[1].item())
+
     def training_step(self, batch):
         """forward + MultiBox loss (ssd3d.py:467-531): matching, hard/soft labelling, CE + L1 and their
         gradients w.r.t. the head outputs run in the loss kernels; ``loss.backward()`` continues through the

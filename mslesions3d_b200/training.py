@@ -73,6 +73,7 @@ class FlatParams:
         self.exp_avg_sq = torch.zeros((off,), dtype=torch.float32, device=dev)
         self.views_grad: Dict[str, torch.Tensor] = {}
         self.step = 0
+        self.status = torch.zeros((2,), dtype=torch.int32, device=dev)   # [non-finite this step, skipped steps]
         with torch.no_grad():
             for n, p in weights + biases:
                 o = self.offsets[n]
@@ -328,7 +329,7 @@ def _optimizer_step(model, flat, world_size, allreduce):
         # same batch (ssd3d.py:525-527): optimizer step k (1-based) runs at the k-th scheduled rate
         lr = cosine_lr(lr, flat.step)
     ops.adam_step(flat.param, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.bias_start, lr, 2.0 * lr, flat.step,
-                  weight_decay=0.0005, grad_scale=1.0 / float(world_size))
+                  weight_decay=0.0005, grad_scale=1.0 / float(world_size), status=flat.status)
     model.invalidate_packed()
 
 

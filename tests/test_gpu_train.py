@@ -372,3 +372,22 @@ def test_fit_step_follows_reference_optimizer(graph):
         locs, scores = model(x)
         el, es = O.forward({k: v.cpu() for k, v in got_sd.items()}, x, emulate_bf16=True)
     assert float((locs.cpu() - el).abs().max()) < 0.1 and float((scores.cpu() - es).abs().max()) < 0.1
+
+
+def test_fit_step_skips_a_batch_without_positives():
+    """No ground-truth box in the whole batch -> n_pos = 0 -> the MultiBox loss is 0/0 (the reference raises
+    "Loss is NaN", ssd3d.py:938-940): the fused step must leave parameters and Adam moments untouched and count it."""
+    sd, x, boxes, labels = _train_case(1, (64, 64, 64), 2)
+    model = _model(sd, 1, (64, 64, 64), threshold=[0.1, 0.2], lr=1e-3)
+    empty = {"img": x, "boxes": [torch.zeros((0, 6)) for _ in boxes], "labels": [torch.zeros((0,), dtype=torch.long) for _ in labels]}
+    model.fit_step({"img": x, "boxes": boxes, "labels": labels})
+    before = {k: v.clone() for k, v in model.state_dict().items() if "running" not in k and "num_batches" not in k}
+    loss = model.fit_step(empty)
+    assert not bool(torch.isfinite(loss).all())
+    assert model.fit_skipped_steps() == 1
+    after = model.state_dict()
+    for k, v in before.items():
+        assert torch.equal(after[k], v), k
+    loss2 = model.fit_step({"img": x, "boxes": boxes, "labels": labels})
+    assert bool(torch.isfinite(loss2).all()) and model.fit_skipped_steps() == 1
+    assert any(not torch.equal(after[k], before[k]) for k in before)
