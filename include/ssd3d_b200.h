@@ -202,13 +202,14 @@ int ssd3d_pwconv_affine(const void* x, const void* w, const float* scale, const 
 /* BatchNorm3d in training mode + ReLU on a raw conv output z (M, C) bf16 (mobilenet.py:29-30,39,41,44-45):
  * batch mean / biased variance per channel -> scale = gamma/sqrt(var+eps), shift = beta - mean*scale
  * (fp32, C each; also mean and invstd for the backward), running statistics updated in place with
- * `momentum` and the unbiased variance (NULL to skip), a = relu(z*scale + shift) (NULL to skip).
+ * `momentum` and the unbiased variance (NULL to skip), *num_batches_tracked += 1 (device int64, NULL to skip),
+ * a = relu(z*scale + shift) (NULL to skip).
  * workspace: ssd3d_bn_workspace_bytes(C). */
 int64_t ssd3d_bn_workspace_bytes(int C);
 int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* gamma, const float* beta, float eps,
-                       float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                       float* mean, float* invstd, void* a, int* nan_flag, void* workspace, int64_t workspace_bytes,
-                       void* stream);
+                       float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                       float* scale, float* shift, float* mean, float* invstd, void* a, int* nan_flag,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 /* Backward of the same unit: grad_a (M, C) bf16 = dL/da -> dgamma, dbeta (C) fp32 and dz (M, C) bf16
  * (dz may alias grad_a).  The ReLU mask is recomputed from z with the forward's arithmetic. */
 int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, int C, const float* scale, const float* shift,
@@ -283,6 +284,11 @@ int ssd3d_map_class(const float* det_boxes, const float* det_scores, const int32
                     int32_t* sort_index, float* true_positives, float* false_positives, uint8_t* detected,
                     float* true_volumes, float* cum_precision, float* cum_recall, float* out_stats, void* workspace,
                     int64_t workspace_bytes, void* stream);
+
+/* dst[i] = src[index[i]] (0 where index[i] < 0), converted to bf16 (dst_is_bf16 = 1) or kept fp32: every packed
+ * weight layout of the step (stem (32,KPAD), depthwise (27,C), pointwise and its transpose, head (16,27*C) and
+ * its bias) produced from the flat fp32 parameter buffer in one launch after the optimizer step. */
+int ssd3d_gather_cast(const float* src, const int32_t* index, int64_t n, void* dst, int dst_is_bf16, void* stream);
 
 #ifdef __cplusplus
 }

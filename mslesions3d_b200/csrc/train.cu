@@ -139,10 +139,12 @@ __global__ void __launch_bounds__(1024) bn_finalize_fwd_kernel(const float* __re
                                                               float momentum, float* __restrict__ running_mean,
                                                               float* __restrict__ running_var,
                                                               float* __restrict__ scale, float* __restrict__ shift,
-                                                              float* __restrict__ mean, float* __restrict__ invstd) {
+                                                              float* __restrict__ mean, float* __restrict__ invstd,
+                                                              long long* __restrict__ num_batches_tracked) {
   __shared__ double red[FIN_LANES][32][2];
   pdl_wait();
   pdl_launch_dependents();
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
   double s, q;
   colpartials_sum(partial, B, C, c, lane, red, s, q);
@@ -769,6 +771,32 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight packing for the next step as ONE launch: dst[i] = bf16(src[index[i]]) (index < 0 -> 0).  The index map
+// (built once on the host) encodes every layout the kernels want -- stem (32, KPAD) zero padded, depthwise
+// (27, C), pointwise (Cout, Cin) and its transpose, head (16, 27*C) with loc | class rows -- over the flat fp32
+// parameter buffer the optimizer updates.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_cast_bf16_kernel(const float* __restrict__ src,
+                                                               const int* __restrict__ index, long long n,
+                                                               bf16* __restrict__ dst) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = index[i];
+    dst[i] = __float2bfloat16_rn(k >= 0 ? src[k] : 0.f);
+  }
+}
+__global__ void __launch_bounds__(256) gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ index,
+                                                         long long n, float* __restrict__ dst) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = index[i];
+    dst[i] = k >= 0 ? src[k] : 0.f;
+  }
+}
+
 static inline int grid_for(long long total, int block, int cap) {
   long long b = (total + block - 1) / block;
   if (b > cap) b = cap;
@@ -801,9 +829,9 @@ static int colreduce_plan(long long M, int C, int* threads, long long* rows_per_
 extern "C" int64_t ssd3d_bn_workspace_bytes(int C) { return (int64_t)COLRED_MAX_BLOCKS * 2 * C * 4; }
 
 extern "C" int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* gamma, const float* beta, float eps,
-                                  float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                                  float* mean, float* invstd, void* a, int* nan_flag, void* workspace,
-                                  int64_t workspace_bytes, void* stream) {
+                                  float momentum, float* running_mean, float* running_var,
+                                  int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
+                                  void* a, int* nan_flag, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!z || !scale || !shift || !mean || !invstd || !workspace || M <= 0) return SSD3D_ERR_ARG;
   int threads;
   long long rpb;
@@ -815,7 +843,8 @@ extern "C" int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* 
   SSD3D_LAUNCH_PDL(colreduce_kernel<0>, dim3(B), dim3(threads), 0, st, zp, (const bf16*)nullptr, (const float*)nullptr,
                    (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (long long)M, C, rpb, partial);
   SSD3D_LAUNCH_PDL(bn_finalize_fwd_kernel, dim3((C + 31) / 32), dim3(1024), 0, st, (const float*)partial, B, C,
-                   (long long)M, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
+                   (long long)M, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd,
+                   reinterpret_cast<long long*>(num_batches_tracked));
   if (a) {
     const long long total_vec = (long long)M * (C / 8);
     SSD3D_LAUNCH_PDL(bn_apply_relu_kernel, dim3(grid_for(total_vec, 256, 148 * 8)), dim3(256), 0, st, zp,
@@ -1082,5 +1111,19 @@ extern "C" int ssd3d_adam_step(float* param, const float* grad, float* exp_avg, 
   SSD3D_LAUNCH_PDL(adam_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq,
                    (long long)n, (long long)bias_start, lr, lr_bias, beta1, beta2, eps, weight_decay, (float)bc1,
                    (float)sqrt(bc2), grad_scale, status);
+  return SSD3D_OK;
+}
+
+// ---- weight packing -------------------------------------------------------------------------------------
+extern "C" int ssd3d_gather_cast(const float* src, const int32_t* index, int64_t n, void* dst, int dst_is_bf16,
+                                 void* stream) {
+  if (!src || !index || !dst || n <= 0) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dst_is_bf16)
+    SSD3D_LAUNCH_PDL(gather_cast_bf16_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, st, src, index, (long long)n,
+                     static_cast<bf16*>(dst));
+  else
+    SSD3D_LAUNCH_PDL(gather_f32_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, st, src, index, (long long)n,
+                     static_cast<float*>(dst));
   return SSD3D_OK;
 }

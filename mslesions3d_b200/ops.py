@@ -475,13 +475,13 @@ def bn_train_relu(z: torch.Tensor, bn: torch.nn.BatchNorm3d, nan_flag: Optional[
     ws = _workspace(need, z.device)
     track = bn.track_running_stats and bn.running_mean is not None
     momentum = 0.1 if bn.momentum is None else float(bn.momentum)
-    if track and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
-        if bn.momentum is None:
-            raise NotImplementedError("cumulative-average BatchNorm (momentum=None) is not used by the reference")
+    if track and bn.momentum is None:
+        raise NotImplementedError("cumulative-average BatchNorm (momentum=None) is not used by the reference")
+    nbt = bn.num_batches_tracked if (track and bn.num_batches_tracked is not None) else None
     rc = lib.ssd3d_bn_train_fwd(z.data_ptr(), m, c, _ptr(bn.weight.detach() if bn.weight is not None else None),
                                 _ptr(bn.bias.detach() if bn.bias is not None else None), float(bn.eps), momentum,
                                 _ptr(bn.running_mean if track else None), _ptr(bn.running_var if track else None),
+                                _ptr(nbt),
                                 st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
                                 a.data_ptr(), _ptr(nan_flag), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "ssd3d_bn_train_fwd")
@@ -632,3 +632,12 @@ def map_class(det_boxes: torch.Tensor, det_scores: torch.Tensor, det_images: tor
     _lib.check(rc, "ssd3d_map_class")
     LAUNCHES[0] += 5 if nt else 4
     return out
+
+
+def gather_cast(src: torch.Tensor, index: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[i] = src[index[i]] (0 where index < 0), cast to dst's dtype (bf16 or fp32): one-launch weight packing."""
+    _need_cuda(src, index, dst)
+    rc = _lib.load().ssd3d_gather_cast(src.data_ptr(), index.data_ptr(), dst.numel(), dst.data_ptr(),
+                                       int(dst.dtype == BF16), _stream())
+    _lib.check(rc, "ssd3d_gather_cast")
+    LAUNCHES[0] += 1

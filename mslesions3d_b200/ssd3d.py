@@ -629,12 +629,20 @@ class LSSD3D(_LightningBase):
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.get("_plans", {}).clear()
         self.__dict__["_state_tensors"] = None
+        eng = self.__dict__.get("_train_engine")
+        if eng is not None:      # parameters are about to be replaced: the flat buffers / packed views die with them
+            eng.flat, eng.packed = None, None
+            eng.plans.clear()
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
         self.__dict__.get("_plans", {}).clear()
         self.__dict__["_state_tensors"] = None
-        return super().load_state_dict(*args, **kwargs)
+        out = super().load_state_dict(*args, **kwargs)
+        eng = self.__dict__.get("_train_engine")
+        if eng is not None and eng.packed is not None:
+            eng.packed.refresh()     # values were copied into the flat buffer in place
+        return out
 
     def _plan_for(self, image: torch.Tensor, slot: int = 0) -> _InferencePlan:
         if self.training:

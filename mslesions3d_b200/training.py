@@ -83,12 +83,83 @@ class FlatParams:
                 self.views_grad[n] = self.grad[o:o + p.numel()].view(p.shape)
 
 
+class PackedWeights:
+    """bf16 copies of every conv weight in the layouts the kernels read (stem (32,KPAD), depthwise (27,C),
+    pointwise (Cout,Cin) and its transpose for the data gradient, head (16,27*C)) plus the fp32 head biases, all
+    views of two buffers that ONE gather launch each refreshes from the flat fp32 parameter buffer after an
+    optimizer step (instead of ~45 small torch launches per step inside the captured graph).  The index maps are
+    built once on the host by pushing flat indices through the same reshapes / permutes the packing does."""
+
+    def __init__(self, model, flat: "FlatParams"):
+        dev = flat.param.device
+        segs, fsegs = [], []           # (name, index tensor (int64, CPU), shape)
+        self.views: Dict[str, torch.Tensor] = {}
+
+        def idx(name):
+            p = dict(model.named_parameters())[name]
+            o = flat.offsets[name]
+            return (o + torch.arange(p.numel(), dtype=torch.int64)).view(p.shape)
+
+        for i, feat in enumerate(model.base.features):
+            p = "base.features.%d" % i
+            if isinstance(feat, ConvBN):
+                w = idx(p + ".0.weight")
+                co, ci = w.shape[0], w.shape[1]
+                kpad = 64 if 27 * ci <= 64 else 128
+                m = torch.full((co, kpad), -1, dtype=torch.int64)
+                m[:, :27 * ci] = w.reshape(co, 27 * ci)
+                segs.append((p + ".stem", m))
+            else:
+                w1 = idx(p + ".conv1.weight")
+                segs.append((p + ".dw", w1.reshape(w1.shape[0], 27).t().contiguous()))
+                w2 = idx(p + ".conv2.weight")
+                w2 = w2.reshape(w2.shape[0], w2.shape[1])
+                segs.append((p + ".pw", w2.contiguous()))
+                segs.append((p + ".pwT", w2.t().contiguous()))
+        for j in range(len(model.pred_convs.loc_convs)):
+            lw = idx("pred_convs.loc_convs.%d.weight" % j)
+            cw = idx("pred_convs.cl_convs.%d.weight" % j)
+            c = lw.shape[1]
+            rows = lw.shape[0] + cw.shape[0]
+            npad = (rows + 15) // 16 * 16
+            m = torch.full((npad, 27 * c), -1, dtype=torch.int64)
+            m[:lw.shape[0]] = lw.permute(0, 2, 3, 4, 1).reshape(lw.shape[0], 27 * c)
+            m[lw.shape[0]:rows] = cw.permute(0, 2, 3, 4, 1).reshape(cw.shape[0], 27 * c)
+            segs.append(("head%d.w" % j, m))
+            b = torch.full((npad,), -1, dtype=torch.int64)
+            b[:lw.shape[0]] = idx("pred_convs.loc_convs.%d.bias" % j)
+            b[lw.shape[0]:rows] = idx("pred_convs.cl_convs.%d.bias" % j)
+            fsegs.append(("head%d.b" % j, b))
+
+        def build(seg_list, dtype):
+            offs, total = [], 0
+            for _, m in seg_list:
+                offs.append(total)
+                total += (m.numel() + 127) // 128 * 128          # 256-byte aligned segments (TMA bases)
+            index = torch.full((total,), -1, dtype=torch.int32)
+            for (name, m), o in zip(seg_list, offs):
+                index[o:o + m.numel()] = m.reshape(-1).to(torch.int32)
+            buf = torch.zeros((total,), dtype=dtype, device=dev)
+            for (name, m), o in zip(seg_list, offs):
+                self.views[name] = buf[o:o + m.numel()].view(m.shape)
+            return index.to(dev), buf
+
+        self.index_bf16, self.buf_bf16 = build(segs, torch.bfloat16)
+        self.index_f32, self.buf_f32 = build(fsegs, torch.float32)
+        self.flat = flat
+
+    def refresh(self):
+        ops.gather_cast(self.flat.param, self.index_bf16, self.buf_bf16)
+        ops.gather_cast(self.flat.param, self.index_f32, self.buf_f32)
+
+
 class TrainEngine:
     """Train-mode forward with a tape + hand-written backward for ``LSSD3D`` (MobileNet base + SSD heads)."""
 
     def __init__(self, model):
         self.model = model
         self.flat: Optional[FlatParams] = None
+        self.packed: Optional[PackedWeights] = None
         self.tape = None
         self.plans = {}
 
@@ -96,12 +167,17 @@ class TrainEngine:
     def flatten(self) -> FlatParams:
         if self.flat is None or self.flat.param.device != self.model.device:
             self.flat = FlatParams(self.model)
+            self.packed = PackedWeights(self.model, self.flat)
+            self.packed.refresh()
+            self.plans.clear()
             self.model.invalidate_packed()
         return self.flat
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, image: torch.Tensor):
-        """image (N, Cin, D, H, W) -> locs (N,P,6), scores (N,P,n_classes); records the tape."""
+    def forward(self, image: torch.Tensor, packed: Optional[PackedWeights] = None):
+        """image (N, Cin, D, H, W) -> locs (N,P,6), scores (N,P,n_classes); records the tape.  ``packed``: the
+        fused step's pre-packed weights (kept current by the optimizer step); otherwise the weights are packed
+        from the parameters here."""
         m = self.model
         dev = m.device
         if dev.type != "cuda":
@@ -123,21 +199,23 @@ class TrainEngine:
             if isinstance(feat, ConvBN):
                 conv, bn = feat[0], feat[1]
                 sd = _stride3(conv.stride)[0]
-                w = ops.pack_stem_weight(conv.weight)
+                w = packed.views["base.features.%d.stem" % i] if packed else ops.pack_stem_weight(conv.weight)
                 z = ops.stem_conv_raw(x, w, sd)
                 a, st = ops.bn_train_relu(z, bn, flag)
                 tape["units"].append(dict(kind="stem", idx=i, x=x, z=z, st=st, stride=sd))
                 x = a
             elif isinstance(feat, Block):
                 s = _stride3(feat.conv1.stride)[0]
-                wd = ops.pack_dw_weight(feat.conv1.weight)
+                pre = "base.features.%d" % i
+                wd = packed.views[pre + ".dw"] if packed else ops.pack_dw_weight(feat.conv1.weight)
                 z1 = ops.dwconv3d_raw(x, wd, s)
                 a1, st1 = ops.bn_train_relu(z1, feat.bn1, None)
-                wp = ops.pack_pw_weight(feat.conv2.weight)
+                wp = packed.views[pre + ".pw"] if packed else ops.pack_pw_weight(feat.conv2.weight)
                 z2 = ops.pwconv_raw(a1, wp)
                 a2, st2 = ops.bn_train_relu(z2, feat.bn2, flag)
+                wpt = packed.views[pre + ".pwT"] if packed else None
                 tape["units"].append(dict(kind="block", idx=i, x=x, z1=z1, st1=st1, a1=a1, z2=z2, st2=st2, wd=wd, wp=wp,
-                                          stride=s))
+                                          wpt=wpt, stride=s))
                 x = a2
             else:
                 raise NotImplementedError("unexpected backbone layer %r" % type(feat))
@@ -153,10 +231,11 @@ class TrainEngine:
         locs = torch.empty((n, total, 6), dtype=torch.float32, device=dev)
         scores = torch.empty((n, total, pc.n_classes), dtype=torch.float32, device=dev)
         off = 0
-        packed = pc._pack()
+        head_w = ([(packed.views["head%d.w" % j], packed.views["head%d.b" % j]) for j in range(len(keys))]
+                  if packed else pc._pack())
         for j, k in enumerate(keys):
-            pc.run_head(j, feats[k], locs, scores, off, flag)
-            tape["heads"].append(dict(j=j, layer=k, feat=feats[k], w=packed[j][0], off=off, bpl=pc.n_boxes[k]))
+            ops.head_conv(feats[k], head_w[j][0], head_w[j][1], locs, scores, pc.n_boxes[k], pc.n_classes, off, flag)
+            tape["heads"].append(dict(j=j, layer=k, feat=feats[k], w=head_w[j][0], off=off, bpl=pc.n_boxes[k]))
             off += counts[j]
         self.tape = tape
         return locs, scores
@@ -198,7 +277,7 @@ class TrainEngine:
                 ops.pwconv_wgrad(dz2, u["a1"], grads[p + ".conv2.weight"])
                 g1 = torch.empty_like(u["a1"])
                 nn_, c1, d1, h1, w1 = u["a1"].shape
-                wt = u["wp"].t().contiguous()           # (Cin, Cout): data gradient = dz . W
+                wt = u["wpt"] if u["wpt"] is not None else u["wp"].t().contiguous()   # (Cin, Cout): dx = dz . W
                 ops.pw_gemm_raw(nn_ * d1 * h1 * w1, dz2, wt, g1)
                 dz1 = ops.bn_relu_backward(u["z1"], g1, u["st1"], grads[p + ".bn1.weight"], grads[p + ".bn1.bias"])
                 ops.dwconv3d_wgrad(dz1, u["x"], u["stride"], grads[p + ".conv1.weight"])
@@ -283,7 +362,7 @@ class _TrainPlan:
         eng = model.train_engine()
         lf = model.loss_fn
         t0, t1 = (lf.threshold, lf.threshold) if lf.thresholding_mode == "hard" else lf.threshold
-        locs, scores = eng.forward(self.image)
+        locs, scores = eng.forward(self.image, eng.packed)
         m = ops.match_priors_packed(self.gt_boxes, self.gt_labels, self.offsets, self.n, self.tmax,
                                     model._priors_on(model.device), t0, t1)
         out, n_pos, g_locs, g_scores = ops.multibox_loss(locs, scores, m["true_classes"], m["true_locs"],
@@ -309,7 +388,6 @@ class _TrainPlan:
         with torch.no_grad():
             for k, v in model.named_buffers():
                 v.copy_(buffers[k])
-        model.invalidate_packed()      # the weight packing must be recorded too: it runs again on every replay
         graph = torch.cuda.CUDAGraph()
         before = ops.LAUNCHES[0]
         with torch.no_grad(), torch.cuda.graph(graph):
@@ -330,6 +408,7 @@ def _optimizer_step(model, flat, world_size, allreduce):
         lr = cosine_lr(lr, flat.step)
     ops.adam_step(flat.param, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.bias_start, lr, 2.0 * lr, flat.step,
                   weight_decay=0.0005, grad_scale=1.0 / float(world_size), status=flat.status)
+    model.train_engine().packed.refresh()      # every packed weight layout for the next step: two launches
     model.invalidate_packed()
 
 
@@ -367,7 +446,7 @@ def fit_step(model, batch, world_size: int = 1, allreduce=None):
     gt_boxes = [b.to(dev) for b in gt_boxes]
     gt_labels = [l.to(dev) for l in gt_labels]
     with torch.no_grad():
-        locs, scores = eng.forward(images)
+        locs, scores = eng.forward(images, eng.packed)
         lf = model.loss_fn
         lf_m = lf.match(gt_boxes, gt_labels)
         out, n_pos, g_locs, g_scores = ops.multibox_loss(locs, scores, lf_m["true_classes"], lf_m["true_locs"],
