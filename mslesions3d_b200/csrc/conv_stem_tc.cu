@@ -54,10 +54,37 @@ __device__ __forceinline__ float relu_nan1(float v, float floor) {
   return r;
 }
 
+// registers -> TMEM: 32 consecutive 32-bit columns of this thread's lane (thread i of a warp <-> lane base + i)
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (128 rows x 16 bf16 = 8 columns of packed pairs) comes from
+// tensor memory, where the gather wrote it with tcgen05.st -- it never touches shared memory.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Persistent CTA: loops over tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  Per tile
-//   TMA halo box (double buffered, prefetched two tiles ahead)  ->  gather into the swizzled A tile (double
-//   buffered)  ->  4*KB UMMAs into one of two 32-column TMEM accumulators (asynchronous)  ->  epilogue of the
-//   PREVIOUS tile (TMEM -> scale/shift/ReLU -> 64-byte store) while this tile's UMMAs run.
+//   TMA halo box (double buffered, prefetched two tiles ahead)  ->  gather of the 27*CIN taps into registers  ->
+//   tcgen05.st into the A operand in TENSOR MEMORY (double buffered; the A tile never exists in shared memory,
+//   whose bandwidth was the kernel's limit: 16 KB written + 16 KB read back per tile)  ->  4*KB UMMAs (A from
+//   TMEM, B from smem) into one of two 32-column TMEM accumulators (asynchronous)  ->  epilogue of the PREVIOUS
+//   tile (TMEM -> scale/shift/ReLU -> swizzled staging tile -> TMA store) while this tile's UMMAs run.
 // Weights (B operand), scale and shift are loaded once per CTA; 3 CTAs are resident per SM.
 template <typename TIn, int CIN>
 __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__ CUtensorMap tmX,
@@ -72,8 +99,8 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  uint8_t* sA = smem;                                   // 2 x KB x (128 rows x 128 B)
-  uint8_t* sB = sA + 2 * KB * 16384;                    // KB x (32 rows x 128 B)
+  uint8_t* sB = smem;                                   // KB x (32 rows x 128 B)
+  constexpr uint32_t TMEM_COLS = (64 + 2 * NREG <= 128) ? 128u : 256u;   // 2 accumulators + 2 A buffers
   uint8_t* ctl = sB + KB * 4096;                        // mbarriers + TMEM slot (128 B), then scale/shift (256 B)
   const int tile_elems = CIN * p.TDI * p.THI * p.TWI;
   const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(TIn));
@@ -101,7 +128,7 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc(tmem_slot, 64);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -244,14 +271,13 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
     }
     // the A buffer of this parity was last read by the UMMAs of tile it-2: their completion was observed
     // in the epilogue of tile it-2 (bar_mma wait), which every thread has passed
-    uint8_t* a_dst = sA + (size_t)buf * KB * 16384;
+    const uint32_t a_tmem = tmem_base + 64u + (uint32_t)(buf * NREG);
+    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < KPAD / 8; ++j) {
-      *reinterpret_cast<uint4*>(a_dst + (j >> 3) * 16384 + sw128_offset(tid, j & 7)) =
-          make_uint4(regs[4 * j], regs[4 * j + 1], regs[4 * j + 2], regs[4 * j + 3]);
-    }
-    fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    __syncthreads();              // all rows written; everyone is also done reading sX[buf]
+    for (int j = 0; j < NREG; j += 32) tmem_st_32x32b_x32(a_tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)j, &regs[j]);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();              // all rows are in TMEM; everyone is also done reading sX[buf]
 
     if (tid == 32) {
       // the halo buffer is free: prefetch the tile two iterations ahead
@@ -261,12 +287,11 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
       const uint32_t idesc = umma_idesc_bf16(128, 32);
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
-        const uint64_t da = umma_desc_k_sw128(smem_u32(a_dst + kb * 16384));
         const uint64_t db = umma_desc_k_sw128(smem_u32(sB + kb * 4096));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_base + (uint32_t)(buf * 32), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                       (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)      // 16 bf16 of K = 8 TMEM columns of A
+          umma_bf16_ts(tmem_base + (uint32_t)(buf * 32), a_tmem + (uint32_t)((kb * 4 + k) * 8), db + (uint64_t)(2 * k),
+                       idesc, (kb | k) != 0 ? 1u : 0u);
       }
       umma_commit(&bar_mma[buf]);
     }
@@ -295,7 +320,7 @@ __global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -325,7 +350,7 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
     if (r != CUDA_SUCCESS) return SSD3D_ERR_TMA;
   }
   const size_t tile_pitch = ((size_t)CIN * p.TDI * p.THI * p.TWI * sizeof(TIn) + 127) & ~(size_t)127;
-  const size_t smem = 1024 + (size_t)KB * (2 * 16384 + 4096) + 1024 + 8192 + 2 * tile_pitch + 128;
+  const size_t smem = 1024 + (size_t)KB * 4096 + 1024 + 8192 + 2 * tile_pitch + 128;
   CUtensorMap tmY;
   {
     const uint64_t dims[5] = {32ull, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.Do, (uint64_t)p.N};
@@ -335,11 +360,12 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
   }
   cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<TIn, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  // persistent grid: up to 4 CTAs per SM (smem ~54 KB, 64 TMEM columns, <= 128 registers each), never more CTAs
-  // than tiles
+  // persistent grid: CTAs per SM bounded by shared memory (~31 KB each), tensor memory (128 or 256 of 512
+  // columns each) and registers (launch bounds 3); never more CTAs than tiles
   const int n_sm = persistent_sms();
   const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
-  const long long per_sm = (smem + 1024) * 4 <= 227 * 1024 ? 4 : ((smem + 1024) * 3 <= 227 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1));
+  long long per_sm = (smem + 1024) * 3 <= 227 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1);
+  if (KPAD > 64 && per_sm > 2) per_sm = 2;      // 256 TMEM columns per CTA
   const unsigned grid = (unsigned)(tiles < per_sm * n_sm ? tiles : per_sm * n_sm);
   SSD3D_LAUNCH_PDL((stem_tc_kernel<TIn, CIN>), dim3(grid), dim3(128), smem, st, tm, tmY, p);
   return SSD3D_OK;
