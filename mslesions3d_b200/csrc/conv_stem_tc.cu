@@ -87,7 +87,7 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 //   tile (TMEM -> scale/shift/ReLU -> swizzled staging tile -> TMA store) while this tile's UMMAs run.
 // Weights (B operand), scale and shift are loaded once per CTA; 3 CTAs are resident per SM.
 template <typename TIn, int CIN>
-__global__ void __launch_bounds__(128, 3) stem_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(128, 4) stem_tc_kernel(const __grid_constant__ CUtensorMap tmX,
                                                          const __grid_constant__ CUtensorMap tmY, const StemParams p) {
   constexpr int KREAL = 27 * CIN;
   constexpr int KPAD = (KREAL <= 64) ? 64 : 128;
@@ -364,7 +364,7 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
   // columns each) and registers (launch bounds 3); never more CTAs than tiles
   const int n_sm = persistent_sms();
   const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
-  long long per_sm = (smem + 1024) * 3 <= 227 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1);
+  long long per_sm = (smem + 1024) * 4 <= 227 * 1024 ? 4 : ((smem + 1024) * 3 <= 227 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1));
   if (KPAD > 64 && per_sm > 2) per_sm = 2;      // 256 TMEM columns per CTA
   const unsigned grid = (unsigned)(tiles < per_sm * n_sm ? tiles : per_sm * n_sm);
   SSD3D_LAUNCH_PDL((stem_tc_kernel<TIn, CIN>), dim3(grid), dim3(128), smem, st, tm, tmY, p);
