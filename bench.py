@@ -279,7 +279,7 @@ def main():
             for b, l, s in model.predict_batches(batches, to_host=True):
                 assert not b[0].is_cuda
         # per step: padded boxes/labels/scores (top_k rows per volume) + the count/status/flag words
-        d2h_bytes[0] = BATCH * TOP_K * (24 + 8 + 4) + 4 * (BATCH + 2)
+        d2h_bytes[0] = BATCH * TOP_K * (24 + 4 + 8 + 8) + 4 * (BATCH + 2)
 
     # ---- resident-input throughput (value) --------------------------------------------------------
     # Build (capture) the inference plan of every pipeline slot first: that is one-off setup, not a step.

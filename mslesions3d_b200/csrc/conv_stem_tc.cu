@@ -199,8 +199,7 @@ __global__ void __launch_bounds__(128, 4) stem_tc_kernel(const __grid_constant__
       }
       o4[q] = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    if (tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read sOut
-    __syncthreads();
+    // (sOut is free: tid 32 waited for the previous store's read before this iteration's gather barrier)
 #pragma unroll
     for (int q = 0; q < 4; ++q)      // 64-byte swizzle: 16-byte chunk ^= (row >> 1) & 3
       *reinterpret_cast<uint4*>(sOut + tid * 64 + ((q ^ ((tid >> 1) & 3)) << 4)) = o4[q];
@@ -277,7 +276,10 @@ __global__ void __launch_bounds__(128, 4) stem_tc_kernel(const __grid_constant__
     for (int j = 0; j < NREG; j += 32) tmem_st_32x32b_x32(a_tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)j, &regs[j]);
     tmem_st_wait();
     tc_fence_before();
-    __syncthreads();              // all rows are in TMEM; everyone is also done reading sX[buf]
+    // the TMA store issued in the previous iteration has had the whole gather to read the staging tile: waiting
+    // here (not in the epilogue) lets the barrier below also publish "sOut is free"
+    if (tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();              // all rows are in TMEM; everyone is also done reading sX[buf]; sOut is free
 
     if (tid == 32) {
       // the halo buffer is free: prefetch the tile two iterations ahead
@@ -309,6 +311,8 @@ __global__ void __launch_bounds__(128, 4) stem_tc_kernel(const __grid_constant__
   }
   if (prev_tile >= 0) {
     const int pb = (it - 1) & 1;
+    if (tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // sOut free for the last tile
+    __syncthreads();
     mbar_wait(&bar_mma[pb], (uint32_t)(((it - 1) >> 1) & 1));
     tc_fence_after();
     epilogue(prev_tile, pb);
