@@ -315,11 +315,20 @@ static bool head2_plan(int N, int C, int D, int H, int W, int NPAD, Head2Params&
 
 using namespace ssd3d;
 
+// conv_head_kw.cu
+int64_t ssd3d_head_kw_workspace_bytes(int N, int C, int D, int H, int W);
+bool ssd3d_head_kw_applicable(int N, int C, int D, int H, int W, int NPAD);
+
 extern "C" int64_t ssd3d_head_workspace_bytes(int N, int C, int D, int H, int W, int NPAD) {
   Head2Params p{};
   if (N <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
-  if (!head2_plan(N, C, D, H, W, NPAD, p) || p.S == 1) return 0;
-  return (int64_t)p.S * p.tiles_total * p.J * 128 * NPAD * 4;
+  int64_t need = 0;
+  if (head2_plan(N, C, D, H, W, NPAD, p) && p.S > 1) need = (int64_t)p.S * p.tiles_total * p.J * 128 * NPAD * 4;
+  if (ssd3d_head_kw_applicable(N, C, D, H, W, NPAD)) {
+    const int64_t kw = ssd3d_head_kw_workspace_bytes(N, C, D, H, W);
+    if (kw > need) need = kw;
+  }
+  return need;
 }
 
 // returns SSD3D_ERR_UNSUPPORTED when the shape is outside this kernel (caller falls back to the per-tap kernel)

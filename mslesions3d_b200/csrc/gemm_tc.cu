@@ -332,6 +332,11 @@ int ssd3d_head_conv_halo(const void* x, const void* w, const float* bias, float*
                          int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset,
                          int* nan_flag, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
+// conv_head_kw.cu: kw-GEMM + stencil for large maps
+int ssd3d_head_conv_kw(const void* x, const void* w, const float* bias, float* locs, float* scores, int N, int C, int D,
+                       int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset, int* nan_flag,
+                       void* workspace, int64_t workspace_bytes, cudaStream_t st);
+
 extern "C" int ssd3d_head_conv(const void* x, const void* w, const float* bias, float* locs, float* scores, int N,
                                int C, int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P,
                                int64_t prior_offset, int* nan_flag, void* workspace, int64_t workspace_bytes,
@@ -343,6 +348,12 @@ extern "C" int ssd3d_head_conv(const void* x, const void* w, const float* bias, 
   // auto: the halo-tile kernel wins where it can split K across CTAs (small maps: 8^3 23.6 vs 49 us,
   // 4^3 23.6 vs 88 us at batch 8); on large maps both are bound by the UMMA issue rate (~128 cycles per
   // M=128 instruction whatever N) and the per-tap kernel issues fewer of them (no halo rows): 30.7 vs 43.9 us
+  // large maps: kw-GEMM (N = 144 columns per UMMA, 3 instead of 27 activation reads) + (kd,kh) stencil
+  if (algo == 3 || algo == 0) {
+    const int rc = ssd3d_head_conv_kw(x, w, bias, locs, scores, N, C, D, H, W, bpl, n_classes, NPAD, P, prior_offset,
+                                      nan_flag, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    if (rc != SSD3D_ERR_UNSUPPORTED || algo == 3) return rc;
+  }
   const bool small_map = (long long)N * D * H * W < 128ll * 128;
   if (algo == 2 || (algo == 0 && small_map)) {
     const int rc = ssd3d_head_conv_halo(x, w, bias, locs, scores, N, C, D, H, W, bpl, n_classes, NPAD, P, prior_offset,

@@ -122,7 +122,7 @@ def head_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, locs:
               bpl: int, n_classes: int, prior_offset: int, nan_flag: Optional[torch.Tensor] = None,
               algo: int = 0) -> None:
     """Fused loc+class 3x3x3 head of one feature map, written into locs (N,P,6) / scores (N,P,n_classes).
-    algo: 0 auto, 1 per-tap TMA kernel, 2 halo-tile kernel."""
+    algo: 0 auto, 1 per-tap TMA kernel, 2 halo-tile kernel, 3 kw-GEMM + stencil (large maps)."""
     _need_cuda(x, w_packed, bias, locs, scores, nan_flag)
     x = to_channels_last_bf16(x)
     n, c, d, h, w = x.shape

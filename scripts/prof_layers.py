@@ -100,7 +100,9 @@ with torch.no_grad():
         f = fmaps[k]
         wpk, bpk = packed[hi]
         vox = f.numel() // f.shape[1]
-        for algo in (2, 1):
+        for algo in (2, 1, 3, 0):
+            if algo == 3 and vox < 16384:
+                continue
             run("head f%d C=%d %d^3 algo%d" % (k, f.shape[1], f.shape[2], algo),
                 lambda f=f, wpk=wpk, bpk=bpk, off=off, algo=algo: ops.head_conv(f, wpk, bpk, locs, scores, 2, 2, off,
                                                                               flag, algo=algo),

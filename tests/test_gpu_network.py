@@ -173,12 +173,17 @@ def test_pointwise_nan_flag():
     (128, (16, 16, 16), 2, 2),     # several 4x8x8 tiles, J = 3 row blocks, no K split
     (256, (8, 8, 8), 8, 2),        # K split across CTAs + ordered reduction
     (64, (9, 7, 20), 1, 2),        # one chunk, ragged tiles
+    (128, (16, 16, 16), 8, 2),     # the benchmark's f3 head: kw-GEMM + stencil territory (M = 32768)
+    (64, (21, 19, 23), 2, 2),      # M = 18354, ragged tiles on every axis
+    (256, (16, 16, 16), 4, 2),
 ])
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 3])
 def test_head_conv_tcgen05(c, size, batch, n_classes, algo):
     ops = _ops()
     if algo == 2 and c % 64:
         pytest.skip("halo-tile kernel needs C % 64 == 0 (the per-tap kernel covers C = 32)")
+    if algo == 3 and (c % 64 or n_classes != 2 or batch * size[0] * size[1] * size[2] < 16384):
+        pytest.skip("kw-GEMM + stencil is for large maps with C % 64 == 0 and NPAD == 16")
     g = torch.Generator().manual_seed(c + size[2] + n_classes)
     bpl = 2
     x = bf16r(torch.randn((batch, c) + size, generator=g))
