@@ -83,7 +83,7 @@ int ssd3d_pwconv_bn_relu(const void* x, const void* w, const float* scale, const
  *          reduce partial sums in a fixed order)
  *   algo   0 = auto; 1 = per-tap TMA kernel (27 shifted 5-D boxes per chunk); 2 = halo-tile kernel (each
  *          activation voxel loaded once per 64-channel chunk, taps = row-shifted smem descriptors; needs
- *          C % 64 == 0 and NPAD <= 64); 3 = kw-GEMM + (kd,kh) stencil for large maps (N*D*H*W >= 16384,
+ *          C % 64 == 0 and NPAD <= 64); 3 = kw-GEMM + (kd,kh) stencil for maps with N*D*H*W >= 256 (
  *          C % 64 == 0, NPAD == 16): an implicit GEMM over the 3 W-taps with 144 output columns (9x the work
  *          per UMMA, 3 instead of 27 activation reads), then nine shifted reads per output from the L2-resident
  *          intermediate (in the workspace) */

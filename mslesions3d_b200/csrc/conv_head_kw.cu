@@ -23,6 +23,7 @@ struct HeadKwParams {
   int TW, TH, TD, TN;
   int tiles_w, tiles_h, tiles_d;
   int num_kb, stages;
+  int BN, tmem_cols;           // columns per CTA (144, or 48 with three column tiles on small maps)
   float* Y;                    // (N*D*H*W, 144) fp32
   // stencil
   int n_loc, n_cls, bpl, n_classes;
@@ -66,8 +67,9 @@ __global__ void __launch_bounds__(192, 2) head_kw_gemm_kernel(const __grid_const
   const uint32_t raw = smem_u32(kw_raw);
   uint8_t* smem = kw_raw + ((1024u - (raw & 1023u)) & 1023u);
   constexpr int A_BYTES = 128 * 64 * 2;
-  constexpr int B_BYTES = KW_N * 64 * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  const int B_BYTES = p.BN * 64 * 2;
+  const int STAGE_BYTES = A_BYTES + B_BYTES;
+  const int n0 = blockIdx.y * p.BN;            // first Y column of this CTA
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(192, 2) head_kw_gemm_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 5) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -107,13 +109,13 @@ __global__ void __launch_bounds__(192, 2) head_kw_gemm_kernel(const __grid_const
         mbar_arrive_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
         const int kw = kb / KC, kc = kb - kw * KC;
         tma_load_5d(a_dst, &tmA, &full[s], kc * 64, tw0 + kw - 1, th0, td0, tn0);
-        tma_load_2d(a_dst + A_BYTES, &tmB, &full[s], kw * p.C + kc * 64, 0);
+        tma_load_2d(a_dst + A_BYTES, &tmB, &full[s], kw * p.C + kc * 64, n0);
       }
     }
     __syncwarp();
   } else if (warp == 5) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, KW_N);
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % p.stages;
         mbar_wait(&full[s], (uint32_t)((kb / p.stages) & 1));
@@ -140,8 +142,8 @@ __global__ void __launch_bounds__(192, 2) head_kw_gemm_kernel(const __grid_const
     const int d = td0 + r % p.TD; r /= p.TD;
     const int n = tn0 + r;
     const bool valid = (w < p.W) && (h < p.H) && (d < p.D) && (n < p.N);
-    float* yrow = p.Y + ((((long long)n * p.D + d) * p.H + h) * p.W + w) * KW_N;
-    for (int c = 0; c < KW_N; c += 16) {
+    float* yrow = p.Y + ((((long long)n * p.D + d) * p.H + h) * p.W + w) * KW_N + n0;
+    for (int c = 0; c < p.BN; c += 16) {
       uint32_t v[16];
       tmem_ld_32x32b_x16(taddr + (uint32_t)c, v);
       tmem_ld_wait();
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(192, 2) head_kw_gemm_kernel(const __grid_const
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -221,7 +223,7 @@ int64_t ssd3d_head_kw_workspace_bytes(int N, int C, int D, int H, int W) {
 }
 
 bool ssd3d_head_kw_applicable(int N, int C, int D, int H, int W, int NPAD) {
-  return NPAD == 16 && C % 64 == 0 && (long long)N * D * H * W >= 16384;
+  return NPAD == 16 && C % 64 == 0 && (long long)N * D * H * W >= 256;
 }
 
 int ssd3d_head_conv_kw(const void* x, const void* w, const float* bias, float* locs, float* scores, int N, int C, int D,
@@ -252,7 +254,12 @@ int ssd3d_head_conv_kw(const void* x, const void* w, const float* bias, float* l
   p.tiles_d = (D + p.TD - 1) / p.TD;
   const int tiles_n = (N + p.TN - 1) / p.TN;
   p.num_kb = 3 * (C / 64);
-  p.stages = p.num_kb < 3 ? p.num_kb : 3;     // 3 x 34 KB: two CTAs per SM (256 TMEM columns each)
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_d * tiles_n;
+  p.BN = (m_tiles >= 148) ? KW_N : 48;        // small maps: three column tiles so that more SMs take part
+  p.tmem_cols = (p.BN == KW_N) ? 256 : 64;
+  // 3 x 34 KB stages: two CTAs per SM on large maps; deeper ring for the long K loops of the small ones
+  p.stages = (p.BN == KW_N) ? 3 : 6;
+  if (p.stages > p.num_kb) p.stages = p.num_kb;
   p.Y = Y;
   p.n_loc = bpl * 6; p.n_cls = bpl * n_classes; p.bpl = bpl; p.n_classes = n_classes;
   p.P = P; p.prior_off = prior_offset; p.locs = locs; p.scores = scores; p.bias = bias; p.nan_flag = nan_flag;
@@ -267,13 +274,13 @@ int ssd3d_head_conv_kw(const void* x, const void* w, const float* bias, float* l
   {
     const uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)KW_N};
     const uint64_t strides[1] = {(uint64_t)3 * C * 2};
-    const uint32_t box[2] = {64u, (uint32_t)KW_N};
+    const uint32_t box[2] = {64u, (uint32_t)p.BN};
     if (make_tma_bf16(&tmB, w2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return SSD3D_ERR_TMA;
   }
-  const size_t smem = (size_t)p.stages * (128 * 64 * 2 + KW_N * 64 * 2) + (2 * p.stages + 1) * 8 + 16 + 1024;
+  const size_t smem = (size_t)p.stages * (128 * 64 * 2 + p.BN * 64 * 2) + (2 * p.stages + 1) * 8 + 16 + 1024;
   cudaError_t e = cudaFuncSetAttribute(head_kw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_d * tiles_n));
+  dim3 grid((unsigned)m_tiles, (unsigned)(KW_N / p.BN));
   SSD3D_LAUNCH_PDL(head_kw_gemm_kernel, grid, dim3(192), smem, st, tmA, tmB, p);
   const long long total = M * 4;
   SSD3D_LAUNCH_PDL(head_stencil_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);

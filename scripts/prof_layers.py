@@ -101,7 +101,7 @@ with torch.no_grad():
         wpk, bpk = packed[hi]
         vox = f.numel() // f.shape[1]
         for algo in (2, 1, 3, 0):
-            if algo == 3 and vox < 16384:
+            if algo == 3 and vox < 256:
                 continue
             run("head f%d C=%d %d^3 algo%d" % (k, f.shape[1], f.shape[2], algo),
                 lambda f=f, wpk=wpk, bpk=bpk, off=off, algo=algo: ops.head_conv(f, wpk, bpk, locs, scores, 2, 2, off,
