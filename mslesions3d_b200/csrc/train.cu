@@ -404,6 +404,23 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
       }
     }
   }
+  if (MODE == 1) {
+    // head: the slab is laid out like the conv weight itself, [n][c][tap], so that the final sum is a plain
+    // contiguous reduction (k = tap*C + c: this CTA's 64 k values share one tap)
+    const int tap = k0 / p.C, cb = k0 - tap * p.C + warp * 8 * NB;
+    float* out = p.partial + ((size_t)blockIdx.z * p.n_pad + n0) * p.K;
+#pragma unroll
+    for (int a = 0; a < NT / 16; ++a)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const int n = a * 16 + (lane >> 2), c = cb + b * 8 + (lane & 3) * 2;
+        out[((size_t)n * p.C + c) * 27 + tap] = acc[a][b][0];
+        out[((size_t)n * p.C + c + 1) * 27 + tap] = acc[a][b][1];
+        out[((size_t)(n + 8) * p.C + c) * 27 + tap] = acc[a][b][2];
+        out[((size_t)(n + 8) * p.C + c + 1) * 27 + tap] = acc[a][b][3];
+      }
+    return;
+  }
   float* out = p.partial + ((size_t)blockIdx.z * p.n_pad + n0) * p.K + k0 + warp * 8 * NB;
 #pragma unroll
   for (int a = 0; a < NT / 16; ++a)
@@ -439,38 +456,6 @@ __global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restr
 #pragma unroll
     for (int l = 1; l < FIN_LANES; ++l) t += red[l][ox];
     out[(size_t)r * dst_ld + c] = t;
-  }
-}
-
-// head: partial [S][16][27*C] (k = tap*C + c) -> loc (n_loc, C, 27) and class (n_cls, C, 27) conv weight grads
-__global__ void __launch_bounds__(1024) head_wgrad_finalize_kernel(const float* __restrict__ partial, int S, int C,
-                                                                  int n_loc, int n_cls, float* __restrict__ dw_loc,
-                                                                  float* __restrict__ dw_cls) {
-  __shared__ float red[FIN_LANES][32];
-  pdl_wait();
-  pdl_launch_dependents();
-  // thread ox walks the SOURCE order (n, tap, c) so that the partial reads are coalesced
-  const int ox = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const long long total = (long long)(n_loc + n_cls) * C * 27;
-  const long long i = (long long)blockIdx.x * 32 + ox;
-  const bool valid = i < total;
-  const size_t slab = (size_t)16 * 27 * C;
-  float s = 0.f;
-  if (valid) {
-#pragma unroll 4
-    for (int k = lane; k < S; k += FIN_LANES) s += partial[k * slab + (size_t)i];
-  }
-  red[lane][ox] = s;
-  __syncthreads();
-  if (lane == 0 && valid) {
-    float t = red[0][ox];
-#pragma unroll
-    for (int l = 1; l < FIN_LANES; ++l) t += red[l][ox];
-    const int c = (int)(i % C);
-    const int tap = (int)((i / C) % 27);
-    const int n = (int)(i / (27ll * C));
-    if (n < n_loc) dw_loc[((size_t)n * C + c) * 27 + tap] = t;
-    else dw_cls[((size_t)(n - n_loc) * C + c) * 27 + tap] = t;
   }
 }
 
@@ -944,9 +929,13 @@ extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int
   int S = 0;
   const int rc = run_wgrad<16, 1, 64>(p, 16, st, &S);
   if (rc) return rc;
-  const long long total = (long long)(n_loc + n_cls) * C * 27;
-  SSD3D_LAUNCH_PDL(head_wgrad_finalize_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st,
-                   (const float*)p.partial, S, C, n_loc, n_cls, dw_loc, dw_cls);
+  // slabs are [16][C][27] = the layout of the two conv weights stacked: two contiguous fixed-order sums
+  const long long slab = 16ll * 27 * C;
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)(((long long)n_loc * 27 * C + 31) / 32)), dim3(1024), 0, st,
+                   (const float*)p.partial, S, slab, 1, n_loc * 27 * C, n_loc * 27 * C, n_loc * 27 * C, dw_loc);
+  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)(((long long)n_cls * 27 * C + 31) / 32)), dim3(1024), 0, st,
+                   (const float*)(p.partial + (size_t)n_loc * 27 * C), S, slab, 1, n_cls * 27 * C, n_cls * 27 * C,
+                   n_cls * 27 * C, dw_cls);
   return SSD3D_OK;
 }
 
