@@ -345,10 +345,12 @@ extern "C" int ssd3d_head_conv(const void* x, const void* w, const float* bias, 
   if (C <= 0 || (C % 32) || bpl <= 0 || n_classes <= 0) return SSD3D_ERR_ARG;
   if (NPAD % 16 || NPAD > 256 || NPAD < bpl * (6 + n_classes)) return SSD3D_ERR_ARG;
   if (prior_offset < 0 || prior_offset + (int64_t)D * H * W * bpl > P) return SSD3D_ERR_ARG;
-  // auto: the halo-tile kernel wins where it can split K across CTAs (small maps: 8^3 23.6 vs 49 us,
-  // 4^3 23.6 vs 88 us at batch 8); on large maps both are bound by the UMMA issue rate (~128 cycles per
-  // M=128 instruction whatever N) and the per-tap kernel issues fewer of them (no halo rows): 30.7 vs 43.9 us
-  // large maps: kw-GEMM (N = 144 columns per UMMA, 3 instead of 27 activation reads) + (kd,kh) stencil
+  // auto, in order of preference:
+  //   kw-GEMM + (kd,kh) stencil (C % 64 == 0, NPAD == 16, >= 256 voxels): N = 144 columns per UMMA, 3 instead of
+  //     27 activation reads -- 16-22 us on the benchmark's three heads;
+  //   halo-tile kernel on small maps, where it can split K across CTAs (8^3: 23.6 vs 49 us, 4^3: 23.6 vs 88 us);
+  //   per-tap kernel otherwise (e.g. the 32-channel layer-0 head): both older kernels are bound by the UMMA issue
+  //     rate (~128 cycles per M=128 instruction whatever N) and the per-tap one issues fewer (30.7 vs 43.9 us)
   if (algo == 3 || algo == 0) {
     const int rc = ssd3d_head_conv_kw(x, w, bias, locs, scores, N, C, D, H, W, bpl, n_classes, NPAD, P, prior_offset,
                                       nan_flag, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
