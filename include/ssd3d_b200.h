@@ -293,6 +293,16 @@ int ssd3d_map_class(const float* det_boxes, const float* det_scores, const int32
  * its bias) produced from the flat fp32 parameter buffer in one launch after the optimizer step. */
 int ssd3d_gather_cast(const float* src, const int32_t* index, int64_t n, void* dst, int dst_is_bf16, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input preparation: MONAI NormalizeIntensity(nonzero=True) of the data module
+ * (datasets.py:403) on the device.  x: `items` = N*C contiguous volumes of `voxels` fp32 values (NCDHW);
+ * per item z-score over the non-zero voxels (population std; std == 0 -> 1; zeros stay zero), written as fp32 or
+ * bf16 in the same layout -- the stem's input format.  workspace: ssd3d_normalize_workspace_bytes(items).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t ssd3d_normalize_workspace_bytes(int items);
+int ssd3d_normalize_intensity_nonzero(const float* x, int items, int64_t voxels, void* y, int y_is_bf16,
+                                      void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

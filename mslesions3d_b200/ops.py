@@ -641,3 +641,24 @@ def gather_cast(src: torch.Tensor, index: torch.Tensor, dst: torch.Tensor) -> No
                                        int(dst.dtype == BF16), _stream())
     _lib.check(rc, "ssd3d_gather_cast")
     LAUNCHES[0] += 1
+
+
+def normalize_intensity_nonzero(x: torch.Tensor, out_dtype: torch.dtype = BF16) -> torch.Tensor:
+    """MONAI ``NormalizeIntensity(nonzero=True)`` (datasets.py:403) per (volume, channel) on the device:
+    x (N, C, D, H, W) fp32 -> z-scored over its non-zero voxels, fp32 or bf16 (the stem's input format)."""
+    _need_cuda(x)
+    if x.dim() != 5:
+        raise RuntimeError("expected a 5-D (N, C, D, H, W) tensor")
+    if out_dtype not in (torch.float32, BF16):
+        raise RuntimeError("out_dtype must be float32 or bfloat16")
+    x = x.float().contiguous()
+    n, c = x.shape[0], x.shape[1]
+    vox = x.numel() // (n * c)
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    lib = _lib.load()
+    ws = torch.empty((lib.ssd3d_normalize_workspace_bytes(n * c),), dtype=torch.uint8, device=x.device)
+    rc = lib.ssd3d_normalize_intensity_nonzero(x.data_ptr(), n * c, vox, y.data_ptr(), int(out_dtype == BF16),
+                                               ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_normalize_intensity_nonzero")
+    LAUNCHES[0] += 3
+    return y

@@ -264,3 +264,25 @@ def test_predict_entry_point_writes_reference_style_outputs(tmp_path):
     with torch.no_grad():
         b, l, s = model.predict_step({"img": torch.from_numpy(vols[:2])}, 0)
     assert torch.equal(torch.tensor(res["0"]["scores"]), s[0].cpu()) and torch.equal(torch.tensor(res["1"]["boxes"]), b[1].cpu())
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 32, 32, 32), (3, 2, 17, 19, 23), (1, 1, 64, 64, 64)])
+def test_normalize_intensity_nonzero_matches_data_module(shape):
+    """datasets.py:403 (MONAI NormalizeIntensity(nonzero=True)) restated in synthetic.normalize_nonzero (numpy,
+    fp64 statistics): the device version must agree to fp32 rounding, keep zeros at zero, and emit the stem's bf16."""
+    import numpy as np
+    from mslesions3d_b200 import ops, synthetic
+    rs = np.random.RandomState(sum(shape))
+    x = rs.rand(*shape).astype(np.float32)
+    x[x < 0.3] = 0.0                                   # plenty of exact zeros (background)
+    x[0, 0, :2] = 0.0
+    want = np.stack([np.stack([synthetic.normalize_nonzero(x[n, c]) for c in range(shape[1])]) for n in range(shape[0])])
+    got = ops.normalize_intensity_nonzero(torch.from_numpy(x).cuda(), torch.float32).cpu().numpy()
+    assert np.array_equal(got == 0, x == 0) or np.all(got[x == 0] == 0)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+    got16 = ops.normalize_intensity_nonzero(torch.from_numpy(x).cuda()).float().cpu()
+    assert torch.equal(got16, torch.from_numpy(got).to(torch.bfloat16).float())
+    z = torch.zeros(1, 1, 8, 8, 8, device="cuda")
+    assert float(ops.normalize_intensity_nonzero(z, torch.float32).abs().max()) == 0.0
+    c = torch.full((1, 1, 8, 8, 8), 3.0, device="cuda")           # std == 0 -> divide by 1
+    assert float(ops.normalize_intensity_nonzero(c, torch.float32).abs().max()) == 0.0
