@@ -224,6 +224,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     _lib.load()
+    if world > 1:
+        from mslesions3d_b200.parallel import bind_to_gpu_cpus
+        bind_to_gpu_cpus(local_rank)      # pinned staging buffers next to the GPU they feed
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

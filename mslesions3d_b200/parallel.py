@@ -51,3 +51,25 @@ def gather_detections(local: Sequence, dst: int = 0) -> List:
     for part in out:
         merged.extend(part)
     return merged
+
+
+def bind_to_gpu_cpus(local_rank: int) -> Sequence[int]:
+    """Pin this process to the CPUs NVML reports as local to its GPU (same NUMA node / PCIe root), so that pinned
+    host staging buffers allocated afterwards are first-touched next to the GPU they feed: with 8 ranks copying
+    67 MB per step each, cross-socket traffic otherwise halves the per-GPU host->device bandwidth.  Best effort:
+    returns the CPU list it bound to, or () when NVML / affinity control is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return ()
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return ()
