@@ -219,7 +219,6 @@ def main():
     import torch.distributed as dist
     from mslesions3d_b200 import _lib, ops
     from mslesions3d_b200.ssd3d import LSSD3D
-    from oracle import ssd3d_oracle as O  # weights only (random_state_dict); never on the timed path
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -234,7 +233,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- model + inputs -------------------------------------------------------------------------
-    sd = O.random_state_dict(CHANNELS, seed=0)
+    from mslesions3d_b200 import synthetic
+    sd = synthetic.random_state_dict(CHANNELS, seed=0)
     model = LSSD3D(n_classes=2, input_channels=CHANNELS, input_size=SIZE, min_score=MIN_SCORE,
                    max_overlap=MAX_OVERLAP, top_k=TOP_K)
     model.load_state_dict(sd)

@@ -114,3 +114,68 @@ def make_batch(batch_size: int, channels: int = 1, image_size: Sequence[int] = (
     if with_boxes:
         return vols, boxes, labels
     return vols
+
+
+# --------------------------------------------------------------------------------------------------
+# random-init weights of the SSD3D-MobileNet architecture (benchmark / test input generation)
+# --------------------------------------------------------------------------------------------------
+_MOBILENET_PLAN = ((64, 1, 2), (128, 2, 2), (256, 2, 2), (512, 6, 2), (1024, 2, 1))   # mobilenet.py:13-20
+_DEFAULT_ASPECT_RATIOS = {3: [1.0], 5: [1.0], 7: [1]}                                  # ssd3d.py:25
+
+
+def _backbone_plan(in_channels: int, last_layer: int):
+    """(kind, cin, cout) of every backbone layer up to ``last_layer`` (ssd3d.py:56-75)."""
+    layers = [("stem", in_channels, 32)]
+    c_in = 32
+    for c, n, _ in _MOBILENET_PLAN:
+        for _i in range(n):
+            if len(layers) - 1 == last_layer:
+                return layers
+            layers.append(("block", c_in, c))
+            c_in = c
+    return layers
+
+
+def random_state_dict(in_channels=1, aspect_ratios=None, n_classes=2, seed=0, randomize_bn=True):
+    """Random-init weights with the reference's 103 state-dict keys / shapes: conv weights
+    ~ U(-b, b), b = sqrt(6 / fan_in); BN affine parameters and running statistics randomised so that folding is
+    exercised.  Deterministic in ``seed`` (torch CPU generator)."""
+    import math
+    import torch
+    if not aspect_ratios:
+        aspect_ratios = _DEFAULT_ASPECT_RATIOS
+    g = torch.Generator().manual_seed(seed)
+    layers = _backbone_plan(in_channels, max(aspect_ratios.keys()))
+    sd = {}
+
+    def conv_w(co, ci, k):
+        bound = math.sqrt(6.0 / (ci * k ** 3))
+        return (torch.rand((co, ci, k, k, k), generator=g) * 2 - 1) * bound
+
+    def bn(prefix, c):
+        sd[prefix + ".weight"] = 1.0 + 0.2 * (torch.rand(c, generator=g) - 0.5) if randomize_bn else torch.ones(c)
+        sd[prefix + ".bias"] = 0.1 * torch.randn(c, generator=g) if randomize_bn else torch.zeros(c)
+        sd[prefix + ".running_mean"] = 0.1 * torch.randn(c, generator=g) if randomize_bn else torch.zeros(c)
+        sd[prefix + ".running_var"] = 0.5 + torch.rand(c, generator=g) if randomize_bn else torch.ones(c)
+        sd[prefix + ".num_batches_tracked"] = torch.tensor(0)
+
+    first_pred = min(aspect_ratios.keys())
+    sd["rescale_factors"] = torch.full((1, layers[first_pred][2], 1, 1, 1), 20.0)
+    for i, (kind, cin, cout) in enumerate(layers):
+        p = "base.features.%d" % i
+        if kind == "stem":
+            sd[p + ".0.weight"] = conv_w(cout, cin, 3)
+            bn(p + ".1", cout)
+        else:
+            sd[p + ".conv1.weight"] = conv_w(cin, 1, 3)
+            bn(p + ".bn1", cin)
+            sd[p + ".conv2.weight"] = conv_w(cout, cin, 1)
+            bn(p + ".bn2", cout)
+    for hi, f in enumerate(aspect_ratios.keys()):
+        c = layers[f][2]
+        nb = len(aspect_ratios[f]) + 1      # boxes_per_location is hard-coded to 2 (ssd3d.py:213)
+        sd["pred_convs.loc_convs.%d.weight" % hi] = conv_w(nb * 6, c, 3)
+        sd["pred_convs.loc_convs.%d.bias" % hi] = 0.05 * torch.randn(nb * 6, generator=g)
+        sd["pred_convs.cl_convs.%d.weight" % hi] = conv_w(nb * n_classes, c, 3)
+        sd["pred_convs.cl_convs.%d.bias" % hi] = 0.05 * torch.randn(nb * n_classes, generator=g)
+    return sd

@@ -438,48 +438,11 @@ def multibox_loss(predicted_locs, predicted_scores, boxes: List[torch.Tensor], l
 # weights
 # --------------------------------------------------------------------------- #
 def random_state_dict(in_channels=1, aspect_ratios=None, n_classes=2, seed=0, randomize_bn=True):
-    """Random-init weights with the reference's 103 state-dict keys/shapes.
-
-    Conv weights ~ kaiming-uniform-like U(-b, b) with b = sqrt(6/fan_in); BN
-    running stats randomised so that folding is exercised.
-    """
-    if not aspect_ratios:
-        aspect_ratios = DEFAULT_ASPECT_RATIOS
-    g = torch.Generator().manual_seed(seed)
-    layers = backbone_layers(in_channels, True, max(aspect_ratios.keys()))
-    sd = {}
-
-    def conv_w(co, ci, k):
-        bound = math.sqrt(6.0 / (ci * k ** 3))
-        return (torch.rand((co, ci, k, k, k), generator=g) * 2 - 1) * bound
-
-    def bn(prefix, c):
-        sd[prefix + ".weight"] = 1.0 + 0.2 * (torch.rand(c, generator=g) - 0.5) if randomize_bn else torch.ones(c)
-        sd[prefix + ".bias"] = 0.1 * torch.randn(c, generator=g) if randomize_bn else torch.zeros(c)
-        sd[prefix + ".running_mean"] = 0.1 * torch.randn(c, generator=g) if randomize_bn else torch.zeros(c)
-        sd[prefix + ".running_var"] = 0.5 + torch.rand(c, generator=g) if randomize_bn else torch.ones(c)
-        sd[prefix + ".num_batches_tracked"] = torch.tensor(0)
-
-    first_pred = min(aspect_ratios.keys())
-    sd["rescale_factors"] = torch.full((1, layers[first_pred]["cout"], 1, 1, 1), 20.0)
-    for i, L in enumerate(layers):
-        p = "base.features.%d" % i
-        if L["kind"] == "stem":
-            sd[p + ".0.weight"] = conv_w(L["cout"], L["cin"], 3)
-            bn(p + ".1", L["cout"])
-        else:
-            sd[p + ".conv1.weight"] = conv_w(L["cin"], 1, 3)
-            bn(p + ".bn1", L["cin"])
-            sd[p + ".conv2.weight"] = conv_w(L["cout"], L["cin"], 1)
-            bn(p + ".bn2", L["cout"])
-    for hi, f in enumerate(aspect_ratios.keys()):
-        c = layers[f]["cout"]
-        nb = len(aspect_ratios[f]) + BOXES_PER_LOCATION - 1
-        sd["pred_convs.loc_convs.%d.weight" % hi] = conv_w(nb * 6, c, 3)
-        sd["pred_convs.loc_convs.%d.bias" % hi] = 0.05 * torch.randn(nb * 6, generator=g)
-        sd["pred_convs.cl_convs.%d.weight" % hi] = conv_w(nb * n_classes, c, 3)
-        sd["pred_convs.cl_convs.%d.bias" % hi] = 0.05 * torch.randn(nb * n_classes, generator=g)
-    return sd
+    """Random-init weights with the reference's 103 state-dict keys/shapes: input
+    generation, shared with the benchmark, lives in ``mslesions3d_b200.synthetic`` (the oracle is the checker, not
+    the source of inputs)."""
+    from mslesions3d_b200 import synthetic
+    return synthetic.random_state_dict(in_channels, aspect_ratios, n_classes, seed, randomize_bn)
 
 
 # --------------------------------------------------------------------------- #

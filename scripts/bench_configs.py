@@ -17,7 +17,7 @@ import torch  # noqa: E402
 
 from mslesions3d_b200 import synthetic  # noqa: E402
 from mslesions3d_b200.ssd3d import LSSD3D  # noqa: E402
-from oracle import ssd3d_oracle as O  # noqa: E402
+from oracle import ssd3d_oracle as O  # noqa: E402  (CPU baseline leg only)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--json", default="")
@@ -36,7 +36,7 @@ CASES = [
 rows = []
 for c in CASES:
     kw = dict(aspect_ratios=c["ar"]) if c["ar"] else {}
-    sd = O.random_state_dict(c["ch"], c["ar"], seed=0)
+    sd = synthetic.random_state_dict(c["ch"], c["ar"], seed=0)
     model = LSSD3D(n_classes=2, input_channels=c["ch"], input_size=c["size"], min_score=c["min_score"],
                    top_k=c["top_k"], **kw)
     model.load_state_dict(sd)

@@ -47,7 +47,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     size = (args.size,) * 3
-    sd = O.random_state_dict(args.channels, seed=0)
+    sd = synthetic.random_state_dict(args.channels, seed=0)
     model = LSSD3D(n_classes=2, input_channels=args.channels, input_size=size, threshold=[0.1, 0.2], lr=1e-4)
     model.load_state_dict(sd)
     model = model.to(dev).train()

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mslesions3d_b200 import ops  # noqa: E402
 from mslesions3d_b200.ssd3d import LSSD3D  # noqa: E402
-from oracle import ssd3d_oracle as O  # noqa: E402  (random weights only)
+from mslesions3d_b200 import synthetic as O  # noqa: E402  (random weights)
 
 dev = torch.device("cuda")
 N, S = 8, 128

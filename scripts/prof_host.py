@@ -10,7 +10,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mslesions3d_b200.ssd3d import LSSD3D  # noqa: E402
-from oracle import ssd3d_oracle as O  # noqa: E402
+from mslesions3d_b200 import synthetic as O  # noqa: E402
 
 dev = torch.device("cuda")
 model = LSSD3D(n_classes=2, input_channels=2, input_size=(128, 128, 128))
