@@ -20,8 +20,10 @@ run head     tests/test_gpu_network.py -k "head"
 run forward  tests/test_gpu_network.py -k "forward"
 run detect   tests/test_gpu_detect.py
 run match    tests/test_gpu_match_loss.py
+run train    tests/test_gpu_train.py
+run metrics  tests/test_gpu_metrics.py
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; r=$?
 echo "== smoke: exit $r: $(tail -1 gpurun_out/smoke.log)"; [ $r -ne 0 ] && rc=1
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; r=$?
+timeout 900 python bench.py --steps 100 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; r=$?
 echo "== bench: exit $r"; cat gpurun_out/bench.json; [ $r -ne 0 ] && { rc=1; tail -5 gpurun_out/bench.err; }
 exit $rc
