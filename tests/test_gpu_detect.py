@@ -286,3 +286,29 @@ def test_normalize_intensity_nonzero_matches_data_module(shape):
     assert float(ops.normalize_intensity_nonzero(z, torch.float32).abs().max()) == 0.0
     c = torch.full((1, 1, 8, 8, 8), 3.0, device="cuda")           # std == 0 -> divide by 1
     assert float(ops.normalize_intensity_nonzero(c, torch.float32).abs().max()) == 0.0
+
+
+def test_predict_batches_ragged_last_batch_and_early_stop():
+    """A loader whose last batch is smaller gets its own plan; abandoning the generator early leaves the model usable."""
+    from mslesions3d_b200 import synthetic
+    from mslesions3d_b200.ssd3d import LSSD3D
+    sd = O.random_state_dict(1, seed=3)
+    m = LSSD3D(n_classes=2, input_channels=1, input_size=(64, 64, 64), min_score=0.4, top_k=30)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    vols = torch.from_numpy(synthetic.make_batch(7, 1, (64, 64, 64)))
+    batches = [vols[0:3], vols[3:6], vols[6:7]]
+    with torch.no_grad():
+        ref = [m.predict_step({"img": b.cuda()}, 0) for b in batches]
+        got = list(m.predict_batches({"img": b.pin_memory()} for b in batches))
+        assert [len(g[0]) for g in got] == [3, 3, 1]
+        for r, g in zip(ref, got):
+            for i in range(len(r[0])):
+                assert torch.equal(r[0][i], g[0][i]) and torch.equal(r[1][i], g[1][i]) and torch.equal(r[2][i], g[2][i])
+        gen = m.predict_batches({"img": b.cuda()} for b in batches * 3)
+        first = next(gen)
+        gen.close()                                   # consumer walks away with batches still in flight
+        again = list(m.predict_batches({"img": b.cuda()} for b in batches))
+        for r, g in zip(ref, again):
+            assert torch.equal(r[0][0], g[0][0]) and torch.equal(r[2][0], g[2][0])
+        assert torch.equal(first[0][0], ref[0][0][0])

@@ -391,3 +391,36 @@ def test_fit_step_skips_a_batch_without_positives():
     loss2 = model.fit_step({"img": x, "boxes": boxes, "labels": labels})
     assert bool(torch.isfinite(loss2).all()) and model.fit_skipped_steps() == 1
     assert any(not torch.equal(after[k], before[k]) for k in before)
+
+
+def test_training_step_noncube_input_and_bf16_images():
+    """Non-cubic volumes use stem stride (1,2,2) (ssd3d.py:60) and the x/y-swapped prior axes; the
+    fused step also accepts bf16 images.  Losses against the bf16-emulating oracle, gradients by cosine."""
+    size, channels = (32, 64, 48), 2
+    sd = O.random_state_dict(channels, seed=8)
+    x, b, l = synthetic.make_batch(4, channels, size, first_idx=3, with_boxes=True)
+    x = torch.from_numpy(x)
+    boxes, labels = [torch.from_numpy(v) for v in b], [torch.from_numpy(v) for v in l]
+    thr = [0.1, 0.2]
+    model = _model(sd, channels, size, threshold=thr)
+    out = model.training_step({"img": x, "boxes": boxes, "labels": labels})
+    out["loss"].backward()
+    pri = O.prior_boxes(size, in_channels=channels)
+    emu = O.train_step_grads(sd, x, boxes, labels, pri, thr, emulate_bf16=True)
+    assert abs(float(out["log"]["train_conf_loss"]) - float(emu["conf"])) <= 5e-3 * abs(float(emu["conf"]))
+    assert abs(float(out["log"]["train_loc_loss"]) - float(emu["loc"])) <= 5e-3 * abs(float(emu["loc"]))
+    params = dict(model.named_parameters())
+    num = den = 0.0
+    for k, want in emu["grads"].items():
+        if want is None or float(want.norm()) == 0.0:
+            continue
+        got = params[k].grad.cpu()
+        num += float((got - want).norm()) ** 2
+        den += float(want.norm()) ** 2
+    assert (num / den) ** 0.5 <= 0.15, (num / den) ** 0.5
+    # fused step on bf16 images: same first loss as on the fp32 images (the stem rounds fp32 inputs to bf16 itself)
+    m1 = _model(sd, channels, size, threshold=thr, lr=1e-4)
+    m2 = _model(sd, channels, size, threshold=thr, lr=1e-4)
+    l1 = m1.fit_step({"img": x, "boxes": boxes, "labels": labels}).cpu()
+    l2 = m2.fit_step({"img": x.to(torch.bfloat16), "boxes": boxes, "labels": labels}).cpu()
+    assert torch.equal(l1, l2)
