@@ -86,11 +86,15 @@ int ssd3d_pwconv_bn_relu(const void* x, const void* w, const float* scale, const
  *          C % 64 == 0 and NPAD <= 64); 3 = kw-GEMM + (kd,kh) stencil for maps with N*D*H*W >= 256 (
  *          C % 64 == 0, NPAD == 16): an implicit GEMM over the 3 W-taps with 144 output columns (9x the work
  *          per UMMA, 3 instead of 27 activation reads), then nine shifted reads per output from the L2-resident
- *          intermediate (in the workspace) */
+ *          intermediate (in the workspace); 4 = the same with `w` ALREADY in the (144, 3*C) tiling produced by
+ *          ssd3d_head_weight_kw (saves the per-call re-tiling when the weights are static, i.e. inference) */
 int64_t ssd3d_head_workspace_bytes(int N, int C, int D, int H, int W, int NPAD);
 int ssd3d_head_conv(const void* x, const void* w, const float* bias, float* locs, float* scores, int N, int C,
                     int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset,
                     int* nan_flag, void* workspace, int64_t workspace_bytes, int algo, void* stream);
+/* (16, 27*C) packed head weight -> w_kw (144, 3*C) bf16: row (kd*3+kh)*16 + n, column kw*C + c.  C % 64 == 0 */
+int ssd3d_head_weight_kw(const void* w, int C, void* w_kw, void* stream);
+int ssd3d_head_kw_supported(int N, int C, int D, int H, int W, int NPAD);
 
 /* ------------------------------------------------------------------------------------------------
  * Box geometry (utils.py:42-149).  All fp32, every arithmetic step separately rounded (no FMA).

@@ -33,6 +33,8 @@ SIGNATURES = {
     "ssd3d_head_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "ssd3d_head_conv": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
                                 c_int64, P, P, c_int64, c_int, P]),
+    "ssd3d_head_weight_kw": (c_int, [P, c_int, P, P]),
+    "ssd3d_head_kw_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "ssd3d_box_transform": (c_int, [c_int, P, P, P, c_int64, P]),
     "ssd3d_iou3d_pairwise": (c_int, [P, P, P, c_int64, c_int64, c_int, P]),
     "ssd3d_detect_workspace_bytes": (c_int64, [c_int, c_int64, c_int, c_int]),

@@ -226,19 +226,22 @@ bool ssd3d_head_kw_applicable(int N, int C, int D, int H, int W, int NPAD) {
   return NPAD == 16 && C % 64 == 0 && (long long)N * D * H * W >= 256;
 }
 
-int ssd3d_head_conv_kw(const void* x, const void* w, const float* bias, float* locs, float* scores, int N, int C, int D,
-                       int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset, int* nan_flag,
-                       void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+// w_is_kw != 0: `w` already is the (144, 3*C) tiling (ssd3d_head_weight_kw); otherwise it is re-tiled here per call
+int ssd3d_head_conv_kw(const void* x, const void* w, int w_is_kw, const float* bias, float* locs, float* scores, int N,
+                       int C, int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset,
+                       int* nan_flag, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   if (!ssd3d_head_kw_applicable(N, C, D, H, W, NPAD)) return SSD3D_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < ssd3d_head_kw_workspace_bytes(N, C, D, H, W)) return SSD3D_ERR_ARG;
   const long long M = (long long)N * D * H * W;
   float* Y = static_cast<float*>(workspace);
-  __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) +
-                                                       ((M * KW_N * 4 + 1023) & ~1023ll));
-  {
+  const __nv_bfloat16* w2 = static_cast<const __nv_bfloat16*>(w);
+  if (!w_is_kw) {
+    __nv_bfloat16* tmp = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(workspace) +
+                                                          ((M * KW_N * 4 + 1023) & ~1023ll));
     const int total = KW_N * 3 * C / 8;
     SSD3D_LAUNCH_PDL(head_kw_repack_kernel, dim3((total + 255) / 256), dim3(256), 0, st,
-                     static_cast<const __nv_bfloat16*>(w), w2, C);
+                     static_cast<const __nv_bfloat16*>(w), tmp, C);
+    w2 = tmp;
   }
   HeadKwParams p{};
   p.C = C; p.D = D; p.H = H; p.W = W; p.N = N;
@@ -285,4 +288,17 @@ int ssd3d_head_conv_kw(const void* x, const void* w, const float* bias, float* l
   const long long total = M * 4;
   SSD3D_LAUNCH_PDL(head_stencil_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);
   return SSD3D_OK;
+}
+
+// (NPAD = 16, 27*C) packed head weight -> (144, 3*C) tiling of the kw-GEMM, once per weight version
+extern "C" int ssd3d_head_weight_kw(const void* w, int C, void* w_kw, void* stream) {
+  if (!w || !w_kw || C <= 0 || (C % 64)) return SSD3D_ERR_ARG;
+  const int total = KW_N * 3 * C / 8;
+  SSD3D_LAUNCH_PDL(head_kw_repack_kernel, dim3((total + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                   static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(w_kw), C);
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_head_kw_supported(int N, int C, int D, int H, int W, int NPAD) {
+  return ssd3d_head_kw_applicable(N, C, D, H, W, NPAD) ? 1 : 0;
 }

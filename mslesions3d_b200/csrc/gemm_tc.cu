@@ -333,9 +333,9 @@ int ssd3d_head_conv_halo(const void* x, const void* w, const float* bias, float*
                          int* nan_flag, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
 // conv_head_kw.cu: kw-GEMM + stencil for large maps
-int ssd3d_head_conv_kw(const void* x, const void* w, const float* bias, float* locs, float* scores, int N, int C, int D,
-                       int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset, int* nan_flag,
-                       void* workspace, int64_t workspace_bytes, cudaStream_t st);
+int ssd3d_head_conv_kw(const void* x, const void* w, int w_is_kw, const float* bias, float* locs, float* scores, int N,
+                       int C, int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P, int64_t prior_offset,
+                       int* nan_flag, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
 extern "C" int ssd3d_head_conv(const void* x, const void* w, const float* bias, float* locs, float* scores, int N,
                                int C, int D, int H, int W, int bpl, int n_classes, int NPAD, int64_t P,
@@ -351,8 +351,11 @@ extern "C" int ssd3d_head_conv(const void* x, const void* w, const float* bias, 
   //   halo-tile kernel on small maps, where it can split K across CTAs (8^3: 23.6 vs 49 us, 4^3: 23.6 vs 88 us);
   //   per-tap kernel otherwise (e.g. the 32-channel layer-0 head): both older kernels are bound by the UMMA issue
   //     rate (~128 cycles per M=128 instruction whatever N) and the per-tap one issues fewer (30.7 vs 43.9 us)
+  if (algo == 4)     // kw path, `w` already in the (144, 3*C) tiling of ssd3d_head_weight_kw
+    return ssd3d_head_conv_kw(x, w, 1, bias, locs, scores, N, C, D, H, W, bpl, n_classes, NPAD, P, prior_offset, nan_flag,
+                              workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   if (algo == 3 || algo == 0) {
-    const int rc = ssd3d_head_conv_kw(x, w, bias, locs, scores, N, C, D, H, W, bpl, n_classes, NPAD, P, prior_offset,
+    const int rc = ssd3d_head_conv_kw(x, w, 0, bias, locs, scores, N, C, D, H, W, bpl, n_classes, NPAD, P, prior_offset,
                                       nan_flag, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (rc != SSD3D_ERR_UNSUPPORTED || algo == 3) return rc;
   }

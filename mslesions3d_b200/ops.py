@@ -127,7 +127,7 @@ def head_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, locs:
     x = to_channels_last_bf16(x)
     n, c, d, h, w = x.shape
     lib = _lib.load()
-    npad = w_packed.shape[0]
+    npad = w_packed.shape[0] if algo != 4 else 16
     need = lib.ssd3d_head_workspace_bytes(n, c, d, h, w, npad) if algo != 1 else 0
     ws = torch.empty((need,), dtype=torch.uint8, device=x.device) if need else None
     rc = lib.ssd3d_head_conv(x.data_ptr(), w_packed.data_ptr(), bias.data_ptr(), locs.data_ptr(), scores.data_ptr(),
@@ -135,6 +135,21 @@ def head_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, locs:
                              _ptr(ws), need, algo, _stream())
     _lib.check(rc, "ssd3d_head_conv")
     LAUNCHES[0] += 2 if need else 1
+
+
+def head_kw_supported(x: torch.Tensor, npad: int) -> bool:
+    n, c, d, h, w = x.shape
+    return bool(_lib.load().ssd3d_head_kw_supported(n, c, d, h, w, npad))
+
+
+def pack_head_weight_kw(w_packed: torch.Tensor) -> torch.Tensor:
+    """(16, 27*C) packed head weight -> (144, 3*C) tiling of the kw-GEMM head kernel (once per weight version)."""
+    _need_cuda(w_packed)
+    c = w_packed.shape[1] // 27
+    out = torch.empty((144, 3 * c), dtype=BF16, device=w_packed.device)
+    rc = _lib.load().ssd3d_head_weight_kw(w_packed.data_ptr(), c, out.data_ptr(), _stream())
+    _lib.check(rc, "ssd3d_head_weight_kw")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

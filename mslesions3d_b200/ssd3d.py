@@ -184,6 +184,7 @@ class PredictionConvolutions(nn.Module):
         self.loc_convs = nn.ModuleList(loc_convs)
         self.cl_convs = nn.ModuleList(cl_convs)
         self._packed = None
+        self._packed_kw = None
         self._packed_key = None
 
     def init(self):
@@ -200,6 +201,9 @@ class PredictionConvolutions(nn.Module):
         if self._packed is None or key != self._packed_key:
             self._packed = [ops.pack_head_weight(lc.weight, lc.bias, cc.weight, cc.bias)
                             for lc, cc in zip(self.loc_convs, self.cl_convs)]
+            # the kw-GEMM head kernel's own tiling, once per weight version (C % 64 == 0, 16 output columns)
+            self._packed_kw = [ops.pack_head_weight_kw(w) if (w.is_cuda and w.shape[0] == 16 and (w.shape[1] // 27) % 64 == 0)
+                               else None for w, _ in self._packed]
             self._packed_key = key
         return self._packed
 
@@ -231,7 +235,11 @@ class PredictionConvolutions(nn.Module):
         """Head ``i`` (i-th prediction layer) on its feature map, written at ``prior_offset``."""
         w, b = self._pack()[i]
         bpl = self.n_boxes[list(self.aspect_ratios.keys())[i]]
-        ops.head_conv(feat, w, b, locs, classes_scores, bpl, self.n_classes, prior_offset, nan_flag)
+        w_kw = self._packed_kw[i]
+        if w_kw is not None and ops.head_kw_supported(feat, w.shape[0]):
+            ops.head_conv(feat, w_kw, b, locs, classes_scores, bpl, self.n_classes, prior_offset, nan_flag, algo=4)
+        else:
+            ops.head_conv(feat, w, b, locs, classes_scores, bpl, self.n_classes, prior_offset, nan_flag)
 
 
 class _InferencePlan:
