@@ -4,7 +4,9 @@ Layout:
   csrc/            CUDA kernels + the C ABI (include/ssd3d_b200.h), built into libssd3d_b200.so
   _lib, ops        ctypes binding and tensor-level launch wrappers
   mobilenet, ssd3d, utils, predict   the reference's module/class/function surface on top of the kernels
-  synthetic        in-memory synthetic lesion volumes (the benchmark input spec)
+  training         train-mode forward with a tape, hand-written backward, flat-buffer Adam, captured fit_step
+  parallel         batch-of-volumes data parallelism helpers (torchrun / NCCL, gloo in CPU tests)
+  synthetic        in-memory synthetic lesion volumes and random-init weights (the benchmark input spec)
 """
 __version__ = "0.1.0"
 
