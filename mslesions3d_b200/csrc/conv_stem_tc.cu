@@ -328,6 +328,188 @@ __global__ void __launch_bounds__(128, 4) stem_tc_kernel(const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stem WEIGHT gradient on the same tiles: dW[co][k] = sum_voxels dz[v][co] * im2col(x)[v][k], k = ci*27 + tap.
+// The forward kernel's machinery produces im2col rows from a TMA halo box in shared memory (36 four-byte LDS per
+// voxel instead of 27 scalar global loads with index arithmetic); here the row goes to a padded smem tile and
+// mma.sync (bf16, fp32 accumulate) contracts it with the voxel's 32 gradient channels.  Accumulators live in
+// registers across all tiles of the persistent CTA; one (32, KPAD) partial slab per CTA, summed by the caller.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sw_ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sw_mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename TIn, int CIN>
+__global__ void __launch_bounds__(128, 4) stem_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                 const StemParams p,
+                                                                 const __nv_bfloat16* __restrict__ dz,
+                                                                 float* __restrict__ partial) {
+  constexpr int KREAL = 27 * CIN;
+  constexpr int KPAD = (KREAL <= 64) ? 64 : 128;
+  constexpr int NREG = KPAD / 2;
+  constexpr int PADL = 16 / (int)sizeof(TIn);
+  constexpr int NG = 9 * CIN;
+  constexpr int XP = KPAD + 8;            // padded pitches (elements): conflict-free ldmatrix
+  constexpr int ZP = 40;
+  constexpr int NB = KPAD / 64;           // 16-column groups per warp (each warp owns KPAD/4 columns)
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((128u - (raw & 127u)) & 127u);
+  __nv_bfloat16* sXc = reinterpret_cast<__nv_bfloat16*>(smem);                 // [128][XP]
+  __nv_bfloat16* sZ = sXc + 128 * XP;                                          // [128][ZP]
+  uint64_t* bar_in = reinterpret_cast<uint64_t*>(sZ + 128 * ZP);               // [2]
+  const int tile_elems = CIN * p.TDI * p.THI * p.TWI;
+  const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(TIn));
+  const uint32_t tile_pitch = (tile_bytes + 127u) & ~127u;
+  uint8_t* sX = reinterpret_cast<uint8_t*>(bar_in) + 128;                      // 2 x halo tile
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_d * p.N;
+  if (tid == 32) {
+    tma_prefetch_desc(&tmX);
+    mbar_init(&bar_in[0], 1);
+    mbar_init(&bar_in[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue_tma = [&](int tile, int buf) {
+    int t = tile;
+    const int w0 = (t % p.tiles_w) * p.TW; t /= p.tiles_w;
+    const int h0 = (t % p.tiles_h) * p.TH; t /= p.tiles_h;
+    const int d0 = (t % p.tiles_d) * p.TD; t /= p.tiles_d;
+    mbar_arrive_expect_tx(&bar_in[buf], tile_bytes);
+    tma_load_4d(sX + (size_t)buf * tile_pitch, &tmX, &bar_in[buf], 2 * w0 - PADL, 2 * h0 - 1, p.sd * d0 - 1, t * CIN);
+  };
+  const int first = blockIdx.x;
+  pdl_wait();
+  pdl_launch_dependents();
+  if (tid == 32) {
+    if (first < total_tiles) issue_tma(first, 0);
+    if (first + (int)gridDim.x < total_tiles) issue_tma(first + gridDim.x, 1);
+  }
+  const int wl = tid % p.TW;
+  const int hl = (tid / p.TW) % p.TH;
+  const int dl = tid / (p.TW * p.TH);
+  const int vox_off = ((p.sd * dl) * p.THI + 2 * hl) * p.TWI + 2 * wl + PADL;
+  const int plane = p.TDI * p.THI * p.TWI;
+
+  float acc[2][2 * NB][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2 * NB; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  const uint32_t sXc_u = smem_u32(sXc), sZ_u = smem_u32(sZ);
+  const int lq = lane >> 3, lr = lane & 7;
+
+  int it = 0;
+  for (int tile = first; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    mbar_wait(&bar_in[buf], (uint32_t)((it >> 1) & 1));
+    // ---- im2col row of this thread's voxel (same gather as the forward kernel) ----
+    uint32_t regs[NREG];
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) regs[i] = 0u;
+    const TIn* xt = reinterpret_cast<const TIn*>(sX + (size_t)buf * tile_pitch) + vox_off;
+    if constexpr (sizeof(TIn) == 2) {
+      uint32_t wa[NG], wb[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int ci = g / 9, kd = (g / 3) % 3, kh = g % 3;
+        const TIn* src = xt + ci * plane + (kd * p.THI + kh) * p.TWI;
+        wa[g] = *reinterpret_cast<const uint32_t*>(src - 2);
+        wb[g] = *reinterpret_cast<const uint32_t*>(src);
+      }
+#pragma unroll
+      for (int g = 0; g + 1 < NG; g += 2) {
+        const int r = (3 * g) >> 1;
+        regs[r] = __byte_perm(wa[g], wb[g], 0x5432);
+        regs[r + 1] = __byte_perm(wb[g], wa[g + 1], 0x7632);
+        regs[r + 2] = wb[g + 1];
+      }
+      if constexpr (NG & 1) {
+        const int g = NG - 1, r = (3 * g) >> 1;
+        regs[r] = __byte_perm(wa[g], wb[g], 0x5432);
+        regs[r + 1] = wb[g] >> 16;
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int ci = g / 9, kd = (g / 3) % 3, kh = g % 3;
+        const float* src = reinterpret_cast<const float*>(xt) + ci * plane + (kd * p.THI + kh) * p.TWI;
+        const float a = src[-1];
+        const float2 b = *reinterpret_cast<const float2*>(src);
+        const uint32_t e0 = bf16_bits(a), e1 = bf16_bits(b.x), e2 = bf16_bits(b.y);
+        const int k0 = g * 3;
+        regs[(k0 + 0) >> 1] |= e0 << (16 * ((k0 + 0) & 1));
+        regs[(k0 + 1) >> 1] |= e1 << (16 * ((k0 + 1) & 1));
+        regs[(k0 + 2) >> 1] |= e2 << (16 * ((k0 + 2) & 1));
+      }
+    }
+    // ---- this voxel's 32 gradient channels (zero outside the volume) ----
+    int t = tile;
+    const int wo = (t % p.tiles_w) * p.TW + wl; t /= p.tiles_w;
+    const int ho = (t % p.tiles_h) * p.TH + hl; t /= p.tiles_h;
+    const int dzo = (t % p.tiles_d) * p.TD + dl; t /= p.tiles_d;
+    uint4 g4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g4[q] = make_uint4(0u, 0u, 0u, 0u);
+    if (wo < p.Wo && ho < p.Ho && dzo < p.Do) {
+      const uint4* src = reinterpret_cast<const uint4*>(dz + ((((long long)t * p.Do + dzo) * p.Ho + ho) * p.Wo + wo) * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g4[q] = __ldg(src + q);
+    }
+    __syncthreads();            // the previous tile's fragments have been read; everyone is done with sX[buf]
+    if (tid == 32) {
+      const int nxt = tile + 2 * (int)gridDim.x;
+      if (nxt < total_tiles) issue_tma(nxt, buf);
+    }
+#pragma unroll
+    for (int j = 0; j < KPAD / 8; ++j)
+      *reinterpret_cast<uint4*>(sXc + tid * XP + j * 8) = make_uint4(regs[4 * j], regs[4 * j + 1], regs[4 * j + 2], regs[4 * j + 3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(sZ + tid * ZP + q * 8) = g4[q];
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int kk = ks * 16;
+      uint32_t afr[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)      // A = dz^T (16 co x 16 voxels), transposed on load
+        sw_ldsm_x4_t(sZ_u + (uint32_t)(((kk + (lq >> 1) * 8 + lr) * ZP + a * 16 + (lq & 1) * 8) * 2), afr[a]);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        uint32_t bfr[4];               // B = im2col rows (16 voxels x 16 k), two n8 tiles
+        sw_ldsm_x4_t(sXc_u + (uint32_t)(((kk + (lq & 1) * 8 + lr) * XP + warp * (KPAD / 4) + b * 16 + (lq >> 1) * 8) * 2), bfr);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          sw_mma_bf16(acc[a][2 * b], afr[a], bfr[0], bfr[1]);
+          sw_mma_bf16(acc[a][2 * b + 1], afr[a], bfr[2], bfr[3]);
+        }
+      }
+    }
+  }
+  float* out = partial + (size_t)blockIdx.x * 32 * KPAD + warp * (KPAD / 4);
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2 * NB; ++b) {
+      const int co = a * 16 + (lane >> 2), k = b * 8 + (lane & 3) * 2;
+      *reinterpret_cast<float2*>(out + (size_t)co * KPAD + k) = make_float2(acc[a][b][0], acc[a][b][1]);
+      *reinterpret_cast<float2*>(out + (size_t)(co + 8) * KPAD + k) = make_float2(acc[a][b][2], acc[a][b][3]);
+    }
+}
+
 static inline int p2ceil(int v) {
   int r = 1;
   while (r < v) r <<= 1;
@@ -375,6 +557,39 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
   return SSD3D_OK;
 }
 
+template <typename TIn, int CIN>
+static int launch_stem_wgrad(const void* x, const StemParams& p, CUtensorMapDataType dt, const __nv_bfloat16* dz,
+                             float* partial, int max_slabs, int* slabs, cudaStream_t st) {
+  constexpr int KPAD = (27 * CIN <= 64) ? 64 : 128;
+  CUtensorMap tm;
+  {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return SSD3D_ERR_TMA;
+    const cuuint64_t es = sizeof(TIn);
+    cuuint64_t gdim[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N * CIN};
+    cuuint64_t gstr[3] = {(cuuint64_t)p.W * es, (cuuint64_t)p.W * p.H * es, (cuuint64_t)p.W * p.H * p.D * es};
+    cuuint32_t box[4] = {(cuuint32_t)p.TWI, (cuuint32_t)p.THI, (cuuint32_t)p.TDI, (cuuint32_t)CIN};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tm, dt, 4, const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return SSD3D_ERR_TMA;
+  }
+  const size_t tile_pitch = ((size_t)CIN * p.TDI * p.THI * p.TWI * sizeof(TIn) + 127) & ~(size_t)127;
+  const size_t smem = 128 + (size_t)128 * (KPAD + 8) * 2 + 128 * 40 * 2 + 128 + 2 * tile_pitch;
+  cudaError_t e = cudaFuncSetAttribute(stem_wgrad_tile_kernel<TIn, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
+  long long per_sm = (smem + 1024) * 4 <= 227 * 1024 ? 4 : ((smem + 1024) * 3 <= 227 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1));
+  long long grid = per_sm * persistent_sms();
+  if (grid > tiles) grid = tiles;
+  if (grid > max_slabs) grid = max_slabs;
+  if (grid < 1) return SSD3D_ERR_ARG;
+  SSD3D_LAUNCH_PDL((stem_wgrad_tile_kernel<TIn, CIN>), dim3((unsigned)grid), dim3(128), smem, st, tm, p, dz, partial);
+  *slabs = (int)grid;
+  return SSD3D_OK;
+}
+
 }  // namespace ssd3d
 
 using namespace ssd3d;
@@ -385,10 +600,8 @@ extern "C" int ssd3d_stem_tc_supported(int x_is_bf16, int Cin, int W) {
   return ((W * (x_is_bf16 ? 2 : 4)) % 16 == 0) ? 1 : 0;
 }
 
-static int stem_tc(const void* x, int x_is_bf16, const void* w_tc, const float* scale, const float* shift, void* y,
-                   int N, int Cin, int D, int H, int W, int stride_d, int relu, cudaStream_t st) {
-  StemParams p{};
-  p.floor = SSD3D_FLOOR(relu);
+// output tile + halo box of one 128-voxel tile (shared by the forward and the weight-gradient kernels)
+static int stem_tiling(StemParams& p, int x_is_bf16, int N, int D, int H, int W, int stride_d) {
   p.N = N; p.D = D; p.H = H; p.W = W; p.sd = stride_d;
   p.Do = (D - 1) / stride_d + 1; p.Ho = (H - 1) / 2 + 1; p.Wo = (W - 1) / 2 + 1;
   // output tile: widest W extent (<= 64) that wastes < 15 % of its columns, then H, then D
@@ -414,6 +627,14 @@ static int stem_tc(const void* x, int x_is_bf16, const void* w_tc, const float* 
   p.tiles_w = (p.Wo + p.TW - 1) / p.TW;
   p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
   p.tiles_d = (p.Do + p.TD - 1) / p.TD;
+  return SSD3D_OK;
+}
+
+static int stem_tc(const void* x, int x_is_bf16, const void* w_tc, const float* scale, const float* shift, void* y,
+                   int N, int Cin, int D, int H, int W, int stride_d, int relu, cudaStream_t st) {
+  StemParams p{};
+  p.floor = SSD3D_FLOOR(relu);
+  if (const int rc = stem_tiling(p, x_is_bf16, N, D, H, W, stride_d)) return rc;
   p.wt = static_cast<const __nv_bfloat16*>(w_tc);
   p.scale = scale;
   p.shift = shift;
@@ -461,3 +682,33 @@ extern "C" int ssd3d_stem_conv_bn_relu(const void* x, int x_is_bf16, const void*
                                        void* stream) {
   return ssd3d_stem_conv_affine(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, 1, stream);
 }
+
+// Tile-based stem weight gradient (used by ssd3d_stem_wgrad in train.cu): writes `*slabs` partial slabs of
+// (32, *kpad) fp32 to `partial`; SSD3D_ERR_UNSUPPORTED when TMA cannot address the input rows.
+namespace ssd3d {
+int stem_wgrad_tiles(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W, int stride_d,
+                     float* partial, int max_slabs, int* slabs, int* kpad, cudaStream_t st) {
+  if (!ssd3d_stem_tc_supported(x_is_bf16, Cin, W)) return SSD3D_ERR_UNSUPPORTED;
+  StemParams p{};
+  if (const int rc = stem_tiling(p, x_is_bf16, N, D, H, W, stride_d)) return rc;
+  *kpad = (27 * Cin <= 64) ? 64 : 128;
+  const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(dz);
+#define STEM_WG(T, DT, C) return launch_stem_wgrad<T, C>(x, p, DT, g, partial, max_slabs, slabs, st)
+  if (x_is_bf16) {
+    switch (Cin) {
+      case 1: STEM_WG(__nv_bfloat16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 1);
+      case 2: STEM_WG(__nv_bfloat16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+      case 3: STEM_WG(__nv_bfloat16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3);
+      default: STEM_WG(__nv_bfloat16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4);
+    }
+  } else {
+    switch (Cin) {
+      case 1: STEM_WG(float, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1);
+      case 2: STEM_WG(float, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2);
+      case 3: STEM_WG(float, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3);
+      default: STEM_WG(float, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
+    }
+  }
+#undef STEM_WG
+}
+}  // namespace ssd3d

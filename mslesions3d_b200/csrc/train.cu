@@ -1046,6 +1046,11 @@ extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int
   return SSD3D_OK;
 }
 
+namespace ssd3d {
+int stem_wgrad_tiles(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W, int stride_d,
+                     float* partial, int max_slabs, int* slabs, int* kpad, cudaStream_t st);   // conv_stem_tc.cu
+}
+
 extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W,
                                 int stride_d, float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!dz || !x || !dw || !workspace || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
@@ -1055,6 +1060,22 @@ extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, in
   const int K = (27 * Cin <= 32) ? 32 : (27 * Cin + 63) / 64 * 64;     // one 32-wide k tile for Cin = 1
   if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, 32, 27 * Cin)) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool use_tiles = [] { const char* e = getenv("SSD3D_STEM_WGRAD_TILES"); return !(e && e[0] == '0'); }();
+  if (use_tiles && M >= 128 * 148) {
+    // halo tiles through TMA + im2col in shared memory (the forward stem's gather), one slab per persistent CTA
+    const int kp = (27 * Cin <= 64) ? 64 : 128;
+    const int max_slabs = (int)std::min<long long>(workspace_bytes / (32ll * kp * 4), 4096);
+    int S = 0, kpad = 0;
+    const int rc = stem_wgrad_tiles(dz, x, x_is_bf16, N, Cin, D, H, W, stride_d, static_cast<float*>(workspace),
+                                    max_slabs, &S, &kpad, st);
+    if (rc == SSD3D_OK) {
+      const long long total = 32ll * 27 * Cin;
+      SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st,
+                       (const float*)workspace, S, 32ll * kpad, 32, 27 * Cin, kpad, 27 * Cin, dw);
+      return SSD3D_OK;
+    }
+    if (rc != SSD3D_ERR_UNSUPPORTED) return rc;
+  }
   WgradParams p{};
   p.dz = static_cast<const bf16*>(dz); p.ldz = 32; p.M = M;
   p.K = K;

@@ -169,7 +169,11 @@ def test_depthwise_raw_dgrad_wgrad(c, n, size, stride):
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cin,n,size,sd,dtype", [(1, 2, (16, 16, 16), 2, torch.float32), (2, 1, (12, 16, 24), 1, torch.bfloat16),
                                                  (1, 1, (9, 11, 13), 2, torch.float32), (3, 2, (8, 8, 8), 2, torch.float32),
-                                                 (4, 1, (8, 16, 8), 1, torch.bfloat16), (1, 2, (48, 48, 48), 2, torch.float32)])
+                                                 (4, 1, (8, 16, 8), 1, torch.bfloat16), (1, 2, (48, 48, 48), 2, torch.float32),
+                                                 # large enough for the halo-tile kernel (>= 148 tiles of 128 voxels)
+                                                 (2, 2, (40, 44, 48), 1, torch.bfloat16), (3, 2, (33, 50, 56), 2, torch.float32),
+                                                 (4, 3, (32, 48, 40), 2, torch.bfloat16), (1, 3, (31, 45, 72), 1, torch.bfloat16),
+                                                 (2, 1, (64, 64, 64), 2, torch.float32)])
 def test_stem_raw_wgrad(cin, n, size, sd, dtype):
     ops = _ops()
     g = torch.Generator().manual_seed(cin * 7 + sd)
