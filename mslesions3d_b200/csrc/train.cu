@@ -12,6 +12,7 @@
 //   * fused Adam over the flat parameter / gradient buffers (ssd3d.py:704-722)
 // Activations and activation gradients are channels-last bf16; every reduction accumulates in fp32 (fp64
 // for the final cross-block sums) and is bit-reproducible run to run.
+#include <algorithm>
 #include "common.cuh"
 #include "../../include/ssd3d_b200.h"
 
@@ -432,31 +433,185 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
     }
 }
 
-// out[r*dst_ld + c] = sum over splits of partial[s][r*src_ld + c],  c < cols.  32 outputs x 32 split lanes per
-// CTA; lane l adds splits l, l+32, ... in order and the 32 lane sums are combined in order: fixed for a given S.
+// ------------------------------------------------------------------------------------------------
+// Head weight gradient, activation-stationary form.  dW[n][c][tap] = sum_v dO[v][n] * x[v + off(tap)][c] is the
+// same sum over u = v + off(tap):  sum_u x[u][c] * dO[u - off(tap)][n].  So a 64-voxel chunk of x (64 channels)
+// is loaded ONCE and contracted against G[u][j*16 + n] = dO[u - off(kd, j)][n], the 9 (kh, kw) shifts of the
+// 16-column gradient rows (32 bytes each, zero outside the map, L1/L2 resident), instead of gathering the 27
+// shifted activation tiles.  CTA = (64-channel tile, kd, voxel split); cp.async double buffering; warp w owns
+// channels 16w..16w+15 x 144 columns (72 accumulator registers).  Slab layout [split][16][C][27] as before.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct HeadWgradParams {
+  const bf16* dO;             // (M, 16)
+  const bf16* x;              // (M, C) channels-last
+  int N, D, H, W, C;
+  long long M;
+  int chunks_per_split;
+  float* partial;             // [splits][16][C][27]
+};
+
+constexpr int HW_XP = 72;     // sX pitch (elements)
+constexpr int HW_GP = 152;    // sG pitch
+
+__global__ void __launch_bounds__(128, 3) head_wgrad_g_kernel(const HeadWgradParams p) {
+  extern __shared__ __align__(16) uint8_t hw_smem[];
+  bf16* sX = reinterpret_cast<bf16*>(hw_smem);                   // [2][64][HW_XP]
+  bf16* sG = sX + 2 * 64 * HW_XP;                                // [2][64][HW_GP]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c0 = blockIdx.x * 64, kd = blockIdx.y;
+  const long long chunk0 = (long long)blockIdx.z * p.chunks_per_split;
+  const long long n_chunks_all = (p.M + 63) / 64;
+  long long rem = n_chunks_all - chunk0;
+  const int n_chunks = (int)(rem < p.chunks_per_split ? rem : p.chunks_per_split);
+  const uint32_t sX_u = smem_u32(sX), sG_u = smem_u32(sG);
+  const int row = tid >> 1, half = tid & 1;
+
+  pdl_wait();
+  pdl_launch_dependents();
+  auto load_chunk = [&](int ci, int buf) {
+    const long long u0 = (chunk0 + ci) * 64;
+    // activations: 64 rows x 8 chunks of 16 bytes
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = tid + i * 128, r = q >> 3, cc = q & 7;
+      const long long u = u0 + r;
+      const bool ok = u < p.M;
+      cp_async16(sX_u + (uint32_t)(((buf * 64 + r) * HW_XP + cc * 8) * 2), p.x + (ok ? u : 0) * p.C + c0 + cc * 8, ok);
+    }
+    // shifted gradient rows: this thread's voxel, taps half, half+2, ...
+    const long long u = u0 + row;
+    const bool in = u < p.M;
+    long long t = in ? u : 0;
+    const int w = (int)(t % p.W); t /= p.W;
+    const int h = (int)(t % p.H); t /= p.H;
+    const int d = (int)(t % p.D);
+    const int dd = d - (kd - 1);
+    const bool okd = in && dd >= 0 && dd < p.D;
+#pragma unroll
+    for (int jj = 0; jj < 5; ++jj) {
+      const int j = half + 2 * jj;
+      if (j < 9) {
+        const int kh = j / 3, kw = j % 3;
+        const int hh = h - (kh - 1), ww = w - (kw - 1);
+        const bool ok = okd && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
+        const long long v = ok ? u - ((long long)((kd - 1) * p.H + (kh - 1)) * p.W + (kw - 1)) : 0;
+        const uint32_t dst = sG_u + (uint32_t)(((buf * 64 + row) * HW_GP + j * 16) * 2);
+        cp_async16(dst, p.dO + v * 16, ok);
+        cp_async16(dst + 16, p.dO + v * 16 + 8, ok);
+      }
+    }
+  };
+
+  float acc[18][4];
+#pragma unroll
+  for (int b = 0; b < 18; ++b)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[b][c] = 0.f;
+  const int lq = lane >> 3, lr = lane & 7;
+
+  if (n_chunks > 0) load_chunk(0, 0);
+  cp_async_commit();
+  for (int ci = 0; ci < n_chunks; ++ci) {
+    const int buf = ci & 1;
+    if (ci + 1 < n_chunks) load_chunk(ci + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int kk = ks * 16;
+      uint32_t afr[4];        // A = x^T (16 channels x 16 voxels), transposed on load
+      ldsm_x4_t(sX_u + (uint32_t)(((buf * 64 + kk + (lq >> 1) * 8 + lr) * HW_XP + warp * 16 + (lq & 1) * 8) * 2), afr);
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        uint32_t bfr[4];      // B = G (16 voxels x 16 columns of tap j)
+        ldsm_x4_t(sG_u + (uint32_t)(((buf * 64 + kk + (lq & 1) * 8 + lr) * HW_GP + j * 16 + (lq >> 1) * 8) * 2), bfr);
+        mma_bf16(acc[2 * j], afr, bfr[0], bfr[1]);
+        mma_bf16(acc[2 * j + 1], afr, bfr[2], bfr[3]);
+      }
+    }
+    __syncthreads();
+  }
+  // acc[2j + hi][..]: row = channel c0 + 16*warp + lane/4 (+8), column n = hi*8 + (lane&3)*2 (+1) of tap kd*9 + j
+  float* out = p.partial + (size_t)blockIdx.z * 16 * p.C * 27;
+#pragma unroll
+  for (int j = 0; j < 9; ++j)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      const int c = c0 + warp * 16 + (lane >> 2), n = hi * 8 + (lane & 3) * 2, tap = kd * 9 + j;
+      out[((size_t)n * p.C + c) * 27 + tap] = acc[2 * j + hi][0];
+      out[((size_t)(n + 1) * p.C + c) * 27 + tap] = acc[2 * j + hi][1];
+      out[((size_t)n * p.C + c + 8) * 27 + tap] = acc[2 * j + hi][2];
+      out[((size_t)(n + 1) * p.C + c + 8) * 27 + tap] = acc[2 * j + hi][3];
+    }
+}
+
+static int head_wgrad_splits(long long M, int C) {
+  const long long chunks = (M + 63) / 64;
+  const int tiles = (C / 64) * 3;
+  long long s = (444 + tiles - 1) / tiles;
+  if (s > chunks) s = chunks;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+// out[r*dst_ld + c] = sum over splits of partial[s][r*src_ld + c],  c < cols.  1024/LANES outputs x LANES split
+// lanes per CTA; lane l adds splits l, l+LANES, ... in order and the lane sums are combined in order: fixed for a
+// given S.  LANES follows S (few slabs: one thread per output; many: 32 lanes) so that the pass stays a plain
+// coalesced read of the slabs instead of a latency-bound serial loop or a mostly idle CTA.
+template <int LANES>
 __global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restrict__ partial, int S,
                                                            long long slab, int rows, int cols, int src_ld,
                                                            int dst_ld, float* __restrict__ out) {
-  __shared__ float red[FIN_LANES][32];
+  constexpr int OUTS = 1024 / LANES;
+  __shared__ float red[LANES > 1 ? LANES : 1][LANES > 1 ? OUTS : 1];
   pdl_wait();
   pdl_launch_dependents();
-  const int ox = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const long long i = (long long)blockIdx.x * 32 + ox;
+  const int ox = threadIdx.x % OUTS, lane = threadIdx.x / OUTS;
+  const long long i = (long long)blockIdx.x * OUTS + ox;
   const bool valid = i < (long long)rows * cols;
   const int r = valid ? (int)(i / cols) : 0, c = valid ? (int)(i % cols) : 0;
   float s = 0.f;
   if (valid) {
 #pragma unroll 4
-    for (int k = lane; k < S; k += FIN_LANES) s += partial[(size_t)k * slab + (size_t)r * src_ld + c];
+    for (int k = lane; k < S; k += LANES) s += partial[(size_t)k * slab + (size_t)r * src_ld + c];
   }
-  red[lane][ox] = s;
-  __syncthreads();
-  if (lane == 0 && valid) {
-    float t = red[0][ox];
+  if constexpr (LANES == 1) {
+    if (valid) out[(size_t)r * dst_ld + c] = s;
+  } else {
+    red[lane][ox] = s;
+    __syncthreads();
+    if (lane == 0 && valid) {
+      float t = red[0][ox];
 #pragma unroll
-    for (int l = 1; l < FIN_LANES; ++l) t += red[l][ox];
-    out[(size_t)r * dst_ld + c] = t;
+      for (int l = 1; l < LANES; ++l) t += red[l][ox];
+      out[(size_t)r * dst_ld + c] = t;
+    }
   }
+}
+
+static int launch_sum_partials(const float* partial, int S, long long slab, int rows, int cols, int src_ld, int dst_ld,
+                               float* out, cudaStream_t st) {
+  const long long total = (long long)rows * cols;
+  if (S <= 3) {
+    SSD3D_LAUNCH_PDL(sum_partials_kernel<1>, dim3((unsigned)((total + 1023) / 1024)), dim3(1024), 0, st, partial, S, slab,
+                     rows, cols, src_ld, dst_ld, out);
+  } else if (S <= 24) {
+    SSD3D_LAUNCH_PDL(sum_partials_kernel<4>, dim3((unsigned)((total + 255) / 256)), dim3(1024), 0, st, partial, S, slab,
+                     rows, cols, src_ld, dst_ld, out);
+  } else {
+    SSD3D_LAUNCH_PDL(sum_partials_kernel<32>, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st, partial, S, slab,
+                     rows, cols, src_ld, dst_ld, out);
+  }
+  return SSD3D_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -983,7 +1138,12 @@ extern "C" int64_t ssd3d_wgrad_workspace_bytes(int64_t M, int n_out, int K) {
   const int np = n_out <= 16 ? 16 : (n_out <= 32 ? 32 : (n_out + 63) / 64 * 64);
   const int nt = np <= 16 ? 16 : (np <= 32 ? 32 : 64);
   const int S = wgrad_splits(M, (kp / 64) * (np / nt));
-  return (int64_t)S * np * kp * 4;
+  int64_t need = (int64_t)S * np * kp * 4;
+  if (np == 16 && K % (27 * 64) == 0) {     // SSD head: slabs of the activation-stationary kernel
+    const int C = K / 27;
+    need = std::max<int64_t>(need, (int64_t)head_wgrad_splits(M, C) * 16 * 27 * C * 4);
+  }
+  return need;
 }
 
 template <int NT, int MODE, int KT>
@@ -1014,9 +1174,7 @@ extern "C" int ssd3d_pwconv_wgrad(const void* dz, const void* x, int64_t M, int 
   int S = 0;
   const int rc = run_wgrad<64, 0, 64>(p, Cout, st, &S);
   if (rc) return rc;
-  const long long total = (long long)Cout * Cin;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st,
-                   (const float*)p.partial, S, (long long)p.n_pad * p.K, Cout, Cin, p.K, Cin, dw);
+  if (const int rc_s = launch_sum_partials((const float*)p.partial, S, (long long)p.n_pad * p.K, Cout, Cin, p.K, Cin, dw, st)) return rc_s;
   return SSD3D_OK;
 }
 
@@ -1028,6 +1186,26 @@ extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int
   const long long M = (long long)N * D * H * W;
   if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, 16, 27 * C)) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool use_g = [] { const char* e = getenv("SSD3D_HEAD_WGRAD_G"); return !(e && e[0] == '0'); }();
+  if (use_g) {
+    HeadWgradParams q{};
+    q.dO = static_cast<const bf16*>(dO); q.x = static_cast<const bf16*>(x);
+    q.N = N; q.D = D; q.H = H; q.W = W; q.C = C; q.M = M;
+    const long long chunks = (M + 63) / 64;
+    const int S0 = head_wgrad_splits(M, C);
+    q.chunks_per_split = (int)((chunks + S0 - 1) / S0);
+    const int S = (int)((chunks + q.chunks_per_split - 1) / q.chunks_per_split);
+    q.partial = static_cast<float*>(workspace);
+    const size_t smem = (size_t)2 * 64 * (HW_XP + HW_GP) * 2;
+    cudaError_t e = cudaFuncSetAttribute(head_wgrad_g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    SSD3D_LAUNCH_PDL(head_wgrad_g_kernel, dim3((unsigned)(C / 64), 3u, (unsigned)S), dim3(128), smem, st, q);
+    const long long slab = 16ll * 27 * C;
+    if (const int rc_s = launch_sum_partials(q.partial, S, slab, 1, n_loc * 27 * C, n_loc * 27 * C, n_loc * 27 * C, dw_loc, st)) return rc_s;
+    if (const int rc_s = launch_sum_partials(q.partial + (size_t)n_loc * 27 * C, S, slab, 1, n_cls * 27 * C, n_cls * 27 * C, n_cls * 27 * C,
+                        dw_cls, st)) return rc_s;
+    return SSD3D_OK;
+  }
   WgradParams p{};
   p.dz = static_cast<const bf16*>(dO); p.ldz = 16; p.M = M;
   p.K = 27 * C;
@@ -1038,11 +1216,9 @@ extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int
   if (rc) return rc;
   // slabs are [16][C][27] = the layout of the two conv weights stacked: two contiguous fixed-order sums
   const long long slab = 16ll * 27 * C;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)(((long long)n_loc * 27 * C + 31) / 32)), dim3(1024), 0, st,
-                   (const float*)p.partial, S, slab, 1, n_loc * 27 * C, n_loc * 27 * C, n_loc * 27 * C, dw_loc);
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)(((long long)n_cls * 27 * C + 31) / 32)), dim3(1024), 0, st,
-                   (const float*)(p.partial + (size_t)n_loc * 27 * C), S, slab, 1, n_cls * 27 * C, n_cls * 27 * C,
-                   n_cls * 27 * C, dw_cls);
+  if (const int rc_s = launch_sum_partials((const float*)p.partial, S, slab, 1, n_loc * 27 * C, n_loc * 27 * C, n_loc * 27 * C, dw_loc, st)) return rc_s;
+  if (const int rc_s = launch_sum_partials((const float*)(p.partial + (size_t)n_loc * 27 * C), S, slab, 1, n_cls * 27 * C, n_cls * 27 * C,
+                   n_cls * 27 * C, dw_cls, st)) return rc_s;
   return SSD3D_OK;
 }
 
@@ -1069,9 +1245,7 @@ extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, in
     const int rc = stem_wgrad_tiles(dz, x, x_is_bf16, N, Cin, D, H, W, stride_d, static_cast<float*>(workspace),
                                     max_slabs, &S, &kpad, st);
     if (rc == SSD3D_OK) {
-      const long long total = 32ll * 27 * Cin;
-      SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st,
-                       (const float*)workspace, S, 32ll * kpad, 32, 27 * Cin, kpad, 27 * Cin, dw);
+      if (const int rc_s = launch_sum_partials((const float*)workspace, S, 32ll * kpad, 32, 27 * Cin, kpad, 27 * Cin, dw, st)) return rc_s;
       return SSD3D_OK;
     }
     if (rc != SSD3D_ERR_UNSUPPORTED) return rc;
@@ -1085,9 +1259,7 @@ extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, in
   int S = 0;
   const int rc = (K == 32) ? run_wgrad<32, 2, 32>(p, 32, st, &S) : run_wgrad<32, 2, 64>(p, 32, st, &S);
   if (rc) return rc;
-  const long long total = 32ll * 27 * Cin;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st,
-                   (const float*)p.partial, S, (long long)p.n_pad * p.K, 32, 27 * Cin, p.K, 27 * Cin, dw);
+  if (const int rc_s = launch_sum_partials((const float*)p.partial, S, (long long)p.n_pad * p.K, 32, 27 * Cin, p.K, 27 * Cin, dw, st)) return rc_s;
   return SSD3D_OK;
 }
 
@@ -1110,10 +1282,10 @@ extern "C" int ssd3d_head_grad_pack(const float* dlocs, const float* dscores, in
   SSD3D_LAUNCH_PDL(head_grad_pack_kernel, dim3(blocks), dim3(256), 0, st, dlocs, dscores, (long long)P,
                    (long long)prior_offset, V, N, bpl, n_classes, static_cast<bf16*>(dO), partial);
   // column sums: partial is [blocks][16] -> rows = 1, cols = 16 with slab = 16
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3(1), dim3(1024), 0, st, (const float*)partial, blocks, 16ll, 1, bpl * 6, 16,
-                   bpl * 6, dbias_loc);
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3(1), dim3(1024), 0, st, (const float*)(partial + bpl * 6), blocks, 16ll, 1,
-                   bpl * n_classes, 16, bpl * n_classes, dbias_cls);
+  if (const int rc_s = launch_sum_partials((const float*)partial, blocks, 16ll, 1, bpl * 6, 16,
+                   bpl * 6, dbias_loc, st)) return rc_s;
+  if (const int rc_s = launch_sum_partials((const float*)(partial + bpl * 6), blocks, 16ll, 1,
+                   bpl * n_classes, 16, bpl * n_classes, dbias_cls, st)) return rc_s;
   return SSD3D_OK;
 }
 
@@ -1187,11 +1359,8 @@ extern "C" int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C,
     const int rc = ssd3d_dwconv3d_wgrad_tma(dz, x, N, C, D, H, W, stride, static_cast<float*>(workspace), 592, &slabs,
                                             static_cast<cudaStream_t>(stream));
     if (rc == SSD3D_OK) {
-      const long long total = (long long)C * 27;
-      SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0,
-                       static_cast<cudaStream_t>(stream), (const float*)workspace, slabs, (long long)C * 27, C, 27, 27,
-                       27, dw);
-      return SSD3D_OK;
+      return launch_sum_partials((const float*)workspace, slabs, (long long)C * 27, C, 27, 27, 27, dw,
+                                 static_cast<cudaStream_t>(stream));
     }
     if (rc != SSD3D_ERR_UNSUPPORTED) return rc;
   }
@@ -1210,9 +1379,8 @@ extern "C" int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C,
   else
     SSD3D_LAUNCH_PDL(dw_wgrad_kernel<2>, dim3(B), dim3(threads), 0, st, gp, xp, N, C, D, H, W, Do, Ho, Wo, Mo, vpb, G,
                      partial);
-  const long long total = (long long)C * 27;
-  SSD3D_LAUNCH_PDL(sum_partials_kernel, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st, (const float*)partial,
-                   B, (long long)C * 27, C, 27, 27, 27, dw);
+  if (const int rc_s = launch_sum_partials((const float*)partial,
+                   B, (long long)C * 27, C, 27, 27, 27, dw, st)) return rc_s;
   return SSD3D_OK;
 }
 
