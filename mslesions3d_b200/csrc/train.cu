@@ -73,15 +73,16 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const bf16* __restrict__
   }
   const long long m_begin = (long long)blockIdx.x * rows_per_block;
   const long long m_end = (m_begin + rows_per_block < M) ? m_begin + rows_per_block : M;
-  for (long long m = m_begin + r; m < m_end; m += RP) {
+  // four rows in flight per thread (all loads first): the pass is latency-bound with one
+  auto add_row = [&](const uint4& zu, const uint4& gu) {
     float zf[8];
-    unpack8f(ld_nc16(z + m * C + c0), zf);
+    unpack8f(zu, zf);
     if (MODE == 0) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s0[j] += zf[j]; s1[j] = fmaf(zf[j], zf[j], s1[j]); }
     } else {
       float gf[8];
-      unpack8f(ld_nc16(g + m * C + c0), gf);
+      unpack8f(gu, gf);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float pre = __fadd_rn(__fmul_rn(zf[j], sc[j]), sh[j]);
@@ -91,6 +92,22 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const bf16* __restrict__
         s1[j] = fmaf(dy, xh, s1[j]);
       }
     }
+  };
+  long long m = m_begin + r;
+  for (; m + 3ll * RP < m_end; m += 4ll * RP) {
+    uint4 zu[4], gu[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zu[i] = ld_nc16(z + (m + (long long)i * RP) * C + c0);
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gu[i] = ld_nc16(g + (m + (long long)i * RP) * C + c0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) add_row(zu[i], MODE == 1 ? gu[i] : zu[i]);
+  }
+  for (; m < m_end; m += RP) {
+    const uint4 zu = ld_nc16(z + m * C + c0);
+    add_row(zu, MODE == 1 ? ld_nc16(g + m * C + c0) : zu);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s0[j]; red[threadIdx.x * 16 + 8 + j] = s1[j]; }
@@ -217,22 +234,49 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const bf16* __re
                                                                 bf16* dz, long long total_vec, int CV) {
   pdl_wait();
   pdl_launch_dependents();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % CV) << 3;
-    float zf[8], gf[8], sc[8], sh[8], mu[8], is[8], dg[8], db[8], o[8];
-    unpack8f(ld_nc16(z + i * 8), zf);
-    unpack8f(*reinterpret_cast<const uint4*>(g + i * 8), gf);
+  // the grid stride is a multiple of CV for every channel count of the network (powers of two): a thread keeps its
+  // channels, so the per-channel constants are loaded once; two vectors in flight per iteration
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool fixed = (stride % CV) == 0;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // dz = sc*(dy - dbeta/M - xhat*dgamma/M) with xhat = (z - mu)*invstd, regrouped as sc*dy + A + z*B
+  float sc[8], sh[8], ka[8], kb[8];
+  auto load_consts = [&](long long idx) {
+    const int c0 = (int)(idx % CV) << 3;
+    float mu[8], is[8], dg[8], db[8];
     load8(scale + c0, sc); load8(shift + c0, sh); load8(mean + c0, mu); load8(invstd + c0, is);
     load8(dgamma + c0, dg); load8(dbeta + c0, db);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      const float t = sc[j] * is[j] * dg[j] * inv_m;
+      kb[j] = -t;
+      ka[j] = fmaf(mu[j], t, -(sc[j] * db[j] * inv_m));
+    }
+  };
+  auto apply = [&](long long idx, const uint4& zu, const uint4& gu) {
+    float zf[8], gf[8], o[8];
+    unpack8f(zu, zf);
+    unpack8f(gu, gf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
       const float pre = __fadd_rn(__fmul_rn(zf[j], sc[j]), sh[j]);
       const float dy = (pre > 0.f) ? gf[j] : 0.f;
-      const float xh = (zf[j] - mu[j]) * is[j];
-      o[j] = sc[j] * (dy - db[j] * inv_m - xh * (dg[j] * inv_m));
+      o[j] = fmaf(zf[j], kb[j], fmaf(sc[j], dy, ka[j]));
     }
-    *reinterpret_cast<uint4*>(dz + i * 8) = pack8f(o);
+    *reinterpret_cast<uint4*>(dz + idx * 8) = pack8f(o);
+  };
+  if (i < total_vec) load_consts(i);
+  if (fixed) {
+    for (; i + stride < total_vec; i += 2 * stride) {
+      const uint4 z0 = ld_nc16(z + i * 8), z1 = ld_nc16(z + (i + stride) * 8);
+      const uint4 g0 = *reinterpret_cast<const uint4*>(g + i * 8), g1 = *reinterpret_cast<const uint4*>(g + (i + stride) * 8);
+      apply(i, z0, g0);
+      apply(i + stride, z1, g1);
+    }
+  }
+  for (; i < total_vec; i += stride) {
+    if (!fixed) load_consts(i);
+    apply(i, ld_nc16(z + i * 8), *reinterpret_cast<const uint4*>(g + i * 8));
   }
 }
 
@@ -906,6 +950,93 @@ __global__ void __launch_bounds__(256) dw_dgrad_s2_kernel(const bf16* __restrict
   }
 }
 
+// Stride-2 data gradient by OUTPUT BLOCK (maps with C <= 256).  A thread produces 8 channels of the 2x2x2 block of
+// dx voxels (2m + p), p in {0,1}^3, from the 2x2x2 block of gradient voxels (m + a): per axis p = 0 takes tap 1
+// from a = 0, p = 1 takes tap 2 from a = 0 and tap 0 from a = 1 -- all 27 taps once, 8 gradient loads of 16 bytes
+// and 8 stores of 16 bytes per 64 gradient elements, and a warp writes whole 128-byte lines (both W parities back
+// to back) where the per-class kernel wrote every line in two far-apart halves.  Weights sit in shared memory as
+// fp32 (two LDS.128 per tap), the products are packed FFMA2.
+__global__ void __launch_bounds__(256) dw_dgrad_s2_block_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ w,
+                                                                bf16* __restrict__ dx, int N, int C, int D, int H, int W,
+                                                                int Do, int Ho, int Wo, int Md, int Mh, int Mw,
+                                                                long long total) {
+  extern __shared__ __align__(16) float dg_sw[];       // [27][C]
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < 27 * C; i += 256) dg_sw[i] = __bfloat162float(w[i]);
+  __syncthreads();
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (gid >= total) return;
+  const int CV = C >> 3;
+  const int cv = (int)(gid % CV);
+  long long r = gid / CV;
+  const int mw = (int)(r % Mw); r /= Mw;
+  const int mh = (int)(r % Mh); r /= Mh;
+  const int md = (int)(r % Md);
+  const int n = (int)(r / Md);
+  const int c0 = cv << 3;
+  f32x2_t acc[8][4];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[p][q] = 0ull;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int od = md + a;
+    if (od >= Do) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int oh = mh + b;
+      if (oh >= Ho) continue;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int ow = mw + c;
+        if (ow >= Wo) continue;
+        const uint4 u = ld_nc16(dz + ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * C + c0);
+        const f32x2_t g[4] = {tr_bf16x2_to_f32x2(u.x), tr_bf16x2_to_f32x2(u.y), tr_bf16x2_to_f32x2(u.z),
+                              tr_bf16x2_to_f32x2(u.w)};
+#pragma unroll
+        for (int pd = a; pd < 2; ++pd) {               // a = 1 only feeds odd coordinates
+          const int kd = pd == 0 ? 1 : (a == 0 ? 2 : 0);
+#pragma unroll
+          for (int ph = b; ph < 2; ++ph) {
+            const int kh = ph == 0 ? 1 : (b == 0 ? 2 : 0);
+#pragma unroll
+            for (int pw = c; pw < 2; ++pw) {
+              const int kw = pw == 0 ? 1 : (c == 0 ? 2 : 0);
+              const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(dg_sw + ((kd * 3 + kh) * 3 + kw) * C + c0);
+              const ulonglong2 w01 = wp[0], w23 = wp[1];
+              f32x2_t(&o)[4] = acc[(pd * 2 + ph) * 2 + pw];
+              tr_ffma2(o[0], g[0], w01.x);
+              tr_ffma2(o[1], g[1], w01.y);
+              tr_ffma2(o[2], g[2], w23.x);
+              tr_ffma2(o[3], g[3], w23.y);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int pd = 0; pd < 2; ++pd) {
+    const int di = 2 * md + pd;
+    if (di >= D) continue;
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+      const int hi = 2 * mh + ph;
+      if (hi >= H) continue;
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        const int wi = 2 * mw + pw;
+        if (wi >= W) continue;
+        const f32x2_t(&o)[4] = acc[(pd * 2 + ph) * 2 + pw];
+        *reinterpret_cast<uint4*>(dx + ((((long long)n * D + di) * H + hi) * W + wi) * C + c0) =
+            make_uint4(tr_pack_bf16x2(o[0]), tr_pack_bf16x2(o[1]), tr_pack_bf16x2(o[2]), tr_pack_bf16x2(o[3]));
+      }
+    }
+  }
+}
+
 // weight: dw[c][k] = sum_o dz[o][c] * x[S*o + k - 1][c].  thread = (8 channels, kd, voxel lane g): 9 taps x 8
 // channels of accumulators; block partial [C][27] after a fixed-order reduction over the voxel lanes.
 template <int S>
@@ -1319,6 +1450,11 @@ extern "C" int ssd3d_dwconv3d_dgrad(const void* dz, const void* w, void* dx, int
   if (stride == 1) {
     SSD3D_LAUNCH_PDL(dw_dgrad_kernel<1>, dim3(blocks), dim3(256), 0, st, gp, wp, static_cast<bf16*>(dx), N, C, D, H, W,
                      Do, Ho, Wo, total);
+  } else if (C <= 256 && !(getenv("SSD3D_DW_DGRAD_BLOCK") && getenv("SSD3D_DW_DGRAD_BLOCK")[0] == '0')) {
+    const int Md = (D + 1) / 2, Mh = (H + 1) / 2, Mw = (W + 1) / 2;
+    const long long tot = (long long)N * Md * Mh * Mw * (C / 8);
+    SSD3D_LAUNCH_PDL(dw_dgrad_s2_block_kernel, dim3((unsigned)((tot + 255) / 256)), dim3(256), (size_t)27 * C * 4, st, gp,
+                     wp, static_cast<bf16*>(dx), N, C, D, H, W, Do, Ho, Wo, Md, Mh, Mw, tot);
   } else {
     // one block row per parity class; the largest class (all coordinates even) sizes the grid
     const long long biggest = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * (((W + 1) / 2 + 3) / 4) * (C / 4);
