@@ -206,19 +206,39 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(const bf16* __restri
   pdl_wait();
   pdl_launch_dependents();
   bool bad = false;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % CV) << 3;
-    float zf[8], sc[8], sh[8], o[8];
-    unpack8f(ld_nc16(z + i * 8), zf);
+  // the grid stride is a multiple of CV for power-of-two channel counts: scale/shift are loaded once per thread
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool fixed = (stride % CV) == 0;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float sc[8], sh[8];
+  auto load_consts = [&](long long idx) {
+    const int c0 = (int)(idx % CV) << 3;
     load8(scale + c0, sc);
     load8(shift + c0, sh);
+  };
+  auto apply = [&](long long idx, const uint4& zu) {
+    float zf[8], o[8];
+    unpack8f(zu, zf);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       o[j] = relu_nan(__fadd_rn(__fmul_rn(zf[j], sc[j]), sh[j]));
       bad |= (o[j] != o[j]);
     }
-    *reinterpret_cast<uint4*>(a + i * 8) = pack8f(o);
+    *reinterpret_cast<uint4*>(a + idx * 8) = pack8f(o);
+  };
+  if (i < total_vec) load_consts(i);
+  if (fixed) {
+    for (; i + 3 * stride < total_vec; i += 4 * stride) {
+      uint4 zu[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) zu[k] = ld_nc16(z + (i + k * stride) * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) apply(i + k * stride, zu[k]);
+    }
+  }
+  for (; i < total_vec; i += stride) {
+    if (!fixed) load_consts(i);
+    apply(i, ld_nc16(z + i * 8));
   }
   if (bad && nan_flag) atomicOr(nan_flag, SSD3D_NAN_BACKBONE);
 }
@@ -1470,7 +1490,8 @@ static int dw_wgrad_plan(long long Mo, int C, int* threads, int* G, long long* v
   if (C <= 0 || (C & 7) || CV * 3 > 256) return -1;
   *G = 256 / (CV * 3);
   *threads = CV * 3 * (*G);
-  long long B = (Mo + (*G) * 8 - 1) / ((*G) * 8);
+  static const int vpl = [] { const char* e = getenv("SSD3D_DW_WGRAD_VPL"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : v; }();
+  long long B = (Mo + (*G) * vpl - 1) / ((*G) * vpl);       // >= vpl voxels per voxel lane
   if (B > 592) B = 592;
   if (B < 1) B = 1;
   *vpb = (Mo + B - 1) / B;
