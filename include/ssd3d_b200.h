@@ -307,6 +307,23 @@ int64_t ssd3d_normalize_workspace_bytes(int items);
 int ssd3d_normalize_intensity_nonzero(const float* x, int items, int64_t voxels, void* y, int y_is_bf16,
                                       void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Ground-truth boxes from segmentation volumes (utils.py:438-513 BoundingBoxesGeneratord,
+ * segmentation_mode "binary" (n_classes = 0: every non-zero voxel, label 1) or "classes" (n_classes >= 1: voxels
+ * equal to c in 1..n_classes, label c; classes = [1..n_classes] as datasets.py:405 passes them)).
+ * seg: (N, D, H, W) uint8 (seg_dtype 0) or fp32 (seg_dtype 1).  Per volume: face-connected components
+ * (scipy.ndimage.label's default structure) per class, one box [min d, min h, min w, max d, max h, max w] /
+ * [D, H, W, D, H, W] (inclusive max index, fp32 division) per component, in the reference's order: class
+ * ascending, then the component's first voxel in C order; components one voxel thick along an axis have zero
+ * volume and are dropped (utils.py:475-480).
+ *   boxes (N, max_boxes, 6) fp32, labels (N, max_boxes) int64: rows [0, counts[n]) are valid
+ *   n_components (N): components found before the zero-volume filter; a value > max_boxes means the lists
+ *   were truncated and must not be used.  (The reference's c*1000 instance ids cap a class at 999 components.)
+ * ---------------------------------------------------------------------------------------------- */
+int64_t ssd3d_gt_boxes_workspace_bytes(int N, int D, int H, int W, int max_boxes);
+int ssd3d_gt_boxes_from_segmentation(const void* seg, int seg_dtype, int N, int D, int H, int W, int n_classes,
+                                     int max_boxes, float* boxes, int64_t* labels, int32_t* counts,
+                                     int32_t* n_components, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,3 +101,251 @@ extern "C" int ssd3d_normalize_intensity_nonzero(const float* x, int items, int6
   SSD3D_CHECK_LAUNCH();
   return SSD3D_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Ground-truth boxes from a segmentation volume (utils.py:438-513, BoundingBoxesGeneratord "binary" / "classes"):
+// face-connected components (scipy.ndimage.label, default structure) of each class, one box
+// [min index, max index] / image size per component, ordered by (class, first voxel in C order) = scipy's label
+// order; components that are one voxel thick along an axis have zero volume and are dropped (utils.py:475-480).
+//   init     L[v] = v for class voxels, -1 otherwise                      (one volume-local int per voxel)
+//   merge    lock-free union-find with atomicMin towards the smaller index over the -w/-h/-d neighbours
+//   compress L[v] = root(v); roots append their key class*V + v to the volume's list
+//   rank     rank by counting over the (distinct) keys -> R[root] = position in the reference's order
+//   bbox     per voxel min/max into box[rank], one atomic set per (warp, component) via match_any + redux
+//   finalize divide by the image size (fp32, round to nearest as torch), zero-volume filter, ordered compaction
+// ------------------------------------------------------------------------------------------------
+namespace ssd3d {
+
+template <typename T>
+__device__ __forceinline__ int seg_class(const T* __restrict__ seg, long long i, int n_classes) {
+  const T v = seg[i];
+  if (n_classes <= 0) return v != (T)0 ? 1 : 0;           // binary
+  const int c = (int)v;
+  return ((T)c == v && c >= 1 && c <= n_classes) ? c : 0;
+}
+
+__device__ __forceinline__ int cc_find(const int* L, int x) {
+  int p = L[x];
+  while (p != x) { x = p; p = L[x]; }
+  return x;
+}
+
+__device__ __forceinline__ void cc_unite(int* L, int a, int b) {
+  bool done = false;
+  while (!done) {
+    a = cc_find(L, a);
+    b = cc_find(L, b);
+    if (a < b) { const int old = atomicMin(&L[b], a); done = (old == b); b = old; }
+    else if (b < a) { const int old = atomicMin(&L[a], b); done = (old == a); a = old; }
+    else done = true;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cc_init_kernel(const T* __restrict__ seg, long long total, long long V,
+                                                      int n_classes, int* __restrict__ L) {
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (g >= total) return;
+  L[g] = seg_class(seg, g, n_classes) ? (int)(g % V) : -1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cc_merge_kernel(const T* __restrict__ seg, long long total, int D, int H, int W,
+                                                       int n_classes, int* __restrict__ L) {
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (g >= total) return;
+  const int c = seg_class(seg, g, n_classes);
+  if (!c) return;
+  const long long V = (long long)D * H * W;
+  const int v = (int)(g % V);
+  int* Lv = L + (g - v);
+  const T* sv = seg + (g - v);
+  const int w = v % W, h = (v / W) % H, d = v / (W * H);
+  if (w > 0 && seg_class(sv, v - 1, n_classes) == c) cc_unite(Lv, v, v - 1);
+  if (h > 0 && seg_class(sv, v - W, n_classes) == c) cc_unite(Lv, v, v - W);
+  if (d > 0 && seg_class(sv, v - W * H, n_classes) == c) cc_unite(Lv, v, v - W * H);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cc_compress_kernel(const T* __restrict__ seg, long long total, long long V,
+                                                          int n_classes, int max_boxes, int* __restrict__ L,
+                                                          int* __restrict__ R, long long* __restrict__ root_key,
+                                                          int* __restrict__ root_count) {
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (g >= total) return;
+  const int c = seg_class(seg, g, n_classes);
+  if (!c) return;
+  const int v = (int)(g % V);
+  const int n = (int)(g / V);
+  int* Lv = L + (g - v);
+  const int r = cc_find(Lv, v);
+  Lv[v] = r;
+  if (r == v) {
+    R[g] = -1;
+    const int slot = atomicAdd(&root_count[n], 1);
+    if (slot < max_boxes) root_key[(long long)n * max_boxes + slot] = (long long)c * V + v;
+  }
+}
+
+__global__ void __launch_bounds__(256) cc_rank_kernel(const long long* __restrict__ root_key,
+                                                      const int* __restrict__ root_count, long long V, int max_boxes,
+                                                      int* __restrict__ R, int* __restrict__ ibox,
+                                                      int* __restrict__ cls_of_rank) {
+  const int n = blockIdx.y;
+  const int cnt = min(root_count[n], max_boxes);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= cnt) return;
+  const long long* keys = root_key + (long long)n * max_boxes;
+  const long long k = keys[i];
+  int rank = 0;
+  for (int j = 0; j < cnt; ++j) rank += (keys[j] < k) ? 1 : 0;
+  R[(long long)n * V + (k % V)] = rank;
+  cls_of_rank[n * max_boxes + rank] = (int)(k / V);
+  int* b = ibox + ((long long)n * max_boxes + rank) * 6;
+  b[0] = b[1] = b[2] = 0x7fffffff;
+  b[3] = b[4] = b[5] = -1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cc_bbox_kernel(const T* __restrict__ seg, long long total, int D, int H, int W,
+                                                      int n_classes, int max_boxes, const int* __restrict__ L,
+                                                      const int* __restrict__ R, int* __restrict__ ibox) {
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long V = (long long)D * H * W;
+  int key = -1, d = 0, h = 0, w = 0;
+  if (g < total && seg_class(seg, g, n_classes)) {
+    const int v = (int)(g % V);
+    const int n = (int)(g / V);
+    const int rank = R[(g - v) + L[g]];
+    if (rank >= 0) key = n * max_boxes + rank;
+    w = v % W; h = (v / W) % H; d = v / (W * H);
+  }
+  const unsigned active = __ballot_sync(0xffffffffu, key >= 0);
+  if (key < 0) return;
+  const unsigned grp = __match_any_sync(active, key);
+  const int lo_d = __reduce_min_sync(grp, d), lo_h = __reduce_min_sync(grp, h), lo_w = __reduce_min_sync(grp, w);
+  const int hi_d = __reduce_max_sync(grp, d), hi_h = __reduce_max_sync(grp, h), hi_w = __reduce_max_sync(grp, w);
+  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) {
+    int* b = ibox + (long long)key * 6;
+    atomicMin(b + 0, lo_d); atomicMin(b + 1, lo_h); atomicMin(b + 2, lo_w);
+    atomicMax(b + 3, hi_d); atomicMax(b + 4, hi_h); atomicMax(b + 5, hi_w);
+  }
+}
+
+__global__ void __launch_bounds__(256) cc_finalize_kernel(const int* __restrict__ ibox,
+                                                          const int* __restrict__ cls_of_rank,
+                                                          const int* __restrict__ root_count, int D, int H, int W,
+                                                          int max_boxes, float* __restrict__ boxes,
+                                                          long long* __restrict__ labels, int* __restrict__ counts,
+                                                          int* __restrict__ n_components) {
+  __shared__ int warp_tot[8];
+  __shared__ int base;
+  const int n = blockIdx.x;
+  const int total = root_count[n];
+  const int cnt = min(total, max_boxes);
+  if (threadIdx.x == 0) { base = 0; n_components[n] = total; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r0 = 0; r0 < cnt; r0 += 256) {
+    const int r = r0 + threadIdx.x;
+    int b[6] = {0, 0, 0, 0, 0, 0};
+    bool keep = false;
+    if (r < cnt) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) b[j] = ibox[((long long)n * max_boxes + r) * 6 + j];
+      keep = b[3] > b[0] && b[4] > b[1] && b[5] > b[2];      // zero volume <=> one voxel thick along an axis
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int q = 0; q < warp; ++q) off += warp_tot[q];
+    off += __popc(m & ((1u << lane) - 1u));
+    if (keep) {
+      float* o = boxes + ((long long)n * max_boxes + off) * 6;
+      const float dims[3] = {(float)D, (float)H, (float)W};
+#pragma unroll
+      for (int j = 0; j < 6; ++j) o[j] = __fdiv_rn((float)b[j], dims[j % 3]);
+      labels[(long long)n * max_boxes + off] = cls_of_rank[n * max_boxes + r];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; ++q) t += warp_tot[q]; base += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[n] = base;
+}
+
+struct CcWs {
+  int* L; int* R; long long* root_key; int* root_count; int* ibox; int* cls_of_rank;
+};
+
+static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static CcWs cc_carve(void* ws, int N, long long V, int max_boxes) {
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  CcWs c;
+  c.L = reinterpret_cast<int*>(p); p += al256((size_t)N * V * 4);
+  c.R = reinterpret_cast<int*>(p); p += al256((size_t)N * V * 4);
+  c.root_key = reinterpret_cast<long long*>(p); p += al256((size_t)N * max_boxes * 8);
+  c.root_count = reinterpret_cast<int*>(p); p += al256((size_t)N * 4);
+  c.ibox = reinterpret_cast<int*>(p); p += al256((size_t)N * max_boxes * 6 * 4);
+  c.cls_of_rank = reinterpret_cast<int*>(p);
+  return c;
+}
+
+template <typename T>
+static int run_gt_boxes(const T* seg, int N, int D, int H, int W, int n_classes, int max_boxes, float* boxes,
+                        long long* labels, int* counts, int* n_components, void* ws, cudaStream_t st) {
+  const long long V = (long long)D * H * W, total = V * N;
+  CcWs c = cc_carve(ws, N, V, max_boxes);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaError_t e = cudaMemsetAsync(c.root_count, 0, (size_t)N * 4, st);
+  if (e != cudaSuccess) return (int)e;
+  cc_init_kernel<T><<<blocks, 256, 0, st>>>(seg, total, V, n_classes, c.L);
+  SSD3D_CHECK_LAUNCH();
+  cc_merge_kernel<T><<<blocks, 256, 0, st>>>(seg, total, D, H, W, n_classes, c.L);
+  SSD3D_CHECK_LAUNCH();
+  cc_compress_kernel<T><<<blocks, 256, 0, st>>>(seg, total, V, n_classes, max_boxes, c.L, c.R, c.root_key, c.root_count);
+  SSD3D_CHECK_LAUNCH();
+  cc_rank_kernel<<<dim3((unsigned)((max_boxes + 255) / 256), (unsigned)N), 256, 0, st>>>(c.root_key, c.root_count, V,
+                                                                                         max_boxes, c.R, c.ibox,
+                                                                                         c.cls_of_rank);
+  SSD3D_CHECK_LAUNCH();
+  cc_bbox_kernel<T><<<blocks, 256, 0, st>>>(seg, total, D, H, W, n_classes, max_boxes, c.L, c.R, c.ibox);
+  SSD3D_CHECK_LAUNCH();
+  cc_finalize_kernel<<<(unsigned)N, 256, 0, st>>>(c.ibox, c.cls_of_rank, c.root_count, D, H, W, max_boxes, boxes, labels,
+                                                  counts, n_components);
+  SSD3D_CHECK_LAUNCH();
+  return SSD3D_OK;
+}
+
+}  // namespace ssd3d
+
+extern "C" int64_t ssd3d_gt_boxes_workspace_bytes(int N, int D, int H, int W, int max_boxes) {
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || max_boxes <= 0) return 0;
+  const long long V = (long long)D * H * W;
+  return (int64_t)(2 * ssd3d::al256((size_t)N * V * 4) + ssd3d::al256((size_t)N * max_boxes * 8) +
+                   ssd3d::al256((size_t)N * 4) + ssd3d::al256((size_t)N * max_boxes * 24) +
+                   ssd3d::al256((size_t)N * max_boxes * 4));
+}
+
+extern "C" int ssd3d_gt_boxes_from_segmentation(const void* seg, int seg_dtype, int N, int D, int H, int W,
+                                                int n_classes, int max_boxes, float* boxes, int64_t* labels,
+                                                int32_t* counts, int32_t* n_components, void* workspace,
+                                                int64_t workspace_bytes, void* stream) {
+  if (!seg || !boxes || !labels || !counts || !n_components || !workspace) return SSD3D_ERR_ARG;
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || max_boxes <= 0 || n_classes < 0) return SSD3D_ERR_ARG;
+  const long long V = (long long)D * H * W;
+  if (V >= (1ll << 31)) return SSD3D_ERR_UNSUPPORTED;      // volume-local voxel indices are 32-bit
+  if ((long long)N * max_boxes >= (1ll << 31)) return SSD3D_ERR_UNSUPPORTED;
+  if (workspace_bytes < ssd3d_gt_boxes_workspace_bytes(N, D, H, W, max_boxes)) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long* lab = reinterpret_cast<long long*>(labels);
+  if (seg_dtype == 0)
+    return ssd3d::run_gt_boxes<uint8_t>(static_cast<const uint8_t*>(seg), N, D, H, W, n_classes, max_boxes, boxes, lab,
+                                        counts, n_components, workspace, st);
+  if (seg_dtype == 1)
+    return ssd3d::run_gt_boxes<float>(static_cast<const float*>(seg), N, D, H, W, n_classes, max_boxes, boxes, lab, counts,
+                                      n_components, workspace, st);
+  return SSD3D_ERR_ARG;
+}

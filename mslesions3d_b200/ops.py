@@ -409,9 +409,12 @@ def _ones_zeros(n: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
     return cur
 
 
-def _workspace(nbytes: int, device, slot: str = "ws") -> torch.Tensor:
+_WS_SLOT = ["ws"]      # scratch slot of the stream being issued to (training.py switches it for its side stream)
+
+
+def _workspace(nbytes: int, device, slot: Optional[str] = None) -> torch.Tensor:
     """Grow-only scratch buffer per (device, slot); kernels of one stream use it strictly in order."""
-    key = (str(device), slot)
+    key = (str(device), slot or _WS_SLOT[0])
     cur = _CONST.get(key)
     if cur is None or cur.numel() < nbytes:
         cur = torch.empty((max(int(nbytes), 1 << 20),), dtype=torch.uint8, device=device)
@@ -677,3 +680,36 @@ def normalize_intensity_nonzero(x: torch.Tensor, out_dtype: torch.dtype = BF16) 
     _lib.check(rc, "ssd3d_normalize_intensity_nonzero")
     LAUNCHES[0] += 3
     return y
+
+
+def gt_boxes_from_segmentation(seg: torch.Tensor, n_classes: int = 0, max_boxes: int = 1024):
+    """Ground-truth boxes of segmentation volumes on the device (utils.py:438-513 ``BoundingBoxesGeneratord``,
+    "binary" mode for ``n_classes == 0``, "classes" mode with ``classes = [1..n_classes]`` otherwise).
+    seg (N, D, H, W) or (N, 1, D, H, W), uint8 or floating -> (boxes list[(n_i, 6) fp32], labels list[(n_i,) int64]),
+    fractional [min, max] index boxes in array-axis order, the reference's order and zero-volume filter."""
+    _need_cuda(seg)
+    if seg.dim() == 5 and seg.shape[1] == 1:
+        seg = seg[:, 0]
+    if seg.dim() != 4:
+        raise RuntimeError("expected (N, D, H, W) or (N, 1, D, H, W) segmentations")
+    if seg.dtype == torch.uint8:
+        dt = 0
+    else:
+        seg, dt = seg.float(), 1
+    seg = seg.contiguous()
+    n, d, h, w = seg.shape
+    dev = seg.device
+    boxes = torch.empty((n, max_boxes, 6), dtype=torch.float32, device=dev)
+    labels = torch.empty((n, max_boxes), dtype=torch.int64, device=dev)
+    meta = torch.empty((2, n), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    ws = torch.empty((lib.ssd3d_gt_boxes_workspace_bytes(n, d, h, w, max_boxes),), dtype=torch.uint8, device=dev)
+    rc = lib.ssd3d_gt_boxes_from_segmentation(seg.data_ptr(), dt, n, d, h, w, int(n_classes), int(max_boxes),
+                                              boxes.data_ptr(), labels.data_ptr(), meta[0].data_ptr(),
+                                              meta[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_gt_boxes_from_segmentation")
+    LAUNCHES[0] += 6
+    counts, comps = meta.cpu().tolist()
+    if max(comps) > max_boxes:
+        raise RuntimeError("segmentation has %d connected components, max_boxes=%d" % (max(comps), max_boxes))
+    return [boxes[i, :counts[i]] for i in range(n)], [labels[i, :counts[i]] for i in range(n)]

@@ -19,6 +19,7 @@ PyTorch is plumbing (memory, streams, autograd hand-off, NCCL); every arithmetic
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -162,6 +163,13 @@ class TrainEngine:
         self.packed: Optional[PackedWeights] = None
         self.tape = None
         self.plans = {}
+        self._side = None
+
+    def _wgrad_side_stream(self, main):
+        """Second stream of the backward pass (weight gradients), on ``main``'s device."""
+        if self._side is None or self._side.device != main.device:
+            self._side = torch.cuda.Stream(device=main.device)
+        return self._side
 
     # ------------------------------------------------------------------------------------------
     def flatten(self) -> FlatParams:
@@ -253,6 +261,28 @@ class TrainEngine:
         dscores = dscores.float().contiguous()
         n = tape["image"].shape[0]
         head_at = {h["layer"]: h for h in tape["heads"]}
+        # Weight gradients are leaves of the backward graph: they go to a second (lower-priority) stream and
+        # overlap the critical chain BN-backward -> data gradient -> BN-backward ..., whose small-map kernels
+        # fill a fraction of the SMs.  Inside a CUDA-graph capture the fork/join become graph edges.  The
+        # gradient tensors the side stream reads are kept alive until the join (the allocator would hand their
+        # memory to a later main-stream tensor otherwise); the side stream has its own scratch slot.
+        main = torch.cuda.current_stream()
+        side = self._wgrad_side_stream(main) if os.environ.get("SSD3D_TRAIN_WGRAD_STREAM", "1") != "0" else None
+        keep = []
+
+        def leaf(fn, *tensors):
+            if side is None:
+                fn()
+                return
+            side.wait_stream(main)
+            ops._WS_SLOT[0] = "ws_side"
+            try:
+                with torch.cuda.stream(side):
+                    fn()
+            finally:
+                ops._WS_SLOT[0] = "ws"
+            keep.extend(tensors)
+
         dO = {}
         for h in tape["heads"]:
             j = h["j"]
@@ -261,8 +291,9 @@ class TrainEngine:
             dO[h["layer"]] = ops.head_grad_pack(dlocs, dscores, n, d, hh, w, bpl, pc.n_classes, h["off"],
                                                 grads["pred_convs.loc_convs.%d.bias" % j],
                                                 grads["pred_convs.cl_convs.%d.bias" % j])
-            ops.head_wgrad(dO[h["layer"]], h["feat"], bpl * 6, bpl * pc.n_classes,
-                           grads["pred_convs.loc_convs.%d.weight" % j], grads["pred_convs.cl_convs.%d.weight" % j])
+            leaf(lambda h=h, j=j, bpl=bpl: ops.head_wgrad(
+                dO[h["layer"]], h["feat"], bpl * 6, bpl * pc.n_classes,
+                grads["pred_convs.loc_convs.%d.weight" % j], grads["pred_convs.cl_convs.%d.weight" % j]))
         g = None    # gradient w.r.t. the output of the unit being processed (channels-last bf16)
         for u in reversed(tape["units"]):
             i = u["idx"]
@@ -274,18 +305,22 @@ class TrainEngine:
                 raise RuntimeError("no gradient reaches backbone layer %d" % i)
             if u["kind"] == "block":
                 dz2 = ops.bn_relu_backward(u["z2"], g, u["st2"], grads[p + ".bn2.weight"], grads[p + ".bn2.bias"])
-                ops.pwconv_wgrad(dz2, u["a1"], grads[p + ".conv2.weight"])
+                leaf(lambda dz2=dz2, u=u, p=p: ops.pwconv_wgrad(dz2, u["a1"], grads[p + ".conv2.weight"]), dz2)
                 g1 = torch.empty_like(u["a1"])
                 nn_, c1, d1, h1, w1 = u["a1"].shape
                 wt = u["wpt"] if u["wpt"] is not None else u["wp"].t().contiguous()   # (Cin, Cout): dx = dz . W
                 ops.pw_gemm_raw(nn_ * d1 * h1 * w1, dz2, wt, g1)
                 dz1 = ops.bn_relu_backward(u["z1"], g1, u["st1"], grads[p + ".bn1.weight"], grads[p + ".bn1.bias"])
-                ops.dwconv3d_wgrad(dz1, u["x"], u["stride"], grads[p + ".conv1.weight"])
+                leaf(lambda dz1=dz1, u=u, p=p: ops.dwconv3d_wgrad(dz1, u["x"], u["stride"],
+                                                                  grads[p + ".conv1.weight"]), dz1)
                 g = ops.dwconv3d_dgrad(dz1, u["wd"], u["x"], u["stride"])
             else:
                 dz = ops.bn_relu_backward(u["z"], g, u["st"], grads[p + ".1.weight"], grads[p + ".1.bias"])
                 ops.stem_wgrad(dz, u["x"], u["stride"], grads[p + ".0.weight"])
                 g = None
+        if side is not None:
+            main.wait_stream(side)
+        del keep
 
 
 class _NetFn(torch.autograd.Function):
@@ -390,7 +425,10 @@ class _TrainPlan:
                 v.copy_(buffers[k])
         graph = torch.cuda.CUDAGraph()
         before = ops.LAUNCHES[0]
-        with torch.no_grad(), torch.cuda.graph(graph):
+        # the capture stream is high priority: the critical chain then wins free SM slots over the weight-gradient
+        # side stream (kernel nodes inherit the priority of the stream they were captured on)
+        cap = torch.cuda.Stream(device=model.device, priority=-1)
+        with torch.no_grad(), torch.cuda.graph(graph, stream=cap):
             self._run(model)
         self.n_kernels = ops.LAUNCHES[0] - before
         ops.LAUNCHES[0] = before

@@ -60,7 +60,14 @@ def _install_stubs():
     monai.transforms = _mod("monai.transforms")
     _mod("monai.transforms.transform", MapTransform=_A)
     _mod("monai.transforms.inverse", InvertibleTransform=_B)
-    monai.data = _mod("monai.data", box_area=lambda b: None)
+    def _box_area(boxes):      # monai.data.box_area: product of the (max - min) extents of [mins..., maxs...] boxes
+        nd = boxes.shape[1] // 2
+        area = boxes[:, nd] - boxes[:, 0]
+        for ax in range(1, nd):
+            area = area * (boxes[:, ax + nd] - boxes[:, ax])
+        return area
+
+    monai.data = _mod("monai.data", box_area=_box_area)
     monai.networks = _mod("monai.networks")
     _mod("monai.networks.blocks", Convolution=object)
     mpl = _mod("matplotlib")

@@ -654,3 +654,51 @@ def calculate_map(det_boxes, det_labels, det_scores, true_boxes, true_labels, tr
                       f1=(2 * p * r) / (p + r), cum_precision=prec, cum_recall=rec, p11=p11, volumes=vols)
     out["mAP"] = aps.mean().item()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Ground-truth boxes from a segmentation (utils.py:438-513, BoundingBoxesGeneratord "binary" / "classes")
+# ---------------------------------------------------------------------------------------------------
+def _label_face_connected(mask: np.ndarray):
+    """Face-connected components of a 3-D boolean mask, numbered 1.. in C order of each component's first voxel
+    (what ``scipy.ndimage.label`` with its default structure returns, utils.py:13,447,462).  Plain flood fill."""
+    lab = np.zeros(mask.shape, dtype=np.int64)
+    D, H, W = mask.shape
+    n = 0
+    for start in np.argwhere(mask):          # argwhere is in C order
+        if lab[tuple(start)]:
+            continue
+        n += 1
+        lab[tuple(start)] = n
+        stack = [tuple(start)]
+        while stack:
+            d, h, w = stack.pop()
+            for dd, hh, ww in ((d - 1, h, w), (d + 1, h, w), (d, h - 1, w), (d, h + 1, w), (d, h, w - 1), (d, h, w + 1)):
+                if 0 <= dd < D and 0 <= hh < H and 0 <= ww < W and mask[dd, hh, ww] and not lab[dd, hh, ww]:
+                    lab[dd, hh, ww] = n
+                    stack.append((dd, hh, ww))
+    return lab, n
+
+
+def gt_boxes_from_segmentation(seg, n_classes: int = 0):
+    """One volume (D, H, W) -> (boxes (n, 6) fp32, labels (n,) int64).  ``n_classes == 0``: "binary" mode (non-zero
+    voxels, label 1, utils.py:446-449); otherwise "classes" mode with classes 1..n_classes (utils.py:451-468).
+    Boxes are [min index, max index] / image size (utils.py:500,472); zero-volume boxes are dropped
+    (utils.py:475-480).  A volume without objects gives empty tensors (the reference raises there)."""
+    seg = np.squeeze(np.asarray(seg))
+    boxes, labels = [], []
+    classes = [1] if n_classes == 0 else list(range(1, n_classes + 1))
+    for ci, c in enumerate(classes):
+        mask = (seg != 0) if n_classes == 0 else (seg == c)
+        lab, n = _label_face_connected(mask)
+        for k in range(1, n + 1):
+            idx = np.argwhere(lab == k)
+            boxes.append(list(idx.min(0)) + list(idx.max(0)))
+            labels.append(ci + 1)
+    if not boxes:
+        return torch.zeros((0, 6)), torch.zeros((0,), dtype=torch.long)
+    b = torch.tensor(boxes, dtype=torch.float32) / torch.tensor(list(seg.shape) * 2, dtype=torch.float32)
+    l = torch.tensor(labels, dtype=torch.long)
+    vol = (b[:, 3] - b[:, 0]) * (b[:, 4] - b[:, 1]) * (b[:, 5] - b[:, 2])
+    keep = vol != 0.0
+    return b[keep], l[keep]

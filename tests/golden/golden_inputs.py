@@ -137,3 +137,52 @@ def train_inputs(case):
     x, b, l = synthetic.make_batch(case["batch"], case["channels"], case["size"], first_idx=3 * case["seed"],
                                    with_boxes=True)
     return sd, torch.from_numpy(x), [torch.from_numpy(v) for v in b], [torch.from_numpy(v) for v in l]
+
+
+# ---- ground-truth boxes from segmentations (utils.py:438-513) --------------------------------------------------
+GTBOX_CASES = {
+    # binary: cubes that may touch / overlap (merge into one component), a one-voxel-thick plate and a lone voxel
+    # (zero volume, dropped), two cubes touching only along an edge (separate under face connectivity)
+    "binary_cubes": dict(seed=50, mode="binary", n_classes=0, size=(48, 40, 56), n_volumes=3, kind="cubes"),
+    # classes: values 0..3 with n_classes = 2 (3 is not a class and is ignored); same-class blobs across a class
+    # boundary stay separate, output is ordered by class first
+    "classes2": dict(seed=51, mode="classes", n_classes=2, size=(40, 48, 36), n_volumes=2, kind="classes"),
+    # sparse noise: hundreds of irregular components, many of them flat
+    "binary_noise": dict(seed=52, mode="binary", n_classes=0, size=(20, 18, 22), n_volumes=2, kind="noise"),
+    # non-convex shapes: a spiral / L / U that need several union rounds, and an empty volume
+    "binary_shapes": dict(seed=53, mode="binary", n_classes=0, size=(32, 32, 32), n_volumes=2, kind="shapes"),
+}
+
+
+def gtbox_inputs(case):
+    """-> float32 array (n_volumes, D, H, W) of segmentation values."""
+    rng = np.random.RandomState(case["seed"])
+    D, H, W = case["size"]
+    out = np.zeros((case["n_volumes"], D, H, W), dtype=np.float32)
+    for v in range(case["n_volumes"]):
+        seg = out[v]
+        if case["kind"] in ("cubes", "classes"):
+            for _ in range(rng.randint(4, 9)):
+                side = rng.randint(3, 12)
+                c = [rng.randint(0, dim - side) for dim in (D, H, W)]
+                val = 1 if case["kind"] == "cubes" else rng.randint(1, 4)
+                seg[c[0]:c[0] + side, c[1]:c[1] + side, c[2]:c[2] + side] = val
+            seg[2, 3:9, 4:11] = 1                      # plate: zero extent along axis 0
+            seg[D - 1, H - 1, W - 1] = 1               # lone voxel in the last corner
+            seg[10:13, 20:23, 30:33] = 1               # two cubes sharing one edge only
+            seg[13:16, 23:26, 30:33] = 1
+            if case["kind"] == "classes":
+                seg[20:24, 5:9, 5:9] = 1               # class 1 | class 2 face to face: two components
+                seg[24:28, 5:9, 5:9] = 2
+        elif case["kind"] == "noise":
+            seg[:] = (rng.rand(D, H, W) < 0.22).astype(np.float32)
+        elif case["kind"] == "shapes" and v == 0:
+            seg[4, 4:28, 4] = 1                        # U shape in one plane, 1 voxel thick -> dropped
+            seg[4:20, 4, 4] = 1
+            seg[8:12, 8:28, 8:12] = 1                  # L shape, thick
+            seg[8:24, 24:28, 8:12] = 1
+            for k in range(40):                        # staircase: connected through faces only step by step
+                seg[16 + k // 4, 10 + (k % 4), 16 + k // 3] = 1
+                seg[16 + k // 4, 10 + (k % 4), min(31, 17 + k // 3)] = 1
+                seg[min(31, 17 + k // 4), 10 + (k % 4), 16 + k // 3] = 1
+    return out

@@ -36,9 +36,37 @@ def build_reference_model(ssd3d, case, **over):
     return ssd3d.LSSD3D(**kw).eval()
 
 
+def gtbox_goldens(utils):
+    """BoundingBoxesGeneratord.converter of the reference on seeded segmentations (utils.py:438-482)."""
+    from tests.golden.golden_inputs import GTBOX_CASES, gtbox_inputs
+    out = {}
+    for name, case in GTBOX_CASES.items():
+        segs = gtbox_inputs(case)
+        kw = dict(segmentation_mode=case["mode"])
+        if case["mode"] == "classes":
+            kw["n_classes"] = case["n_classes"]
+        gen = utils.BoundingBoxesGeneratord(keys=["seg"], **kw)
+        res = []
+        for v in range(segs.shape[0]):
+            try:
+                res.append(gen.converter(segs[v][None].copy()))
+            except RuntimeError as e:      # a volume without objects: FloatTensor([]) / FloatTensor(6) raises
+                assert segs[v].sum() == 0, e
+                res.append((None, None))
+        out[name] = dict(boxes=[None if b is None else b.clone() for b, _ in res],
+                         labels=[None if l is None else l.clone() for _, l in res],
+                         in_sum=float(segs.astype(np.float64).sum()))
+        print("gtbox", name, [None if b is None else int(b.shape[0]) for b, _ in res])
+    torch.save(out, os.path.join(HERE, "gtbox.pt"))
+
+
 def main():
     ssd3d, mobilenet, utils = load_reference()
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "gtbox":      # only this section (the others are unchanged)
+        gtbox_goldens(utils)
+        return
+    gtbox_goldens(utils)
 
     # ---- priors --------------------------------------------------------------
     out = {}

@@ -146,3 +146,30 @@ def test_train_step_matches_reference(name):
             assert int(got) == int(v)
         else:
             torch.testing.assert_close(got, v, rtol=1e-4, atol=1e-5, msg=k)
+
+
+@pytest.mark.parametrize("name", list(GI.GTBOX_CASES))
+def test_gt_boxes_match_reference(name):
+    """Oracle connected-component box extraction vs BoundingBoxesGeneratord.converter of the unmodified reference
+    (boxes bit-exact, same order, same zero-volume filter)."""
+    case, gold = GI.GTBOX_CASES[name], load_golden("gtbox.pt")[name]
+    segs = GI.gtbox_inputs(case)
+    assert float(segs.astype("float64").sum()) == gold["in_sum"]
+    for v in range(segs.shape[0]):
+        b, l = O.gt_boxes_from_segmentation(segs[v], case["n_classes"])
+        if gold["boxes"][v] is None:           # the reference raises on a volume without objects
+            assert b.shape == (0, 6) and l.shape == (0,)
+            continue
+        assert torch.equal(b, gold["boxes"][v]) and torch.equal(l, gold["labels"][v])
+
+
+def test_synthetic_ground_truth_is_what_the_extractor_finds():
+    """The in-memory generator's GT boxes (synthetic.boxes_from_mask, scipy labelling as the reference) equal the
+    oracle's flood-fill extraction on the generator's own masks, touching cubes included."""
+    import numpy as np
+    from mslesions3d_b200 import synthetic
+    for idx in range(8):
+        _, mask, _ = synthetic.generate_volume(idx, (40, 40, 40), (1, 5), (6, 14), 0)
+        b, l = O.gt_boxes_from_segmentation(mask, 0)
+        want = synthetic.boxes_from_mask(mask)
+        assert np.array_equal(b.numpy(), want) and int(l.sum()) == want.shape[0]
