@@ -154,6 +154,12 @@ class PackedWeights:
         ops.gather_cast(self.flat.param, self.index_f32, self.buf_f32)
 
 
+def dims_of(x, count, bpl):
+    """Spatial shape of ``x`` if it holds ``count`` priors at ``bpl`` boxes per location, else ()."""
+    sp = tuple(x.shape[2:])
+    return sp if sp[0] * sp[1] * sp[2] * bpl == count else ()
+
+
 class TrainEngine:
     """Train-mode forward with a tape + hand-written backward for ``LSSD3D`` (MobileNet base + SSD heads)."""
 
@@ -203,6 +209,25 @@ class TrainEngine:
         x = image
         feats = {}
         keys = list(m.aspect_ratios.keys())
+        pc = m.pred_convs
+        n = image.shape[0]
+        # head outputs are allocated up front (feature-map sizes follow from the strides) so that each head can be
+        # issued on the side stream as soon as its feature map exists, overlapping the rest of the backbone
+        dims, counts_at = tuple(image.shape[2:]), {}
+        for i, feat in enumerate(m.base.features):
+            st3 = _stride3(feat[0].stride if isinstance(feat, ConvBN) else feat.conv1.stride)
+            dims = tuple(ops.conv_out(v, s_) for v, s_ in zip(dims, st3))
+            if i in keys:
+                counts_at[i] = dims[0] * dims[1] * dims[2] * pc.n_boxes[i]
+        counts = [counts_at[k] for k in keys]
+        offs = [int(sum(counts[:j])) for j in range(len(keys))]
+        total = int(sum(counts))
+        locs = torch.empty((n, total, 6), dtype=torch.float32, device=dev)
+        scores = torch.empty((n, total, pc.n_classes), dtype=torch.float32, device=dev)
+        head_w = ([(packed.views["head%d.w" % j], packed.views["head%d.b" % j]) for j in range(len(keys))]
+                  if packed else pc._pack())
+        main = torch.cuda.current_stream()
+        side = self._wgrad_side_stream(main) if os.environ.get("SSD3D_TRAIN_WGRAD_STREAM", "1") != "0" else None
         for i, feat in enumerate(m.base.features):
             if isinstance(feat, ConvBN):
                 conv, bn = feat[0], feat[1]
@@ -229,22 +254,24 @@ class TrainEngine:
                 raise NotImplementedError("unexpected backbone layer %r" % type(feat))
             if i in keys:
                 feats[i] = x
-        pc = m.pred_convs
-        n = image.shape[0]
-        counts = []
-        for j, k in enumerate(keys):
-            _, _, d, h, w_ = feats[k].shape
-            counts.append(d * h * w_ * pc.n_boxes[k])
-        total = int(sum(counts))
-        locs = torch.empty((n, total, 6), dtype=torch.float32, device=dev)
-        scores = torch.empty((n, total, pc.n_classes), dtype=torch.float32, device=dev)
-        off = 0
-        head_w = ([(packed.views["head%d.w" % j], packed.views["head%d.b" % j]) for j in range(len(keys))]
-                  if packed else pc._pack())
-        for j, k in enumerate(keys):
-            ops.head_conv(feats[k], head_w[j][0], head_w[j][1], locs, scores, pc.n_boxes[k], pc.n_classes, off, flag)
-            tape["heads"].append(dict(j=j, layer=k, feat=feats[k], w=head_w[j][0], off=off, bpl=pc.n_boxes[k]))
-            off += counts[j]
+                j = keys.index(i)
+                if tuple(x.shape[2:]) != dims_of(x, counts_at[i], pc.n_boxes[i]):
+                    raise RuntimeError("feature map %d has an unexpected shape %r" % (i, tuple(x.shape)))
+                if side is not None:
+                    side.wait_stream(main)
+                    ops._WS_SLOT[0] = "ws_side"
+                    try:
+                        with torch.cuda.stream(side):
+                            ops.head_conv(x, head_w[j][0], head_w[j][1], locs, scores, pc.n_boxes[i], pc.n_classes,
+                                          offs[j], flag)
+                    finally:
+                        ops._WS_SLOT[0] = "ws"
+                else:
+                    ops.head_conv(x, head_w[j][0], head_w[j][1], locs, scores, pc.n_boxes[i], pc.n_classes, offs[j],
+                                  flag)
+                tape["heads"].append(dict(j=j, layer=i, feat=x, w=head_w[j][0], off=offs[j], bpl=pc.n_boxes[i]))
+        if side is not None:
+            main.wait_stream(side)
         self.tape = tape
         return locs, scores
 
