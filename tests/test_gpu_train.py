@@ -59,7 +59,9 @@ def rel_l2(got, want):
 # train-mode BatchNorm + ReLU, forward and backward
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,c,size", [(2, 32, (9, 10, 11)), (3, 64, (8, 8, 8)), (1, 128, (5, 6, 7)),
-                                      (2, 512, (2, 2, 2)), (4, 256, (3, 3, 3)), (2, 32, (24, 24, 24))])
+                                      (2, 512, (2, 2, 2)), (4, 256, (3, 3, 3)), (2, 32, (24, 24, 24)),
+                                      # the single-kernel path takes M <= 4096 rows: the C3 tail, the cap, just above
+                                      (16, 256, (6, 6, 6)), (1, 32, (16, 16, 16)), (1, 32, (16, 16, 17))])
 def test_bn_train_relu_forward_backward(n, c, size):
     ops = _ops()
     g = torch.Generator().manual_seed(c + n)
