@@ -1211,13 +1211,14 @@ using namespace ssd3d;
 // ================================================================================================
 static const int COLRED_MAX_BLOCKS = 592;   // 4 x 148 SMs
 
-static int colreduce_plan(long long M, int C, int* threads, long long* rows_per_block) {
+static int colreduce_plan(long long M, int C, int* threads, long long* rows_per_block,
+                          int max_blocks = COLRED_MAX_BLOCKS) {
   const int CV = C / 8;
   if (C <= 0 || (C & 7) || CV > 256) return -1;
   const int RP = 256 / CV;
   *threads = CV * RP;
   long long B = (M + RP * 4 - 1) / (RP * 4);
-  if (B > COLRED_MAX_BLOCKS) B = COLRED_MAX_BLOCKS;
+  if (B > max_blocks) B = max_blocks;
   if (B < 1) B = 1;
   long long rpb = (M + B - 1) / B;
   *rows_per_block = rpb;
@@ -1258,7 +1259,9 @@ extern "C" int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, i
     return SSD3D_ERR_ARG;
   int threads;
   long long rpb;
-  const int B = colreduce_plan(M, C, &threads, &rpb);
+  // the backward reduction holds 84 registers: three CTAs per SM are resident, so at most 3 x 148 blocks (a fourth
+  // quarter of the grid would run as a second, mostly empty wave)
+  const int B = colreduce_plan(M, C, &threads, &rpb, 444);
   if (B < 0 || workspace_bytes < (int64_t)B * 2 * C * 4) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
