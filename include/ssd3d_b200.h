@@ -150,6 +150,30 @@ int ssd3d_decode_softmax(const float* locs, const float* scores, const float* pr
 int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_overlap, uint8_t* keep, void* mask_ws,
                        void* stream);
 
+/* Greedy NMS over a score-sorted list of ANY length (ssd3d.py:407-426 without the n x n IoU matrix, which
+ * is 25 TB at the 2.5 M candidates of the whole-brain NMS-stress setting, model_insight.py:146): the list
+ * is walked in chunks of `chunk` boxes (0 = default 4096; a multiple of 64 in [64, SSD3D_SORT_MAX]); each
+ * chunk is first tested against the compact list of boxes kept so far, then resolved with the bit matrix.
+ * Same keep decisions as ssd3d_nms3d_sorted, bit for bit.  keep (n) uint8; kept_count (device int64, may
+ * be NULL) receives the number of kept boxes; no host synchronisation. */
+int64_t ssd3d_nms3d_chunked_workspace_bytes(int64_t n, int chunk);
+int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, float max_overlap, uint8_t* keep,
+                               int64_t* kept_count, void* workspace, int64_t workspace_bytes, int chunk,
+                               void* stream);
+
+/* Ascending stable sort of n 64-bit keys in place (`Tensor.sort` of ssd3d.py:397,450 on the packed
+ * {~orderable(score), index} keys, for lists the single-block sort cannot hold): 16384-key block sorts +
+ * merge passes.  tmp: n keys of scratch (may be NULL when n <= SSD3D_SORT_MAX). */
+int ssd3d_sort_keys_u64(uint64_t* keys, int64_t n, uint64_t* tmp, void* stream);
+
+/* Stage 1 of detect_objects alone (ssd3d.py:363-388): softmax, decode to boundary coords, keep candidates
+ * with score > min_score.  boxes_xyz (N,P,6); segment seg = img*(n_classes-1) + (c-1) owns
+ * cand[seg*P .. seg*P + count[seg]) = keys {~orderable(score) << 32 | prior index} in arbitrary order;
+ * count (N*(n_classes-1)) int32 is zeroed by the call. */
+int ssd3d_decode_filter(const float* locs, const float* scores, const float* priors, int N, int64_t P,
+                        int n_classes, float min_score, float* boxes_xyz, uint64_t* cand, int32_t* count,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Training: prior <-> ground-truth matching and the MultiBox loss (ssd3d.py:741-941)
  * ---------------------------------------------------------------------------------------------- */

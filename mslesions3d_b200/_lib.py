@@ -42,6 +42,10 @@ SIGNATURES = {
                                      c_int64, P, P]),
     "ssd3d_decode_softmax": (c_int, [P, P, P, c_int, c_int64, c_int, P, P, P]),
     "ssd3d_nms3d_sorted": (c_int, [P, c_int64, c_float, P, P, P]),
+    "ssd3d_nms3d_chunked_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "ssd3d_nms3d_sorted_chunked": (c_int, [P, c_int64, c_float, P, P, P, c_int64, c_int, P]),
+    "ssd3d_sort_keys_u64": (c_int, [P, c_int64, P, P]),
+    "ssd3d_decode_filter": (c_int, [P, P, P, c_int, c_int64, c_int, c_float, P, P, P, P]),
     "ssd3d_match_priors": (c_int, [P, P, P, c_int, c_int64, P, c_int64, c_float, c_float, P, P, P, P, P, P, P]),
     "ssd3d_multibox_workspace_bytes": (c_int64, [c_int, c_int64]),
     "ssd3d_multibox_loss": (c_int, [P, P, P, P, c_int, c_int64, c_int, c_float, c_int, c_int, P, P, P, P, P,

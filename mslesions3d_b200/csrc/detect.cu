@@ -240,10 +240,11 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
 // exactly the greedy result of ssd3d.py:414-426.  The rows of the kept boxes are then OR-ed into the later
 // words, one warp per word, with redux.or across the 32 lanes.
 __device__ __forceinline__ void nms_scan_core(const unsigned long long* M, int n, int stride,
-                                              unsigned long long* removed, unsigned long long* keptw) {
+                                              unsigned long long* removed, unsigned long long* keptw,
+                                              const unsigned long long* removed_init = nullptr) {
   const int words = (n + 63) >> 6;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0ull;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = removed_init ? removed_init[w] : 0ull;
   __syncthreads();
   for (int k = 0; k < words; ++k) {
     const int rows = min(64, n - k * 64);
@@ -443,6 +444,140 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long*
   for (int i = threadIdx.x; i < n; i += blockDim.x) keep[i] = (uint8_t)((keptw[i >> 6] >> (i & 63)) & 1ull);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Greedy NMS over score-sorted lists of ANY length (the NMS-stress setting: min_score = 0 and a top_k
+// that defeats the 10*top_k truncation).  The reference's n x n IoU matrix
+// (ssd3d.py:407) is 25 TB at n = 2.5 M; the bit matrix above would still be 390 GB.  Here the list is
+// walked in chunks of B boxes (score order):
+//   cross : every box of the chunk against the boxes KEPT so far (compact list, 32 B per box: corners +
+//           volume) -> initial `removed` bits of the chunk.  One thread per chunk box, the kept list
+//           streamed through shared memory in tiles of 256, tiles strided over gridDim.y.
+//   mask  : nms_mask_kernel on the chunk alone (B x B/64 words)
+//   scan  : the greedy scan above, started from the cross bits; kept boxes are appended to the list.
+// A box is removed iff an earlier KEPT box overlaps it by more than the threshold, which is exactly the
+// reference's loop (ssd3d.py:414-426); the decisions use the same iou_exceeds() as the bit matrix.
+// Work is O(n * kept) IoU tests and 3 launches per chunk, nothing is read back by the host.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict__ boxes, int n,
+                                                        const float4* __restrict__ kept,
+                                                        const long long* __restrict__ nk_ptr, float thr,
+                                                        unsigned int* __restrict__ rem32) {
+  __shared__ float4 tile[256][2];
+  const long long nk = *nk_ptr;
+  const long long tiles = (nk + 255) >> 8;
+  if ((long long)blockIdx.y >= tiles) return;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const bool live = i < n;
+  Box6 a;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) a.v[k] = 0.f;
+  if (live) a = load_box(boxes + (long long)i * 6);
+  const float va = box_volume(a);
+  bool rem = false;
+  for (long long t = blockIdx.y; t < tiles; t += gridDim.y) {
+    __syncthreads();
+    const long long j = t * 256 + threadIdx.x;
+    if (j < nk) {
+      tile[threadIdx.x][0] = kept[2 * j];
+      tile[threadIdx.x][1] = kept[2 * j + 1];
+    }
+    __syncthreads();
+    const long long left = nk - t * 256;
+    const int jn = left < 256 ? (int)left : 256;
+    if (live && !rem) {
+      for (int b = 0; b < jn; ++b) {
+        const float4 p = tile[b][0], q = tile[b][1];
+        Box6 o;
+        o.v[0] = p.x; o.v[1] = p.y; o.v[2] = p.z; o.v[3] = p.w; o.v[4] = q.x; o.v[5] = q.y;
+        const float inter = box_intersection(a, o);
+        const float uni = __fsub_rn(__fadd_rn(va, q.z), inter);
+        if (iou_exceeds(inter, uni, thr)) rem = true;
+      }
+    }
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, live && rem);
+  if ((threadIdx.x & 31) == 0 && ballot != 0u) atomicOr(&rem32[i >> 5], ballot);
+}
+
+__global__ void __launch_bounds__(1024) nms_chunk_scan_kernel(const unsigned long long* __restrict__ mask,
+                                                              const float* __restrict__ boxes, int n, int words,
+                                                              const unsigned long long* __restrict__ removed_init,
+                                                              float4* __restrict__ kept, long long* __restrict__ nk_ptr,
+                                                              uint8_t* __restrict__ keep) {
+  extern __shared__ unsigned long long sm[];
+  unsigned long long* removed = sm;
+  unsigned long long* keptw = sm + words;
+  int* prefix = reinterpret_cast<int*>(sm + 2 * words);
+  __shared__ long long s_base;
+  nms_scan_core(mask, n, words, removed, keptw, removed_init);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < words; ++w) {
+      prefix[w] = run;
+      run += __popcll(keptw[w]);
+    }
+    const long long base = *nk_ptr;
+    s_base = base;
+    *nk_ptr = base + run;
+  }
+  __syncthreads();
+  const long long base = s_base;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long kw = keptw[i >> 6];
+    const bool k = (kw >> (i & 63)) & 1ull;
+    keep[i] = (uint8_t)k;
+    if (k) {
+      const long long pos = base + prefix[i >> 6] + __popcll(kw & ((1ull << (i & 63)) - 1ull));
+      const Box6 b = load_box(boxes + (long long)i * 6);
+      kept[2 * pos] = make_float4(b.v[0], b.v[1], b.v[2], b.v[3]);
+      kept[2 * pos + 1] = make_float4(b.v[4], b.v[5], box_volume(b), 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 64-bit key sort of any length (ascending, stable): 16384-key chunks by the shared-memory bitonic
+// network, then log2(chunks) merge passes in which every key finds its output slot by a binary search in
+// the sibling run (left run first on ties).  Used for candidate lists the single-block sort cannot hold.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) sort_chunks_kernel(unsigned long long* __restrict__ data, long long n) {
+  extern __shared__ unsigned long long keys[];
+  const long long begin = (long long)blockIdx.x * SSD3D_SORT_MAX;
+  long long len = n - begin;
+  if (len > SSD3D_SORT_MAX) len = SSD3D_SORT_MAX;
+  if (len <= 0) return;
+  bitonic_sort_smem(keys, data + begin, (int)len);
+  for (int i = threadIdx.x; i < (int)len; i += blockDim.x) data[begin + i] = keys[i];
+}
+
+__global__ void __launch_bounds__(256) merge_pass_kernel(const unsigned long long* __restrict__ src,
+                                                         unsigned long long* __restrict__ dst, long long n,
+                                                         long long run) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const long long r = e / run;
+  const long long i = e - r * run;
+  const unsigned long long key = src[e];
+  const long long sib = (r ^ 1ll) * run;
+  long long sib_len = n - sib;
+  if (sib_len > run) sib_len = run;
+  long long lo = 0;
+  if (sib_len > 0) {
+    const unsigned long long* s = src + sib;
+    long long hi = sib_len;
+    const bool right = (r & 1ll) != 0;       // right run: count sibling keys <= key; left run: < key
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      const unsigned long long v = s[mid];
+      const bool before = right ? (v <= key) : (v < key);
+      if (before) lo = mid + 1; else hi = mid;
+    }
+  }
+  dst[(r & ~1ll) * run + i + lo] = key;
+}
+
 static inline long long align256(long long v) { return (v + 255) & ~255ll; }
 
 // shared-memory words available for staging the bit matrix of up to n_max candidates (<= ~200 KB)
@@ -522,6 +657,119 @@ extern "C" int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_o
   }
   nms_scan_kernel<<<1, 256, smem, st>>>(static_cast<const unsigned long long*>(mask_ws), (int)n, words, stage_words,
                                         keep);
+  SSD3D_CHECK_LAUNCH();
+  return SSD3D_OK;
+}
+
+// ---- chunked NMS / long sort / filter stage entry points ------------------------------------------
+namespace ssd3d {
+struct ChunkedNmsLayout {
+  int chunk;
+  long long off_removed, off_nk, off_kept, off_mask, total;
+};
+static ChunkedNmsLayout chunked_nms_layout(long long n, int chunk) {
+  ChunkedNmsLayout L;
+  if (chunk <= 0) chunk = 4096;
+  L.chunk = chunk;
+  const long long cw = chunk / 64;
+  const long long chunks = (n + chunk - 1) / chunk;
+  long long o = 0;
+  L.off_removed = o; o += align256(8ll * chunks * cw);
+  L.off_nk = o; o += 256;
+  L.off_kept = o; o += align256(32ll * n);
+  L.off_mask = o; o += align256(8ll * chunk * cw);
+  L.total = o;
+  return L;
+}
+static inline bool chunk_ok(int chunk) { return chunk == 0 || (chunk >= 64 && chunk <= SSD3D_SORT_MAX && chunk % 64 == 0); }
+}  // namespace ssd3d
+
+extern "C" int64_t ssd3d_nms3d_chunked_workspace_bytes(int64_t n, int chunk) {
+  if (n <= 0 || !chunk_ok(chunk)) return 0;
+  return chunked_nms_layout(n, chunk).total;
+}
+
+extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, float max_overlap, uint8_t* keep,
+                                          int64_t* kept_count, void* workspace, int64_t workspace_bytes, int chunk,
+                                          void* stream) {
+  if (!boxes_xyz || !keep || !workspace || n <= 0 || !chunk_ok(chunk)) return SSD3D_ERR_ARG;
+  const ChunkedNmsLayout L = chunked_nms_layout(n, chunk);
+  if (workspace_bytes < L.total) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  unsigned long long* removed = reinterpret_cast<unsigned long long*>(ws + L.off_removed);
+  long long* nk = reinterpret_cast<long long*>(ws + L.off_nk);
+  float4* kept = reinterpret_cast<float4*>(ws + L.off_kept);
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + L.off_mask);
+  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)L.off_kept, st);      // removed bits + kept counter
+  if (e != cudaSuccess) return (int)e;
+  const int B = L.chunk, cw = B / 64;
+  const long long chunks = (n + B - 1) / B;
+  const int splits = 74;                    // x (B / 256) row blocks: 1184 = 148 x 8 CTAs at B = 4096
+  for (long long c = 0; c < chunks; ++c) {
+    const long long first = c * B;
+    const int rows = (int)((n - first) < B ? (n - first) : B);
+    const int words = (rows + 63) / 64;
+    const float* cb = boxes_xyz + first * 6;
+    unsigned long long* crem = removed + c * cw;
+    if (c > 0) {
+      dim3 grid((unsigned)((rows + 255) / 256), (unsigned)splits);
+      nms_cross_kernel<<<grid, 256, 0, st>>>(cb, rows, kept, nk, max_overlap, reinterpret_cast<unsigned int*>(crem));
+      SSD3D_CHECK_LAUNCH();
+    }
+    dim3 mgrid((unsigned)words, (unsigned)words, 1);
+    nms_mask_kernel<<<mgrid, 64, 0, st>>>(cb, nullptr, rows, 0, words, 0, max_overlap, mask);
+    SSD3D_CHECK_LAUNCH();
+    const size_t smem = (size_t)(2 * words) * 8 + (size_t)(words + 2) * 4;
+    nms_chunk_scan_kernel<<<1, 1024, smem, st>>>(mask, cb, rows, words, crem, kept, nk, keep + first);
+    SSD3D_CHECK_LAUNCH();
+  }
+  if (kept_count) {
+    e = cudaMemcpyAsync(kept_count, nk, 8, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_sort_keys_u64(uint64_t* keys, int64_t n, uint64_t* tmp, void* stream) {
+  if (!keys || n < 0 || (n > SSD3D_SORT_MAX && !tmp)) return SSD3D_ERR_ARG;
+  if (n <= 1) return SSD3D_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int cap = 1;
+  while (cap < n && cap < SSD3D_SORT_MAX) cap <<= 1;
+  const size_t smem = (size_t)cap * 8;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(sort_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const long long chunks = (n + SSD3D_SORT_MAX - 1) / SSD3D_SORT_MAX;
+  sort_chunks_kernel<<<(unsigned)chunks, 1024, smem, st>>>(reinterpret_cast<unsigned long long*>(keys), (long long)n);
+  SSD3D_CHECK_LAUNCH();
+  unsigned long long* src = reinterpret_cast<unsigned long long*>(keys);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(tmp);
+  for (long long run = SSD3D_SORT_MAX; run < n; run <<= 1) {
+    merge_pass_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, (long long)n, run);
+    SSD3D_CHECK_LAUNCH();
+    unsigned long long* t = src; src = dst; dst = t;
+  }
+  if (src != reinterpret_cast<unsigned long long*>(keys)) {
+    cudaError_t e = cudaMemcpyAsync(keys, src, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_decode_filter(const float* locs, const float* scores, const float* priors, int N, int64_t P,
+                                   int n_classes, float min_score, float* boxes_xyz, uint64_t* cand, int32_t* count,
+                                   void* stream) {
+  if (!locs || !scores || !priors || !boxes_xyz || !cand || !count) return SSD3D_ERR_ARG;
+  if (N <= 0 || P <= 0 || n_classes < 2 || P > 0x7fffffffll) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(count, 0, (size_t)N * (n_classes - 1) * 4, st);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)((P + 255) / 256), (unsigned)N);
+  decode_filter_kernel<<<grid, 256, 0, st>>>(locs, scores, priors, (long long)P, n_classes, min_score, boxes_xyz,
+                                             reinterpret_cast<unsigned long long*>(cand), count);
   SSD3D_CHECK_LAUNCH();
   return SSD3D_OK;
 }

@@ -265,6 +265,125 @@ def nms3d_sorted(boxes_xyz: torch.Tensor, max_overlap: float) -> torch.Tensor:
     return keep.bool()
 
 
+def nms3d_sorted_chunked(boxes_xyz: torch.Tensor, max_overlap: float, chunk: int = 0,
+                         return_count: bool = False):
+    """Greedy NMS over a score-sorted list of any length (ssd3d.py:407-426): chunks of ``chunk`` boxes
+    (0 = the library default), each tested against the kept list first, then resolved with the bit matrix.
+    -> bool keep mask (and the device int64 kept count)."""
+    boxes_xyz = _boxes(boxes_xyz, "boxes")
+    n = boxes_xyz.shape[0]
+    dev = boxes_xyz.device
+    keep = torch.empty((n,), dtype=torch.uint8, device=dev)
+    count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    if n == 0:
+        return (keep.bool(), count) if return_count else keep.bool()
+    lib = _lib.load()
+    need = lib.ssd3d_nms3d_chunked_workspace_bytes(n, int(chunk))
+    if need <= 0:
+        raise ValueError("nms3d_sorted_chunked: chunk must be 0 or a multiple of 64 in [64, %d]" % _lib.SORT_MAX)
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    rc = lib.ssd3d_nms3d_sorted_chunked(boxes_xyz.data_ptr(), n, f32(max_overlap), keep.data_ptr(), count.data_ptr(),
+                                        ws.data_ptr(), need, int(chunk), _stream())
+    _lib.check(rc, "ssd3d_nms3d_sorted_chunked")
+    per = int(chunk) if chunk else 4096
+    LAUNCHES[0] += 3 * ((n + per - 1) // per) - 1
+    return (keep.bool(), count) if return_count else keep.bool()
+
+
+def sort_keys_u64(keys: torch.Tensor) -> torch.Tensor:
+    """Ascending stable in-place sort of packed 64-bit keys held in an int64 tensor (compared as unsigned)."""
+    _need_cuda(keys)
+    if keys.dtype != torch.int64 or not keys.is_contiguous() or keys.dim() != 1:
+        raise ValueError("sort_keys_u64 needs a contiguous 1-D int64 tensor")
+    n = keys.numel()
+    if n <= 1:
+        return keys
+    tmp = torch.empty_like(keys) if n > _lib.SORT_MAX else None
+    rc = _lib.load().ssd3d_sort_keys_u64(keys.data_ptr(), n, tmp.data_ptr() if tmp is not None else None, _stream())
+    _lib.check(rc, "ssd3d_sort_keys_u64")
+    runs = (n + _lib.SORT_MAX - 1) // _lib.SORT_MAX
+    LAUNCHES[0] += 1 + max(0, (runs - 1).bit_length())
+    return keys
+
+
+def decode_filter(locs: torch.Tensor, scores: torch.Tensor, priors: torch.Tensor, min_score: float):
+    """Stage 1 of detect_objects -> (boxes_xyz (N,P,6), cand (S,P) int64 keys, count (S,) int32), S = N*(C-1)."""
+    _need_cuda(locs, scores, priors)
+    locs, scores, priors = locs.float().contiguous(), scores.float().contiguous(), priors.float().contiguous()
+    n, p, c = scores.shape
+    if locs.shape[0] != n or locs.shape[1] != p or priors.shape[0] != p:
+        raise AssertionError("prior / prediction count mismatch")  # ssd3d.py:370
+    dev = locs.device
+    boxes = torch.empty((n, p, 6), dtype=torch.float32, device=dev)
+    cand = torch.empty((n * (c - 1), p), dtype=torch.int64, device=dev)
+    count = torch.empty((n * (c - 1),), dtype=torch.int32, device=dev)
+    rc = _lib.load().ssd3d_decode_filter(locs.data_ptr(), scores.data_ptr(), priors.data_ptr(), n, p, c,
+                                         f32(min_score), boxes.data_ptr(), cand.data_ptr(), count.data_ptr(), _stream())
+    _lib.check(rc, "ssd3d_decode_filter")
+    LAUNCHES[0] += 1
+    return boxes, cand, count
+
+
+def _key_scores(keys: torch.Tensor) -> torch.Tensor:
+    """fp32 score packed in the high word of a candidate key ({~orderable(score) << 32 | index})."""
+    u = (~(keys >> 32)) & 0xFFFFFFFF                       # orderable(score)
+    bits = torch.where((u & 0x80000000) != 0, u & 0x7FFFFFFF, (~u) & 0xFFFFFFFF)
+    return bits.to(torch.int32).view(torch.float32) if bits.numel() else bits.to(torch.float32)
+
+
+def detect_needs_long_lists(n_priors: int, top_k: int) -> bool:
+    """True where the fused ssd3d_detect_objects stops (P > SORT_MAX and 10*top_k > SORT_MAX/2): the
+    NMS-stress settings (model_insight.py:146) go through ``detect_objects_long`` instead."""
+    return n_priors > _lib.SORT_MAX and 10 * int(top_k) > _lib.SORT_MAX // 2
+
+
+def detect_objects_long(locs: torch.Tensor, scores: torch.Tensor, priors: torch.Tensor, min_score: float,
+                        max_overlap: float, top_k: int, return_prior: bool = False, chunk: int = 0):
+    """``detect_objects`` (ssd3d.py:344-460) for candidate lists of any length: filter/decode, key sort and
+    greedy NMS are this library's kernels (decode_filter, sort_keys_u64, nms3d_sorted_chunked); the host
+    reads the per-(image, class) candidate counts once and strings the stages together with tensor slicing.
+    Same outputs as the fused path (ties: ascending prior index)."""
+    top_k = int(top_k)
+    n, p, c = scores.shape
+    boxes, cand, count = decode_filter(locs, scores, priors, min_score)
+    dev = boxes.device
+    counts = count.cpu().tolist()                          # the one read-back before the per-segment stages
+    out_b, out_l, out_s, out_p = [], [], [], []
+    for i in range(n):
+        ib, ik, il = [], [], []
+        for cls in range(1, c):
+            seg = i * (c - 1) + (cls - 1)
+            m = counts[seg]
+            if m == 0:                                     # ssd3d.py:390-391
+                continue
+            keys = sort_keys_u64(cand[seg, :m])
+            keys = keys[:min(m, 10 * top_k)]               # ssd3d.py:401
+            prior = keys & 0xFFFFFFFF
+            sboxes = boxes[i].index_select(0, prior)
+            keep = nms3d_sorted_chunked(sboxes, max_overlap, chunk)
+            ib.append(sboxes[keep])
+            ik.append(keys[keep])
+            il.append(torch.full((ib[-1].shape[0],), cls, dtype=torch.int64, device=dev))
+        if not ib:                                         # ssd3d.py:437-440
+            out_b.append(torch.tensor([[0., 0., 0., 1., 1., 1.]], device=dev))
+            out_l.append(torch.zeros((1,), dtype=torch.int64, device=dev))
+            out_s.append(torch.zeros((1,), dtype=torch.float32, device=dev))
+            out_p.append(torch.full((1,), -1, dtype=torch.int64, device=dev))
+            continue
+        b, k, l = torch.cat(ib), torch.cat(ik), torch.cat(il)
+        if b.shape[0] > top_k:                             # ssd3d.py:449-453, stable: class order on ties
+            order_keys = ((k >> 32) << 32) | torch.arange(k.shape[0], dtype=torch.int64, device=dev)
+            order = (sort_keys_u64(order_keys.contiguous()) & 0xFFFFFFFF)[:top_k]
+            b, k, l = b[order], k[order], l[order]
+        out_b.append(b)
+        out_l.append(l)
+        out_s.append(_key_scores(k))
+        out_p.append(k & 0xFFFFFFFF)
+    if return_prior:
+        return out_b, out_l, out_s, out_p
+    return out_b, out_l, out_s
+
+
 class DetectOutput:
     """Padded device-side result of one detect call (rows >= count[i] are undefined)."""
     __slots__ = ("boxes", "scores", "labels", "prior", "count", "status")

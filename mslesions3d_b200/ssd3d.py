@@ -615,6 +615,10 @@ class LSSD3D(_LightningBase):
     def detect_objects(self, predicted_locs, predicted_scores, min_score, max_overlap, top_k, return_prior=False):
         """Decode + per-class NMS + top-k (ssd3d.py:344-460) -> lists of per-image boxes, labels, scores."""
         priors = self._priors_on(predicted_locs.device)
+        if ops.detect_needs_long_lists(priors.shape[0], top_k):
+            # NMS-stress settings (model_insight.py:146: min_score=0, top_k=50000): lists of any length
+            return ops.detect_objects_long(predicted_locs, predicted_scores, priors, min_score, max_overlap, top_k,
+                                           return_prior=return_prior)
         out = ops.detect_objects_padded(predicted_locs, predicted_scores, priors, min_score, max_overlap, top_k)
         return ops.detect_lists(out, return_prior=return_prior)
 
@@ -673,7 +677,7 @@ class LSSD3D(_LightningBase):
         sync for the whole batch.  ``batch["img"]`` may live on the host (pinned memory makes the copy
         asynchronous)."""
         image = batch["img"]
-        if not self.use_cuda_graph:
+        if not self.use_cuda_graph or ops.detect_needs_long_lists(self.priors_cxcycz.shape[0], self.top_k):
             return self._predict_step_eager(image)
         if self.device.type != "cuda":
             raise RuntimeError("LSSD3D.predict_step needs the model on a CUDA device; there is no CPU path")
@@ -693,6 +697,11 @@ class LSSD3D(_LightningBase):
             self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
             self.__dict__["_post_stream"] = torch.cuda.Stream(device=self.device)
         copy_stream, post_stream = self.__dict__["_copy_stream"], self.__dict__["_post_stream"]
+        if ops.detect_needs_long_lists(self.priors_cxcycz.shape[0], self.top_k):
+            for batch in batches:          # candidate lists of any length: no captured plan, one batch at a time
+                b, l, s = self._predict_step_eager(batch["img"])
+                yield ([t.cpu() for t in b], [t.cpu() for t in l], [t.cpu() for t in s]) if to_host else (b, l, s)
+            return
         caller = torch.cuda.current_stream()
         depth = max(1, int(self.pipeline_depth))
         inflight = []
@@ -718,6 +727,12 @@ class LSSD3D(_LightningBase):
         finally:
             self.defer_nan_check = prev
         priors = self._priors_on(predicted_locs.device)
+        if ops.detect_needs_long_lists(priors.shape[0], self.top_k):
+            flag = self.base.nan_flag(predicted_locs.device)
+            if int(flag.cpu()[0]):
+                self._raise_on_nan(flag)
+            return ops.detect_objects_long(predicted_locs, predicted_scores, priors, self.min_score,
+                                           self.max_overlap, self.top_k)
         out = ops.detect_objects_padded(predicted_locs, predicted_scores, priors, self.min_score, self.max_overlap,
                                         self.top_k)
         flag = self.base.nan_flag(predicted_locs.device)

@@ -2,7 +2,7 @@
 """The other BASELINE.json configs through the public API (LSSD3D.predict_batches, device-resident inputs):
   C1  1ch 64^3 batch 1 (the reference's CPU-runnable case)
   C4  whole-brain 2ch 160x192x160 batch 1: default prediction layers (43 800 priors) and with a layer-0 head
-      (2 501 400 priors), realistic (min_score .5, top_k 100) and NMS-stress (min_score 0, top_k 800) settings
+      (2 501 400 priors), realistic (min_score .5, top_k 100) and NMS-stress (min_score 0, top_k 800; and top_k = P/10: no truncation at all) settings
 One JSON line per case: volumes/s, ms/step (CUDA events), priors; the CPU oracle timed on the same shape where it
 finishes in seconds (C1).  `python scripts/bench_configs.py [--json out.json]`"""
 import argparse
@@ -22,6 +22,7 @@ from oracle import ssd3d_oracle as O  # noqa: E402  (CPU baseline leg only)
 ap = argparse.ArgumentParser()
 ap.add_argument("--json", default="")
 ap.add_argument("--steps", type=int, default=40)
+ap.add_argument("--only", default="", help="substring of the case name")
 args = ap.parse_args()
 dev = torch.device("cuda")
 CASES = [
@@ -32,9 +33,16 @@ CASES = [
          ar={0: [1.], 3: [1.], 5: [1.], 7: [1.]}, min_score=0.5, top_k=100, cpu=False),
     dict(name="C4 whole-brain + layer-0 head (2.5M priors), NMS stress", ch=2, size=(160, 192, 160), batch=1,
          ar={0: [1.], 3: [1.], 5: [1.], 7: [1.]}, min_score=0.0, top_k=800, cpu=False),
+    # top_k = P/10 defeats the 10*top_k truncation: ALL 2.5 M candidates are sorted and go through
+    # the chunked greedy NMS (ops.detect_objects_long); the reference would need a 25 TB IoU matrix here
+    dict(name="C4 whole-brain + layer-0 head (2.5M priors), NMS stress untruncated", ch=2, size=(160, 192, 160),
+         batch=1, ar={0: [1.], 3: [1.], 5: [1.], 7: [1.]}, min_score=0.0, top_k=250140, cpu=False, steps=2),
 ]
 rows = []
 for c in CASES:
+    if args.only and args.only not in c["name"]:
+        continue
+    steps = c.get("steps", args.steps)
     kw = dict(aspect_ratios=c["ar"]) if c["ar"] else {}
     sd = synthetic.random_state_dict(c["ch"], c["ar"], seed=0)
     model = LSSD3D(n_classes=2, input_channels=c["ch"], input_size=c["size"], min_score=c["min_score"],
@@ -45,17 +53,17 @@ for c in CASES:
           for i in range(3)]
     depth = model.pipeline_depth
     with torch.no_grad():
-        for _ in model.predict_batches({"img": xs[i % 3]} for i in range(depth + 3)):
+        for _ in model.predict_batches({"img": xs[i % 3]} for i in range(min(depth + 3, steps))):
             pass
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         n_det = 0
-        for boxes, labels, scores in model.predict_batches({"img": xs[i % 3]} for i in range(args.steps)):
+        for boxes, labels, scores in model.predict_batches({"img": xs[i % 3]} for i in range(steps)):
             n_det = int(boxes[0].shape[0])
         b.record()
         torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / args.steps
+    ms = a.elapsed_time(b) / steps
     row = dict(config=c["name"], priors=int(model.priors_cxcycz.shape[0]), ms_per_step=ms,
                volumes_per_s=c["batch"] / (ms / 1e3), min_score=c["min_score"], top_k=c["top_k"], detections=n_det,
                pipeline_depth=depth)
