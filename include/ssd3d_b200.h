@@ -154,12 +154,16 @@ int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_overlap, uin
  * is 25 TB at the 2.5 M candidates of the whole-brain NMS-stress setting, model_insight.py:146): the list
  * is walked in chunks of `chunk` boxes (0 = default 4096; a multiple of 64 in [64, SSD3D_SORT_MAX]); each
  * chunk is first tested against the compact list of boxes kept so far, then resolved with the bit matrix.
+ * With max_overlap >= 0 the cross test is pruned by a uniform grid over the boxes' minimum corners (only
+ * intersecting boxes can suppress each other); SSD3D_NMS_NO_GRID in `flags` forces the dense cross test.
  * Same keep decisions as ssd3d_nms3d_sorted, bit for bit.  keep (n) uint8; kept_count (device int64, may
- * be NULL) receives the number of kept boxes; no host synchronisation. */
+ * be NULL) receives the number of kept boxes; no host synchronisation.  chunk = 0: 4096, or 8192 from
+ * n = 1.5 M on (measured optimum). */
+#define SSD3D_NMS_NO_GRID 1
 int64_t ssd3d_nms3d_chunked_workspace_bytes(int64_t n, int chunk);
 int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, float max_overlap, uint8_t* keep,
                                int64_t* kept_count, void* workspace, int64_t workspace_bytes, int chunk,
-                               void* stream);
+                               int flags, void* stream);
 
 /* Ascending stable sort of n 64-bit keys in place (`Tensor.sort` of ssd3d.py:397,450 on the packed
  * {~orderable(score), index} keys, for lists the single-block sort cannot hold): 16384-key block sorts +

@@ -18,6 +18,7 @@ SSD3D_ERR_TMA = 10002
 SSD3D_ERR_UNSUPPORTED = 10003
 NAN_BACKBONE, NAN_LOCS, NAN_SCORES = 1, 2, 4
 SORT_MAX = 16384
+NMS_NO_GRID = 1
 BOX_CXCYCZ_TO_XYZ, BOX_XYZ_TO_CXCYCZ, BOX_GCXGCYGCZ_TO_CXCYCZ, BOX_CXCYCZ_TO_GCXGCYGCZ = 0, 1, 2, 3
 
 P = c_void_p  # every device pointer / stream crosses the ABI as a plain address
@@ -43,7 +44,7 @@ SIGNATURES = {
     "ssd3d_decode_softmax": (c_int, [P, P, P, c_int, c_int64, c_int, P, P, P]),
     "ssd3d_nms3d_sorted": (c_int, [P, c_int64, c_float, P, P, P]),
     "ssd3d_nms3d_chunked_workspace_bytes": (c_int64, [c_int64, c_int]),
-    "ssd3d_nms3d_sorted_chunked": (c_int, [P, c_int64, c_float, P, P, P, c_int64, c_int, P]),
+    "ssd3d_nms3d_sorted_chunked": (c_int, [P, c_int64, c_float, P, P, P, c_int64, c_int, c_int, P]),
     "ssd3d_sort_keys_u64": (c_int, [P, c_int64, P, P]),
     "ssd3d_decode_filter": (c_int, [P, P, P, c_int, c_int64, c_int, c_float, P, P, P, P]),
     "ssd3d_match_priors": (c_int, [P, P, P, c_int, c_int64, P, c_int64, c_float, c_float, P, P, P, P, P, P, P]),

@@ -504,7 +504,9 @@ __global__ void __launch_bounds__(1024) nms_chunk_scan_kernel(const unsigned lon
                                                               const float* __restrict__ boxes, int n, int words,
                                                               const unsigned long long* __restrict__ removed_init,
                                                               float4* __restrict__ kept, long long* __restrict__ nk_ptr,
-                                                              uint8_t* __restrict__ keep) {
+                                                              uint8_t* __restrict__ keep,
+                                                              const int* __restrict__ slot_of,
+                                                              uint8_t* __restrict__ state) {
   extern __shared__ unsigned long long sm[];
   unsigned long long* removed = sm;
   unsigned long long* keptw = sm + words;
@@ -533,8 +535,217 @@ __global__ void __launch_bounds__(1024) nms_chunk_scan_kernel(const unsigned lon
       const Box6 b = load_box(boxes + (long long)i * 6);
       kept[2 * pos] = make_float4(b.v[0], b.v[1], b.v[2], b.v[3]);
       kept[2 * pos + 1] = make_float4(b.v[4], b.v[5], box_volume(b), 0.f);
+      if (slot_of) state[slot_of[i]] = 1;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spatial pruning of the cross test.  With a threshold >= 0 only boxes that really intersect can suppress
+// each other, so the kept boxes a chunk box has to be tested against lie in a small neighbourhood.  Once
+// per call ALL n boxes are counting-sorted into a uniform G^3 grid by their minimum corner (x fastest),
+// as 32-byte records {corners, volume}, with one `state` byte per slot that the scan kernel sets when the
+// box is kept.  A kept box o can intersect a query box a only if, per axis,
+//     o.min <= a.max   and   o.min >= a.min - wmax      (wmax = largest extent of any box, rounded up)
+// and cell() is monotone, so the slots to visit are the cells [cell(a.min - wmax), cell(a.max)]: per
+// (y, z) row one contiguous slot range.  One warp per query box: lanes stride over the range, look at the
+// state byte and test only kept boxes.  Boxes of the same or later chunks still have state 0, which is
+// exactly the "earlier kept boxes" the greedy loop asks for.  Decisions are unchanged (same iou_exceeds).
+// ------------------------------------------------------------------------------------------------
+// Size levels: a single very large box would widen every query's neighbourhood, so the grid is replicated
+// NMS_LEVELS times and a box goes to the finest level l whose bound W / 2^l (W = largest extent of any box,
+// any axis) still covers its largest extent; a query walks level l with that bound instead of W.  A level
+// whose boxes are all too small to reach the threshold against the query box (volume <= bound^3 and
+// IoU <= min volume / max volume) ends the walk.
+#define NMS_LEVELS 4
+struct GridMap {
+  float lo[3], scale[3], wmax[3], W;
+  int G;
+};
+// rng: [0..2] orderable min of the min corners, [3..5] orderable max, [6..8] bits of the largest extents
+__device__ __forceinline__ GridMap load_grid(const unsigned int* __restrict__ rng, int G) {
+  GridMap m;
+  m.G = G;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float lo = float_from_orderable(rng[k]), hi = float_from_orderable(rng[3 + k]);
+    const float d = hi - lo;
+    m.lo[k] = lo;
+    m.scale[k] = (d > 0.f && d < 3.0e38f) ? (float)G / d : 0.f;
+    m.wmax[k] = __uint_as_float(rng[6 + k]);
+  }
+  m.W = fmaxf(m.wmax[0], fmaxf(m.wmax[1], m.wmax[2]));
+  return m;
+}
+// finest level whose bound W / 2^l is >= every extent of the box (extents rounded up, as in wmax)
+__device__ __forceinline__ int box_level(const GridMap& m, const Box6& b) {
+  float e = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float ext = __fsub_ru(b.v[3 + k], b.v[k]);
+    if (ext > e) e = ext;
+  }
+  int l = 0;
+  float w = m.W * 0.5f;
+  while (l < NMS_LEVELS - 1 && e <= w) {
+    ++l;
+    w *= 0.5f;
+  }
+  return l;
+}
+// monotone non-decreasing in x (NaN -> 0)
+__device__ __forceinline__ int cell_coord(const GridMap& m, int k, float x) {
+  const float f = floorf((x - m.lo[k]) * m.scale[k]);
+  return (f >= (float)m.G) ? m.G - 1 : ((f > 0.f) ? (int)f : 0);
+}
+
+__global__ void __launch_bounds__(256) nms_grid_range_kernel(const float* __restrict__ boxes, long long n,
+                                                             unsigned int* __restrict__ rng) {
+  unsigned int mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u}, wx[3] = {0u, 0u, 0u};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const Box6 b = load_box(boxes + i * 6);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned int o = float_orderable(b.v[k]);
+      mn[k] = min(mn[k], o);
+      mx[k] = max(mx[k], o);
+      float ext = __fsub_ru(b.v[3 + k], b.v[k]);
+      if (!(ext > 0.f)) ext = 0.f;
+      wx[k] = max(wx[k], __float_as_uint(ext));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const unsigned int a = __reduce_min_sync(0xffffffffu, mn[k]);
+    const unsigned int b = __reduce_max_sync(0xffffffffu, mx[k]);
+    const unsigned int c = __reduce_max_sync(0xffffffffu, wx[k]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&rng[k], a);
+      atomicMax(&rng[3 + k], b);
+      atomicMax(&rng[6 + k], c);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) nms_grid_count_kernel(const float* __restrict__ boxes, long long n,
+                                                             const unsigned int* __restrict__ rng, int G,
+                                                             int* __restrict__ cell_count, int* __restrict__ cell_of) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const GridMap m = load_grid(rng, G);
+  const Box6 b = load_box(boxes + i * 6);
+  const int c = ((box_level(m, b) * G + cell_coord(m, 2, b.v[2])) * G + cell_coord(m, 1, b.v[1])) * G +
+                cell_coord(m, 0, b.v[0]);
+  cell_of[i] = c;
+  atomicAdd(&cell_count[c], 1);
+}
+
+// exclusive scan of the cell counts (one block): cell_start[0..cells], counts reset to 0 for the scatter
+__global__ void __launch_bounds__(1024) nms_grid_scan_kernel(int* __restrict__ cell_count, int cells,
+                                                             int* __restrict__ cell_start) {
+  __shared__ int part[1024];
+  const int per = (cells + 1023) / 1024;
+  const int b0 = threadIdx.x * per, b1 = min(cells, b0 + per);
+  int sum = 0;
+  for (int c = b0; c < b1; ++c) sum += cell_count[c];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - sum;
+  for (int c = b0; c < b1; ++c) {
+    const int v = cell_count[c];
+    cell_start[c] = run;
+    cell_count[c] = 0;
+    run += v;
+  }
+  if (threadIdx.x == 1023) cell_start[cells] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) nms_grid_scatter_kernel(const float* __restrict__ boxes, long long n,
+                                                               const int* __restrict__ cell_start,
+                                                               int* __restrict__ cursor, int* __restrict__ slot_of,
+                                                               float4* __restrict__ sorted) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = slot_of[i];
+  const int slot = cell_start[c] + atomicAdd(&cursor[c], 1);
+  const Box6 b = load_box(boxes + i * 6);
+  sorted[2ll * slot] = make_float4(b.v[0], b.v[1], b.v[2], b.v[3]);
+  sorted[2ll * slot + 1] = make_float4(b.v[4], b.v[5], box_volume(b), 0.f);
+  slot_of[i] = slot;
+}
+
+__global__ void __launch_bounds__(256) nms_cross_grid_kernel(const float* __restrict__ boxes, int n,
+                                                             const unsigned int* __restrict__ rng, int G,
+                                                             const int* __restrict__ cell_start,
+                                                             const float4* __restrict__ sorted,
+                                                             const uint8_t* __restrict__ state, float thr,
+                                                             unsigned int* __restrict__ rem32) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;                                   // whole warp
+  const GridMap m = load_grid(rng, G);
+  const Box6 a = load_box(boxes + (long long)i * 6);
+  const float va = box_volume(a);
+  int chi[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) chi[k] = cell_coord(m, k, a.v[3 + k]);
+  bool found = false;
+  float w = m.W;
+  for (int level = 0; level < NMS_LEVELS && !found; ++level, w *= 0.5f) {
+    // boxes of this and every finer level have volume <= w^3: too small to reach thr against a (1 % margin
+    // over the few-ulp rounding of the exact test; false for NaN / non-positive volumes)
+    if (__fmul_rn(__fmul_rn(__fmul_rn(w, w), w), 1.01f) < __fmul_rn(thr, va)) break;
+    int clo[3], hi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      clo[k] = cell_coord(m, k, __fsub_rd(a.v[k], fminf(w, m.wmax[k])));
+      hi[k] = chi[k] < clo[k] ? clo[k] : chi[k];         // malformed box (max < min): still a valid range
+    }
+    const int ny = hi[1] - clo[1] + 1;
+    const int nrows = ny * (hi[2] - clo[2] + 1);
+    for (int r0 = 0; r0 < nrows && !found; r0 += 32) {
+      // every lane fetches the slot range of one (y, z) row; the warp then walks the rows one by one
+      int my_begin = 0, my_end = 0;
+      const int r = r0 + lane;
+      if (r < nrows) {
+        const int cz = clo[2] + r / ny, cy = clo[1] + r % ny;
+        const int base = ((level * G + cz) * G + cy) * G;
+        my_begin = cell_start[base + clo[0]];
+        my_end = cell_start[base + hi[0] + 1];
+      }
+      const int nr = min(32, nrows - r0);
+      for (int t = 0; t < nr && !found; ++t) {
+        const int begin = __shfl_sync(0xffffffffu, my_begin, t);
+        const int end = __shfl_sync(0xffffffffu, my_end, t);
+        if (begin == end) continue;
+        bool hit = false;
+        int k = begin + lane;
+        uint8_t s_next = (k < end) ? state[k] : (uint8_t)0;
+        while (k < end) {
+          const uint8_t s = s_next;
+          const int kn = k + 32;
+          s_next = (kn < end) ? state[kn] : (uint8_t)0;
+          if (s && !hit) {
+            const float4 p = sorted[2ll * k], q = sorted[2ll * k + 1];
+            Box6 o;
+            o.v[0] = p.x; o.v[1] = p.y; o.v[2] = p.z; o.v[3] = p.w; o.v[4] = q.x; o.v[5] = q.y;
+            const float inter = box_intersection(a, o);
+            const float uni = __fsub_rn(__fadd_rn(va, q.z), inter);
+            hit = iou_exceeds(inter, uni, thr);
+          }
+          k = kn;
+        }
+        found = __any_sync(0xffffffffu, hit);
+      }
+    }
+  }
+  if (lane == 0 && found) atomicOr(&rem32[i >> 5], 1u << (i & 31));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -664,20 +875,30 @@ extern "C" int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_o
 // ---- chunked NMS / long sort / filter stage entry points ------------------------------------------
 namespace ssd3d {
 struct ChunkedNmsLayout {
-  int chunk;
-  long long off_removed, off_nk, off_kept, off_mask, total;
+  int chunk, G, cells;
+  long long off_removed, off_nk, off_rng, off_kept, off_mask, off_cellstart, off_cursor, off_sorted, off_slot, off_state,
+      total;
 };
 static ChunkedNmsLayout chunked_nms_layout(long long n, int chunk) {
   ChunkedNmsLayout L;
-  if (chunk <= 0) chunk = 4096;
+  if (chunk <= 0) chunk = (n >= 1500000) ? 8192 : 4096;
   L.chunk = chunk;
+  int G = (int)cbrt((double)n / 8.0);
+  L.G = G < 1 ? 1 : (G > 64 ? 64 : G);
+  L.cells = NMS_LEVELS * L.G * L.G * L.G;
   const long long cw = chunk / 64;
   const long long chunks = (n + chunk - 1) / chunk;
   long long o = 0;
   L.off_removed = o; o += align256(8ll * chunks * cw);
   L.off_nk = o; o += 256;
+  L.off_rng = o; o += 256;
   L.off_kept = o; o += align256(32ll * n);
   L.off_mask = o; o += align256(8ll * chunk * cw);
+  L.off_cellstart = o; o += align256(4ll * (L.cells + 1));
+  L.off_cursor = o; o += align256(4ll * L.cells);
+  L.off_sorted = o; o += align256(32ll * n);
+  L.off_slot = o; o += align256(4ll * n);
+  L.off_state = o; o += align256(n);
   L.total = o;
   return L;
 }
@@ -685,26 +906,51 @@ static inline bool chunk_ok(int chunk) { return chunk == 0 || (chunk >= 64 && ch
 }  // namespace ssd3d
 
 extern "C" int64_t ssd3d_nms3d_chunked_workspace_bytes(int64_t n, int chunk) {
-  if (n <= 0 || !chunk_ok(chunk)) return 0;
+  if (n <= 0 || n > 0x7fffffffll || !chunk_ok(chunk)) return 0;
   return chunked_nms_layout(n, chunk).total;
 }
 
 extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, float max_overlap, uint8_t* keep,
                                           int64_t* kept_count, void* workspace, int64_t workspace_bytes, int chunk,
-                                          void* stream) {
-  if (!boxes_xyz || !keep || !workspace || n <= 0 || !chunk_ok(chunk)) return SSD3D_ERR_ARG;
+                                          int flags, void* stream) {
+  if (!boxes_xyz || !keep || !workspace || n <= 0 || n > 0x7fffffffll || !chunk_ok(chunk)) return SSD3D_ERR_ARG;
   const ChunkedNmsLayout L = chunked_nms_layout(n, chunk);
   if (workspace_bytes < L.total) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   unsigned long long* removed = reinterpret_cast<unsigned long long*>(ws + L.off_removed);
   long long* nk = reinterpret_cast<long long*>(ws + L.off_nk);
+  unsigned int* rng = reinterpret_cast<unsigned int*>(ws + L.off_rng);
   float4* kept = reinterpret_cast<float4*>(ws + L.off_kept);
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + L.off_mask);
-  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)L.off_kept, st);      // removed bits + kept counter
+  int* cell_start = reinterpret_cast<int*>(ws + L.off_cellstart);
+  int* cursor = reinterpret_cast<int*>(ws + L.off_cursor);
+  float4* sorted = reinterpret_cast<float4*>(ws + L.off_sorted);
+  int* slot_of = reinterpret_cast<int*>(ws + L.off_slot);
+  uint8_t* state = ws + L.off_state;
+  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)L.off_kept, st);      // removed bits, kept counter, grid range
   if (e != cudaSuccess) return (int)e;
   const int B = L.chunk, cw = B / 64;
   const long long chunks = (n + B - 1) / B;
+  // The grid only helps when disjoint boxes cannot suppress each other (threshold >= 0; NaN compares false).
+  const bool use_grid = chunks > 1 && max_overlap >= 0.0f && !(flags & SSD3D_NMS_NO_GRID);
+  if (use_grid) {
+    e = cudaMemsetAsync(rng, 0xff, 12, st);                            // running minima start at the top
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(cursor, 0, (size_t)L.cells * 4, st);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(state, 0, (size_t)n, st);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    nms_grid_range_kernel<<<nb < 1184u ? nb : 1184u, 256, 0, st>>>(boxes_xyz, (long long)n, rng);
+    SSD3D_CHECK_LAUNCH();
+    nms_grid_count_kernel<<<nb, 256, 0, st>>>(boxes_xyz, (long long)n, rng, L.G, cursor, slot_of);
+    SSD3D_CHECK_LAUNCH();
+    nms_grid_scan_kernel<<<1, 1024, 0, st>>>(cursor, L.cells, cell_start);
+    SSD3D_CHECK_LAUNCH();
+    nms_grid_scatter_kernel<<<nb, 256, 0, st>>>(boxes_xyz, (long long)n, cell_start, cursor, slot_of, sorted);
+    SSD3D_CHECK_LAUNCH();
+  }
   const int splits = 74;                    // x (B / 256) row blocks: 1184 = 148 x 8 CTAs at B = 4096
   for (long long c = 0; c < chunks; ++c) {
     const long long first = c * B;
@@ -712,7 +958,11 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
     const int words = (rows + 63) / 64;
     const float* cb = boxes_xyz + first * 6;
     unsigned long long* crem = removed + c * cw;
-    if (c > 0) {
+    if (c > 0 && use_grid) {
+      nms_cross_grid_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cb, rows, rng, L.G, cell_start, sorted, state,
+                                                                       max_overlap, reinterpret_cast<unsigned int*>(crem));
+      SSD3D_CHECK_LAUNCH();
+    } else if (c > 0) {
       dim3 grid((unsigned)((rows + 255) / 256), (unsigned)splits);
       nms_cross_kernel<<<grid, 256, 0, st>>>(cb, rows, kept, nk, max_overlap, reinterpret_cast<unsigned int*>(crem));
       SSD3D_CHECK_LAUNCH();
@@ -721,7 +971,8 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
     nms_mask_kernel<<<mgrid, 64, 0, st>>>(cb, nullptr, rows, 0, words, 0, max_overlap, mask);
     SSD3D_CHECK_LAUNCH();
     const size_t smem = (size_t)(2 * words) * 8 + (size_t)(words + 2) * 4;
-    nms_chunk_scan_kernel<<<1, 1024, smem, st>>>(mask, cb, rows, words, crem, kept, nk, keep + first);
+    nms_chunk_scan_kernel<<<1, 1024, smem, st>>>(mask, cb, rows, words, crem, kept, nk, keep + first,
+                                                 use_grid ? slot_of + first : (const int*)nullptr, state);
     SSD3D_CHECK_LAUNCH();
   }
   if (kept_count) {

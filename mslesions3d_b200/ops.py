@@ -266,9 +266,10 @@ def nms3d_sorted(boxes_xyz: torch.Tensor, max_overlap: float) -> torch.Tensor:
 
 
 def nms3d_sorted_chunked(boxes_xyz: torch.Tensor, max_overlap: float, chunk: int = 0,
-                         return_count: bool = False):
+                         return_count: bool = False, use_grid: bool = True):
     """Greedy NMS over a score-sorted list of any length (ssd3d.py:407-426): chunks of ``chunk`` boxes
-    (0 = the library default), each tested against the kept list first, then resolved with the bit matrix.
+    (0 = the library default), each tested against the boxes kept so far (found through a uniform grid when
+    ``max_overlap >= 0`` and ``use_grid``, else the whole kept list), then resolved with the bit matrix.
     -> bool keep mask (and the device int64 kept count)."""
     boxes_xyz = _boxes(boxes_xyz, "boxes")
     n = boxes_xyz.shape[0]
@@ -283,10 +284,11 @@ def nms3d_sorted_chunked(boxes_xyz: torch.Tensor, max_overlap: float, chunk: int
         raise ValueError("nms3d_sorted_chunked: chunk must be 0 or a multiple of 64 in [64, %d]" % _lib.SORT_MAX)
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     rc = lib.ssd3d_nms3d_sorted_chunked(boxes_xyz.data_ptr(), n, f32(max_overlap), keep.data_ptr(), count.data_ptr(),
-                                        ws.data_ptr(), need, int(chunk), _stream())
+                                        ws.data_ptr(), need, int(chunk), 0 if use_grid else _lib.NMS_NO_GRID,
+                                        _stream())
     _lib.check(rc, "ssd3d_nms3d_sorted_chunked")
-    per = int(chunk) if chunk else 4096
-    LAUNCHES[0] += 3 * ((n + per - 1) // per) - 1
+    per = int(chunk) if chunk else (8192 if n >= 1500000 else 4096)
+    LAUNCHES[0] += 3 * ((n + per - 1) // per) - 1 + (4 if use_grid and n > per else 0)
     return (keep.bool(), count) if return_count else keep.bool()
 
 

@@ -64,6 +64,10 @@ for n in (1000, 4000, 16000, 64000, 256000, 1000000, 2500000):
     row = dict(n=n, us=us, kept=kept, candidates_per_s=n / us * 1e6, algorithmic_MB=n * 36 / 1e6,
                GBs=n * 36 / us / 1e3, frac_hbm=n * 36 / us / 1e3 / peak,
                iou_tests_upper_bound=float(n) * kept / 2, reference_iou_matrix_GB=4.0 * n * n / 1e9)
+    if n >= 64000:
+        row["dense_cross_us"] = gpu_us(lambda: ops.nms3d_sorted_chunked(boxes, 0.5, 4096, use_grid=False), 1)
+        for ch in (4096, 8192, 16384):
+            row["grid_chunk%d_us" % ch] = gpu_us(lambda: ops.nms3d_sorted_chunked(boxes, 0.5, ch), args.reps)
     if n <= 131072:
         row["bit_matrix_us"] = gpu_us(lambda: ops.nms3d_sorted(boxes, 0.5), args.reps)
     if not args.no_cpu and n <= 16000:
@@ -72,9 +76,10 @@ for n in (1000, 4000, 16000, 64000, 256000, 1000000, 2500000):
         row["cpu_us"] = (time.perf_counter() - t0) * 1e6
         row["exact_vs_cpu"] = bool(torch.equal(want, keep.cpu()))
     out["nms_full"].append(row)
-    print("n=%8d  %11.1f us  kept %8d  %.3g cand/s  bit-matrix %s us  cpu %s us  %s" % (
+    print("n=%8d  %11.1f us  kept %8d  %.3g cand/s  bit-matrix %s us  cpu %s us  %s  %s" % (
         n, us, kept, row["candidates_per_s"], "%.0f" % row["bit_matrix_us"] if "bit_matrix_us" in row else "-",
-        "%.0f" % row["cpu_us"] if "cpu_us" in row else "-", row.get("exact_vs_cpu", "")), flush=True)
+        "%.0f" % row["cpu_us"] if "cpu_us" in row else "-", row.get("exact_vs_cpu", ""),
+        " ".join("%s=%.0f" % (k, v) for k, v in row.items() if k.startswith(("grid_chunk", "dense_cross")))), flush=True)
     del boxes, keep
 
 print("== 64-bit key sort (block bitonic + merge passes) ==")

@@ -66,13 +66,34 @@ def test_chunked_nms_keep_mask_bit_exact_vs_oracle(n, thr, dup, chunk):
     ops = _ops()
     g = torch.Generator().manual_seed(n + chunk)
     boxes = _dense_boxes(n, g, extent=0.3 if n >= 1000 else 0.15, dup=dup)
-    keep, count = ops.nms3d_sorted_chunked(boxes.cuda(), thr, chunk, return_count=True)
     want = O.greedy_nms(boxes, ops.f32(thr))
-    keep = keep.cpu()
-    assert torch.equal(keep, want), "keep masks differ at %d positions" % int((keep != want).sum())
-    assert int(count.item()) == int(want.sum()) and bool(keep[0])
+    for use_grid in (True, False):                          # grid-pruned and dense cross test
+        keep, count = ops.nms3d_sorted_chunked(boxes.cuda(), thr, chunk, return_count=True, use_grid=use_grid)
+        keep = keep.cpu()
+        assert torch.equal(keep, want), "grid=%s: keep masks differ at %d positions" % (use_grid, int((keep != want).sum()))
+        assert int(count.item()) == int(want.sum()) and bool(keep[0])
     if n >= 1000:
         assert 0.05 * n < int(want.sum()) < 0.95 * n       # the case really exercises suppression
+
+
+@pytest.mark.parametrize("thr", [0.0, -0.25, 0.5])
+def test_chunked_nms_threshold_edge_and_arbitrary_coordinates(thr):
+    """thr = 0: touching boxes (intersection 0) survive; thr < 0: even disjoint boxes suppress each other (the
+    grid must not be used); coordinates far outside [0, 1] (voxel units, negative offsets) map onto the grid."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    boxes = _dense_boxes(6000, g, extent=0.3) * 37.0 - 11.0
+    boxes[100:200] = boxes[:100]                            # exact duplicates
+    lattice = torch.arange(0, 500, dtype=torch.float32)[:, None] * torch.tensor([1., 0, 0, 1., 0, 0]) + \
+        torch.tensor([40., 40, 40, 41, 41, 41])             # 500 unit cubes in a row, each touching the next
+    boxes = torch.cat([boxes, lattice]).contiguous()
+    want = O.greedy_nms(boxes, ops.f32(thr))
+    keep = ops.nms3d_sorted_chunked(boxes.cuda(), thr, 512).cpu()
+    assert torch.equal(keep, want), "%d differences" % int((keep != want).sum())
+    if thr == 0.0:
+        assert bool(want[-500:].all())
+    if thr < 0:
+        assert int(want.sum()) == 1
 
 
 def test_chunked_nms_matches_bit_matrix_at_100k():
@@ -80,9 +101,9 @@ def test_chunked_nms_matches_bit_matrix_at_100k():
     g = torch.Generator().manual_seed(7)
     boxes = _dense_boxes(100000, g, extent=0.5, dup=500).cuda()
     want = ops.nms3d_sorted(boxes, 0.5)                     # pinned by the oracle in test_gpu_detect.py
-    for chunk in (0, 16384, 1984):
-        keep = ops.nms3d_sorted_chunked(boxes, 0.5, chunk)
-        assert torch.equal(keep, want), "chunk %d: %d differences" % (chunk, int((keep != want).sum()))
+    for chunk, use_grid in ((0, True), (16384, True), (1984, True), (4096, False)):
+        keep = ops.nms3d_sorted_chunked(boxes, 0.5, chunk, use_grid=use_grid)
+        assert torch.equal(keep, want), "chunk %d grid %s: %d differences" % (chunk, use_grid, int((keep != want).sum()))
     assert 0.05 < float(want.float().mean()) < 0.95
 
 
@@ -98,6 +119,8 @@ def test_chunked_nms_full_size_properties():
     keep, count = ops.nms3d_sorted_chunked(boxes, 0.5, return_count=True)
     kept = int(keep.sum().item())
     assert int(count.item()) == kept and 0 < kept < n and bool(keep[0])
+    dense = ops.nms3d_sorted_chunked(boxes, 0.5, 4096, use_grid=False)
+    assert torch.equal(keep, dense), "grid-pruned and dense cross tests differ at %d boxes" % int((keep != dense).sum())
     m = 50000                                               # the first m decisions do not depend on the rest
     assert torch.equal(keep[:m], ops.nms3d_sorted(boxes[:m].contiguous(), 0.5))
     again = ops.nms3d_sorted_chunked(boxes[keep].contiguous(), 0.5)
