@@ -190,10 +190,11 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float uni, float thr) {
   return __fdiv_rn(inter, uni) > thr;
 }
 
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sboxes, const int* __restrict__ nkeep,
-                                                      int n_fixed, long long seg_stride_boxes, int words,
-                                                      long long seg_stride_mask, float thr,
-                                                      unsigned long long* __restrict__ mask) {
+template <bool TR>
+__device__ __forceinline__ void nms_mask_body(const float* __restrict__ sboxes, const int* __restrict__ nkeep,
+                                              int n_fixed, long long seg_stride_boxes, int words,
+                                              long long seg_stride_mask, float thr,
+                                              unsigned long long* __restrict__ mask) {
   pdl_wait();
   pdl_launch_dependents();
   const int cb = blockIdx.x, rb = blockIdx.y, seg = blockIdx.z;
@@ -227,7 +228,21 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
     if (iou_exceeds(inter, uni, thr)) bits |= (1ull << b);
   }
   if (cb == rb) bits &= ~(1ull << t);       // a box does not suppress itself (ssd3d.py:425-426)
-  mask[(long long)seg * seg_stride_mask + (long long)i * words + cb] = bits;
+  // TR: word-major layout [word][row] with `words` = rows per word-row (coalesced for the chunk scan)
+  if (TR) mask[(long long)seg * seg_stride_mask + (long long)cb * words + i] = bits;
+  else mask[(long long)seg * seg_stride_mask + (long long)i * words + cb] = bits;
+}
+
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sboxes, const int* __restrict__ nkeep,
+                                                      int n_fixed, long long seg_stride_boxes, int words,
+                                                      long long seg_stride_mask, float thr,
+                                                      unsigned long long* __restrict__ mask) {
+  nms_mask_body<false>(sboxes, nkeep, n_fixed, seg_stride_boxes, words, seg_stride_mask, thr, mask);
+}
+// same bits, stored word-major: mask[word * row_stride + row] (row_stride passed in `words`)
+__global__ void __launch_bounds__(64) nms_mask_tr_kernel(const float* __restrict__ sboxes, int n, int row_stride,
+                                                         float thr, unsigned long long* __restrict__ mask) {
+  nms_mask_body<true>(sboxes, nullptr, n, 0, row_stride, 0, thr, mask);
 }
 
 // Greedy scan of one segment's bit matrix M (rows `stride` words apart; shared or global memory).
@@ -500,8 +515,84 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
   if ((threadIdx.x & 31) == 0 && ballot != 0u) atomicOr(&rem32[i >> 5], ballot);
 }
 
+// The greedy scan of nms_scan_core on the word-major matrix MT[word * stride + row]: the 64 diagonal words of
+// a step and the 64 rows OR-ed into a later word are contiguous (one 512-byte request instead of 64 sectors),
+// the diagonal words of step k+1 are fetched while step k is being resolved, and a warp has the loads of
+// four later words in flight at once.  Rows past n hold garbage that the kept bits mask out.
+__device__ __forceinline__ void nms_scan_core_tr(const unsigned long long* __restrict__ MT, int n, int stride,
+                                                 unsigned long long* removed, unsigned long long* keptw,
+                                                 const unsigned long long* __restrict__ removed_init) {
+  const int words = (n + 63) >> 6;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = removed_init ? removed_init[w] : 0ull;
+  unsigned long long r0n = 0ull, r1n = 0ull;
+  if (warp == 0) {
+    r0n = MT[lane];
+    r1n = MT[lane + 32];
+  }
+  __syncthreads();
+  for (int k = 0; k < words; ++k) {
+    const int rows = min(64, n - k * 64);
+    if (warp == 0) {
+      const unsigned long long r0 = (lane < rows) ? r0n : 0ull;
+      const unsigned long long r1 = (lane + 32 < rows) ? r1n : 0ull;
+      if (k + 1 < words) {
+        const long long d = (long long)(k + 1) * stride + (k + 1) * 64;
+        r0n = MT[d + lane];
+        r1n = MT[d + lane + 32];
+      }
+      const unsigned long long e0 = r0 & ((1ull << lane) - 1ull);
+      const unsigned long long e1 = r1 & ((1ull << (lane + 32)) - 1ull);
+      unsigned long long rem = removed[k];
+      if (rows < 64) rem |= (~0ull) << rows;            // rows past the end are never kept
+      unsigned long long und = ~rem, kept = 0ull;
+      while (und != 0ull) {
+        const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
+        const bool x0 = u0 && (e0 & kept) != 0ull, x1 = u1 && (e1 & kept) != 0ull;
+        const bool k0 = u0 && !x0 && (e0 & und) == 0ull, k1 = u1 && !x1 && (e1 & und) == 0ull;
+        const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+        const unsigned long long nx = (unsigned long long)__ballot_sync(0xffffffffu, x0) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, x1) << 32);
+        kept |= nk;
+        und &= ~(nk | nx);
+      }
+      if (lane == 0) keptw[k] = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = keptw[k];
+    if (kept != 0ull) {
+      const unsigned long long m0 = ((kept >> lane) & 1ull) ? ~0ull : 0ull;
+      const unsigned long long m1 = ((kept >> (lane + 32)) & 1ull) ? ~0ull : 0ull;
+      for (int w0 = k + 1 + warp; w0 < words; w0 += 4 * nwarps) {
+        unsigned long long v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int w = w0 + u * nwarps;
+          v[u] = 0ull;
+          if (w < words) {
+            const unsigned long long* row = MT + (long long)w * stride + k * 64;
+            v[u] = (row[lane] & m0) | (row[lane + 32] & m1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int w = w0 + u * nwarps;
+          if (w < words) {
+            const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)v[u]);
+            const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(v[u] >> 32));
+            if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(1024) nms_chunk_scan_kernel(const unsigned long long* __restrict__ mask,
                                                               const float* __restrict__ boxes, int n, int words,
+                                                              int stride,
                                                               const unsigned long long* __restrict__ removed_init,
                                                               float4* __restrict__ kept, long long* __restrict__ nk_ptr,
                                                               uint8_t* __restrict__ keep,
@@ -512,7 +603,7 @@ __global__ void __launch_bounds__(1024) nms_chunk_scan_kernel(const unsigned lon
   unsigned long long* keptw = sm + words;
   int* prefix = reinterpret_cast<int*>(sm + 2 * words);
   __shared__ long long s_base;
-  nms_scan_core(mask, n, words, removed, keptw, removed_init);
+  nms_scan_core_tr(mask, n, stride, removed, keptw, removed_init);
   __syncthreads();
   if (threadIdx.x == 0) {
     int run = 0;
@@ -692,9 +783,22 @@ __global__ void __launch_bounds__(256) nms_cross_grid_kernel(const float* __rest
   const GridMap m = load_grid(rng, G);
   const Box6 a = load_box(boxes + (long long)i * 6);
   const float va = box_volume(a);
+  // IoU > thr needs, on every axis, overlap_k > thr * extent_k(a) (inter / vol(a) <= overlap_k / extent_k), i.e.
+  //   o.min_k < a.max_k - s_k   and   o.max_k > a.min_k + s_k,   s_k = thr' * extent_k(a)
+  // with thr' = thr (1 - 1e-4): the margin dwarfs the few-ulp difference between the exact fp32 test and real
+  // arithmetic; s_k is rounded down and the bounds outwards.  No shrink for volumes near the denormal range.
+  float sh[3] = {0.f, 0.f, 0.f};
+  if (thr > 0.f && va > 1e-20f) {
+    const float thr1 = __fmul_rd(thr, 0.9999f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float ext = __fsub_rd(a.v[3 + k], a.v[k]);
+      sh[k] = ext > 0.f ? __fmul_rd(thr1, ext) : 0.f;
+    }
+  }
   int chi[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) chi[k] = cell_coord(m, k, a.v[3 + k]);
+  for (int k = 0; k < 3; ++k) chi[k] = cell_coord(m, k, __fsub_ru(a.v[3 + k], sh[k]));
   bool found = false;
   float w = m.W;
   for (int level = 0; level < NMS_LEVELS && !found; ++level, w *= 0.5f) {
@@ -704,7 +808,7 @@ __global__ void __launch_bounds__(256) nms_cross_grid_kernel(const float* __rest
     int clo[3], hi[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      clo[k] = cell_coord(m, k, __fsub_rd(a.v[k], fminf(w, m.wmax[k])));
+      clo[k] = cell_coord(m, k, __fsub_rd(__fadd_rd(a.v[k], sh[k]), fminf(w, m.wmax[k])));
       hi[k] = chi[k] < clo[k] ? clo[k] : chi[k];         // malformed box (max < min): still a valid range
     }
     const int ny = hi[1] - clo[1] + 1;
@@ -968,10 +1072,10 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
       SSD3D_CHECK_LAUNCH();
     }
     dim3 mgrid((unsigned)words, (unsigned)words, 1);
-    nms_mask_kernel<<<mgrid, 64, 0, st>>>(cb, nullptr, rows, 0, words, 0, max_overlap, mask);
+    nms_mask_tr_kernel<<<mgrid, 64, 0, st>>>(cb, rows, B, max_overlap, mask);
     SSD3D_CHECK_LAUNCH();
     const size_t smem = (size_t)(2 * words) * 8 + (size_t)(words + 2) * 4;
-    nms_chunk_scan_kernel<<<1, 1024, smem, st>>>(mask, cb, rows, words, crem, kept, nk, keep + first,
+    nms_chunk_scan_kernel<<<1, 1024, smem, st>>>(mask, cb, rows, words, B, crem, kept, nk, keep + first,
                                                  use_grid ? slot_of + first : (const int*)nullptr, state);
     SSD3D_CHECK_LAUNCH();
   }

@@ -204,3 +204,37 @@ def test_model_detect_objects_routes_long_lists():
     wb, wl, ws, widx = O.detect_from_decoded(probs.cpu(), boxes.cpu(), 0.0, _ops().f32(0.5), 50000, return_indices=True)
     assert torch.equal(idx[0].cpu(), widx[0]) and torch.equal(s[0].cpu(), ws[0]) and torch.equal(b[0].cpu(), wb[0])
     assert torch.equal(pb[0], b[0]) and torch.equal(pl[0], l[0]) and torch.equal(ps[0], s[0])
+
+
+def _slice_cases(thr):
+    """Adversarial pairs for the pruned search range: o is a slab of a (so IoU = the slab fraction f) flush with
+    one face of a, f a few ulp either side of thr.  All slabs come first (kept), the big boxes later."""
+    g = torch.Generator().manual_seed(int(thr * 1000) + 1)
+    n = 600
+    idx = torch.arange(n)
+    lo = torch.stack([(idx % 10) * 3.0, ((idx // 10) % 10) * 3.0, (idx // 100) * 3.0], 1) + torch.rand(n, 3, generator=g)
+    ext = 0.5 + 1.5 * torch.rand(n, 3, generator=g)
+    a = torch.cat([lo, lo + ext], 1)
+    f = thr * (1.0 + (torch.randint(-3, 4, (n,), generator=g).float() * 1.5e-6))
+    axis = torch.randint(0, 3, (n,), generator=g)
+    right = torch.rand(n, generator=g) < 0.5
+    o = a.clone()
+    for i in range(n):
+        k = int(axis[i])
+        if bool(right[i]):
+            o[i, k] = a[i, 3 + k] - f[i] * ext[i, k]
+        else:
+            o[i, 3 + k] = a[i, k] + f[i] * ext[i, k]
+    return torch.cat([o, a]).contiguous()
+
+
+@pytest.mark.parametrize("thr", [0.5, 0.25, 0.7])
+def test_chunked_nms_pruned_range_is_conservative_at_the_threshold(thr):
+    ops = _ops()
+    boxes = _slice_cases(thr)
+    want = O.greedy_nms(boxes, ops.f32(thr))
+    n_removed = int((~want).sum())
+    assert 100 < n_removed < 500                            # both outcomes occur
+    for chunk in (64, 256):
+        keep = ops.nms3d_sorted_chunked(boxes.cuda(), thr, chunk).cpu()
+        assert torch.equal(keep, want), "chunk %d: %d differences" % (chunk, int((keep != want).sum()))
