@@ -157,8 +157,8 @@ int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_overlap, uin
  * With max_overlap >= 0 the cross test is pruned by a uniform grid over the boxes' minimum corners (only
  * intersecting boxes can suppress each other); SSD3D_NMS_NO_GRID in `flags` forces the dense cross test.
  * Same keep decisions as ssd3d_nms3d_sorted, bit for bit.  keep (n) uint8; kept_count (device int64, may
- * be NULL) receives the number of kept boxes; no host synchronisation.  chunk = 0: 4096, or 8192 from
- * n = 1.5 M on (measured optimum). */
+ * be NULL) receives the number of kept boxes; no host synchronisation.  chunk = 0: 4096 (the measured
+ * optimum from 64 k to 2.5 M candidates). */
 #define SSD3D_NMS_NO_GRID 1
 int64_t ssd3d_nms3d_chunked_workspace_bytes(int64_t n, int chunk);
 int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, float max_overlap, uint8_t* keep,

@@ -517,8 +517,9 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
 
 // The greedy scan of nms_scan_core on the word-major matrix MT[word * stride + row]: the 64 diagonal words of
 // a step and the 64 rows OR-ed into a later word are contiguous (one 512-byte request instead of 64 sectors),
-// the diagonal words of step k+1 are fetched while step k is being resolved, and a warp has the loads of
-// four later words in flight at once.  Rows past n hold garbage that the kept bits mask out.
+// and both are fetched one step ahead (the addresses do not depend on the step's outcome), so the serial chain
+// per 64 boxes is resolve -> barrier -> warp OR-reductions -> barrier with no exposed memory latency.  Rows
+// past n hold garbage that the kept bits mask out.
 __device__ __forceinline__ void nms_scan_core_tr(const unsigned long long* __restrict__ MT, int n, int stride,
                                                  unsigned long long* removed, unsigned long long* keptw,
                                                  const unsigned long long* __restrict__ removed_init) {
@@ -529,6 +530,19 @@ __device__ __forceinline__ void nms_scan_core_tr(const unsigned long long* __res
   if (warp == 0) {
     r0n = MT[lane];
     r1n = MT[lane + 32];
+  }
+  // rows of step k for this warp's words k+1+warp+u*nwarps, fetched one step ahead (the addresses do not
+  // depend on the outcome of the step, only the masks do)
+  unsigned long long c0[4], c1[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int w = 1 + warp + u * nwarps;
+    c0[u] = c1[u] = 0ull;
+    if (w < words) {
+      const unsigned long long* row = MT + (long long)w * stride;
+      c0[u] = row[lane];
+      c1[u] = row[lane + 32];
+    }
   }
   __syncthreads();
   for (int k = 0; k < words; ++k) {
@@ -561,30 +575,42 @@ __device__ __forceinline__ void nms_scan_core_tr(const unsigned long long* __res
     }
     __syncthreads();
     const unsigned long long kept = keptw[k];
+    unsigned long long n0[4], n1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                       // next step's rows: in flight during the reductions
+      const int w = k + 2 + warp + u * nwarps;
+      n0[u] = n1[u] = 0ull;
+      if (w < words) {
+        const unsigned long long* row = MT + (long long)w * stride + (k + 1) * 64;
+        n0[u] = row[lane];
+        n1[u] = row[lane + 32];
+      }
+    }
     if (kept != 0ull) {
       const unsigned long long m0 = ((kept >> lane) & 1ull) ? ~0ull : 0ull;
       const unsigned long long m1 = ((kept >> (lane + 32)) & 1ull) ? ~0ull : 0ull;
-      for (int w0 = k + 1 + warp; w0 < words; w0 += 4 * nwarps) {
-        unsigned long long v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int w = w0 + u * nwarps;
-          v[u] = 0ull;
-          if (w < words) {
-            const unsigned long long* row = MT + (long long)w * stride + k * 64;
-            v[u] = (row[lane] & m0) | (row[lane + 32] & m1);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int w = w0 + u * nwarps;
-          if (w < words) {
-            const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)v[u]);
-            const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(v[u] >> 32));
-            if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
-          }
+      for (int u = 0; u < 4; ++u) {
+        const int w = k + 1 + warp + u * nwarps;
+        if (w < words) {
+          const unsigned long long v = (c0[u] & m0) | (c1[u] & m1);
+          const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)v);
+          const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(v >> 32));
+          if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
         }
       }
+      for (int w = k + 1 + warp + 4 * nwarps; w < words; w += nwarps) {   // chunks beyond 4 * nwarps words
+        const unsigned long long* row = MT + (long long)w * stride + k * 64;
+        const unsigned long long v = (row[lane] & m0) | (row[lane + 32] & m1);
+        const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)v);
+        const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(v >> 32));
+        if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      c0[u] = n0[u];
+      c1[u] = n1[u];
     }
     __syncthreads();
   }
@@ -731,30 +757,44 @@ __global__ void __launch_bounds__(256) nms_grid_count_kernel(const float* __rest
   atomicAdd(&cell_count[c], 1);
 }
 
-// exclusive scan of the cell counts (one block): cell_start[0..cells], counts reset to 0 for the scatter
+// exclusive scan of the cell counts (one block, 1024 cells per pass): cell_start[0..cells], counts reset to 0
+// for the scatter
 __global__ void __launch_bounds__(1024) nms_grid_scan_kernel(int* __restrict__ cell_count, int cells,
                                                              int* __restrict__ cell_start) {
-  __shared__ int part[1024];
-  const int per = (cells + 1023) / 1024;
-  const int b0 = threadIdx.x * per, b1 = min(cells, b0 + per);
-  int sum = 0;
-  for (int c = b0; c < b1; ++c) sum += cell_count[c];
-  part[threadIdx.x] = sum;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const int v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0;
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int carry = 0;
+  for (int base = 0; base < cells; base += 1024) {
+    const int c = base + threadIdx.x;
+    const int v = (c < cells) ? cell_count[c] : 0;
+    int x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
     __syncthreads();
-    part[threadIdx.x] += v;
+    if (warp == 0) {
+      int t = wsum[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, t, off);
+        if (lane >= off) t += y;
+      }
+      wsum[lane] = t;
+    }
+    __syncthreads();
+    const int before = (warp > 0 ? wsum[warp - 1] : 0) + x - v;
+    const int total = wsum[31];
+    if (c < cells) {
+      cell_start[c] = carry + before;
+      cell_count[c] = 0;
+    }
+    carry += total;
     __syncthreads();
   }
-  int run = part[threadIdx.x] - sum;
-  for (int c = b0; c < b1; ++c) {
-    const int v = cell_count[c];
-    cell_start[c] = run;
-    cell_count[c] = 0;
-    run += v;
-  }
-  if (threadIdx.x == 1023) cell_start[cells] = part[1023];
+  if (threadIdx.x == 0) cell_start[cells] = carry;
 }
 
 __global__ void __launch_bounds__(256) nms_grid_scatter_kernel(const float* __restrict__ boxes, long long n,
@@ -985,7 +1025,7 @@ struct ChunkedNmsLayout {
 };
 static ChunkedNmsLayout chunked_nms_layout(long long n, int chunk) {
   ChunkedNmsLayout L;
-  if (chunk <= 0) chunk = (n >= 1500000) ? 8192 : 4096;
+  if (chunk <= 0) chunk = 4096;                          // measured optimum from 64 k to 2.5 M candidates
   L.chunk = chunk;
   int G = (int)cbrt((double)n / 8.0);
   L.G = G < 1 ? 1 : (G > 64 ? 64 : G);

@@ -287,7 +287,7 @@ def nms3d_sorted_chunked(boxes_xyz: torch.Tensor, max_overlap: float, chunk: int
                                         ws.data_ptr(), need, int(chunk), 0 if use_grid else _lib.NMS_NO_GRID,
                                         _stream())
     _lib.check(rc, "ssd3d_nms3d_sorted_chunked")
-    per = int(chunk) if chunk else (8192 if n >= 1500000 else 4096)
+    per = int(chunk) if chunk else 4096
     LAUNCHES[0] += 3 * ((n + per - 1) // per) - 1 + (4 if use_grid and n > per else 0)
     return (keep.bool(), count) if return_count else keep.bool()
 
