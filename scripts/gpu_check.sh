@@ -19,6 +19,7 @@ run pw       tests/test_gpu_network.py -k "pointwise"
 run head     tests/test_gpu_network.py -k "head"
 run forward  tests/test_gpu_network.py -k "forward"
 run detect   tests/test_gpu_detect.py
+run nmslong  tests/test_gpu_nms_long.py
 run match    tests/test_gpu_match_loss.py
 run train    tests/test_gpu_train.py
 run metrics  tests/test_gpu_metrics.py
