@@ -194,7 +194,8 @@ template <bool TR>
 __device__ __forceinline__ void nms_mask_body(const float* __restrict__ sboxes, const int* __restrict__ nkeep,
                                               int n_fixed, long long seg_stride_boxes, int words,
                                               long long seg_stride_mask, float thr,
-                                              unsigned long long* __restrict__ mask) {
+                                              unsigned long long* __restrict__ mask,
+                                              unsigned long long* __restrict__ block_flags, int flag_words) {
   pdl_wait();
   pdl_launch_dependents();
   const int cb = blockIdx.x, rb = blockIdx.y, seg = blockIdx.z;
@@ -214,35 +215,44 @@ __device__ __forceinline__ void nms_mask_body(const float* __restrict__ sboxes, 
   }
   __syncthreads();
   const int i = rb * 64 + t;
-  if (i >= n) return;
-  const Box6 a = load_box(base + (long long)i * 6);
-  const float va = box_volume(a);
-  const int jn = min(64, n - cb * 64);
   unsigned long long bits = 0ull;
-  for (int b = 0; b < jn; ++b) {
-    Box6 o;
+  if (i < n) {
+    const Box6 a = load_box(base + (long long)i * 6);
+    const float va = box_volume(a);
+    const int jn = min(64, n - cb * 64);
+    for (int b = 0; b < jn; ++b) {
+      Box6 o;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) o.v[k] = cbox[b][k];
-    const float inter = box_intersection(a, o);
-    const float uni = __fsub_rn(__fadd_rn(va, cvol[b]), inter);
-    if (iou_exceeds(inter, uni, thr)) bits |= (1ull << b);
+      for (int k = 0; k < 6; ++k) o.v[k] = cbox[b][k];
+      const float inter = box_intersection(a, o);
+      const float uni = __fsub_rn(__fadd_rn(va, cvol[b]), inter);
+      if (iou_exceeds(inter, uni, thr)) bits |= (1ull << b);
+    }
+    if (cb == rb) bits &= ~(1ull << t);       // a box does not suppress itself (ssd3d.py:425-426)
+    // TR: word-major layout [word][row] with `words` = rows per word-row (coalesced for the chunk scan)
+    if (TR) mask[(long long)seg * seg_stride_mask + (long long)cb * words + i] = bits;
+    else mask[(long long)seg * seg_stride_mask + (long long)i * words + cb] = bits;
   }
-  if (cb == rb) bits &= ~(1ull << t);       // a box does not suppress itself (ssd3d.py:425-426)
-  // TR: word-major layout [word][row] with `words` = rows per word-row (coalesced for the chunk scan)
-  if (TR) mask[(long long)seg * seg_stride_mask + (long long)cb * words + i] = bits;
-  else mask[(long long)seg * seg_stride_mask + (long long)i * words + cb] = bits;
+  if constexpr (TR) {
+    // one flag per 64 x 64 block that holds any bit: most blocks of a sparse scene are empty and the scan
+    // skips them (and whole steps) without touching the matrix
+    if (__syncthreads_or(bits != 0ull) && t == 0)
+      atomicOr(&block_flags[(long long)rb * flag_words + (cb >> 6)], 1ull << (cb & 63));
+  }
 }
 
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sboxes, const int* __restrict__ nkeep,
                                                       int n_fixed, long long seg_stride_boxes, int words,
                                                       long long seg_stride_mask, float thr,
                                                       unsigned long long* __restrict__ mask) {
-  nms_mask_body<false>(sboxes, nkeep, n_fixed, seg_stride_boxes, words, seg_stride_mask, thr, mask);
+  nms_mask_body<false>(sboxes, nkeep, n_fixed, seg_stride_boxes, words, seg_stride_mask, thr, mask, nullptr, 0);
 }
-// same bits, stored word-major: mask[word * row_stride + row] (row_stride passed in `words`)
+// same bits, stored word-major: mask[word * row_stride + row], plus the per-block "any bit" flags
+// block_flags[row_word * flag_words + col_word / 64] bit (col_word % 64)
 __global__ void __launch_bounds__(64) nms_mask_tr_kernel(const float* __restrict__ sboxes, int n, int row_stride,
-                                                         float thr, unsigned long long* __restrict__ mask) {
-  nms_mask_body<true>(sboxes, nullptr, n, 0, row_stride, 0, thr, mask);
+                                                         float thr, unsigned long long* __restrict__ mask,
+                                                         unsigned long long* __restrict__ block_flags, int flag_words) {
+  nms_mask_body<true>(sboxes, nullptr, n, 0, row_stride, 0, thr, mask, block_flags, flag_words);
 }
 
 // Greedy scan of one segment's bit matrix M (rows `stride` words apart; shared or global memory).
@@ -515,102 +525,75 @@ __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict_
   if ((threadIdx.x & 31) == 0 && ballot != 0u) atomicOr(&rem32[i >> 5], ballot);
 }
 
-// The greedy scan of nms_scan_core on the word-major matrix MT[word * stride + row]: the 64 diagonal words of
-// a step and the 64 rows OR-ed into a later word are contiguous (one 512-byte request instead of 64 sectors),
-// and both are fetched one step ahead (the addresses do not depend on the step's outcome), so the serial chain
-// per 64 boxes is resolve -> barrier -> warp OR-reductions -> barrier with no exposed memory latency.  Rows
-// past n hold garbage that the kept bits mask out.
+// The greedy scan of nms_scan_core on the word-major matrix MT[word * stride + row], driven by the block flags:
+//   * a step whose row of blocks is empty off the diagonal concerns nobody but warp 0, which resolves it
+//     (kept = not removed, when the diagonal block is empty too) and moves on WITHOUT a barrier; the other
+//     warps skip the step, so a sparse scene costs a few dozen instructions per 64 boxes;
+//   * otherwise: resolve -> barrier -> the flagged words are dealt round-robin to the warps, whose 64 rows
+//     are contiguous (one 512-byte request) -> OR-reduction -> barrier.
+// Rows past n hold garbage that the kept bits mask out.  `sflags` is the shared-memory copy of the flags.
 __device__ __forceinline__ void nms_scan_core_tr(const unsigned long long* __restrict__ MT, int n, int stride,
                                                  unsigned long long* removed, unsigned long long* keptw,
-                                                 const unsigned long long* __restrict__ removed_init) {
+                                                 const unsigned long long* __restrict__ removed_init,
+                                                 const unsigned long long* sflags, int fw) {
   const int words = (n + 63) >> 6;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = removed_init ? removed_init[w] : 0ull;
-  unsigned long long r0n = 0ull, r1n = 0ull;
-  if (warp == 0) {
-    r0n = MT[lane];
-    r1n = MT[lane + 32];
-  }
-  // rows of step k for this warp's words k+1+warp+u*nwarps, fetched one step ahead (the addresses do not
-  // depend on the outcome of the step, only the masks do)
-  unsigned long long c0[4], c1[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int w = 1 + warp + u * nwarps;
-    c0[u] = c1[u] = 0ull;
-    if (w < words) {
-      const unsigned long long* row = MT + (long long)w * stride;
-      c0[u] = row[lane];
-      c1[u] = row[lane + 32];
-    }
-  }
   __syncthreads();
   for (int k = 0; k < words; ++k) {
     const int rows = min(64, n - k * 64);
+    const unsigned long long* fr = sflags + k * fw;
+    const int kq = k >> 6;
+    const unsigned long long kbit = 1ull << (k & 63);
+    bool od_any = false;
+    for (int q = kq; q < fw; ++q) od_any |= ((q == kq) ? (fr[q] & ~kbit) : fr[q]) != 0ull;
     if (warp == 0) {
-      const unsigned long long r0 = (lane < rows) ? r0n : 0ull;
-      const unsigned long long r1 = (lane + 32 < rows) ? r1n : 0ull;
-      if (k + 1 < words) {
-        const long long d = (long long)(k + 1) * stride + (k + 1) * 64;
-        r0n = MT[d + lane];
-        r1n = MT[d + lane + 32];
-      }
-      const unsigned long long e0 = r0 & ((1ull << lane) - 1ull);
-      const unsigned long long e1 = r1 & ((1ull << (lane + 32)) - 1ull);
       unsigned long long rem = removed[k];
       if (rows < 64) rem |= (~0ull) << rows;            // rows past the end are never kept
       unsigned long long und = ~rem, kept = 0ull;
-      while (und != 0ull) {
-        const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
-        const bool x0 = u0 && (e0 & kept) != 0ull, x1 = u1 && (e1 & kept) != 0ull;
-        const bool k0 = u0 && !x0 && (e0 & und) == 0ull, k1 = u1 && !x1 && (e1 & und) == 0ull;
-        const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
-                                      ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
-        const unsigned long long nx = (unsigned long long)__ballot_sync(0xffffffffu, x0) |
-                                      ((unsigned long long)__ballot_sync(0xffffffffu, x1) << 32);
-        kept |= nk;
-        und &= ~(nk | nx);
+      if ((fr[kq] & kbit) == 0ull) {
+        kept = und;                                     // no overlaps inside the word: everything left is kept
+      } else if (und != 0ull) {
+        const long long d = (long long)k * stride + k * 64;
+        const unsigned long long r0 = (lane < rows) ? MT[d + lane] : 0ull;
+        const unsigned long long r1 = (lane + 32 < rows) ? MT[d + lane + 32] : 0ull;
+        const unsigned long long e0 = r0 & ((1ull << lane) - 1ull);
+        const unsigned long long e1 = r1 & ((1ull << (lane + 32)) - 1ull);
+        while (und != 0ull) {
+          const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
+          const bool x0 = u0 && (e0 & kept) != 0ull, x1 = u1 && (e1 & kept) != 0ull;
+          const bool k0 = u0 && !x0 && (e0 & und) == 0ull, k1 = u1 && !x1 && (e1 & und) == 0ull;
+          const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+          const unsigned long long nx = (unsigned long long)__ballot_sync(0xffffffffu, x0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, x1) << 32);
+          kept |= nk;
+          und &= ~(nk | nx);
+        }
       }
       if (lane == 0) keptw[k] = kept;
     }
+    if (!od_any) continue;                              // block-uniform: nobody else needs this step
     __syncthreads();
     const unsigned long long kept = keptw[k];
-    unsigned long long n0[4], n1[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {                       // next step's rows: in flight during the reductions
-      const int w = k + 2 + warp + u * nwarps;
-      n0[u] = n1[u] = 0ull;
-      if (w < words) {
-        const unsigned long long* row = MT + (long long)w * stride + (k + 1) * 64;
-        n0[u] = row[lane];
-        n1[u] = row[lane + 32];
-      }
-    }
     if (kept != 0ull) {
       const unsigned long long m0 = ((kept >> lane) & 1ull) ? ~0ull : 0ull;
       const unsigned long long m1 = ((kept >> (lane + 32)) & 1ull) ? ~0ull : 0ull;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int w = k + 1 + warp + u * nwarps;
-        if (w < words) {
-          const unsigned long long v = (c0[u] & m0) | (c1[u] & m1);
+      int idx = 0;
+      for (int q = kq; q < fw; ++q) {
+        unsigned long long f = (q == kq) ? (fr[q] & ~kbit) : fr[q];
+        while (f != 0ull) {
+          const int b = __ffsll((long long)f) - 1;
+          f &= f - 1ull;
+          if ((idx++ % nwarps) != warp) continue;
+          const int w = q * 64 + b;
+          const unsigned long long* row = MT + (long long)w * stride + k * 64;
+          const unsigned long long v = (row[lane] & m0) | (row[lane + 32] & m1);
           const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)v);
           const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(v >> 32));
           if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
         }
       }
-      for (int w = k + 1 + warp + 4 * nwarps; w < words; w += nwarps) {   // chunks beyond 4 * nwarps words
-        const unsigned long long* row = MT + (long long)w * stride + k * 64;
-        const unsigned long long v = (row[lane] & m0) | (row[lane + 32] & m1);
-        const unsigned int lo = __reduce_or_sync(0xffffffffu, (unsigned int)v);
-        const unsigned int hi = __reduce_or_sync(0xffffffffu, (unsigned int)(v >> 32));
-        if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      c0[u] = n0[u];
-      c1[u] = n1[u];
     }
     __syncthreads();
   }
@@ -623,13 +606,19 @@ __global__ void __launch_bounds__(1024) nms_chunk_scan_kernel(const unsigned lon
                                                               float4* __restrict__ kept, long long* __restrict__ nk_ptr,
                                                               uint8_t* __restrict__ keep,
                                                               const int* __restrict__ slot_of,
-                                                              uint8_t* __restrict__ state) {
+                                                              uint8_t* __restrict__ state,
+                                                              unsigned long long* __restrict__ block_flags, int fw) {
   extern __shared__ unsigned long long sm[];
   unsigned long long* removed = sm;
   unsigned long long* keptw = sm + words;
-  int* prefix = reinterpret_cast<int*>(sm + 2 * words);
+  unsigned long long* sflags = sm + 2 * words;
+  int* prefix = reinterpret_cast<int*>(sm + 2 * words + words * fw);
   __shared__ long long s_base;
-  nms_scan_core_tr(mask, n, stride, removed, keptw, removed_init);
+  for (int e = threadIdx.x; e < words * fw; e += blockDim.x) {
+    sflags[e] = block_flags[e];
+    block_flags[e] = 0ull;                               // ready for the next chunk's mask kernel
+  }
+  nms_scan_core_tr(mask, n, stride, removed, keptw, removed_init, sflags, fw);
   __syncthreads();
   if (threadIdx.x == 0) {
     int run = 0;
@@ -1020,7 +1009,7 @@ extern "C" int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_o
 namespace ssd3d {
 struct ChunkedNmsLayout {
   int chunk, G, cells;
-  long long off_removed, off_nk, off_rng, off_kept, off_mask, off_cellstart, off_cursor, off_sorted, off_slot, off_state,
+  long long off_removed, off_nk, off_rng, off_flags, off_kept, off_mask, off_cellstart, off_cursor, off_sorted, off_slot, off_state,
       total;
 };
 static ChunkedNmsLayout chunked_nms_layout(long long n, int chunk) {
@@ -1036,6 +1025,7 @@ static ChunkedNmsLayout chunked_nms_layout(long long n, int chunk) {
   L.off_removed = o; o += align256(8ll * chunks * cw);
   L.off_nk = o; o += 256;
   L.off_rng = o; o += 256;
+  L.off_flags = o; o += align256(8ll * cw * ((cw + 63) / 64));
   L.off_kept = o; o += align256(32ll * n);
   L.off_mask = o; o += align256(8ll * chunk * cw);
   L.off_cellstart = o; o += align256(4ll * (L.cells + 1));
@@ -1072,9 +1062,10 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
   float4* sorted = reinterpret_cast<float4*>(ws + L.off_sorted);
   int* slot_of = reinterpret_cast<int*>(ws + L.off_slot);
   uint8_t* state = ws + L.off_state;
-  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)L.off_kept, st);      // removed bits, kept counter, grid range
+  unsigned long long* block_flags = reinterpret_cast<unsigned long long*>(ws + L.off_flags);
+  cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)L.off_kept, st);      // removed bits, kept counter, grid range, flags
   if (e != cudaSuccess) return (int)e;
-  const int B = L.chunk, cw = B / 64;
+  const int B = L.chunk, cw = B / 64, fw = (cw + 63) / 64;
   const long long chunks = (n + B - 1) / B;
   // The grid only helps when disjoint boxes cannot suppress each other (threshold >= 0; NaN compares false).
   const bool use_grid = chunks > 1 && max_overlap >= 0.0f && !(flags & SSD3D_NMS_NO_GRID);
@@ -1112,11 +1103,11 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
       SSD3D_CHECK_LAUNCH();
     }
     dim3 mgrid((unsigned)words, (unsigned)words, 1);
-    nms_mask_tr_kernel<<<mgrid, 64, 0, st>>>(cb, rows, B, max_overlap, mask);
+    nms_mask_tr_kernel<<<mgrid, 64, 0, st>>>(cb, rows, B, max_overlap, mask, block_flags, fw);
     SSD3D_CHECK_LAUNCH();
-    const size_t smem = (size_t)(2 * words) * 8 + (size_t)(words + 2) * 4;
-    nms_chunk_scan_kernel<<<1, 1024, smem, st>>>(mask, cb, rows, words, B, crem, kept, nk, keep + first,
-                                                 use_grid ? slot_of + first : (const int*)nullptr, state);
+    const size_t smem = (size_t)(2 * words + words * fw) * 8 + (size_t)(words + 2) * 4;
+    nms_chunk_scan_kernel<<<1, 512, smem, st>>>(mask, cb, rows, words, B, crem, kept, nk, keep + first,
+                                                use_grid ? slot_of + first : (const int*)nullptr, state, block_flags, fw);
     SSD3D_CHECK_LAUNCH();
   }
   if (kept_count) {
