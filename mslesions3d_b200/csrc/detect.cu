@@ -805,9 +805,12 @@ __global__ void __launch_bounds__(256) nms_cross_grid_kernel(const float* __rest
                                                              const int* __restrict__ cell_start,
                                                              const float4* __restrict__ sorted,
                                                              const uint8_t* __restrict__ state, float thr,
-                                                             unsigned int* __restrict__ rem32) {
+                                                             unsigned int* __restrict__ rem32, int split) {
+  // `split` warps share a query (they walk alternate rows): a chunk has too few boxes to fill the machine with
+  // one latency-bound warp each
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int i = gw / split, part = gw - i * split;
   if (i >= n) return;                                   // whole warp
   const GridMap m = load_grid(rng, G);
   const Box6 a = load_box(boxes + (long long)i * 6);
@@ -853,7 +856,7 @@ __global__ void __launch_bounds__(256) nms_cross_grid_kernel(const float* __rest
         my_end = cell_start[base + hi[0] + 1];
       }
       const int nr = min(32, nrows - r0);
-      for (int t = 0; t < nr && !found; ++t) {
+      for (int t = part; t < nr && !found; t += split) {
         const int begin = __shfl_sync(0xffffffffu, my_begin, t);
         const int end = __shfl_sync(0xffffffffu, my_end, t);
         if (begin == end) continue;
@@ -1094,8 +1097,9 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
     const float* cb = boxes_xyz + first * 6;
     unsigned long long* crem = removed + c * cw;
     if (c > 0 && use_grid) {
-      nms_cross_grid_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cb, rows, rng, L.G, cell_start, sorted, state,
-                                                                       max_overlap, reinterpret_cast<unsigned int*>(crem));
+      const int split = rows <= 4736 ? 2 : 1;           // 148 SMs x 64 warps = 9472 resident warps
+      nms_cross_grid_kernel<<<(unsigned)(((long long)rows * split + 7) / 8), 256, 0, st>>>(
+          cb, rows, rng, L.G, cell_start, sorted, state, max_overlap, reinterpret_cast<unsigned int*>(crem), split);
       SSD3D_CHECK_LAUNCH();
     } else if (c > 0) {
       dim3 grid((unsigned)((rows + 255) / 256), (unsigned)splits);

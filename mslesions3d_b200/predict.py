@@ -2,11 +2,13 @@
 
 Same flags and the same ``predict_example(...)`` signature.  The reference reads NIfTI volumes through
 MONAI/nibabel (absent here, and data loading is outside the accelerated path): this entry point accepts
-either a ``.npy``/``.pt`` stack of volumes at ``--dataset_path`` or, by default, generates the synthetic
-cube volumes of ``generate_artificial_dataset.py`` in memory.  Checkpoints are the reference's
+a data-set directory in the generator's layout (``images/sub-XXXX_image.nii.gz`` + ``labels/sub-XXXX_seg.nii.gz``,
+read by the package's own NIfTI-1 reader, ground-truth boxes extracted from the masks), a ``.npy``/``.pt`` stack
+of volumes at ``--dataset_path`` or, by default, generates the synthetic cube volumes of
+``generate_artificial_dataset.py`` in memory.  Checkpoints are the reference's
 PyTorch-Lightning ``.ckpt`` files (``state_dict`` + ``hyper_parameters``).  Outputs follow the reference's
 (predict.py:155-232,85-150,279-281): per subject ``sub-{id}_preds.csv`` / ``.json`` and the box-outline volume
-(``.npy`` instead of NIfTI), ``aa_metrics_per_subject_(min_IoU=0.5|0.1).json`` from the device-side
+``sub-{id}_preds.nii.gz`` (NIfTI-1 written by ``mslesions3d_b200/nifti.py``), ``aa_metrics_per_subject_(min_IoU=0.5|0.1).json`` from the device-side
 ``calculate_mAP``, plus one ``predictions.json`` with every subject's boxes / labels / scores.
 """
 from __future__ import annotations
@@ -21,13 +23,15 @@ import numpy as np
 import torch
 
 from . import synthetic
+from .nifti import save_nifti
 from .ssd3d import LSSD3D, device
 
 
 def build_parser() -> argparse.ArgumentParser:
     parser = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     parser.add_argument('-d', '--dataset_path', type=str, default=r'../data/artificial_dataset',
-                        help="path to a .npy/.pt stack of volumes (N,C,D,H,W); synthetic volumes if it does not exist")
+                        help="data-set directory (images/*.nii.gz + labels/*.nii.gz) or a .npy/.pt stack of volumes "
+                             "(N,C,D,H,W); synthetic volumes if it does not exist")
     parser.add_argument('-dn', '--dataset_name', type=str, help="name of dataset to use", default=None)
     parser.add_argument('-m', '--model_path', type=str, help="path to model", default=r'model_final.onnx')
     parser.add_argument('-mn', '--model_name', type=str, help="wandb model name", default=None)
@@ -44,7 +48,7 @@ def build_parser() -> argparse.ArgumentParser:
                         help="if there are a lot of resulting detection across all classes, keep only the top 'k'")
     parser.add_argument('-o', '--output_dir', type=str, help="path to output", default=r"../data/predictions/")
     parser.add_argument('-si', '--save_images', type=int, default=1,
-                        help="whether to save the predictions (JSON here; NIfTI in the reference)")
+                        help="whether to save the prediction volumes (NIfTI) and predictions.json")
     parser.add_argument('-bs', '--batch_size', type=int, default=8, help="volumes per forward (reference: 1)")
     parser.add_argument('-n', '--n_subjects', type=int, default=16, help="synthetic subjects when no dataset file")
     return parser
@@ -96,17 +100,17 @@ def box_outline_segmentation(det_boxes, det_labels, det_scores, img_shape, min_s
 
 
 def save_predictions_example(subjects, img_shape, det_locs, det_labels, det_scores, min_score=0.5,
-                             output_dir=r"./predictions", save_images=True):
+                             output_dir=r"./predictions", save_images=True, affine=None):
     """Per subject ``sub-{id}_preds.csv`` (label_id, score), ``sub-{id}_preds.json`` (the reference's ``all_infos``)
-    and the box-outline volume (predict.py:155-232).  The reference writes the volume as NIfTI through nibabel,
-    which is absent here: it is saved as ``sub-{id}_preds.npy``."""
+    and the box-outline volume ``sub-{id}_preds.nii.gz`` (predict.py:155-232; float64 voxels like the reference's
+    ``np.zeros(img_shape)``, written by the package's NIfTI-1 writer since nibabel is absent)."""
     if not pexists(output_dir):
         os.makedirs(output_dir)
     for i, subj in enumerate(subjects):
         seg, scores_map, infos = box_outline_segmentation(det_locs[i].cpu(), det_labels[i].cpu(), det_scores[i].cpu(),
                                                           img_shape, min_score)
         if save_images:
-            np.save(pjoin(output_dir, f"sub-{subj}_preds.npy"), seg.astype(np.uint16))
+            save_nifti(pjoin(output_dir, f"sub-{subj}_preds.nii.gz"), seg, affine)
         with open(pjoin(output_dir, f"sub-{subj}_preds.csv"), "w") as f:
             f.write(",label_id,score\n")
             for r, (lid, sc) in enumerate(scores_map):
@@ -162,15 +166,22 @@ def predict_example(model_path, output_dir, dataset_path, dataset_name, n_classe
     model.min_score = min_score
 
     gt_boxes = gt_labels = None
-    if dataset_path and os.path.isfile(dataset_path):
+    subjects = None
+    if dataset_path and os.path.isdir(pjoin(dataset_path, "images")):
+        # the generator's on-disk layout (generate_artificial_dataset.py:54-111): NIfTI volumes + masks
+        subjects, vols, gt_boxes, gt_labels = synthetic.load_dataset_dir(dataset_path, with_boxes=True)
+        n = max(1, int(round(len(subjects) * percentage)))
+        subjects, vols, gt_boxes, gt_labels = subjects[:n], vols[:n], gt_boxes[:n], gt_labels[:n]
+    elif dataset_path and os.path.isfile(dataset_path):
         vols = load_volumes(dataset_path, n_subjects, model.input_channels, tuple(model.input_size), percentage)
     else:   # synthetic cube volumes come with their ground-truth boxes (generate_artificial_dataset.py)
         n = max(1, int(round(n_subjects * percentage)))
         vols, gt_boxes, gt_labels = synthetic.make_batch(n, model.input_channels, tuple(model.input_size),
                                                          with_boxes=True)
-    subjects = list(range(vols.shape[0]))
+    if subjects is None:
+        subjects = list(range(vols.shape[0]))
     if subject is not None:
-        k = int(subject)
+        k = subjects.index(subject) if subject in subjects else int(subject)
         vols, subjects = vols[k:k + 1], subjects[k:k + 1]
         if gt_boxes is not None:
             gt_boxes, gt_labels = gt_boxes[k:k + 1], gt_labels[k:k + 1]

@@ -116,6 +116,48 @@ def make_batch(batch_size: int, channels: int = 1, image_size: Sequence[int] = (
     return vols
 
 
+def write_dataset(output_dir: str, num_images: int, image_size: Sequence[int] = (64, 64, 64), num_objects=(1, 5),
+                  object_size=None, random_seed: int = 0) -> str:
+    """The on-disk data set of generate_artificial_dataset.py:54-111: ``images/sub-XXXX_image.nii.gz`` (raw
+    float64 volume) and ``labels/sub-XXXX_seg.nii.gz`` (mask), identity affine."""
+    import os
+    from .nifti import save_nifti
+    image_dir, seg_dir = os.path.join(output_dir, "images"), os.path.join(output_dir, "labels")
+    os.makedirs(image_dir, exist_ok=True)
+    os.makedirs(seg_dir, exist_ok=True)
+    for idx in range(num_images):
+        data, mask, _ = generate_volume(idx, image_size, num_objects, object_size, random_seed)
+        save_nifti(os.path.join(image_dir, "sub-%s_image.nii.gz" % str(idx).zfill(4)), data)
+        save_nifti(os.path.join(seg_dir, "sub-%s_seg.nii.gz" % str(idx).zfill(4)), mask.astype(np.float64))
+    return output_dir
+
+
+def load_dataset_dir(dataset_dir: str, with_boxes: bool = False):
+    """Read a data set written by ``write_dataset`` / the reference's generator: -> subject ids, normalised
+    volumes (N, 1, D, H, W) fp32 (datasets.py:403), and with ``with_boxes`` the GT boxes / labels extracted from
+    the masks like ``BoundingBoxesGeneratord`` does (utils.py:446-500)."""
+    import os
+    from .nifti import load_nifti
+    image_dir, seg_dir = os.path.join(dataset_dir, "images"), os.path.join(dataset_dir, "labels")
+    names = sorted(f for f in os.listdir(image_dir) if f.endswith("_image.nii.gz") or f.endswith("_image.nii"))
+    subjects, vols, boxes, labels = [], [], [], []
+    for f in names:
+        sid = f.split("_image")[0].replace("sub-", "")
+        data, _ = load_nifti(os.path.join(image_dir, f))
+        subjects.append(sid)
+        vols.append(normalize_nonzero(data)[None])
+        if with_boxes:
+            seg_name = f.replace("_image", "_seg")
+            mask, _ = load_nifti(os.path.join(seg_dir, seg_name))
+            bx = boxes_from_mask((mask != 0).astype(np.uint8))
+            boxes.append(bx)
+            labels.append(np.ones((bx.shape[0],), dtype=np.int64))
+    vols = np.stack(vols).astype(np.float32)
+    if with_boxes:
+        return subjects, vols, boxes, labels
+    return subjects, vols
+
+
 # --------------------------------------------------------------------------------------------------
 # random-init weights of the SSD3D-MobileNet architecture (benchmark / test input generation)
 # --------------------------------------------------------------------------------------------------

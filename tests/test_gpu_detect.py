@@ -246,7 +246,7 @@ def test_predict_entry_point_writes_reference_style_outputs(tmp_path):
     out_dir = tmp_path / "out" / "synthetic" / "train_set" / "min_score_0.3"
     assert len(res) == 5
     for i in range(5):
-        for ext in ("csv", "json", "npy"):
+        for ext in ("csv", "json", "nii.gz"):
             assert os.path.isfile(out_dir / ("sub-%d_preds.%s" % (i, ext)))
         info = json.load(open(out_dir / ("sub-%d_preds.json" % i)))
         n_det = len(res[str(i)]["boxes"])
@@ -264,6 +264,31 @@ def test_predict_entry_point_writes_reference_style_outputs(tmp_path):
     with torch.no_grad():
         b, l, s = model.predict_step({"img": torch.from_numpy(vols[:2])}, 0)
     assert torch.equal(torch.tensor(res["0"]["scores"]), s[0].cpu()) and torch.equal(torch.tensor(res["1"]["boxes"]), b[1].cpu())
+
+
+def test_predict_entry_point_reads_generator_dataset_directory(tmp_path):
+    """The generator's on-disk layout (images/*.nii.gz + labels/*.nii.gz) in, NIfTI outline volumes and per-subject
+    mAP out; same detections as the in-memory synthetic path (same seeds -> same volumes)."""
+    import json
+    from mslesions3d_b200 import nifti, predict, synthetic
+    sd = O.random_state_dict(1, seed=9)
+    ckpt = tmp_path / "model.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": dict(n_classes=2, input_channels=1, input_size=(64, 64, 64))}, ckpt)
+    data_dir = synthetic.write_dataset(str(tmp_path / "data"), 3, (64, 64, 64))
+    res = predict.predict_example(str(ckpt), str(tmp_path / "out"), dataset_path=data_dir, dataset_name=None,
+                                  min_score=0.3, top_k=20, batch_size=2)
+    mem = predict.predict_example(str(ckpt), str(tmp_path / "out_mem"), dataset_path="", dataset_name=None,
+                                  min_score=0.3, top_k=20, n_subjects=3, batch_size=2)
+    assert list(res) == ["0000", "0001", "0002"]
+    for i, sid in enumerate(res):
+        assert res[sid] == mem[str(i)]
+    out_dir = tmp_path / "out" / "train_set" / "min_score_0.3"
+    seg, affine = nifti.load_nifti(str(out_dir / "sub-0000_preds.nii.gz"))
+    info = json.load(open(out_dir / "sub-0000_preds.json"))
+    assert seg.shape == (64, 64, 64) and (affine == torch.eye(4).numpy()).all()
+    assert set(int(v) for v in set(seg.flatten().tolist())) == {0} | {int(k) for k in info}
+    m = json.load(open(out_dir / "aa_metrics_per_subject_(min_IoU=0.5).json"))
+    assert set(m) == {"0000", "0001", "0002"}
 
 
 @pytest.mark.parametrize("shape", [(2, 1, 32, 32, 32), (3, 2, 17, 19, 23), (1, 1, 64, 64, 64)])

@@ -181,3 +181,51 @@ def test_box_outline_segmentation_known_answer():
     assert infos[1][1] == [4, 4, 4, 8, 8, 8] and infos[1][2] == 1
     assert seg.max() == 1 and seg[4, 4, 4] == 1 and seg[9, 9, 9] == 1 and seg[6, 6, 6] == 0 and seg[4, 6, 6] == 1
     assert int((seg == 1).sum()) == 6 * 6 * 6 - 4 * 4 * 4      # the shell of the 6^3 block [4, 9]^3
+
+
+def test_nifti_writer_known_answer_header_and_round_trip(tmp_path):
+    """NIfTI-1 single-file layout (what nib.save writes for predict.py:225-226 / generate_artificial_dataset.py:
+    106-111): 348-byte header, magic n+1, vox_offset 352, Fortran-ordered voxels, affine in the sform."""
+    import gzip
+    import struct
+    import numpy as np
+    from mslesions3d_b200 import nifti
+    rs = np.random.RandomState(0)
+    vol = rs.rand(5, 6, 7)
+    aff = np.array([[2., 0, 0, -10], [0, 3., 0, 5], [0, 0, 4., 1], [0, 0, 0, 1]])
+    path = str(tmp_path / "v.nii.gz")
+    nifti.save_nifti(path, vol, aff)
+    blob = gzip.open(path, "rb").read()
+    assert len(blob) == 352 + vol.size * 8
+    assert struct.unpack_from("<i", blob, 0)[0] == 348 and blob[344:348] == b"n+1\x00"
+    assert struct.unpack_from("<8h", blob, 40) == (3, 5, 6, 7, 1, 1, 1, 1)
+    assert struct.unpack_from("<2h", blob, 70) == (64, 64)                      # float64, 64 bits
+    assert struct.unpack_from("<4f", blob, 76) == (1.0, 2.0, 3.0, 4.0)          # qfac, voxel sizes
+    assert struct.unpack_from("<f", blob, 108)[0] == 352.0
+    assert struct.unpack_from("<2h", blob, 252) == (0, 2)                       # qform_code, sform_code
+    assert struct.unpack_from("<4f", blob, 280) == (2.0, 0.0, 0.0, -10.0)
+    first = np.frombuffer(blob, dtype="<f8", count=6, offset=352)
+    assert (first[:5] == vol[:, 0, 0]).all() and first[5] == vol[0, 1, 0]       # first axis fastest
+    back, aff2 = nifti.load_nifti(path)
+    assert back.dtype == np.float64 and (back == vol).all() and (aff2 == aff).all()
+    for dt in ("uint8", "int16", "uint16", "int32", "float32"):
+        a = (rs.rand(3, 4, 2, 2) * 100).astype(dt)
+        p2 = str(tmp_path / ("a_%s.nii" % dt))
+        nifti.save_nifti(p2, a)
+        b, eye = nifti.load_nifti(p2)
+        assert b.dtype == a.dtype and (b == a).all() and (eye == np.eye(4)).all()
+
+
+def test_dataset_directory_round_trip(tmp_path):
+    """write_dataset / load_dataset_dir reproduce make_batch (same generator stream, normalisation and GT boxes)."""
+    import numpy as np
+    from mslesions3d_b200 import synthetic
+    d = synthetic.write_dataset(str(tmp_path / "ds"), 3, (32, 32, 32))
+    import os
+    assert sorted(os.listdir(os.path.join(d, "images"))) == ["sub-000%d_image.nii.gz" % i for i in range(3)]
+    assert sorted(os.listdir(os.path.join(d, "labels"))) == ["sub-000%d_seg.nii.gz" % i for i in range(3)]
+    subjects, vols, boxes, labels = synthetic.load_dataset_dir(d, with_boxes=True)
+    want, wb, wl = synthetic.make_batch(3, 1, (32, 32, 32), with_boxes=True)
+    assert subjects == ["0000", "0001", "0002"] and (vols == want).all()
+    for a, b, la, lb in zip(boxes, wb, labels, wl):
+        assert (a == b).all() and (la == lb).all()
