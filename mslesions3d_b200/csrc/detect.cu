@@ -599,16 +599,57 @@ __device__ __forceinline__ void nms_scan_core_tr(const unsigned long long* __res
   }
 }
 
-__global__ void __launch_bounds__(1024) nms_chunk_scan_kernel(const unsigned long long* __restrict__ mask,
-                                                              const float* __restrict__ boxes, int n, int words,
-                                                              int stride,
-                                                              const unsigned long long* __restrict__ removed_init,
-                                                              float4* __restrict__ kept, long long* __restrict__ nk_ptr,
-                                                              uint8_t* __restrict__ keep,
-                                                              const int* __restrict__ slot_of,
-                                                              uint8_t* __restrict__ state,
-                                                              unsigned long long* __restrict__ block_flags, int fw) {
+// One launch per chunk: CTA 0 resolves chunk c (greedy scan + append / flag the kept boxes); the other CTAs
+// -- the scan leaves 147 SMs idle -- already build the word-major bit matrix and block flags of chunk c+1
+// into the other buffer (8 tiles of 64 x 64 per CTA), which takes the matrix off the serial path.
+__global__ void __launch_bounds__(512) nms_scan_mask_kernel(
+    const unsigned long long* __restrict__ mask, const float* __restrict__ boxes, int n, int words, int stride,
+    const unsigned long long* __restrict__ removed_init, float4* __restrict__ kept, long long* __restrict__ nk_ptr,
+    uint8_t* __restrict__ keep, const int* __restrict__ slot_of, uint8_t* __restrict__ state,
+    unsigned long long* __restrict__ block_flags, int fw,
+    const float* __restrict__ boxes_next, int n_next, float thr, unsigned long long* __restrict__ mask_next,
+    unsigned long long* __restrict__ flags_next) {
   extern __shared__ unsigned long long sm[];
+  if (blockIdx.x != 0) {
+    __shared__ float cbox[8][64][6];
+    __shared__ float cvol[8][64];
+    const int words_next = (n_next + 63) >> 6;
+    const int sub = threadIdx.x >> 6, t = threadIdx.x & 63;
+    const long long tile = (long long)(blockIdx.x - 1) * 8 + sub;
+    const int rb = (int)(tile / words_next), cb = (int)(tile - (long long)rb * words_next);
+    const bool active = rb < words_next && cb >= rb;
+    if (active) {
+      const int cj = cb * 64 + t;
+      if (cj < n_next) {
+        const Box6 bx = load_box(boxes_next + (long long)cj * 6);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cbox[sub][t][k] = bx.v[k];
+        cvol[sub][t] = box_volume(bx);
+      }
+    }
+    __syncthreads();
+    if (!active) return;
+    const int i = rb * 64 + t;
+    unsigned long long bits = 0ull;
+    if (i < n_next) {
+      const Box6 a = load_box(boxes_next + (long long)i * 6);
+      const float va = box_volume(a);
+      const int jn = min(64, n_next - cb * 64);
+      for (int b = 0; b < jn; ++b) {
+        Box6 o;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o.v[k] = cbox[sub][b][k];
+        const float inter = box_intersection(a, o);
+        const float uni = __fsub_rn(__fadd_rn(va, cvol[sub][b]), inter);
+        if (iou_exceeds(inter, uni, thr)) bits |= (1ull << b);
+      }
+      if (cb == rb) bits &= ~(1ull << t);       // a box does not suppress itself (ssd3d.py:425-426)
+      mask_next[(long long)cb * stride + i] = bits;
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, bits != 0ull);
+    if (any != 0u && (threadIdx.x & 31) == 0) atomicOr(&flags_next[(long long)rb * fw + (cb >> 6)], 1ull << (cb & 63));
+    return;
+  }
   unsigned long long* removed = sm;
   unsigned long long* keptw = sm + words;
   unsigned long long* sflags = sm + 2 * words;
@@ -616,7 +657,7 @@ __global__ void __launch_bounds__(1024) nms_chunk_scan_kernel(const unsigned lon
   __shared__ long long s_base;
   for (int e = threadIdx.x; e < words * fw; e += blockDim.x) {
     sflags[e] = block_flags[e];
-    block_flags[e] = 0ull;                               // ready for the next chunk's mask kernel
+    block_flags[e] = 0ull;                               // ready for the mask of the chunk after next
   }
   nms_scan_core_tr(mask, n, stride, removed, keptw, removed_init, sflags, fw);
   __syncthreads();
@@ -1012,6 +1053,7 @@ extern "C" int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_o
 namespace ssd3d {
 struct ChunkedNmsLayout {
   int chunk, G, cells;
+  long long flags_bytes, mask_bytes;
   long long off_removed, off_nk, off_rng, off_flags, off_kept, off_mask, off_cellstart, off_cursor, off_sorted, off_slot, off_state,
       total;
 };
@@ -1028,9 +1070,11 @@ static ChunkedNmsLayout chunked_nms_layout(long long n, int chunk) {
   L.off_removed = o; o += align256(8ll * chunks * cw);
   L.off_nk = o; o += 256;
   L.off_rng = o; o += 256;
-  L.off_flags = o; o += align256(8ll * cw * ((cw + 63) / 64));
+  L.flags_bytes = align256(8ll * cw * ((cw + 63) / 64));
+  L.off_flags = o; o += 2 * L.flags_bytes;
   L.off_kept = o; o += align256(32ll * n);
-  L.off_mask = o; o += align256(8ll * chunk * cw);
+  L.mask_bytes = align256(8ll * chunk * cw);
+  L.off_mask = o; o += 2 * L.mask_bytes;
   L.off_cellstart = o; o += align256(4ll * (L.cells + 1));
   L.off_cursor = o; o += align256(4ll * L.cells);
   L.off_sorted = o; o += align256(32ll * n);
@@ -1059,13 +1103,11 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
   long long* nk = reinterpret_cast<long long*>(ws + L.off_nk);
   unsigned int* rng = reinterpret_cast<unsigned int*>(ws + L.off_rng);
   float4* kept = reinterpret_cast<float4*>(ws + L.off_kept);
-  unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + L.off_mask);
   int* cell_start = reinterpret_cast<int*>(ws + L.off_cellstart);
   int* cursor = reinterpret_cast<int*>(ws + L.off_cursor);
   float4* sorted = reinterpret_cast<float4*>(ws + L.off_sorted);
   int* slot_of = reinterpret_cast<int*>(ws + L.off_slot);
   uint8_t* state = ws + L.off_state;
-  unsigned long long* block_flags = reinterpret_cast<unsigned long long*>(ws + L.off_flags);
   cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)L.off_kept, st);      // removed bits, kept counter, grid range, flags
   if (e != cudaSuccess) return (int)e;
   const int B = L.chunk, cw = B / 64, fw = (cw + 63) / 64;
@@ -1106,12 +1148,23 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
       nms_cross_kernel<<<grid, 256, 0, st>>>(cb, rows, kept, nk, max_overlap, reinterpret_cast<unsigned int*>(crem));
       SSD3D_CHECK_LAUNCH();
     }
-    dim3 mgrid((unsigned)words, (unsigned)words, 1);
-    nms_mask_tr_kernel<<<mgrid, 64, 0, st>>>(cb, rows, B, max_overlap, mask, block_flags, fw);
-    SSD3D_CHECK_LAUNCH();
+    unsigned long long* mask_cur = reinterpret_cast<unsigned long long*>(ws + L.off_mask + (c & 1) * L.mask_bytes);
+    unsigned long long* mask_nxt = reinterpret_cast<unsigned long long*>(ws + L.off_mask + ((c + 1) & 1) * L.mask_bytes);
+    unsigned long long* flags_cur = reinterpret_cast<unsigned long long*>(ws + L.off_flags + (c & 1) * L.flags_bytes);
+    unsigned long long* flags_nxt = reinterpret_cast<unsigned long long*>(ws + L.off_flags + ((c + 1) & 1) * L.flags_bytes);
+    if (c == 0) {                                       // later chunks get their matrix from the previous launch
+      dim3 mgrid((unsigned)words, (unsigned)words, 1);
+      nms_mask_tr_kernel<<<mgrid, 64, 0, st>>>(cb, rows, B, max_overlap, mask_cur, flags_cur, fw);
+      SSD3D_CHECK_LAUNCH();
+    }
+    const long long nfirst = first + B;
+    const int nrows = (c + 1 < chunks) ? (int)((n - nfirst) < B ? (n - nfirst) : B) : 0;
+    const long long nwords = (nrows + 63) / 64;
+    const unsigned blocks = 1u + (unsigned)((nwords * nwords + 7) / 8);
     const size_t smem = (size_t)(2 * words + words * fw) * 8 + (size_t)(words + 2) * 4;
-    nms_chunk_scan_kernel<<<1, 512, smem, st>>>(mask, cb, rows, words, B, crem, kept, nk, keep + first,
-                                                use_grid ? slot_of + first : (const int*)nullptr, state, block_flags, fw);
+    nms_scan_mask_kernel<<<blocks, 512, smem, st>>>(mask_cur, cb, rows, words, B, crem, kept, nk, keep + first,
+                                                    use_grid ? slot_of + first : (const int*)nullptr, state, flags_cur,
+                                                    fw, boxes_xyz + nfirst * 6, nrows, max_overlap, mask_nxt, flags_nxt);
     SSD3D_CHECK_LAUNCH();
   }
   if (kept_count) {
