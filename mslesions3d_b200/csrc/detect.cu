@@ -485,11 +485,15 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long*
 // Work is O(n * kept) IoU tests and 3 launches per chunk, nothing is read back by the host.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict__ boxes, int n,
-                                                        const float4* __restrict__ kept,
-                                                        const long long* __restrict__ nk_ptr, float thr,
+                                                        const float4* __restrict__ kept_all,
+                                                        const long long* __restrict__ lo_ptr,
+                                                        const long long* __restrict__ hi_ptr, float thr,
                                                         unsigned int* __restrict__ rem32) {
+  // kept-list entries [*lo_ptr, *hi_ptr): everything kept so far (dense mode) or the previous chunk's (delta)
   __shared__ float4 tile[256][2];
-  const long long nk = *nk_ptr;
+  const long long lo = *lo_ptr;
+  const long long nk = *hi_ptr - lo;
+  const float4* kept = kept_all + 2 * lo;
   const long long tiles = (nk + 255) >> 8;
   if ((long long)blockIdx.y >= tiles) return;
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -596,94 +600,6 @@ __device__ __forceinline__ void nms_scan_core_tr(const unsigned long long* __res
       }
     }
     __syncthreads();
-  }
-}
-
-// One launch per chunk: CTA 0 resolves chunk c (greedy scan + append / flag the kept boxes); the other CTAs
-// -- the scan leaves 147 SMs idle -- already build the word-major bit matrix and block flags of chunk c+1
-// into the other buffer (8 tiles of 64 x 64 per CTA), which takes the matrix off the serial path.
-__global__ void __launch_bounds__(512) nms_scan_mask_kernel(
-    const unsigned long long* __restrict__ mask, const float* __restrict__ boxes, int n, int words, int stride,
-    const unsigned long long* __restrict__ removed_init, float4* __restrict__ kept, long long* __restrict__ nk_ptr,
-    uint8_t* __restrict__ keep, const int* __restrict__ slot_of, uint8_t* __restrict__ state,
-    unsigned long long* __restrict__ block_flags, int fw,
-    const float* __restrict__ boxes_next, int n_next, float thr, unsigned long long* __restrict__ mask_next,
-    unsigned long long* __restrict__ flags_next) {
-  extern __shared__ unsigned long long sm[];
-  if (blockIdx.x != 0) {
-    __shared__ float cbox[8][64][6];
-    __shared__ float cvol[8][64];
-    const int words_next = (n_next + 63) >> 6;
-    const int sub = threadIdx.x >> 6, t = threadIdx.x & 63;
-    const long long tile = (long long)(blockIdx.x - 1) * 8 + sub;
-    const int rb = (int)(tile / words_next), cb = (int)(tile - (long long)rb * words_next);
-    const bool active = rb < words_next && cb >= rb;
-    if (active) {
-      const int cj = cb * 64 + t;
-      if (cj < n_next) {
-        const Box6 bx = load_box(boxes_next + (long long)cj * 6);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) cbox[sub][t][k] = bx.v[k];
-        cvol[sub][t] = box_volume(bx);
-      }
-    }
-    __syncthreads();
-    if (!active) return;
-    const int i = rb * 64 + t;
-    unsigned long long bits = 0ull;
-    if (i < n_next) {
-      const Box6 a = load_box(boxes_next + (long long)i * 6);
-      const float va = box_volume(a);
-      const int jn = min(64, n_next - cb * 64);
-      for (int b = 0; b < jn; ++b) {
-        Box6 o;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) o.v[k] = cbox[sub][b][k];
-        const float inter = box_intersection(a, o);
-        const float uni = __fsub_rn(__fadd_rn(va, cvol[sub][b]), inter);
-        if (iou_exceeds(inter, uni, thr)) bits |= (1ull << b);
-      }
-      if (cb == rb) bits &= ~(1ull << t);       // a box does not suppress itself (ssd3d.py:425-426)
-      mask_next[(long long)cb * stride + i] = bits;
-    }
-    const unsigned any = __ballot_sync(0xffffffffu, bits != 0ull);
-    if (any != 0u && (threadIdx.x & 31) == 0) atomicOr(&flags_next[(long long)rb * fw + (cb >> 6)], 1ull << (cb & 63));
-    return;
-  }
-  unsigned long long* removed = sm;
-  unsigned long long* keptw = sm + words;
-  unsigned long long* sflags = sm + 2 * words;
-  int* prefix = reinterpret_cast<int*>(sm + 2 * words + words * fw);
-  __shared__ long long s_base;
-  for (int e = threadIdx.x; e < words * fw; e += blockDim.x) {
-    sflags[e] = block_flags[e];
-    block_flags[e] = 0ull;                               // ready for the mask of the chunk after next
-  }
-  nms_scan_core_tr(mask, n, stride, removed, keptw, removed_init, sflags, fw);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int w = 0; w < words; ++w) {
-      prefix[w] = run;
-      run += __popcll(keptw[w]);
-    }
-    const long long base = *nk_ptr;
-    s_base = base;
-    *nk_ptr = base + run;
-  }
-  __syncthreads();
-  const long long base = s_base;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const unsigned long long kw = keptw[i >> 6];
-    const bool k = (kw >> (i & 63)) & 1ull;
-    keep[i] = (uint8_t)k;
-    if (k) {
-      const long long pos = base + prefix[i >> 6] + __popcll(kw & ((1ull << (i & 63)) - 1ull));
-      const Box6 b = load_box(boxes + (long long)i * 6);
-      kept[2 * pos] = make_float4(b.v[0], b.v[1], b.v[2], b.v[3]);
-      kept[2 * pos + 1] = make_float4(b.v[4], b.v[5], box_volume(b), 0.f);
-      if (slot_of) state[slot_of[i]] = 1;
-    }
   }
 }
 
@@ -841,16 +757,15 @@ __global__ void __launch_bounds__(256) nms_grid_scatter_kernel(const float* __re
   slot_of[i] = slot;
 }
 
-__global__ void __launch_bounds__(256) nms_cross_grid_kernel(const float* __restrict__ boxes, int n,
-                                                             const unsigned int* __restrict__ rng, int G,
-                                                             const int* __restrict__ cell_start,
-                                                             const float4* __restrict__ sorted,
-                                                             const uint8_t* __restrict__ state, float thr,
-                                                             unsigned int* __restrict__ rem32, int split) {
+__device__ __forceinline__ void nms_cross_grid_query(int gw, const float* __restrict__ boxes, int n,
+                                                     const unsigned int* __restrict__ rng, int G,
+                                                     const int* __restrict__ cell_start,
+                                                     const float4* __restrict__ sorted,
+                                                     const uint8_t* __restrict__ state, float thr,
+                                                     unsigned int* __restrict__ rem32, int split) {
   // `split` warps share a query (they walk alternate rows): a chunk has too few boxes to fill the machine with
   // one latency-bound warp each
   const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int i = gw / split, part = gw - i * split;
   if (i >= n) return;                                   // whole warp
   const GridMap m = load_grid(rng, G);
@@ -923,6 +838,108 @@ __global__ void __launch_bounds__(256) nms_cross_grid_kernel(const float* __rest
     }
   }
   if (lane == 0 && found) atomicOr(&rem32[i >> 5], 1u << (i & 31));
+}
+
+// One launch per chunk: CTA 0 resolves chunk c (greedy scan + append / flag the kept boxes, kept-list length
+// recorded in nk_hist[c+1]); the other CTAs -- the scan leaves 147 SMs idle -- already work for chunk c+1:
+//   * CTAs 1 .. mask_blocks: its word-major bit matrix and block flags into the other buffer (8 tiles of
+//     64 x 64 per CTA);
+//   * the rest: its grid-pruned cross test (16 warps per CTA).  They read `state` while CTA 0 may be setting
+//     bytes of chunk c: harmless, a set byte is always a really kept EARLIER box; what they can miss -- boxes
+//     kept in chunk c -- is covered afterwards by a dense "delta" pass over kept-list entries
+//     [nk_hist[c], nk_hist[c+1]) (at most one chunk of boxes, ~10 us).
+// This takes both the matrix and the cross test off the serial path: per chunk it is scan + delta.
+__global__ void __launch_bounds__(512) nms_scan_mask_kernel(
+    const unsigned long long* __restrict__ mask, const float* __restrict__ boxes, int n, int words, int stride,
+    const unsigned long long* __restrict__ removed_init, float4* __restrict__ kept, long long* __restrict__ nk_ptr,
+    uint8_t* __restrict__ keep, const int* __restrict__ slot_of, uint8_t* __restrict__ state,
+    unsigned long long* __restrict__ block_flags, int fw,
+    const float* __restrict__ boxes_next, int n_next, float thr, unsigned long long* __restrict__ mask_next,
+    unsigned long long* __restrict__ flags_next, long long* __restrict__ nk_hist_next, int mask_blocks,
+    const unsigned int* __restrict__ rng, int G, const int* __restrict__ cell_start,
+    const float4* __restrict__ sorted, unsigned int* __restrict__ rem32_next, int split) {
+  extern __shared__ unsigned long long sm[];
+  if ((int)blockIdx.x > mask_blocks) {
+    const int gw = ((int)blockIdx.x - 1 - mask_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    nms_cross_grid_query(gw, boxes_next, n_next, rng, G, cell_start, sorted, state, thr, rem32_next, split);
+    return;
+  }
+  if (blockIdx.x != 0) {
+    __shared__ float cbox[8][64][6];
+    __shared__ float cvol[8][64];
+    const int words_next = (n_next + 63) >> 6;
+    const int sub = threadIdx.x >> 6, t = threadIdx.x & 63;
+    const long long tile = (long long)(blockIdx.x - 1) * 8 + sub;
+    const int rb = (int)(tile / words_next), cb = (int)(tile - (long long)rb * words_next);
+    const bool active = rb < words_next && cb >= rb;
+    if (active) {
+      const int cj = cb * 64 + t;
+      if (cj < n_next) {
+        const Box6 bx = load_box(boxes_next + (long long)cj * 6);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cbox[sub][t][k] = bx.v[k];
+        cvol[sub][t] = box_volume(bx);
+      }
+    }
+    __syncthreads();
+    if (!active) return;
+    const int i = rb * 64 + t;
+    unsigned long long bits = 0ull;
+    if (i < n_next) {
+      const Box6 a = load_box(boxes_next + (long long)i * 6);
+      const float va = box_volume(a);
+      const int jn = min(64, n_next - cb * 64);
+      for (int b = 0; b < jn; ++b) {
+        Box6 o;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o.v[k] = cbox[sub][b][k];
+        const float inter = box_intersection(a, o);
+        const float uni = __fsub_rn(__fadd_rn(va, cvol[sub][b]), inter);
+        if (iou_exceeds(inter, uni, thr)) bits |= (1ull << b);
+      }
+      if (cb == rb) bits &= ~(1ull << t);       // a box does not suppress itself (ssd3d.py:425-426)
+      mask_next[(long long)cb * stride + i] = bits;
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, bits != 0ull);
+    if (any != 0u && (threadIdx.x & 31) == 0) atomicOr(&flags_next[(long long)rb * fw + (cb >> 6)], 1ull << (cb & 63));
+    return;
+  }
+  unsigned long long* removed = sm;
+  unsigned long long* keptw = sm + words;
+  unsigned long long* sflags = sm + 2 * words;
+  int* prefix = reinterpret_cast<int*>(sm + 2 * words + words * fw);
+  __shared__ long long s_base;
+  for (int e = threadIdx.x; e < words * fw; e += blockDim.x) {
+    sflags[e] = block_flags[e];
+    block_flags[e] = 0ull;                               // ready for the mask of the chunk after next
+  }
+  nms_scan_core_tr(mask, n, stride, removed, keptw, removed_init, sflags, fw);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < words; ++w) {
+      prefix[w] = run;
+      run += __popcll(keptw[w]);
+    }
+    const long long base = *nk_ptr;
+    s_base = base;
+    *nk_ptr = base + run;
+    *nk_hist_next = base + run;
+  }
+  __syncthreads();
+  const long long base = s_base;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long kw = keptw[i >> 6];
+    const bool k = (kw >> (i & 63)) & 1ull;
+    keep[i] = (uint8_t)k;
+    if (k) {
+      const long long pos = base + prefix[i >> 6] + __popcll(kw & ((1ull << (i & 63)) - 1ull));
+      const Box6 b = load_box(boxes + (long long)i * 6);
+      kept[2 * pos] = make_float4(b.v[0], b.v[1], b.v[2], b.v[3]);
+      kept[2 * pos + 1] = make_float4(b.v[4], b.v[5], box_volume(b), 0.f);
+      if (slot_of) state[slot_of[i]] = 1;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1054,7 +1071,7 @@ namespace ssd3d {
 struct ChunkedNmsLayout {
   int chunk, G, cells;
   long long flags_bytes, mask_bytes;
-  long long off_removed, off_nk, off_rng, off_flags, off_kept, off_mask, off_cellstart, off_cursor, off_sorted, off_slot, off_state,
+  long long off_removed, off_nk, off_rng, off_hist, off_flags, off_kept, off_mask, off_cellstart, off_cursor, off_sorted, off_slot, off_state,
       total;
 };
 static ChunkedNmsLayout chunked_nms_layout(long long n, int chunk) {
@@ -1070,6 +1087,7 @@ static ChunkedNmsLayout chunked_nms_layout(long long n, int chunk) {
   L.off_removed = o; o += align256(8ll * chunks * cw);
   L.off_nk = o; o += 256;
   L.off_rng = o; o += 256;
+  L.off_hist = o; o += align256(8ll * (chunks + 1));
   L.flags_bytes = align256(8ll * cw * ((cw + 63) / 64));
   L.off_flags = o; o += 2 * L.flags_bytes;
   L.off_kept = o; o += align256(32ll * n);
@@ -1131,21 +1149,19 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
     nms_grid_scatter_kernel<<<nb, 256, 0, st>>>(boxes_xyz, (long long)n, cell_start, cursor, slot_of, sorted);
     SSD3D_CHECK_LAUNCH();
   }
-  const int splits = 74;                    // x (B / 256) row blocks: 1184 = 148 x 8 CTAs at B = 4096
+  long long* hist = reinterpret_cast<long long*>(ws + L.off_hist);      // hist[c] = kept boxes before chunk c
   for (long long c = 0; c < chunks; ++c) {
     const long long first = c * B;
     const int rows = (int)((n - first) < B ? (n - first) : B);
     const int words = (rows + 63) / 64;
     const float* cb = boxes_xyz + first * 6;
     unsigned long long* crem = removed + c * cw;
-    if (c > 0 && use_grid) {
-      const int split = rows <= 4736 ? 2 : 1;           // 148 SMs x 64 warps = 9472 resident warps
-      nms_cross_grid_kernel<<<(unsigned)(((long long)rows * split + 7) / 8), 256, 0, st>>>(
-          cb, rows, rng, L.G, cell_start, sorted, state, max_overlap, reinterpret_cast<unsigned int*>(crem), split);
-      SSD3D_CHECK_LAUNCH();
-    } else if (c > 0) {
-      dim3 grid((unsigned)((rows + 255) / 256), (unsigned)splits);
-      nms_cross_kernel<<<grid, 256, 0, st>>>(cb, rows, kept, nk, max_overlap, reinterpret_cast<unsigned int*>(crem));
+    if (c > 0) {
+      // grid mode: the grid-pruned cross test of this chunk ran inside the previous launch; what is left are
+      // the boxes kept in chunk c-1.  Dense mode: the whole kept list.  x (B / 256) row blocks.
+      dim3 grid((unsigned)((rows + 255) / 256), use_grid ? 16u : 74u);
+      nms_cross_kernel<<<grid, 256, 0, st>>>(cb, rows, kept, use_grid ? hist + (c - 1) : hist, hist + c, max_overlap,
+                                             reinterpret_cast<unsigned int*>(crem));
       SSD3D_CHECK_LAUNCH();
     }
     unsigned long long* mask_cur = reinterpret_cast<unsigned long long*>(ws + L.off_mask + (c & 1) * L.mask_bytes);
@@ -1160,11 +1176,14 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
     const long long nfirst = first + B;
     const int nrows = (c + 1 < chunks) ? (int)((n - nfirst) < B ? (n - nfirst) : B) : 0;
     const long long nwords = (nrows + 63) / 64;
-    const unsigned blocks = 1u + (unsigned)((nwords * nwords + 7) / 8);
+    const int mask_blocks = (int)((nwords * nwords + 7) / 8);
+    const int split = nrows <= 4736 ? 2 : 1;            // 148 SMs x 64 warps = 9472 resident warps
+    const int cross_blocks = use_grid ? (int)(((long long)nrows * split + 15) / 16) : 0;
     const size_t smem = (size_t)(2 * words + words * fw) * 8 + (size_t)(words + 2) * 4;
-    nms_scan_mask_kernel<<<blocks, 512, smem, st>>>(mask_cur, cb, rows, words, B, crem, kept, nk, keep + first,
-                                                    use_grid ? slot_of + first : (const int*)nullptr, state, flags_cur,
-                                                    fw, boxes_xyz + nfirst * 6, nrows, max_overlap, mask_nxt, flags_nxt);
+    nms_scan_mask_kernel<<<(unsigned)(1 + mask_blocks + cross_blocks), 512, smem, st>>>(
+        mask_cur, cb, rows, words, B, crem, kept, nk, keep + first, use_grid ? slot_of + first : (const int*)nullptr,
+        state, flags_cur, fw, boxes_xyz + nfirst * 6, nrows, max_overlap, mask_nxt, flags_nxt, hist + (c + 1),
+        mask_blocks, rng, L.G, cell_start, sorted, reinterpret_cast<unsigned int*>(removed + (c + 1) * cw), split);
     SSD3D_CHECK_LAUNCH();
   }
   if (kept_count) {

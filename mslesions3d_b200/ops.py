@@ -288,7 +288,7 @@ def nms3d_sorted_chunked(boxes_xyz: torch.Tensor, max_overlap: float, chunk: int
                                         _stream())
     _lib.check(rc, "ssd3d_nms3d_sorted_chunked")
     per = int(chunk) if chunk else 4096
-    LAUNCHES[0] += 3 * ((n + per - 1) // per) - 1 + (4 if use_grid and n > per else 0)
+    LAUNCHES[0] += 2 * ((n + per - 1) // per) + (4 if use_grid and n > per else 0)   # delta + fused launch per chunk
     return (keep.bool(), count) if return_count else keep.bool()
 
 
