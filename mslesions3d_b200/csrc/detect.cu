@@ -788,11 +788,25 @@ __device__ __forceinline__ void nms_cross_grid_query(int gw, const float* __rest
 #pragma unroll
   for (int k = 0; k < 3; ++k) chi[k] = cell_coord(m, k, __fsub_ru(a.v[3 + k], sh[k]));
   bool found = false;
-  float w = m.W;
-  for (int level = 0; level < NMS_LEVELS && !found; ++level, w *= 0.5f) {
-    // boxes of this and every finer level have volume <= w^3: too small to reach thr against a (1 % margin
-    // over the few-ulp rounding of the exact test; false for NaN / non-positive volumes)
-    if (__fmul_rn(__fmul_rn(__fmul_rn(w, w), w), 1.01f) < __fmul_rn(thr, va)) break;
+  // Levels are walked starting from the query's own size class (where its suppressor most likely lives, so
+  // a removed box leaves early).  A level is skipped when
+  //   * its boxes are too small: volume <= w^3 < thr * vol(a)  (IoU <= min volume / max volume), or
+  //   * its boxes are too large: IoU > thr also needs extent_k(o) < extent_k(a) / thr on every axis, and every
+  //     box of level l < last has a largest extent > W / 2^(l+1).
+  // Both with margins far above the few-ulp rounding of the exact test; false for NaN / non-positive volumes.
+  const int own = box_level(m, a);
+  float too_large = 3.0e38f;
+  if (thr > 0.f && va > 1e-20f) {
+    float e = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) e = fmaxf(e, __fsub_ru(a.v[3 + k], a.v[k]));
+    too_large = __fmul_ru(__fdiv_ru(e, __fmul_rd(thr, 0.9999f)), 1.001f);
+  }
+  for (int li = 0; li < NMS_LEVELS && !found; ++li) {
+    const int level = (own + li) % NMS_LEVELS;
+    const float w = m.W * (1.0f / (float)(1 << level));          // exact power-of-two scaling
+    if (__fmul_rn(__fmul_rn(__fmul_rn(w, w), w), 1.01f) < __fmul_rn(thr, va)) continue;
+    if (level < NMS_LEVELS - 1 && w * 0.5f >= too_large) continue;
     int clo[3], hi[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -1177,7 +1191,7 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
     const int nrows = (c + 1 < chunks) ? (int)((n - nfirst) < B ? (n - nfirst) : B) : 0;
     const long long nwords = (nrows + 63) / 64;
     const int mask_blocks = (int)((nwords * nwords + 7) / 8);
-    const int split = nrows <= 4736 ? 2 : 1;            // 148 SMs x 64 warps = 9472 resident warps
+    const int split = nrows <= 4736 ? 4 : (nrows <= 9472 ? 2 : 1);   // the cross test is latency-bound: more warps per query
     const int cross_blocks = use_grid ? (int)(((long long)nrows * split + 15) / 16) : 0;
     const size_t smem = (size_t)(2 * words + words * fw) * 8 + (size_t)(words + 2) * 4;
     nms_scan_mask_kernel<<<(unsigned)(1 + mask_blocks + cross_blocks), 512, smem, st>>>(
