@@ -352,6 +352,17 @@ int ssd3d_gt_boxes_from_segmentation(const void* seg, int seg_dtype, int N, int 
                                      int max_boxes, float* boxes, int64_t* labels, int32_t* counts,
                                      int32_t* n_components, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same for segmentation_mode "instances" (utils.py:439-441,483-513): the volume holds one integer id per
+ * object; thresholds (device int32 [n_thresholds][2]) map the id range [min_c, max_c) to class c+1.  One box per
+ * id over ALL its voxels, ordered by class, then ascending id (np.unique); ids outside every range, non-integer
+ * values and ids >= id_limit are ignored; ranges must not overlap.  Same outputs and zero-volume filter as
+ * above; n_components = ids that fell into a range. */
+int64_t ssd3d_gt_boxes_instances_workspace_bytes(int N, int id_limit, int max_boxes);
+int ssd3d_gt_boxes_from_instances(const void* seg, int seg_dtype, int N, int D, int H, int W,
+                                  const int32_t* thresholds, int n_thresholds, int id_limit, int max_boxes,
+                                  float* boxes, int64_t* labels, int32_t* counts, int32_t* n_components,
+                                  void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

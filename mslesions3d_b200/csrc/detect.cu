@@ -475,14 +475,17 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const unsigned long long*
 // that defeats the 10*top_k truncation).  The reference's n x n IoU matrix
 // (ssd3d.py:407) is 25 TB at n = 2.5 M; the bit matrix above would still be 390 GB.  Here the list is
 // walked in chunks of B boxes (score order):
-//   cross : every box of the chunk against the boxes KEPT so far (compact list, 32 B per box: corners +
-//           volume) -> initial `removed` bits of the chunk.  One thread per chunk box, the kept list
-//           streamed through shared memory in tiles of 256, tiles strided over gridDim.y.
-//   mask  : nms_mask_kernel on the chunk alone (B x B/64 words)
-//   scan  : the greedy scan above, started from the cross bits; kept boxes are appended to the list.
+//   cross : every box of the chunk against the boxes KEPT so far -> initial `removed` bits of the chunk.
+//           With a threshold >= 0 through the spatial grid further down (nms_cross_grid_query); otherwise,
+//           and for the "delta" of the grid path, the dense kernel below: one thread per chunk box, a range of
+//           the compact kept list (32 B per box: corners + volume) streamed through shared memory in tiles
+//           of 256, tiles strided over gridDim.y.
+//   mask  : the bit matrix of the chunk alone (B x B/64 words, word-major, with per-block flags)
+//   scan  : the greedy scan, started from the cross bits; kept boxes are appended to the list.
 // A box is removed iff an earlier KEPT box overlaps it by more than the threshold, which is exactly the
 // reference's loop (ssd3d.py:414-426); the decisions use the same iou_exceeds() as the bit matrix.
-// Work is O(n * kept) IoU tests and 3 launches per chunk, nothing is read back by the host.
+// Two launches per chunk (nms_scan_mask_kernel, which also carries the mask and grid cross test of the NEXT
+// chunk, and the dense cross / delta pass); nothing is read back by the host.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nms_cross_kernel(const float* __restrict__ boxes, int n,
                                                         const float4* __restrict__ kept_all,

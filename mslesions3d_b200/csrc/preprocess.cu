@@ -275,6 +275,100 @@ __global__ void __launch_bounds__(256) cc_finalize_kernel(const int* __restrict_
   if (threadIdx.x == 0) counts[n] = base;
 }
 
+// ------------------------------------------------------------------------------------------------
+// "instances" mode (utils.py:439-441,483-513): the volume already holds one integer id per object, and
+// `thresholds` [(min_c, max_c)] map id ranges to classes 1, 2, ...  One box per id, [min index, max index] of
+// ALL its voxels (an id may be spread over several blobs), ordered by class, then by ascending id (np.unique).
+//   mark   table[id] = present                       (table of K = max id + 1 entries per volume)
+//   rank   per class, ids in ascending order get consecutive ranks (block scan over the table)
+//   bbox   per voxel min/max into box[rank] (same warp aggregation as above), then cc_finalize_kernel
+// Ids outside every range are ignored; ranges must not overlap (the host checks).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int inst_id(const T* __restrict__ seg, long long i, int K) {
+  const T v = seg[i];
+  const int c = (int)v;
+  return ((T)c == v && c >= 1 && c < K) ? c : 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) inst_mark_kernel(const T* __restrict__ seg, long long total, long long V, int K,
+                                                        int* __restrict__ table) {
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (g >= total) return;
+  const int id = inst_id(seg, g, K);
+  if (id) table[(g / V) * K + id] = -2;                 // present, not ranked yet (the table starts at -1)
+}
+
+__global__ void __launch_bounds__(256) inst_rank_kernel(const int* __restrict__ thr, int n_thr, int K, int max_boxes,
+                                                        int* __restrict__ table, int* __restrict__ ibox,
+                                                        int* __restrict__ cls_of_rank, int* __restrict__ root_count) {
+  __shared__ int warp_tot[8];
+  __shared__ int base;
+  const int n = blockIdx.x;
+  int* tab = table + (long long)n * K;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = 0; c < n_thr; ++c) {
+    const int lo = max(thr[2 * c], 1), hi = min(thr[2 * c + 1], K);
+    for (int id0 = lo; id0 < hi; id0 += 256) {
+      const int id = id0 + threadIdx.x;
+      const bool flag = id < hi && tab[id] == -2;
+      const unsigned m = __ballot_sync(0xffffffffu, flag);
+      if (lane == 0) warp_tot[warp] = __popc(m);
+      __syncthreads();
+      int off = base;
+      for (int q = 0; q < warp; ++q) off += warp_tot[q];
+      off += __popc(m & ((1u << lane) - 1u));
+      if (flag) {
+        if (off < max_boxes) {
+          tab[id] = off;
+          cls_of_rank[n * max_boxes + off] = c + 1;
+          int* b = ibox + ((long long)n * max_boxes + off) * 6;
+          b[0] = b[1] = b[2] = 0x7fffffff;
+          b[3] = b[4] = b[5] = -1;
+        } else {
+          tab[id] = -1;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; ++q) t += warp_tot[q]; base += t; }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) root_count[n] = base;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) inst_bbox_kernel(const T* __restrict__ seg, long long total, int D, int H, int W,
+                                                        int K, int max_boxes, const int* __restrict__ table,
+                                                        int* __restrict__ ibox) {
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long V = (long long)D * H * W;
+  int key = -1, d = 0, h = 0, w = 0;
+  if (g < total) {
+    const int id = inst_id(seg, g, K);
+    if (id) {
+      const int v = (int)(g % V);
+      const int n = (int)(g / V);
+      const int rank = table[(long long)n * K + id];
+      if (rank >= 0) key = n * max_boxes + rank;
+      w = v % W; h = (v / W) % H; d = v / (W * H);
+    }
+  }
+  const unsigned active = __ballot_sync(0xffffffffu, key >= 0);
+  if (key < 0) return;
+  const unsigned grp = __match_any_sync(active, key);
+  const int lo_d = __reduce_min_sync(grp, d), lo_h = __reduce_min_sync(grp, h), lo_w = __reduce_min_sync(grp, w);
+  const int hi_d = __reduce_max_sync(grp, d), hi_h = __reduce_max_sync(grp, h), hi_w = __reduce_max_sync(grp, w);
+  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) {
+    int* b = ibox + (long long)key * 6;
+    atomicMin(b + 0, lo_d); atomicMin(b + 1, lo_h); atomicMin(b + 2, lo_w);
+    atomicMax(b + 3, hi_d); atomicMax(b + 4, hi_h); atomicMax(b + 5, hi_w);
+  }
+}
+
 struct CcWs {
   int* L; int* R; long long* root_key; int* root_count; int* ibox; int* cls_of_rank;
 };
@@ -319,7 +413,68 @@ static int run_gt_boxes(const T* seg, int N, int D, int H, int W, int n_classes,
   return SSD3D_OK;
 }
 
+struct InstWs {
+  int* table; int* root_count; int* ibox; int* cls_of_rank;
+};
+static InstWs inst_carve(void* ws, int N, int K, int max_boxes) {
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  InstWs c;
+  c.table = reinterpret_cast<int*>(p); p += al256((size_t)N * K * 4);
+  c.root_count = reinterpret_cast<int*>(p); p += al256((size_t)N * 4);
+  c.ibox = reinterpret_cast<int*>(p); p += al256((size_t)N * max_boxes * 6 * 4);
+  c.cls_of_rank = reinterpret_cast<int*>(p);
+  return c;
+}
+
+template <typename T>
+static int run_gt_boxes_instances(const T* seg, int N, int D, int H, int W, const int* thr, int n_thr, int K,
+                                  int max_boxes, float* boxes, long long* labels, int* counts, int* n_components,
+                                  void* ws, cudaStream_t st) {
+  const long long V = (long long)D * H * W, total = V * N;
+  InstWs c = inst_carve(ws, N, K, max_boxes);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaError_t e = cudaMemsetAsync(c.table, 0xff, (size_t)N * K * 4, st);
+  if (e != cudaSuccess) return (int)e;
+  inst_mark_kernel<T><<<blocks, 256, 0, st>>>(seg, total, V, K, c.table);
+  SSD3D_CHECK_LAUNCH();
+  inst_rank_kernel<<<(unsigned)N, 256, 0, st>>>(thr, n_thr, K, max_boxes, c.table, c.ibox, c.cls_of_rank, c.root_count);
+  SSD3D_CHECK_LAUNCH();
+  inst_bbox_kernel<T><<<blocks, 256, 0, st>>>(seg, total, D, H, W, K, max_boxes, c.table, c.ibox);
+  SSD3D_CHECK_LAUNCH();
+  cc_finalize_kernel<<<(unsigned)N, 256, 0, st>>>(c.ibox, c.cls_of_rank, c.root_count, D, H, W, max_boxes, boxes, labels,
+                                                  counts, n_components);
+  SSD3D_CHECK_LAUNCH();
+  return SSD3D_OK;
+}
+
 }  // namespace ssd3d
+
+extern "C" int64_t ssd3d_gt_boxes_instances_workspace_bytes(int N, int id_limit, int max_boxes) {
+  if (N <= 0 || id_limit <= 0 || max_boxes <= 0) return 0;
+  return (int64_t)(ssd3d::al256((size_t)N * id_limit * 4) + ssd3d::al256((size_t)N * 4) +
+                   ssd3d::al256((size_t)N * max_boxes * 24) + ssd3d::al256((size_t)N * max_boxes * 4));
+}
+
+extern "C" int ssd3d_gt_boxes_from_instances(const void* seg, int seg_dtype, int N, int D, int H, int W,
+                                             const int32_t* thresholds, int n_thresholds, int id_limit, int max_boxes,
+                                             float* boxes, int64_t* labels, int32_t* counts, int32_t* n_components,
+                                             void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!seg || !thresholds || !boxes || !labels || !counts || !n_components || !workspace) return SSD3D_ERR_ARG;
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || max_boxes <= 0 || n_thresholds <= 0 || id_limit <= 1) return SSD3D_ERR_ARG;
+  const long long V = (long long)D * H * W;
+  if (V >= (1ll << 31) || (long long)N * max_boxes >= (1ll << 31) || (long long)N * id_limit >= (1ll << 31))
+    return SSD3D_ERR_UNSUPPORTED;
+  if (workspace_bytes < ssd3d_gt_boxes_instances_workspace_bytes(N, id_limit, max_boxes)) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long* lab = reinterpret_cast<long long*>(labels);
+  if (seg_dtype == 0)
+    return ssd3d::run_gt_boxes_instances<uint8_t>(static_cast<const uint8_t*>(seg), N, D, H, W, thresholds, n_thresholds,
+                                                  id_limit, max_boxes, boxes, lab, counts, n_components, workspace, st);
+  if (seg_dtype == 1)
+    return ssd3d::run_gt_boxes_instances<float>(static_cast<const float*>(seg), N, D, H, W, thresholds, n_thresholds,
+                                                id_limit, max_boxes, boxes, lab, counts, n_components, workspace, st);
+  return SSD3D_ERR_ARG;
+}
 
 extern "C" int64_t ssd3d_gt_boxes_workspace_bytes(int N, int D, int H, int W, int max_boxes) {
   if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || max_boxes <= 0) return 0;

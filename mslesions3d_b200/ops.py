@@ -834,3 +834,50 @@ def gt_boxes_from_segmentation(seg: torch.Tensor, n_classes: int = 0, max_boxes:
     if max(comps) > max_boxes:
         raise RuntimeError("segmentation has %d connected components, max_boxes=%d" % (max(comps), max_boxes))
     return [boxes[i, :counts[i]] for i in range(n)], [labels[i, :counts[i]] for i in range(n)]
+
+
+def gt_boxes_from_instances(seg: torch.Tensor, thresholds, max_boxes: int = 1024):
+    """``BoundingBoxesGeneratord`` in "instances" mode on the device (utils.py:439-441,483-513): ``seg`` holds one
+    integer id per object, ``thresholds`` = [(min_c, max_c), ...] maps the id range [min_c, max_c) to class c+1
+    (``max_c`` may be ``inf``).  One box per id over all its voxels, ordered by class then ascending id; same output
+    format, box convention and zero-volume filter as ``gt_boxes_from_segmentation``."""
+    _need_cuda(seg)
+    if seg.dim() == 5 and seg.shape[1] == 1:
+        seg = seg[:, 0]
+    if seg.dim() != 4:
+        raise RuntimeError("expected (N, D, H, W) or (N, 1, D, H, W) segmentations")
+    if seg.dtype == torch.uint8:
+        dt = 0
+    else:
+        seg, dt = seg.float(), 1
+    seg = seg.contiguous()
+    n, d, h, w = seg.shape
+    dev = seg.device
+    thr = [(float(a), float(b)) for a, b in thresholds]
+    if not thr:
+        raise ValueError("instances mode needs thresholds")          # utils.py:417
+    srt = sorted(thr)
+    if any(srt[i][1] > srt[i + 1][0] for i in range(len(srt) - 1)):
+        raise NotImplementedError("overlapping id ranges are not supported")
+    top = max(b for _, b in thr)
+    if top == float("inf"):                       # open range: the largest id present decides the table size
+        top = float(seg.max().item()) + 1.0
+    id_limit = int(min(max(2.0, top), 2.0 ** 30))
+    import math
+    thr_dev = torch.tensor([[int(math.ceil(max(a, 0.0))), int(min(math.ceil(b), id_limit)) if b != float("inf")
+                             else id_limit] for a, b in thr], dtype=torch.int32, device=dev)
+    boxes = torch.empty((n, max_boxes, 6), dtype=torch.float32, device=dev)
+    labels = torch.empty((n, max_boxes), dtype=torch.int64, device=dev)
+    meta = torch.empty((2, n), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    need = lib.ssd3d_gt_boxes_instances_workspace_bytes(n, id_limit, max_boxes)
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    rc = lib.ssd3d_gt_boxes_from_instances(seg.data_ptr(), dt, n, d, h, w, thr_dev.data_ptr(), len(thr), id_limit,
+                                           int(max_boxes), boxes.data_ptr(), labels.data_ptr(), meta[0].data_ptr(),
+                                           meta[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_gt_boxes_from_instances")
+    LAUNCHES[0] += 4
+    counts, comps = meta.cpu().tolist()
+    if max(comps) > max_boxes:
+        raise RuntimeError("segmentation has %d instances, max_boxes=%d" % (max(comps), max_boxes))
+    return [boxes[i, :counts[i]] for i in range(n)], [labels[i, :counts[i]] for i in range(n)]

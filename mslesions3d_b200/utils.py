@@ -168,8 +168,8 @@ class BoundingBoxesGeneratord:
     """Device-side mirror of the reference's dictionary transform (utils.py:398-513): ``d["boxes"]``,
     ``d["labels"]`` from the segmentation under each key.  ``segmentation_mode`` "binary" (every non-zero voxel,
     label 1) and "classes" (voxels equal to c, for ``classes = [1..n_classes]`` as the data modules pass them,
-    datasets.py:405) run on the GPU; "instances" (pre-labelled volumes with per-class id ranges) is data-set
-    preparation that the synthetic / ``classes`` pipelines never take and is not provided.
+    datasets.py:405) and "instances" (pre-labelled volumes, ``thresholds`` = per-class id ranges [min, max)) all
+    run on the GPU.
 
     The segmentation may be one volume ((D,H,W) or (1,D,H,W): boxes (n,6), labels (n,), like the reference) or a
     batch (N,1,D,H,W): lists of per-volume tensors, the format ``training_step`` consumes (ssd3d.py:470-472)."""
@@ -185,11 +185,11 @@ class BoundingBoxesGeneratord:
         assert segmentation_mode in ["instances", "binary", "classes"]
         assert segmentation_mode != "binary" or (not classes and not n_classes) or n_classes == 1
         assert segmentation_mode != "classes" or type(classes) in [list, dict]
-        if segmentation_mode == "instances":
-            raise NotImplementedError("segmentation_mode='instances' is not part of the accelerated path")
+        assert segmentation_mode != "instances" or thresholds          # utils.py:417
         if segmentation_mode == "classes" and list(classes) != list(range(1, n_classes + 1)):
             raise NotImplementedError("classes must be [1..n_classes] (datasets.py:405)")
         self.segmentation_mode = segmentation_mode
+        self.thresholds = thresholds
         self.classes = classes
         self.n_classes = n_classes
         self.max_boxes = max_boxes
@@ -198,8 +198,11 @@ class BoundingBoxesGeneratord:
         from . import ops
         batched = seg.dim() == 5
         s = seg if batched else seg.reshape((1,) + tuple(seg.shape[-3:]))
-        boxes, labels = ops.gt_boxes_from_segmentation(
-            s, 0 if self.segmentation_mode == "binary" else int(self.n_classes), self.max_boxes)
+        if self.segmentation_mode == "instances":
+            boxes, labels = ops.gt_boxes_from_instances(s, self.thresholds, self.max_boxes)
+        else:
+            boxes, labels = ops.gt_boxes_from_segmentation(
+                s, 0 if self.segmentation_mode == "binary" else int(self.n_classes), self.max_boxes)
         return (boxes, labels) if batched else (boxes[0], labels[0])
 
     def __call__(self, data):

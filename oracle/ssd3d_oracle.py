@@ -702,3 +702,25 @@ def gt_boxes_from_segmentation(seg, n_classes: int = 0):
     vol = (b[:, 3] - b[:, 0]) * (b[:, 4] - b[:, 1]) * (b[:, 5] - b[:, 2])
     keep = vol != 0.0
     return b[keep], l[keep]
+
+
+def gt_boxes_from_instances(seg, thresholds):
+    """``BoundingBoxesGeneratord`` "instances" mode (utils.py:439-441,483-513) on one volume (D, H, W) whose voxels
+    hold one id per object: per class c (id range [min_c, max_c)), one box [min index, max index] / image size per
+    id in ascending id order (np.unique), label c+1; zero-volume boxes dropped (utils.py:475-480)."""
+    seg = np.squeeze(np.asarray(seg))
+    ids = [v for v in np.unique(seg) if v != 0]                                 # utils.py:491-492
+    boxes, labels = [], []
+    for c, (lo, hi) in enumerate(thresholds):                                   # utils.py:493-511
+        for v in ids:
+            if lo <= v < hi:
+                idx = np.argwhere(seg == v)
+                boxes.append(list(idx.min(0)) + list(idx.max(0)))
+                labels.append(c + 1)
+    if not boxes:
+        return torch.zeros((0, 6)), torch.zeros((0,), dtype=torch.long)
+    b = torch.tensor(boxes, dtype=torch.float32) / torch.tensor(list(seg.shape) * 2, dtype=torch.float32)
+    l = torch.tensor(labels, dtype=torch.long)
+    vol = (b[:, 3] - b[:, 0]) * (b[:, 4] - b[:, 1]) * (b[:, 5] - b[:, 2])
+    keep = vol != 0.0
+    return b[keep], l[keep]

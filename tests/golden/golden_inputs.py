@@ -186,3 +186,40 @@ def gtbox_inputs(case):
                 seg[16 + k // 4, 10 + (k % 4), min(31, 17 + k // 3)] = 1
                 seg[min(31, 17 + k // 4), 10 + (k % 4), 16 + k // 3] = 1
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# BoundingBoxesGeneratord "instances" mode (utils.py:439-441,483-513): volumes that already hold one id per object
+# ---------------------------------------------------------------------------------------------------
+GTBOX_INSTANCE_CASES = {
+    # two classes by id range; ids outside every range (5, 3500) are ignored; id 1003 is split over two far-apart
+    # blobs (one box around both); id 2002 is one voxel thick (zero volume, dropped); class-2 ids are painted
+    # before class-1 ids so that the output order (class, then id) differs from the voxel order
+    "two_ranges": dict(seed=60, size=(40, 36, 44), n_volumes=2, thresholds=[(1000, 2000), (2000, 3000)]),
+    # one open range (1, inf), small ids, the last volume is empty
+    "open_range": dict(seed=61, size=(24, 28, 20), n_volumes=3, thresholds=[(1, float("inf"))]),
+}
+
+
+def gtbox_instance_inputs(case):
+    """-> float32 array (n_volumes, D, H, W) of instance ids."""
+    rng = np.random.RandomState(case["seed"])
+    D, H, W = case["size"]
+    out = np.zeros((case["n_volumes"], D, H, W), dtype=np.float32)
+    two = len(case["thresholds"]) == 2
+    for v in range(case["n_volumes"]):
+        if not two and v == case["n_volumes"] - 1:
+            continue                                    # empty volume
+        seg = out[v]
+        ids = ([2000 + k for k in range(1, 5)] + [1000 + k for k in range(1, 7)] + [5, 3500]) if two \
+            else [int(k) for k in rng.permutation(np.arange(1, 12))]
+        for i in ids:
+            side = rng.randint(2, 9)
+            c = [rng.randint(0, dim - side) for dim in (D, H, W)]
+            seg[c[0]:c[0] + side, c[1]:c[1] + side, c[2]:c[2] + side] = i
+        if two:
+            seg[1:4, 1:4, 1:4] = 1003                   # second blob of id 1003
+            seg[D - 4:D - 1, H - 4:H - 1, W - 4:W - 1] = 1003
+            seg[seg == 2002] = 0
+            seg[7, 3:9, 5:12] = 2002                    # plate: zero extent along axis 0
+    return out

@@ -60,12 +60,37 @@ def gtbox_goldens(utils):
     torch.save(out, os.path.join(HERE, "gtbox.pt"))
 
 
+def gtbox_instance_goldens(utils):
+    """BoundingBoxesGeneratord.converter in "instances" mode (utils.py:439-441,483-513) -> gtbox_instances.pt."""
+    from tests.golden.golden_inputs import GTBOX_INSTANCE_CASES, gtbox_instance_inputs
+    out = {}
+    for name, case in GTBOX_INSTANCE_CASES.items():
+        segs = gtbox_instance_inputs(case)
+        gen = utils.BoundingBoxesGeneratord(keys=["seg"], segmentation_mode="instances", thresholds=case["thresholds"])
+        res = []
+        for v in range(segs.shape[0]):
+            try:
+                res.append(gen.converter(segs[v][None].copy()))
+            except RuntimeError as e:      # a volume without objects: FloatTensor([]) / FloatTensor(6) raises
+                assert segs[v].sum() == 0, e
+                res.append((None, None))
+        out[name] = dict(boxes=[None if b is None else b.clone() for b, _ in res],
+                         labels=[None if l is None else l.clone() for _, l in res],
+                         in_sum=float(segs.astype(np.float64).sum()))
+        print("gtbox instances", name, [None if b is None else (int(b.shape[0]), l.tolist()) for b, l in res])
+    torch.save(out, os.path.join(HERE, "gtbox_instances.pt"))
+
+
 def main():
     ssd3d, mobilenet, utils = load_reference()
     torch.set_num_threads(1)
     if len(sys.argv) > 1 and sys.argv[1] == "gtbox":      # only this section (the others are unchanged)
         gtbox_goldens(utils)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "gtbox_instances":
+        gtbox_instance_goldens(utils)
+        return
+    gtbox_instance_goldens(utils)
     gtbox_goldens(utils)
 
     # ---- priors --------------------------------------------------------------

@@ -31,6 +31,43 @@ def test_gt_boxes_match_reference_golden(name, dtype):
         assert torch.equal(labels[v].cpu(), gold["labels"][v])
 
 
+@pytest.mark.parametrize("name", list(GI.GTBOX_INSTANCE_CASES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.uint8])
+def test_gt_boxes_instances_match_reference_golden(name, dtype):
+    """"instances" mode (utils.py:439-441,483-513) against the reference's converter: bit-exact boxes in class-then-id
+    order, ids outside the ranges ignored, split ids boxed as one, plates dropped, empty volume."""
+    case, gold = GI.GTBOX_INSTANCE_CASES[name], load_golden("gtbox_instances.pt")[name]
+    segs = GI.gtbox_instance_inputs(case)
+    if dtype == torch.uint8 and segs.max() > 255:
+        pytest.skip("ids beyond uint8")
+    boxes, labels = _ops().gt_boxes_from_instances(torch.from_numpy(segs).to(dtype).cuda(), case["thresholds"])
+    for v in range(segs.shape[0]):
+        if gold["boxes"][v] is None:
+            assert boxes[v].shape == (0, 6) and labels[v].shape == (0,)
+            continue
+        assert torch.equal(boxes[v].cpu(), gold["boxes"][v]), name
+        assert torch.equal(labels[v].cpu(), gold["labels"][v])
+
+
+def test_gt_boxes_instances_many_ids_against_oracle():
+    """Hundreds of ids in three ranges (one of them open), batch of 2, ids listed out of order in the volume."""
+    rs = np.random.RandomState(9)
+    seg = np.zeros((2, 30, 34, 26), dtype=np.float32)
+    for v in range(2):
+        for i in rs.permutation(np.concatenate([np.arange(10, 140), np.arange(500, 620), np.arange(5000, 5030)])):
+            c = [rs.randint(0, d - 3) for d in seg.shape[1:]]
+            e = rs.randint(1, 4, size=3)
+            seg[v, c[0]:c[0] + e[0], c[1]:c[1] + e[1], c[2]:c[2] + e[2]] = i
+    thr = [(500, 1000), (10, 100), (1000, float("inf"))]
+    boxes, labels = _ops().gt_boxes_from_instances(torch.from_numpy(seg).cuda(), thr)
+    for v in range(2):
+        b, l = O.gt_boxes_from_instances(seg[v], thr)
+        assert torch.equal(boxes[v].cpu(), b) and torch.equal(labels[v].cpu(), l)
+        assert set(l.tolist()) == {1, 2, 3}
+    with pytest.raises(NotImplementedError):
+        _ops().gt_boxes_from_instances(torch.from_numpy(seg).cuda(), [(1, 100), (50, 200)])
+
+
 @pytest.mark.parametrize("size,batch", [((96, 96, 96), 4), ((33, 47, 61), 3), ((160, 192, 160), 1)])
 def test_gt_boxes_of_generated_volumes(size, batch):
     """Masks of the synthetic generator (touching cubes merge) at BASELINE sizes: same boxes as the host path that
@@ -65,8 +102,13 @@ def test_bounding_boxes_generator_transform_interface():
     batch = torch.from_numpy(np.stack([mask, np.zeros_like(mask)]).astype(np.float32))[:, None].cuda()
     d = utils.BoundingBoxesGeneratord(keys="seg", segmentation_mode="binary")({"seg": batch})
     assert torch.equal(d["boxes"][0].cpu(), want) and d["boxes"][1].shape == (0, 6)
-    with pytest.raises(NotImplementedError):
-        utils.BoundingBoxesGeneratord(keys=["seg"], segmentation_mode="instances", thresholds=[(1, 100)])
+    with pytest.raises(AssertionError):            # utils.py:417: instances mode needs thresholds
+        utils.BoundingBoxesGeneratord(keys=["seg"], segmentation_mode="instances")
+    inst = utils.BoundingBoxesGeneratord(keys=["seg"], segmentation_mode="instances", thresholds=[(1, 100)])
+    d = inst({"seg": torch.from_numpy(mask.astype(np.float32))[None].cuda() * 7})      # one id: one box around all cubes
+    pos = np.argwhere(mask)
+    assert d["labels"].cpu().tolist() == [1]
+    assert torch.equal(d["boxes"].cpu()[0], torch.tensor(list(pos.min(0)) + list(pos.max(0)), dtype=torch.float32) / 48)
     with pytest.raises(KeyError):
         gen({"image": batch})
     with pytest.raises(RuntimeError):              # more components than the caller allowed for

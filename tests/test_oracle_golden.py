@@ -163,6 +163,21 @@ def test_gt_boxes_match_reference(name):
         assert torch.equal(b, gold["boxes"][v]) and torch.equal(l, gold["labels"][v])
 
 
+@pytest.mark.parametrize("name", list(GI.GTBOX_INSTANCE_CASES))
+def test_gt_boxes_instances_match_reference(name):
+    """Oracle "instances" mode vs BoundingBoxesGeneratord.converter(segmentation_mode="instances") of the unmodified
+    reference: boxes bit-exact, class-then-id order, ids outside the ranges ignored, zero-volume filter."""
+    case, gold = GI.GTBOX_INSTANCE_CASES[name], load_golden("gtbox_instances.pt")[name]
+    segs = GI.gtbox_instance_inputs(case)
+    assert float(segs.astype("float64").sum()) == gold["in_sum"]
+    for v in range(segs.shape[0]):
+        b, l = O.gt_boxes_from_instances(segs[v], case["thresholds"])
+        if gold["boxes"][v] is None:           # the reference raises on a volume without objects
+            assert b.shape == (0, 6) and l.shape == (0,)
+            continue
+        assert torch.equal(b, gold["boxes"][v]) and torch.equal(l, gold["labels"][v])
+
+
 def test_synthetic_ground_truth_is_what_the_extractor_finds():
     """The in-memory generator's GT boxes (synthetic.boxes_from_mask, scipy labelling as the reference) equal the
     oracle's flood-fill extraction on the generator's own masks, touching cubes included."""
