@@ -610,12 +610,12 @@ __device__ __forceinline__ void nms_scan_core_tr(const unsigned long long* __res
 // Spatial pruning of the cross test.  With a threshold >= 0 only boxes that really intersect can suppress
 // each other, so the kept boxes a chunk box has to be tested against lie in a small neighbourhood.  Once
 // per call ALL n boxes are counting-sorted into a uniform G^3 grid by their minimum corner (x fastest),
-// as 32-byte records {corners, volume}, with one `state` byte per slot that the scan kernel sets when the
+// as 32-byte records {corners, volume}, with one `state` BIT per slot that the scan kernel sets when the
 // box is kept.  A kept box o can intersect a query box a only if, per axis,
 //     o.min <= a.max   and   o.min >= a.min - wmax      (wmax = largest extent of any box, rounded up)
 // and cell() is monotone, so the slots to visit are the cells [cell(a.min - wmax), cell(a.max)]: per
 // (y, z) row one contiguous slot range.  One warp per query box: lanes stride over the range, look at the
-// state byte and test only kept boxes.  Boxes of the same or later chunks still have state 0, which is
+// state bits and test only kept boxes.  Boxes of the same or later chunks still have state 0, which is
 // exactly the "earlier kept boxes" the greedy loop asks for.  Decisions are unchanged (same iou_exceeds).
 // ------------------------------------------------------------------------------------------------
 // Size levels: a single very large box would widen every query's neighbourhood, so the grid is replicated
@@ -764,10 +764,10 @@ __device__ __forceinline__ void nms_cross_grid_query(int gw, const float* __rest
                                                      const unsigned int* __restrict__ rng, int G,
                                                      const int* __restrict__ cell_start,
                                                      const float4* __restrict__ sorted,
-                                                     const uint8_t* __restrict__ state, float thr,
+                                                     const unsigned int* __restrict__ state32, float thr,
                                                      unsigned int* __restrict__ rem32, int split) {
-  // `split` warps share a query (they walk alternate rows): a chunk has too few boxes to fill the machine with
-  // one latency-bound warp each
+  // `split` warps share a query (they take alternate batches of 32 rows): a chunk has too few boxes to fill
+  // the machine with one latency-bound warp each
   const int lane = threadIdx.x & 31;
   const int i = gw / split, part = gw - i * split;
   if (i >= n) return;                                   // whole warp
@@ -818,39 +818,69 @@ __device__ __forceinline__ void nms_cross_grid_query(int gw, const float* __rest
     }
     const int ny = hi[1] - clo[1] + 1;
     const int nrows = ny * (hi[2] - clo[2] + 1);
-    for (int r0 = 0; r0 < nrows && !found; r0 += 32) {
-      // every lane fetches the slot range of one (y, z) row; the warp then walks the rows one by one
-      int my_begin = 0, my_end = 0;
+    for (int r0 = part * 32; r0 < nrows && !found; r0 += 32 * split) {
+      // Every lane owns one (y, z) row = one contiguous slot range, and reads the kept BITS of that range one
+      // 32-slot word per round (a row is 1-3 words).  The set bits of all 32 lanes are then dealt out evenly:
+      // candidate j lives in the lane s with excl[s] <= j < incl[s] (binary search over the lanes' prefix sums),
+      // at the (j - excl[s] + 1)-th set bit of that lane's word.  One memory round trip fetches the state of up
+      // to 1024 slots, and every box load that follows is a really kept box.
+      int begin = 0, end = 0;
       const int r = r0 + lane;
       if (r < nrows) {
         const int cz = clo[2] + r / ny, cy = clo[1] + r % ny;
         const int base = ((level * G + cz) * G + cy) * G;
-        my_begin = cell_start[base + clo[0]];
-        my_end = cell_start[base + hi[0] + 1];
+        begin = cell_start[base + clo[0]];
+        end = cell_start[base + hi[0] + 1];
       }
-      const int nr = min(32, nrows - r0);
-      for (int t = part; t < nr && !found; t += split) {
-        const int begin = __shfl_sync(0xffffffffu, my_begin, t);
-        const int end = __shfl_sync(0xffffffffu, my_end, t);
-        if (begin == end) continue;
-        bool hit = false;
-        int k = begin + lane;
-        uint8_t s_next = (k < end) ? state[k] : (uint8_t)0;
-        while (k < end) {
-          const uint8_t s = s_next;
-          const int kn = k + 32;
-          s_next = (kn < end) ? state[kn] : (uint8_t)0;
-          if (s && !hit) {
-            const float4 p = sorted[2ll * k], q = sorted[2ll * k + 1];
+      bool more = end > begin;
+      int wi = begin >> 5;
+      const int wlast = (end - 1) >> 5;
+      while (!found && __any_sync(0xffffffffu, more)) {
+        unsigned int bits = 0u;
+        if (more) {
+          bits = state32[wi];
+          const int lo_bit = begin - (wi << 5), hi_bit = end - (wi << 5);
+          if (lo_bit > 0) bits &= 0xffffffffu << lo_bit;
+          if (hi_bit < 32) bits &= (1u << hi_bit) - 1u;
+        }
+        const int base_slot = wi << 5;
+        const int pc = __popc(bits);
+        int incl = pc;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += y;
+        }
+        const int excl = incl - pc;
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int j0 = 0; j0 < total && !found; j0 += 32) {
+          const int j = j0 + lane;
+          int src = 0;                                  // largest lane with excl <= j
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const int cand = src + step;
+            const int ex = __shfl_sync(0xffffffffu, excl, cand & 31);
+            if (cand < 32 && ex <= j) src = cand;
+          }
+          const unsigned int word_s = __shfl_sync(0xffffffffu, bits, src);
+          const int base_s = __shfl_sync(0xffffffffu, base_slot, src);
+          const int excl_s = __shfl_sync(0xffffffffu, excl, src);
+          bool hit = false;
+          if (j < total) {
+            const long long k = base_s + (int)__fns(word_s, 0u, j - excl_s + 1);
+            const float4 p = sorted[2 * k], q = sorted[2 * k + 1];
             Box6 o;
             o.v[0] = p.x; o.v[1] = p.y; o.v[2] = p.z; o.v[3] = p.w; o.v[4] = q.x; o.v[5] = q.y;
             const float inter = box_intersection(a, o);
             const float uni = __fsub_rn(__fadd_rn(va, q.z), inter);
             hit = iou_exceeds(inter, uni, thr);
           }
-          k = kn;
+          found = __any_sync(0xffffffffu, hit);
         }
-        found = __any_sync(0xffffffffu, hit);
+        if (more) {
+          if (wi >= wlast) more = false;
+          else ++wi;
+        }
       }
     }
   }
@@ -862,14 +892,14 @@ __device__ __forceinline__ void nms_cross_grid_query(int gw, const float* __rest
 //   * CTAs 1 .. mask_blocks: its word-major bit matrix and block flags into the other buffer (8 tiles of
 //     64 x 64 per CTA);
 //   * the rest: its grid-pruned cross test (16 warps per CTA).  They read `state` while CTA 0 may be setting
-//     bytes of chunk c: harmless, a set byte is always a really kept EARLIER box; what they can miss -- boxes
+//     bits of chunk c: harmless, a set bit is always a really kept EARLIER box; what they can miss -- boxes
 //     kept in chunk c -- is covered afterwards by a dense "delta" pass over kept-list entries
 //     [nk_hist[c], nk_hist[c+1]) (at most one chunk of boxes, ~10 us).
 // This takes both the matrix and the cross test off the serial path: per chunk it is scan + delta.
 __global__ void __launch_bounds__(512) nms_scan_mask_kernel(
     const unsigned long long* __restrict__ mask, const float* __restrict__ boxes, int n, int words, int stride,
     const unsigned long long* __restrict__ removed_init, float4* __restrict__ kept, long long* __restrict__ nk_ptr,
-    uint8_t* __restrict__ keep, const int* __restrict__ slot_of, uint8_t* __restrict__ state,
+    uint8_t* __restrict__ keep, const int* __restrict__ slot_of, unsigned int* __restrict__ state,
     unsigned long long* __restrict__ block_flags, int fw,
     const float* __restrict__ boxes_next, int n_next, float thr, unsigned long long* __restrict__ mask_next,
     unsigned long long* __restrict__ flags_next, long long* __restrict__ nk_hist_next, int mask_blocks,
@@ -954,7 +984,10 @@ __global__ void __launch_bounds__(512) nms_scan_mask_kernel(
       const Box6 b = load_box(boxes + (long long)i * 6);
       kept[2 * pos] = make_float4(b.v[0], b.v[1], b.v[2], b.v[3]);
       kept[2 * pos + 1] = make_float4(b.v[4], b.v[5], box_volume(b), 0.f);
-      if (slot_of) state[slot_of[i]] = 1;
+      if (slot_of) {
+        const int slot = slot_of[i];
+        atomicOr(&state[slot >> 5], 1u << (slot & 31));
+      }
     }
   }
 }
@@ -1142,7 +1175,7 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
   int* cursor = reinterpret_cast<int*>(ws + L.off_cursor);
   float4* sorted = reinterpret_cast<float4*>(ws + L.off_sorted);
   int* slot_of = reinterpret_cast<int*>(ws + L.off_slot);
-  uint8_t* state = ws + L.off_state;
+  unsigned int* state = reinterpret_cast<unsigned int*>(ws + L.off_state);   // one kept bit per grid slot
   cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)L.off_kept, st);      // removed bits, kept counter, grid range, flags
   if (e != cudaSuccess) return (int)e;
   const int B = L.chunk, cw = B / 64, fw = (cw + 63) / 64;
@@ -1154,7 +1187,7 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
     if (e != cudaSuccess) return (int)e;
     e = cudaMemsetAsync(cursor, 0, (size_t)L.cells * 4, st);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemsetAsync(state, 0, (size_t)n, st);
+    e = cudaMemsetAsync(state, 0, (size_t)((n + 31) / 32) * 4, st);
     if (e != cudaSuccess) return (int)e;
     const unsigned nb = (unsigned)((n + 255) / 256);
     nms_grid_range_kernel<<<nb < 1184u ? nb : 1184u, 256, 0, st>>>(boxes_xyz, (long long)n, rng);
@@ -1194,7 +1227,7 @@ extern "C" int ssd3d_nms3d_sorted_chunked(const float* boxes_xyz, int64_t n, flo
     const int nrows = (c + 1 < chunks) ? (int)((n - nfirst) < B ? (n - nfirst) : B) : 0;
     const long long nwords = (nrows + 63) / 64;
     const int mask_blocks = (int)((nwords * nwords + 7) / 8);
-    const int split = nrows <= 4736 ? 4 : (nrows <= 9472 ? 2 : 1);   // the cross test is latency-bound: more warps per query
+    const int split = nrows <= 4736 ? 2 : 1;            // 148 SMs x 64 warps = 9472 resident warps
     const int cross_blocks = use_grid ? (int)(((long long)nrows * split + 15) / 16) : 0;
     const size_t smem = (size_t)(2 * words + words * fw) * 8 + (size_t)(words + 2) * 4;
     nms_scan_mask_kernel<<<(unsigned)(1 + mask_blocks + cross_blocks), 512, smem, st>>>(
