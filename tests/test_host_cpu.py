@@ -229,3 +229,24 @@ def test_dataset_directory_round_trip(tmp_path):
     assert subjects == ["0000", "0001", "0002"] and (vols == want).all()
     for a, b, la, lb in zip(boxes, wb, labels, wl):
         assert (a == b).all() and (la == lb).all()
+
+
+def test_long_list_detect_routing_and_key_decoding():
+    """Host logic of the any-length detect path: which (P, top_k) leave the fused kernel (ssd3d_b200.h: P > SORT_MAX
+    and 10*top_k > SORT_MAX/2), and the {~orderable(score) << 32 | prior} key layout the device kernels emit."""
+    import torch
+    from mslesions3d_b200 import _lib, ops
+    assert not ops.detect_needs_long_lists(9344, 100)               # C2
+    assert not ops.detect_needs_long_lists(9344, 50000)             # P <= SORT_MAX: one block sorts everything
+    assert not ops.detect_needs_long_lists(2501400, 800)            # 8000 candidates through the fused NMS
+    assert ops.detect_needs_long_lists(2501400, 820)
+    assert ops.detect_needs_long_lists(_lib.SORT_MAX + 1, 50000)    # model_insight.py:146
+    score = torch.tensor([1.0, 0.75, 0.5, 1e-30, 0.0, 0.2500001])
+    bits = score.view(torch.int32).to(torch.int64) | 0x80000000      # orderable() of a non-negative float
+    keys = (((~bits) & 0xFFFFFFFF) << 32) | torch.arange(6)
+    assert bool((keys >= 0).all())                                   # compare equal as signed and unsigned
+    assert torch.equal(ops._key_scores(keys), score)
+    order = torch.argsort(keys)                                      # ascending key = descending score
+    assert order.tolist() == [0, 1, 2, 5, 3, 4]
+    with __import__("pytest").raises(RuntimeError):
+        ops.nms3d_sorted_chunked(torch.zeros(4, 6), 0.5)             # CPU tensors are refused: no CPU path
