@@ -35,6 +35,14 @@ DETECT_CASES = {
     "cube96": dict(channels=1, size=(96, 96, 96), batch=1, seed=15, min_score=0.2, max_overlap=0.5, top_k=300),
 }
 
+# detect_objects beyond the fused kernel's limits (P > 16384 priors and 10*top_k > 8192): a layer-0 head on a
+# non-cubic volume gives 25 016 priors; min_score keeps ~12 000 of them, top_k = 900 truncates the list to 9 000
+# candidates that ALL go through the greedy NMS (the reference builds a 9 000 x 9 000 IoU matrix here)
+DETECT_LONG_CASES = {
+    "layer0_topk900": dict(channels=1, size=(32, 48, 32), batch=1, seed=16, min_score=0.45, max_overlap=0.5, top_k=900,
+                           aspect_ratios={0: [1.], 3: [1.], 5: [1.], 7: [1.]}),
+}
+
 MATCH_CASES = {
     "hard05": dict(channels=1, size=(64, 64, 64), seed=20, threshold=0.5, n_obj=[3, 1, 6, 0]),
     "soft": dict(channels=1, size=(64, 64, 64), seed=21, threshold=[0.1, 0.2], n_obj=[2, 5, 4, 3]),
@@ -54,6 +62,22 @@ def forward_inputs(case):
                              seed=100 + case["seed"])
     x = synthetic.make_batch(case["batch"], case["channels"], case["size"], first_idx=7 * case["seed"])
     return sd, torch.from_numpy(x)
+
+
+def detect_long_inputs(case, n_priors):
+    """Like ``detect_inputs`` for tens of thousands of priors, where random fp32 probabilities would collide: the
+    class-1 probabilities are a random permutation of (k + 0.5) / P (spacing far above an fp32 ulp), so the
+    reference's unstable sort has a unique answer."""
+    g = torch.Generator().manual_seed(case["seed"])
+    n = case["batch"]
+    locs = torch.randn(n, n_priors, 6, generator=g) * 0.7
+    p = torch.stack([(torch.randperm(n_priors, generator=g).double() + 0.5) / n_priors for _ in range(n)])
+    scores = torch.stack([torch.zeros_like(p), torch.log(p / (1.0 - p))], 2).float()
+    probs = torch.softmax(scores, 2)
+    for i in range(n):
+        if torch.unique(probs[i, :, 1]).numel() != n_priors:
+            raise AssertionError("tie in golden scores; change the seed of case %r" % (case,))
+    return locs, scores
 
 
 def detect_inputs(case, n_priors):

@@ -81,9 +81,29 @@ def gtbox_instance_goldens(utils):
     torch.save(out, os.path.join(HERE, "gtbox_instances.pt"))
 
 
+def detect_long_goldens(ssd3d):
+    """LSSD3D.detect_objects of the reference on candidate lists beyond the fused kernel's limits -> detect_long.pt."""
+    from tests.golden.golden_inputs import DETECT_LONG_CASES, detect_long_inputs
+    out = {}
+    for name, case in DETECT_LONG_CASES.items():
+        m = build_reference_model(ssd3d, case)
+        locs, scores = detect_long_inputs(case, m.priors_cxcycz.shape[0])
+        with torch.no_grad():
+            b, l, s = m.detect_objects(locs, scores, case["min_score"], case["max_overlap"], case["top_k"])
+        out[name] = dict(boxes=[t.clone() for t in b], labels=[t.clone() for t in l], scores=[t.clone() for t in s],
+                         n_priors=int(m.priors_cxcycz.shape[0]),
+                         in_sum=checksum(torch.cat([locs.flatten(), scores.flatten()])))
+        print("detect_long", name, m.priors_cxcycz.shape[0], [t.shape[0] for t in b])
+    torch.save(out, os.path.join(HERE, "detect_long.pt"))
+
+
 def main():
     ssd3d, mobilenet, utils = load_reference()
     torch.set_num_threads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "detect_long":
+        torch.set_num_threads(8)
+        detect_long_goldens(ssd3d)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "gtbox":      # only this section (the others are unchanged)
         gtbox_goldens(utils)
         return

@@ -78,6 +78,26 @@ def test_detect_matches_reference(name):
         assert idx[i].shape == l[i].shape
 
 
+@pytest.mark.parametrize("name", list(GI.DETECT_LONG_CASES))
+def test_detect_long_lists_match_reference(name):
+    """detect_objects of the unmodified reference beyond the fused kernel's limits (25 016 priors, 9 000 candidates
+    through the greedy NMS, top-k cut of the kept list): pins the oracle that the any-length GPU path is tested
+    against (tests/test_gpu_nms_long.py)."""
+    case, gold = GI.DETECT_LONG_CASES[name], load_golden("detect_long.pt")[name]
+    priors = O.prior_boxes_fast(case["size"], case["aspect_ratios"], in_channels=case["channels"])
+    assert priors.shape[0] == gold["n_priors"] > 16384 and 10 * case["top_k"] > 8192
+    assert torch.equal(priors, O.prior_boxes(case["size"], case["aspect_ratios"], in_channels=case["channels"]))
+    locs, scores = GI.detect_long_inputs(case, priors.shape[0])
+    assert GI.checksum(torch.cat([locs.flatten(), scores.flatten()])) == gold["in_sum"]
+    b, l, s, idx = O.detect_objects(locs, scores, priors, case["min_score"], case["max_overlap"], case["top_k"],
+                                    return_indices=True)
+    for i in range(case["batch"]):
+        assert l[i].shape[0] == case["top_k"]
+        assert torch.equal(l[i], gold["labels"][i])
+        assert torch.equal(s[i], gold["scores"][i])
+        assert torch.equal(b[i], gold["boxes"][i])
+
+
 @pytest.mark.parametrize("name", list(GI.MATCH_CASES))
 def test_multibox_loss_matches_reference(name):
     case, gold = GI.MATCH_CASES[name], load_golden("match.pt")[name]
