@@ -724,3 +724,49 @@ def gt_boxes_from_instances(seg, thresholds):
     vol = (b[:, 3] - b[:, 0]) * (b[:, 4] - b[:, 1]) * (b[:, 5] - b[:, 2])
     keep = vol != 0.0
     return b[keep], l[keep]
+
+
+def greedy_nms_grid(boxes_sorted: torch.Tensor, max_overlap: float) -> torch.Tensor:
+    """The same keep mask as :func:`greedy_nms` (ssd3d.py:407-426) for lists far beyond what the n x n formulation
+    can hold on the CPU (hundreds of thousands of boxes), for ``max_overlap >= 0`` and finite, well-formed boxes.
+
+    Boxes are visited in score order; the kept ones are hashed by the cell of their minimum corner (cell edge = the
+    largest extent of any box, so two intersecting boxes are at most one cell apart on every axis), and a box is
+    tested, with the reference's exact fp32 IoU arithmetic (utils.py:105-149, one rounded op at a time), only
+    against the kept boxes of the 27 surrounding cells.  IoU > max_overlap >= 0 needs a positive intersection, so
+    no other kept box can suppress it.  Checked against :func:`greedy_nms` in tests/test_oracle_golden.py."""
+    if not max_overlap >= 0:
+        raise ValueError("greedy_nms_grid needs max_overlap >= 0")
+    b = boxes_sorted.numpy().astype(np.float32)
+    n = b.shape[0]
+    keep = np.zeros(n, dtype=bool)
+    if n == 0:
+        return torch.from_numpy(keep)
+    thr = np.float32(max_overlap)
+    ext = b[:, 3:] - b[:, :3]
+    cell = float(max(ext.max(), 1e-6))
+    lo = b[:, :3].min(0)
+    cells = np.floor((b[:, :3] - lo) / cell).astype(np.int64)
+    vol = (ext[:, 0] * ext[:, 1]) * ext[:, 2]                                  # utils.py:142-147
+    buckets: Dict[Tuple[int, int, int], List[int]] = {}
+    offsets = [(dx, dy, dz) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)]
+    for i in range(n):
+        cx, cy, cz = (int(v) for v in cells[i])
+        cand: List[int] = []
+        for dx, dy, dz in offsets:
+            lst = buckets.get((cx + dx, cy + dy, cz + dz))
+            if lst:
+                cand.extend(lst)
+        suppressed = False
+        if cand:
+            o = b[cand]
+            d = np.minimum(b[i, 3:], o[:, 3:]) - np.maximum(b[i, :3], o[:, :3])  # utils.py:119-121
+            d = np.where(d < 0, np.float32(0), d)
+            inter = (d[:, 0] * d[:, 1]) * d[:, 2]
+            union = (vol[i] + vol[cand]) - inter                                  # utils.py:148
+            with np.errstate(divide="ignore", invalid="ignore"):
+                suppressed = bool(((inter / union) > thr).any())                  # NaN > thr is False
+        if not suppressed:
+            keep[i] = True
+            buckets.setdefault((cx, cy, cz), []).append(i)
+    return torch.from_numpy(keep)

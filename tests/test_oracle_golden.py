@@ -208,3 +208,25 @@ def test_synthetic_ground_truth_is_what_the_extractor_finds():
         b, l = O.gt_boxes_from_segmentation(mask, 0)
         want = synthetic.boxes_from_mask(mask)
         assert np.array_equal(b.numpy(), want) and int(l.sum()) == want.shape[0]
+
+
+@pytest.mark.parametrize("n,thr,extent,dup,scale", [(1, 0.5, 0.3, 0, 1.0), (500, 0.5, 0.1, 20, 1.0), (3000, 0.5, 0.3, 50, 1.0),
+                                                    (3000, 0.0, 0.3, 0, 1.0), (4000, 0.3, 0.25, 10, 37.0),
+                                                    (2500, 0.7, 0.15, 0, 1.0)])
+def test_grid_nms_oracle_equals_the_reference_loop(n, thr, extent, dup, scale):
+    """The spatially hashed CPU oracle used for the 120 k-candidate GPU parity test gives exactly the keep mask of
+    the n x n restatement of ssd3d.py:407-426 (which is itself pinned by the reference's golden detections)."""
+    import numpy as np
+    g = torch.Generator().manual_seed(n + int(thr * 10))
+    c = extent * torch.rand(n, 3, generator=g)
+    s = (0.03 + 0.05 * torch.rand(n, 1, generator=g)).expand(n, 3)
+    b = torch.cat([c - s / 2, c + s / 2], 1).contiguous()
+    if dup:
+        b[n - dup:] = b[:dup]
+    if scale != 1.0:
+        b = b * scale - 11.0
+    t = float(np.float32(thr))
+    want = O.greedy_nms(b, t)
+    assert torch.equal(O.greedy_nms_grid(b, t), want)
+    if n >= 500:
+        assert 0 < int((~want).sum()) < n
