@@ -17,6 +17,8 @@ The single JSON line printed by rank 0 carries
                HBM peak of MEASURED_PEAKS.json
   cpu_baseline the CPU oracle (a restatement of the reference's torch-CPU path) on a bounded sample of the
                same workload, best thread count
+  extras       (N = 1) a secondary number outside the headline metric: greedy 3-D NMS over 2.5 M score-sorted
+               candidates without truncation (configs[3]/[4]); a failure there is recorded, never fatal
 ``--impl reference`` times that CPU path alone (rank 0 only) and prints the same line shape.
 """
 from __future__ import annotations
@@ -351,6 +353,35 @@ def main():
                    "algorithmic_bytes_per_launch": dw_bytes, "kernel_ms": dw_ms}
     del f0s, f0
 
+    # ---- secondary measurement (rank 0, N = 1 only): any-length greedy NMS, BASELINE configs[3]/[4] ----------
+    # Never allowed to break the bench line: any failure is recorded instead.
+    extras = None
+    if rank == 0 and world == 1:
+        try:
+            n_nms = 2500000
+            gen = torch.Generator(device=dev).manual_seed(n_nms)
+            ctr = torch.rand((n_nms, 3), device=dev, generator=gen)
+            side = 0.02 + 0.08 * torch.rand((n_nms, 1), device=dev, generator=gen)
+            nms_boxes = torch.cat([ctr - side / 2, ctr + side / 2], 1).contiguous()
+            keep, kept = ops.nms3d_sorted_chunked(nms_boxes, MAX_OVERLAP, return_count=True)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ops.nms3d_sorted_chunked(nms_boxes, MAX_OVERLAP)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            extras = {"nms_any_length": {"candidates": n_nms, "kept": int(kept.item()), "ms": sorted(ts)[1],
+                                         "workload": "greedy 3-D NMS over ALL score-sorted candidates (no 10*top_k "
+                                                     "truncation), cubic boxes of side 0.02-0.1 at uniform centres, "
+                                                     "threshold 0.5 (SURVEY 8d C5); the reference's n x n IoU matrix "
+                                                     "would be 25 TB"}}
+            del nms_boxes, keep
+        except Exception as exc:      # noqa: BLE001
+            extras = {"nms_any_length_error": repr(exc)}
+
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -378,6 +409,7 @@ def main():
             "roofline": roofline,
             "roofline_depthwise": roofline_dw,
             "cpu_baseline": cpu,
+            "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
