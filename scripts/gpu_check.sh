@@ -24,6 +24,7 @@ run match    tests/test_gpu_match_loss.py
 run train    tests/test_gpu_train.py
 run metrics  tests/test_gpu_metrics.py
 run gtbox    tests/test_gpu_gtbox.py
+run nms120k  tests/test_gpu_zz_nms_oracle_120k.py
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; r=$?
 echo "== smoke: exit $r: $(tail -1 gpurun_out/smoke.log)"; [ $r -ne 0 ] && rc=1
 timeout 900 python bench.py --steps 100 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; r=$?
