@@ -1,21 +1,27 @@
-"""Import the UNMODIFIED reference (``/root/reference/lesions3d``) on CPU.
+"""Import the UNMODIFIED reference (``lesions3d/{ssd3d,mobilenet,utils,base_network}.py``) on CPU.
 
-TEST INFRASTRUCTURE ONLY.  The reference depends on pytorch_lightning / monai /
+TEST / BASELINE INFRASTRUCTURE ONLY.  The reference depends on pytorch_lightning / monai /
 matplotlib, none of which are installed; this shim registers inert stand-ins
 for the names the reference touches at import time and
-then imports ``ssd3d``, ``mobilenet`` and ``utils`` from the read-only mount.
+then imports ``ssd3d``, ``mobilenet`` and ``utils``.
 
-``/root/reference`` exists only in the build container, never on the GPU box,
-so nothing under ``tests/ -m gpu``, ``bench.py`` or ``smoke()`` may call this.
-It is used by ``tests/golden/make_golden.py`` (to produce the committed golden
-vectors) and by the container-only ``tests/test_oracle_vs_reference.py``.
+Where the modules come from: the read-only mount ``/root/reference/lesions3d`` in the build
+container, else the byte-identical copies ``oracle/make_ref.py`` staged under ``oracle/_ref/``
+(git-ignored; they travel to the GPU box, where the mount does not exist).  Users:
+``tests/golden/make_golden.py`` (produces the committed golden vectors),
+``tests/test_oracle_vs_reference.py`` (live oracle-vs-reference comparison) and the
+``--impl reference`` arm of ``bench.py`` (times the reference's own forward + detect_objects).
+The GPU parity tests and ``smoke()`` never touch it.
 """
 import importlib
 import os
 import sys
 import types
 
-REFERENCE_DIR = os.environ.get("MSL3D_REFERENCE_DIR", "/root/reference/lesions3d")
+_MOUNT = "/root/reference/lesions3d"
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "lesions3d")
+REFERENCE_DIR = os.environ.get("MSL3D_REFERENCE_DIR") or (
+    _MOUNT if os.path.isfile(os.path.join(_MOUNT, "ssd3d.py")) else _STAGED)
 
 
 def reference_available() -> bool:
