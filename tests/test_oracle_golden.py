@@ -230,3 +230,39 @@ def test_grid_nms_oracle_equals_the_reference_loop(n, thr, extent, dup, scale):
     assert torch.equal(O.greedy_nms_grid(b, t), want)
     if n >= 500:
         assert 0 < int((~want).sum()) < n
+
+
+# ---- the C restatement of the greedy NMS (oracle/nms_oracle.c), used for the 1 M / 2.5 M GPU comparisons -------
+def _nms_boxes(n, seed, lo=0.02, hi=0.1, spread=0.4, cubic=True):
+    g = torch.Generator().manual_seed(seed)
+    c = spread * torch.rand(n, 3, generator=g)
+    s = lo + (hi - lo) * torch.rand(n, 1 if cubic else 3, generator=g)
+    return torch.cat([c - s / 2, c + s / 2], 1).contiguous()
+
+
+@pytest.mark.parametrize("n,thr,cubic", [(3000, 0.5, True), (5000, 0.3, True), (4000, 0.0, True), (3500, 0.7, False),
+                                         (2500, 0.45, False)])
+def test_c_nms_oracle_matches_nxn_restatement(n, thr, cubic):
+    import numpy as np
+    from oracle import nms_oracle
+    b = _nms_boxes(n, 900 + n, cubic=cubic)
+    b[n // 2:n // 2 + 200] = b[:200]                 # exact duplicates (IoU = 1)
+    b[7] = torch.tensor([.1, .1, .1, .1, .2, .2])    # zero-volume box: IoU 0 or NaN, never suppresses / suppressed
+    want = O.greedy_nms(b, np.float32(thr))
+    got = torch.from_numpy(nms_oracle.greedy_nms(b.numpy(), thr))
+    assert torch.equal(got, want)
+    assert 0 < int(want.sum()) < n
+
+
+def test_c_nms_oracle_voxel_units_and_preconditions():
+    import numpy as np
+    from oracle import nms_oracle
+    b = _nms_boxes(3000, 77, lo=4.0, hi=30.0, spread=200.0, cubic=False)
+    assert torch.equal(torch.from_numpy(nms_oracle.greedy_nms(b.numpy(), 0.5)), O.greedy_nms(b, np.float32(0.5)))
+    with pytest.raises(ValueError):
+        nms_oracle.greedy_nms(b.numpy(), -0.1)
+    bad = b.clone()
+    bad[3, 0] = float("nan")
+    with pytest.raises(ValueError):
+        nms_oracle.greedy_nms(bad.numpy(), 0.5)
+    assert nms_oracle.greedy_nms(np.zeros((0, 6), np.float32), 0.5).shape == (0,)
