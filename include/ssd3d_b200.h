@@ -261,24 +261,27 @@ int ssd3d_pwconv_wgrad(const void* dz, const void* x, int64_t M, int Cin, int Co
 /* stem: dz (N, Do, Ho, Wo, 32) bf16, x (N, Cin, D, H, W) fp32|bf16 -> dw (32, Cin, 3, 3, 3) fp32 */
 int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W, int stride_d,
                      float* dw, void* workspace, int64_t workspace_bytes, void* stream);
-/* head: dO (N*D*H*W, 16) bf16 gradient rows (ssd3d_head_grad_pack), x (N, D, H, W, C) bf16
- * -> dw_loc (n_loc, C, 3,3,3), dw_cls (n_cls, C, 3,3,3) fp32.  C % 64 == 0, n_loc + n_cls <= 16 */
+/* head: dO (G, N*D*H*W, 16) bf16 gradient rows in G = ceil((n_loc+n_cls)/16) column groups
+ * (ssd3d_head_grad_pack), x (N, D, H, W, C) bf16 -> dw_loc (n_loc, C, 3,3,3), dw_cls (n_cls, C, 3,3,3) fp32
+ * (ssd3d.py:131-132: any n_classes).  One 16-column contraction pass per group.  C % 64 == 0, n_loc + n_cls <= 256 */
 int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int D, int H, int W, int n_loc, int n_cls,
                      float* dw_loc, float* dw_cls, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Head gradient rows of one feature map from d(loss)/d(locs (N,P,6)), d(loss)/d(scores (N,P,n_classes)):
- * dO (N*D*H*W, 16) bf16 in the column order of the fused head GEMM ([loc | class | zero pad]), and the bias
- * gradients dbias_loc (bpl*6), dbias_cls (bpl*n_classes) fp32 (column sums of the fp32 values).
- * Needs bpl*(6+n_classes) <= 16.  workspace: ssd3d_head_grad_workspace_bytes(N, D, H, W). */
-int64_t ssd3d_head_grad_workspace_bytes(int N, int D, int H, int W);
+ * dO (G, N*D*H*W, 16) bf16, G = ceil(n_cols/16) groups of 16 columns in the column order of the fused head GEMM
+ * ([loc | class | zero pad], n_cols = bpl*(6+n_classes) <= 256), and the bias gradients dbias_loc (bpl*6),
+ * dbias_cls (bpl*n_classes) fp32 (column sums of the fp32 values).
+ * workspace: ssd3d_head_grad_workspace_bytes(N, D, H, W, n_cols). */
+int64_t ssd3d_head_grad_workspace_bytes(int N, int D, int H, int W, int n_cols);
 int ssd3d_head_grad_pack(const float* dlocs, const float* dscores, int N, int D, int H, int W, int bpl,
                          int n_classes, int64_t P, int64_t prior_offset, void* dO, float* dbias_loc, float* dbias_cls,
                          void* workspace, int64_t workspace_bytes, void* stream);
 /* Head data gradient (transposed 3x3x3 conv): dx (N, D, H, W, C) bf16 = conv_transpose(dO, w) + addend
  * (addend: the gradient arriving from the next backbone block, may be NULL, may alias dx).
- * w: the packed head weight (16, 27*C) bf16 of ssd3d_head_conv.  C % 64 == 0 */
+ * dO (G, N*D*H*W, 16) as above; w: the packed head weight (16*G, 27*C) bf16 of ssd3d_head_conv; n_cols =
+ * bpl*(6+n_classes).  C % 64 == 0 */
 int ssd3d_head_dgrad(const void* dO, const void* w, const void* addend, void* dx, int N, int C, int D, int H, int W,
-                     void* stream);
+                     int n_cols, void* stream);
 
 /* Depthwise 3x3x3 backward: dz (N, Do, Ho, Wo, C) bf16, w (27, C) bf16, x (N, D, H, W, C) bf16
  * -> dx (N, D, H, W, C) bf16;  dw (C, 1, 3, 3, 3) fp32.  workspace: ssd3d_dw_wgrad_workspace_bytes(C). */
@@ -299,6 +302,17 @@ int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C, int D, int
 int ssd3d_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                     int64_t bias_start, float lr, float lr_bias, float beta1, float beta2, float eps,
                     float weight_decay, int step, float grad_scale, int32_t* status, void* stream);
+
+/* The same step with its whole state on the device, so that forward .. backward .. all-reduce .. optimizer can be
+ * ONE captured CUDA graph (no host scalar changes between replays): state (4 int32, zeroed once by the caller) =
+ * {non-finite flag of this step, skipped steps, APPLIED steps, unused}; scalars (8 fp32 scratch).  The applied-step
+ * counter k drives both the bias correction and the reference's CosineAnnealingLR(T_max = t_max), stepped once
+ * per batch before the optimizer step (ssd3d.py:525-527, 718-720): lr_k = base_lr * (1 + cos(pi*k/t_max)) / 2
+ * (t_max = 0: constant base_lr); biases use lr_k * bias_lr_mult (ssd3d.py:715).  A step with a non-finite gradient
+ * is skipped and advances neither the counter nor the schedule (the reference raises and applies no step). */
+int ssd3d_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        int64_t bias_start, float base_lr, float bias_lr_mult, int t_max, float beta1, float beta2,
+                        float eps, float weight_decay, float grad_scale, int32_t* state, float* scalars, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Detection metrics of ONE class (utils.py:155-230 compute_metrics_per_class + the cumulative precision /

@@ -73,10 +73,10 @@ SIGNATURES = {
     "ssd3d_pwconv_wgrad": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P]),
     "ssd3d_stem_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int64, P]),
     "ssd3d_head_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int64, P]),
-    "ssd3d_head_grad_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
+    "ssd3d_head_grad_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "ssd3d_head_grad_pack": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, P, P, P, P,
                                      c_int64, P]),
-    "ssd3d_head_dgrad": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "ssd3d_head_dgrad": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "ssd3d_dwconv3d_dgrad": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "ssd3d_dw_wgrad_workspace_bytes": (c_int64, [c_int]),
     "ssd3d_dwconv3d_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int64, P]),
@@ -85,6 +85,8 @@ SIGNATURES = {
                                 c_int64, P]),
     "ssd3d_adam_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, c_float,
                                 c_int, c_float, P, P]),
+    "ssd3d_adam_step_dev": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_int, c_float, c_float, c_float,
+                                    c_float, c_float, P, P, P]),
 }
 
 _lib = None

@@ -686,41 +686,52 @@ static int launch_sum_partials(const float* partial, int S, long long slab, int 
 __global__ void __launch_bounds__(256) head_grad_pack_kernel(const float* __restrict__ dlocs,
                                                              const float* __restrict__ dscores, long long P,
                                                              long long prior_off, long long V, int N, int bpl,
-                                                             int n_classes, bf16* __restrict__ dO,
+                                                             int n_classes, int groups, bf16* __restrict__ dO,
                                                              float* __restrict__ bias_partial) {
   __shared__ float red[256][16];
   pdl_wait();
   pdl_launch_dependents();
   const long long M = (long long)N * V;
-  float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = 0.f;
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nl = bpl * 6, nc = bpl * n_classes;
+  const float* lp = nullptr;
+  const float* sp = nullptr;
   if (m < M) {
     const long long n = m / V, vox = m - n * V;
-    const float* lp = dlocs + (n * P + prior_off + vox * bpl) * 6;
-    const float* sp = dscores + (n * P + prior_off + vox * bpl) * n_classes;
-    const int nl = bpl * 6, nc = bpl * n_classes;
+    lp = dlocs + (n * P + prior_off + vox * bpl) * 6;
+    sp = dscores + (n * P + prior_off + vox * bpl) * n_classes;
+  }
+  // column group g holds columns 16g .. 16g+15 of [loc (bpl*6) | class (bpl*n_classes) | zero pad]; dO is
+  // (groups, M, 16): every group is a contiguous 16-column matrix for the 16-column contraction kernels
+  for (int g = 0; g < groups; ++g) {
+    float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      if (j < nl) v[j] = lp[j];
-      else if (j < nl + nc) v[j] = sp[j - nl];
+      const int col = g * 16 + j;
+      v[j] = 0.f;
+      if (m < M) {
+        if (col < nl) v[j] = lp[col];
+        else if (col < nl + nc) v[j] = sp[col - nl];
+      }
     }
-    float lo[8], hi[8];
+    if (m < M) {
+      float lo[8], hi[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-    uint4* dst = reinterpret_cast<uint4*>(dO + m * 16);
-    dst[0] = pack8f(lo);
-    dst[1] = pack8f(hi);
-  }
-  // block-level column sums of the fp32 values (bias gradient), fixed order
+      for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+      uint4* dst = reinterpret_cast<uint4*>(dO + ((long long)g * M + m) * 16);
+      dst[0] = pack8f(lo);
+      dst[1] = pack8f(hi);
+    }
+    // block-level column sums of the fp32 values (bias gradient), fixed order
+    if (g) __syncthreads();
 #pragma unroll
-  for (int j = 0; j < 16; ++j) red[threadIdx.x][j] = v[j];
-  __syncthreads();
-  if (threadIdx.x < 16) {
-    float s = 0.f;
-    for (int t = 0; t < 256; ++t) s += red[t][threadIdx.x];
-    bias_partial[(size_t)blockIdx.x * 16 + threadIdx.x] = s;
+    for (int j = 0; j < 16; ++j) red[threadIdx.x][j] = v[j];
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      float s = 0.f;
+      for (int t = 0; t < 256; ++t) s += red[t][threadIdx.x];
+      bias_partial[(size_t)blockIdx.x * (groups * 16) + g * 16 + threadIdx.x] = s;
+    }
   }
 }
 
@@ -1169,6 +1180,55 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// ---- the same step with ALL of its state on the device (capturable in a CUDA graph, no host scalars) ----------
+// state[0] non-finite flag of this step, state[1] skipped steps, state[2] applied steps, state[3] unused.
+// One thread turns the step counter into the scalars of the step: the optimizer step counter and the position of
+// CosineAnnealingLR(T_max) advance ONLY when the update is applied (a skipped step leaves both where they were --
+// torch.optim / the reference apply no step when "Loss is NaN" is raised, ssd3d.py:938-940).
+//   lr_k = eta_min + (base - eta_min) * (1 + cos(pi * k / T_max)) / 2,  k = applied step (1-based): the reference
+//   steps the scheduler inside training_step, before the optimizer step of the same batch (ssd3d.py:525-527).
+__global__ void adam_prepare_kernel(int* __restrict__ state, float* __restrict__ scal, float base_lr,
+                                    float bias_lr_mult, int t_max, float beta1, float beta2) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (state[0] & 1) {
+    state[1] += 1;
+    scal[4] = 0.f;          // skip
+    return;
+  }
+  const int k = ++state[2];
+  double lr = (double)base_lr;
+  if (t_max > 0) lr = lr * (1.0 + cos(3.14159265358979323846 * (double)k / (double)t_max)) * 0.5;
+  scal[0] = (float)lr;
+  scal[1] = (float)(lr * (double)bias_lr_mult);
+  scal[2] = (float)(1.0 - pow((double)beta1, (double)k));
+  scal[3] = (float)sqrt(1.0 - pow((double)beta2, (double)k));
+  scal[4] = 1.f;
+}
+
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, long long n,
+                                                       long long bias_start, const float* __restrict__ scal,
+                                                       float beta1, float beta2, float eps, float weight_decay,
+                                                       float grad_scale) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (scal[4] == 0.f) return;            // non-finite gradient: parameters and moments untouched
+  const float lr = scal[0], lr_bias = scal[1], bc1 = scal[2], bc2_sqrt = scal[3];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    const float gi = g[i] * grad_scale + weight_decay * pi;
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float step = (i >= bias_start ? lr_bias : lr) / bc1;
+    p[i] = pi - step * (mi / denom);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight packing for the next step as ONE launch: dst[i] = bf16(src[index[i]]) (index < 0 -> 0).  The index map
 // (built once on the host) encodes every layout the kernels want -- stem (32, KPAD) zero padded, depthwise
@@ -1332,47 +1392,65 @@ extern "C" int ssd3d_pwconv_wgrad(const void* dz, const void* x, int64_t M, int 
   return SSD3D_OK;
 }
 
+// Rows 16g .. 16g+15 of the packed head weight [loc rows | class rows | pad] -> the two conv weight gradients:
+// the slabs of column group g are [S][16][C][27]; its rows land in dw_loc / dw_cls as (at most) one contiguous run each.
+static int head_wgrad_scatter(const float* partial, int S, int C, int g, int n_loc, int n_cls, float* dw_loc,
+                              float* dw_cls, cudaStream_t st) {
+  const long long slab = 16ll * 27 * C, row = 27ll * C;
+  const int r0 = 16 * g, r1 = r0 + 16;
+  const int l0 = r0 < n_loc ? r0 : n_loc, l1 = r1 < n_loc ? r1 : n_loc;                        // loc rows [l0, l1)
+  if (l1 > l0)
+    if (const int rc = launch_sum_partials(partial + (size_t)(l0 - r0) * row, S, slab, 1, (int)((l1 - l0) * row),
+                                           (int)((l1 - l0) * row), (int)((l1 - l0) * row), dw_loc + (size_t)l0 * row, st))
+      return rc;
+  const int c0 = (r0 > n_loc ? r0 : n_loc), c1 = (r1 < n_loc + n_cls ? r1 : n_loc + n_cls);      // class rows [c0, c1)
+  if (c1 > c0)
+    if (const int rc = launch_sum_partials(partial + (size_t)(c0 - r0) * row, S, slab, 1, (int)((c1 - c0) * row),
+                                           (int)((c1 - c0) * row), (int)((c1 - c0) * row),
+                                           dw_cls + (size_t)(c0 - n_loc) * row, st))
+      return rc;
+  return SSD3D_OK;
+}
+
 extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int D, int H, int W, int n_loc, int n_cls,
                                 float* dw_loc, float* dw_cls, void* workspace, int64_t workspace_bytes,
                                 void* stream) {
   if (!dO || !x || !dw_loc || !dw_cls || !workspace || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
-  if (C <= 0 || (C % 64) || n_loc + n_cls > 16 || n_loc <= 0 || n_cls <= 0) return SSD3D_ERR_UNSUPPORTED;
+  if (C <= 0 || (C % 64) || n_loc <= 0 || n_cls <= 0 || n_loc + n_cls > 256) return SSD3D_ERR_UNSUPPORTED;
   const long long M = (long long)N * D * H * W;
   if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, 16, 27 * C)) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static const bool use_g = [] { const char* e = getenv("SSD3D_HEAD_WGRAD_G"); return !(e && e[0] == '0'); }();
-  if (use_g) {
-    HeadWgradParams q{};
-    q.dO = static_cast<const bf16*>(dO); q.x = static_cast<const bf16*>(x);
-    q.N = N; q.D = D; q.H = H; q.W = W; q.C = C; q.M = M;
-    const long long chunks = (M + 63) / 64;
-    const int S0 = head_wgrad_splits(M, C);
-    q.chunks_per_split = (int)((chunks + S0 - 1) / S0);
-    const int S = (int)((chunks + q.chunks_per_split - 1) / q.chunks_per_split);
-    q.partial = static_cast<float*>(workspace);
-    const size_t smem = (size_t)2 * 64 * (HW_XP + HW_GP) * 2;
-    cudaError_t e = cudaFuncSetAttribute(head_wgrad_g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    SSD3D_LAUNCH_PDL(head_wgrad_g_kernel, dim3((unsigned)(C / 64), 3u, (unsigned)S), dim3(128), smem, st, q);
-    const long long slab = 16ll * 27 * C;
-    if (const int rc_s = launch_sum_partials(q.partial, S, slab, 1, n_loc * 27 * C, n_loc * 27 * C, n_loc * 27 * C, dw_loc, st)) return rc_s;
-    if (const int rc_s = launch_sum_partials(q.partial + (size_t)n_loc * 27 * C, S, slab, 1, n_cls * 27 * C, n_cls * 27 * C, n_cls * 27 * C,
-                        dw_cls, st)) return rc_s;
-    return SSD3D_OK;
+  const int groups = (n_loc + n_cls + 15) / 16;      // 16 output columns per pass (dO is (groups, M, 16))
+  for (int g = 0; g < groups; ++g) {
+    const bf16* dOg = static_cast<const bf16*>(dO) + (size_t)g * M * 16;
+    if (use_g) {
+      HeadWgradParams q{};
+      q.dO = dOg; q.x = static_cast<const bf16*>(x);
+      q.N = N; q.D = D; q.H = H; q.W = W; q.C = C; q.M = M;
+      const long long chunks = (M + 63) / 64;
+      const int S0 = head_wgrad_splits(M, C);
+      q.chunks_per_split = (int)((chunks + S0 - 1) / S0);
+      const int S = (int)((chunks + q.chunks_per_split - 1) / q.chunks_per_split);
+      q.partial = static_cast<float*>(workspace);
+      const size_t smem = (size_t)2 * 64 * (HW_XP + HW_GP) * 2;
+      cudaError_t e = cudaFuncSetAttribute(head_wgrad_g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      SSD3D_LAUNCH_PDL(head_wgrad_g_kernel, dim3((unsigned)(C / 64), 3u, (unsigned)S), dim3(128), smem, st, q);
+      if (const int rc_s = head_wgrad_scatter(q.partial, S, C, g, n_loc, n_cls, dw_loc, dw_cls, st)) return rc_s;
+      continue;
+    }
+    WgradParams p{};
+    p.dz = dOg; p.ldz = 16; p.M = M;
+    p.K = 27 * C;
+    p.x = x; p.C = C; p.N = N; p.D = D; p.H = H; p.W = W; p.n_pad = 16;
+    p.partial = static_cast<float*>(workspace);
+    int S = 0;
+    const int rc = run_wgrad<16, 1, 64>(p, 16, st, &S);
+    if (rc) return rc;
+    // slabs are [16][C][27] = the layout of the conv weight rows of this group
+    if (const int rc_s = head_wgrad_scatter((const float*)p.partial, S, C, g, n_loc, n_cls, dw_loc, dw_cls, st)) return rc_s;
   }
-  WgradParams p{};
-  p.dz = static_cast<const bf16*>(dO); p.ldz = 16; p.M = M;
-  p.K = 27 * C;
-  p.x = x; p.C = C; p.N = N; p.D = D; p.H = H; p.W = W; p.n_pad = 16;
-  p.partial = static_cast<float*>(workspace);
-  int S = 0;
-  const int rc = run_wgrad<16, 1, 64>(p, 16, st, &S);
-  if (rc) return rc;
-  // slabs are [16][C][27] = the layout of the two conv weights stacked: two contiguous fixed-order sums
-  const long long slab = 16ll * 27 * C;
-  if (const int rc_s = launch_sum_partials((const float*)p.partial, S, slab, 1, n_loc * 27 * C, n_loc * 27 * C, n_loc * 27 * C, dw_loc, st)) return rc_s;
-  if (const int rc_s = launch_sum_partials((const float*)(p.partial + (size_t)n_loc * 27 * C), S, slab, 1, n_cls * 27 * C, n_cls * 27 * C,
-                   n_cls * 27 * C, dw_cls, st)) return rc_s;
   return SSD3D_OK;
 }
 
@@ -1418,44 +1496,55 @@ extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, in
 }
 
 // ---- head gradient rows + bias gradient, head data gradient ---------------------------------------------
-extern "C" int64_t ssd3d_head_grad_workspace_bytes(int N, int D, int H, int W) {
+extern "C" int64_t ssd3d_head_grad_workspace_bytes(int N, int D, int H, int W, int n_cols) {
   const long long M = (long long)N * D * H * W;
-  return (int64_t)((M + 255) / 256) * 16 * 4;
+  const int groups = (n_cols + 15) / 16;
+  return (int64_t)((M + 255) / 256) * groups * 16 * 4;
 }
 
 extern "C" int ssd3d_head_grad_pack(const float* dlocs, const float* dscores, int N, int D, int H, int W, int bpl,
                                     int n_classes, int64_t P, int64_t prior_offset, void* dO, float* dbias_loc,
                                     float* dbias_cls, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!dlocs || !dscores || !dO || !dbias_loc || !dbias_cls || !workspace || N <= 0) return SSD3D_ERR_ARG;
-  if (bpl * (6 + n_classes) > 16) return SSD3D_ERR_UNSUPPORTED;
+  const int n_cols = bpl * (6 + n_classes);
+  if (bpl <= 0 || n_classes <= 0 || n_cols > 256) return SSD3D_ERR_UNSUPPORTED;
+  const int groups = (n_cols + 15) / 16, ld = groups * 16;
   const long long V = (long long)D * H * W, M = (long long)N * V;
   const int blocks = (int)((M + 255) / 256);
-  if (workspace_bytes < (int64_t)blocks * 16 * 4) return SSD3D_ERR_ARG;
+  if (workspace_bytes < (int64_t)blocks * ld * 4) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
   SSD3D_LAUNCH_PDL(head_grad_pack_kernel, dim3(blocks), dim3(256), 0, st, dlocs, dscores, (long long)P,
-                   (long long)prior_offset, V, N, bpl, n_classes, static_cast<bf16*>(dO), partial);
-  // column sums: partial is [blocks][16] -> rows = 1, cols = 16 with slab = 16
-  if (const int rc_s = launch_sum_partials((const float*)partial, blocks, 16ll, 1, bpl * 6, 16,
+                   (long long)prior_offset, V, N, bpl, n_classes, groups, static_cast<bf16*>(dO), partial);
+  // column sums: partial is [blocks][ld] -> rows = 1, slab = ld
+  if (const int rc_s = launch_sum_partials((const float*)partial, blocks, (long long)ld, 1, bpl * 6, ld,
                    bpl * 6, dbias_loc, st)) return rc_s;
-  if (const int rc_s = launch_sum_partials((const float*)(partial + bpl * 6), blocks, 16ll, 1,
-                   bpl * n_classes, 16, bpl * n_classes, dbias_cls, st)) return rc_s;
+  if (const int rc_s = launch_sum_partials((const float*)(partial + bpl * 6), blocks, (long long)ld, 1,
+                   bpl * n_classes, ld, bpl * n_classes, dbias_cls, st)) return rc_s;
   return SSD3D_OK;
 }
 
 extern "C" int ssd3d_head_dgrad(const void* dO, const void* w, const void* addend, void* dx, int N, int C, int D,
-                                int H, int W, void* stream) {
+                                int H, int W, int n_cols, void* stream) {
   if (!dO || !w || !dx || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
-  if (C <= 0 || (C % 64)) return SSD3D_ERR_UNSUPPORTED;
-  HeadDgradParams p{};
-  p.dO = static_cast<const bf16*>(dO); p.w = static_cast<const bf16*>(w);
-  p.addend = static_cast<const bf16*>(addend); p.dx = static_cast<bf16*>(dx);
-  p.N = N; p.D = D; p.H = H; p.W = W; p.C = C; p.M = (long long)N * D * H * W;
+  if (C <= 0 || (C % 64) || n_cols <= 0 || n_cols > 256) return SSD3D_ERR_UNSUPPORTED;
+  const long long M = (long long)N * D * H * W;
+  const int groups = (n_cols + 15) / 16;
   const size_t smem = (size_t)(27 * 16 * 72 + 2 * 64 * 24) * 2;
   cudaError_t e = cudaFuncSetAttribute(head_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid((unsigned)((p.M + 63) / 64), (unsigned)(C / 64));
-  SSD3D_LAUNCH_PDL(head_dgrad_kernel, grid, dim3(128), smem, static_cast<cudaStream_t>(stream), p);
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)(C / 64));
+  // 16 gradient columns per pass: dx = addend + sum_g dO_g . W_g, group g > 0 accumulating onto the result so far
+  // (every element is read and written by the same thread of the same CTA: in place is safe)
+  for (int g = 0; g < groups; ++g) {
+    HeadDgradParams p{};
+    p.dO = static_cast<const bf16*>(dO) + (size_t)g * M * 16;
+    p.w = static_cast<const bf16*>(w) + (size_t)g * 16 * 27 * C;
+    p.addend = g == 0 ? static_cast<const bf16*>(addend) : static_cast<const bf16*>(dx);
+    p.dx = static_cast<bf16*>(dx);
+    p.N = N; p.D = D; p.H = H; p.W = W; p.C = C; p.M = M;
+    SSD3D_LAUNCH_PDL(head_dgrad_kernel, grid, dim3(128), smem, static_cast<cudaStream_t>(stream), p);
+  }
   return SSD3D_OK;
 }
 
@@ -1560,6 +1649,23 @@ extern "C" int ssd3d_adam_step(float* param, const float* grad, float* exp_avg, 
   SSD3D_LAUNCH_PDL(adam_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq,
                    (long long)n, (long long)bias_start, lr, lr_bias, beta1, beta2, eps, weight_decay, (float)bc1,
                    (float)sqrt(bc2), grad_scale, status);
+  return SSD3D_OK;
+}
+
+extern "C" int ssd3d_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                   int64_t bias_start, float base_lr, float bias_lr_mult, int t_max, float beta1,
+                                   float beta2, float eps, float weight_decay, float grad_scale, int32_t* state,
+                                   float* scalars, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !state || !scalars || n <= 0 || t_max < 0) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(state, 0, 4, st);
+  if (e != cudaSuccess) return (int)e;
+  SSD3D_LAUNCH_PDL(grad_nonfinite_kernel, dim3(grid_for(n, 256, 148 * 4)), dim3(256), 0, st, grad, (long long)n, state);
+  SSD3D_LAUNCH_PDL(adam_prepare_kernel, dim3(1), dim3(32), 0, st, state, scalars, base_lr, bias_lr_mult, t_max, beta1,
+                   beta2);
+  SSD3D_LAUNCH_PDL(adam_dev_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq,
+                   (long long)n, (long long)bias_start, (const float*)scalars, beta1, beta2, eps, weight_decay,
+                   grad_scale);
   return SSD3D_OK;
 }
 

@@ -8,9 +8,10 @@ only: ``forward`` packs their tensors once (bf16, channels-last, BN folded to sc
 the CUDA kernels; activations travel between modules as logical (N,C,D,H,W) tensors stored
 channels-last-3d in bf16.
 
-Called stand-alone these modules run in ``eval()`` mode only (and raise otherwise instead of falling back):
-the training-mode forward (batch-statistic BatchNorm) and the backward kernels are driven by
-``training.TrainEngine`` through ``LSSD3D``, which owns the tape of saved activations.
+In ``eval()`` mode BatchNorm is folded into the conv epilogues.  In training mode (the reference's modules work
+stand-alone there too, mobilenet.py:34-49) each module is one autograd node over the train-mode kernels
+(``train_modules.py``: batch-statistic BatchNorm, running-statistic update, hand-written backward); inside
+``LSSD3D`` the fused ``training.TrainEngine`` drives the same kernels for the whole network at once.
 """
 from __future__ import annotations
 
@@ -42,13 +43,6 @@ def _bn_tensors(bn):
     return (bn.weight, bn.bias, bn.running_mean, bn.running_var)
 
 
-def _require_eval(mod: nn.Module):
-    if mod.training:
-        raise NotImplementedError(
-            "%s: stand-alone training-mode forward is not supported; train through LSSD3D (training_step / fit_step), "
-            "or call .eval()" % type(mod).__name__)
-
-
 def _stride3(stride):
     if isinstance(stride, int):
         return (stride, stride, stride)
@@ -77,11 +71,13 @@ class ConvBN(nn.Sequential):
         return self._packed
 
     def forward(self, x, out=None):
-        _require_eval(self)
         conv = self[0]
         sd, sh, sw = _stride3(conv.stride)
         if conv.out_channels != 32 or (sh, sw) != (2, 2) or sd not in (1, 2):
             raise NotImplementedError("stem kernel is built for Cout=32 and stride (1|2, 2, 2), as ssd3d.py:60-61 uses it")
+        if self.training:
+            from .train_modules import conv_bn_train
+            return conv_bn_train(self, x)
         w, scale, shift = self._pack()
         return ops.stem_conv_bn_relu(x, w, scale, shift, sd, out=out)
 
@@ -114,10 +110,12 @@ class Block(nn.Module):
         return self._packed
 
     def forward(self, x):
-        _require_eval(self)
         s = _stride3(self.conv1.stride)
         if s[0] != s[1] or s[1] != s[2] or s[0] not in (1, 2):
             raise NotImplementedError("depthwise kernel is built for isotropic stride 1 or 2 (mobilenet.py:13-20)")
+        if self.training:
+            from .train_modules import block_train
+            return block_train(self, x)
         wd, s1, b1, wp, s2, b2 = self._pack()
         own_flag = self.nan_flag is None
         flag = torch.zeros((1,), dtype=torch.int32, device=x.device) if own_flag else self.nan_flag

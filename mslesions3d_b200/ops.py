@@ -531,16 +531,29 @@ def _ones_zeros(n: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 _WS_SLOT = ["ws"]      # scratch slot of the stream being issued to (training.py switches it for its side stream)
+_WS_PINNED = set()     # data_ptr of scratch buffers whose address a captured CUDA graph has baked in
+_WS_RETIRED = []       # pinned buffers that were outgrown: kept alive for the graphs that still replay into them
 
 
 def _workspace(nbytes: int, device, slot: Optional[str] = None) -> torch.Tensor:
-    """Grow-only scratch buffer per (device, slot); kernels of one stream use it strictly in order."""
+    """Grow-only scratch buffer per (device, slot); kernels of one stream use it strictly in order.  A buffer a
+    captured graph refers to (``pin_workspaces``) is never freed: when a later call needs more, a new buffer takes
+    over for eager launches and the old one stays alive for the graph's replays."""
     key = (str(device), slot or _WS_SLOT[0])
     cur = _CONST.get(key)
     if cur is None or cur.numel() < nbytes:
+        if cur is not None and cur.data_ptr() in _WS_PINNED:
+            _WS_RETIRED.append(cur)
         cur = torch.empty((max(int(nbytes), 1 << 20),), dtype=torch.uint8, device=device)
         _CONST[key] = cur
     return cur
+
+
+def pin_workspaces() -> None:
+    """Called after a CUDA-graph capture that used the scratch slots: their current buffers must outlive the graph."""
+    for key, cur in _CONST.items():
+        if isinstance(cur, torch.Tensor) and cur.dtype == torch.uint8:
+            _WS_PINNED.add(cur.data_ptr())
 
 
 def stem_conv_raw(x: torch.Tensor, w_packed: torch.Tensor, stride_d: int) -> torch.Tensor:
@@ -625,6 +638,12 @@ def bn_train_relu(z: torch.Tensor, bn: torch.nn.BatchNorm3d, nan_flag: Optional[
                                 a.data_ptr(), _ptr(nan_flag), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "ssd3d_bn_train_fwd")
     LAUNCHES[0] += 3
+    if track:
+        # the kernel updated the running statistics through raw pointers: bump their version counters (host-side
+        # only, no launch) so that caches keyed on (data_ptr, _version) -- folded eval-mode BN, captured inference
+        # plans -- see the change
+        bufs = [t for t in (bn.running_mean, bn.running_var, nbt) if t is not None]
+        torch._C._autograd._unsafe_set_version_counter(bufs, [t._version + 1 for t in bufs])
     return a, st
 
 
@@ -666,10 +685,12 @@ def stem_wgrad(dz: torch.Tensor, x: torch.Tensor, stride_d: int, dw: torch.Tenso
 
 
 def head_grad_pack(dlocs, dscores, n, d, h, w, bpl, n_classes, prior_offset, dbias_loc, dbias_cls) -> torch.Tensor:
-    """-> dO (N*D*H*W, 16) bf16 gradient rows of one head; fills the two bias gradients."""
+    """-> dO (G, N*D*H*W, 16) bf16 gradient rows of one head in G = ceil(bpl*(6+n_classes)/16) column groups;
+    fills the two bias gradients."""
     lib = _lib.load()
-    dO = torch.empty((n * d * h * w, 16), dtype=BF16, device=dlocs.device)
-    ws = _workspace(lib.ssd3d_head_grad_workspace_bytes(n, d, h, w), dlocs.device)
+    n_cols = bpl * (6 + n_classes)
+    dO = torch.empty(((n_cols + 15) // 16, n * d * h * w, 16), dtype=BF16, device=dlocs.device)
+    ws = _workspace(lib.ssd3d_head_grad_workspace_bytes(n, d, h, w, n_cols), dlocs.device)
     rc = lib.ssd3d_head_grad_pack(dlocs.data_ptr(), dscores.data_ptr(), n, d, h, w, bpl, n_classes, dlocs.shape[1],
                                   prior_offset, dO.data_ptr(), dbias_loc.data_ptr(), dbias_cls.data_ptr(),
                                   ws.data_ptr(), ws.numel(), _stream())
@@ -685,17 +706,21 @@ def head_wgrad(dO: torch.Tensor, x: torch.Tensor, n_loc: int, n_cls: int, dw_loc
     rc = lib.ssd3d_head_wgrad(dO.data_ptr(), x.data_ptr(), n, c, d, h, w, n_loc, n_cls, dw_loc.data_ptr(),
                               dw_cls.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "ssd3d_head_wgrad")
-    LAUNCHES[0] += 2
+    LAUNCHES[0] += 3 * ((n_loc + n_cls + 15) // 16)
 
 
-def head_dgrad(dO: torch.Tensor, w_packed: torch.Tensor, like: torch.Tensor, addend: Optional[torch.Tensor] = None):
-    """-> d(loss)/d(feature map) (channels-last bf16, shape of ``like``) [+ addend, written in place]."""
+def head_dgrad(dO: torch.Tensor, w_packed: torch.Tensor, like: torch.Tensor, addend: Optional[torch.Tensor] = None,
+               n_cols: Optional[int] = None):
+    """-> d(loss)/d(feature map) (channels-last bf16, shape of ``like``) [+ addend, written in place].
+    ``n_cols`` = bpl*(6+n_classes) real gradient columns (default: all 16*G of dO)."""
     n, c, d, h, w = like.shape
     out = addend if addend is not None else _alloc_ndhwc(n, c, d, h, w, like.device)
+    groups = dO.shape[0] if dO.dim() == 3 else 1
+    n_cols = 16 * groups if n_cols is None else int(n_cols)
     rc = _lib.load().ssd3d_head_dgrad(dO.data_ptr(), w_packed.data_ptr(), _ptr(addend), out.data_ptr(), n, c, d, h, w,
-                                      _stream())
+                                      n_cols, _stream())
     _lib.check(rc, "ssd3d_head_dgrad")
-    LAUNCHES[0] += 1
+    LAUNCHES[0] += groups
     return out
 
 
@@ -729,6 +754,21 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, ex
                                      int(step), grad_scale, _ptr(status), _stream())
     _lib.check(rc, "ssd3d_adam_step")
     LAUNCHES[0] += 2 if status is not None else 1
+
+
+def adam_step_dev(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                  bias_start: int, base_lr: float, state: torch.Tensor, scalars: torch.Tensor, t_max: int = 0,
+                  bias_lr_mult: float = 2.0, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                  grad_scale: float = 1.0) -> None:
+    """Adam with the step counter, the cosine schedule and the skip-on-non-finite logic on the device (see the
+    header): ``state`` (4,) int32 = [non-finite, skipped, applied, -], ``scalars`` (8,) fp32 scratch."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, state, scalars)
+    rc = _lib.load().ssd3d_adam_step_dev(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                         param.numel(), bias_start, float(base_lr), float(bias_lr_mult), int(t_max),
+                                         betas[0], betas[1], eps, weight_decay, grad_scale, state.data_ptr(),
+                                         scalars.data_ptr(), _stream())
+    _lib.check(rc, "ssd3d_adam_step_dev")
+    LAUNCHES[0] += 3
 
 
 # ----------------------------------------------------------------------------------------------

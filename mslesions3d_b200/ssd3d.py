@@ -208,9 +208,10 @@ class PredictionConvolutions(nn.Module):
         return self._packed
 
     def forward(self, feats, nan_flag: Optional[torch.Tensor] = None, out=None):
-        if self.training:
-            raise NotImplementedError("PredictionConvolutions: stand-alone training-mode forward is not supported; "
-                                      "train through LSSD3D (training_step / fit_step), or call .eval()")
+        if self.training and torch.is_grad_enabled() and out is None:
+            # stand-alone use with gradients (ssd3d.py:134-169 under autograd): one autograd node over the head kernels
+            from .train_modules import heads_train
+            return heads_train(self, feats, nan_flag)
         feat_keys = list(feats.keys())
         first = feats[min(feat_keys)]
         batch_size = first.size(0)
@@ -387,6 +388,10 @@ class _InferencePlan:
     def _launch(self, image: torch.Tensor, copy_stream, compute):
         compute.wait_event(self.cloned)          # static outputs of the previous use of this plan were consumed
         if image.is_cuda:
+            # the batch (or its dtype-converted temporary) was allocated on the caller's stream but is read by the
+            # stem on `compute`: tell the caching allocator, or the block could be handed out again while the
+            # kernel still reads it (up to pipeline_depth batches are in flight)
+            image.record_stream(compute)
             self.stem(image, out=self.stem_out)
         else:
             if copy_stream is None:
@@ -430,6 +435,7 @@ class _InferencePlan:
                 torch.cuda.set_stream(current)
         if not to_host and stream is not current:
             current.wait_event(self.cloned)      # later work on the caller's stream sees complete tensors
+            buf.record_stream(current)           # allocated on `stream`, used (and eventually freed) by the caller's
         boxes, scores, labels, _ = self._views(buf, int(self.args[2]))
         return ([boxes[i, :k] for i, k in enumerate(counts)], [labels[i, :k] for i, k in enumerate(counts)],
                 [scores[i, :k] for i, k in enumerate(counts)])

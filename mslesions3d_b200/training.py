@@ -23,6 +23,7 @@ import os
 from typing import Dict, List, Optional
 
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 
 from . import _lib, ops
@@ -73,8 +74,10 @@ class FlatParams:
         self.exp_avg = torch.zeros((off,), dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros((off,), dtype=torch.float32, device=dev)
         self.views_grad: Dict[str, torch.Tensor] = {}
-        self.step = 0
-        self.status = torch.zeros((2,), dtype=torch.int32, device=dev)   # [non-finite this step, skipped steps]
+        # optimizer state on the device (the whole step is one captured graph: no host scalars):
+        # [non-finite gradient this step, skipped steps, APPLIED steps, -] and the per-step scalars derived from it
+        self.status = torch.zeros((4,), dtype=torch.int32, device=dev)
+        self.scalars = torch.zeros((8,), dtype=torch.float32, device=dev)
         with torch.no_grad():
             for n, p in weights + biases:
                 o = self.offsets[n]
@@ -82,6 +85,11 @@ class FlatParams:
                 view.copy_(p.detach().float())
                 p.data = view
                 self.views_grad[n] = self.grad[o:o + p.numel()].view(p.shape)
+
+    @property
+    def step(self) -> int:
+        """Optimizer steps APPLIED so far (reads the device counter: synchronises)."""
+        return int(self.status[2].item())
 
 
 class PackedWeights:
@@ -154,6 +162,51 @@ class PackedWeights:
         ops.gather_cast(self.flat.param, self.index_f32, self.buf_f32)
 
 
+def broadcast_replica_state(model, flat: "FlatParams", src: int = 0) -> None:
+    """Make every rank a replica of rank ``src`` before the first data-parallel step -- what DistributedDataParallel
+    does at construction (parameter broadcast) and with ``broadcast_buffers``: the flat parameter buffer, the Adam
+    moments and step counter, and every BatchNorm buffer (running_mean / running_var / num_batches_tracked) and
+    ``rescale_factors``.  Without it, ranks built from different RNG states or checkpoints would silently train
+    divergent replicas on averaged gradients.  During training the BatchNorm statistics stay rank-local (each rank
+    sees its own volumes; the reference has no SyncBN); ``sync_batchnorm_buffers`` averages them on
+    demand (e.g. before validation / checkpointing)."""
+    with torch.no_grad():
+        for t in (flat.param, flat.exp_avg, flat.exp_avg_sq, flat.status):
+            dist.broadcast(t, src)
+        for _, b in model.named_buffers():
+            dist.broadcast(b, src)
+        for n, p in model.named_parameters():
+            if n not in flat.offsets:          # parameters outside the flat buffer (rescale_factors)
+                dist.broadcast(p.data, src)
+
+
+def sync_batchnorm_buffers(model) -> None:
+    """Average the BatchNorm running statistics over the ranks (num_batches_tracked: maximum)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    world = float(dist.get_world_size())
+    with torch.no_grad():
+        for n, b in model.named_buffers():
+            if b.is_floating_point():
+                dist.all_reduce(b)
+                b.div_(world)
+            else:
+                dist.all_reduce(b, op=dist.ReduceOp.MAX)
+    model.invalidate_packed()
+
+
+def replica_checksum_matches(flat: "FlatParams") -> bool:
+    """True when every rank holds bit-identical parameters (a cheap health check for long runs)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return True
+    v = flat.param.view(torch.int32).to(torch.int64)
+    mine = torch.stack([v.sum(), (v * torch.arange(1, v.numel() + 1, device=v.device)).sum()])
+    lo, hi = mine.clone(), mine.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(torch.equal(lo, hi))
+
+
 def dims_of(x, count, bpl):
     """Spatial shape of ``x`` if it holds ``count`` priors at ``bpl`` boxes per location, else ()."""
     sp = tuple(x.shape[2:])
@@ -170,6 +223,10 @@ class TrainEngine:
         self.tape = None
         self.plans = {}
         self._side = None
+        # tests set this to a dict: backward() then stores the tape and clones of every gradient that flows through
+        # a unit (the in-situ stage-wise parity test replays each stage through torch-CPU autograd)
+        self.record = None
+        self.collective_mode = "none"
 
     def _wgrad_side_stream(self, main):
         """Second stream of the backward pass (weight gradients), on ``main``'s device."""
@@ -181,6 +238,8 @@ class TrainEngine:
     def flatten(self) -> FlatParams:
         if self.flat is None or self.flat.param.device != self.model.device:
             self.flat = FlatParams(self.model)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                broadcast_replica_state(self.model, self.flat)
             self.packed = PackedWeights(self.model, self.flat)
             self.packed.refresh()
             self.plans.clear()
@@ -196,9 +255,6 @@ class TrainEngine:
         dev = m.device
         if dev.type != "cuda":
             raise RuntimeError("training needs the model on a CUDA device; there is no CPU path")
-        if m.n_classes * m.boxes_per_location + 6 * m.boxes_per_location > 16:
-            raise NotImplementedError("the head backward kernels are built for bpl*(6+n_classes) <= 16 "
-                                      "(the reference's binary lesion/background setting)")
         if image.device != dev:
             image = image.to(dev, non_blocking=True)
         if image.dtype not in (torch.float32, torch.bfloat16):
@@ -276,16 +332,31 @@ class TrainEngine:
         return locs, scores
 
     # ------------------------------------------------------------------------------------------
-    def backward(self, dlocs: torch.Tensor, dscores: torch.Tensor, grads: _Grads) -> None:
-        """d(loss)/d(locs), d(loss)/d(scores) -> every parameter gradient (written into ``grads``)."""
-        tape = self.tape
+    def take_tape(self):
+        """Hand the tape of the latest forward to its owner (the autograd node): later train-mode forwards then
+        record their own tape without disturbing a backward that has not run yet."""
+        tape, self.tape = self.tape, None
+        return tape
+
+    def backward(self, dlocs: torch.Tensor, dscores: torch.Tensor, grads: _Grads, tape=None) -> None:
+        """d(loss)/d(locs), d(loss)/d(scores) -> every parameter gradient (written into ``grads``).
+        ``tape``: the forward's tape (``take_tape``); default: the latest forward of this engine."""
+        if tape is None:
+            tape = self.tape
+            self.tape = None
         if tape is None:
             raise RuntimeError("TrainEngine.backward without a recorded forward")
-        self.tape = None
         m = self.model
         pc = m.pred_convs
         dlocs = dlocs.float().contiguous()
         dscores = dscores.float().contiguous()
+        rec = self.record
+        if rec is not None:
+            rec.clear()
+            rec.update(tape=tape, dlocs=dlocs.clone(), dscores=dscores.clone(), units={}, heads={})
+
+        def snap(t):
+            return None if t is None else t.clone(memory_format=torch.preserve_format)
         n = tape["image"].shape[0]
         head_at = {h["layer"]: h for h in tape["heads"]}
         # Weight gradients are leaves of the backward graph: they go to a second (lower-priority) stream and
@@ -325,24 +396,45 @@ class TrainEngine:
         for u in reversed(tape["units"]):
             i = u["idx"]
             p = "base.features.%d" % i
+            r = None
+            if rec is not None:
+                r = rec["units"][i] = {}
             if i in head_at:
                 h = head_at[i]
-                g = ops.head_dgrad(dO[i], h["w"], h["feat"], addend=g)
+                if rec is not None:
+                    rec["heads"][i] = dict(dO=snap(dO[i]), addend=snap(g))
+                g = ops.head_dgrad(dO[i], h["w"], h["feat"], addend=g, n_cols=h["bpl"] * (6 + pc.n_classes))
+                if rec is not None:
+                    rec["heads"][i]["out"] = snap(g)
             if g is None:
                 raise RuntimeError("no gradient reaches backbone layer %d" % i)
             if u["kind"] == "block":
+                if r is not None:
+                    r["g2"] = snap(g)
                 dz2 = ops.bn_relu_backward(u["z2"], g, u["st2"], grads[p + ".bn2.weight"], grads[p + ".bn2.bias"])
+                if r is not None:
+                    r["dz2"] = snap(dz2)
                 leaf(lambda dz2=dz2, u=u, p=p: ops.pwconv_wgrad(dz2, u["a1"], grads[p + ".conv2.weight"]), dz2)
                 g1 = torch.empty_like(u["a1"])
                 nn_, c1, d1, h1, w1 = u["a1"].shape
                 wt = u["wpt"] if u["wpt"] is not None else u["wp"].t().contiguous()   # (Cin, Cout): dx = dz . W
                 ops.pw_gemm_raw(nn_ * d1 * h1 * w1, dz2, wt, g1)
+                if r is not None:
+                    r["g1"] = snap(g1)
                 dz1 = ops.bn_relu_backward(u["z1"], g1, u["st1"], grads[p + ".bn1.weight"], grads[p + ".bn1.bias"])
+                if r is not None:
+                    r["dz1"] = snap(dz1)
                 leaf(lambda dz1=dz1, u=u, p=p: ops.dwconv3d_wgrad(dz1, u["x"], u["stride"],
                                                                   grads[p + ".conv1.weight"]), dz1)
                 g = ops.dwconv3d_dgrad(dz1, u["wd"], u["x"], u["stride"])
+                if r is not None:
+                    r["dx"] = snap(g)
             else:
+                if r is not None:
+                    r["g"] = snap(g)
                 dz = ops.bn_relu_backward(u["z"], g, u["st"], grads[p + ".1.weight"], grads[p + ".1.bias"])
+                if r is not None:
+                    r["dz"] = snap(dz)
                 ops.stem_wgrad(dz, u["x"], u["stride"], grads[p + ".0.weight"])
                 g = None
         if side is not None:
@@ -358,13 +450,17 @@ class _NetFn(torch.autograd.Function):
     def forward(ctx, engine, image, names, *params):
         ctx.engine, ctx.names, ctx.params = engine, names, params
         locs, scores = engine.forward(image)
+        ctx.tape = engine.take_tape()
         return locs, scores
 
     @staticmethod
     def backward(ctx, dlocs, dscores):
         eng = ctx.engine
         grads = _Grads(zip(ctx.names, ctx.params))
-        eng.backward(dlocs, dscores, grads)
+        tape, ctx.tape = ctx.tape, None
+        if tape is None:
+            raise RuntimeError("backward through the same LSSD3D forward twice (the saved activations were released)")
+        eng.backward(dlocs, dscores, grads, tape=tape)
         out = []
         for name, p in zip(ctx.names, ctx.params):
             out.append(grads.t.get(name) if name != "rescale_factors" else None)
@@ -385,17 +481,20 @@ def cosine_lr(base_lr: float, step: int, t_max: int = 40, eta_min: float = 0.0) 
 
 
 class _TrainPlan:
-    """forward + matching + loss + backward of one step for one input signature, captured into a CUDA graph
-    (the eager step is host-bound: ~180 launches).  Inputs are staged into static buffers: the image batch,
-    the concatenated ground-truth boxes / labels (capacity ``tmax`` rows) and the per-image offsets.  The
-    gradient all-reduce and the Adam launch stay outside the graph (host scalars: step count, learning rate)."""
+    """One whole optimisation step for one input signature, captured into ONE CUDA graph (the eager step is
+    host-bound: ~190 launches): forward, matching, loss, backward, the gradient all-reduce (NCCL, captured like any
+    other node), Adam and the re-packing of the bf16 weights.  Nothing in it depends on a host scalar: the step
+    counter, the cosine learning-rate schedule and the skip-on-NaN decision live on the device
+    (``ssd3d_adam_step_dev``).  Inputs are staged into static buffers: the image batch, the concatenated
+    ground-truth boxes / labels (capacity ``tmax`` rows) and the per-image offsets."""
 
-    def __init__(self, model, images: torch.Tensor, tmax: int):
+    def __init__(self, model, images: torch.Tensor, tmax: int, world_size: int, allreduce):
         eng = model.train_engine()
         self.flat = eng.flatten()
         dev = model.device
         n = images.shape[0]
         self.n, self.tmax = n, tmax
+        self.world_size, self.allreduce = world_size, allreduce
         self.image = torch.empty(tuple(images.shape), dtype=images.dtype, device=dev)
         self.gt_boxes = torch.zeros((tmax, 6), dtype=torch.float32, device=dev)
         self.gt_labels = torch.zeros((tmax,), dtype=torch.int64, device=dev)
@@ -403,6 +502,7 @@ class _TrainPlan:
         self.loss = None
         self.n_kernels = 0
         self.graph = None
+        self.optimizer_in_graph = False
 
     def load(self, images, gt_boxes, gt_labels):
         self.image.copy_(images, non_blocking=True)
@@ -420,7 +520,7 @@ class _TrainPlan:
             self.gt_boxes[:total].copy_(torch.cat([b.reshape(-1, 6) for b in gt_boxes]).float(), non_blocking=True)
             self.gt_labels[:total].copy_(torch.cat([l.reshape(-1) for l in gt_labels]).long(), non_blocking=True)
 
-    def _run(self, model):
+    def _run(self, model, with_optimizer: bool):
         eng = model.train_engine()
         lf = model.loss_fn
         t0, t1 = (lf.threshold, lf.threshold) if lf.thresholding_mode == "hard" else lf.threshold
@@ -434,79 +534,113 @@ class _TrainPlan:
         grads = _Grads(((n, p) for n, p in model.named_parameters() if p.requires_grad and n != "rescale_factors"),
                        self.flat)
         eng.backward(g_locs, g_scores, grads)
+        if with_optimizer:
+            _optimizer_step(model, self.flat, self.world_size, self.allreduce)
         self.loss = out
 
     def capture(self, model):
-        """Warm up (lazy module loading, workspaces) and record.  The warm-up steps run for real, so the
-        BatchNorm buffers they touch are restored afterwards; parameters are not modified by this part."""
+        """Warm up (lazy module loading, workspaces, the NCCL communicator) and record.  The warm-up steps run
+        for real, so everything they touch -- BatchNorm buffers, parameters, Adam moments and counters -- is
+        restored afterwards."""
+        flat = self.flat
+        in_graph = os.environ.get("SSD3D_TRAIN_OPT_IN_GRAPH", "1") != "0"
         buffers = {k: v.clone() for k, v in model.named_buffers()}
+        saved = [t.clone() for t in (flat.param, flat.exp_avg, flat.exp_avg_sq, flat.status)]
         side = torch.cuda.Stream(device=model.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(2):
-                self._run(model)
+                self._run(model, in_graph)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        with torch.no_grad():
-            for k, v in model.named_buffers():
-                v.copy_(buffers[k])
-        graph = torch.cuda.CUDAGraph()
-        before = ops.LAUNCHES[0]
+
+        def restore():
+            with torch.no_grad():
+                for k, v in model.named_buffers():
+                    v.copy_(buffers[k])
+                for t, v in zip((flat.param, flat.exp_avg, flat.exp_avg_sq, flat.status), saved):
+                    t.copy_(v)
+                model.train_engine().packed.refresh()
+            torch.cuda.synchronize()
+
+        restore()
         # the capture stream is high priority: the critical chain then wins free SM slots over the weight-gradient
         # side stream (kernel nodes inherit the priority of the stream they were captured on)
         cap = torch.cuda.Stream(device=model.device, priority=-1)
-        with torch.no_grad(), torch.cuda.graph(graph, stream=cap):
-            self._run(model)
+        before = ops.LAUNCHES[0]
+        graph = torch.cuda.CUDAGraph()
+        try:
+            # thread_local: the NCCL watchdog thread may query events of earlier collectives while we capture
+            with torch.no_grad(), torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
+                self._run(model, in_graph)
+            self.optimizer_in_graph = in_graph
+        except Exception:
+            if not (in_graph and self.allreduce is not None):
+                raise
+            # a collective that cannot be captured (a custom ``allreduce`` callable): optimizer outside the graph
+            torch.cuda.synchronize()
+            restore()
+            ops.LAUNCHES[0] = before
+            graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
+                self._run(model, False)
+            self.optimizer_in_graph = False
         self.n_kernels = ops.LAUNCHES[0] - before
         ops.LAUNCHES[0] = before
         self.graph = graph
+        ops.pin_workspaces()     # the graph bakes the scratch addresses in: they must outlive it
+
+
+T_MAX = 40      # CosineAnnealingLR(optimizer, T_max=40), ssd3d.py:719
 
 
 def _optimizer_step(model, flat, world_size, allreduce):
+    """(all-reduce) + Adam + re-pack; everything on the device, capturable."""
     if allreduce is not None:
         allreduce(flat.grad)
-    flat.step += 1
-    lr = float(model.lr)
-    if model.scheduler != "none":
-        # the reference steps the scheduler inside training_step, i.e. before the optimizer step of the
-        # same batch (ssd3d.py:525-527): optimizer step k (1-based) runs at the k-th scheduled rate
-        lr = cosine_lr(lr, flat.step)
-    ops.adam_step(flat.param, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.bias_start, lr, 2.0 * lr, flat.step,
-                  weight_decay=0.0005, grad_scale=1.0 / float(world_size), status=flat.status)
+    ops.adam_step_dev(flat.param, flat.grad, flat.exp_avg, flat.exp_avg_sq, flat.bias_start, float(model.lr),
+                      flat.status, flat.scalars, t_max=(T_MAX if model.scheduler != "none" else 0), bias_lr_mult=2.0,
+                      weight_decay=0.0005, grad_scale=1.0 / float(world_size))
     model.train_engine().packed.refresh()      # every packed weight layout for the next step: two launches
-    model.invalidate_packed()
 
 
 def fit_step(model, batch, world_size: int = 1, allreduce=None):
     """One fused optimisation step: forward, MultiBox loss + its gradient, backward into the flat gradient
     buffer, (all-reduce), fused Adam.  Returns a (2,) device tensor [conf_loss, loc_loss] -- no host sync.
-    With ``model.use_cuda_graph`` the forward..backward part is one CUDA-graph replay per step."""
+    With ``model.use_cuda_graph`` the whole step is one CUDA-graph replay."""
     eng = model.train_engine()
     flat = eng.flatten()
     dev = model.device
     images, gt_boxes, gt_labels = batch["img"], batch["boxes"], batch["labels"]
     if images.dtype not in (torch.float32, torch.bfloat16):
         images = images.float()
+    eng.collective_mode = "none" if allreduce is None else ("nccl all_reduce of the flat gradient, captured in the "
+                                                            "step's CUDA graph")
     if model.use_cuda_graph:
         total = sum(int(b.shape[0]) for b in gt_boxes)
-        key = (tuple(images.shape), images.dtype)
+        key = (tuple(images.shape), images.dtype, int(world_size), allreduce)
         plan = eng.plans.get(key)
         if plan is None or plan.tmax < total:
             tmax = 64
             while tmax < total:
                 tmax *= 2
-            plan = _TrainPlan(model, images, tmax)
+            plan = _TrainPlan(model, images, tmax, world_size, allreduce)
             plan.load(images, gt_boxes, gt_labels)
             model.invalidate_packed()
             plan.capture(model)
-            eng.plans.clear()
+            eng.plans.pop(key, None)
+            if len(eng.plans) >= 4:
+                eng.plans.clear()
             eng.plans[key] = plan
         else:
             plan.load(images, gt_boxes, gt_labels)
         plan.graph.replay()
         ops.LAUNCHES[0] += plan.n_kernels
         with torch.no_grad():
-            _optimizer_step(model, flat, world_size, allreduce)
+            if not plan.optimizer_in_graph:
+                eng.collective_mode = "none" if allreduce is None else "all_reduce after the graph replay"
+                _optimizer_step(model, flat, world_size, allreduce)
+            model.invalidate_packed()
             return plan.loss.clone()
     gt_boxes = [b.to(dev) for b in gt_boxes]
     gt_labels = [l.to(dev) for l in gt_labels]
@@ -521,4 +655,5 @@ def fit_step(model, batch, world_size: int = 1, allreduce=None):
                        flat)
         eng.backward(g_locs, g_scores, grads)
         _optimizer_step(model, flat, world_size, allreduce)
+        model.invalidate_packed()
     return out

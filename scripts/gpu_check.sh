@@ -22,11 +22,14 @@ run detect   tests/test_gpu_detect.py
 run nmslong  tests/test_gpu_nms_long.py
 run match    tests/test_gpu_match_loss.py
 run train    tests/test_gpu_train.py
+run insitu   tests/test_gpu_train_insitu.py -s
+run trainmod tests/test_gpu_train_modules.py
 run metrics  tests/test_gpu_metrics.py
 run gtbox    tests/test_gpu_gtbox.py
 run nms120k  tests/test_gpu_zz_nms_oracle_120k.py
+run nmsbig   tests/test_gpu_zz_nms_oracle_big.py
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; r=$?
 echo "== smoke: exit $r: $(tail -1 gpurun_out/smoke.log)"; [ $r -ne 0 ] && rc=1
-timeout 900 python bench.py --steps 100 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; r=$?
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; r=$?
 echo "== bench: exit $r"; cat gpurun_out/bench.json; [ $r -ne 0 ] && { rc=1; tail -5 gpurun_out/bench.err; }
 exit $rc

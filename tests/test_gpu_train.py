@@ -195,11 +195,13 @@ def test_stem_raw_wgrad(cin, n, size, sd, dtype):
 # ---------------------------------------------------------------------------------------------------
 # SSD heads: gradient rows, bias / weight / data gradients
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("c,n,size", [(128, 2, (6, 6, 6)), (256, 2, (3, 3, 3)), (512, 3, (2, 2, 2)), (128, 1, (5, 7, 4)),
-                                      (128, 1, (12, 12, 12))])
-def test_head_backward(c, n, size):
+@pytest.mark.parametrize("c,n,size,ncls", [(128, 2, (6, 6, 6), 2), (256, 2, (3, 3, 3), 2), (512, 3, (2, 2, 2), 2),
+                                           (128, 1, (5, 7, 4), 2), (128, 1, (12, 12, 12), 2),
+                                           # n_classes >= 3: bpl*(6+n_classes) > 16 -> several 16-column groups
+                                           (128, 2, (6, 6, 6), 3), (256, 1, (4, 3, 5), 5), (128, 1, (5, 5, 5), 11)])
+def test_head_backward(c, n, size, ncls):
     ops = _ops()
-    bpl, ncls = 2, 2
+    bpl = 2
     g = torch.Generator().manual_seed(c + size[0])
     x = bf16r(torch.randn((n, c) + size, generator=g)).requires_grad_(True)
     lw = bf16r(torch.randn((bpl * 6, c, 3, 3, 3), generator=g) * 0.05).requires_grad_(True)
@@ -224,16 +226,20 @@ def test_head_backward(c, n, size):
     torch.testing.assert_close(dbc.cpu(), dscores[:, off:off + v * bpl].reshape(-1, bpl * ncls).sum(0), rtol=1e-4,
                                atol=1e-4)
     want_rows = torch.cat([dl_used.reshape(n * v, bpl * 6), ds_used.reshape(n * v, bpl * ncls)], 1)
-    assert torch.equal(dO.float().cpu(), want_rows)
+    groups = (want_rows.shape[1] + 15) // 16
+    want_rows = F.pad(want_rows, (0, groups * 16 - want_rows.shape[1]))
+    assert tuple(dO.shape) == (groups, n * v, 16)
+    assert torch.equal(dO.float().cpu().permute(1, 0, 2).reshape(n * v, groups * 16), want_rows)
     dwl, dwc = torch.empty_like(lw, device="cuda"), torch.empty_like(cw, device="cuda")
     ops.head_wgrad(dO, to_cl(x.detach()), bpl * 6, bpl * ncls, dwl, dwc)
     assert rel_l2(dwl, lw.grad) < 2e-3 and rel_l2(dwc, cw.grad) < 2e-3, (rel_l2(dwl, lw.grad), rel_l2(dwc, cw.grad))
     wpk, _ = ops.pack_head_weight(lw.detach().cuda(), lb.detach().cuda(), cw.detach().cuda(), cb.detach().cuda())
-    dx = ops.head_dgrad(dO, wpk, to_cl(x.detach()))
-    assert_bf16_close(dx, bf16r(x.grad), "head dgrad")
+    # one pass per 16-column group, each rounding the running sum to bf16
+    dx = ops.head_dgrad(dO, wpk, to_cl(x.detach()), n_cols=bpl * (6 + ncls))
+    assert_bf16_close(dx, bf16r(x.grad), "head dgrad", ulps=1.0 + 0.5 * (groups - 1))
     add = bf16r(torch.randn(x.shape, generator=g))
-    dx2 = ops.head_dgrad(dO, wpk, to_cl(x.detach()), addend=to_cl(add))
-    assert_bf16_close(dx2, bf16r(x.grad + add), "head dgrad + addend", ulps=1.5)
+    dx2 = ops.head_dgrad(dO, wpk, to_cl(x.detach()), addend=to_cl(add), n_cols=bpl * (6 + ncls))
+    assert_bf16_close(dx2, bf16r(x.grad + add), "head dgrad + addend", ulps=1.5 + 0.5 * (groups - 1))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -257,6 +263,44 @@ def test_adam_matches_torch():
         ops.adam_step(p, (grad * 4).cuda(), m, v, bias_start, lr, 2 * lr, step, weight_decay=0.0005, grad_scale=0.25)
         want = torch.cat([pw.detach(), pb.detach()])
         torch.testing.assert_close(p.cpu(), want, rtol=2e-6, atol=2e-7)
+
+
+def test_adam_dev_state_schedule_and_skip():
+    """The graph-capturable step (ssd3d_adam_step_dev): step counter, bias correction and the reference's
+    CosineAnnealingLR(T_max=40) (scheduler stepped BEFORE the optimizer step of the same batch, ssd3d.py:525-527)
+    all on the device; a non-finite gradient skips the update and advances neither counter nor schedule."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    n, bias_start = 5003, 4000
+    p0 = torch.randn(n, generator=g)
+    pw = p0[:bias_start].clone().requires_grad_(True)
+    pb = p0[bias_start:].clone().requires_grad_(True)
+    lr = 1e-3
+    opt = torch.optim.Adam([{"params": [pb], "lr": 2 * lr}, {"params": [pw]}], lr=lr, weight_decay=0.0005)
+    sch = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=40)
+    p = p0.clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    state = torch.zeros(4, dtype=torch.int32, device="cuda")
+    scal = torch.zeros(8, dtype=torch.float32, device="cuda")
+    import warnings
+    for step in range(1, 46):
+        grad = torch.randn(n, generator=g)
+        if step in (3, 17):                  # a batch without positives: NaN gradient -> skipped, nothing advances
+            bad = grad.clone()
+            bad[11] = float("nan")
+            before = p.clone()
+            ops.adam_step_dev(p, bad.cuda(), m, v, bias_start, lr, state, scal, t_max=40, weight_decay=0.0005)
+            assert torch.equal(p, before)
+        pw.grad, pb.grad = grad[:bias_start].clone(), grad[bias_start:].clone()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sch.step()                       # ssd3d.py:525-527: before the optimizer step
+        opt.step()
+        ops.adam_step_dev(p, (grad * 2).cuda(), m, v, bias_start, lr, state, scal, t_max=40, weight_decay=0.0005,
+                          grad_scale=0.5)
+        want = torch.cat([pw.detach(), pb.detach()])
+        torch.testing.assert_close(p.cpu(), want, rtol=3e-6, atol=3e-7, msg="step %d" % step)
+    assert state.cpu().tolist()[:3] == [0, 2, 45]
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -112,3 +112,60 @@ def test_gloo_flat_gradient_allreduce():
     assert ret[0][1:3] == ret[1][1:3]                    # identical layout on every rank
     assert ret[0][1] >= 949936 - 128 and ret[0][1] < 949936 + 8 * 103   # all trainable parameters + padding
     assert ret[0][3] == 1.0 and abs(ret[0][4]) < 1e-12 and abs(ret[0][5] - 0.5) < 1e-12
+
+
+def _replica_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mslesions3d_b200.ssd3d import LSSD3D
+        from mslesions3d_b200.training import (FlatParams, broadcast_replica_state, replica_checksum_matches,
+                                               sync_batchnorm_buffers)
+        torch.manual_seed(100 + rank)                       # every rank builds a DIFFERENT model
+        model = LSSD3D(n_classes=2, input_channels=1, input_size=(64, 64, 64))
+        with torch.no_grad():
+            for _, b in model.named_buffers():
+                if b.is_floating_point():
+                    b.add_(float(rank))                      # and different BatchNorm statistics
+            model.rescale_factors.fill_(20.0 + rank)
+        flat = FlatParams(model)
+        flat.exp_avg.fill_(float(rank))
+        flat.status[2] = 7 * rank
+        differ = not replica_checksum_matches(flat)
+        broadcast_replica_state(model, flat, src=0)
+        same = replica_checksum_matches(flat)
+        digest = float(flat.param.double().sum())
+        bn = float(model.base.features[3].bn2.running_mean.double().sum())
+        ok = bool((flat.exp_avg == 0).all()) and int(flat.status[2]) == 0 and float(model.rescale_factors.mean()) == 20.0
+        # parameters still alias the flat buffer after the broadcast
+        p = dict(model.named_parameters())["base.features.0.0.weight"]
+        ok = ok and p.data_ptr() == flat.param.data_ptr() + 4 * flat.offsets["base.features.0.0.weight"]
+        # rank-local statistics drift apart during training; the on-demand average brings them together again
+        with torch.no_grad():
+            model.base.features[3].bn2.running_mean.add_(float(rank))
+        sync_batchnorm_buffers(model)
+        bn2 = float(model.base.features[3].bn2.running_mean.double().sum())
+        ret[rank] = (differ, same, digest, bn, ok, bn2)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_replicas_start_identical_from_different_seeds():
+    """multi-rank fit_step only all-reduced gradients; ranks built from different RNG states must be
+    made replicas of rank 0 (parameters, Adam state, BatchNorm buffers) before the first step."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_replica_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert ret[0][0] and ret[1][0]                 # they really started different
+    assert ret[0][1] and ret[1][1]                 # and are bit-identical afterwards
+    assert ret[0][2] == ret[1][2] and ret[0][3] == ret[1][3]
+    assert ret[0][4] and ret[1][4]
+    assert ret[0][5] == ret[1][5] and abs(ret[0][5] - (ret[0][3] + 0.5 * 128)) < 1e-3
