@@ -33,6 +33,31 @@ extern "C" {
 #define SSD3D_NAN_LOCS 2
 #define SSD3D_NAN_SCORES 4
 
+/* ------------------------------------------------------------------------------------------------
+ * Prior (default) boxes as a closed-form function of the prior index (ssd3d.py:286-342).
+ * Prior p of layer l (start[l] <= p < start[l+1]):  local = p - start[l], b = local % n_boxes[l],
+ * v = local / n_boxes[l], (i, j, k) = unravel(v, (d0, d1, d2)):
+ *     cx = fp32((j + 0.5) / d1)   cy = fp32((i + 0.5) / d0)   cz = fp32((k + 0.5) / d2)     -- evaluated in
+ * float64 and rounded once to fp32, exactly what the reference's Python doubles -> torch.FloatTensor do (note
+ * the axis quirk: cx follows array axis 1, cy axis 0, ssd3d.py:304-309);  edge = size[l][b] three times, the
+ * host-computed fp32(clamp(s + s/div, 0, 1)) of ssd3d.py:311,330.  Entry points whose name ends in _analytic
+ * take a DEVICE copy of this table where their sibling takes the (P, 6) prior tensor, and recompute each prior
+ * from its index instead of reading 24 bytes of it (60 MB per volume at 2.5 M priors); results are bit-identical.
+ * ---------------------------------------------------------------------------------------------- */
+#define SSD3D_MAX_PRIOR_LAYERS 8
+#define SSD3D_MAX_PRIOR_SIZES 4
+typedef struct ssd3d_prior_table {
+  int32_t n_layers;
+  int32_t d0[SSD3D_MAX_PRIOR_LAYERS], d1[SSD3D_MAX_PRIOR_LAYERS], d2[SSD3D_MAX_PRIOR_LAYERS];
+  int32_t n_boxes[SSD3D_MAX_PRIOR_LAYERS];
+  int32_t pad_;
+  int64_t start[SSD3D_MAX_PRIOR_LAYERS + 1];
+  float size[SSD3D_MAX_PRIOR_LAYERS][SSD3D_MAX_PRIOR_SIZES];
+} ssd3d_prior_table;
+
+/* Materialise the table: out (P, 6) fp32 = create_prior_boxes() (ssd3d.py:286-342).  table: device pointer. */
+int ssd3d_prior_boxes(const ssd3d_prior_table* table, int64_t P, float* out, void* stream);
+
 /* Library / build identification ("ssd3d_b200 sm_100a <n>"). */
 const char* ssd3d_version(void);
 
@@ -291,6 +316,25 @@ int64_t ssd3d_dw_wgrad_workspace_bytes(int C);
 int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C, int D, int H, int W, int stride, float* dw,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Analytic-prior siblings (see ssd3d_prior_table above): identical contracts and bit-identical results, with a
+ * device pointer to the prior table where the sibling takes the (P, 6) prior tensor
+ * (ssd3d_decode_softmax / ssd3d_decode_filter / ssd3d_detect_objects: ssd3d.py:344-460;
+ * ssd3d_match_priors: ssd3d.py:786-888). */
+int ssd3d_decode_softmax_analytic(const float* locs, const float* scores, const ssd3d_prior_table* table, int N,
+                                  int64_t P, int n_classes, float* probs, float* boxes_xyz, void* stream);
+int ssd3d_decode_filter_analytic(const float* locs, const float* scores, const ssd3d_prior_table* table, int N,
+                                 int64_t P, int n_classes, float min_score, float* boxes_xyz, uint64_t* cand,
+                                 int32_t* count, void* stream);
+int ssd3d_detect_objects_analytic(const float* locs, const float* scores, const ssd3d_prior_table* table, int N,
+                                  int64_t P, int n_classes, float min_score, float max_overlap, int top_k,
+                                  float* out_boxes, float* out_scores, int64_t* out_labels, int64_t* out_prior,
+                                  int32_t* out_count, void* workspace, int64_t workspace_bytes, int32_t* status,
+                                  void* stream);
+int ssd3d_match_priors_analytic(const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets, int N,
+                                int64_t T, const ssd3d_prior_table* table, int64_t P, float t0, float t1,
+                                int64_t* true_classes, float* true_locs, float* overlap, int32_t* object_for_prior,
+                                int32_t* prior_for_object, void* best_key_ws, void* stream);
+
 /* One Adam step over flat fp32 buffers with torch.optim.Adam's arithmetic (L2 weight decay added to the
  * gradient, bias-corrected moments; ssd3d.py:716): elements [0, bias_start) use lr, [bias_start, n) use
  * lr_bias (the reference's "biases at 2x lr" group, ssd3d.py:715).  grad is multiplied by grad_scale first
@@ -348,6 +392,19 @@ int ssd3d_gather_cast(const float* src, const int32_t* index, int64_t n, void* d
 int64_t ssd3d_normalize_workspace_bytes(int items);
 int ssd3d_normalize_intensity_nonzero(const float* x, int items, int64_t voxels, void* y, int y_is_bf16,
                                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Synthetic lesion volumes on the device (generate_artificial_dataset.py:63-105): per volume
+ * first_idx + n uniform noise in [0, 1) per channel, randint(num_lo, num_hi) + 1 cubes of side
+ * randint(size_lo, size_hi) at corner randint(0, dim - side) per axis (shared by the channels), each adding 0.4 and
+ * clipping to [0, 1], and the binary mask of the cubes.  Every value is a pure function of (seed, volume index,
+ * channel, voxel) through Philox4x32-10 (the reference's serial MT19937 stream is NOT reproduced; same
+ * distribution, same construction; restated in numpy by oracle/philox_oracle.py).
+ *   out_raw (N, C, D, H, W) fp32 raw intensities (feed ssd3d_normalize_intensity_nonzero for datasets.py:403)
+ *   mask    (N, D, H, W) uint8, may be NULL      (feed ssd3d_gt_boxes_from_segmentation for utils.py:438-513)
+ *   cubes   (N, max_cubes, 4) int32 {side, corner d, h, w}, n_cubes (N) int32;  max_cubes <= 64 */
+int ssd3d_generate_volumes(uint64_t seed, int64_t first_idx, int N, int C, int D, int H, int W, int num_lo,
+                           int num_hi, int size_lo, int size_hi, int max_cubes, float* out_raw, uint8_t* mask,
+                           int32_t* cubes, int32_t* n_cubes, void* stream);
 
 /* Ground-truth boxes from segmentation volumes (utils.py:438-513 BoundingBoxesGeneratord,
  * segmentation_mode "binary" (n_classes = 0: every non-zero voxel, label 1) or "classes" (n_classes >= 1: voxels

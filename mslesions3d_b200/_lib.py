@@ -23,6 +23,17 @@ BOX_CXCYCZ_TO_XYZ, BOX_XYZ_TO_CXCYCZ, BOX_GCXGCYGCZ_TO_CXCYCZ, BOX_CXCYCZ_TO_GCX
 
 P = c_void_p  # every device pointer / stream crosses the ABI as a plain address
 
+MAX_PRIOR_LAYERS, MAX_PRIOR_SIZES = 8, 4
+
+
+class PriorTable(ctypes.Structure):
+    """``ssd3d_prior_table`` of include/ssd3d_b200.h (prior boxes as a closed-form function of the prior index)."""
+    _fields_ = [("n_layers", c_int32),
+                ("d0", c_int32 * MAX_PRIOR_LAYERS), ("d1", c_int32 * MAX_PRIOR_LAYERS), ("d2", c_int32 * MAX_PRIOR_LAYERS),
+                ("n_boxes", c_int32 * MAX_PRIOR_LAYERS), ("pad_", c_int32),
+                ("start", c_int64 * (MAX_PRIOR_LAYERS + 1)),
+                ("size", (c_float * MAX_PRIOR_SIZES) * MAX_PRIOR_LAYERS)]
+
 # name -> (restype, argtypes); mirrors include/ssd3d_b200.h one to one
 SIGNATURES = {
     "ssd3d_version": (c_char_p, []),
@@ -85,6 +96,15 @@ SIGNATURES = {
                                 c_int64, P]),
     "ssd3d_adam_step": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_float, c_float, c_float, c_float,
                                 c_int, c_float, P, P]),
+    "ssd3d_generate_volumes": (c_int, [ctypes.c_uint64, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, P, P, P, P, P]),
+    "ssd3d_prior_boxes": (c_int, [P, c_int64, P, P]),
+    "ssd3d_decode_softmax_analytic": (c_int, [P, P, P, c_int, c_int64, c_int, P, P, P]),
+    "ssd3d_decode_filter_analytic": (c_int, [P, P, P, c_int, c_int64, c_int, c_float, P, P, P, P]),
+    "ssd3d_detect_objects_analytic": (c_int, [P, P, P, c_int, c_int64, c_int, c_float, c_float, c_int, P, P, P, P, P,
+                                              P, c_int64, P, P]),
+    "ssd3d_match_priors_analytic": (c_int, [P, P, P, c_int, c_int64, P, c_int64, c_float, c_float, P, P, P, P, P, P,
+                                            P]),
     "ssd3d_adam_step_dev": (c_int, [P, P, P, P, c_int64, c_int64, c_float, c_float, c_int, c_float, c_float, c_float,
                                     c_float, c_float, P, P, P]),
 }

@@ -87,6 +87,42 @@ __device__ __forceinline__ Box6 cxcycz_to_gcxgcygcz(const Box6& c, const Box6& p
   return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Prior source: the (P, 6) tensor, or the closed form of ssd3d.py:300-330 evaluated from the prior index
+// (float64 arithmetic rounded once to fp32, like the reference's Python doubles -> FloatTensor).
+// ------------------------------------------------------------------------------------------------
+static_assert(sizeof(ssd3d_prior_table) == 336, "ssd3d_prior_table layout is part of the ABI (_lib.PriorTable mirrors it)");
+
+struct PriorSrc {
+  const float* ptr;                  // (P, 6) centre-size priors, or nullptr
+  const ssd3d_prior_table* tbl;      // device copy of the table (used when ptr == nullptr)
+};
+
+__device__ __forceinline__ Box6 prior_from_table(const ssd3d_prior_table* __restrict__ t, long long p) {
+  int l = 0;
+  const int nl = t->n_layers;
+  while (l + 1 < nl && p >= t->start[l + 1]) ++l;
+  const long long local = p - t->start[l];
+  const int nb = t->n_boxes[l];
+  const int b = (int)(local % nb);
+  long long v = local / nb;
+  const int d0 = t->d0[l], d1 = t->d1[l], d2 = t->d2[l];
+  const int k = (int)(v % d2); v /= d2;
+  const int j = (int)(v % d1);
+  const int i = (int)(v / d1);
+  Box6 r;
+  r.v[0] = __double2float_rn(__ddiv_rn((double)j + 0.5, (double)d1));     // cx <- array axis 1 (ssd3d.py:305)
+  r.v[1] = __double2float_rn(__ddiv_rn((double)i + 0.5, (double)d0));     // cy <- array axis 0 (ssd3d.py:306)
+  r.v[2] = __double2float_rn(__ddiv_rn((double)k + 0.5, (double)d2));     // cz <- array axis 2 (ssd3d.py:304)
+  const float s = t->size[l][b];
+  r.v[3] = s; r.v[4] = s; r.v[5] = s;
+  return r;
+}
+
+__device__ __forceinline__ Box6 load_prior(const PriorSrc& src, long long p) {
+  return src.ptr ? load_box(src.ptr + p * 6) : prior_from_table(src.tbl, p);
+}
+
 // order-preserving map float -> uint32 (ascending)
 __device__ __forceinline__ uint32_t float_orderable(float f) {
   const uint32_t u = __float_as_uint(f);

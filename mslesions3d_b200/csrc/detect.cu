@@ -27,13 +27,13 @@ __device__ __forceinline__ void softmax_small(const float* s, int C, F&& emit) {
 
 __global__ void __launch_bounds__(256) decode_softmax_kernel(const float* __restrict__ locs,
                                                              const float* __restrict__ scores,
-                                                             const float* __restrict__ priors, long long P, int C,
+                                                             const PriorSrc priors, long long P, int C,
                                                              float* __restrict__ probs, float* __restrict__ boxes) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int img = blockIdx.y;
   if (p >= P) return;
   const long long ip = (long long)img * P + p;
-  const Box6 xyz = cxcycz_to_xyz(gcxgcygcz_to_cxcycz(load_box(locs + ip * 6), load_box(priors + p * 6)));
+  const Box6 xyz = cxcycz_to_xyz(gcxgcygcz_to_cxcycz(load_box(locs + ip * 6), load_prior(priors, p)));
   store_box(boxes + ip * 6, xyz);
   const float* s = scores + ip * C;
   float* o = probs + ip * C;
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) decode_softmax_kernel(const float* __rest
 // cand layout: segment seg = img*(C-1) + (c-1) owns cand[seg*P .. seg*P + count[seg])
 __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restrict__ locs,
                                                             const float* __restrict__ scores,
-                                                            const float* __restrict__ priors, long long P, int C,
+                                                            const PriorSrc priors, long long P, int C,
                                                             float min_score, float* __restrict__ boxes,
                                                             unsigned long long* __restrict__ cand,
                                                             int* __restrict__ count) {
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
   const bool live = p < P;
   const long long ip = (long long)img * P + (live ? p : 0);
   if (live) {
-    const Box6 xyz = cxcycz_to_xyz(gcxgcygcz_to_cxcycz(load_box(locs + ip * 6), load_box(priors + p * 6)));
+    const Box6 xyz = cxcycz_to_xyz(gcxgcygcz_to_cxcycz(load_box(locs + ip * 6), load_prior(priors, p)));
     store_box(boxes + ip * 6, xyz);
   }
   const float* s = scores + ip * C;
@@ -1085,14 +1085,39 @@ extern "C" int64_t ssd3d_detect_workspace_bytes(int N, int64_t P, int n_classes,
   return detect_layout(N, P, n_classes, top_k).total;
 }
 
-extern "C" int ssd3d_decode_softmax(const float* locs, const float* scores, const float* priors, int N, int64_t P,
-                                    int n_classes, float* probs, float* boxes_xyz, void* stream) {
-  if (!locs || !scores || !priors || !probs || !boxes_xyz || N <= 0 || P <= 0 || n_classes < 1) return SSD3D_ERR_ARG;
+namespace ssd3d {
+__global__ void __launch_bounds__(256) prior_boxes_kernel(const ssd3d_prior_table* __restrict__ tbl, long long P,
+                                                          float* __restrict__ out) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) store_box(out + p * 6, prior_from_table(tbl, p));
+}
+}  // namespace ssd3d
+
+extern "C" int ssd3d_prior_boxes(const ssd3d_prior_table* table, int64_t P, float* out, void* stream) {
+  if (!table || !out || P <= 0) return SSD3D_ERR_ARG;
+  prior_boxes_kernel<<<(unsigned)((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, (long long)P, out);
+  SSD3D_CHECK_LAUNCH();
+  return SSD3D_OK;
+}
+
+static int decode_softmax_impl(const float* locs, const float* scores, PriorSrc priors, int N, int64_t P,
+                               int n_classes, float* probs, float* boxes_xyz, void* stream) {
+  if (!locs || !scores || (!priors.ptr && !priors.tbl) || !probs || !boxes_xyz || N <= 0 || P <= 0 || n_classes < 1)
+    return SSD3D_ERR_ARG;
   dim3 grid((unsigned)((P + 255) / 256), (unsigned)N);
   decode_softmax_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(locs, scores, priors, P, n_classes, probs,
                                                                             boxes_xyz);
   SSD3D_CHECK_LAUNCH();
   return SSD3D_OK;
+}
+extern "C" int ssd3d_decode_softmax(const float* locs, const float* scores, const float* priors, int N, int64_t P,
+                                    int n_classes, float* probs, float* boxes_xyz, void* stream) {
+  return decode_softmax_impl(locs, scores, PriorSrc{priors, nullptr}, N, P, n_classes, probs, boxes_xyz, stream);
+}
+extern "C" int ssd3d_decode_softmax_analytic(const float* locs, const float* scores, const ssd3d_prior_table* table,
+                                             int N, int64_t P, int n_classes, float* probs, float* boxes_xyz,
+                                             void* stream) {
+  return decode_softmax_impl(locs, scores, PriorSrc{nullptr, table}, N, P, n_classes, probs, boxes_xyz, stream);
 }
 
 extern "C" int ssd3d_nms3d_sorted(const float* boxes_xyz, int64_t n, float max_overlap, uint8_t* keep, void* mask_ws,
@@ -1271,10 +1296,10 @@ extern "C" int ssd3d_sort_keys_u64(uint64_t* keys, int64_t n, uint64_t* tmp, voi
   return SSD3D_OK;
 }
 
-extern "C" int ssd3d_decode_filter(const float* locs, const float* scores, const float* priors, int N, int64_t P,
-                                   int n_classes, float min_score, float* boxes_xyz, uint64_t* cand, int32_t* count,
-                                   void* stream) {
-  if (!locs || !scores || !priors || !boxes_xyz || !cand || !count) return SSD3D_ERR_ARG;
+static int decode_filter_impl(const float* locs, const float* scores, PriorSrc priors, int N, int64_t P,
+                              int n_classes, float min_score, float* boxes_xyz, uint64_t* cand, int32_t* count,
+                              void* stream) {
+  if (!locs || !scores || (!priors.ptr && !priors.tbl) || !boxes_xyz || !cand || !count) return SSD3D_ERR_ARG;
   if (N <= 0 || P <= 0 || n_classes < 2 || P > 0x7fffffffll) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(count, 0, (size_t)N * (n_classes - 1) * 4, st);
@@ -1286,11 +1311,24 @@ extern "C" int ssd3d_decode_filter(const float* locs, const float* scores, const
   return SSD3D_OK;
 }
 
-extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, const float* priors, int N, int64_t P,
-                                    int n_classes, float min_score, float max_overlap, int top_k, float* out_boxes,
-                                    float* out_scores, int64_t* out_labels, int64_t* out_prior, int32_t* out_count,
-                                    void* workspace, int64_t workspace_bytes, int32_t* status, void* stream) {
-  if (!locs || !scores || !priors || !out_boxes || !out_scores || !out_labels || !out_prior || !out_count || !workspace)
+extern "C" int ssd3d_decode_filter(const float* locs, const float* scores, const float* priors, int N, int64_t P,
+                                   int n_classes, float min_score, float* boxes_xyz, uint64_t* cand, int32_t* count,
+                                   void* stream) {
+  return decode_filter_impl(locs, scores, PriorSrc{priors, nullptr}, N, P, n_classes, min_score, boxes_xyz, cand, count,
+                            stream);
+}
+extern "C" int ssd3d_decode_filter_analytic(const float* locs, const float* scores, const ssd3d_prior_table* table,
+                                            int N, int64_t P, int n_classes, float min_score, float* boxes_xyz,
+                                            uint64_t* cand, int32_t* count, void* stream) {
+  return decode_filter_impl(locs, scores, PriorSrc{nullptr, table}, N, P, n_classes, min_score, boxes_xyz, cand, count,
+                            stream);
+}
+
+static int detect_objects_impl(const float* locs, const float* scores, PriorSrc priors, int N, int64_t P,
+                               int n_classes, float min_score, float max_overlap, int top_k, float* out_boxes,
+                               float* out_scores, int64_t* out_labels, int64_t* out_prior, int32_t* out_count,
+                               void* workspace, int64_t workspace_bytes, int32_t* status, void* stream) {
+  if (!locs || !scores || (!priors.ptr && !priors.tbl) || !out_boxes || !out_scores || !out_labels || !out_prior || !out_count || !workspace)
     return SSD3D_ERR_ARG;
   if (N <= 0 || P <= 0 || n_classes < 2 || top_k <= 0 || P > 0x7fffffffll) return SSD3D_ERR_ARG;
   const DetectLayout L = detect_layout(N, P, n_classes, top_k);
@@ -1377,4 +1415,23 @@ extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, cons
                      reinterpret_cast<long long*>(out_labels), reinterpret_cast<long long*>(out_prior), out_count);
   }
   return SSD3D_OK;
+}
+
+extern "C" int ssd3d_detect_objects(const float* locs, const float* scores, const float* priors, int N, int64_t P,
+                                    int n_classes, float min_score, float max_overlap, int top_k, float* out_boxes,
+                                    float* out_scores, int64_t* out_labels, int64_t* out_prior, int32_t* out_count,
+                                    void* workspace, int64_t workspace_bytes, int32_t* status, void* stream) {
+  return detect_objects_impl(locs, scores, PriorSrc{priors, nullptr}, N, P, n_classes, min_score, max_overlap, top_k,
+                             out_boxes, out_scores, out_labels, out_prior, out_count, workspace, workspace_bytes, status,
+                             stream);
+}
+
+extern "C" int ssd3d_detect_objects_analytic(const float* locs, const float* scores, const ssd3d_prior_table* table,
+                                             int N, int64_t P, int n_classes, float min_score, float max_overlap,
+                                             int top_k, float* out_boxes, float* out_scores, int64_t* out_labels,
+                                             int64_t* out_prior, int32_t* out_count, void* workspace,
+                                             int64_t workspace_bytes, int32_t* status, void* stream) {
+  return detect_objects_impl(locs, scores, PriorSrc{nullptr, table}, N, P, n_classes, min_score, max_overlap, top_k,
+                             out_boxes, out_scores, out_labels, out_prior, out_count, workspace, workspace_bytes, status,
+                             stream);
 }

@@ -15,7 +15,7 @@ constexpr int OBJ_CHUNK = 64;
 
 __global__ void __launch_bounds__(256) match_iou_kernel(const float* __restrict__ gt_boxes,
                                                         const int* __restrict__ gt_offsets,
-                                                        const float* __restrict__ priors, long long P,
+                                                        const PriorSrc priors, long long P,
                                                         float* __restrict__ overlap, int* __restrict__ obj_for_prior,
                                                         unsigned long long* __restrict__ best_key) {
   const int img = blockIdx.y;
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) match_iou_kernel(const float* __restrict_
   Box6 pr;
   float vp = 0.f;
   if (live) {
-    pr = cxcycz_to_xyz(load_box(priors + p * 6));   // MultiBoxLoss.priors_xyz, ssd3d.py:753
+    pr = cxcycz_to_xyz(load_prior(priors, p));   // MultiBoxLoss.priors_xyz, ssd3d.py:753
     vp = box_volume(pr);
   }
   __shared__ float ob[OBJ_CHUNK][6];
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) match_iou_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) match_assign_kernel(const float* __restrict__ gt_boxes,
                                                            const long long* __restrict__ gt_labels,
                                                            const int* __restrict__ gt_offsets,
-                                                           const float* __restrict__ priors, long long P, float t0,
+                                                           const PriorSrc priors, long long P, float t0,
                                                            float t1, const unsigned long long* __restrict__ best_key,
                                                            float* __restrict__ overlap, int* __restrict__ obj_for_prior,
                                                            int* __restrict__ prior_for_obj,
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) match_assign_kernel(const float* __restri
   overlap[ip] = ovl;
   obj_for_prior[ip] = o;
   const Box6 enc = cxcycz_to_gcxgcygcz(xyz_to_cxcycz(load_box(gt_boxes + (long long)(g0 + o) * 6)),
-                                       load_box(priors + p * 6));
+                                       load_prior(priors, p));
   store_box(true_locs + ip * 6, enc);
 }
 
@@ -344,11 +344,11 @@ static inline long long align256(long long v) { return (v + 255) & ~255ll; }
 
 using namespace ssd3d;
 
-extern "C" int ssd3d_match_priors(const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets, int N,
-                                  int64_t T, const float* priors_cxcycz, int64_t P, float t0, float t1,
-                                  int64_t* true_classes, float* true_locs, float* overlap, int32_t* object_for_prior,
-                                  int32_t* prior_for_object, void* best_key_ws, void* stream) {
-  if (!gt_offsets || !priors_cxcycz || !true_classes || !true_locs || !overlap || !object_for_prior) return SSD3D_ERR_ARG;
+static int match_priors_impl(const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets, int N,
+                             int64_t T, PriorSrc priors_cxcycz, int64_t P, float t0, float t1,
+                             int64_t* true_classes, float* true_locs, float* overlap, int32_t* object_for_prior,
+                             int32_t* prior_for_object, void* best_key_ws, void* stream) {
+  if (!gt_offsets || (!priors_cxcycz.ptr && !priors_cxcycz.tbl) || !true_classes || !true_locs || !overlap || !object_for_prior) return SSD3D_ERR_ARG;
   if (N <= 0 || P <= 0 || T < 0 || P > 0x7fffffffll) return SSD3D_ERR_ARG;
   if (T > 0 && (!gt_boxes || !gt_labels || !prior_for_object || !best_key_ws)) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -367,6 +367,22 @@ extern "C" int ssd3d_match_priors(const float* gt_boxes, const int64_t* gt_label
                                             reinterpret_cast<long long*>(true_classes), true_locs);
   SSD3D_CHECK_LAUNCH();
   return SSD3D_OK;
+}
+
+extern "C" int ssd3d_match_priors(const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets, int N,
+                                  int64_t T, const float* priors_cxcycz, int64_t P, float t0, float t1,
+                                  int64_t* true_classes, float* true_locs, float* overlap, int32_t* object_for_prior,
+                                  int32_t* prior_for_object, void* best_key_ws, void* stream) {
+  return match_priors_impl(gt_boxes, gt_labels, gt_offsets, N, T, PriorSrc{priors_cxcycz, nullptr}, P, t0, t1,
+                           true_classes, true_locs, overlap, object_for_prior, prior_for_object, best_key_ws, stream);
+}
+extern "C" int ssd3d_match_priors_analytic(const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets,
+                                           int N, int64_t T, const ssd3d_prior_table* table, int64_t P, float t0,
+                                           float t1, int64_t* true_classes, float* true_locs, float* overlap,
+                                           int32_t* object_for_prior, int32_t* prior_for_object, void* best_key_ws,
+                                           void* stream) {
+  return match_priors_impl(gt_boxes, gt_labels, gt_offsets, N, T, PriorSrc{nullptr, table}, P, t0, t1, true_classes,
+                           true_locs, overlap, object_for_prior, prior_for_object, best_key_ws, stream);
 }
 
 extern "C" int64_t ssd3d_multibox_workspace_bytes(int N, int64_t P) {

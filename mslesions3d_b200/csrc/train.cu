@@ -740,12 +740,13 @@ __global__ void __launch_bounds__(256) head_grad_pack_kernel(const float* __rest
 // implicit GEMM, M x C output, K = 27 taps x 16; CTA = 64 rows x 64 channels, 4 warps (16 rows each).
 // ------------------------------------------------------------------------------------------------
 struct HeadDgradParams {
-  const bf16* dO;        // (M, 16)
-  const bf16* w;         // (16, 27*C)
+  const bf16* dO;        // (groups, M, 16)
+  const bf16* w;         // (16*groups, 27*C)
   const bf16* addend;    // (M, C) or null
   bf16* dx;              // (M, C)
   int N, D, H, W, C;
   long long M;
+  int groups;            // 16 gradient columns each, accumulated in fp32 inside the kernel
 };
 
 __global__ void __launch_bounds__(128) head_dgrad_kernel(const HeadDgradParams p) {
@@ -758,12 +759,6 @@ __global__ void __launch_bounds__(128) head_dgrad_kernel(const HeadDgradParams p
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long m0 = (long long)blockIdx.x * 64;
   const int c0 = blockIdx.y * 64;
-  for (int q = tid; q < 27 * 16 * 8; q += 128) {
-    const int row = q >> 3, cc = q & 7;          // row = tap*16 + n
-    const int tap = row >> 4, n = row & 15;
-    *reinterpret_cast<uint4*>(&sB[row * BP + cc * 8]) =
-        ld_nc16(p.w + (size_t)n * 27 * p.C + (size_t)tap * p.C + c0 + cc * 8);
-  }
   // gather role: row = tid/2, half = tid%2
   const int arow = tid >> 1, ahalf = tid & 1;
   const long long am = m0 + arow;
@@ -783,25 +778,36 @@ __global__ void __launch_bounds__(128) head_dgrad_kernel(const HeadDgradParams p
     for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
   const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
   const int lq = lane >> 3, lr = lane & 7;
-  for (int tap = 0; tap < 27; ++tap) {
-    const int buf = tap & 1;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    {
-      const int d = ad - (tap / 9 - 1), h = ah - ((tap / 3) % 3 - 1), w = aw - (tap % 3 - 1);
-      if (am < p.M && (unsigned)d < (unsigned)p.D && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
-        v = ld_nc16(p.dO + ((((long long)an * p.D + d) * p.H + h) * p.W + w) * 16 + ahalf * 8);
+  for (int g = 0; g < p.groups; ++g) {
+    const bf16* wg = p.w + (size_t)g * 16 * 27 * p.C;
+    const bf16* dOg = p.dO + (size_t)g * p.M * 16;
+    if (g) __syncthreads();                        // every warp is done with the previous group's weights / rows
+    for (int q = tid; q < 27 * 16 * 8; q += 128) {
+      const int row = q >> 3, cc = q & 7;          // row = tap*16 + n
+      const int tap = row >> 4, n = row & 15;
+      *reinterpret_cast<uint4*>(&sB[row * BP + cc * 8]) =
+          ld_nc16(wg + (size_t)n * 27 * p.C + (size_t)tap * p.C + c0 + cc * 8);
     }
-    *reinterpret_cast<uint4*>(&sA[(buf * 64 + arow) * AP + ahalf * 8]) = v;
-    __syncthreads();
-    uint32_t afr[4];
-    // A (16 rows x k16): matrices {rows 0-7 | 8-15} x {cols 0-7 | 8-15}
-    ldsm_x4(sA_u + (uint32_t)(((buf * 64 + warp * 16 + (lq & 1) * 8 + lr) * AP + (lq >> 1) * 8) * 2), afr);
+    for (int tap = 0; tap < 27; ++tap) {
+      const int buf = tap & 1;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      {
+        const int d = ad - (tap / 9 - 1), h = ah - ((tap / 3) % 3 - 1), w = aw - (tap % 3 - 1);
+        if (am < p.M && (unsigned)d < (unsigned)p.D && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W)
+          v = ld_nc16(dOg + ((((long long)an * p.D + d) * p.H + h) * p.W + w) * 16 + ahalf * 8);
+      }
+      *reinterpret_cast<uint4*>(&sA[(buf * 64 + arow) * AP + ahalf * 8]) = v;
+      __syncthreads();
+      uint32_t afr[4];
+      // A (16 rows x k16): matrices {rows 0-7 | 8-15} x {cols 0-7 | 8-15}
+      ldsm_x4(sA_u + (uint32_t)(((buf * 64 + warp * 16 + (lq & 1) * 8 + lr) * AP + (lq >> 1) * 8) * 2), afr);
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      uint32_t bfr[4];
-      ldsm_x4_t(sB_u + (uint32_t)(((tap * 16 + (lq & 1) * 8 + lr) * BP + jj * 16 + (lq >> 1) * 8) * 2), bfr);
-      mma_bf16(acc[jj * 2], afr, bfr[0], bfr[1]);
-      mma_bf16(acc[jj * 2 + 1], afr, bfr[2], bfr[3]);
+      for (int jj = 0; jj < 4; ++jj) {
+        uint32_t bfr[4];
+        ldsm_x4_t(sB_u + (uint32_t)(((tap * 16 + (lq & 1) * 8 + lr) * BP + jj * 16 + (lq >> 1) * 8) * 2), bfr);
+        mma_bf16(acc[jj * 2], afr, bfr[0], bfr[1]);
+        mma_bf16(acc[jj * 2 + 1], afr, bfr[2], bfr[3]);
+      }
     }
   }
 #pragma unroll
@@ -1534,17 +1540,14 @@ extern "C" int ssd3d_head_dgrad(const void* dO, const void* w, const void* adden
   cudaError_t e = cudaFuncSetAttribute(head_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)((M + 63) / 64), (unsigned)(C / 64));
-  // 16 gradient columns per pass: dx = addend + sum_g dO_g . W_g, group g > 0 accumulating onto the result so far
-  // (every element is read and written by the same thread of the same CTA: in place is safe)
-  for (int g = 0; g < groups; ++g) {
-    HeadDgradParams p{};
-    p.dO = static_cast<const bf16*>(dO) + (size_t)g * M * 16;
-    p.w = static_cast<const bf16*>(w) + (size_t)g * 16 * 27 * C;
-    p.addend = g == 0 ? static_cast<const bf16*>(addend) : static_cast<const bf16*>(dx);
-    p.dx = static_cast<bf16*>(dx);
-    p.N = N; p.D = D; p.H = H; p.W = W; p.C = C; p.M = M;
-    SSD3D_LAUNCH_PDL(head_dgrad_kernel, grid, dim3(128), smem, static_cast<cudaStream_t>(stream), p);
-  }
+  // 16 gradient columns per group, all groups accumulated in fp32 registers inside ONE launch
+  HeadDgradParams p{};
+  p.dO = static_cast<const bf16*>(dO);
+  p.w = static_cast<const bf16*>(w);
+  p.addend = static_cast<const bf16*>(addend);
+  p.dx = static_cast<bf16*>(dx);
+  p.N = N; p.D = D; p.H = H; p.W = W; p.C = C; p.M = M; p.groups = groups;
+  SSD3D_LAUNCH_PDL(head_dgrad_kernel, grid, dim3(128), smem, static_cast<cudaStream_t>(stream), p);
   return SSD3D_OK;
 }
 

@@ -233,17 +233,73 @@ def iou3d_pairwise(a: torch.Tensor, b: torch.Tensor, want_iou: bool = True) -> t
 
 
 # ----------------------------------------------------------------------------------------------
+# prior boxes as a function of the prior index (ssd3d.py:286-342)
+# ----------------------------------------------------------------------------------------------
+class PriorTable:
+    """Device copy of ``ssd3d_prior_table`` + the prior count.  ``fmap_dims``: (d0, d1, d2) per prediction layer in
+    prior order; ``sizes``: per layer the box edges as Python floats (float64), e.g. [s, s + s/1] -- rounded to
+    fp32 and clamped to [0, 1] here exactly like ``torch.FloatTensor(...).clamp_(0, 1)`` does."""
+
+    def __init__(self, fmap_dims, sizes, device):
+        if len(fmap_dims) != len(sizes) or not 0 < len(fmap_dims) <= _lib.MAX_PRIOR_LAYERS:
+            raise ValueError("1..%d prediction layers expected" % _lib.MAX_PRIOR_LAYERS)
+        t = _lib.PriorTable()
+        t.n_layers = len(fmap_dims)
+        start = 0
+        for l, ((d0, d1, d2), sz) in enumerate(zip(fmap_dims, sizes)):
+            if not 0 < len(sz) <= _lib.MAX_PRIOR_SIZES:
+                raise ValueError("1..%d boxes per location expected" % _lib.MAX_PRIOR_SIZES)
+            t.d0[l], t.d1[l], t.d2[l], t.n_boxes[l] = int(d0), int(d1), int(d2), len(sz)
+            t.start[l] = start
+            for b, v in enumerate(sz):
+                t.size[l][b] = float(min(max(np.float32(v), np.float32(0.0)), np.float32(1.0)))
+            start += int(d0) * int(d1) * int(d2) * len(sz)
+        t.start[len(fmap_dims)] = start
+        self.count = start
+        self.host = t
+        raw = np.frombuffer(bytes(t), dtype=np.uint8).copy()
+        self.dev = torch.from_numpy(raw).to(device)
+
+    def data_ptr(self) -> int:
+        return self.dev.data_ptr()
+
+    def materialize(self) -> torch.Tensor:
+        """(P, 6) fp32 priors computed on the device: bit-identical to ``LSSD3D.create_prior_boxes()``."""
+        out = torch.empty((self.count, 6), dtype=torch.float32, device=self.dev.device)
+        rc = _lib.load().ssd3d_prior_boxes(self.dev.data_ptr(), self.count, out.data_ptr(), _stream())
+        _lib.check(rc, "ssd3d_prior_boxes")
+        LAUNCHES[0] += 1
+        return out
+
+
+def _prior_arg(priors):
+    """-> (pointer, analytic?) for a (P, 6) tensor or a PriorTable."""
+    if isinstance(priors, PriorTable):
+        return priors.data_ptr(), True
+    return priors.data_ptr(), False
+
+
+def _prior_count(priors) -> int:
+    return priors.count if isinstance(priors, PriorTable) else int(priors.shape[0])
+
+
+# ----------------------------------------------------------------------------------------------
 # detection
 # ----------------------------------------------------------------------------------------------
 def decode_softmax(locs: torch.Tensor, scores: torch.Tensor, priors: torch.Tensor):
     """-> (probs (N,P,C), boxes_xyz (N,P,6)); ssd3d.py:363,373-374."""
-    _need_cuda(locs, scores, priors)
-    locs, scores, priors = locs.float().contiguous(), scores.float().contiguous(), priors.float().contiguous()
+    _need_cuda(locs, scores)
+    locs, scores = locs.float().contiguous(), scores.float().contiguous()
+    if not isinstance(priors, PriorTable):
+        _need_cuda(priors)
+        priors = priors.float().contiguous()
     n, p, c = scores.shape
     probs = torch.empty_like(scores)
     boxes = torch.empty_like(locs)
-    rc = _lib.load().ssd3d_decode_softmax(locs.data_ptr(), scores.data_ptr(), priors.data_ptr(), n, p, c,
-                                          probs.data_ptr(), boxes.data_ptr(), _stream())
+    pp, analytic = _prior_arg(priors)
+    lib = _lib.load()
+    fn = lib.ssd3d_decode_softmax_analytic if analytic else lib.ssd3d_decode_softmax
+    rc = fn(locs.data_ptr(), scores.data_ptr(), pp, n, p, c, probs.data_ptr(), boxes.data_ptr(), _stream())
     _lib.check(rc, "ssd3d_decode_softmax")
     LAUNCHES[0] += 1
     return probs, boxes
@@ -310,17 +366,23 @@ def sort_keys_u64(keys: torch.Tensor) -> torch.Tensor:
 
 def decode_filter(locs: torch.Tensor, scores: torch.Tensor, priors: torch.Tensor, min_score: float):
     """Stage 1 of detect_objects -> (boxes_xyz (N,P,6), cand (S,P) int64 keys, count (S,) int32), S = N*(C-1)."""
-    _need_cuda(locs, scores, priors)
-    locs, scores, priors = locs.float().contiguous(), scores.float().contiguous(), priors.float().contiguous()
+    _need_cuda(locs, scores)
+    locs, scores = locs.float().contiguous(), scores.float().contiguous()
+    if not isinstance(priors, PriorTable):
+        _need_cuda(priors)
+        priors = priors.float().contiguous()
     n, p, c = scores.shape
-    if locs.shape[0] != n or locs.shape[1] != p or priors.shape[0] != p:
+    if locs.shape[0] != n or locs.shape[1] != p or _prior_count(priors) != p:
         raise AssertionError("prior / prediction count mismatch")  # ssd3d.py:370
     dev = locs.device
     boxes = torch.empty((n, p, 6), dtype=torch.float32, device=dev)
     cand = torch.empty((n * (c - 1), p), dtype=torch.int64, device=dev)
     count = torch.empty((n * (c - 1),), dtype=torch.int32, device=dev)
-    rc = _lib.load().ssd3d_decode_filter(locs.data_ptr(), scores.data_ptr(), priors.data_ptr(), n, p, c,
-                                         f32(min_score), boxes.data_ptr(), cand.data_ptr(), count.data_ptr(), _stream())
+    pp, analytic = _prior_arg(priors)
+    lib = _lib.load()
+    fn = lib.ssd3d_decode_filter_analytic if analytic else lib.ssd3d_decode_filter
+    rc = fn(locs.data_ptr(), scores.data_ptr(), pp, n, p, c, f32(min_score), boxes.data_ptr(), cand.data_ptr(),
+            count.data_ptr(), _stream())
     _lib.check(rc, "ssd3d_decode_filter")
     LAUNCHES[0] += 1
     return boxes, cand, count
@@ -402,10 +464,13 @@ def detect_objects_padded(locs: torch.Tensor, scores: torch.Tensor, priors: torc
     """The whole of ``detect_objects`` on the device, no host sync; see include/ssd3d_b200.h.
     ``out_count`` (N,) / ``status`` (1,) int32 may be supplied (e.g. slices of one buffer that is read back
     with a single copy)."""
-    _need_cuda(locs, scores, priors)
-    locs, scores, priors = locs.float().contiguous(), scores.float().contiguous(), priors.float().contiguous()
+    _need_cuda(locs, scores)
+    locs, scores = locs.float().contiguous(), scores.float().contiguous()
+    if not isinstance(priors, PriorTable):
+        _need_cuda(priors)
+        priors = priors.float().contiguous()
     n, p, c = scores.shape
-    if locs.shape[0] != n or locs.shape[1] != p or priors.shape[0] != p:
+    if locs.shape[0] != n or locs.shape[1] != p or _prior_count(priors) != p:
         raise AssertionError("prior / prediction count mismatch")  # ssd3d.py:370
     dev = locs.device
     top_k = int(top_k)
@@ -424,10 +489,11 @@ def detect_objects_padded(locs: torch.Tensor, scores: torch.Tensor, priors: torc
         out_count = torch.empty((n,), dtype=torch.int32, device=dev)
     if status is None:
         status = torch.empty((1,), dtype=torch.int32, device=dev)
-    rc = lib.ssd3d_detect_objects(locs.data_ptr(), scores.data_ptr(), priors.data_ptr(), n, p, c, f32(min_score),
-                                  f32(max_overlap), top_k, out_boxes.data_ptr(), out_scores.data_ptr(),
-                                  out_labels.data_ptr(), out_prior.data_ptr(), out_count.data_ptr(),
-                                  workspace.data_ptr(), workspace.numel(), status.data_ptr(), _stream())
+    pp, analytic = _prior_arg(priors)
+    fn = lib.ssd3d_detect_objects_analytic if analytic else lib.ssd3d_detect_objects
+    rc = fn(locs.data_ptr(), scores.data_ptr(), pp, n, p, c, f32(min_score), f32(max_overlap), top_k,
+            out_boxes.data_ptr(), out_scores.data_ptr(), out_labels.data_ptr(), out_prior.data_ptr(),
+            out_count.data_ptr(), workspace.data_ptr(), workspace.numel(), status.data_ptr(), _stream())
     _lib.check(rc, "ssd3d_detect_objects")
     LAUNCHES[0] += 4
     return DetectOutput(out_boxes, out_scores, out_labels, out_prior, out_count, status)
@@ -454,8 +520,8 @@ def detect_lists(out: DetectOutput, return_prior: bool = False):
 def match_priors(boxes: Sequence[torch.Tensor], labels: Sequence[torch.Tensor], priors_cxcycz: torch.Tensor,
                  t0: float, t1: float):
     """-> dict(true_classes (N,P) int64, true_locs (N,P,6), overlap, object_for_prior, prior_for_object)."""
-    _need_cuda(priors_cxcycz, *boxes, *labels)
-    dev = priors_cxcycz.device
+    _need_cuda(*boxes, *labels)
+    dev = priors_cxcycz.dev.device if isinstance(priors_cxcycz, PriorTable) else priors_cxcycz.device
     n = len(boxes)
     counts = [int(b.shape[0]) for b in boxes]
     offsets = torch.tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), device=dev)
@@ -473,18 +539,20 @@ def match_priors_packed(gt_boxes: Optional[torch.Tensor], gt_labels: Optional[to
     """Same, on already concatenated ground truth: gt_boxes (>= total, 6) fp32, gt_labels (>= total) int64,
     offsets (n+1) int32 on the device.  ``total`` may be a CAPACITY larger than offsets[-1] (static buffers of a
     captured training step): rows past offsets[-1] are never read."""
-    dev = priors_cxcycz.device
-    p = priors_cxcycz.shape[0]
+    analytic = isinstance(priors_cxcycz, PriorTable)
+    dev = priors_cxcycz.dev.device if analytic else priors_cxcycz.device
+    p = _prior_count(priors_cxcycz)
     tc = torch.empty((n, p), dtype=torch.int64, device=dev)
     tl = torch.empty((n, p, 6), dtype=torch.float32, device=dev)
     ov = torch.empty((n, p), dtype=torch.float32, device=dev)
     ofp = torch.empty((n, p), dtype=torch.int32, device=dev)
     pfo = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
     ws = torch.empty((max(total, 1),), dtype=torch.int64, device=dev)
-    pri = priors_cxcycz.float().contiguous()
-    rc = _lib.load().ssd3d_match_priors(_ptr(gt_boxes), _ptr(gt_labels), offsets.data_ptr(), n, total, pri.data_ptr(),
-                                        p, f32(t0), f32(t1), tc.data_ptr(), tl.data_ptr(), ov.data_ptr(),
-                                        ofp.data_ptr(), pfo.data_ptr(), ws.data_ptr(), _stream())
+    pri = priors_cxcycz if analytic else priors_cxcycz.float().contiguous()
+    lib = _lib.load()
+    fn = lib.ssd3d_match_priors_analytic if analytic else lib.ssd3d_match_priors
+    rc = fn(_ptr(gt_boxes), _ptr(gt_labels), offsets.data_ptr(), n, total, pri.data_ptr(), p, f32(t0), f32(t1),
+            tc.data_ptr(), tl.data_ptr(), ov.data_ptr(), ofp.data_ptr(), pfo.data_ptr(), ws.data_ptr(), _stream())
     _lib.check(rc, "ssd3d_match_priors")
     LAUNCHES[0] += 2
     return dict(true_classes=tc, true_locs=tl, overlap=ov, object_for_prior=ofp, prior_for_object=pfo[:total])
@@ -720,7 +788,7 @@ def head_dgrad(dO: torch.Tensor, w_packed: torch.Tensor, like: torch.Tensor, add
     rc = _lib.load().ssd3d_head_dgrad(dO.data_ptr(), w_packed.data_ptr(), _ptr(addend), out.data_ptr(), n, c, d, h, w,
                                       n_cols, _stream())
     _lib.check(rc, "ssd3d_head_dgrad")
-    LAUNCHES[0] += groups
+    LAUNCHES[0] += 1
     return out
 
 
@@ -921,3 +989,26 @@ def gt_boxes_from_instances(seg: torch.Tensor, thresholds, max_boxes: int = 1024
     if max(comps) > max_boxes:
         raise RuntimeError("segmentation has %d instances, max_boxes=%d" % (max(comps), max_boxes))
     return [boxes[i, :counts[i]] for i in range(n)], [labels[i, :counts[i]] for i in range(n)]
+
+
+def generate_volumes(n: int, channels: int, image_size, first_idx: int = 0, seed: int = 0, num_objects=(1, 5),
+                     object_size=(6, 14), device=None, max_cubes: int = 64):
+    """Raw synthetic volumes on the device (generate_artificial_dataset.py:63-105 with a counter-based RNG, see
+    the header): -> (raw (N, C, D, H, W) fp32, mask (N, D, H, W) uint8, cubes (N, max_cubes, 4) int32, n_cubes (N,))."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("generate_volumes runs on a CUDA device; the host generator is synthetic.make_batch")
+    d, h, w = (int(v) for v in image_size)
+    raw = torch.empty((n, channels, d, h, w), dtype=torch.float32, device=dev)
+    mask = torch.empty((n, d, h, w), dtype=torch.uint8, device=dev)
+    cubes = torch.zeros((n, max_cubes, 4), dtype=torch.int32, device=dev)
+    n_cubes = torch.zeros((n,), dtype=torch.int32, device=dev)
+    smin, smax = sorted(int(v) for v in object_size)
+    with torch.cuda.device(dev):
+        rc = _lib.load().ssd3d_generate_volumes(int(seed) & 0xFFFFFFFFFFFFFFFF, int(first_idx), n, channels, d, h, w,
+                                                int(num_objects[0]), int(num_objects[1]), smin, smax, max_cubes,
+                                                raw.data_ptr(), mask.data_ptr(), cubes.data_ptr(), n_cubes.data_ptr(),
+                                                _stream())
+    _lib.check(rc, "ssd3d_generate_volumes")
+    LAUNCHES[0] += 2
+    return raw, mask, cubes, n_cubes

@@ -352,7 +352,7 @@ class _InferencePlan:
             for hs in self.head_streams:
                 tail.wait_stream(hs)
             b_, s_, l_, p_ = self.out_views
-            self.out = ops.detect_objects_padded(locs, scores, model._priors_on(dev), ms, mo, k,
+            self.out = ops.detect_objects_padded(locs, scores, model._prior_source(dev), ms, mo, k,
                                                  out_count=self.meta[:self.n], status=self.meta[self.n:self.n + 1],
                                                  out=(b_, s_, l_, p_))
             self.meta[self.n + 1:].copy_(flag)
@@ -508,6 +508,8 @@ class LSSD3D(_LightningBase):
         nn.init.constant_(self.rescale_factors, 20)
 
         self.priors_cxcycz = self.create_prior_boxes()
+        self.__dict__["_priors_origin"] = self.priors_cxcycz
+        self.__dict__["_priors_version"] = self.priors_cxcycz._version
         self.loss_fn = MultiBoxLoss(self.priors_cxcycz, threshold=threshold, alpha=alpha)
         self.defer_nan_check = False
         self.use_cuda_graph = True     # predict_step replays a captured forward+detect graph
@@ -551,12 +553,7 @@ class LSSD3D(_LightningBase):
             cx = (np.arange(d1, dtype=np.float64) + 0.5) / d1
             cz = (np.arange(d2, dtype=np.float64) + 0.5) / d2
             CY, CX, CZ = np.meshgrid(cy, cx, cz, indexing="ij")
-            sizes = []
-            for ratio in self.aspect_ratios[fmap]:
-                sizes.append(s)
-                if ratio == 1.:
-                    for div in list(range(1, self.boxes_per_location)):
-                        sizes.append(s + s / div)
+            sizes = self._prior_sizes(fmap)
             per = np.empty((d0, d1, d2, len(sizes), 6), dtype=np.float64)
             per[..., 0] = CX[..., None]
             per[..., 1] = CY[..., None]
@@ -570,12 +567,49 @@ class LSSD3D(_LightningBase):
         prior_boxes.clamp_(0, 1)
         return prior_boxes
 
+    def _prior_sizes(self, fmap):
+        """Box edges at one location of prediction layer ``fmap`` as Python floats (ssd3d.py:311-330)."""
+        s = float(self.scales[fmap])
+        sizes = []
+        for ratio in self.aspect_ratios[fmap]:
+            sizes.append(s)
+            if ratio == 1.:
+                for div in list(range(1, self.boxes_per_location)):
+                    sizes.append(s + s / div)
+        return sizes
+
     # ------------------------------------------------------------------------------------------
     def _priors_on(self, dev) -> torch.Tensor:
         if self.priors_cxcycz.device != dev:
+            mine = (self.priors_cxcycz is self.__dict__.get("_priors_origin")
+                    and self.priors_cxcycz._version == self.__dict__.get("_priors_version"))
             self.priors_cxcycz = self.priors_cxcycz.to(dev)
+            if mine:
+                self.__dict__["_priors_origin"] = self.priors_cxcycz
+                self.__dict__["_priors_version"] = self.priors_cxcycz._version
             self.loss_fn.set_priors(self.priors_cxcycz)
         return self.priors_cxcycz
+
+    def _prior_source(self, dev):
+        """What the decode / matching kernels take their priors from: the closed-form table (SURVEY.md 8f rank 3:
+        every prior is recomputed from its index in float64 -> fp32, bit-identical to ``create_prior_boxes`` -- no
+        24-byte read per prior) while ``priors_cxcycz`` is still the constructor's tensor; the tensor itself once a
+        caller has replaced or edited it (it is a public attribute of the reference's class)."""
+        pri = self._priors_on(dev)
+        if (os.environ.get("SSD3D_ANALYTIC_PRIORS", "1") == "0" or pri is not self.__dict__.get("_priors_origin")
+                or pri._version != self.__dict__.get("_priors_version")):
+            return pri
+        tbl = self.__dict__.get("_prior_table")
+        if tbl is None or tbl.dev.device != dev:
+            fmd = self.base.get_feature_map_infos(self.input_size)[0]
+            keys = list(self.aspect_ratios.keys())
+            if len(keys) > _lib.MAX_PRIOR_LAYERS or any(len(self._prior_sizes(k)) > _lib.MAX_PRIOR_SIZES for k in keys):
+                return pri
+            tbl = ops.PriorTable([fmd[k] for k in keys], [self._prior_sizes(k) for k in keys], dev)
+            if tbl.count != pri.shape[0]:
+                return pri
+            self.__dict__["_prior_table"] = tbl
+        return tbl
 
     def _raise_on_nan(self, flag: torch.Tensor):
         bits = int(flag.item())
@@ -620,8 +654,8 @@ class LSSD3D(_LightningBase):
 
     def detect_objects(self, predicted_locs, predicted_scores, min_score, max_overlap, top_k, return_prior=False):
         """Decode + per-class NMS + top-k (ssd3d.py:344-460) -> lists of per-image boxes, labels, scores."""
-        priors = self._priors_on(predicted_locs.device)
-        if ops.detect_needs_long_lists(priors.shape[0], top_k):
+        priors = self._prior_source(predicted_locs.device)
+        if ops.detect_needs_long_lists(self.priors_cxcycz.shape[0], top_k):
             # NMS-stress settings (model_insight.py:146: min_score=0, top_k=50000): lists of any length
             return ops.detect_objects_long(predicted_locs, predicted_scores, priors, min_score, max_overlap, top_k,
                                            return_prior=return_prior)
@@ -732,8 +766,8 @@ class LSSD3D(_LightningBase):
             predicted_locs, predicted_scores = self(image)
         finally:
             self.defer_nan_check = prev
-        priors = self._priors_on(predicted_locs.device)
-        if ops.detect_needs_long_lists(priors.shape[0], self.top_k):
+        priors = self._prior_source(predicted_locs.device)
+        if ops.detect_needs_long_lists(self.priors_cxcycz.shape[0], self.top_k):
             flag = self.base.nan_flag(predicted_locs.device)
             if int(flag.cpu()[0]):
                 self._raise_on_nan(flag)

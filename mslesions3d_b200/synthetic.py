@@ -8,7 +8,10 @@ normalisation the data module applies (datasets.py:403).  Ground-truth boxes use
 the reference's convention ``[min_idx, max_idx] / dims`` in array-axis order with
 an inclusive max index (utils.py:472,500).
 
-Host-side numpy only: this is data preparation, outside the accelerated path.
+``make_batch`` & co. are host-side numpy and reproduce the reference's MT19937 stream (the golden vectors and the
+benchmark inputs come from them).  ``make_batch_device`` is the same construction generated where it is consumed
+(SURVEY.md 8f rank 2): Philox4x32-10 keyed by (seed, volume, channel, voxel) -- the numpy stream is NOT reproduced
+there, only the distribution -- followed by the device-side NormalizeIntensity and ground-truth box extraction.
 """
 from __future__ import annotations
 
@@ -114,6 +117,28 @@ def make_batch(batch_size: int, channels: int = 1, image_size: Sequence[int] = (
     if with_boxes:
         return vols, boxes, labels
     return vols
+
+
+def make_batch_device(batch_size: int, channels: int = 1, image_size: Sequence[int] = (64, 64, 64), first_idx: int = 0,
+                      random_seed: int = 0, num_objects=(1, 5), object_size=None, with_boxes: bool = False,
+                      device=None, dtype=None):
+    """``make_batch`` without the host: volumes are generated (``ssd3d_generate_volumes``), normalised
+    (``ssd3d_normalize_intensity_nonzero``, datasets.py:403) and -- with ``with_boxes`` -- turned into ground-truth
+    boxes (``ssd3d_gt_boxes_from_segmentation``, utils.py:438-513: connected components of the mask, so touching
+    cubes merge exactly as in the reference's data module) on the device.  Returns CUDA tensors: volumes
+    (N, C, D, H, W) in ``dtype`` (bf16 by default, the stem's input format) [+ boxes / labels lists].
+    A different random stream than ``make_batch`` (see the module docstring)."""
+    import torch
+    from . import ops
+    if object_size is None:
+        object_size = default_object_size(image_size)
+    raw, mask, _, _ = ops.generate_volumes(batch_size, channels, image_size, first_idx, random_seed, num_objects,
+                                           object_size, device)
+    vols = ops.normalize_intensity_nonzero(raw, torch.bfloat16 if dtype is None else dtype)
+    if not with_boxes:
+        return vols
+    boxes, labels = ops.gt_boxes_from_segmentation(mask)
+    return vols, boxes, labels
 
 
 def write_dataset(output_dir: str, num_images: int, image_size: Sequence[int] = (64, 64, 64), num_objects=(1, 5),

@@ -526,7 +526,7 @@ class _TrainPlan:
         t0, t1 = (lf.threshold, lf.threshold) if lf.thresholding_mode == "hard" else lf.threshold
         locs, scores = eng.forward(self.image, eng.packed)
         m = ops.match_priors_packed(self.gt_boxes, self.gt_labels, self.offsets, self.n, self.tmax,
-                                    model._priors_on(model.device), t0, t1)
+                                    model._prior_source(model.device), t0, t1)
         out, n_pos, g_locs, g_scores = ops.multibox_loss(locs, scores, m["true_classes"], m["true_locs"],
                                                          alpha=float(lf.alpha),
                                                          hard_negative_mining=lf.hard_negative_mining,

@@ -234,12 +234,12 @@ def test_head_backward(c, n, size, ncls):
     ops.head_wgrad(dO, to_cl(x.detach()), bpl * 6, bpl * ncls, dwl, dwc)
     assert rel_l2(dwl, lw.grad) < 2e-3 and rel_l2(dwc, cw.grad) < 2e-3, (rel_l2(dwl, lw.grad), rel_l2(dwc, cw.grad))
     wpk, _ = ops.pack_head_weight(lw.detach().cuda(), lb.detach().cuda(), cw.detach().cuda(), cb.detach().cuda())
-    # one pass per 16-column group, each rounding the running sum to bf16
+    # all 16-column groups accumulate in fp32 inside one launch: one rounding, whatever n_classes
     dx = ops.head_dgrad(dO, wpk, to_cl(x.detach()), n_cols=bpl * (6 + ncls))
-    assert_bf16_close(dx, bf16r(x.grad), "head dgrad", ulps=1.0 + 0.5 * (groups - 1))
+    assert_bf16_close(dx, bf16r(x.grad), "head dgrad")
     add = bf16r(torch.randn(x.shape, generator=g))
     dx2 = ops.head_dgrad(dO, wpk, to_cl(x.detach()), addend=to_cl(add), n_cols=bpl * (6 + ncls))
-    assert_bf16_close(dx2, bf16r(x.grad + add), "head dgrad + addend", ulps=1.5 + 0.5 * (groups - 1))
+    assert_bf16_close(dx2, bf16r(x.grad + add), "head dgrad + addend", ulps=1.5)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -361,7 +361,12 @@ def test_training_step_gradients(channels, size, batch):
         num += float((got.cpu() - want).norm()) ** 2
         den += float(want.norm()) ** 2
         print("%-40s rel L2 %.4f cos %.5f" % (k, r, cos))
-        assert r <= 0.45 and cos >= 0.90, "%s: rel L2 %.4f cos %.5f" % (k, r, cos)
+        # Two bf16 pipelines (this one and the emulating oracle) differ where a rounded pre-activation lands on the
+        # other side of a ReLU or an L1 residual changes sign; measured on B200 (profiles/r02_train_parity.txt):
+        # backbone tensors <= 0.25, the loc head of a layer with a handful of positives <= 0.38, class heads
+        # <= 0.006.  The exact per-stage check (<= 2e-3 everywhere) is tests/test_gpu_train_insitu.py.
+        limit = 0.45 if k.startswith("pred_convs.loc_convs") else 0.35
+        assert r <= limit and cos >= 0.92, "%s: rel L2 %.4f cos %.5f" % (k, r, cos)
         if k.startswith("pred_convs.cl_convs") or k.endswith(("3.bn2.weight", "5.bn2.weight", "7.bn2.weight")):
             # before any amplification: class-head gradients and the BN right under a head
             assert r <= 0.02, "%s: rel L2 %.4f" % (k, r)
@@ -369,7 +374,7 @@ def test_training_step_gradients(channels, size, batch):
         cos32 = float((got.cpu().flatten() * w32.flatten()).sum() / (got.norm().cpu() * w32.norm()))
         assert cos32 >= 0.85, "%s: cosine vs fp32 oracle %.4f" % (k, cos32)
     print("worst rel L2 vs emulating oracle: %.4f (%s); whole gradient: %.4f" % (worst + ((num / den) ** 0.5,)))
-    assert (num / den) ** 0.5 <= 0.12
+    assert (num / den) ** 0.5 <= 0.02          # measured 0.0014 / 0.0022
 
 
 def test_training_step_is_reproducible_and_eval_still_works():

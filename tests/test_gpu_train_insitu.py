@@ -123,6 +123,7 @@ def test_training_step_stagewise_in_situ(n_classes, channels, size, batch):
     # ---- heads: weight / bias / data gradients from the loss gradient rows the kernels really used ----
     pc = model.pred_convs
     dlocs, dscores = rec["dlocs"].cpu(), rec["dscores"].cpu()
+    loc_norms = []
     for h in tape["heads"]:
         j, layer, bpl = h["j"], h["layer"], h["bpl"]
         hr = rec["heads"][layer]
@@ -144,11 +145,14 @@ def test_training_step_stagewise_in_situ(n_classes, channels, size, batch):
         g_c = rows[:, nl:nl + nc].reshape(n, d, hh, w, nc).permute(0, 4, 1, 2, 3)
         torch.autograd.backward([ol, oc], [g_l, g_c])
         r_l, r_c = rel_l2(pc.loc_convs[j].weight.grad, lw.grad), rel_l2(pc.cl_convs[j].weight.grad, cw.grad)
+        assert float(cw.grad.norm()) > 0
+        loc_norms.append(float(lw.grad.norm()))         # a layer without a positive prior has no loc gradient
         assert r_l <= 2e-3 and r_c <= 2e-3, "head %d dW: loc %.2e class %.2e" % (j, r_l, r_c)
         torch.testing.assert_close(pc.loc_convs[j].bias.grad.cpu(), want_rows[:, :nl].sum(0), rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(pc.cl_convs[j].bias.grad.cpu(), want_rows[:, nl:].sum(0), rtol=1e-4, atol=1e-5)
         want_dx = xl.grad + (hr["addend"].float().cpu() if hr["addend"] is not None else 0.0)
-        bad = bf16_mismatch(hr["out"], bf16r(want_dx), 1.5 + 0.5 * (groups - 1))
+        bad = bf16_mismatch(hr["out"], bf16r(want_dx), 1.5)
         assert bad == 0.0, "head %d data gradient: %.2e of elements off" % (j, bad)
         report.append("head %d (layer %d, %d cols)     dW loc %.1e class %.1e" % (j, layer, nl + nc, r_l, r_c))
+    assert max(loc_norms) > 0, "no localisation gradient reached any head"
     print("\n".join(report))
