@@ -338,8 +338,6 @@ def train_leg(dev, rank, world, steps, warmup, barrier, max_over_ranks):
         barrier()
         out["allreduce_ms"] = max_over_ranks(e0.elapsed_time(e1), dev) / 20.0
         out["allreduce_bytes"] = int(g.numel() * 4)
-        ms1, _, _ = region(steps * reps, world_size=1)
-        out["ms_per_step_without_allreduce"] = ms1 / (steps * reps)
     else:
         out["allreduce_ms"] = 0.0
     del model, batches
@@ -619,7 +617,14 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The training step's CUDA graph holds captured NCCL work; tearing the communicator down under it
+        # (destroy_process_group) was seen to block forever after the line had been printed.  Everything that had
+        # to be measured and reported is done: leave together, without the teardown.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -81,6 +81,19 @@ int ssd3d_stem_conv_bn_relu_simt(const void* x, int x_is_bf16, const void* w, co
                                  void* stream);
 int ssd3d_stem_tc_supported(int x_is_bf16, int Cin, int W);
 
+/* One whole Block (mobilenet.py:34-49, eval mode) in ONE kernel: depthwise 3x3x3 + BN1 + ReLU -> pointwise 1x1x1 on
+ * tcgen05 + BN2 + ReLU.  The depthwise tile (128 voxels x Cin, bf16, rounded exactly as the stand-alone kernel
+ * stores it) stays in shared memory as the A operand of the pointwise GEMM, so the intermediate activation never
+ * touches HBM.  Same arguments as ssd3d_dwconv3d_bn_relu followed by ssd3d_pwconv_bn_relu:
+ *   x (N, D, H, W, Cin) bf16; w1 (27, Cin) bf16; w2 (Cout, Cin) bf16; scale / shift fp32; y (N, Do, Ho, Wo, Cout).
+ * Built for the three large blocks of the backbone -- (Cin, Cout, stride) = (32, 64, 2), (64, 128, 2), (128, 128, 1)
+ * on maps with Wo >= 8, Ho >= 4, Do >= 4 (ssd3d_block_fused_supported); other shapes return
+ * SSD3D_ERR_UNSUPPORTED and the caller runs the two stand-alone kernels. */
+int ssd3d_block_fused_supported(int Cin, int Cout, int D, int H, int W, int stride);
+int ssd3d_block_dwpw_bn_relu(const void* x, const void* w1, const float* scale1, const float* shift1, const void* w2,
+                             const float* scale2, const float* shift2, void* y, int N, int Cin, int Cout, int D, int H,
+                             int W, int stride, int* nan_flag, void* stream);
+
 /* Depthwise Conv3d(C, C, k3, pad 1, stride s in {1,2}, groups=C, no bias) + BN + ReLU.
  * Replaces mobilenet.py:38,44 (Block.conv1/bn1).
  *   x (N, D, H, W, C) bf16;  w (27, C) bf16, row = tap;  scale, shift (C) fp32;  C % 8 == 0

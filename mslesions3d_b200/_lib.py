@@ -41,6 +41,8 @@ SIGNATURES = {
     "ssd3d_stem_conv_bn_relu_simt": (c_int, [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "ssd3d_stem_tc_supported": (c_int, [c_int, c_int, c_int]),
     "ssd3d_dwconv3d_bn_relu": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "ssd3d_block_fused_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "ssd3d_block_dwpw_bn_relu": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
     "ssd3d_pwconv_bn_relu": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, P, P]),
     "ssd3d_head_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "ssd3d_head_conv": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,

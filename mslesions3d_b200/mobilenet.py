@@ -15,6 +15,8 @@ stand-alone there too, mobilenet.py:34-49) each module is one autograd node over
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -33,6 +35,11 @@ config_mobilenet = [32,
 MOBILENET_CONFIGS = {
     "mobilenet": config_mobilenet
 }
+
+
+# fused depthwise -> pointwise Block kernel (csrc/conv_dwpw.cu) for the shapes it is built for; SSD3D_FUSE_DWPW=0
+# (or FUSE_DWPW[0] = False) runs the two stand-alone kernels everywhere
+FUSE_DWPW = [os.environ.get("SSD3D_FUSE_DWPW", "1") != "0"]
 
 
 def _versions(*tensors):
@@ -119,8 +126,12 @@ class Block(nn.Module):
         wd, s1, b1, wp, s2, b2 = self._pack()
         own_flag = self.nan_flag is None
         flag = torch.zeros((1,), dtype=torch.int32, device=x.device) if own_flag else self.nan_flag
-        out = ops.dwconv3d_bn_relu(x, wd, s1, b1, s[0])
-        out = ops.pwconv_bn_relu(out, wp, s2, b2, flag)
+        if FUSE_DWPW[0] and x.is_cuda and x.dim() == 5 and ops.block_fused_supported(x, wp.shape[0], s[0]):
+            # the three large blocks: depthwise tile -> shared memory -> tcgen05 pointwise GEMM, one kernel
+            out = ops.block_dwpw_bn_relu(x, wd, s1, b1, wp, s2, b2, s[0], flag)
+        else:
+            out = ops.dwconv3d_bn_relu(x, wd, s1, b1, s[0])
+            out = ops.pwconv_bn_relu(out, wp, s2, b2, flag)
         if own_flag and int(flag.item()) != 0:   # stand-alone use keeps the reference's check (mobilenet.py:46-48)
             raise Exception("NaN Loss in MobileNet Block")
         return out

@@ -118,6 +118,29 @@ def pwconv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor,
     return y
 
 
+def block_fused_supported(x: torch.Tensor, cout: int, stride: int) -> bool:
+    n, c, d, h, w = x.shape
+    return bool(_lib.load().ssd3d_block_fused_supported(c, cout, d, h, w, stride))
+
+
+def block_dwpw_bn_relu(x: torch.Tensor, w_dw: torch.Tensor, scale1: torch.Tensor, shift1: torch.Tensor,
+                       w_pw: torch.Tensor, scale2: torch.Tensor, shift2: torch.Tensor, stride: int,
+                       nan_flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A whole Block (depthwise + BN + ReLU -> pointwise + BN + ReLU, mobilenet.py:34-49) in one kernel: the
+    depthwise tile stays in shared memory as the tcgen05 A operand.  Check ``block_fused_supported`` first."""
+    _need_cuda(x, w_dw, scale1, shift1, w_pw, scale2, shift2, nan_flag)
+    x = to_channels_last_bf16(x)
+    n, c, d, h, w = x.shape
+    cout = w_pw.shape[0]
+    y = _alloc_ndhwc(n, cout, conv_out(d, stride), conv_out(h, stride), conv_out(w, stride), x.device)
+    rc = _lib.load().ssd3d_block_dwpw_bn_relu(x.data_ptr(), w_dw.data_ptr(), scale1.data_ptr(), shift1.data_ptr(),
+                                              w_pw.data_ptr(), scale2.data_ptr(), shift2.data_ptr(), y.data_ptr(), n, c,
+                                              cout, d, h, w, stride, _ptr(nan_flag), _stream())
+    _lib.check(rc, "ssd3d_block_dwpw_bn_relu")
+    LAUNCHES[0] += 1
+    return y
+
+
 def head_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tensor, locs: torch.Tensor, scores: torch.Tensor,
               bpl: int, n_classes: int, prior_offset: int, nan_flag: Optional[torch.Tensor] = None,
               algo: int = 0) -> None:
