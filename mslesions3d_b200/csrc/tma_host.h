@@ -27,8 +27,11 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 // bf16 tensor of `rank` dims; dims[0] is the innermost (contiguous) dimension.  strides_bytes[i] is
 // the byte stride of dims[i+1] (rank-1 entries).  Out-of-bounds box elements read as zero.
+// elem_strides (optional): traversal stride per dimension; along a dimension with stride s the box spans box[i]
+// tensor elements and ceil(box[i] / s) of them are loaded.
 inline int make_tma_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                         const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+                         const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle,
+                         const uint32_t* elem_strides = nullptr) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return 1;
   cuuint64_t gdim[5];
@@ -38,7 +41,7 @@ inline int make_tma_bf16(CUtensorMap* map, const void* base, int rank, const uin
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,

@@ -37,9 +37,18 @@ MOBILENET_CONFIGS = {
 }
 
 
-# fused depthwise -> pointwise Block kernel (csrc/conv_dwpw.cu) for the shapes it is built for; SSD3D_FUSE_DWPW=0
-# (or FUSE_DWPW[0] = False) runs the two stand-alone kernels everywhere
-FUSE_DWPW = [os.environ.get("SSD3D_FUSE_DWPW", "1") != "0"]
+# fused depthwise -> pointwise Block kernel (csrc/conv_dwpw.cu) for the shapes it is built for.  SSD3D_FUSE_DWPW is a
+# bit mask over the depthwise channel count of the block (1: 32 ch = f1, 2: 64 ch = f2, 4: 128 ch = f3); 0 runs
+# the two stand-alone kernels everywhere.  Measured on B200 at the benchmark size (profiles/r02_block_fused.md):
+# alone, every fused block beats its two kernels (f1 41 vs 49, f2 16.5 vs 20.6, f3 18.8 vs 22.8 us) and f1 keeps
+# 33.6 MB per step out of HBM; in the 6-deep inference pipeline only f1 is throughput-neutral -- the fused CTAs
+# own their SM (200 KB of shared memory), while the stand-alone pointwise GEMMs of f2 / f3 run underneath other
+# batches' kernels -- so f1 is the default
+FUSE_DWPW = [int(os.environ.get("SSD3D_FUSE_DWPW", "1"))]
+
+
+def _fuse_bit(cin: int) -> int:
+    return {32: 1, 64: 2, 128: 4}.get(int(cin), 0)
 
 
 def _versions(*tensors):
@@ -126,7 +135,8 @@ class Block(nn.Module):
         wd, s1, b1, wp, s2, b2 = self._pack()
         own_flag = self.nan_flag is None
         flag = torch.zeros((1,), dtype=torch.int32, device=x.device) if own_flag else self.nan_flag
-        if FUSE_DWPW[0] and x.is_cuda and x.dim() == 5 and ops.block_fused_supported(x, wp.shape[0], s[0]):
+        if (int(FUSE_DWPW[0]) & _fuse_bit(x.shape[1])) and x.is_cuda and x.dim() == 5 and \
+                ops.block_fused_supported(x, wp.shape[0], s[0]):
             # the three large blocks: depthwise tile -> shared memory -> tcgen05 pointwise GEMM, one kernel
             out = ops.block_dwpw_bn_relu(x, wd, s1, b1, wp, s2, b2, s[0], flag)
         else:

@@ -86,16 +86,17 @@ def test_block_module_uses_the_fused_kernel_and_matches_unfused():
     model = model.cuda().eval()
     x = torch.from_numpy(synthetic.make_batch(2, 2, size)).cuda()
     from mslesions3d_b200 import ops
+    mobilenet.FUSE_DWPW[0] = 7
     with torch.no_grad():
         before = ops.LAUNCHES[0]
         l1, s1 = model(x)
         fused_launches = ops.LAUNCHES[0] - before
-        mobilenet.FUSE_DWPW[0] = False
+        saved, mobilenet.FUSE_DWPW[0] = mobilenet.FUSE_DWPW[0], 0
         try:
             before = ops.LAUNCHES[0]
             l0, s0 = model(x)
             plain_launches = ops.LAUNCHES[0] - before
         finally:
-            mobilenet.FUSE_DWPW[0] = True
+            mobilenet.FUSE_DWPW[0] = saved
     assert fused_launches < plain_launches            # 64^3: blocks f1 (32^3 -> 16^3) and f2/f3 (8^3) qualify
     assert torch.equal(l0, l1) and torch.equal(s0, s1)
