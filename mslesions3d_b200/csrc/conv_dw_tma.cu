@@ -190,6 +190,163 @@ __global__ void __launch_bounds__(256, 1) dw_tma_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stride 2, de-interleaved halo.  With stride 2 every input position one instruction touches has the same parity
+// along each axis for all outputs, so with 64-byte voxels the four 8-lane groups of a warp hit the same 16 of the
+// 32 banks: ncu showed 4 shared-memory wavefronts per 8-byte load instead of 2, and the kernel is bound by exactly
+// that pipe.  Here the halo arrives as TWO boxes with a TMA traversal stride of 2 along W (E = halo columns
+// 0, 2, .., 16; O = columns 1, 3, .., 17), the lane groups of a warp take four CONSECUTIVE output columns (so
+// consecutive E / O entries: alternating bank halves) and a thread owns 4 channels x 2 outputs along H: 5 input
+// rows x {E[w], O[w], E[w+1]} per kd = 45 loads per 2 outputs as before, every one conflict free.  Each output
+// still accumulates its 27 taps in (kd, kh, kw) order: bit-identical to the direct kernel.
+// ------------------------------------------------------------------------------------------------
+struct DwS2 {
+  static constexpr int TD = 4, TH = 4, TW = 8;
+  static constexpr int TDI = 9, THI = 9, TWI = 9;                   // per parity box
+  static constexpr int BOX_BYTES = TDI * THI * TWI * DW_CB * 2;     // 46656
+  static constexpr int BOX_PITCH = (BOX_BYTES + 127) & ~127;
+  static constexpr int PITCH = 2 * BOX_PITCH;
+  static constexpr int ITEMS = TD * (TH / 2) * TW * 8;              // 512
+  static constexpr size_t SMEM = 128 + 2 * (size_t)PITCH + 16;
+};
+
+__global__ void __launch_bounds__(256, 1) dw_tma_s2_kernel(const __grid_constant__ CUtensorMap tm, const DwTmaParams p) {
+  using T = DwS2;
+  extern __shared__ uint8_t dw_raw[];
+  const uint32_t raw = smem_u32(dw_raw);
+  uint8_t* smem = dw_raw + ((128u - (raw & 127u)) & 127u);
+  uint8_t* tiles = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * T::PITCH);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
+  const int chunk = blockIdx.x % p.chunks;
+  const int cbase = chunk * DW_CB;
+  const int first = blockIdx.x / p.chunks;
+  const int step = gridDim.x / p.chunks;
+  auto decode = [&](int tile, int& ow0, int& oh0, int& od0, int& n) {
+    int t = tile;
+    ow0 = (t % p.tiles_w) * T::TW; t /= p.tiles_w;
+    oh0 = (t % p.tiles_h) * T::TH; t /= p.tiles_h;
+    od0 = (t % p.tiles_d) * T::TD;
+    n = t / p.tiles_d;
+  };
+  auto issue = [&](int tile, int buf) {
+    int ow0, oh0, od0, n;
+    decode(tile, ow0, oh0, od0, n);
+    uint8_t* dst = tiles + (size_t)buf * T::PITCH;
+    mbar_arrive_expect_tx(&full[buf], (uint32_t)(2 * T::BOX_BYTES));
+    tma_load_5d(dst, &tm, &full[buf], cbase, ow0 * 2 - 1, oh0 * 2 - 1, od0 * 2 - 1, n);
+    tma_load_5d(dst + T::BOX_PITCH, &tm, &full[buf], cbase, ow0 * 2, oh0 * 2 - 1, od0 * 2 - 1, n);
+  };
+  if (tid == 0 && first < p.spatial_tiles) issue(first, 0);
+
+  const int cv = tid & 7;
+  const int c0 = cbase + cv * 4;
+  f32x2 wreg[27][2];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.w + (size_t)t * p.C + c0));
+    wreg[t][0] = bf16x2_to_f32x2(u.x);
+    wreg[t][1] = bf16x2_to_f32x2(u.y);
+  }
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+
+  int it = 0;
+  for (int tile = first; tile < p.spatial_tiles; tile += step, ++it) {
+    const int buf = it & 1;
+    const int next = tile + step;
+    if (tid == 0 && next < p.spatial_tiles) issue(next, buf ^ 1);   // released by the trailing barrier of it-1
+    int ow0, oh0, od0, n;
+    decode(tile, ow0, oh0, od0, n);
+    mbar_wait(&full[buf], (uint32_t)((it >> 1) & 1));
+    const uint8_t* in = tiles + (size_t)buf * T::PITCH;
+#pragma unroll 1
+    for (int item = tid; item < T::ITEMS; item += 256) {
+      const int w = (item >> 3) & 7, hp = (item >> 6) & 1, d = item >> 7;
+      const int od = od0 + d, oh = oh0 + 2 * hp, wo = ow0 + w;
+      if (od >= p.Do || oh >= p.Ho || wo >= p.Wo) continue;
+      f32x2 acc0[2] = {0ull, 0ull}, acc1[2] = {0ull, 0ull};
+      const uint8_t* base = in + ((size_t)(((2 * d) * T::THI + 4 * hp) * T::TWI + w) * DW_CB + cv * 4) * 2;
+#pragma unroll
+      for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          const uint8_t* row = base + (size_t)((kd * T::THI + r) * T::TWI) * DW_CB * 2;
+          const uint2 u0 = *reinterpret_cast<const uint2*>(row);                    // E[w]   : kw = 0
+          const uint2 u1 = *reinterpret_cast<const uint2*>(row + T::BOX_PITCH);     // O[w]   : kw = 1
+          const uint2 u2 = *reinterpret_cast<const uint2*>(row + DW_CB * 2);        // E[w+1] : kw = 2
+          const f32x2 x0[2] = {bf16x2_to_f32x2(u0.x), bf16x2_to_f32x2(u0.y)};
+          const f32x2 x1[2] = {bf16x2_to_f32x2(u1.x), bf16x2_to_f32x2(u1.y)};
+          const f32x2 x2[2] = {bf16x2_to_f32x2(u2.x), bf16x2_to_f32x2(u2.y)};
+          if (r <= 2) {          // output row 2hp: kh = r
+            const int t = (kd * 3 + r) * 3;
+            ffma2(acc0[0], x0[0], wreg[t][0]);     ffma2(acc0[1], x0[1], wreg[t][1]);
+            ffma2(acc0[0], x1[0], wreg[t + 1][0]); ffma2(acc0[1], x1[1], wreg[t + 1][1]);
+            ffma2(acc0[0], x2[0], wreg[t + 2][0]); ffma2(acc0[1], x2[1], wreg[t + 2][1]);
+          }
+          if (r >= 2) {          // output row 2hp + 1: kh = r - 2
+            const int t = (kd * 3 + (r - 2)) * 3;
+            ffma2(acc1[0], x0[0], wreg[t][0]);     ffma2(acc1[1], x0[1], wreg[t][1]);
+            ffma2(acc1[0], x1[0], wreg[t + 1][0]); ffma2(acc1[1], x1[1], wreg[t + 1][1]);
+            ffma2(acc1[0], x2[0], wreg[t + 2][0]); ffma2(acc1[1], x2[1], wreg[t + 2][1]);
+          }
+        }
+      }
+      __nv_bfloat16* o = p.y + ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + wo) * p.C + c0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (e == 1 && oh + 1 >= p.Ho) break;
+        float a0, a1, a2, a3;
+        unpack_f32x2(e ? acc1[0] : acc0[0], a0, a1);
+        unpack_f32x2(e ? acc1[1] : acc0[1], a2, a3);
+        a0 = clamp_floor(__fadd_rn(__fmul_rn(a0, sc.x), sh.x), p.floor);
+        a1 = clamp_floor(__fadd_rn(__fmul_rn(a1, sc.y), sh.y), p.floor);
+        a2 = clamp_floor(__fadd_rn(__fmul_rn(a2, sc.z), sh.z), p.floor);
+        a3 = clamp_floor(__fadd_rn(__fmul_rn(a3, sc.w), sh.w), p.floor);
+        *reinterpret_cast<uint2*>(o + (long long)e * p.Wo * p.C) = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
+      }
+    }
+    __syncthreads();   // tile[buf] is free again
+  }
+}
+
+static int launch_dw_tma_s2(const void* x, DwTmaParams& p, cudaStream_t st) {
+  using T = DwS2;
+  p.tiles_w = (p.Wo + T::TW - 1) / T::TW;
+  p.tiles_h = (p.Ho + T::TH - 1) / T::TH;
+  p.tiles_d = (p.Do + T::TD - 1) / T::TD;
+  p.chunks = p.C / DW_CB;
+  const long long spatial = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
+  if (spatial * p.chunks > 0x3fffffffll) return SSD3D_ERR_UNSUPPORTED;
+  p.spatial_tiles = (int)spatial;
+  CUtensorMap tm;
+  const uint64_t dims[5] = {(uint64_t)p.C, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.N};
+  const uint64_t strides[4] = {(uint64_t)p.C * 2, (uint64_t)p.W * p.C * 2, (uint64_t)p.H * p.W * p.C * 2,
+                               (uint64_t)p.D * p.H * p.W * p.C * 2};
+  // the box spans 17 columns of which every second one is loaded (9 per parity box)
+  const uint32_t box[5] = {(uint32_t)DW_CB, 17u, (uint32_t)T::THI, (uint32_t)T::TDI, 1u};
+  const uint32_t estr[5] = {1u, 2u, 1u, 1u, 1u};
+  if (make_tma_bf16(&tm, x, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, estr)) return SSD3D_ERR_TMA;
+  cudaError_t e = cudaFuncSetAttribute(dw_tma_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  const int n_sm = persistent_sms();
+  long long grid = n_sm;
+  if (grid > spatial * p.chunks) grid = spatial * p.chunks;
+  grid = grid / p.chunks * p.chunks;
+  if (grid < p.chunks) grid = p.chunks;
+  SSD3D_LAUNCH_PDL(dw_tma_s2_kernel, dim3((unsigned)grid), dim3(256), T::SMEM, st, tm, p);
+  return SSD3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Depthwise WEIGHT gradient with the same tiling: dw[c][tap] = sum_o dz[o][c] * x[S*o + tap - 1][c].
 // Roles swapped w.r.t. the forward kernel: the 27 x 4 accumulators live in registers for the whole kernel, the
 // 4-channel dz vector of each output is the multiplier.  At the end the threads of a CTA that own the same
@@ -409,7 +566,8 @@ int ssd3d_dwconv3d_tma(const void* x, const void* w, const float* scale, const f
   p.N = N; p.C = C; p.D = D; p.H = H; p.W = W; p.Do = Do; p.Ho = Ho; p.Wo = Wo;
   p.w = static_cast<const __nv_bfloat16*>(w);
   p.scale = scale; p.shift = shift; p.y = static_cast<__nv_bfloat16*>(y); p.floor = floor;
-  if (stride == 2) return launch_dw_tma<2, 2, 4, 4, 8>(x, p, st);
+  static const bool deint = [] { const char* e = getenv("SSD3D_DW_S2_DEINTERLEAVE"); return !(e && e[0] == '0'); }();
+  if (stride == 2) return deint ? launch_dw_tma_s2(x, p, st) : launch_dw_tma<2, 2, 4, 4, 8>(x, p, st);
   return launch_dw_tma<1, 4, 4, 8, 8>(x, p, st);
 }
 

@@ -37,14 +37,15 @@ MOBILENET_CONFIGS = {
 }
 
 
-# fused depthwise -> pointwise Block kernel (csrc/conv_dwpw.cu) for the shapes it is built for.  SSD3D_FUSE_DWPW is a
-# bit mask over the depthwise channel count of the block (1: 32 ch = f1, 2: 64 ch = f2, 4: 128 ch = f3); 0 runs
-# the two stand-alone kernels everywhere.  Measured on B200 at the benchmark size (profiles/r02_block_fused.md):
-# alone, every fused block beats its two kernels (f1 41 vs 49, f2 16.5 vs 20.6, f3 18.8 vs 22.8 us) and f1 keeps
-# 33.6 MB per step out of HBM; in the 6-deep inference pipeline only f1 is throughput-neutral -- the fused CTAs
-# own their SM (200 KB of shared memory), while the stand-alone pointwise GEMMs of f2 / f3 run underneath other
-# batches' kernels -- so f1 is the default
-FUSE_DWPW = [int(os.environ.get("SSD3D_FUSE_DWPW", "1"))]
+# fused depthwise -> pointwise Block kernel (csrc/conv_dwpw.cu) for the shapes it is built for.  FUSE_DWPW is a bit
+# mask over the depthwise channel count of the block (1: 32 ch = f1, 2: 64 ch = f2, 4: 128 ch = f3); 0 runs the two
+# stand-alone kernels everywhere.  Measured on B200 at the benchmark size (profiles/r02_block_fused.md): alone,
+# every fused block beats its two kernels (f1 41 vs 47, f2 16.5 vs 20.6, f3 18.8 vs 22.8 us) and f1 keeps 33.6 MB
+# per step out of HBM -- so eager calls and the lone ``predict_step`` (latency) fuse all three -- but in the
+# 6-deep ``predict_batches`` pipeline (throughput) the fused CTAs own their SM (200 KB of shared memory) while the
+# stand-alone pointwise GEMMs they replace run underneath other batches' kernels: there the plans are captured
+# unfused (LSSD3D.fuse_blocks_pipeline).  SSD3D_FUSE_DWPW / SSD3D_FUSE_DWPW_PIPELINE override the two masks.
+FUSE_DWPW = [int(os.environ.get("SSD3D_FUSE_DWPW", "7"))]
 
 
 def _fuse_bit(cin: int) -> int:

@@ -252,8 +252,9 @@ class _InferencePlan:
     whose per-image counts, the detect status word and the NaN flag are packed in one int32 vector that is
     read back with a single device->host copy."""
 
-    def __init__(self, model: "LSSD3D", shape, dtype, min_score, max_overlap, top_k):
+    def __init__(self, model: "LSSD3D", shape, dtype, min_score, max_overlap, top_k, fuse_mask=None):
         dev = model.device
+        self.fuse_mask = fuse_mask          # which Blocks run as the fused depthwise->pointwise kernel (None: default)
         n = shape[0]
         self.key = None
         self.inp = torch.empty(shape, dtype=dtype, device=dev)
@@ -301,12 +302,17 @@ class _InferencePlan:
             self.stem(self.inp, out=self.stem_out)
 
     def _run(self, model: "LSSD3D"):
+        from . import mobilenet
         dev = self.inp.device
         model.base.nan_flag(dev)
         prev_flag = model.base.use_nan_flag(self.flag)
+        prev_mask = mobilenet.FUSE_DWPW[0]
+        if self.fuse_mask is not None:
+            mobilenet.FUSE_DWPW[0] = int(self.fuse_mask)
         try:
             self._run_with_flag(model, self.flag)
         finally:
+            mobilenet.FUSE_DWPW[0] = prev_mask
             model.base.use_nan_flag(prev_flag)
 
     def _run_with_flag(self, model: "LSSD3D", flag: torch.Tensor):
@@ -515,6 +521,8 @@ class LSSD3D(_LightningBase):
         self.use_cuda_graph = True     # predict_step replays a captured forward+detect graph
         self.pipeline_depth = int(os.environ.get("SSD3D_PIPELINE_DEPTH", "6"))   # batches in flight in predict_batches
         self.tail_from = int(os.environ.get("SSD3D_TAIL_FROM", "3"))   # first backbone layer on the high-priority stream
+        # fused Block kernels in the streaming pipeline (see mobilenet.FUSE_DWPW): off, measured slower there
+        self.fuse_blocks_pipeline = int(os.environ.get("SSD3D_FUSE_DWPW_PIPELINE", "0"))
         self._plans = {}
 
     # ------------------------------------------------------------------------------------------
@@ -696,18 +704,19 @@ class LSSD3D(_LightningBase):
             eng.packed.refresh()     # values were copied into the flat buffer in place
         return out
 
-    def _plan_for(self, image: torch.Tensor, slot: int = 0) -> _InferencePlan:
+    def _plan_for(self, image: torch.Tensor, slot: int = 0, fuse_mask=None) -> _InferencePlan:
         if self.training:
             raise RuntimeError("predict_step needs eval() mode (BatchNorm running statistics)")
         dtype = image.dtype if image.dtype in (torch.float32, torch.bfloat16) else torch.float32
         key = (tuple(image.shape), dtype, str(self.device), float(self.min_score), float(self.max_overlap),
-               int(self.top_k), slot)
+               int(self.top_k), slot, fuse_mask)
         ver = self._state_version()
         plan = self._plans.get(key)
         if plan is None or plan.key != ver:
-            if len(self._plans) > 16:
+            if len(self._plans) > 24:
                 self._plans.clear()
-            plan = _InferencePlan(self, tuple(image.shape), dtype, self.min_score, self.max_overlap, self.top_k)
+            plan = _InferencePlan(self, tuple(image.shape), dtype, self.min_score, self.max_overlap, self.top_k,
+                                  fuse_mask)
             plan.key = ver
             self._plans[key] = plan
         return plan
@@ -750,7 +759,7 @@ class LSSD3D(_LightningBase):
             image = batch["img"]
             if len(inflight) == depth:
                 yield inflight.pop(0).results(self, post_stream, to_host, caller)
-            plan = self._plan_for(image, slot)
+            plan = self._plan_for(image, slot, self.fuse_blocks_pipeline)
             if image.dtype != plan.inp.dtype:
                 image = image.to(plan.inp.dtype)
             plan.launch(image, copy_stream, own_stream=True, caller_stream=caller)
