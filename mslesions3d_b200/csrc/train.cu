@@ -301,6 +301,179 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const bf16* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same two "apply" passes with the cross-block finalize folded in (one launch less per BatchNorm pass, and the
+// single-CTA finalize kernels -- pure latency on the critical chain: 28 launches x ~7 us per step -- are gone):
+// EVERY CTA first sums the column partials of all C channels itself -- fp64, fixed order: lane l of a channel adds
+// blocks l, l+L, ..., the lanes are combined in order, so all CTAs (and all runs) get bit-identical values -- keeps
+// the per-channel constants in shared memory, and CTA 0 also writes them out (BN state for the backward pass,
+// running statistics / the parameter gradients).  colreduce_plan_fused keeps B*C small enough for that prologue
+// to cost ~2 us.
+// ------------------------------------------------------------------------------------------------
+constexpr int FIN_MAX_C = 512;
+
+// -> fin[c][0] = sum_b partial[b][c], fin[c][1] = sum_b partial[b][C + c]   (doubles, all C channels)
+__device__ __forceinline__ void cta_colpartials_sum(const float* __restrict__ partial, int B, int C,
+                                                    double (*red)[2], double (*fin)[2]) {
+  const int L = (C >= 256) ? 1 : 256 / C;              // block lanes per channel
+  for (int it = threadIdx.x; it < C * L; it += 256) {
+    const int c = it % C, l = it / C;
+    double ls = 0.0, lq = 0.0;
+    int b = l;
+    for (; b + 7 * L < B; b += 8 * L) {                // 16 independent loads in flight, then the ordered adds
+      float a0[8], a1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a0[u] = partial[(size_t)(b + u * L) * 2 * C + c];
+        a1[u] = partial[(size_t)(b + u * L) * 2 * C + C + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { ls += (double)a0[u]; lq += (double)a1[u]; }
+    }
+    for (; b < B; b += L) {
+      ls += (double)partial[(size_t)b * 2 * C + c];
+      lq += (double)partial[(size_t)b * 2 * C + C + c];
+    }
+    red[it][0] = ls;
+    red[it][1] = lq;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double s = 0.0, q = 0.0;
+    for (int l = 0; l < L; ++l) { s += red[l * C + c][0]; q += red[l * C + c][1]; }
+    fin[c][0] = s;
+    fin[c][1] = q;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) bn_apply_relu_fin_kernel(const bf16* __restrict__ z,
+                                                                const float* __restrict__ partial, int B, int C,
+                                                                long long M, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps,
+                                                                float momentum, float* __restrict__ running_mean,
+                                                                float* __restrict__ running_var,
+                                                                long long* __restrict__ num_batches_tracked,
+                                                                float* __restrict__ scale_out,
+                                                                float* __restrict__ shift_out,
+                                                                float* __restrict__ mean_out,
+                                                                float* __restrict__ invstd_out, bf16* __restrict__ a,
+                                                                long long total_vec, int* nan_flag) {
+  __shared__ double red[FIN_MAX_C][2];
+  __shared__ double fin[FIN_MAX_C][2];
+  __shared__ float s_scale[FIN_MAX_C], s_shift[FIN_MAX_C];
+  pdl_wait();
+  pdl_launch_dependents();
+  cta_colpartials_sum(partial, B, C, red, fin);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const double mu = fin[c][0] / (double)M;
+    double var = fin[c][1] / (double)M - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float istd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const float sc = ga * istd;
+    const float sh = be - (float)mu * sc;
+    s_scale[c] = sc;
+    s_shift[c] = sh;
+    if (blockIdx.x == 0) {
+      scale_out[c] = sc;
+      shift_out[c] = sh;
+      mean_out[c] = (float)mu;
+      invstd_out[c] = istd;
+      if (running_mean && running_var) {
+        const double unbiased = (M > 1) ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mu);
+        running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+      }
+    }
+  }
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
+  __syncthreads();
+  if (!a) return;
+  const int CV = C >> 3;
+  bool bad = false;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += 2 * stride) {
+    const long long i1 = i + stride;
+    const uint4 z0 = ld_nc16(z + i * 8);
+    uint4 z1 = make_uint4(0u, 0u, 0u, 0u);
+    if (i1 < total_vec) z1 = ld_nc16(z + i1 * 8);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long idx = k ? i1 : i;
+      if (idx >= total_vec) break;
+      const int c0 = (int)(idx % CV) << 3;
+      float zf[8], o[8];
+      unpack8f(k ? z1 : z0, zf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = relu_nan(__fadd_rn(__fmul_rn(zf[j], s_scale[c0 + j]), s_shift[c0 + j]));
+        bad |= (o[j] != o[j]);
+      }
+      *reinterpret_cast<uint4*>(a + idx * 8) = pack8f(o);
+    }
+  }
+  if (bad && nan_flag) atomicOr(nan_flag, SSD3D_NAN_BACKBONE);
+}
+
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_fin_kernel(const bf16* __restrict__ z, const bf16* g,
+                                                                    const float* __restrict__ partial, int B, int C,
+                                                                    const float* __restrict__ scale,
+                                                                    const float* __restrict__ shift,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ invstd,
+                                                                    float* __restrict__ dgamma,
+                                                                    float* __restrict__ dbeta, float inv_m, bf16* dz,
+                                                                    long long total_vec) {
+  __shared__ double red[FIN_MAX_C][2];
+  __shared__ double fin[FIN_MAX_C][2];
+  __shared__ float s_sc[FIN_MAX_C], s_sh[FIN_MAX_C], s_ka[FIN_MAX_C], s_kb[FIN_MAX_C];
+  pdl_wait();
+  pdl_launch_dependents();
+  cta_colpartials_sum(partial, B, C, red, fin);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float db = (float)fin[c][0], dg = (float)fin[c][1];
+    if (blockIdx.x == 0) { dbeta[c] = db; dgamma[c] = dg; }
+    // dz = sc*(dy - dbeta/M - xhat*dgamma/M) with xhat = (z - mu)*invstd, regrouped as sc*dy + A + z*B
+    const float sc = scale[c], is = invstd[c], mu = mean[c];
+    const float t = sc * is * dg * inv_m;
+    s_sc[c] = sc;
+    s_sh[c] = shift[c];
+    s_kb[c] = -t;
+    s_ka[c] = fmaf(mu, t, -(sc * db * inv_m));
+  }
+  __syncthreads();
+  const int CV = C >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += 2 * stride) {
+    const long long i1 = i + stride;
+    const bool two = i1 < total_vec;
+    const uint4 z0 = ld_nc16(z + i * 8);
+    const uint4 g0 = *reinterpret_cast<const uint4*>(g + i * 8);
+    uint4 z1 = make_uint4(0u, 0u, 0u, 0u), g1 = make_uint4(0u, 0u, 0u, 0u);
+    if (two) {
+      z1 = ld_nc16(z + i1 * 8);
+      g1 = *reinterpret_cast<const uint4*>(g + i1 * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k && !two) break;
+      const long long idx = k ? i1 : i;
+      const int c0 = (int)(idx % CV) << 3;
+      float zf[8], gf[8], o[8];
+      unpack8f(k ? z1 : z0, zf);
+      unpack8f(k ? g1 : g0, gf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = __fadd_rn(__fmul_rn(zf[j], s_sc[c0 + j]), s_sh[c0 + j]);
+        const float dy = (pre > 0.f) ? gf[j] : 0.f;
+        o[j] = fmaf(zf[j], s_kb[c0 + j], fmaf(s_sc[c0 + j], dy, s_ka[c0 + j]));
+      }
+      *reinterpret_cast<uint4*>(dz + idx * 8) = pack8f(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // mma.sync helpers (bf16 x bf16 -> fp32, m16n8k16)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
@@ -1293,6 +1466,17 @@ static int colreduce_plan(long long M, int C, int* threads, long long* rows_per_
 
 extern "C" int64_t ssd3d_bn_workspace_bytes(int C) { return (int64_t)COLRED_MAX_BLOCKS * 2 * C * 4; }
 
+// the apply kernels finalize in every CTA (see above): keep blocks x channels bounded so that this costs ~2 us
+// MEASURED (B200, C3 step): 1.82 ms with the fused finalize against 1.59 ms with the separate single-CTA finalize
+// kernels -- every one of the ~1000 apply CTAs re-reads B x 2C partials from L2 (up to 150 KB each) and the
+// reduction runs with fewer blocks -- so it is OFF by default (SSD3D_BN_FUSED_FINALIZE=1 switches it on).
+static const bool g_bn_fused_finalize = [] { const char* e = getenv("SSD3D_BN_FUSED_FINALIZE"); return e && e[0] == '1'; }();
+static int colreduce_cap_fused(int C, int cap) {
+  int b = 18944 / (C > 0 ? C : 1);
+  if (b < 16) b = 16;
+  return b < cap ? b : cap;
+}
+
 extern "C" int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* gamma, const float* beta, float eps,
                                   float momentum, float* running_mean, float* running_var,
                                   int64_t* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
@@ -1300,13 +1484,23 @@ extern "C" int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* 
   if (!z || !scale || !shift || !mean || !invstd || !workspace || M <= 0) return SSD3D_ERR_ARG;
   int threads;
   long long rpb;
-  const int B = colreduce_plan(M, C, &threads, &rpb);
+  const bool fused = g_bn_fused_finalize && C <= FIN_MAX_C;
+  const int B = colreduce_plan(M, C, &threads, &rpb, fused ? colreduce_cap_fused(C, COLRED_MAX_BLOCKS) : COLRED_MAX_BLOCKS);
   if (B < 0 || workspace_bytes < (int64_t)B * 2 * C * 4) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
   const bf16* zp = static_cast<const bf16*>(z);
   SSD3D_LAUNCH_PDL(colreduce_kernel<0>, dim3(B), dim3(threads), 0, st, zp, (const bf16*)nullptr, (const float*)nullptr,
                    (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (long long)M, C, rpb, partial);
+  if (fused) {
+    const long long total_vec = (long long)M * (C / 8);
+    const int grid = a ? grid_for((total_vec + 1) / 2, 256, 148 * 8) : 1;
+    SSD3D_LAUNCH_PDL(bn_apply_relu_fin_kernel, dim3(grid), dim3(256), 0, st, zp, (const float*)partial, B, C, (long long)M,
+                     gamma, beta, eps, momentum, running_mean, running_var,
+                     reinterpret_cast<long long*>(num_batches_tracked), scale, shift, mean, invstd,
+                     static_cast<bf16*>(a), total_vec, nan_flag);
+    return SSD3D_OK;
+  }
   SSD3D_LAUNCH_PDL(bn_finalize_fwd_kernel, dim3((C + 31) / 32), dim3(1024), 0, st, (const float*)partial, B, C,
                    (long long)M, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd,
                    reinterpret_cast<long long*>(num_batches_tracked));
@@ -1327,7 +1521,8 @@ extern "C" int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, i
   long long rpb;
   // the backward reduction holds 84 registers: three CTAs per SM are resident, so at most 3 x 148 blocks (a fourth
   // quarter of the grid would run as a second, mostly empty wave)
-  const int B = colreduce_plan(M, C, &threads, &rpb, 444);
+  const bool fused = g_bn_fused_finalize && C <= FIN_MAX_C;
+  const int B = colreduce_plan(M, C, &threads, &rpb, fused ? colreduce_cap_fused(C, 444) : 444);
   if (B < 0 || workspace_bytes < (int64_t)B * 2 * C * 4) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);
@@ -1335,6 +1530,13 @@ extern "C" int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, i
   const bf16* gp = static_cast<const bf16*>(grad_a);
   SSD3D_LAUNCH_PDL(colreduce_kernel<1>, dim3(B), dim3(threads), 0, st, zp, gp, scale, shift, mean, invstd, (long long)M,
                    C, rpb, partial);
+  if (fused) {
+    const long long total_vec = (long long)M * (C / 8);
+    SSD3D_LAUNCH_PDL(bn_relu_bwd_apply_fin_kernel, dim3(grid_for((total_vec + 1) / 2, 256, 148 * 8)), dim3(256), 0, st, zp,
+                     gp, (const float*)partial, B, C, scale, shift, mean, invstd, dgamma, dbeta,
+                     (float)(1.0 / (double)M), static_cast<bf16*>(dz), total_vec);
+    return SSD3D_OK;
+  }
   SSD3D_LAUNCH_PDL(bn_finalize_bwd_kernel, dim3((C + 31) / 32), dim3(1024), 0, st, (const float*)partial, B, C, dgamma,
                    dbeta);
   const long long total_vec = (long long)M * (C / 8);
