@@ -92,19 +92,35 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(const float* __restr
 // ({~orderable(score), prior index}), so the result is exactly the first `nmax` entries of the full sort.
 // Empty slots hold the sentinel ~0, which sorts last and is dropped at the end.
 // ------------------------------------------------------------------------------------------------
+// Stages whose compare-exchange distance j fits inside a warp's own contiguous chunk of np2 / nwarps keys
+// (2j <= chunk) only need __syncwarp: for 8192 keys on 32 warps that is 76 of the 91 stages, and the block-wide
+// barrier -- what the network's run time was made of -- remains for the 15 long-distance ones.
 __device__ __forceinline__ int bitonic_sort_smem(unsigned long long* keys, const unsigned long long* src, int n) {
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   for (int i = threadIdx.x; i < np2; i += blockDim.x) keys[i] = (i < n) ? src[i] : ~0ull;
   __syncthreads();
+  const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int chunk = np2 / nwarps;                     // power of two (blockDim.x is a power of two), maybe < 2
+  if (chunk < 2) chunk = 0;
+  auto cmpx = [&](int t, int j, int k) {
+    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const int hi = lo | j;
+    const bool up = (lo & k) == 0;
+    const unsigned long long a = keys[lo], b = keys[hi];
+    if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+  };
   for (int k = 2; k <= np2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
-        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int hi = lo | j;
-        const bool up = (lo & k) == 0;
-        const unsigned long long a = keys[lo], b = keys[hi];
-        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+    int j = k >> 1;
+    for (; j > 0 && 2 * j > chunk; j >>= 1) {   // long distance: the whole block, one barrier per stage
+      for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) cmpx(t, j, k);
+      __syncthreads();
+    }
+    if (j > 0) {                                // the rest of this level stays inside each warp's chunk
+      const int t0 = warp * (chunk >> 1);
+      for (; j > 0; j >>= 1) {
+        for (int t = lane; t < (chunk >> 1); t += 32) cmpx(t0 + t, j, k);
+        __syncwarp();
       }
       __syncthreads();
     }
@@ -190,6 +206,9 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float uni, float thr) {
   return __fdiv_rn(inter, uni) > thr;
 }
 
+// exact fallback of iou_exceeds, kept out of the hot loop
+__device__ __noinline__ bool iou_exceeds_exact(float inter, float uni, float thr) { return __fdiv_rn(inter, uni) > thr; }
+
 template <bool TR>
 __device__ __forceinline__ void nms_mask_body(const float* __restrict__ sboxes, const int* __restrict__ nkeep,
                                               int n_fixed, long long seg_stride_boxes, int words,
@@ -202,16 +221,15 @@ __device__ __forceinline__ void nms_mask_body(const float* __restrict__ sboxes, 
   if (cb < rb) return;
   const int n = nkeep ? nkeep[seg] : n_fixed;
   if (rb * 64 >= n || cb * 64 >= n) return;
-  __shared__ float cbox[64][6];
-  __shared__ float cvol[64];
+  // column boxes as two 16-byte records each: {x0, y0, z0, x1}, {y1, z1, volume, -}: two broadcast LDS.128 per pair
+  __shared__ float4 cb0[64], cb1[64];
   const float* base = sboxes + (long long)seg * seg_stride_boxes;
   const int t = threadIdx.x;
   const int cj = cb * 64 + t;
   if (cj < n) {
     const Box6 b = load_box(base + (long long)cj * 6);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) cbox[t][k] = b.v[k];
-    cvol[t] = box_volume(b);
+    cb0[t] = make_float4(b.v[0], b.v[1], b.v[2], b.v[3]);
+    cb1[t] = make_float4(b.v[4], b.v[5], box_volume(b), 0.f);
   }
   __syncthreads();
   const int i = rb * 64 + t;
@@ -220,14 +238,36 @@ __device__ __forceinline__ void nms_mask_body(const float* __restrict__ sboxes, 
     const Box6 a = load_box(base + (long long)i * 6);
     const float va = box_volume(a);
     const int jn = min(64, n - cb * 64);
-    for (int b = 0; b < jn; ++b) {
-      Box6 o;
+    const bool thr_pos = thr > 0.0f;
+    const float thr_hi = thr * 1.000004f, thr_lo = thr * 0.999996f;
+    (void)thr_hi; (void)thr_lo;
+    unsigned int half[2] = {0u, 0u};
 #pragma unroll
-      for (int k = 0; k < 6; ++k) o.v[k] = cbox[b][k];
-      const float inter = box_intersection(a, o);
-      const float uni = __fsub_rn(__fadd_rn(va, cvol[b]), inter);
-      if (iou_exceeds(inter, uni, thr)) bits |= (1ull << b);
+    for (int hb = 0; hb < 2; ++hb) {
+      unsigned int acc = 0u;
+#pragma unroll 8
+      for (int bb = 0; bb < 32; ++bb) {
+        const int b = hb * 32 + bb;
+        if (b >= jn) break;
+        const float4 p = cb0[b], q = cb1[b];
+        // utils.py:119-122, one rounded op at a time (clamp: NaN propagates like torch.clamp)
+        const float d0 = clamp_min0(__fsub_rn(fminf(a.v[3], p.w), fmaxf(a.v[0], p.x)));
+        const float d1 = clamp_min0(__fsub_rn(fminf(a.v[4], q.x), fmaxf(a.v[1], p.y)));
+        const float d2 = clamp_min0(__fsub_rn(fminf(a.v[5], q.y), fmaxf(a.v[2], p.z)));
+        const float inter = __fmul_rn(__fmul_rn(d0, d1), d2);
+        const float uni = __fsub_rn(__fadd_rn(va, q.z), inter);
+        // iou_exceeds: multiply pre-test with a guard band, exact IEEE division only near the threshold / for
+        // degenerate unions
+        const float tt = thr * uni;
+        const bool yes = inter > tt * 1.000004f, no = inter < tt * 0.999996f;
+        bool hit;
+        if (thr_pos && uni > 1e-30f && uni < 1e30f && (yes || no)) hit = yes;
+        else hit = iou_exceeds_exact(inter, uni, thr);
+        acc |= hit ? (1u << bb) : 0u;
+      }
+      half[hb] = acc;
     }
+    bits = ((unsigned long long)half[1] << 32) | half[0];
     if (cb == rb) bits &= ~(1ull << t);       // a box does not suppress itself (ssd3d.py:425-426)
     // TR: word-major layout [word][row] with `words` = rows per word-row (coalesced for the chunk scan)
     if (TR) mask[(long long)seg * seg_stride_mask + (long long)cb * words + i] = bits;
@@ -271,44 +311,58 @@ __device__ __forceinline__ void nms_scan_core(const unsigned long long* M, int n
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = removed_init ? removed_init[w] : 0ull;
   __syncthreads();
-  for (int k = 0; k < words; ++k) {
-    const int rows = min(64, n - k * 64);
-    if (warp == 0) {
-      const unsigned long long r0 = (lane < rows) ? M[(long long)(k * 64 + lane) * stride + k] : 0ull;
-      const unsigned long long r1 = (lane + 32 < rows) ? M[(long long)(k * 64 + lane + 32) * stride + k] : 0ull;
-      const unsigned long long e0 = r0 & ((1ull << lane) - 1ull);
-      const unsigned long long e1 = r1 & ((1ull << (lane + 32)) - 1ull);
-      unsigned long long rem = removed[k];
-      if (rows < 64) rem |= (~0ull) << rows;            // rows past the end are never kept
-      unsigned long long und = ~rem, kept = 0ull;
-      while (und != 0ull) {
-        const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
-        const bool x0 = u0 && (e0 & kept) != 0ull, x1 = u1 && (e1 & kept) != 0ull;
-        const bool k0 = u0 && !x0 && (e0 & und) == 0ull, k1 = u1 && !x1 && (e1 & und) == 0ull;
-        const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
-                                      ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
-        const unsigned long long nx = (unsigned long long)__ballot_sync(0xffffffffu, x0) |
-                                      ((unsigned long long)__ballot_sync(0xffffffffu, x1) << 32);
-        kept |= nk;
-        und &= ~(nk | nx);
-      }
-      if (lane == 0) keptw[k] = kept;
-    }
-    __syncthreads();
-    const unsigned long long kept = keptw[k];
-    if (kept != 0ull) {
-      for (int w = k + 1 + warp; w < words; w += nwarps) {
-        unsigned int lo = 0u, hi = 0u;
+  // OR of the rows of chunk k's kept boxes, word w, by one warp (redux.or across the lanes)
+  auto or_word = [&](int k, unsigned long long kept, int w) {
+    unsigned int lo = 0u, hi = 0u;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int b = h * 32 + lane;
-          unsigned long long v = 0ull;
-          if ((kept >> b) & 1ull) v = M[(long long)(k * 64 + b) * stride + w];
-          lo |= __reduce_or_sync(0xffffffffu, (unsigned int)v);
-          hi |= __reduce_or_sync(0xffffffffu, (unsigned int)(v >> 32));
-        }
-        if (lane == 0) removed[w] |= ((unsigned long long)hi << 32) | lo;
+    for (int h = 0; h < 2; ++h) {
+      const int b = h * 32 + lane;
+      unsigned long long v = 0ull;
+      if ((kept >> b) & 1ull) v = M[(long long)(k * 64 + b) * stride + w];
+      lo |= __reduce_or_sync(0xffffffffu, (unsigned int)v);
+      hi |= __reduce_or_sync(0xffffffffu, (unsigned int)(v >> 32));
+    }
+    if (lane == 0) atomicOr(&removed[w], ((unsigned long long)hi << 32) | lo);
+  };
+  // ONE block barrier per chunk.  In iteration k warp 0 resolves chunk k and immediately ORs its kept rows into
+  // word k+1 (all the next chunk needs from this one); meanwhile the other warps spread chunk k-1's kept rows
+  // over the words >= k+1.  Word k is complete when warp 0 reads it: chunk k-1's part was added by warp 0 itself
+  // one iteration ago, the parts of chunks <= k-2 by the helpers at least one barrier ago.
+  for (int k = 0; k <= words; ++k) {
+    if (warp == 0) {
+      if (nwarps == 1 && k >= 1) {                        // no helpers in a one-warp block: do their part first
+        const unsigned long long kp = keptw[k - 1];
+        if (kp != 0ull)
+          for (int w = k + 1; w < words; ++w) or_word(k - 1, kp, w);
+        __syncwarp();
       }
+      if (k < words) {
+        const int rows = min(64, n - k * 64);
+        const unsigned long long r0 = (lane < rows) ? M[(long long)(k * 64 + lane) * stride + k] : 0ull;
+        const unsigned long long r1 = (lane + 32 < rows) ? M[(long long)(k * 64 + lane + 32) * stride + k] : 0ull;
+        const unsigned long long e0 = r0 & ((1ull << lane) - 1ull);
+        const unsigned long long e1 = r1 & ((1ull << (lane + 32)) - 1ull);
+        unsigned long long rem = removed[k];
+        if (rows < 64) rem |= (~0ull) << rows;            // rows past the end are never kept
+        unsigned long long und = ~rem, kept = 0ull;
+        while (und != 0ull) {
+          const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
+          const bool x0 = u0 && (e0 & kept) != 0ull, x1 = u1 && (e1 & kept) != 0ull;
+          const bool k0 = u0 && !x0 && (e0 & und) == 0ull, k1 = u1 && !x1 && (e1 & und) == 0ull;
+          const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, k0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+          const unsigned long long nx = (unsigned long long)__ballot_sync(0xffffffffu, x0) |
+                                        ((unsigned long long)__ballot_sync(0xffffffffu, x1) << 32);
+          kept |= nk;
+          und &= ~(nk | nx);
+        }
+        if (lane == 0) keptw[k] = kept;
+        if (kept != 0ull && k + 1 < words) or_word(k, kept, k + 1);
+      }
+    } else if (k >= 1) {                                    // (nwarps > 1 here)
+      const unsigned long long kept = keptw[k - 1];       // published before the previous barrier
+      if (kept != 0ull)
+        for (int w = k + 1 + (warp - 1); w < words; w += nwarps - 1) or_word(k - 1, kept, w);
     }
     __syncthreads();
   }
@@ -321,11 +375,10 @@ __device__ void nms_scan(const unsigned long long* __restrict__ mask, int n, int
                          long long stage_words) {
   const int words = (n + 63) >> 6;
   if ((long long)n * words <= stage_words) {
-    const int total = n * words;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-      const int i = e / words, w = e - i * words;
-      if (w >= (i >> 6)) stage[e] = mask[(long long)i * row_stride + w];
-    }
+    // only the words w >= i / 64 of row i exist; a half-warp copies one row (words <= 16 for the default 1000)
+    const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15, nhw = blockDim.x >> 4;
+    for (int i = hw; i < n; i += nhw)
+      for (int w = (i >> 6) + hl; w < words; w += 16) stage[i * words + w] = mask[(long long)i * row_stride + w];
     __syncthreads();
     nms_scan_core(stage, n, words, removed, keptw);
   } else {
@@ -347,7 +400,7 @@ __device__ __forceinline__ int count_greater(const float* s, int n, float v, boo
   return lo;
 }
 
-__global__ void __launch_bounds__(256) nms_select_kernel(const unsigned long long* __restrict__ mask,
+__global__ void __launch_bounds__(512) nms_select_kernel(const unsigned long long* __restrict__ mask,
                                                          const int* __restrict__ nkeep, int C, int nmax, int words_max,
                                                          long long stage_words, const float* __restrict__ sboxes,
                                                          const float* __restrict__ sscores,
@@ -1410,7 +1463,7 @@ static int detect_objects_impl(const float* locs, const float* scores, PriorSrc 
       e = cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;
     }
-    SSD3D_LAUNCH_PDL(nms_select_kernel, dim3(N), dim3(256), smem, st, mask, nkeep, n_classes, L.nmax, L.words, stage_words,
+    SSD3D_LAUNCH_PDL(nms_select_kernel, dim3(N), dim3(512), smem, st, mask, nkeep, n_classes, L.nmax, L.words, stage_words,
                      sboxes, sscores, sprior, keptpos, keptscore, keptcnt, top_k, out_boxes, out_scores,
                      reinterpret_cast<long long*>(out_labels), reinterpret_cast<long long*>(out_prior), out_count);
   }
