@@ -24,7 +24,8 @@ struct HeadKwParams {
   int tiles_w, tiles_h, tiles_d;
   int num_kb, stages;
   int BN, tmem_cols;           // columns per CTA (144, or 48 with three column tiles on small maps)
-  float* Y;                    // (N*D*H*W, 144) fp32
+  float* Y;                    // (N, 144, D*H*W) fp32: column-major per image, so that the row-per-thread epilogue
+                               // of the GEMM and the voxel-per-thread stencil both access it coalesced
   // stencil
   int n_loc, n_cls, bpl, n_classes;
   long long P, prior_off;
@@ -142,17 +143,18 @@ __global__ void __launch_bounds__(192, 2) head_kw_gemm_kernel(const __grid_const
     const int d = td0 + r % p.TD; r /= p.TD;
     const int n = tn0 + r;
     const bool valid = (w < p.W) && (h < p.H) && (d < p.D) && (n < p.N);
-    float* yrow = p.Y + ((((long long)n * p.D + d) * p.H + h) * p.W + w) * KW_N + n0;
+    // Y is stored column-major per image: the 32 lanes of a warp are consecutive voxels of the tile (8 along W,
+    // then H), so each scalar store instruction writes whole 32-byte sectors (4 per warp) instead of 32 half-used
+    // lines with the row-major float4 stores this replaces
+    const long long V = (long long)p.D * p.H * p.W;
+    float* ycol = p.Y + ((long long)n * KW_N + n0) * V + ((long long)d * p.H + h) * p.W + w;
     for (int c = 0; c < p.BN; c += 16) {
       uint32_t v[16];
       tmem_ld_32x32b_x16(taddr + (uint32_t)c, v);
       tmem_ld_wait();
       if (valid) {
-        float4* dst = reinterpret_cast<float4*>(yrow + c);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                               __uint_as_float(v[4 * q + 3]));
+        for (int q = 0; q < 16; ++q) ycol[(long long)(c + q) * V] = __uint_as_float(v[q]);
       }
     }
   }
@@ -164,40 +166,43 @@ __global__ void __launch_bounds__(192, 2) head_kw_gemm_kernel(const __grid_const
   }
 }
 
-// out[d,h,w][c] = bias[c] + sum_{g = kd*3+kh ascending, in bounds} Y[d+kd-1, h+kh-1, w][g*16 + c]
-__global__ void __launch_bounds__(256) head_stencil_kernel(const HeadKwParams p) {
+// out[d,h,w][c] = bias[c] + sum_{g = kd*3+kh ascending, in bounds} Y[g*16 + c][d+kd-1, h+kh-1, w]
+// thread = one voxel, all 16 columns: every load is coalesced across the warp (consecutive voxels of a column)
+__global__ void __launch_bounds__(128) head_stencil_kernel(const HeadKwParams p) {
   pdl_wait();
   pdl_launch_dependents();
-  const long long total = (long long)p.N * p.D * p.H * p.W * 4;
+  const long long V = (long long)p.D * p.H * p.W;
+  const long long total = (long long)p.N * V;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int c0 = (int)(gid & 3) * 4;
-  long long r = gid >> 2;
+  const int n = (int)(gid / V);
+  long long r = gid - (long long)n * V;
   const int w = (int)(r % p.W); r /= p.W;
-  const int h = (int)(r % p.H); r /= p.H;
-  const int d = (int)(r % p.D);
-  const int n = (int)(r / p.D);
+  const int h = (int)(r % p.H);
+  const int d = (int)(r / p.H);
   const int ncol = p.n_loc + p.n_cls;
-  if (c0 >= ncol) return;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
 #pragma unroll
   for (int g = 0; g < 9; ++g) {
     const int dd = d + g / 3 - 1, hh = h + g % 3 - 1;
     if ((unsigned)dd >= (unsigned)p.D || (unsigned)hh >= (unsigned)p.H) continue;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(
-        p.Y + ((((long long)n * p.D + dd) * p.H + hh) * p.W + w) * KW_N + g * 16 + c0));
-    acc[0] = __fadd_rn(acc[0], v.x); acc[1] = __fadd_rn(acc[1], v.y);
-    acc[2] = __fadd_rn(acc[2], v.z); acc[3] = __fadd_rn(acc[3], v.w);
+    const float* src = p.Y + ((long long)n * KW_N + g * 16) * V + ((long long)dd * p.H + hh) * p.W + w;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = __ldg(src + (long long)c * V);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = __fadd_rn(acc[c], v[c]);
   }
   const long long prior = p.prior_off + (((long long)d * p.H + h) * p.W + w) * p.bpl;
   float* lp = p.locs + ((long long)n * p.P + prior) * 6;
   float* sp = p.scores + ((long long)n * p.P + prior) * p.n_classes;
   bool bad_l = false, bad_s = false;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int c = c0 + q;
+  for (int c = 0; c < 16; ++c) {
     if (c >= ncol) break;
-    const float val = __fadd_rn(acc[q], __ldg(p.bias + c));
+    const float val = __fadd_rn(acc[c], __ldg(p.bias + c));
     if (c < p.n_loc) { lp[c] = val; bad_l |= (val != val); }
     else { sp[c - p.n_loc] = val; bad_s |= (val != val); }
   }
@@ -285,8 +290,7 @@ int ssd3d_head_conv_kw(const void* x, const void* w, int w_is_kw, const float* b
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)m_tiles, (unsigned)(KW_N / p.BN));
   SSD3D_LAUNCH_PDL(head_kw_gemm_kernel, grid, dim3(192), smem, st, tmA, tmB, p);
-  const long long total = M * 4;
-  SSD3D_LAUNCH_PDL(head_stencil_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);
+  SSD3D_LAUNCH_PDL(head_stencil_kernel, dim3((unsigned)((M + 127) / 128)), dim3(128), 0, st, p);
   return SSD3D_OK;
 }
 

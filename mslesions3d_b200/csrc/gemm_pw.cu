@@ -2,9 +2,11 @@
 // for the large maps, where the one-tile-per-CTA kernel of gemm_tc.cu spends most of its time in per-CTA latency
 // (barrier init, TMEM allocation, one TMA round trip, one commit, the epilogue -- all in sequence: 28 % of the HBM
 // peak on the 262 144 x 32 -> 64 layer).  Here a CTA walks tiles t = blockIdx.x, + gridDim.x, ...:
-//   warp 4   TMA producer: keeps a ring of {A,B} stages full ACROSS tile boundaries
-//   warp 5   UMMA issuer: accumulates tile j into TMEM buffer j & 1 (2 x BN fp32 columns)
-//   warps 0-3 epilogue: drain buffer j & 1 (tcgen05.ld, BN scale/shift from smem, activation floor, bf16 pack)
+//   warp 8   TMA producer: keeps a ring of {A,B} stages full ACROSS tile boundaries
+//   warp 9   UMMA issuer: accumulates tile j into TMEM buffer j & 1 (2 x BN fp32 columns)
+//   warps 0-7 epilogue, TWO warps per TMEM lane quarter (columns 0-31 / 32-63 of the row: ncu showed the four-warp
+//            epilogue, not the loads or the MMAs, setting the tile rate -- barrier and long-scoreboard stalls):
+//            drain buffer j & 1 (tcgen05.ld, BN scale/shift from smem, activation floor, bf16 pack)
 //            into a 128B-swizzled staging tile and hand it to ONE TMA store (cp.async.bulk.tensor ... global.shared)
 //            while the issuer already works on tile j + 1.  (A thread owns a row, so direct stores would make every
 //            warp-wide 16-byte store touch 32 different 128-byte lines: half-used sectors, 8 instructions per row.)
@@ -39,7 +41,7 @@ __device__ __forceinline__ uint64_t pw_desc(uint32_t smem_addr) {
 }
 
 template <int BK>
-__global__ void __launch_bounds__(192) gemm_pw_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320) gemm_pw_persistent_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const __grid_constant__ CUtensorMap tmY,
                                                                     const PwParams p) {
@@ -60,15 +62,15 @@ __global__ void __launch_bounds__(192) gemm_pw_persistent_kernel(const __grid_co
   uint8_t* stage_out = smem + (((size_t)p.stages * STAGE_BYTES + 256 + (size_t)p.Cout * 8 + 1023) & ~(size_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmY);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 256); }
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(192) gemm_pw_persistent_kernel(const __grid_co
   __syncthreads();
 
   const int total_tiles = p.m_tiles * p.n_tiles;
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(192) gemm_pw_persistent_kernel(const __grid_co
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN);
       int it = 0, j = 0;
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(192) gemm_pw_persistent_kernel(const __grid_co
     }
     __syncwarp();
   } else {
-    const int row = warp * 32 + lane;
+    const int q = warp & 3, hf = warp >> 2;          // TMEM lane quarter, column half (32 columns) of this warp
+    const int row = q * 32 + lane;
     bool bad = false;
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
@@ -134,23 +137,24 @@ __global__ void __launch_bounds__(192) gemm_pw_persistent_kernel(const __grid_co
       mbar_wait(&tmem_full[ab], (uint32_t)(u & 1));
       __syncwarp();
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * 64);
-      uint32_t v[64];
-#pragma unroll
-      for (int c = 0; c < 64; c += 16) tmem_ld_32x32b_x16(taddr + (uint32_t)c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 64 + hf * 32);
+      uint32_t v[32];
+      tmem_ld_32x32b_x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+      tmem_ld_32x32b_x16(taddr + 16u, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&tmem_empty[ab]);        // accumulator is in registers: 128 arrivals release the TMEM buffer
+      mbar_arrive(&tmem_empty[ab]);        // accumulator is in registers: 256 arrivals release the TMEM buffer
       // staging buffer ab was handed to a TMA store two tiles ago: wait until that store has READ it
       if (threadIdx.x == 0 && u > 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       uint8_t* dst_row = stage_out + (size_t)ab * 16384 + (size_t)row * 128;
 #pragma unroll
-      for (int c = 0; c < 64; c += 8) {
-        const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + n0 + c);
-        const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + n0 + c + 4);
-        const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + n0 + c);
-        const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + n0 + c + 4);
+      for (int c = 0; c < 32; c += 8) {
+        const int cc = hf * 32 + c;            // column inside the 64-wide tile
+        const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + n0 + cc);
+        const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + n0 + cc + 4);
+        const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + n0 + cc);
+        const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + n0 + cc + 4);
         const float r0 = clamp_floor(__fadd_rn(__fmul_rn(__uint_as_float(v[c + 0]), sc0.x), sh0.x), p.floor);
         const float r1 = clamp_floor(__fadd_rn(__fmul_rn(__uint_as_float(v[c + 1]), sc0.y), sh0.y), p.floor);
         const float r2 = clamp_floor(__fadd_rn(__fmul_rn(__uint_as_float(v[c + 2]), sc0.z), sh0.z), p.floor);
@@ -162,12 +166,12 @@ __global__ void __launch_bounds__(192) gemm_pw_persistent_kernel(const __grid_co
         // NaN check on the sum: NaN iff any term is NaN (or +inf and -inf meet, which the next layer turns into NaN anyway)
         const float chk = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
         bad |= (chk != chk) && ((r0 != r0) | (r1 != r1) | (r2 != r2) | (r3 != r3) | (r4 != r4) | (r5 != r5) | (r6 != r6) | (r7 != r7));
-        // 16-byte chunk (c / 8) of this row, 128-byte swizzle: chunk ^ (row & 7)
-        *reinterpret_cast<uint4*>(dst_row + ((((c >> 3) ^ (row & 7))) << 4)) =
+        // 16-byte chunk (cc / 8) of this row, 128-byte swizzle: chunk ^ (row & 7)
+        *reinterpret_cast<uint4*>(dst_row + ((((cc >> 3) ^ (row & 7))) << 4)) =
             make_uint4(pack_bf16x2(r0, r1), pack_bf16x2(r2, r3), pack_bf16x2(r4, r5), pack_bf16x2(r6, r7));
       }
       fence_proxy_async_smem();            // generic-proxy writes -> visible to the TMA (async proxy)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) {
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                          reinterpret_cast<uint64_t>(&tmY)),
@@ -181,7 +185,7 @@ __global__ void __launch_bounds__(192) gemm_pw_persistent_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -259,11 +263,11 @@ int ssd3d_pwconv_persistent(const void* x, const void* w, const float* scale, co
   if (BK == 64) {
     e = cudaFuncSetAttribute(gemm_pw_persistent_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    SSD3D_LAUNCH_PDL(gemm_pw_persistent_kernel<64>, dim3(grid), dim3(192), smem, st, tmA, tmB, tmY, p);
+    SSD3D_LAUNCH_PDL(gemm_pw_persistent_kernel<64>, dim3(grid), dim3(320), smem, st, tmA, tmB, tmY, p);
   } else {
     e = cudaFuncSetAttribute(gemm_pw_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    SSD3D_LAUNCH_PDL(gemm_pw_persistent_kernel<32>, dim3(grid), dim3(192), smem, st, tmA, tmB, tmY, p);
+    SSD3D_LAUNCH_PDL(gemm_pw_persistent_kernel<32>, dim3(grid), dim3(320), smem, st, tmA, tmB, tmY, p);
   }
   return SSD3D_OK;
 }
