@@ -1,0 +1,500 @@
+// Stem (dense 3x3x3 Cin -> 32, stride (sd,2,2), BN, ReLU; mobilenet.py:26-31) FUSED with the depthwise conv of the
+// first Block (3x3x3, 32 channels, stride 2, BN, ReLU; mobilenet.py:38,44): the stem's activation -- 134 MB
+// written and 134 MB read back per batch of eight 2ch 128^3 volumes, half of the whole step's HBM traffic, and
+// HBM writes top out at 3.9 TB/s on this part (scripts/probe_hbm.py) -- never leaves the SM.
+//
+// Stem part = the banded-B tcgen05 GEMM of conv_stem_tz.cu (A operand = raw TMA'd input rows, B = Toeplitz
+// weights, M = 16 row slots of 32 stem voxels, N = 4 voxels x 32 channels).  Geometry for stem rows of 64 voxels
+// (W = 128):
+//   * a PLANE JOB is one stem plane P restricted to 16 stem rows (15 used: 2*7+1) = two M-tiles (left / right
+//     half of the row) = 36 UMMAs into two of the four 128-column TMEM accumulators;
+//   * the epilogue warps apply BN+ReLU and write the plane to ONE shared-memory buffer, de-interleaved along W
+//     (odd columns O[0..32] incl. the zero padding column -1, even columns E[0..31]) and chunk-swizzled
+//     (16-byte unit ^= line & 7), so that both the epilogue's 16-byte stores (lanes = consecutive 4-voxel
+//     groups) and the depthwise loads (lanes = 8 channel quads x 4 consecutive outputs) are conflict free;
+//     rows / planes outside the stem map are written as zeros (the depthwise conv's padding);
+//   * depthwise part: thread = (4 channels, output column w), owns the 7 output rows of the tile for TWO output
+//     planes in registers (accA = plane d, accB = plane d+1): stem plane 2d adds its kd=1 taps to accA, plane
+//     2d+1 its kd=2 taps to accA and its kd=0 taps to accB, then plane d is finished (BN+ReLU, 8-byte stores,
+//     a warp writes 256 contiguous bytes) and accB becomes accA.  Taps are applied in (kd, kh, kw) order with
+//     fma.rn.f32x2: bit-identical to the stand-alone depthwise kernels on the same stem values.
+//   * a CTA marches along D through a contiguous run of (image, 7-row tile, plane d) steps (8.6 per SM for the
+//     benchmark); a run that starts at d > 0 first computes stem plane 2d-1 (its kd=0 share).
+//   * warp roles: warp 0 = TMA producer (six (half, kd) units of 3 (kd,kh) boxes = one plane job, refilled unit by unit), warp 1 = UMMA issuer,
+//     warps 2..9 = epilogue + depthwise.  The UMMAs of job j+1 run while the CUDA cores finish job j.
+// Requirements: bf16 volumes, Cin <= 2, W = 128 (stem rows of 64 voxels), even stem H and D.
+#include "common.cuh"
+#include "tma_host.h"
+
+namespace ssd3d {
+
+struct StemDwParams {
+  int N, D, H, W, sd;
+  int Ds, Hs;                  // stem map (Ws = 64)
+  int Dd, Hd;                  // depthwise output map (Wd = 32)
+  int HT;                      // 7-row tiles along Hd
+  int steps;                   // N * HT * Dd
+  int kpad;                    // row pitch of wt
+  const __nv_bfloat16* wt;     // stem (32, kpad) bf16, k = ((ci*3+kd)*3+kh)*3+kw
+  const float* scale0;         // stem BN
+  const float* shift0;
+  const __nv_bfloat16* wd;     // depthwise (27, 32) bf16
+  const float* scale1;         // depthwise BN
+  const float* shift1;
+  __nv_bfloat16* y;            // (N, Dd, Hd, 32, 32)
+};
+
+namespace sdw {
+
+constexpr int SLOT_BYTES = 144;
+constexpr int CI_BYTES = 16 * SLOT_BYTES;     // 2304: 16 row slots of one input channel
+constexpr int B_BYTES = 4096;
+constexpr int NU = 6;                         // (half, kd) units of 3 boxes: exactly one plane job
+constexpr int THREADS = 320;
+constexpr int TH = 7;                         // depthwise rows per tile
+constexpr int O_BYTES = 17 * 128;             // 33 odd-column entries of 64 B
+constexpr int ROW_BYTES = 33 * 128;           // O then E (32 entries)
+constexpr int PLANE_BYTES = 16 * ROW_BYTES;   // 67584 (row 15 is never read)
+
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ uint64_t desc_k_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ float relu_nan1(float v) {   // max.NaN: torch.relu semantics
+  float r;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack_f32x2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+  return r;
+}
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t u) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(u << 16), "r"(u & 0xffff0000u));
+  return r;
+}
+__device__ __forceinline__ void ffma2(f32x2& acc, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2 v, float& lo, float& hi) {
+  uint32_t a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+  lo = __uint_as_float(a);
+  hi = __uint_as_float(b);
+}
+
+// byte offset of 16-byte unit c4 (0..3) of entry e inside a de-interleaved column array (O or E) of the plane
+__device__ __forceinline__ uint32_t entry_off(int e, int c4) {
+  const int line = e >> 1;
+  return (uint32_t)(line * 128 + (((((e & 1) << 2) | c4) ^ (line & 7)) << 4));
+}
+
+// The plane jobs of a CTA's run of steps [L0, L1), identical in every warp role.
+struct Jobs {
+  int L, L0, L1, Dd, stage;
+  int col, d, P, role;      // role 0: plane 2d-1 (kd=0 share only), 1: plane 2d (kd=1), 2: plane 2d+1 (kd=2, then finish)
+  bool cont;                // role 2: the run goes on with plane d+1 of the same column (kd=0 share into accB)
+  __device__ Jobs(int l0, int l1, int dd) : L(l0), L0(l0), L1(l1), Dd(dd), stage(0), col(0), d(0), P(0), role(0), cont(false) {}
+  __device__ bool next() {
+    if (L >= L1) return false;
+    col = L / Dd;
+    d = L - col * Dd;
+    if (stage == 0) {
+      stage = 1;
+      if (L == L0 && d > 0) { P = 2 * d - 1; role = 0; return true; }
+    }
+    if (stage == 1) { stage = 2; P = 2 * d; role = 1; return true; }
+    P = 2 * d + 1; role = 2;
+    cont = (L + 1 < L1) && (d + 1 < Dd);
+    stage = 0;
+    ++L;
+    return true;
+  }
+};
+
+}  // namespace sdw
+
+template <int CIN>
+__global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                 const StemDwParams p) {
+  using namespace sdw;
+  constexpr int NT = 9 * CIN;
+  constexpr int BOX_BYTES = CIN * CI_BYTES;          // one (kd,kh) box of one half: [ci][16 rows][72]
+  constexpr int UNIT_BYTES = 3 * BOX_BYTES;
+  constexpr uint32_t TMEM_COLS = 512;                // four 128-column accumulators
+
+  extern __shared__ uint8_t sdw_raw[];
+  const uint32_t raw = smem_u32(sdw_raw);
+  uint8_t* smem = sdw_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* sP = smem;                                            // stem plane buffer
+  uint8_t* sB = sP + PLANE_BYTES;                                // NT x 4096
+  uint8_t* sA = sB + NT * B_BYTES;                               // NU x UNIT_BYTES
+  float* sWd = reinterpret_cast<float*>(sA + NU * UNIT_BYTES);   // depthwise weights fp32 [27][32]
+  float* sSc0 = sWd + 27 * 32;                                   // stem BN scale[32], shift[32]
+  float* sSh0 = sSc0 + 32;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sSh0 + 32);
+  uint64_t* empty = full + NU;
+  uint64_t* acc_full = empty + NU;                               // [4]
+  uint64_t* acc_empty = acc_full + 4;                            // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < NU; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // ---- banded B operand, depthwise weights, stem BN; the plane buffer starts as zeros (column -1 stays zero) ----
+  for (int i = tid; i < (PLANE_BYTES + NT * B_BYTES) / 16; i += THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 27 * 32; i += THREADS) sWd[i] = __bfloat162float(p.wd[i]);
+  if (tid < 32) { sSc0[tid] = __ldg(p.scale0 + tid); sSh0[tid] = __ldg(p.shift0 + tid); }
+  __syncthreads();
+  for (int i = tid; i < NT * 3 * 32; i += THREADS) {
+    const int co = i & 31, tk = i >> 5;
+    const int t = tk / 3, kw = tk - 3 * t;
+    const __nv_bfloat16 wv = p.wt[co * p.kpad + tk];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = j * 32 + co, k = 7 + 2 * j + kw;
+      *reinterpret_cast<__nv_bfloat16*>(sB + t * B_BYTES + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = wv;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int L0 = (int)(((long long)blockIdx.x * p.steps) / gridDim.x);
+  const int L1 = (int)(((long long)(blockIdx.x + 1) * p.steps) / gridDim.x);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    const uint32_t sA_u = smem_u32(sA);
+    int j = 0;
+    Jobs jobs(L0, L1, p.Dd);
+    while (jobs.next()) {
+      const int n = jobs.col / p.HT, ht = jobs.col - n * p.HT;
+      const int ch = 4 * (ht * TH) - 3;                // input row of stem row 2*h0 - 1, tap kh = 0
+      const int cd = p.sd * jobs.P - 1;
+      const uint32_t ph = (uint32_t)(j & 1);
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {                    // unit = (half c, kd), fixed place in shared memory
+        const int c = u / 3, kd = u - 3 * c;
+        mbar_wait(&empty[u], ph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[u], (uint32_t)UNIT_BYTES);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+            tma_load_4d(sA_u + (uint32_t)(u * UNIT_BYTES + kh * BOX_BYTES), &tmX, &full[u], 64 * c - 8, ch + kh, cd + kd,
+                        n * CIN);
+        }
+        __syncwarp();
+      }
+      ++j;
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(128, 128);
+    const uint64_t da0 = desc_k_nosw(smem_u32(sA), 16u, (uint32_t)SLOT_BYTES);
+    const uint64_t db0 = desc_k_nosw(smem_u32(sB), 128u, 256u);
+    int j = 0;
+    Jobs jobs(L0, L1, p.Dd);
+    while (jobs.next()) {
+      const uint32_t apar = (uint32_t)((j >> 1) & 1);
+      const uint32_t ph = (uint32_t)(j & 1);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int buf = (j & 1) * 2 + c;
+        mbar_wait(&acc_empty[buf], apar ^ 1u);
+        const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+          const int u = c * 3 + kd;
+          mbar_wait(&full[u], ph);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int ci = 0; ci < CIN; ++ci)
+                umma_bf16_ss(dcol, da0 + (uint64_t)((u * UNIT_BYTES + kh * BOX_BYTES + ci * CI_BYTES) >> 4),
+                             db0 + (uint64_t)(((ci * 9 + kd * 3 + kh) * B_BYTES) >> 4), idesc, (kd | kh | ci) != 0 ? 1u : 0u);
+            umma_commit(&empty[u]);
+            if (kd == 2) umma_commit(&acc_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+      ++j;
+    }
+  } else {
+    // ===================== epilogue (TMEM -> BN/ReLU -> plane buffer) + depthwise =====================
+    const int ct = tid - 64;                     // 0..255
+    // epilogue role
+    const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;              // voxels j = 2*hh, 2*hh + 1 of a group
+    const int row = (q * 32 + lane) >> 3;        // stem row slot 0..15
+    const int g = lane & 7;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 64);
+    const uint32_t sP_u = smem_u32(sP);
+    // depthwise role
+    const int cg = ct & 7;                       // channels 4*cg .. 4*cg+3
+    const int w = ct >> 3;                       // output column 0..31
+    float4 sc1 = __ldg(reinterpret_cast<const float4*>(p.scale1 + 4 * cg));
+    float4 sh1 = __ldg(reinterpret_cast<const float4*>(p.shift1 + 4 * cg));
+    const uint32_t rdE = sP_u + (uint32_t)O_BYTES + entry_off(w, cg >> 1) + (uint32_t)((cg & 1) * 8);
+    const uint32_t rdO0 = sP_u + entry_off(w, cg >> 1) + (uint32_t)((cg & 1) * 8);
+    const uint32_t rdO1 = sP_u + entry_off(w + 1, cg >> 1) + (uint32_t)((cg & 1) * 8);
+    f32x2 accA[TH][2], accB[TH][2];
+#pragma unroll
+    for (int i = 0; i < TH; ++i) { accA[i][0] = accA[i][1] = 0ull; accB[i][0] = accB[i][1] = 0ull; }
+
+    int j = 0;
+    Jobs jobs(L0, L1, p.Dd);
+    while (jobs.next()) {
+      const int n = jobs.col / p.HT, ht = jobs.col - n * p.HT;
+      const int h0 = ht * TH;                    // first depthwise row of the tile
+      const uint32_t apar = (uint32_t)((j >> 1) & 1);
+      const int hs = 2 * h0 - 1 + row;           // stem row of this thread's slot
+      const bool row_ok = (hs >= 0) && (hs < p.Hs) && (row < 15);
+      // ---------------- phase A: both halves of the plane ----------------
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int buf = (j & 1) * 2 + c;
+        mbar_wait(&acc_full[buf], apar);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld_x32(lane_addr + (uint32_t)(buf * 128), v0);
+        tmem_ld_x32(lane_addr + (uint32_t)(buf * 128 + 32), v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        uint32_t out[32];
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          const float4 s = *reinterpret_cast<const float4*>(sSc0 + k);
+          const float4 b = *reinterpret_cast<const float4*>(sSh0 + k);
+          out[(k >> 1)] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[k]), s.x), b.x)),
+                                      relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[k + 1]), s.y), b.y)));
+          out[(k >> 1) + 1] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[k + 2]), s.z), b.z)),
+                                          relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[k + 3]), s.w), b.w)));
+          out[16 + (k >> 1)] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[k]), s.x), b.x)),
+                                           relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[k + 1]), s.y), b.y)));
+          out[16 + (k >> 1) + 1] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[k + 2]), s.z), b.z)),
+                                               relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[k + 3]), s.w), b.w)));
+        }
+        if (!row_ok) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) out[k] = 0u;
+        }
+        // the depthwise pass of the previous job must be done with the plane buffer
+        if (c == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (row < 15) {
+          // voxel 32c + 4g + 2hh (even column -> E[16c + 2g + hh]), voxel + 1 (odd column -> O[16c + 2g + hh + 1])
+          const int e = 16 * c + 2 * g + hh;
+          const uint32_t rowb = sP_u + (uint32_t)(row * ROW_BYTES);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (uint32_t)O_BYTES + entry_off(e, c4)),
+                         "r"(out[4 * c4]), "r"(out[4 * c4 + 1]), "r"(out[4 * c4 + 2]), "r"(out[4 * c4 + 3])
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + entry_off(e + 1, c4)),
+                         "r"(out[16 + 4 * c4]), "r"(out[16 + 4 * c4 + 1]), "r"(out[16 + 4 * c4 + 2]), "r"(out[16 + 4 * c4 + 3])
+                         : "memory");
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the plane is complete
+      // ---------------- phase B: this plane's taps ----------------
+      {
+        const int role = jobs.role;
+        const bool toB = (role == 2) && jobs.cont;
+        // kdA: the kd whose taps go to accA (role 0: kd 0, role 1: kd 1, role 2: kd 2); accB always gets kd 0
+        const float* wA = sWd + (role * 9) * 32 + 4 * cg;
+        const float* wB = sWd + 4 * cg;
+        f32x2 wa[9][2], wb[9][2];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float4 a = *reinterpret_cast<const float4*>(wA + t * 32);
+          wa[t][0] = pack_f32x2(a.x, a.y); wa[t][1] = pack_f32x2(a.z, a.w);
+          const float4 b = *reinterpret_cast<const float4*>(wB + t * 32);
+          wb[t][0] = pack_f32x2(b.x, b.y); wb[t][1] = pack_f32x2(b.z, b.w);
+        }
+#pragma unroll
+        for (int r = 0; r < 15; ++r) {
+          uint2 u0, u1, u2;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u0.x), "=r"(u0.y) : "r"(rdO0 + (uint32_t)(r * ROW_BYTES)));
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u1.x), "=r"(u1.y) : "r"(rdE + (uint32_t)(r * ROW_BYTES)));
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u2.x), "=r"(u2.y) : "r"(rdO1 + (uint32_t)(r * ROW_BYTES)));
+          const f32x2 x0[2] = {bf16x2_to_f32x2(u0.x), bf16x2_to_f32x2(u0.y)};
+          const f32x2 x1[2] = {bf16x2_to_f32x2(u1.x), bf16x2_to_f32x2(u1.y)};
+          const f32x2 x2[2] = {bf16x2_to_f32x2(u2.x), bf16x2_to_f32x2(u2.y)};
+          // stem row r is tap kh = r - 2i of output row i: even r -> (i = r/2, kh 0) and (i = r/2 - 1, kh 2); odd r -> kh 1.
+          // Output row i sees its kh = 0, 1, 2 rows in ascending r: (kd, kh, kw) order as in the stand-alone kernels.
+          if ((r & 1) == 0) {
+            if (r >= 2) {
+              const int i = r / 2 - 1;
+              ffma2(accA[i][0], x0[0], wa[6][0]); ffma2(accA[i][1], x0[1], wa[6][1]);
+              ffma2(accA[i][0], x1[0], wa[7][0]); ffma2(accA[i][1], x1[1], wa[7][1]);
+              ffma2(accA[i][0], x2[0], wa[8][0]); ffma2(accA[i][1], x2[1], wa[8][1]);
+              if (toB) {
+                ffma2(accB[i][0], x0[0], wb[6][0]); ffma2(accB[i][1], x0[1], wb[6][1]);
+                ffma2(accB[i][0], x1[0], wb[7][0]); ffma2(accB[i][1], x1[1], wb[7][1]);
+                ffma2(accB[i][0], x2[0], wb[8][0]); ffma2(accB[i][1], x2[1], wb[8][1]);
+              }
+            }
+            if (r <= 12) {
+              const int i = r / 2;
+              ffma2(accA[i][0], x0[0], wa[0][0]); ffma2(accA[i][1], x0[1], wa[0][1]);
+              ffma2(accA[i][0], x1[0], wa[1][0]); ffma2(accA[i][1], x1[1], wa[1][1]);
+              ffma2(accA[i][0], x2[0], wa[2][0]); ffma2(accA[i][1], x2[1], wa[2][1]);
+              if (toB) {
+                ffma2(accB[i][0], x0[0], wb[0][0]); ffma2(accB[i][1], x0[1], wb[0][1]);
+                ffma2(accB[i][0], x1[0], wb[1][0]); ffma2(accB[i][1], x1[1], wb[1][1]);
+                ffma2(accB[i][0], x2[0], wb[2][0]); ffma2(accB[i][1], x2[1], wb[2][1]);
+              }
+            }
+          } else {
+            const int i = r / 2;
+            ffma2(accA[i][0], x0[0], wa[3][0]); ffma2(accA[i][1], x0[1], wa[3][1]);
+            ffma2(accA[i][0], x1[0], wa[4][0]); ffma2(accA[i][1], x1[1], wa[4][1]);
+            ffma2(accA[i][0], x2[0], wa[5][0]); ffma2(accA[i][1], x2[1], wa[5][1]);
+            if (toB) {
+              ffma2(accB[i][0], x0[0], wb[3][0]); ffma2(accB[i][1], x0[1], wb[3][1]);
+              ffma2(accB[i][0], x1[0], wb[4][0]); ffma2(accB[i][1], x1[1], wb[4][1]);
+              ffma2(accB[i][0], x2[0], wb[5][0]); ffma2(accB[i][1], x2[1], wb[5][1]);
+            }
+          }
+        }
+        if (role == 2) {
+          // depthwise plane d of this tile is complete
+          __nv_bfloat16* o = p.y + ((((long long)n * p.Dd + jobs.d) * p.Hd + h0) * 32 + w) * 32 + 4 * cg;
+#pragma unroll
+          for (int i = 0; i < TH; ++i) {
+            if (h0 + i < p.Hd) {
+              float a0, a1, a2, a3;
+              unpack_f32x2(accA[i][0], a0, a1);
+              unpack_f32x2(accA[i][1], a2, a3);
+              a0 = relu_nan1(__fadd_rn(__fmul_rn(a0, sc1.x), sh1.x));
+              a1 = relu_nan1(__fadd_rn(__fmul_rn(a1, sc1.y), sh1.y));
+              a2 = relu_nan1(__fadd_rn(__fmul_rn(a2, sc1.z), sh1.z));
+              a3 = relu_nan1(__fadd_rn(__fmul_rn(a3, sc1.w), sh1.w));
+              *reinterpret_cast<uint2*>(o + (long long)i * 32 * 32) = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
+            }
+            accA[i][0] = accB[i][0]; accA[i][1] = accB[i][1];
+            accB[i][0] = 0ull; accB[i][1] = 0ull;
+          }
+        }
+      }
+      ++j;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int CIN>
+static int launch_stem_dw(const void* x, const StemDwParams& p, cudaStream_t st) {
+  using namespace sdw;
+  CUtensorMap tm;
+  {
+    const uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.N * CIN};
+    const uint64_t strides[3] = {(uint64_t)p.W * 2, (uint64_t)p.W * p.H * 2, (uint64_t)p.W * p.H * p.D * 2};
+    const uint32_t box[4] = {72u, 31u, 1u, (uint32_t)CIN};      // 16 input rows, every second one
+    const uint32_t estr[4] = {1u, 2u, 1u, 1u};
+    if (make_tma_bf16(&tm, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, estr)) return SSD3D_ERR_TMA;
+  }
+  const size_t smem = 1024 + (size_t)PLANE_BYTES + (size_t)9 * CIN * B_BYTES + (size_t)NU * 3 * CIN * CI_BYTES +
+                      27 * 32 * 4 + 256 + 256;
+  if (smem > 232448) return SSD3D_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(stem_dw_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  long long grid = persistent_sms();
+  if (grid > p.steps) grid = p.steps;
+  SSD3D_LAUNCH_PDL((stem_dw_kernel<CIN>), dim3((unsigned)grid), dim3(THREADS), smem, st, tm, p);
+  return SSD3D_OK;
+}
+
+}  // namespace ssd3d
+
+using namespace ssd3d;
+
+// 1 when stem + first depthwise conv can run as one kernel: bf16 volumes, Cin <= 2, rows of 128 voxels, even stem map
+extern "C" int ssd3d_stem_dw_fused_supported(int x_is_bf16, int Cin, int D, int H, int W, int stride_d) {
+  if (!x_is_bf16 || Cin < 1 || Cin > 2 || W != 128) return 0;
+  if (stride_d != 1 && stride_d != 2) return 0;
+  if (H < 2 || D < 2 || (H & 1)) return 0;
+  const int Ds = (D - 1) / stride_d + 1, Hs = (H - 1) / 2 + 1;
+  return ((Ds & 1) == 0 && (Hs & 1) == 0) ? 1 : 0;
+}
+
+extern "C" int ssd3d_stem_dw_fused(const void* x, int x_is_bf16, const void* w_stem, const float* scale0,
+                                   const float* shift0, const void* w_dw, const float* scale1, const float* shift1,
+                                   void* y, int N, int Cin, int D, int H, int W, int stride_d, void* stream) {
+  if (!x || !w_stem || !scale0 || !shift0 || !w_dw || !scale1 || !shift1 || !y || N <= 0) return SSD3D_ERR_ARG;
+  if (!ssd3d_stem_dw_fused_supported(x_is_bf16, Cin, D, H, W, stride_d)) return SSD3D_ERR_UNSUPPORTED;
+  StemDwParams p{};
+  p.N = N; p.D = D; p.H = H; p.W = W; p.sd = stride_d;
+  p.Ds = (D - 1) / stride_d + 1; p.Hs = (H - 1) / 2 + 1;
+  p.Dd = (p.Ds - 1) / 2 + 1; p.Hd = (p.Hs - 1) / 2 + 1;
+  p.HT = (p.Hd + sdw::TH - 1) / sdw::TH;
+  const long long steps = (long long)N * p.HT * p.Dd;
+  if (steps > 0x3fffffffll) return SSD3D_ERR_UNSUPPORTED;
+  p.steps = (int)steps;
+  p.kpad = (27 * Cin <= 64) ? 64 : 128;
+  p.wt = static_cast<const __nv_bfloat16*>(w_stem);
+  p.scale0 = scale0; p.shift0 = shift0;
+  p.wd = static_cast<const __nv_bfloat16*>(w_dw);
+  p.scale1 = scale1; p.shift1 = shift1;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return Cin == 1 ? launch_stem_dw<1>(x, p, st) : launch_stem_dw<2>(x, p, st);
+}

@@ -662,12 +662,34 @@ extern "C" int ssd3d_stem_conv_affine_simt(const void* x, int x_is_bf16, const v
                                            const float* shift, void* y, int N, int Cin, int D, int H, int W,
                                            int stride_d, int relu, void* stream);
 
+extern "C" int ssd3d_stem_conv_affine_tz(const void* x, int x_is_bf16, const void* w, const float* scale,
+                                         const float* shift, void* y, int N, int Cin, int D, int H, int W, int stride_d,
+                                         int relu, void* stream);
+extern "C" int ssd3d_stem_tz_supported(int x_is_bf16, int Cin, int W);
+
+// The banded-B kernel (conv_stem_tz.cu) runs at the same speed as the gather kernel at the benchmark shape (both sit
+// on the 3.9 TB/s HBM write ceiling: 44.5 vs 45.5 us) and is slower when Wo is not a multiple of its 32-voxel row
+// slots (Wo = 48: 53 vs 37 us), so it is opt-in here (SSD3D_STEM_TZ=1); it is the front half of the fused
+// stem + depthwise kernel (conv_stem_dw.cu), where it pays.
+static bool stem_tz_wanted(int x_is_bf16, int Cin, int W) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("SSD3D_STEM_TZ");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on && ssd3d_stem_tz_supported(x_is_bf16, Cin, W) && (W - 1) / 2 + 1 >= 24;
+}
+
 extern "C" int ssd3d_stem_conv_affine(const void* x, int x_is_bf16, const void* w, const float* scale,
                                       const float* shift, void* y, int N, int Cin, int D, int H, int W, int stride_d,
                                       int relu, void* stream) {
   if (!x || !w || !scale || !shift || !y || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
   if (stride_d != 1 && stride_d != 2) return SSD3D_ERR_ARG;
   if (Cin < 1 || Cin > 4) return SSD3D_ERR_UNSUPPORTED;
+  if (stem_tz_wanted(x_is_bf16, Cin, W)) {
+    const int rc = ssd3d_stem_conv_affine_tz(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, relu, stream);
+    if (rc != SSD3D_ERR_UNSUPPORTED) return rc;
+  }
   if (ssd3d_stem_tc_supported(x_is_bf16, Cin, W)) {
     const int rc = stem_tc(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, relu,
                            static_cast<cudaStream_t>(stream));

@@ -62,9 +62,12 @@ def _alloc_ndhwc(n, c, d, h, w, device) -> torch.Tensor:
 
 
 def stem_conv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor,
-                      stride_d: int, force_simt: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      stride_d: int, force_simt: bool = False, out: Optional[torch.Tensor] = None,
+                      kernel: Optional[str] = None) -> torch.Tensor:
     """x (N,Cin,D,H,W) contiguous fp32|bf16 -> (N,32,Do,Ho,Wo) channels-last bf16.  mobilenet.py:28-30.
-    tcgen05 implicit GEMM when TMA can address the rows, CUDA-core kernel otherwise (or when forced)."""
+    The library picks the kernel: banded-B tcgen05 GEMM on raw TMA rows (bf16 volumes, Cin <= 2), gather-based
+    tcgen05 implicit GEMM when TMA can address the rows, CUDA-core kernel otherwise.  ``kernel`` = "tz" | "tc" |
+    "simt" forces one (tests; "tz" raises when it does not apply)."""
     _need_cuda(x, w_packed, scale, shift)
     if x.dim() != 5:
         raise RuntimeError("expected (N, C, D, H, W) input")
@@ -75,10 +78,43 @@ def stem_conv_bn_relu(x: torch.Tensor, w_packed: torch.Tensor, scale: torch.Tens
     y = out if out is not None else _alloc_ndhwc(n, 32, conv_out(d, stride_d), conv_out(h, 2), conv_out(w, 2),
                                                  x.device)
     lib = _lib.load()
-    fn = lib.ssd3d_stem_conv_bn_relu_simt if force_simt else lib.ssd3d_stem_conv_bn_relu
+    if kernel in ("tz", "tc"):
+        fn = lib.ssd3d_stem_conv_affine_tz if kernel == "tz" else lib.ssd3d_stem_conv_affine_tc
+        rc = fn(x.data_ptr(), int(x.dtype == BF16), w_packed.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                y.data_ptr(), n, cin, d, h, w, stride_d, 1, _stream())
+        _lib.check(rc, "ssd3d_stem_conv_affine_" + kernel)
+        LAUNCHES[0] += 1
+        return y
+    fn = lib.ssd3d_stem_conv_bn_relu_simt if (force_simt or kernel == "simt") else lib.ssd3d_stem_conv_bn_relu
     rc = fn(x.data_ptr(), int(x.dtype == BF16), w_packed.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(),
             n, cin, d, h, w, stride_d, _stream())
     _lib.check(rc, "ssd3d_stem_conv_bn_relu")
+    LAUNCHES[0] += 1
+    return y
+
+
+def stem_dw_fused_supported(x: torch.Tensor, stride_d: int) -> bool:
+    """True when stem + first depthwise conv can run as one kernel on ``x`` (N, Cin, D, H, W)."""
+    if x.dim() != 5 or not x.is_cuda:
+        return False
+    n, cin, d, h, w = x.shape
+    return bool(_lib.load().ssd3d_stem_dw_fused_supported(int(x.dtype == BF16), cin, d, h, w, stride_d))
+
+
+def stem_dw_bn_relu(x: torch.Tensor, w_stem: torch.Tensor, scale0: torch.Tensor, shift0: torch.Tensor,
+                    w_dw: torch.Tensor, scale1: torch.Tensor, shift1: torch.Tensor, stride_d: int,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stem conv_bn (mobilenet.py:28-30) + depthwise 3x3x3 stride 2 + BN + ReLU of the first Block
+    (mobilenet.py:38,44) in one kernel: x (N,Cin,D,H,128) bf16 -> (N,32,Dd,Hd,32) channels-last bf16."""
+    _need_cuda(x, w_stem, scale0, shift0, w_dw, scale1, shift1)
+    x = x.contiguous()
+    n, cin, d, h, w = x.shape
+    ds, hs, ws = conv_out(d, stride_d), conv_out(h, 2), conv_out(w, 2)
+    y = out if out is not None else _alloc_ndhwc(n, 32, conv_out(ds, 2), conv_out(hs, 2), conv_out(ws, 2), x.device)
+    rc = _lib.load().ssd3d_stem_dw_fused(x.data_ptr(), int(x.dtype == BF16), w_stem.data_ptr(), scale0.data_ptr(),
+                                         shift0.data_ptr(), w_dw.data_ptr(), scale1.data_ptr(), shift1.data_ptr(),
+                                         y.data_ptr(), n, cin, d, h, w, stride_d, _stream())
+    _lib.check(rc, "ssd3d_stem_dw_fused")
     LAUNCHES[0] += 1
     return y
 
