@@ -680,6 +680,15 @@ static bool stem_tz_wanted(int x_is_bf16, int Cin, int W) {
   return on && ssd3d_stem_tz_supported(x_is_bf16, Cin, W) && (W - 1) / 2 + 1 >= 24;
 }
 
+extern "C" int ssd3d_stem_conv_affine_tc(const void* x, int x_is_bf16, const void* w, const float* scale,
+                                         const float* shift, void* y, int N, int Cin, int D, int H, int W, int stride_d,
+                                         int relu, void* stream) {
+  if (!x || !w || !scale || !shift || !y || N <= 0 || D <= 0 || H <= 0 || W <= 0) return SSD3D_ERR_ARG;
+  if (stride_d != 1 && stride_d != 2) return SSD3D_ERR_ARG;
+  if (!ssd3d_stem_tc_supported(x_is_bf16, Cin, W)) return SSD3D_ERR_UNSUPPORTED;
+  return stem_tc(x, x_is_bf16, w, scale, shift, y, N, Cin, D, H, W, stride_d, relu, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int ssd3d_stem_conv_affine(const void* x, int x_is_bf16, const void* w, const float* scale,
                                       const float* shift, void* y, int N, int Cin, int D, int H, int W, int stride_d,
                                       int relu, void* stream) {
