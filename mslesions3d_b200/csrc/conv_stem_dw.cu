@@ -20,7 +20,8 @@
 //     fma.rn.f32x2: bit-identical to the stand-alone depthwise kernels on the same stem values.
 //   * a CTA marches along D through a contiguous run of (image, 7-row tile, plane d) steps (8.6 per SM for the
 //     benchmark); a run that starts at d > 0 first computes stem plane 2d-1 (its kd=0 share).
-//   * warp roles: warp 0 = TMA producer (six (half, kd) units of 3 (kd,kh) boxes = one plane job, refilled unit by unit), warp 1 = UMMA issuer,
+//   * warp roles: warp 0 = TMA producer (ring of nine (half, kd) units = 1.5 plane jobs; a unit holds the 17 even and
+//     16 odd input rows of the tile once: tap kh = 2 reads the even rows one slot further), warp 1 = UMMA issuer,
 //     warps 2..9 = epilogue + depthwise.  The UMMAs of job j+1 run while the CUDA cores finish job j.
 // Requirements: bf16 volumes, Cin <= 2, W = 128 (stem rows of 64 voxels), even stem H and D.
 #include "common.cuh"
@@ -42,19 +43,25 @@ struct StemDwParams {
   const float* scale1;         // depthwise BN
   const float* shift1;
   __nv_bfloat16* y;            // (N, Dd, Hd, 32, 32)
+  float one;                   // 1.0f (a run-time value on purpose: see fadd2)
 };
 
 namespace sdw {
 
 constexpr int SLOT_BYTES = 144;
-constexpr int CI_BYTES = 16 * SLOT_BYTES;     // 2304: 16 row slots of one input channel
+// One (half c, kd) unit of the A ring holds, per input channel, the 33 input rows the 16 stem rows of the tile read:
+// the 17 even ones (taps kh = 0 and, one slot further, kh = 2) and the 16 odd ones (kh = 1).
+constexpr int EVEN_BYTES = 2560;              // 17 x 144 = 2448, padded to a multiple of 128 (TMA destination)
+constexpr int ODD_BYTES = 16 * SLOT_BYTES;    // 2304
+constexpr int CI_BYTES = EVEN_BYTES + ODD_BYTES;   // 4864
+constexpr int CI_TX = 17 * SLOT_BYTES + ODD_BYTES; // bytes TMA really writes per input channel
 constexpr int B_BYTES = 4096;
-constexpr int NU = 6;                         // (half, kd) units of 3 boxes: exactly one plane job
+constexpr int NU = 9;                         // ring of units: 1.5 plane jobs
 constexpr int THREADS = 320;
 constexpr int TH = 7;                         // depthwise rows per tile
 constexpr int O_BYTES = 17 * 128;             // 33 odd-column entries of 64 B
 constexpr int ROW_BYTES = 33 * 128;           // O then E (32 entries)
-constexpr int PLANE_BYTES = 16 * ROW_BYTES;   // 67584 (row 15 is never read)
+constexpr int PLANE_BYTES = 15 * ROW_BYTES;   // 63360: the 15 stem rows a 7-row tile reads
 
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {
@@ -112,6 +119,33 @@ __device__ __forceinline__ void unpack_f32x2(f32x2 v, float& lo, float& hi) {
   hi = __uint_as_float(b);
 }
 
+// Separately rounded packed multiply and add.  ptxas turns mul.rn.f32x2 + add.rn.f32x2 (and fma(a,b,-0) followed
+// by fma(t,1,c), with or without -fmad=false) into ONE FFMA2 -- a contraction the .rn modifiers should forbid, seen
+// in the SASS and as 1-ulp flips against the stand-alone kernels.  The add is therefore an fma with a multiplier
+// of 1.0 that ptxas cannot see through (read from shared memory at run time): t * 1 + b rounds exactly like add.rn.
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b, f32x2 one) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(one), "l"(b));
+  return r;
+}
+// (separately rounded) a * s + b on two channels, rounded to bf16, then ReLU on the packed pair: rounding is
+// monotonic and keeps the sign, so relu(round(v)) == round(relu(v)); max.NaN propagates NaN like torch.relu
+__device__ __forceinline__ uint32_t bn_relu_pack(uint32_t a_lo, uint32_t a_hi, f32x2 s, f32x2 b, f32x2 one) {
+  f32x2 a;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(a_lo), "r"(a_hi));
+  const f32x2 v = fadd2(fmul2(a, s), b, one);
+  uint32_t lo, hi, r;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  asm("max.NaN.bf16x2 %0, %0, %1;" : "+r"(r) : "r"(0u));
+  return r;
+}
+
 // byte offset of 16-byte unit c4 (0..3) of entry e inside a de-interleaved column array (O or E) of the plane
 __device__ __forceinline__ uint32_t entry_off(int e, int c4) {
   const int line = e >> 1;
@@ -141,15 +175,58 @@ struct Jobs {
   }
 };
 
+// The taps of one stem plane (15 rows in shared memory) for this thread's 4 channels and output column: kd share
+// `wa` into accA and, when TOB, the kd = 0 share `wb` into accB.  Stem row r is tap kh = r - 2i of output row i:
+// even r -> (i = r/2, kh 0) and (i = r/2 - 1, kh 2); odd r -> kh 1.  Output row i sees its kh = 0, 1, 2 rows in
+// ascending r: (kd, kh, kw) order as in the stand-alone depthwise kernels.
+template <bool TOB>
+__device__ __forceinline__ void dw_plane(f32x2 (&accA)[TH][2], f32x2 (&accB)[TH][2], const float* wA, const float* wB,
+                                         uint32_t rdO0, uint32_t rdE, uint32_t rdO1) {
+  f32x2 wa[9][2], wb[9][2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(wA + t * 32);
+    wa[t][0] = a.x; wa[t][1] = a.y;
+    if (TOB) {
+      const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(wB + t * 32);
+      wb[t][0] = b.x; wb[t][1] = b.y;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 15; ++r) {
+    uint2 u0, u1, u2;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u0.x), "=r"(u0.y) : "r"(rdO0 + (uint32_t)(r * ROW_BYTES)));
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u1.x), "=r"(u1.y) : "r"(rdE + (uint32_t)(r * ROW_BYTES)));
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u2.x), "=r"(u2.y) : "r"(rdO1 + (uint32_t)(r * ROW_BYTES)));
+    const f32x2 x[3][2] = {{bf16x2_to_f32x2(u0.x), bf16x2_to_f32x2(u0.y)},
+                           {bf16x2_to_f32x2(u1.x), bf16x2_to_f32x2(u1.y)},
+                           {bf16x2_to_f32x2(u2.x), bf16x2_to_f32x2(u2.y)}};
+#pragma unroll
+    for (int kh = 2; kh >= 0; --kh) {            // kh = 2 of row i-1 first: it closes that row's (kd) share
+      if (((r - kh) & 1) != 0 || r - kh < 0 || (r - kh) / 2 >= TH) continue;
+      const int i = (r - kh) / 2;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        ffma2(accA[i][0], x[kw][0], wa[kh * 3 + kw][0]);
+        ffma2(accA[i][1], x[kw][1], wa[kh * 3 + kw][1]);
+        if (TOB) {
+          ffma2(accB[i][0], x[kw][0], wb[kh * 3 + kw][0]);
+          ffma2(accB[i][1], x[kw][1], wb[kh * 3 + kw][1]);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace sdw
 
 template <int CIN>
-__global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_constant__ CUtensorMap tmE,
+                                                                 const __grid_constant__ CUtensorMap tmO,
                                                                  const StemDwParams p) {
   using namespace sdw;
   constexpr int NT = 9 * CIN;
-  constexpr int BOX_BYTES = CIN * CI_BYTES;          // one (kd,kh) box of one half: [ci][16 rows][72]
-  constexpr int UNIT_BYTES = 3 * BOX_BYTES;
+  constexpr int UNIT_BYTES = CIN * CI_BYTES;         // one (half c, kd) unit: [ci][17 even rows | 16 odd rows][72]
   constexpr uint32_t TMEM_COLS = 512;                // four 128-column accumulators
 
   extern __shared__ uint8_t sdw_raw[];
@@ -161,7 +238,8 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
   float* sWd = reinterpret_cast<float*>(sA + NU * UNIT_BYTES);   // depthwise weights fp32 [27][32]
   float* sSc0 = sWd + 27 * 32;                                   // stem BN scale[32], shift[32]
   float* sSh0 = sSc0 + 32;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sSh0 + 32);
+  float* sOne = sSh0 + 32;                                       // {1, 1}: see fadd2
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOne + 2);
   uint64_t* empty = full + NU;
   uint64_t* acc_full = empty + NU;                               // [4]
   uint64_t* acc_empty = acc_full + 4;                            // [4]
@@ -171,7 +249,8 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
   const int warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmE);
+    tma_prefetch_desc(&tmO);
     for (int s = 0; s < NU; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     fence_barrier_init();
@@ -188,6 +267,7 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
   for (int i = tid; i < (PLANE_BYTES + NT * B_BYTES) / 16; i += THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < 27 * 32; i += THREADS) sWd[i] = __bfloat162float(p.wd[i]);
   if (tid < 32) { sSc0[tid] = __ldg(p.scale0 + tid); sSh0[tid] = __ldg(p.shift0 + tid); }
+  if (tid < 2) sOne[tid] = p.one;
   __syncthreads();
   for (int i = tid; i < NT * 3 * 32; i += THREADS) {
     const int co = i & 31, tk = i >> 5;
@@ -211,27 +291,29 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
   if (warp == 0) {
     // ===================== TMA producer =====================
     const uint32_t sA_u = smem_u32(sA);
-    int j = 0;
+    int u = 0;
+    uint32_t ph = 1;                                   // parity to wait for on empty[u]: the first lap passes
     Jobs jobs(L0, L1, p.Dd);
     while (jobs.next()) {
       const int n = jobs.col / p.HT, ht = jobs.col - n * p.HT;
       const int ch = 4 * (ht * TH) - 3;                // input row of stem row 2*h0 - 1, tap kh = 0
       const int cd = p.sd * jobs.P - 1;
-      const uint32_t ph = (uint32_t)(j & 1);
-#pragma unroll
-      for (int u = 0; u < 6; ++u) {                    // unit = (half c, kd), fixed place in shared memory
-        const int c = u / 3, kd = u - 3 * c;
-        mbar_wait(&empty[u], ph ^ 1u);
+#pragma unroll 1
+      for (int cu = 0; cu < 6; ++cu) {                 // unit = (half c, kd)
+        const int c = cu >= 3 ? 1 : 0, kd = cu - 3 * c;
+        mbar_wait(&empty[u], ph);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[u], (uint32_t)UNIT_BYTES);
+          mbar_arrive_expect_tx(&full[u], (uint32_t)(CIN * CI_TX));
+          const uint32_t dst = sA_u + (uint32_t)(u * UNIT_BYTES);
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
-            tma_load_4d(sA_u + (uint32_t)(u * UNIT_BYTES + kh * BOX_BYTES), &tmX, &full[u], 64 * c - 8, ch + kh, cd + kd,
-                        n * CIN);
+          for (int ci = 0; ci < CIN; ++ci) {
+            tma_load_4d(dst + ci * CI_BYTES, &tmE, &full[u], 64 * c - 8, ch, cd + kd, n * CIN + ci);
+            tma_load_4d(dst + ci * CI_BYTES + EVEN_BYTES, &tmO, &full[u], 64 * c - 8, ch + 1, cd + kd, n * CIN + ci);
+          }
         }
         __syncwarp();
+        if (++u == NU) { u = 0; ph ^= 1u; }
       }
-      ++j;
     }
   } else if (warp == 1) {
     // ===================== UMMA issuer =====================
@@ -239,10 +321,11 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
     const uint64_t da0 = desc_k_nosw(smem_u32(sA), 16u, (uint32_t)SLOT_BYTES);
     const uint64_t db0 = desc_k_nosw(smem_u32(sB), 128u, 256u);
     int j = 0;
+    int u = 0;
+    uint32_t ph = 0;                                   // parity to wait for on full[u]
     Jobs jobs(L0, L1, p.Dd);
     while (jobs.next()) {
       const uint32_t apar = (uint32_t)((j >> 1) & 1);
-      const uint32_t ph = (uint32_t)(j & 1);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int buf = (j & 1) * 2 + c;
@@ -250,20 +333,24 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
         const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd) {
-          const int u = c * 3 + kd;
           mbar_wait(&full[u], ph);
           tc_fence_after();
           if (elect_one()) {
+            const uint64_t da = da0 + (uint64_t)((uint32_t)(u * UNIT_BYTES) >> 4);
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
+            for (int kh = 0; kh < 3; ++kh) {
+              // kh = 0: even rows from slot 0, kh = 1: odd rows, kh = 2: even rows from slot 1
+              const int off = kh == 0 ? 0 : (kh == 1 ? EVEN_BYTES : SLOT_BYTES);
 #pragma unroll
               for (int ci = 0; ci < CIN; ++ci)
-                umma_bf16_ss(dcol, da0 + (uint64_t)((u * UNIT_BYTES + kh * BOX_BYTES + ci * CI_BYTES) >> 4),
+                umma_bf16_ss(dcol, da + (uint64_t)((off + ci * CI_BYTES) >> 4),
                              db0 + (uint64_t)(((ci * 9 + kd * 3 + kh) * B_BYTES) >> 4), idesc, (kd | kh | ci) != 0 ? 1u : 0u);
+            }
             umma_commit(&empty[u]);
             if (kd == 2) umma_commit(&acc_full[buf]);
           }
           __syncwarp();
+          if (++u == NU) { u = 0; ph ^= 1u; }
         }
       }
       ++j;
@@ -286,6 +373,7 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
     const uint32_t rdE = sP_u + (uint32_t)O_BYTES + entry_off(w, cg >> 1) + (uint32_t)((cg & 1) * 8);
     const uint32_t rdO0 = sP_u + entry_off(w, cg >> 1) + (uint32_t)((cg & 1) * 8);
     const uint32_t rdO1 = sP_u + entry_off(w + 1, cg >> 1) + (uint32_t)((cg & 1) * 8);
+    const f32x2 one2 = *reinterpret_cast<const f32x2*>(sOne);
     f32x2 accA[TH][2], accB[TH][2];
 #pragma unroll
     for (int i = 0; i < TH; ++i) { accA[i][0] = accA[i][1] = 0ull; accB[i][0] = accB[i][1] = 0ull; }
@@ -314,16 +402,12 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
         uint32_t out[32];
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
-          const float4 s = *reinterpret_cast<const float4*>(sSc0 + k);
-          const float4 b = *reinterpret_cast<const float4*>(sSh0 + k);
-          out[(k >> 1)] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[k]), s.x), b.x)),
-                                      relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[k + 1]), s.y), b.y)));
-          out[(k >> 1) + 1] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[k + 2]), s.z), b.z)),
-                                          relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[k + 3]), s.w), b.w)));
-          out[16 + (k >> 1)] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[k]), s.x), b.x)),
-                                           relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[k + 1]), s.y), b.y)));
-          out[16 + (k >> 1) + 1] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[k + 2]), s.z), b.z)),
-                                               relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[k + 3]), s.w), b.w)));
+          const ulonglong2 sc = *reinterpret_cast<const ulonglong2*>(sSc0 + k);
+          const ulonglong2 sh = *reinterpret_cast<const ulonglong2*>(sSh0 + k);
+          out[(k >> 1)] = bn_relu_pack(v0[k], v0[k + 1], sc.x, sh.x, one2);
+          out[(k >> 1) + 1] = bn_relu_pack(v0[k + 2], v0[k + 3], sc.y, sh.y, one2);
+          out[16 + (k >> 1)] = bn_relu_pack(v1[k], v1[k + 1], sc.x, sh.x, one2);
+          out[16 + (k >> 1) + 1] = bn_relu_pack(v1[k + 2], v1[k + 3], sc.y, sh.y, one2);
         }
         if (!row_ok) {
 #pragma unroll
@@ -350,64 +434,11 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
       // ---------------- phase B: this plane's taps ----------------
       {
         const int role = jobs.role;
-        const bool toB = (role == 2) && jobs.cont;
-        // kdA: the kd whose taps go to accA (role 0: kd 0, role 1: kd 1, role 2: kd 2); accB always gets kd 0
+        // kd share of accA: role 0 -> kd 0, role 1 -> kd 1, role 2 -> kd 2; accB (the next output plane) gets kd 0
         const float* wA = sWd + (role * 9) * 32 + 4 * cg;
         const float* wB = sWd + 4 * cg;
-        f32x2 wa[9][2], wb[9][2];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float4 a = *reinterpret_cast<const float4*>(wA + t * 32);
-          wa[t][0] = pack_f32x2(a.x, a.y); wa[t][1] = pack_f32x2(a.z, a.w);
-          const float4 b = *reinterpret_cast<const float4*>(wB + t * 32);
-          wb[t][0] = pack_f32x2(b.x, b.y); wb[t][1] = pack_f32x2(b.z, b.w);
-        }
-#pragma unroll
-        for (int r = 0; r < 15; ++r) {
-          uint2 u0, u1, u2;
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u0.x), "=r"(u0.y) : "r"(rdO0 + (uint32_t)(r * ROW_BYTES)));
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u1.x), "=r"(u1.y) : "r"(rdE + (uint32_t)(r * ROW_BYTES)));
-          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u2.x), "=r"(u2.y) : "r"(rdO1 + (uint32_t)(r * ROW_BYTES)));
-          const f32x2 x0[2] = {bf16x2_to_f32x2(u0.x), bf16x2_to_f32x2(u0.y)};
-          const f32x2 x1[2] = {bf16x2_to_f32x2(u1.x), bf16x2_to_f32x2(u1.y)};
-          const f32x2 x2[2] = {bf16x2_to_f32x2(u2.x), bf16x2_to_f32x2(u2.y)};
-          // stem row r is tap kh = r - 2i of output row i: even r -> (i = r/2, kh 0) and (i = r/2 - 1, kh 2); odd r -> kh 1.
-          // Output row i sees its kh = 0, 1, 2 rows in ascending r: (kd, kh, kw) order as in the stand-alone kernels.
-          if ((r & 1) == 0) {
-            if (r >= 2) {
-              const int i = r / 2 - 1;
-              ffma2(accA[i][0], x0[0], wa[6][0]); ffma2(accA[i][1], x0[1], wa[6][1]);
-              ffma2(accA[i][0], x1[0], wa[7][0]); ffma2(accA[i][1], x1[1], wa[7][1]);
-              ffma2(accA[i][0], x2[0], wa[8][0]); ffma2(accA[i][1], x2[1], wa[8][1]);
-              if (toB) {
-                ffma2(accB[i][0], x0[0], wb[6][0]); ffma2(accB[i][1], x0[1], wb[6][1]);
-                ffma2(accB[i][0], x1[0], wb[7][0]); ffma2(accB[i][1], x1[1], wb[7][1]);
-                ffma2(accB[i][0], x2[0], wb[8][0]); ffma2(accB[i][1], x2[1], wb[8][1]);
-              }
-            }
-            if (r <= 12) {
-              const int i = r / 2;
-              ffma2(accA[i][0], x0[0], wa[0][0]); ffma2(accA[i][1], x0[1], wa[0][1]);
-              ffma2(accA[i][0], x1[0], wa[1][0]); ffma2(accA[i][1], x1[1], wa[1][1]);
-              ffma2(accA[i][0], x2[0], wa[2][0]); ffma2(accA[i][1], x2[1], wa[2][1]);
-              if (toB) {
-                ffma2(accB[i][0], x0[0], wb[0][0]); ffma2(accB[i][1], x0[1], wb[0][1]);
-                ffma2(accB[i][0], x1[0], wb[1][0]); ffma2(accB[i][1], x1[1], wb[1][1]);
-                ffma2(accB[i][0], x2[0], wb[2][0]); ffma2(accB[i][1], x2[1], wb[2][1]);
-              }
-            }
-          } else {
-            const int i = r / 2;
-            ffma2(accA[i][0], x0[0], wa[3][0]); ffma2(accA[i][1], x0[1], wa[3][1]);
-            ffma2(accA[i][0], x1[0], wa[4][0]); ffma2(accA[i][1], x1[1], wa[4][1]);
-            ffma2(accA[i][0], x2[0], wa[5][0]); ffma2(accA[i][1], x2[1], wa[5][1]);
-            if (toB) {
-              ffma2(accB[i][0], x0[0], wb[3][0]); ffma2(accB[i][1], x0[1], wb[3][1]);
-              ffma2(accB[i][0], x1[0], wb[4][0]); ffma2(accB[i][1], x1[1], wb[4][1]);
-              ffma2(accB[i][0], x2[0], wb[5][0]); ffma2(accB[i][1], x2[1], wb[5][1]);
-            }
-          }
-        }
+        if ((role == 2) && jobs.cont) dw_plane<true>(accA, accB, wA, wB, rdO0, rdE, rdO1);
+        else dw_plane<false>(accA, accB, wA, wB, rdO0, rdE, rdO1);
         if (role == 2) {
           // depthwise plane d of this tile is complete
           __nv_bfloat16* o = p.y + ((((long long)n * p.Dd + jobs.d) * p.Hd + h0) * 32 + w) * 32 + 4 * cg;
@@ -444,22 +475,24 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
 template <int CIN>
 static int launch_stem_dw(const void* x, const StemDwParams& p, cudaStream_t st) {
   using namespace sdw;
-  CUtensorMap tm;
+  CUtensorMap tmE, tmO;
   {
     const uint64_t dims[4] = {(uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.N * CIN};
     const uint64_t strides[3] = {(uint64_t)p.W * 2, (uint64_t)p.W * p.H * 2, (uint64_t)p.W * p.H * p.D * 2};
-    const uint32_t box[4] = {72u, 31u, 1u, (uint32_t)CIN};      // 16 input rows, every second one
     const uint32_t estr[4] = {1u, 2u, 1u, 1u};
-    if (make_tma_bf16(&tm, x, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE, estr)) return SSD3D_ERR_TMA;
+    const uint32_t boxE[4] = {72u, 33u, 1u, 1u};      // 17 even input rows of one channel
+    const uint32_t boxO[4] = {72u, 31u, 1u, 1u};      // 16 odd ones
+    if (make_tma_bf16(&tmE, x, 4, dims, strides, boxE, CU_TENSOR_MAP_SWIZZLE_NONE, estr)) return SSD3D_ERR_TMA;
+    if (make_tma_bf16(&tmO, x, 4, dims, strides, boxO, CU_TENSOR_MAP_SWIZZLE_NONE, estr)) return SSD3D_ERR_TMA;
   }
-  const size_t smem = 1024 + (size_t)PLANE_BYTES + (size_t)9 * CIN * B_BYTES + (size_t)NU * 3 * CIN * CI_BYTES +
+  const size_t smem = 1024 + (size_t)PLANE_BYTES + (size_t)9 * CIN * B_BYTES + (size_t)NU * CIN * CI_BYTES +
                       27 * 32 * 4 + 256 + 256;
   if (smem > 232448) return SSD3D_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(stem_dw_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   long long grid = persistent_sms();
   if (grid > p.steps) grid = p.steps;
-  SSD3D_LAUNCH_PDL((stem_dw_kernel<CIN>), dim3((unsigned)grid), dim3(THREADS), smem, st, tm, p);
+  SSD3D_LAUNCH_PDL((stem_dw_kernel<CIN>), dim3((unsigned)grid), dim3(THREADS), smem, st, tmE, tmO, p);
   return SSD3D_OK;
 }
 
@@ -495,6 +528,7 @@ extern "C" int ssd3d_stem_dw_fused(const void* x, int x_is_bf16, const void* w_s
   p.wd = static_cast<const __nv_bfloat16*>(w_dw);
   p.scale1 = scale1; p.shift1 = shift1;
   p.y = static_cast<__nv_bfloat16*>(y);
+  p.one = 1.0f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return Cin == 1 ? launch_stem_dw<1>(x, p, st) : launch_stem_dw<2>(x, p, st);
 }
