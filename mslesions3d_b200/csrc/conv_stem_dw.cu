@@ -56,8 +56,9 @@ constexpr int ODD_BYTES = 16 * SLOT_BYTES;    // 2304
 constexpr int CI_BYTES = EVEN_BYTES + ODD_BYTES;   // 4864
 constexpr int CI_TX = 17 * SLOT_BYTES + ODD_BYTES; // bytes TMA really writes per input channel
 constexpr int B_BYTES = 4096;
-constexpr int NU = 9;                         // ring of units: 1.5 plane jobs
-constexpr int THREADS = 320;
+constexpr int NU = 3;                         // ring of half-plane units (3 kd each): 1.5 plane jobs
+constexpr int CWARPS = 16;                     // epilogue + depthwise warps
+constexpr int THREADS = 64 + CWARPS * 32;     // + TMA producer warp + UMMA issuer warp
 constexpr int TH = 7;                         // depthwise rows per tile
 constexpr int O_BYTES = 17 * 128;             // 33 odd-column entries of 64 B
 constexpr int ROW_BYTES = 33 * 128;           // O then E (32 entries)
@@ -175,46 +176,43 @@ struct Jobs {
   }
 };
 
-// The taps of one stem plane (15 rows in shared memory) for this thread's 4 channels and output column: kd share
+// The taps of one stem plane (15 rows in shared memory) for this thread's 2 channels and output column: kd share
 // `wa` into accA and, when TOB, the kd = 0 share `wb` into accB.  Stem row r is tap kh = r - 2i of output row i:
 // even r -> (i = r/2, kh 0) and (i = r/2 - 1, kh 2); odd r -> kh 1.  Output row i sees its kh = 0, 1, 2 rows in
-// ascending r: (kd, kh, kw) order as in the stand-alone depthwise kernels.
+// ascending r: (kd, kh, kw) order as in the stand-alone depthwise kernels.  The three words of row r+1 are loaded
+// before the FMAs of row r (two compute warps per scheduler do not hide a shared-memory round trip by themselves).
 template <bool TOB>
-__device__ __forceinline__ void dw_plane(f32x2 (&accA)[TH][2], f32x2 (&accB)[TH][2], const float* wA, const float* wB,
+__device__ __forceinline__ void dw_plane(f32x2 (&accA)[TH], f32x2 (&accB)[TH], const float* wA, const float* wB,
                                          uint32_t rdO0, uint32_t rdE, uint32_t rdO1) {
-  f32x2 wa[9][2], wb[9][2];
+  f32x2 wa[9], wb[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
-    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(wA + t * 32);
-    wa[t][0] = a.x; wa[t][1] = a.y;
-    if (TOB) {
-      const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(wB + t * 32);
-      wb[t][0] = b.x; wb[t][1] = b.y;
-    }
+    wa[t] = *reinterpret_cast<const f32x2*>(wA + t * 32);
+    if (TOB) wb[t] = *reinterpret_cast<const f32x2*>(wB + t * 32);
   }
+  uint32_t u[3], un[3];
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u[0]) : "r"(rdO0));
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u[1]) : "r"(rdE));
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u[2]) : "r"(rdO1));
 #pragma unroll
   for (int r = 0; r < 15; ++r) {
-    uint2 u0, u1, u2;
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u0.x), "=r"(u0.y) : "r"(rdO0 + (uint32_t)(r * ROW_BYTES)));
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u1.x), "=r"(u1.y) : "r"(rdE + (uint32_t)(r * ROW_BYTES)));
-    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u2.x), "=r"(u2.y) : "r"(rdO1 + (uint32_t)(r * ROW_BYTES)));
-    const f32x2 x[3][2] = {{bf16x2_to_f32x2(u0.x), bf16x2_to_f32x2(u0.y)},
-                           {bf16x2_to_f32x2(u1.x), bf16x2_to_f32x2(u1.y)},
-                           {bf16x2_to_f32x2(u2.x), bf16x2_to_f32x2(u2.y)}};
+    if (r + 1 < 15) {
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(un[0]) : "r"(rdO0 + (uint32_t)((r + 1) * ROW_BYTES)));
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(un[1]) : "r"(rdE + (uint32_t)((r + 1) * ROW_BYTES)));
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(un[2]) : "r"(rdO1 + (uint32_t)((r + 1) * ROW_BYTES)));
+    }
+    const f32x2 x[3] = {bf16x2_to_f32x2(u[0]), bf16x2_to_f32x2(u[1]), bf16x2_to_f32x2(u[2])};
 #pragma unroll
-    for (int kh = 2; kh >= 0; --kh) {            // kh = 2 of row i-1 first: it closes that row's (kd) share
+    for (int kh = 2; kh >= 0; --kh) {
       if (((r - kh) & 1) != 0 || r - kh < 0 || (r - kh) / 2 >= TH) continue;
       const int i = (r - kh) / 2;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        ffma2(accA[i][0], x[kw][0], wa[kh * 3 + kw][0]);
-        ffma2(accA[i][1], x[kw][1], wa[kh * 3 + kw][1]);
-        if (TOB) {
-          ffma2(accB[i][0], x[kw][0], wb[kh * 3 + kw][0]);
-          ffma2(accB[i][1], x[kw][1], wb[kh * 3 + kw][1]);
-        }
+        ffma2(accA[i], x[kw], wa[kh * 3 + kw]);
+        if (TOB) ffma2(accB[i], x[kw], wb[kh * 3 + kw]);
       }
     }
+    u[0] = un[0]; u[1] = un[1]; u[2] = un[2];
   }
 }
 
@@ -226,7 +224,8 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
                                                                  const StemDwParams p) {
   using namespace sdw;
   constexpr int NT = 9 * CIN;
-  constexpr int UNIT_BYTES = CIN * CI_BYTES;         // one (half c, kd) unit: [ci][17 even rows | 16 odd rows][72]
+  constexpr int KD_BYTES = CIN * CI_BYTES;           // one kd of a unit: [ci][17 even rows | 16 odd rows][72]
+  constexpr int UNIT_BYTES = 3 * KD_BYTES;           // one half (c) of a plane job
   constexpr uint32_t TMEM_COLS = 512;                // four 128-column accumulators
 
   extern __shared__ uint8_t sdw_raw[];
@@ -247,49 +246,22 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const int L0 = (int)(((long long)blockIdx.x * p.steps) / gridDim.x);
+  const int L1 = (int)(((long long)(blockIdx.x + 1) * p.steps) / gridDim.x);
 
   if (tid == 0) {
     tma_prefetch_desc(&tmE);
     tma_prefetch_desc(&tmO);
     for (int s = 0; s < NU; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], CWARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
-  }
-  pdl_wait();
-  pdl_launch_dependents();
-
-  // ---- banded B operand, depthwise weights, stem BN; the plane buffer starts as zeros (column -1 stays zero) ----
-  for (int i = tid; i < (PLANE_BYTES + NT * B_BYTES) / 16; i += THREADS) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < 27 * 32; i += THREADS) sWd[i] = __bfloat162float(p.wd[i]);
-  if (tid < 32) { sSc0[tid] = __ldg(p.scale0 + tid); sSh0[tid] = __ldg(p.shift0 + tid); }
-  if (tid < 2) sOne[tid] = p.one;
-  __syncthreads();
-  for (int i = tid; i < NT * 3 * 32; i += THREADS) {
-    const int co = i & 31, tk = i >> 5;
-    const int t = tk / 3, kw = tk - 3 * t;
-    const __nv_bfloat16 wv = p.wt[co * p.kpad + tk];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = j * 32 + co, k = 7 + 2 * j + kw;
-      *reinterpret_cast<__nv_bfloat16*>(sB + t * B_BYTES + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = wv;
-    }
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int L0 = (int)(((long long)blockIdx.x * p.steps) / gridDim.x);
-  const int L1 = (int)(((long long)(blockIdx.x + 1) * p.steps) / gridDim.x);
+  __syncthreads();              // the barriers exist
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // (does not take part in the weight set-up below: the first units are in flight while the others build B)
+    pdl_wait();                 // the input belongs to earlier work
     const uint32_t sA_u = smem_u32(sA);
     int u = 0;
     uint32_t ph = 1;                                   // parity to wait for on empty[u]: the first lap passes
@@ -299,84 +271,139 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
       const int ch = 4 * (ht * TH) - 3;                // input row of stem row 2*h0 - 1, tap kh = 0
       const int cd = p.sd * jobs.P - 1;
 #pragma unroll 1
-      for (int cu = 0; cu < 6; ++cu) {                 // unit = (half c, kd)
-        const int c = cu >= 3 ? 1 : 0, kd = cu - 3 * c;
+      for (int c = 0; c < 2; ++c) {                    // unit = half c of the plane: 3 kd x CIN x (even, odd) boxes
         mbar_wait(&empty[u], ph);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[u], (uint32_t)(CIN * CI_TX));
+          mbar_arrive_expect_tx(&full[u], (uint32_t)(3 * CIN * CI_TX));
           const uint32_t dst = sA_u + (uint32_t)(u * UNIT_BYTES);
 #pragma unroll
-          for (int ci = 0; ci < CIN; ++ci) {
-            tma_load_4d(dst + ci * CI_BYTES, &tmE, &full[u], 64 * c - 8, ch, cd + kd, n * CIN + ci);
-            tma_load_4d(dst + ci * CI_BYTES + EVEN_BYTES, &tmO, &full[u], 64 * c - 8, ch + 1, cd + kd, n * CIN + ci);
-          }
+          for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+              tma_load_4d(dst + kd * KD_BYTES + ci * CI_BYTES, &tmE, &full[u], 64 * c - 8, ch, cd + kd, n * CIN + ci);
+              tma_load_4d(dst + kd * KD_BYTES + ci * CI_BYTES + EVEN_BYTES, &tmO, &full[u], 64 * c - 8, ch + 1, cd + kd,
+                          n * CIN + ci);
+            }
         }
         __syncwarp();
         if (++u == NU) { u = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else {
+    // ---- weight set-up by warps 1..: banded B operand, depthwise weights, stem BN; the plane buffer starts as
+    //      zeros (column -1 stays zero).  Weights are constants of the (inference) step: this runs BEFORE the
+    //      grid-dependency wait, i.e. under the tail of the previous kernel.
+    constexpr int SETUP = THREADS - 32;
+    const int st = tid - 32;
+    if (warp == 1) {
+      __syncwarp();
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
+    for (int i = st; i < (PLANE_BYTES + NT * B_BYTES) / 16; i += SETUP) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = st; i < 27 * 32; i += SETUP) sWd[i] = __bfloat162float(p.wd[i]);
+    if (st < 32) { sSc0[st] = __ldg(p.scale0 + st); sSh0[st] = __ldg(p.shift0 + st); }
+    if (st < 2) sOne[st] = p.one;
+    __nv_bfloat16 wv[(NT * 3 * 32 + SETUP - 1) / SETUP];
+#pragma unroll
+    for (int it = 0; it < (NT * 3 * 32 + SETUP - 1) / SETUP; ++it) {      // all weight loads in flight together
+      const int i = st + it * SETUP;
+      wv[it] = (i < NT * 3 * 32) ? p.wt[(i & 31) * p.kpad + (i >> 5)] : __float2bfloat16(0.f);
+    }
+    asm volatile("bar.sync 2, %0;" ::"r"(SETUP) : "memory");               // zero fill done
+#pragma unroll
+    for (int it = 0; it < (NT * 3 * 32 + SETUP - 1) / SETUP; ++it) {
+      const int i = st + it * SETUP;
+      if (i < NT * 3 * 32) {
+        const int co = i & 31, tk = i >> 5;
+        const int t = tk / 3, kw = tk - 3 * t;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = j * 32 + co, k = 7 + 2 * j + kw;
+          *reinterpret_cast<__nv_bfloat16*>(sB + t * B_BYTES + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = wv[it];
+        }
+      }
+    }
+    fence_proxy_async_smem();   // generic-proxy writes of B -> visible to the UMMA (async proxy) reads
+    tc_fence_before();
+    asm volatile("bar.sync 2, %0;" ::"r"(SETUP) : "memory");
+    tc_fence_after();
+    pdl_wait();                 // the output buffer's previous readers
+    pdl_launch_dependents();
+  }
+  const uint32_t tmem_base = *tmem_slot;   // (a plain load: a select on the warp index here makes ptxas treat every
+                                            // UMMA operand as non-uniform -> ELECT loops and five R2UR per UMMA)
+
+  if (warp == 1) {
     // ===================== UMMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(128, 128);
-    const uint64_t da0 = desc_k_nosw(smem_u32(sA), 16u, (uint32_t)SLOT_BYTES);
-    const uint64_t db0 = desc_k_nosw(smem_u32(sB), 128u, 256u);
-    int j = 0;
-    int u = 0;
-    uint32_t ph = 0;                                   // parity to wait for on full[u]
-    Jobs jobs(L0, L1, p.Dd);
-    while (jobs.next()) {
-      const uint32_t apar = (uint32_t)((j >> 1) & 1);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int buf = (j & 1) * 2 + c;
-        mbar_wait(&acc_empty[buf], apar ^ 1u);
-        const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
-#pragma unroll
-        for (int kd = 0; kd < 3; ++kd) {
+    // One lane runs the whole loop, outer loops rolled, the 3 x CIN UMMAs of a unit unrolled with immediate
+    // descriptor offsets: ptxas then keeps the descriptors in UNIFORM registers (UIADD3.64 + UTCHMMA, as in
+    // gemm_pw.cu).  With the loops unrolled it precomputes all 36 descriptor pairs in vector registers and pays four
+    // R2UR per UMMA: ~110 cycles of issue per UMMA (measured: independent of N), twice the tensor-pipe time.
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const uint32_t sA_u = smem_u32(sA);
+      const uint64_t db = desc_k_nosw(smem_u32(sB), 128u, 256u);
+      int j = 0, u = 0;
+      uint32_t ph = 0;
+      Jobs jobs(L0, L1, p.Dd);
+      while (jobs.next()) {
+        const uint32_t apar = (uint32_t)((j >> 1) & 1);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          const int buf = (j & 1) * 2 + c;
+          mbar_wait(&acc_empty[buf], apar ^ 1u);
           mbar_wait(&full[u], ph);
           tc_fence_after();
-          if (elect_one()) {
-            const uint64_t da = da0 + (uint64_t)((uint32_t)(u * UNIT_BYTES) >> 4);
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
+          const uint64_t da = desc_k_nosw(sA_u + (uint32_t)(u * UNIT_BYTES), 16u, (uint32_t)SLOT_BYTES);
+          // the 18 UMMAs of the half plane back to back: the issue queue is shallow (issue time == execution time in
+          // scripts/ubench/umma_rate.cu), every cycle this thread spends elsewhere is a cycle the tensor pipe idles
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
               // kh = 0: even rows from slot 0, kh = 1: odd rows, kh = 2: even rows from slot 1
-              const int off = kh == 0 ? 0 : (kh == 1 ? EVEN_BYTES : SLOT_BYTES);
+              const int off = kd * KD_BYTES + (kh == 0 ? 0 : (kh == 1 ? EVEN_BYTES : SLOT_BYTES));
 #pragma unroll
               for (int ci = 0; ci < CIN; ++ci)
                 umma_bf16_ss(dcol, da + (uint64_t)((off + ci * CI_BYTES) >> 4),
-                             db0 + (uint64_t)(((ci * 9 + kd * 3 + kh) * B_BYTES) >> 4), idesc, (kd | kh | ci) != 0 ? 1u : 0u);
+                             db + (uint64_t)(((ci * 9 + kd * 3 + kh) * B_BYTES) >> 4), idesc, (kd | kh | ci) != 0 ? 1u : 0u);
             }
-            umma_commit(&empty[u]);
-            if (kd == 2) umma_commit(&acc_full[buf]);
-          }
-          __syncwarp();
+          umma_commit(&empty[u]);
+          umma_commit(&acc_full[buf]);
           if (++u == NU) { u = 0; ph ^= 1u; }
         }
+        ++j;
       }
-      ++j;
     }
-  } else {
-    // ===================== epilogue (TMEM -> BN/ReLU -> plane buffer) + depthwise =====================
-    const int ct = tid - 64;                     // 0..255
-    // epilogue role
+    __syncwarp();
+  } else if (warp >= 2) {
+    // ===================== 16 warps: epilogue (TMEM -> BN/ReLU -> plane buffer) + depthwise =====================
+    const int ct = tid - 64;                     // 0..511
+    // epilogue role: lane quarter q, voxel jv of the 4-voxel group (32 accumulator columns)
     const int q = warp & 3;
-    const int hh = (warp - 2) >> 2;              // voxels j = 2*hh, 2*hh + 1 of a group
+    const int jv = (warp - 2) >> 2;
     const int row = (q * 32 + lane) >> 3;        // stem row slot 0..15
     const int g = lane & 7;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hh * 64);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(jv * 32);
     const uint32_t sP_u = smem_u32(sP);
-    // depthwise role
-    const int cg = ct & 7;                       // channels 4*cg .. 4*cg+3
-    const int w = ct >> 3;                       // output column 0..31
-    float4 sc1 = __ldg(reinterpret_cast<const float4*>(p.scale1 + 4 * cg));
-    float4 sh1 = __ldg(reinterpret_cast<const float4*>(p.shift1 + 4 * cg));
-    const uint32_t rdE = sP_u + (uint32_t)O_BYTES + entry_off(w, cg >> 1) + (uint32_t)((cg & 1) * 8);
-    const uint32_t rdO0 = sP_u + entry_off(w, cg >> 1) + (uint32_t)((cg & 1) * 8);
-    const uint32_t rdO1 = sP_u + entry_off(w + 1, cg >> 1) + (uint32_t)((cg & 1) * 8);
+    // voxel 32c + 4g + jv: even column -> E[16c + 2g + jv/2], odd column -> O[16c + 2g + (jv+1)/2]
+    const uint32_t wr_base = sP_u + (uint32_t)(row * ROW_BYTES) + ((jv & 1) ? 0u : (uint32_t)O_BYTES);
+    const int wr_e = 2 * g + ((jv + 1) >> 1);
+    // depthwise role: 2 channels x output column w
+    const int cp = ct & 15;                      // channels 2*cp, 2*cp + 1
+    const int w = ct >> 4;                       // output column 0..31
+    const float2 sc1 = __ldg(reinterpret_cast<const float2*>(p.scale1 + 2 * cp));
+    const float2 sh1 = __ldg(reinterpret_cast<const float2*>(p.shift1 + 2 * cp));
+    const uint32_t sub = (uint32_t)((cp & 3) * 4);
+    const uint32_t rdE = sP_u + (uint32_t)O_BYTES + entry_off(w, cp >> 2) + sub;
+    const uint32_t rdO0 = sP_u + entry_off(w, cp >> 2) + sub;
+    const uint32_t rdO1 = sP_u + entry_off(w + 1, cp >> 2) + sub;
     const f32x2 one2 = *reinterpret_cast<const f32x2*>(sOne);
-    f32x2 accA[TH][2], accB[TH][2];
+    f32x2 accA[TH], accB[TH];
 #pragma unroll
-    for (int i = 0; i < TH; ++i) { accA[i][0] = accA[i][1] = 0ull; accB[i][0] = accB[i][1] = 0ull; }
+    for (int i = 0; i < TH; ++i) { accA[i] = 0ull; accB[i] = 0ull; }
 
     int j = 0;
     Jobs jobs(L0, L1, p.Dd);
@@ -385,77 +412,65 @@ __global__ void __launch_bounds__(sdw::THREADS, 1) stem_dw_kernel(const __grid_c
       const int h0 = ht * TH;                    // first depthwise row of the tile
       const uint32_t apar = (uint32_t)((j >> 1) & 1);
       const int hs = 2 * h0 - 1 + row;           // stem row of this thread's slot
-      const bool row_ok = (hs >= 0) && (hs < p.Hs) && (row < 15);
+      const bool row_ok = (hs >= 0) && (hs < p.Hs);
       // ---------------- phase A: both halves of the plane ----------------
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         const int buf = (j & 1) * 2 + c;
         mbar_wait(&acc_full[buf], apar);
         tc_fence_after();
-        uint32_t v0[32], v1[32];
-        tmem_ld_x32(lane_addr + (uint32_t)(buf * 128), v0);
-        tmem_ld_x32(lane_addr + (uint32_t)(buf * 128 + 32), v1);
+        uint32_t v[32];
+        tmem_ld_x32(lane_addr + (uint32_t)(buf * 128), v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        uint32_t out[32];
+        uint32_t out[16];
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
           const ulonglong2 sc = *reinterpret_cast<const ulonglong2*>(sSc0 + k);
           const ulonglong2 sh = *reinterpret_cast<const ulonglong2*>(sSh0 + k);
-          out[(k >> 1)] = bn_relu_pack(v0[k], v0[k + 1], sc.x, sh.x, one2);
-          out[(k >> 1) + 1] = bn_relu_pack(v0[k + 2], v0[k + 3], sc.y, sh.y, one2);
-          out[16 + (k >> 1)] = bn_relu_pack(v1[k], v1[k + 1], sc.x, sh.x, one2);
-          out[16 + (k >> 1) + 1] = bn_relu_pack(v1[k + 2], v1[k + 3], sc.y, sh.y, one2);
+          out[(k >> 1)] = bn_relu_pack(v[k], v[k + 1], sc.x, sh.x, one2);
+          out[(k >> 1) + 1] = bn_relu_pack(v[k + 2], v[k + 3], sc.y, sh.y, one2);
         }
         if (!row_ok) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) out[k] = 0u;
+          for (int k = 0; k < 16; ++k) out[k] = 0u;
         }
         // the depthwise pass of the previous job must be done with the plane buffer
-        if (c == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (c == 0) asm volatile("bar.sync 1, %0;" ::"n"(CWARPS * 32) : "memory");
         if (row < 15) {
-          // voxel 32c + 4g + 2hh (even column -> E[16c + 2g + hh]), voxel + 1 (odd column -> O[16c + 2g + hh + 1])
-          const int e = 16 * c + 2 * g + hh;
-          const uint32_t rowb = sP_u + (uint32_t)(row * ROW_BYTES);
+          const int e = 16 * c + wr_e;
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (uint32_t)O_BYTES + entry_off(e, c4)),
-                         "r"(out[4 * c4]), "r"(out[4 * c4 + 1]), "r"(out[4 * c4 + 2]), "r"(out[4 * c4 + 3])
+          for (int c4 = 0; c4 < 4; ++c4)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr_base + entry_off(e, c4)), "r"(out[4 * c4]),
+                         "r"(out[4 * c4 + 1]), "r"(out[4 * c4 + 2]), "r"(out[4 * c4 + 3])
                          : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + entry_off(e + 1, c4)),
-                         "r"(out[16 + 4 * c4]), "r"(out[16 + 4 * c4 + 1]), "r"(out[16 + 4 * c4 + 2]), "r"(out[16 + 4 * c4 + 3])
-                         : "memory");
-          }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // the plane is complete
+      asm volatile("bar.sync 1, %0;" ::"n"(CWARPS * 32) : "memory");   // the plane is complete
       // ---------------- phase B: this plane's taps ----------------
       {
         const int role = jobs.role;
         // kd share of accA: role 0 -> kd 0, role 1 -> kd 1, role 2 -> kd 2; accB (the next output plane) gets kd 0
-        const float* wA = sWd + (role * 9) * 32 + 4 * cg;
-        const float* wB = sWd + 4 * cg;
+        const float* wA = sWd + (role * 9) * 32 + 2 * cp;
+        const float* wB = sWd + 2 * cp;
         if ((role == 2) && jobs.cont) dw_plane<true>(accA, accB, wA, wB, rdO0, rdE, rdO1);
         else dw_plane<false>(accA, accB, wA, wB, rdO0, rdE, rdO1);
         if (role == 2) {
           // depthwise plane d of this tile is complete
-          __nv_bfloat16* o = p.y + ((((long long)n * p.Dd + jobs.d) * p.Hd + h0) * 32 + w) * 32 + 4 * cg;
+          __nv_bfloat16* o = p.y + ((((long long)n * p.Dd + jobs.d) * p.Hd + h0) * 32 + w) * 32 + 2 * cp;
 #pragma unroll
           for (int i = 0; i < TH; ++i) {
             if (h0 + i < p.Hd) {
-              float a0, a1, a2, a3;
-              unpack_f32x2(accA[i][0], a0, a1);
-              unpack_f32x2(accA[i][1], a2, a3);
+              float a0, a1;
+              unpack_f32x2(accA[i], a0, a1);
               a0 = relu_nan1(__fadd_rn(__fmul_rn(a0, sc1.x), sh1.x));
               a1 = relu_nan1(__fadd_rn(__fmul_rn(a1, sc1.y), sh1.y));
-              a2 = relu_nan1(__fadd_rn(__fmul_rn(a2, sc1.z), sh1.z));
-              a3 = relu_nan1(__fadd_rn(__fmul_rn(a3, sc1.w), sh1.w));
-              *reinterpret_cast<uint2*>(o + (long long)i * 32 * 32) = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
+              *reinterpret_cast<uint32_t*>(o + (long long)i * 32 * 32) = pack_bf16x2(a0, a1);
             }
-            accA[i][0] = accB[i][0]; accA[i][1] = accB[i][1];
-            accB[i][0] = 0ull; accB[i][1] = 0ull;
+            accA[i] = accB[i];
+            accB[i] = 0ull;
           }
         }
       }
@@ -485,7 +500,7 @@ static int launch_stem_dw(const void* x, const StemDwParams& p, cudaStream_t st)
     if (make_tma_bf16(&tmE, x, 4, dims, strides, boxE, CU_TENSOR_MAP_SWIZZLE_NONE, estr)) return SSD3D_ERR_TMA;
     if (make_tma_bf16(&tmO, x, 4, dims, strides, boxO, CU_TENSOR_MAP_SWIZZLE_NONE, estr)) return SSD3D_ERR_TMA;
   }
-  const size_t smem = 1024 + (size_t)PLANE_BYTES + (size_t)9 * CIN * B_BYTES + (size_t)NU * CIN * CI_BYTES +
+  const size_t smem = 1024 + (size_t)PLANE_BYTES + (size_t)9 * CIN * B_BYTES + (size_t)NU * 3 * CIN * CI_BYTES +
                       27 * 32 * 4 + 256 + 256;
   if (smem > 232448) return SSD3D_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(stem_dw_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
