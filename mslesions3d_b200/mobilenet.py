@@ -126,6 +126,13 @@ class Block(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def pointwise_only(self, x):
+        """conv2 + bn2 + ReLU on an activation that already went through conv1 + bn1 + ReLU (the fused stem +
+        depthwise kernel of the inference plan produced it)."""
+        _, _, _, wp, s2, b2 = self._pack()
+        flag = self.nan_flag if self.nan_flag is not None else torch.zeros((1,), dtype=torch.int32, device=x.device)
+        return ops.pwconv_bn_relu(x, wp, s2, b2, flag)
+
     def forward(self, x):
         s = _stride3(self.conv1.stride)
         if s[0] != s[1] or s[1] != s[2] or s[0] not in (1, 2):

@@ -268,6 +268,14 @@ class _InferencePlan:
         self.cloned = torch.cuda.Event()     # results of the latest launch were copied out of the static buffers
         self.copied = torch.cuda.Event()     # the latest host batch has arrived in the static input buffer
         self.stem = model.base.features[0]
+        # stem + depthwise conv of the first Block as ONE eager kernel (csrc/conv_stem_dw.cu; opt-in, see
+        # LSSD3D.fuse_stem_dw): the static buffer the graph reads then holds the depthwise output and the graph
+        # starts at the first Block's pointwise conv
+        blk1 = self.blk1 = model.base.features[1] if len(model.base.features) > 1 else None
+        sd3 = tuple(int(v) for v in self.stem[0].stride)
+        self.front_fused = bool(getattr(model, "fuse_stem_dw", 0)) and blk1 is not None and \
+            tuple(int(v) for v in blk1.conv1.stride) == (2, 2, 2) and blk1.conv1.in_channels == 32 and \
+            ops.stem_dw_fused_supported(self.inp, sd3[0])
         self.flag = torch.zeros((1,), dtype=torch.int32, device=dev)   # this plan's own NaN word: plans may overlap
         self.stream = torch.cuda.Stream(device=dev)                     # compute stream of the streaming API
         # Later stages run at higher stream priority (recorded into the graph's kernel nodes): when two batches
@@ -280,7 +288,7 @@ class _InferencePlan:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():
             self.inp.zero_()
-            self.stem_out = self.stem(self.inp)          # static buffer the captured graph reads
+            self.stem_out = self._front(self.inp, None)   # static buffer the captured graph reads
             for _ in range(2):                # warm-up: lazy module loading, function attributes, packing
                 self._run(model)
         torch.cuda.current_stream().wait_stream(side)
@@ -292,14 +300,15 @@ class _InferencePlan:
         self.n_kernels = ops.LAUNCHES[0] - before + 1  # library kernels per step (graph + the eager stem)
         self.graph = graph
 
-    def run_stem(self, image: torch.Tensor):
-        """The stem runs outside the graph so that a device-resident batch is consumed in place (no staging
-        copy of the largest tensor of the step); a host batch goes through the static input buffer."""
-        if image.is_cuda:
-            self.stem(image, out=self.stem_out)
-        else:
-            self.inp.copy_(image, non_blocking=True)
-            self.stem(self.inp, out=self.stem_out)
+    def _front(self, image: torch.Tensor, out):
+        """features[0] (or, fused, features[0] + the depthwise half of features[1]) on ``image``.  It runs outside
+        the graph so that a device-resident batch is consumed in place (no staging copy of the largest tensor of
+        the step); a host batch goes through the static input buffer."""
+        if not self.front_fused:
+            return self.stem(image, out=out)
+        w0, sc0, sh0 = self.stem._pack()
+        wd, sc1, sh1 = self.blk1._pack()[:3]
+        return ops.stem_dw_bn_relu(image, w0, sc0, sh0, wd, sc1, sh1, int(self.stem[0].stride[0]), out=out)
 
     def _run(self, model: "LSSD3D"):
         from . import mobilenet
@@ -337,7 +346,9 @@ class _InferencePlan:
                 tail.wait_stream(main)
                 cur = tail
             with torch.cuda.stream(cur):
-                if i > 0:
+                if i == 1 and self.front_fused:
+                    out = feat.pointwise_only(out)       # its depthwise half ran with the stem
+                elif i > 0:
                     out = feat(out)
                 if i in keys:
                     j = keys.index(i)
@@ -398,7 +409,7 @@ class _InferencePlan:
             # stem on `compute`: tell the caching allocator, or the block could be handed out again while the
             # kernel still reads it (up to pipeline_depth batches are in flight)
             image.record_stream(compute)
-            self.stem(image, out=self.stem_out)
+            self._front(image, self.stem_out)
         else:
             if copy_stream is None:
                 self.inp.copy_(image, non_blocking=True)
@@ -411,7 +422,7 @@ class _InferencePlan:
                 finally:
                     torch.cuda.set_stream(compute)
                 compute.wait_event(self.copied)
-            self.stem(self.inp, out=self.stem_out)
+            self._front(self.inp, self.stem_out)
         self.graph.replay()
         ops.LAUNCHES[0] += self.n_kernels
         self.host_meta.copy_(self.meta, non_blocking=True)
@@ -523,6 +534,9 @@ class LSSD3D(_LightningBase):
         self.tail_from = int(os.environ.get("SSD3D_TAIL_FROM", "3"))   # first backbone layer on the high-priority stream
         # fused Block kernels in the streaming pipeline (see mobilenet.FUSE_DWPW): off, measured slower there
         self.fuse_blocks_pipeline = int(os.environ.get("SSD3D_FUSE_DWPW_PIPELINE", "0"))
+        # stem + first depthwise conv as one kernel in the captured plans (csrc/conv_stem_dw.cu).  Opt-in: measured
+        # at the benchmark shape it equals the two stand-alone kernels (77 vs 76 us alone), see DESIGN.md section 6
+        self.fuse_stem_dw = int(os.environ.get("SSD3D_FUSE_STEM_DW", "0"))
         self._plans = {}
 
     # ------------------------------------------------------------------------------------------
@@ -709,7 +723,7 @@ class LSSD3D(_LightningBase):
             raise RuntimeError("predict_step needs eval() mode (BatchNorm running statistics)")
         dtype = image.dtype if image.dtype in (torch.float32, torch.bfloat16) else torch.float32
         key = (tuple(image.shape), dtype, str(self.device), float(self.min_score), float(self.max_overlap),
-               int(self.top_k), slot, fuse_mask)
+               int(self.top_k), slot, fuse_mask, int(self.fuse_stem_dw))
         ver = self._state_version()
         plan = self._plans.get(key)
         if plan is None or plan.key != ver:
