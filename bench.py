@@ -506,6 +506,12 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n_launch
 
+    # HBM WRITE ceiling of this box, measured live: a memset of a buffer >> L2.  The copy peak in MEASURED_PEAKS.json
+    # is 3.2 TB/s of reads + 3.2 TB/s of writes at once; pure writes top out well below the sum (3.9 TB/s on the
+    # round-2 boxes, scripts/probe_hbm.py), which is what bounds the stem: two thirds of its bytes are writes.
+    wbuf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    write_gbs = wbuf.numel() / (kernel_ms(lambda i: wbuf.zero_(), 10) / 1000.0) / 1e9
+    del wbuf
     stem_out = ops.stem_conv_bn_relu(dev_bf16[0], w, scale, shift, sd_stride)
     n_launch = max(20, args.steps)
     k_ms = kernel_ms(lambda i: ops.stem_conv_bn_relu(dev_bf16[i % N_ROTATE], w, scale, shift, sd_stride, out=stem_out),
@@ -520,7 +526,13 @@ def main():
                 "traffic_source": "%s (ncu --set full, dram read+write per launch; part of the 134 MB output is still "
                                   "in the 126 MB L2 when the kernel ends)" % traffic_src,
                 "timing": "%d back-to-back launches between one CUDA event pair, inputs rotating over 268 MB" % n_launch,
-                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms, "peak_source": peak_src}
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_ms, "peak_source": peak_src,
+                "write_ceiling": {"measured_write_gbs": write_gbs, "how": "torch zero_ of 512 MiB, 10 back-to-back launches",
+                                  "write_bytes_per_launch": vox_out * 32 * 2,
+                                  "write_floor_ms": vox_out * 32 * 2 / write_gbs / 1e6,
+                                  "frac_of_write_floor": (vox_out * 32 * 2 / write_gbs / 1e6) / k_ms,
+                                  "note": "the kernel cannot finish before its 134 MB of output has been written at the "
+                                          "HBM write rate; reads overlap (a copy sustains read + write at once)"}}
 
     # second HBM-bound kernel the north star names: the first depthwise conv (32 ch, stride 2, 64^3 -> 32^3)
     blk = model.base.features[1]

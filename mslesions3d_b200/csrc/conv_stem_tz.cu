@@ -43,6 +43,7 @@ struct StemTzParams {
   const float* shift;
   __nv_bfloat16* y;            // (N, Do, Ho, Wo, 32)
   float floor;                 // 0 = ReLU, -inf = identity
+  int zero;                    // 0, as a run-time value (keeps the B descriptors out of loop-invariant hoisting)
 };
 
 namespace tz {
@@ -53,7 +54,7 @@ constexpr int CI_BYTES = ROWS * SLOT_BYTES;  // 2304 (a multiple of 128: every T
 constexpr int B_BYTES = 4096;                // one (ci,kd,kh) slice of B: 128 rows x 16 bf16
 constexpr int NGROUP = 6;                    // ring of kd groups (3 (kd,kh) boxes each): 2 tiles
 constexpr int OUT_HALF_BYTES = 16384;        // staging: 128 lines x 128 B (one voxel pair per GEMM row)
-constexpr int THREADS = 320;
+constexpr int THREADS = 64 + 2 * 256;         // TMA producer, UMMA issuer, two groups of 8 epilogue warps
 
 __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {
@@ -117,31 +118,36 @@ __device__ __forceinline__ void tz_produce_tile(const CUtensorMap* tmX, uint32_t
   }
 }
 
-template <int CIN, int TP>
-__device__ __forceinline__ void tz_mma_tile(uint64_t da0, uint64_t db0, uint64_t* full, uint64_t* empty,
-                                            uint64_t* acc_full, uint64_t* acc_empty, uint32_t par, uint32_t tmem_base,
-                                            uint32_t idesc) {
+// Called by ONE lane.  The UMMA issue queue is shallow (scripts/ubench/umma_rate.cu: issue time == execution time, 64
+// cycles per M128 N128 K16), so every cycle the issuer spends between two UMMAs on barrier waits, fences and commits
+// is a cycle the tensor pipe idles: the wait for the NEXT group's boxes sits between the UMMAs of this group, behind
+// UMMAs that are still executing.
+template <int CIN>
+__device__ __forceinline__ void tz_mma_tile(uint64_t da, uint64_t db0, uint64_t* full, uint64_t* empty,
+                                            uint64_t* acc_full, uint32_t par, uint32_t dcol, uint32_t idesc) {
+  // da / full / empty already point at this tile's half of the ring (a run-time offset on purpose: with the ring
+  // position a template constant ptxas precomputes all 36 descriptor pairs in vector registers and pays four R2UR per
+  // UMMA; relative to a per-tile uniform base they are UIADD3.64 with immediates)
   using namespace tz;
   constexpr int BOX_BYTES = CIN * CI_BYTES;
-  mbar_wait(&acc_empty[TP], par ^ 1u);
-  const uint32_t dcol = tmem_base + (uint32_t)(TP * 128);
+  mbar_wait(&full[0], par);
+  tc_fence_after();
 #pragma unroll
   for (int kd = 0; kd < 3; ++kd) {
-    const int g = TP * 3 + kd;
-    mbar_wait(&full[g], par);
-    tc_fence_after();
-    if (elect_one()) {
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+    for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci)
-          umma_bf16_ss(dcol, da0 + (uint64_t)(((g * 3 + kh) * BOX_BYTES + ci * CI_BYTES) >> 4),
-                       db0 + (uint64_t)(((ci * 9 + kd * 3 + kh) * B_BYTES) >> 4), idesc, (kd | kh | ci) != 0 ? 1u : 0u);
-      umma_commit(&empty[g]);                      // the group's boxes are free once these UMMAs have read them
-      if (kd == 2) umma_commit(&acc_full[TP]);     // the accumulator is complete
+      for (int ci = 0; ci < CIN; ++ci)
+        umma_bf16_ss(dcol, da + (uint64_t)(((kd * 3 + kh) * BOX_BYTES + ci * CI_BYTES) >> 4),
+                     db0 + (uint64_t)(((ci * 9 + kd * 3 + kh) * B_BYTES) >> 4), idesc, (kd | kh | ci) != 0 ? 1u : 0u);
+      if (kh == 0 && kd < 2) {
+        mbar_wait(&full[kd + 1], par);
+        tc_fence_after();
+      }
     }
-    __syncwarp();
+    umma_commit(&empty[kd]);                     // the group's boxes are free once these UMMAs have read them
   }
+  umma_commit(acc_full);                         // the accumulator is complete
 }
 
 template <int CIN>
@@ -152,19 +158,19 @@ __global__ void __launch_bounds__(tz::THREADS, 1) stem_tz_kernel(const __grid_co
   using namespace tz;
   constexpr int NT = 9 * CIN;                       // UMMAs per tile
   constexpr int BOX_BYTES = CIN * CI_BYTES;         // one (kd,kh) box
-  constexpr uint32_t TMEM_COLS = 256;               // two 128-column accumulators
+  constexpr uint32_t TMEM_COLS = 512;               // four 128-column accumulators
 
   extern __shared__ uint8_t tz_raw[];
   const uint32_t raw = smem_u32(tz_raw);
   uint8_t* smem = tz_raw + ((1024u - (raw & 1023u)) & 1023u);
-  uint8_t* sOut = smem;                                         // 2 x 16 KB, 1024-aligned (128B swizzle)
-  uint8_t* sB = sOut + 2 * OUT_HALF_BYTES;                      // NT x 4096
+  uint8_t* sOut = smem;                                         // 2 sets x 2 halves x 16 KB, 1024-aligned (128B swizzle)
+  uint8_t* sB = sOut + 4 * OUT_HALF_BYTES;                      // NT x 4096
   uint8_t* sA = sB + NT * B_BYTES;                              // NGROUP x 3 x BOX_BYTES
   uint64_t* full = reinterpret_cast<uint64_t*>(sA + NGROUP * 3 * BOX_BYTES);
   uint64_t* empty = full + NGROUP;
-  uint64_t* acc_full = empty + NGROUP;                          // [2]
-  uint64_t* acc_empty = acc_full + 2;                           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_full = empty + NGROUP;                          // [4]
+  uint64_t* acc_empty = acc_full + 4;                           // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -175,8 +181,7 @@ __global__ void __launch_bounds__(tz::THREADS, 1) stem_tz_kernel(const __grid_co
     tma_prefetch_desc(&tmY0);
     tma_prefetch_desc(&tmY1);
     for (int s = 0; s < NGROUP; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);
+    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -200,6 +205,11 @@ __global__ void __launch_bounds__(tz::THREADS, 1) stem_tz_kernel(const __grid_co
       *reinterpret_cast<__nv_bfloat16*>(sB + t * B_BYTES + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) = wv;
     }
   }
+  if (tid < 32) {
+    float* s_sc = reinterpret_cast<float*>(tmem_slot + 4);
+    s_sc[tid] = __ldg(p.scale + tid);
+    s_sc[32 + tid] = __ldg(p.shift + tid);
+  }
   fence_proxy_async_smem();   // generic-proxy writes of B -> visible to the UMMA (async proxy) reads
   tc_fence_before();
   __syncthreads();
@@ -221,38 +231,46 @@ __global__ void __launch_bounds__(tz::THREADS, 1) stem_tz_kernel(const __grid_co
       else tz_produce_tile<CIN, 0>(&tmX, sA_u, full, empty, par, cw, ch, cd, cn);
     }
   } else if (warp == 1) {
-    // ===================== UMMA issuer (warp-uniform loop, one elected lane issues) =====================
-    const uint32_t idesc = umma_idesc_bf16(128, 128);
-    const uint64_t da0 = desc_k_nosw(smem_u32(sA), 16u, (uint32_t)SLOT_BYTES);
-    const uint64_t db0 = desc_k_nosw(smem_u32(sB), 128u, 256u);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t par = (uint32_t)((it >> 1) & 1);
-      if (it & 1) tz_mma_tile<CIN, 1>(da0, db0, full, empty, acc_full, acc_empty, par, tmem_base, idesc);
-      else tz_mma_tile<CIN, 0>(da0, db0, full, empty, acc_full, acc_empty, par, tmem_base, idesc);
+    // ===================== UMMA issuer: one lane, descriptors in uniform registers =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 128);
+      const uint64_t da0 = desc_k_nosw(smem_u32(sA), 16u, (uint32_t)SLOT_BYTES);
+      const uint64_t db0 = desc_k_nosw(smem_u32(sB), 128u, 256u);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t par = (uint32_t)((it >> 1) & 1);
+        const int ab = it & 3;
+        mbar_wait(&acc_empty[ab], (uint32_t)(((it >> 2) & 1) ^ 1));
+        const uint32_t dcol = tmem_base + (uint32_t)(ab * 128);
+        const int tp = it & 1;
+        tz_mma_tile<CIN>(da0 + (uint64_t)((uint32_t)(tp * 9 * BOX_BYTES) >> 4), db0 + (uint64_t)(uint32_t)(it & p.zero),
+                         full + tp * 3, empty + tp * 3,
+                         &acc_full[ab], par, dcol, idesc);
+      }
     }
+    __syncwarp();
   } else {
-    // ===================== epilogue: 2 independent sets (voxel pair 0 / 1 of each group) of 4 warps =====================
+    // ===================== epilogue: two groups (even / odd tiles) x two half-sets (voxel pair 0 / 1) of 4 warps =====================
+    // A tile's epilogue is a latency chain (accumulator wait, TMEM load, BN, staging, fence, barrier, TMA store:
+    // ~2700 cycles against the 2440 the HBM write stream needs per tile), so two tiles are in the epilogue at once.
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;             // voxels j = 2*half, 2*half + 1 of the group
+    const int grp = (warp - 2) >> 3;              // tiles it = grp, grp + 2, ..
+    const int half = ((warp - 2) >> 2) & 1;       // voxels j = 2*half, 2*half + 1 of the group
     const int r = q * 32 + lane;                  // GEMM row = group = staging line
     const bool leader = (r == 0);
     const CUtensorMap* tmY = half ? &tmY1 : &tmY0;
-    float sc[32], sh[32];
-#pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      *reinterpret_cast<float4*>(&sc[c]) = __ldg(reinterpret_cast<const float4*>(p.scale + c));
-      *reinterpret_cast<float4*>(&sh[c]) = __ldg(reinterpret_cast<const float4*>(p.shift + c));
-    }
+    float* s_sc = reinterpret_cast<float*>(tmem_slot + 4);   // BN scale[32], shift[32] (filled before the set-up barrier)
+    float* s_sh = s_sc + 32;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
-    const uint32_t out_base = smem_u32(sOut + half * OUT_HALF_BYTES);
+    const uint32_t out_base = smem_u32(sOut + (grp * 2 + half) * OUT_HALF_BYTES);   // this group's staging half
     const uint32_t line = out_base + (uint32_t)(r * 128);
     const uint32_t sw = (uint32_t)(r & 7);
-    const int bar_id = 1 + half;
+    const int bar_id = 1 + grp * 2 + half;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int ab = it & 1;
-      mbar_wait(&acc_full[ab], (uint32_t)((it >> 1) & 1));
+      if ((it & 1) != grp) continue;
+      const int ab = it & 3;
+      mbar_wait(&acc_full[ab], (uint32_t)((it >> 2) & 1));
       tc_fence_after();
       uint32_t v0[32], v1[32];
       tmem_ld_x32(lane_addr + (uint32_t)(ab * 128), v0);
@@ -261,22 +279,30 @@ __global__ void __launch_bounds__(tz::THREADS, 1) stem_tz_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ab]);   // the accumulator can be overwritten
-      uint32_t out[32];
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        out[c >> 1] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[c]), sc[c]), sh[c]), p.floor),
-                                  relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v0[c + 1]), sc[c + 1]), sh[c + 1]), p.floor));
-        out[16 + (c >> 1)] = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[c]), sc[c]), sh[c]), p.floor),
-                                         relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v1[c + 1]), sc[c + 1]), sh[c + 1]), p.floor));
-      }
-      // the previous tile's TMA store must have read the staging half before it is overwritten
+      // the group's previous TMA store (two tiles ago) must have read the staging half before it is overwritten
       if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + (((uint32_t)c ^ sw) << 4)), "r"(out[4 * c]),
-                     "r"(out[4 * c + 1]), "r"(out[4 * c + 2]), "r"(out[4 * c + 3])
-                     : "memory");
+      for (int e = 0; e < 2; ++e) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 sc0 = *reinterpret_cast<const float4*>(s_sc + 8 * c4), sc1 = *reinterpret_cast<const float4*>(s_sc + 8 * c4 + 4);
+          const float4 sh0 = *reinterpret_cast<const float4*>(s_sh + 8 * c4), sh1 = *reinterpret_cast<const float4*>(s_sh + 8 * c4 + 4);
+          const uint32_t* v = e ? v1 : v0;
+          const int k = 8 * c4;
+          const uint32_t o0 = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v[k]), sc0.x), sh0.x), p.floor),
+                                          relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v[k + 1]), sc0.y), sh0.y), p.floor));
+          const uint32_t o1 = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v[k + 2]), sc0.z), sh0.z), p.floor),
+                                          relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v[k + 3]), sc0.w), sh0.w), p.floor));
+          const uint32_t o2 = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v[k + 4]), sc1.x), sh1.x), p.floor),
+                                          relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v[k + 5]), sc1.y), sh1.y), p.floor));
+          const uint32_t o3 = pack_bf16x2(relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v[k + 6]), sc1.z), sh1.z), p.floor),
+                                          relu_nan1(__fadd_rn(__fmul_rn(__uint_as_float(v[k + 7]), sc1.w), sh1.w), p.floor));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + (((uint32_t)(4 * e + c4) ^ sw) << 4)), "r"(o0),
+                       "r"(o1), "r"(o2), "r"(o3)
+                       : "memory");
+        }
+      }
       fence_proxy_async_smem();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
       if (leader) {
@@ -325,7 +351,7 @@ static int launch_stem_tz(const void* x, const StemTzParams& p, cudaStream_t st)
     const uint32_t box[5] = {64u, 8u, (uint32_t)p.TH, (uint32_t)p.TD, 1u};
     if (make_tma_bf16(&ty[half], p.y + half * 64, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return SSD3D_ERR_TMA;
   }
-  const size_t smem = 1024 + 2 * (size_t)OUT_HALF_BYTES + (size_t)9 * CIN * B_BYTES + (size_t)NGROUP * 3 * CIN * CI_BYTES + 512;
+  const size_t smem = 1024 + 4 * (size_t)OUT_HALF_BYTES + (size_t)9 * CIN * B_BYTES + (size_t)NGROUP * 3 * CIN * CI_BYTES + 512;
   cudaError_t e = cudaFuncSetAttribute(stem_tz_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const long long tiles = (long long)p.cols * p.tiles_h * p.tiles_d * p.N;
@@ -368,6 +394,7 @@ extern "C" int ssd3d_stem_conv_affine_tz(const void* x, int x_is_bf16, const voi
   p.shift = shift;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.floor = SSD3D_FLOOR(relu);
+  p.zero = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return Cin == 1 ? launch_stem_tz<1>(x, p, st) : launch_stem_tz<2>(x, p, st);
 }
