@@ -1,6 +1,9 @@
 // SSD head for LARGE feature maps as "kw-GEMM + (kd,kh) stencil" (ssd3d.py:131-167).
 //
-// With N = 16 output channels a UMMA costs the same ~128 cycles as one with N = 144, and the per-tap implicit
+// With N = 16 output channels a UMMA costs about as much as one with N = 144 -- not in the tensor pipe (its time is
+// max(M,128)*N/256 cycles: scripts/ubench/umma_rate.cu measures 48 / 64 / 128 cycles at N = 64 / 128 / 256) but in the
+// single issuing thread, whose barrier waits, descriptor arithmetic and commits per UMMA exceed the pipe time of a
+// narrow instruction (the issue queue is shallow) -- and the per-tap implicit
 // GEMM of gemm_tc.cu re-reads every activation 27 times from L2 (221 MB for the 16^3 x 128-channel map of the
 // benchmark).  Here the 3x3x3 conv is split:
 //   1. head_kw_gemm_kernel: Y[v][(kd,kh), n] = sum_{kw,c} x[v + (0,0,kw-1)][c] * w[n][kd,kh,kw][c]
