@@ -519,8 +519,12 @@ def main():
     vox_out = BATCH * (SIZE[0] // 2) * (SIZE[1] // 2) * (SIZE[2] // 2)
     algo_bytes = in_bytes + vox_out * 32 * 2 + 27 * CHANNELS * 32 * 4
     achieved = algo_bytes / (k_ms / 1000.0) / 1e9
-    traffic, traffic_src = ncu_traffic("r02_ncu_full_stem.json", "r01_ncu_full_stem_final.json")
-    roofline = {"kernel": "stem_tc_kernel<bf16,2> (dense 3x3x3 conv 2->32 + BN + ReLU, tcgen05 implicit GEMM)", "bound": "hbm",
+    stem_tz = os.environ.get("SSD3D_STEM_TZ", "") != "0"      # the library's own choice for rows of 128 voxels
+    stem_name = ("stem_tz_kernel<2> (dense 3x3x3 conv 2->32 + BN + ReLU, banded-B tcgen05 GEMM on raw TMA rows)" if stem_tz
+                 else "stem_tc_kernel<bf16,2> (dense 3x3x3 conv 2->32 + BN + ReLU, tcgen05 implicit GEMM)")
+    traffic, traffic_src = (ncu_traffic("r02_ncu_stem_tz.json") if stem_tz else
+                            ncu_traffic("r02_ncu_full_stem.json", "r01_ncu_full_stem_final.json"))
+    roofline = {"kernel": stem_name, "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "traffic_source": "%s (ncu --set full, dram read+write per launch; part of the 134 MB output is still "

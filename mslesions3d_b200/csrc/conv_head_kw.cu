@@ -170,13 +170,17 @@ __global__ void __launch_bounds__(192, 2) head_kw_gemm_kernel(const __grid_const
 }
 
 // out[d,h,w][c] = bias[c] + sum_{g = kd*3+kh ascending, in bounds} Y[g*16 + c][d+kd-1, h+kh-1, w]
-// thread = one voxel, all 16 columns: every load is coalesced across the warp (consecutive voxels of a column)
+// thread = one voxel x 4 of the 16 columns (warp q of the block owns columns 4q .. 4q+3 of the block's 32 voxels):
+// every load is coalesced across the warp (consecutive voxels of a column), and the map's N*D*H*W voxels give four
+// times the threads of a voxel-per-thread mapping -- at 32 768 voxels that one left the machine at 11 % occupancy
+// with 144 dependent L2 loads per thread (14.7 us per launch in profiles/r02_launches_final.csv).
 __global__ void __launch_bounds__(128) head_stencil_kernel(const HeadKwParams p) {
   pdl_wait();
   pdl_launch_dependents();
   const long long V = (long long)p.D * p.H * p.W;
   const long long total = (long long)p.N * V;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cq = threadIdx.x >> 5;                                  // column quad
+  const long long gid = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
   if (gid >= total) return;
   const int n = (int)(gid / V);
   long long r = gid - (long long)n * V;
@@ -184,28 +188,29 @@ __global__ void __launch_bounds__(128) head_stencil_kernel(const HeadKwParams p)
   const int h = (int)(r % p.H);
   const int d = (int)(r / p.H);
   const int ncol = p.n_loc + p.n_cls;
-  float acc[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  const int c0 = 4 * cq;
+  if (c0 >= ncol) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int g = 0; g < 9; ++g) {
     const int dd = d + g / 3 - 1, hh = h + g % 3 - 1;
     if ((unsigned)dd >= (unsigned)p.D || (unsigned)hh >= (unsigned)p.H) continue;
-    const float* src = p.Y + ((long long)n * KW_N + g * 16) * V + ((long long)dd * p.H + hh) * p.W + w;
-    float v[16];
+    const float* src = p.Y + ((long long)n * KW_N + g * 16 + c0) * V + ((long long)dd * p.H + hh) * p.W + w;
+    float v[4];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = __ldg(src + (long long)c * V);
+    for (int c = 0; c < 4; ++c) v[c] = __ldg(src + (long long)c * V);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = __fadd_rn(acc[c], v[c]);
+    for (int c = 0; c < 4; ++c) acc[c] = __fadd_rn(acc[c], v[c]);
   }
   const long long prior = p.prior_off + (((long long)d * p.H + h) * p.W + w) * p.bpl;
   float* lp = p.locs + ((long long)n * p.P + prior) * 6;
   float* sp = p.scores + ((long long)n * p.P + prior) * p.n_classes;
   bool bad_l = false, bad_s = false;
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
+  for (int q = 0; q < 4; ++q) {
+    const int c = c0 + q;
     if (c >= ncol) break;
-    const float val = __fadd_rn(acc[c], __ldg(p.bias + c));
+    const float val = __fadd_rn(acc[q], __ldg(p.bias + c));
     if (c < p.n_loc) { lp[c] = val; bad_l |= (val != val); }
     else { sp[c - p.n_loc] = val; bad_s |= (val != val); }
   }
@@ -293,7 +298,7 @@ int ssd3d_head_conv_kw(const void* x, const void* w, int w_is_kw, const float* b
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)m_tiles, (unsigned)(KW_N / p.BN));
   SSD3D_LAUNCH_PDL(head_kw_gemm_kernel, grid, dim3(192), smem, st, tmA, tmB, p);
-  SSD3D_LAUNCH_PDL(head_stencil_kernel, dim3((unsigned)((M + 127) / 128)), dim3(128), 0, st, p);
+  SSD3D_LAUNCH_PDL(head_stencil_kernel, dim3((unsigned)((M + 31) / 32)), dim3(128), 0, st, p);
   return SSD3D_OK;
 }
 
