@@ -308,6 +308,21 @@ int ssd3d_bn_train_fwd(const void* z, int64_t M, int C, const float* gamma, cons
 int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, int C, const float* scale, const float* shift,
                       const float* mean, const float* invstd, float* dgamma, float* dbeta, void* dz, void* workspace,
                       int64_t workspace_bytes, void* stream);
+/* The same two passes as ONE launch each (csrc/bn_unit.cu): column sums, cross-CTA finalize and the elementwise
+ * apply are three phases of a grid of at most one CTA per SM, separated by grid-wide barriers.  Arguments as
+ * above plus `sync_words`: three device uint32, zero before the first launch, private to the calling stream (the
+ * kernel leaves them zero).  ssd3d_bn_unit_supported: 1 if (M, C) can take this path (C/8 a power of two in
+ * [4, 512]); workspace: ssd3d_bn_unit_workspace_bytes(C).  Replaces the same reference lines
+ * (nn.BatchNorm3d + ReLU in train mode and their autograd backward, mobilenet.py:29-30,44-45). */
+int ssd3d_bn_unit_supported(int64_t M, int C);
+int64_t ssd3d_bn_unit_workspace_bytes(int C);
+int ssd3d_bn_unit_fwd(const void* z, int64_t M, int C, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                      float* scale, float* shift, float* mean, float* invstd, void* a, int* nan_flag,
+                      void* workspace, int64_t workspace_bytes, uint32_t* sync_words, void* stream);
+int ssd3d_bn_unit_bwd(const void* z, const void* grad_a, int64_t M, int C, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, float* dgamma, float* dbeta, void* dz, void* workspace,
+                      int64_t workspace_bytes, uint32_t* sync_words, void* stream);
 
 /* Weight gradients, dW = dz^T . im2col(x), split over rows and reduced in a fixed order.
  * workspace: ssd3d_wgrad_workspace_bytes(M, n_out, K) with (n_out, K) = (Cout, Cin) pointwise,

@@ -87,6 +87,11 @@ SIGNATURES = {
     "ssd3d_gt_boxes_from_instances": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, P,
                                               P, P, c_int64, P]),
     "ssd3d_bn_relu_bwd": (c_int, [P, P, c_int64, c_int, P, P, P, P, P, P, P, P, c_int64, P]),
+    "ssd3d_bn_unit_supported": (c_int, [c_int64, c_int]),
+    "ssd3d_bn_unit_workspace_bytes": (c_int64, [c_int]),
+    "ssd3d_bn_unit_fwd": (c_int, [P, c_int64, c_int, P, P, c_float, c_float, P, P, P, P, P, P, P, P, P, P, c_int64, P,
+                                  P]),
+    "ssd3d_bn_unit_bwd": (c_int, [P, P, c_int64, c_int, P, P, P, P, P, P, P, P, c_int64, P, P]),
     "ssd3d_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "ssd3d_pwconv_wgrad": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P]),
     "ssd3d_stem_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int64, P]),

@@ -1269,28 +1269,37 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ 
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   const long long o_begin = (long long)blockIdx.x * vox_per_block;
   const long long o_end = (o_begin + vox_per_block < Mo) ? o_begin + vox_per_block : Mo;
+  // the ten loads of a voxel (gradient row + nine taps, zero outside the map) are issued together: with the loads
+  // inside the bounds branches the loop ran one L2 latency per tap (22-35 us on the 3^3 / 6^3 maps of the C3 step)
   for (long long o = o_begin + g; o < o_end; o += G) {
-    long long t = o;
-    const int ow = (int)(t % Wo); t /= Wo;
-    const int oh = (int)(t % Ho); t /= Ho;
-    const int od = (int)(t % Do); t /= Do;
+    unsigned t = (unsigned)o;                 // Mo < 2^31 (checked by the launcher)
+    const int ow = (int)(t % (unsigned)Wo); t /= (unsigned)Wo;
+    const int oh = (int)(t % (unsigned)Ho); t /= (unsigned)Ho;
+    const int od = (int)(t % (unsigned)Do); t /= (unsigned)Do;
     const int di = od * S + kd - 1;
     if ((unsigned)di >= (unsigned)D) continue;
-    float gf[8];
-    unpack8f(ld_nc16(dz + o * C + c0), gf);
+    const uint4 gu = ld_nc16(dz + o * C + c0);
+    const bf16* xrow = x + ((long long)t * D + di) * H * (long long)W * C + c0;
+    uint4 xu[9];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int hi = oh * S + kh - 1;
-      if ((unsigned)hi >= (unsigned)H) continue;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int wi = ow * S + kw - 1;
-        if ((unsigned)wi >= (unsigned)W) continue;
-        float xf[8];
-        unpack8f(ld_nc16(x + ((((long long)t * D + di) * H + hi) * W + wi) * C + c0), xf);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[kh * 3 + kw][j] = fmaf(gf[j], xf[j], acc[kh * 3 + kw][j]);
+        xu[kh * 3 + kw] = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W)
+          xu[kh * 3 + kw] = ld_nc16(xrow + ((long long)hi * W + wi) * C);
       }
+    }
+    float gf[8];
+    unpack8f(gu, gf);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float xf[8];
+      unpack8f(xu[k], xf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(gf[j], xf[j], acc[k][j]);
     }
   }
   float* dst = partial + (size_t)blockIdx.x * C * 27;
@@ -1821,7 +1830,7 @@ extern "C" int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C,
   int threads, G;
   long long vpb;
   const int B = dw_wgrad_plan(Mo, C, &threads, &G, &vpb);
-  if (B < 0) return SSD3D_ERR_UNSUPPORTED;
+  if (B < 0 || Mo >= (1ll << 31)) return SSD3D_ERR_UNSUPPORTED;
   if (workspace_bytes < (int64_t)B * C * 27 * 4) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = static_cast<float*>(workspace);

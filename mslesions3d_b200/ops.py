@@ -6,6 +6,8 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence, Tuple
 
+import os
+
 import numpy as np
 import torch
 
@@ -683,6 +685,22 @@ def pin_workspaces() -> None:
             _WS_PINNED.add(cur.data_ptr())
 
 
+def _sync_words(device) -> torch.Tensor:
+    """Barrier words of the single-launch BatchNorm kernels (csrc/bn_unit.cu): zero-initialised once per (device,
+    scratch slot) -- the kernels leave them zero -- and never freed (captured graphs bake the address in)."""
+    key = (str(device), "bn_sync", _WS_SLOT[0])
+    cur = _CONST.get(key)
+    if cur is None:
+        cur = torch.zeros((16,), dtype=torch.int32, device=device)
+        _CONST[key] = cur
+    return cur
+
+
+def _bn_unit_enabled() -> bool:
+    """SSD3D_BN_UNIT=0 selects the three-launch BatchNorm passes of train.cu (kept for A/B measurements)."""
+    return os.environ.get("SSD3D_BN_UNIT", "1") != "0"
+
+
 def stem_conv_raw(x: torch.Tensor, w_packed: torch.Tensor, stride_d: int) -> torch.Tensor:
     """Raw stem conv output (no BN, no ReLU), channels-last bf16."""
     _need_cuda(x, w_packed)
@@ -757,14 +775,19 @@ def bn_train_relu(z: torch.Tensor, bn: torch.nn.BatchNorm3d, nan_flag: Optional[
     if track and bn.momentum is None:
         raise NotImplementedError("cumulative-average BatchNorm (momentum=None) is not used by the reference")
     nbt = bn.num_batches_tracked if (track and bn.num_batches_tracked is not None) else None
-    rc = lib.ssd3d_bn_train_fwd(z.data_ptr(), m, c, _ptr(bn.weight.detach() if bn.weight is not None else None),
-                                _ptr(bn.bias.detach() if bn.bias is not None else None), float(bn.eps), momentum,
-                                _ptr(bn.running_mean if track else None), _ptr(bn.running_var if track else None),
-                                _ptr(nbt),
-                                st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
-                                a.data_ptr(), _ptr(nan_flag), ws.data_ptr(), ws.numel(), _stream())
-    _lib.check(rc, "ssd3d_bn_train_fwd")
-    LAUNCHES[0] += 3
+    args = (z.data_ptr(), m, c, _ptr(bn.weight.detach() if bn.weight is not None else None),
+            _ptr(bn.bias.detach() if bn.bias is not None else None), float(bn.eps), momentum,
+            _ptr(bn.running_mean if track else None), _ptr(bn.running_var if track else None), _ptr(nbt),
+            st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
+            a.data_ptr(), _ptr(nan_flag), ws.data_ptr(), ws.numel())
+    if _bn_unit_enabled() and lib.ssd3d_bn_unit_supported(m, c):
+        rc = lib.ssd3d_bn_unit_fwd(*args, _sync_words(z.device).data_ptr(), _stream())
+        _lib.check(rc, "ssd3d_bn_unit_fwd")
+        LAUNCHES[0] += 1
+    else:
+        rc = lib.ssd3d_bn_train_fwd(*args, _stream())
+        _lib.check(rc, "ssd3d_bn_train_fwd")
+        LAUNCHES[0] += 3
     if track:
         # the kernel updated the running statistics through raw pointers: bump their version counters (host-side
         # only, no launch) so that caches keyed on (data_ptr, _version) -- folded eval-mode BN, captured inference
@@ -779,11 +802,17 @@ def bn_relu_backward(z: torch.Tensor, grad_a: torch.Tensor, st: BNState, dgamma:
     n, c, d, h, w = z.shape
     lib = _lib.load()
     ws = _workspace(lib.ssd3d_bn_workspace_bytes(c), z.device)
-    rc = lib.ssd3d_bn_relu_bwd(z.data_ptr(), grad_a.data_ptr(), n * d * h * w, c, st.scale.data_ptr(),
-                               st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(), dgamma.data_ptr(),
-                               dbeta.data_ptr(), grad_a.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
-    _lib.check(rc, "ssd3d_bn_relu_bwd")
-    LAUNCHES[0] += 3
+    m = n * d * h * w
+    args = (z.data_ptr(), grad_a.data_ptr(), m, c, st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
+            st.invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), grad_a.data_ptr(), ws.data_ptr(), ws.numel())
+    if _bn_unit_enabled() and lib.ssd3d_bn_unit_supported(m, c):
+        rc = lib.ssd3d_bn_unit_bwd(*args, _sync_words(z.device).data_ptr(), _stream())
+        _lib.check(rc, "ssd3d_bn_unit_bwd")
+        LAUNCHES[0] += 1
+    else:
+        rc = lib.ssd3d_bn_relu_bwd(*args, _stream())
+        _lib.check(rc, "ssd3d_bn_relu_bwd")
+        LAUNCHES[0] += 3
     return grad_a
 
 

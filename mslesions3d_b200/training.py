@@ -368,8 +368,14 @@ class TrainEngine:
         side = self._wgrad_side_stream(main) if os.environ.get("SSD3D_TRAIN_WGRAD_STREAM", "1") != "0" else None
         keep = []
 
-        def leaf(fn, *tensors):
-            if side is None:
+        # ... except the heavy ones (the first blocks' maps, tens of MB): they are HBM-bound like the main-chain kernels
+        # around them, so overlapping buys nothing, and their persistent CTAs (180 registers, ~200 KB of shared
+        # memory) would keep the all-resident BatchNorm grids of the main chain (csrc/bn_unit.cu) waiting for SMs.
+        # They run in order on the main stream.
+        heavy_bytes = float(os.environ.get("SSD3D_TRAIN_HEAVY_LEAF_MB", "16")) * 2 ** 20
+
+        def leaf(fn, *tensors, nbytes=0):
+            if side is None or nbytes >= heavy_bytes:
                 fn()
                 return
             side.wait_stream(main)
@@ -414,7 +420,8 @@ class TrainEngine:
                 dz2 = ops.bn_relu_backward(u["z2"], g, u["st2"], grads[p + ".bn2.weight"], grads[p + ".bn2.bias"])
                 if r is not None:
                     r["dz2"] = snap(dz2)
-                leaf(lambda dz2=dz2, u=u, p=p: ops.pwconv_wgrad(dz2, u["a1"], grads[p + ".conv2.weight"]), dz2)
+                leaf(lambda dz2=dz2, u=u, p=p: ops.pwconv_wgrad(dz2, u["a1"], grads[p + ".conv2.weight"]), dz2,
+                     nbytes=2 * (dz2.numel() + u["a1"].numel()))
                 g1 = torch.empty_like(u["a1"])
                 nn_, c1, d1, h1, w1 = u["a1"].shape
                 wt = u["wpt"] if u["wpt"] is not None else u["wp"].t().contiguous()   # (Cin, Cout): dx = dz . W
@@ -425,7 +432,8 @@ class TrainEngine:
                 if r is not None:
                     r["dz1"] = snap(dz1)
                 leaf(lambda dz1=dz1, u=u, p=p: ops.dwconv3d_wgrad(dz1, u["x"], u["stride"],
-                                                                  grads[p + ".conv1.weight"]), dz1)
+                                                                  grads[p + ".conv1.weight"]), dz1,
+                     nbytes=2 * (dz1.numel() + u["x"].numel()))
                 g = ops.dwconv3d_dgrad(dz1, u["wd"], u["x"], u["stride"])
                 if r is not None:
                     r["dx"] = snap(g)

@@ -100,6 +100,50 @@ def test_bn_train_relu_forward_backward(n, c, size):
     assert torch.equal(dg2, dgamma) and torch.equal(db2, dbeta)
 
 
+@pytest.mark.parametrize("n,c,size", [(16, 32, (24, 24, 24)), (4, 32, (48, 48, 48)), (16, 64, (12, 12, 12)),
+                                      (16, 1024, (3, 3, 3)), (16, 512, (6, 6, 6)), (16, 128, (6, 6, 6)), (1, 32, (1, 1, 3)),
+                                      (3, 128, (7, 5, 3)), (16, 256, (12, 12, 12)),
+                                      # more than 32768 rows: the grid-barrier kernel, C/8 = 32, 64, 128
+                                      (1, 256, (34, 33, 31)), (1, 512, (33, 32, 32)), (2, 1024, (17, 32, 32))])
+def test_bn_single_launch_matches_three_launch_path(n, c, size, monkeypatch):
+    """csrc/bn_unit.cu (one launch, grid barriers) against the three-launch passes of train.cu on the same inputs:
+    same statistics to fp32 rounding, same activations / gradients to 1 bf16 ulp; repeated launches (the barrier
+    words are reused) are bit-identical; the launch counter shows which path ran."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(7 * c + n)
+    z = to_cl(bf16r(torch.randn((n, c) + size, generator=g) * 1.3 + 0.4 * torch.randn(1, c, 1, 1, 1, generator=g)))
+    ga = to_cl(bf16r(torch.randn((n, c) + size, generator=g)))
+    res = {}
+    for mode in ("0", "1", "1"):
+        monkeypatch.setenv("SSD3D_BN_UNIT", mode)
+        bn = torch.nn.BatchNorm3d(c)
+        with torch.no_grad():
+            bn.weight.copy_(0.5 + torch.rand(c, generator=torch.Generator().manual_seed(c)))
+            bn.bias.copy_(0.2 * torch.randn(c, generator=torch.Generator().manual_seed(c + 1)))
+        bn = bn.cuda().train()
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        before = ops.LAUNCHES[0]
+        a, st = ops.bn_train_relu(z, bn, flag)
+        assert ops.LAUNCHES[0] - before == (1 if mode == "1" else 3)
+        dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+        dz = ops.bn_relu_backward(z, ga.clone(), st, dgamma, dbeta)
+        torch.cuda.synchronize()
+        cur = dict(a=a, dz=dz, dgamma=dgamma, dbeta=dbeta, scale=st.scale, shift=st.shift, mean=st.mean,
+                   invstd=st.invstd, rm=bn.running_mean.clone(), rv=bn.running_var.clone(), flag=int(flag),
+                   nbt=int(bn.num_batches_tracked))
+        if mode == "1" and "1" in res:
+            for k in ("a", "dz", "dgamma", "dbeta", "scale", "shift", "mean", "invstd", "rm", "rv"):
+                assert torch.equal(cur[k], res["1"][k]), "single-launch path not reproducible: " + k
+        res[mode] = cur
+    three, one = res["0"], res["1"]
+    assert one["flag"] == 0 and one["nbt"] == 1
+    for k in ("scale", "shift", "mean", "invstd", "rm", "rv"):
+        torch.testing.assert_close(one[k], three[k], rtol=2e-6, atol=1e-6)
+    assert rel_l2(one["dgamma"], three["dgamma"]) < 1e-5 and rel_l2(one["dbeta"], three["dbeta"]) < 1e-5
+    assert_bf16_close(one["a"], three["a"], "single-launch bn forward")
+    assert_bf16_close(one["dz"], three["dz"], "single-launch bn backward")
+
+
 def test_bn_train_nan_sets_flag():
     ops = _ops()
     z = torch.randn(1, 32, 4, 4, 4)

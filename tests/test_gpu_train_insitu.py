@@ -63,7 +63,18 @@ def check_unit(name, conv, x_own, w_param, z_own, st, a_own, g_own, dz_own, bn_m
     torch.testing.assert_close(st.mean.cpu(), mean, rtol=1e-4, atol=1e-5, msg=name + " batch mean")
     torch.testing.assert_close(st.invstd.cpu(), 1.0 / torch.sqrt(var + EPS), rtol=1e-4, atol=1e-6, msg=name + " invstd")
     a_ref.backward(g_own)
-    bad = bf16_mismatch(dz_own, bf16r(zl.grad), 1.5)
+    # ReLU ties: z is bf16, so several elements of a channel share one value; where that value's pre-activation
+    # z*scale+shift cancels to within a few fp32 ulps of its terms, its sign (the ReLU mask) depends on how the
+    # implementation rounds scale / shift -- not an error of either side.  Such elements take the reference value.
+    with torch.no_grad():
+        shape = (1, -1, 1, 1, 1)
+        sc64 = (gamma.double() / torch.sqrt(var.double() + EPS)).reshape(shape)
+        zs = z_own.double() * sc64
+        sh64 = (beta.double() - mean.double() * sc64.flatten()).reshape(shape)
+        tie = (zs + sh64).abs() <= 4e-6 * (zs.abs() + sh64.abs())
+        assert float(tie.float().mean()) <= 1e-3, "%s: implausibly many ReLU ties" % name
+        dz_cmp = torch.where(tie, bf16r(zl.grad), dz_own)
+    bad = bf16_mismatch(dz_cmp, bf16r(zl.grad), 1.5)
     r_g, r_b = rel_l2(bn_mod.weight.grad, gamma.grad), rel_l2(bn_mod.bias.grad, beta.grad)
     # a ReLU whose pre-activation rounds to the other side of 0 flips one element: allow a vanishing fraction
     assert bad <= 2e-5, "%s BN+ReLU backward dz: %.2e of elements beyond 1.5 bf16 ulp" % (name, bad)
