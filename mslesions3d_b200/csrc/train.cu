@@ -1591,12 +1591,28 @@ static int run_wgrad(WgradParams& p, int n_out, cudaStream_t st, int* splits_out
   return SSD3D_OK;
 }
 
+// wgrad_tc.cu: the same contraction on tcgen05 (MN-major UMMA operands straight from TMA)
+namespace ssd3d {
+int64_t wgrad_tc_workspace_bytes(long long M, int Cin, int Cout);
+int wgrad_tc_launch(const void* dz, const void* x, long long M, int Cin, int Cout, float* dw, float* partial,
+                    cudaStream_t st);
+}
+// SSD3D_WGRAD_TC=0 keeps the mma.sync kernel (A/B measurements, and the shapes the tcgen05 tiling does not take)
+static const bool g_wgrad_tc = [] { const char* e = getenv("SSD3D_WGRAD_TC"); return !(e && e[0] == '0'); }();
+
 extern "C" int ssd3d_pwconv_wgrad(const void* dz, const void* x, int64_t M, int Cin, int Cout, float* dw,
                                   void* workspace, int64_t workspace_bytes, void* stream) {
   if (!dz || !x || !dw || !workspace || M <= 0) return SSD3D_ERR_ARG;
   if (Cin <= 0 || (Cin % 32) || Cout <= 0 || (Cout % 64)) return SSD3D_ERR_ARG;
   if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, Cout, Cin)) return SSD3D_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_wgrad_tc && workspace_bytes >= wgrad_tc_workspace_bytes(M, Cin, Cout)) {
+    const int S = wgrad_tc_launch(dz, x, M, Cin, Cout, dw, static_cast<float*>(workspace), st);
+    if (S == 1) return SSD3D_OK;
+    if (S > 1)
+      return launch_sum_partials((const float*)workspace, S, (long long)Cout * Cin, Cout, Cin, Cin, Cin, dw, st);
+    if (S < -1) return SSD3D_ERR_ARG;       // -1: shape not taken by the tcgen05 tiling -> mma.sync kernel below
+  }
   WgradParams p{};
   p.dz = static_cast<const bf16*>(dz); p.ldz = Cout; p.M = M;
   p.K = (Cin + 63) / 64 * 64;

@@ -1,0 +1,227 @@
+// Pointwise-conv weight gradient on tcgen05 (autograd of nn.Conv3d(kernel_size=1), mobilenet.py:40 under
+// LSSD3D.training_step, ssd3d.py:467-531):
+//
+//      dW[n][k] = sum_m dz[m][n] * x[m][k]          dz (M, Cout) bf16, x (M, Cin) bf16, dW (Cout, Cin) fp32
+//
+// Both operands are channels-last, so the reduction index m (the voxel) is the SLOW index of both: in UMMA terms
+// A = dz^T and B = x^T are "MN-major" operands.  That is exactly what a plain TMA box of [64 voxels][64 channels]
+// with the 128-byte swizzle puts into shared memory -- rows of 128 B = 64 channels (the M / N index, contiguous),
+// one row per voxel (the K index), 16-byte chunks XOR-ed with the row index modulo 8 -- i.e. the canonical MN-major
+// SWIZZLE_128B layout  ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO))  in elements (cute::UMMA::make_umma_desc<Major::MN>):
+// SBO = 1024 B between 8-voxel groups, LBO = the box size between 64-channel blocks.  No transposition pass, no
+// ldmatrix.trans: the instruction descriptor's a_major / b_major bits tell the tensor core to read them that way.
+// Cin = 32 (the first block) has 64-byte rows: same scheme with the 64-byte swizzle.
+//
+// Work item = (128 output channels, <= 128 input channels, a contiguous range of 64-voxel chunks); CTA = 192 threads:
+// warp 0 TMA producer, warp 1 TMEM owner + single-lane UMMA issue (4 x K16 per chunk), warps 2-5 epilogue
+// (TMEM lane quarter = warp % 4) writing the fp32 tile of this voxel range to its slab; the slabs are added in a
+// fixed order by sum_partials (train.cu), or the tile goes straight to dW when there is a single range.
+// Out-of-range voxels and output channels >= Cout are zero-filled by the TMA unit.
+#include "common.cuh"
+#include "tma_host.h"
+
+namespace ssd3d {
+
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+constexpr int WT_KT = 64;            // voxels per stage
+constexpr int WT_STAGES = 4;
+constexpr int WT_THREADS = 192;
+constexpr int WT_A_BYTES = 2 * WT_KT * 128;        // two 64-channel boxes of dz
+constexpr int WT_B_BYTES = 2 * WT_KT * 128;        // up to two 64-channel boxes of x
+constexpr int WT_STAGE_BYTES = WT_A_BYTES + WT_B_BYTES;
+constexpr int WT_SMEM = WT_STAGES * WT_STAGE_BYTES + 1024 /*alignment*/ + 256 /*barriers*/;
+
+struct WgradTcParams {
+  long long M;
+  int Cin, Cout;
+  int NT;                  // input channels per tile: 32, 64 or 128
+  int chunks_per_split;
+  int n_chunks;            // ceil(M / 64)
+  int ld;                  // row pitch of the output (floats)
+  long long slab;          // floats between two voxel ranges' outputs
+  float* out;
+};
+
+// MN-major operand: `row_bytes` = 128 (SWIZZLE_128B, 64 channels per row) or 64 (SWIZZLE_64B, 32 channels)
+__device__ __forceinline__ uint64_t desc_mn(uint32_t smem_addr, uint32_t row_bytes, uint32_t block_stride) {
+  const uint32_t lbo = block_stride, sbo = 8 * row_bytes;
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(row_bytes == 128 ? 2u : 4u) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZ,
+                                                                 const __grid_constant__ CUtensorMap tmX,
+                                                                 const WgradTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)WT_STAGES * WT_STAGE_BYTES);
+  uint64_t* empty = full + WT_STAGES;
+  uint64_t* acc_full = empty + WT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NT = p.NT;
+  const uint32_t tmem_cols = NT < 32 ? 32u : (uint32_t)NT;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmZ);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < WT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int k0 = blockIdx.x * NT;            // first input channel of the tile
+  const int n0 = blockIdx.y * 128;           // first output channel
+  const int c_begin = blockIdx.z * p.chunks_per_split;
+  int c_end = c_begin + p.chunks_per_split;
+  if (c_end > p.n_chunks) c_end = p.n_chunks;
+  const int n_iter = c_end - c_begin;
+  const uint32_t x_row = NT >= 64 ? 128u : 64u;                    // bytes per voxel row of one x box
+  const int x_boxes = NT >= 64 ? NT / 64 : 1;
+  const uint32_t x_box_bytes = WT_KT * x_row;
+  const uint32_t stage_tx = WT_A_BYTES + (uint32_t)x_boxes * x_box_bytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % WT_STAGES;
+        if (it >= WT_STAGES) mbar_wait(&empty[s], ((it / WT_STAGES) - 1) & 1);
+        uint8_t* a = smem + (size_t)s * WT_STAGE_BYTES;
+        uint8_t* b = a + WT_A_BYTES;
+        const int m0 = (c_begin + it) * WT_KT;
+        mbar_arrive_expect_tx(&full[s], stage_tx);
+        tma_load_2d(a, &tmZ, &full[s], n0, m0);
+        tma_load_2d(a + WT_KT * 128, &tmZ, &full[s], n0 + 64, m0);      // all zero when n0 + 64 >= Cout
+        for (int j = 0; j < x_boxes; ++j) tma_load_2d(b + (size_t)j * x_box_bytes, &tmX, &full[s], k0 + 64 * j, m0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // a_major = b_major = MN (bits 15, 16 of the instruction descriptor)
+      const uint32_t idesc = umma_idesc_bf16(128, NT) | (1u << 15) | (1u << 16);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % WT_STAGES;
+        mbar_wait(&full[s], (it / WT_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a = smem_u32(smem + (size_t)s * WT_STAGE_BYTES);
+        const uint32_t b = a + WT_A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < WT_KT / 16; ++ks) {
+          const uint64_t da = desc_mn(a + ks * 16 * 128, 128, WT_KT * 128);
+          const uint64_t db = desc_mn(b + ks * 16 * x_row, x_row, x_box_bytes);
+          umma_bf16_ss(tmem_base, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);               // the stage is free once these UMMAs have read it
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ===================== epilogue: TMEM -> fp32 tile of this voxel range =====================
+    const int q = warp & 3;                   // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;            // output channel within the tile
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const bool valid = (n0 + row) < p.Cout && n_iter > 0;
+    float* dst = p.out + (size_t)blockIdx.z * p.slab + (size_t)(n0 + row) * p.ld + k0;
+    for (int c = 0; c < NT; c += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + c + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace
+
+// plan shared with the workspace query: tiles, voxel ranges
+static void wgrad_tc_plan(long long M, int Cin, int Cout, int* NT, int* tiles, int* splits, int* cps) {
+  *NT = Cin >= 128 ? 128 : Cin;                       // 32, 64, 128
+  const int kt = Cin / *NT, nt = (Cout + 127) / 128;
+  *tiles = kt * nt;
+  const int chunks = (int)((M + WT_KT - 1) / WT_KT);
+  int s = persistent_sms() / *tiles;
+  if (s < 1) s = 1;
+  const int by_work = (chunks + 3) / 4;               // at least four chunks per range: the pipeline has to fill
+  if (s > by_work) s = by_work;
+  if (s < 1) s = 1;
+  *cps = (chunks + s - 1) / s;
+  *splits = (chunks + *cps - 1) / *cps;
+}
+
+int64_t wgrad_tc_workspace_bytes(long long M, int Cin, int Cout) {
+  int NT, tiles, S, cps;
+  wgrad_tc_plan(M, Cin, Cout, &NT, &tiles, &S, &cps);
+  return S > 1 ? (int64_t)S * Cout * Cin * 4 : 0;
+}
+
+// -> number of voxel ranges S written ([S][Cout][Cin] in `partial`; S == 1: written to dw directly), < 0: error
+int wgrad_tc_launch(const void* dz, const void* x, long long M, int Cin, int Cout, float* dw, float* partial,
+                    cudaStream_t st) {
+  if (M <= 0 || M >= (1ll << 31) - 64 || (Cin != 32 && Cin % 64) || Cin <= 0 || Cout <= 0 || (Cout % 64)) return -1;
+  if (Cin > 128 && Cin % 128) return -1;
+  WgradTcParams p{};
+  int tiles, S, cps;
+  wgrad_tc_plan(M, Cin, Cout, &p.NT, &tiles, &S, &cps);
+  p.M = M; p.Cin = Cin; p.Cout = Cout;
+  p.chunks_per_split = cps;
+  p.n_chunks = (int)((M + WT_KT - 1) / WT_KT);
+  p.ld = Cin;
+  p.slab = (long long)Cout * Cin;
+  p.out = S > 1 ? partial : dw;
+  CUtensorMap tmZ, tmX;
+  {
+    const uint64_t dims[2] = {(uint64_t)Cout, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)Cout * 2};
+    const uint32_t box[2] = {64u, (uint32_t)WT_KT};
+    if (make_tma_bf16(&tmZ, dz, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return -2;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)Cin * 2};
+    const uint32_t box[2] = {Cin >= 64 ? 64u : 32u, (uint32_t)WT_KT};
+    if (make_tma_bf16(&tmX, x, 2, dims, strides, box, Cin >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+      return -2;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM) != cudaSuccess)
+      return -3;
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)(Cin / p.NT), (unsigned)((Cout + 127) / 128), (unsigned)S);
+  if (launch_pdl(wgrad_tc_kernel, grid, dim3(WT_THREADS), (size_t)WT_SMEM, st, tmZ, tmX, p) != cudaSuccess) return -4;
+  return S;
+}
+
+}  // namespace ssd3d
