@@ -60,8 +60,8 @@ __device__ __forceinline__ unsigned bu_ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// All G CTAs are resident (G <= SM count, one CTA per SM fits by construction), so spinning cannot starve a CTA
-// that has not started yet.  bar.sync orders the CTA's earlier writes before thread 0's fence + arrive.
+// All G CTAs are resident (G <= SM count, one CTA per SM fits by construction, cooperative launch), so spinning
+// cannot starve a CTA that has not started yet.  bar.sync orders the CTA's earlier writes before thread 0's fence + arrive.
 __device__ __forceinline__ void bu_grid_barrier(unsigned* word, unsigned G) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -579,6 +579,24 @@ int bn_cluster_plan(long long M, int C, long long* rows_per_cta, int* R) {
   return K;
 }
 
+// The grid-barrier kernel is launched COOPERATIVELY: the driver then guarantees that all CTAs are co-resident
+// (and refuses grids that cannot be), also when kernels of other streams hold SMs, and two such grids of different
+// streams cannot each end up half resident waiting for the other.  (No programmatic dependent launch on this one.)
+template <int MODE>
+cudaError_t launch_bn_unit(const BnUnitParams& p, int G, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)G);
+  cfg.blockDim = dim3(BU_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, bn_unit_kernel<MODE>, p);
+}
+
 template <int MODE, int R>
 cudaError_t launch_bn_cluster(const BnUnitParams& p, int K, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
@@ -665,8 +683,8 @@ extern "C" int ssd3d_bn_unit_fwd(const void* z, int64_t M, int C, const float* g
     const cudaError_t e = launch_bn_cluster_r<0>(p, K, R, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? SSD3D_OK : (int)e;
   }
-  SSD3D_LAUNCH_PDL(bn_unit_kernel<0>, dim3(G), dim3(BU_THREADS), 0, static_cast<cudaStream_t>(stream), p);
-  return SSD3D_OK;
+  const cudaError_t e = launch_bn_unit<0>(p, G, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SSD3D_OK : (int)e;
 }
 
 extern "C" int ssd3d_bn_unit_bwd(const void* z, const void* grad_a, int64_t M, int C, const float* scale,
@@ -695,6 +713,6 @@ extern "C" int ssd3d_bn_unit_bwd(const void* z, const void* grad_a, int64_t M, i
     const cudaError_t e = launch_bn_cluster_r<1>(p, K, R, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? SSD3D_OK : (int)e;
   }
-  SSD3D_LAUNCH_PDL(bn_unit_kernel<1>, dim3(G), dim3(BU_THREADS), 0, static_cast<cudaStream_t>(stream), p);
-  return SSD3D_OK;
+  const cudaError_t e = launch_bn_unit<1>(p, G, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SSD3D_OK : (int)e;
 }

@@ -1812,7 +1812,11 @@ static int dw_wgrad_plan(long long Mo, int C, int* threads, int* G, long long* v
   if (C <= 0 || (C & 7) || CV * 3 > 256) return -1;
   *G = 256 / (CV * 3);
   *threads = CV * 3 * (*G);
-  static const int vpl = [] { const char* e = getenv("SSD3D_DW_WGRAD_VPL"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : v; }();
+  // voxels per voxel lane: the loop over them is serial (one L2 round trip + ~350 instructions each, 1-2 warps per
+  // scheduler), so small maps get as few as 2 -- ~1.5 CTAs per SM -- and pay with more slabs; large ones 8
+  static const int vpl_env = [] { const char* e = getenv("SSD3D_DW_WGRAD_VPL"); return e ? atoi(e) : 0; }();
+  long long vpl = vpl_env > 0 ? vpl_env : Mo / ((long long)(*G) * 222);
+  if (vpl_env <= 0) vpl = vpl < 2 ? 2 : (vpl > 8 ? 8 : vpl);
   long long B = (Mo + (*G) * vpl - 1) / ((*G) * vpl);       // >= vpl voxels per voxel lane
   if (B > 592) B = 592;
   if (B < 1) B = 1;

@@ -230,8 +230,15 @@ class TrainEngine:
 
     def _wgrad_side_stream(self, main):
         """Second stream of the backward pass (weight gradients), on ``main``'s device."""
-        if self._side is None or self._side.device != main.device:
-            self._side = torch.cuda.Stream(device=main.device)
+        return self._side_streams(main)[0]
+
+    def _side_streams(self, main):
+        """The side streams of the step: the weight-gradient leaves are dealt round-robin over them (each is a few
+        small launches -- tens of CTAs -- so independent leaves run next to each other instead of queueing behind
+        one another); every stream has its own scratch slot.  SSD3D_TRAIN_SIDE_STREAMS sets the count."""
+        n = max(1, int(os.environ.get("SSD3D_TRAIN_SIDE_STREAMS", "3")))
+        if self._side is None or self._side[0].device != main.device or len(self._side) != n:
+            self._side = [torch.cuda.Stream(device=main.device) for _ in range(n)]
         return self._side
 
     # ------------------------------------------------------------------------------------------
@@ -365,8 +372,10 @@ class TrainEngine:
         # gradient tensors the side stream reads are kept alive until the join (the allocator would hand their
         # memory to a later main-stream tensor otherwise); the side stream has its own scratch slot.
         main = torch.cuda.current_stream()
-        side = self._wgrad_side_stream(main) if os.environ.get("SSD3D_TRAIN_WGRAD_STREAM", "1") != "0" else None
+        sides = self._side_streams(main) if os.environ.get("SSD3D_TRAIN_WGRAD_STREAM", "1") != "0" else None
+        side = sides[0] if sides else None
         keep = []
+        n_leaf = [0]
 
         # ... except the heavy ones (the first blocks' maps, tens of MB): they are HBM-bound like the main-chain kernels
         # around them, so overlapping buys nothing, and their persistent CTAs (180 registers, ~200 KB of shared
@@ -378,10 +387,12 @@ class TrainEngine:
             if side is None or nbytes >= heavy_bytes:
                 fn()
                 return
-            side.wait_stream(main)
-            ops._WS_SLOT[0] = "ws_side"
+            k = n_leaf[0] % len(sides)
+            n_leaf[0] += 1
+            sides[k].wait_stream(main)
+            ops._WS_SLOT[0] = "ws_side" if k == 0 else "ws_side%d" % k
             try:
-                with torch.cuda.stream(side):
+                with torch.cuda.stream(sides[k]):
                     fn()
             finally:
                 ops._WS_SLOT[0] = "ws"
@@ -445,8 +456,9 @@ class TrainEngine:
                     r["dz"] = snap(dz)
                 ops.stem_wgrad(dz, u["x"], u["stride"], grads[p + ".0.weight"])
                 g = None
-        if side is not None:
-            main.wait_stream(side)
+        if sides is not None:
+            for st in sides:
+                main.wait_stream(st)
         del keep
 
 
