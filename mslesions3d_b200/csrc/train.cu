@@ -1596,6 +1596,8 @@ namespace ssd3d {
 int64_t wgrad_tc_workspace_bytes(long long M, int Cin, int Cout);
 int wgrad_tc_launch(const void* dz, const void* x, long long M, int Cin, int Cout, float* dw, float* partial,
                     cudaStream_t st);
+int head_wgrad_tc_launch(const void* dO16, const void* x, int N, int C, int D, int H, int W, int g, int n_loc, int n_cls,
+                         float* dw_loc, float* dw_cls, float* workspace, int64_t workspace_bytes, cudaStream_t st);
 }
 // SSD3D_WGRAD_TC=0 keeps the mma.sync kernel (A/B measurements, and the shapes the tcgen05 tiling does not take)
 static const bool g_wgrad_tc = [] { const char* e = getenv("SSD3D_WGRAD_TC"); return !(e && e[0] == '0'); }();
@@ -1657,6 +1659,12 @@ extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int
   const int groups = (n_loc + n_cls + 15) / 16;      // 16 output columns per pass (dO is (groups, M, 16))
   for (int g = 0; g < groups; ++g) {
     const bf16* dOg = static_cast<const bf16*>(dO) + (size_t)g * M * 16;
+    if (g_wgrad_tc) {
+      const int rc = head_wgrad_tc_launch(dOg, x, N, C, D, H, W, g, n_loc, n_cls, dw_loc, dw_cls,
+                                          static_cast<float*>(workspace), workspace_bytes, st);
+      if (rc == 0) continue;
+      if (rc < -1) return SSD3D_ERR_ARG;    // -1: no 64-voxel box fits this map -> mma.sync kernel below
+    }
     if (use_g) {
       HeadWgradParams q{};
       q.dO = dOg; q.x = static_cast<const bf16*>(x);

@@ -162,6 +162,171 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const __grid_co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// SSD head (3x3x3, pad 1) weight gradient on tcgen05, one 16-column group of the packed [loc | class] gradient rows
+// (autograd of the loc_convs / cl_convs of PredictionConvolutions, ssd3d.py:131-167):
+//
+//      dW[c][tap][n] = sum_u x[u][c] * dO[u - off(tap)][n]           u = voxel, off(tap) = (kd-1, kh-1, kw-1)
+//
+// i.e. for each kd ONE GEMM  D[c][j*16 + n]  (M = 128 channels, N = 9 (kh,kw) taps x 16 columns = 144, K = voxels)
+// whose B operand is nine shifted views of the (voxel, 16) gradient rows.  K runs over 64-voxel BOXES
+// (bw x bh x bd x bn of the map, chosen per map): a 5-D TMA box of x gives the A rows, the same box shifted by the tap
+// gives that tap's 64 x 16 B block, and voxels outside the map -- the conv's zero padding, and the ragged edge of the
+// tiling -- are zero-filled by the TMA unit in both.  Both operands are MN-major: A as in the pointwise kernel
+// (128-byte rows, SWIZZLE_128B), B with 32-byte rows (16 columns) under SWIZZLE_32B, canonical layout
+// ((8,2,m),(8,k)) : ((1,8,LBO),(16,SBO)) -- SBO = 256 B between 8-voxel groups, LBO = 2 KB between taps.
+// CTA = (128-channel tile, kd, range of boxes); same warp roles as above; the fp32 tile goes to the slab
+// [range][kd][C][144], and head_wsum_kernel adds the ranges in order and scatters to dw_loc / dw_cls (Cout, C, 27).
+// ------------------------------------------------------------------------------------------------
+constexpr int HT_STAGES = 4;
+constexpr int HT_A_BYTES = 2 * 64 * 128;                 // 128 channels x 64 voxels
+constexpr int HT_B_BYTES = 9 * 64 * 32;                  // 9 taps x 64 voxels x 16 columns
+constexpr int HT_STAGE_BYTES = 35 * 1024;                // A + B = 34 KB, stages 1 KB aligned
+constexpr int HT_SMEM = HT_STAGES * HT_STAGE_BYTES + 1024 + 256;
+
+struct HeadWgradTcParams {
+  int C;
+  int bw, bh, bd, bn;          // box extent (product 64)
+  int tw, th, td;              // boxes along W, H, D (tn follows from the total)
+  int n_boxes, boxes_per_split;
+  float* slab;                 // [split][3][C][144]
+};
+
+__device__ __forceinline__ uint64_t desc_mn_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(2048u >> 4) << 16;      // LBO: next 16-column block = next tap
+  d |= (uint64_t)(256u >> 4) << 32;       // SBO: next group of 8 voxels
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                 // SWIZZLE_32B
+  return d;
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1) head_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                      const __grid_constant__ CUtensorMap tmG,
+                                                                      const HeadWgradTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)HT_STAGES * HT_STAGE_BYTES);
+  uint64_t* empty = full + HT_STAGES;
+  uint64_t* acc_full = empty + HT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 256;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmG);
+    for (int s = 0; s < HT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int c0 = blockIdx.x * 128;
+  const int kd = blockIdx.y;
+  const int b_begin = blockIdx.z * p.boxes_per_split;
+  int b_end = b_begin + p.boxes_per_split;
+  if (b_end > p.n_boxes) b_end = p.n_boxes;
+  const int n_iter = b_end - b_begin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % HT_STAGES;
+        if (it >= HT_STAGES) mbar_wait(&empty[s], ((it / HT_STAGES) - 1) & 1);
+        uint8_t* a = smem + (size_t)s * HT_STAGE_BYTES;
+        uint8_t* b = a + HT_A_BYTES;
+        int t = b_begin + it;
+        const int w0 = (t % p.tw) * p.bw; t /= p.tw;
+        const int h0 = (t % p.th) * p.bh; t /= p.th;
+        const int d0 = (t % p.td) * p.bd; t /= p.td;
+        const int n0 = t * p.bn;
+        mbar_arrive_expect_tx(&full[s], HT_A_BYTES + HT_B_BYTES);
+        tma_load_5d(a, &tmX, &full[s], c0, w0, h0, d0, n0);
+        tma_load_5d(a + 64 * 128, &tmX, &full[s], c0 + 64, w0, h0, d0, n0);       // zeros when c0 + 64 >= C
+#pragma unroll
+        for (int j = 0; j < 9; ++j)     // dO[u - off]: the box moves by -(k - 1) along each axis
+          tma_load_5d(b + j * 2048, &tmG, &full[s], 0, w0 - (j % 3 - 1), h0 - (j / 3 - 1), d0 - (kd - 1), n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, 144) | (1u << 15) | (1u << 16);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % HT_STAGES;
+        mbar_wait(&full[s], (it / HT_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a = smem_u32(smem + (size_t)s * HT_STAGE_BYTES);
+        const uint32_t b = a + HT_A_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16_ss(tmem_base, desc_mn(a + ks * 16 * 128, 128, 64 * 128), desc_mn_sw32(b + ks * 16 * 32), idesc,
+                       (it > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const bool valid = (c0 + row) < p.C && n_iter > 0;
+    float* dst = p.slab + (((size_t)blockIdx.z * 3 + kd) * p.C + (c0 + row)) * 144;
+#pragma unroll 1
+    for (int c = 0; c < 144; c += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + c + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// dw_{loc,cls}[row][c][tap] = sum over ranges of slab[s][kd][c][j*16 + n];  row = 16*g + n of the packed
+// [loc rows | class rows | padding] gradient columns.  Thread = (tap, c, n), n fastest: 64-byte reads.
+__global__ void __launch_bounds__(256) head_wsum_kernel(const float* __restrict__ slab, int S, int C, int g, int n_loc,
+                                                        int n_cls, float* __restrict__ dw_loc,
+                                                        float* __restrict__ dw_cls) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 27ll * C * 16) return;
+  const int n = (int)(i & 15);
+  const int c = (int)((i >> 4) % C);
+  const int tap = (int)((i >> 4) / C);
+  const int kd = tap / 9, j = tap - kd * 9;
+  const float* src = slab + ((size_t)kd * C + c) * 144 + j * 16 + n;
+  const size_t stride = (size_t)3 * C * 144;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += src[(size_t)s * stride];
+  const int r = g * 16 + n;
+  if (r < n_loc) dw_loc[((size_t)r * C + c) * 27 + tap] = acc;
+  else if (r - n_loc < n_cls) dw_cls[((size_t)(r - n_loc) * C + c) * 27 + tap] = acc;
+}
+
 }  // namespace
 
 // plan shared with the workspace query: tiles, voxel ranges
@@ -222,6 +387,77 @@ int wgrad_tc_launch(const void* dz, const void* x, long long M, int Cin, int Cou
   const dim3 grid((unsigned)(Cin / p.NT), (unsigned)((Cout + 127) / 128), (unsigned)S);
   if (launch_pdl(wgrad_tc_kernel, grid, dim3(WT_THREADS), (size_t)WT_SMEM, st, tmZ, tmX, p) != cudaSuccess) return -4;
   return S;
+}
+
+
+// 64-voxel box of the (W, H, D, N) map: powers of two with product 64, none larger than its axis; fewest boxes wins.
+static bool head_tc_box(int N, int D, int H, int W, int* box, int* cnt) {
+  long long best = -1;
+  for (int bw = 1; bw <= 64; bw <<= 1)
+    for (int bh = 1; bw * bh <= 64; bh <<= 1)
+      for (int bd = 1; bw * bh * bd <= 64; bd <<= 1) {
+        const int bn = 64 / (bw * bh * bd);
+        if (bw > W || bh > H || bd > D || bn > N) continue;
+        const long long n = (long long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((D + bd - 1) / bd) * ((N + bn - 1) / bn);
+        // ties: the wider box along W (neighbouring voxels are neighbours in memory)
+        if (best < 0 || n < best || (n == best && bw > box[0])) { best = n; box[0] = bw; box[1] = bh; box[2] = bd; box[3] = bn; }
+      }
+  if (best < 0 || best >= (1ll << 30)) return false;
+  *cnt = (int)best;
+  return true;
+}
+
+static void head_tc_plan(int C, int n_boxes, int* S, int* bps) {
+  const int tiles = (C + 127) / 128;
+  int s = persistent_sms() / (tiles * 3);
+  const int by_work = (n_boxes + 7) / 8;
+  if (s > by_work) s = by_work;
+  if (s < 1) s = 1;
+  *bps = (n_boxes + s - 1) / s;
+  *S = (n_boxes + *bps - 1) / *bps;
+}
+
+// one 16-column group.  0: done (dw_loc / dw_cls rows of this group written), -1: shape not taken, < -1: error
+int head_wgrad_tc_launch(const void* dO16, const void* x, int N, int C, int D, int H, int W, int g, int n_loc, int n_cls,
+                         float* dw_loc, float* dw_cls, float* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (C <= 0 || (C % 64)) return -1;
+  HeadWgradTcParams p{};
+  int box[4];
+  if (!head_tc_box(N, D, H, W, box, &p.n_boxes)) return -1;
+  int S;
+  head_tc_plan(C, p.n_boxes, &S, &p.boxes_per_split);
+  if (workspace_bytes < (int64_t)S * 3 * C * 144 * 4) return -1;
+  p.C = C;
+  p.bw = box[0]; p.bh = box[1]; p.bd = box[2]; p.bn = box[3];
+  p.tw = (W + p.bw - 1) / p.bw; p.th = (H + p.bh - 1) / p.bh; p.td = (D + p.bd - 1) / p.bd;
+  p.slab = workspace;
+  CUtensorMap tmX, tmG;
+  {
+    const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    const uint64_t strides[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2,
+                                 (uint64_t)D * H * W * C * 2};
+    const uint32_t bx[5] = {64u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+    if (make_tma_bf16(&tmX, x, 5, dims, strides, bx, CU_TENSOR_MAP_SWIZZLE_128B)) return -2;
+  }
+  {
+    const uint64_t dims[5] = {16u, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+    const uint64_t strides[4] = {32u, (uint64_t)W * 32, (uint64_t)H * W * 32, (uint64_t)D * H * W * 32};
+    const uint32_t bx[5] = {16u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bd, (uint32_t)p.bn};
+    if (make_tma_bf16(&tmG, dO16, 5, dims, strides, bx, CU_TENSOR_MAP_SWIZZLE_32B)) return -2;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(head_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM) != cudaSuccess)
+      return -3;
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)((C + 127) / 128), 3u, (unsigned)S);
+  if (launch_pdl(head_wgrad_tc_kernel, grid, dim3(WT_THREADS), (size_t)HT_SMEM, st, tmX, tmG, p) != cudaSuccess) return -4;
+  const long long total = 27ll * C * 16;
+  if (launch_pdl(head_wsum_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float*)workspace, S,
+                 C, g, n_loc, n_cls, dw_loc, dw_cls) != cudaSuccess)
+    return -4;
+  return 0;
 }
 
 }  // namespace ssd3d

@@ -242,7 +242,11 @@ def test_stem_raw_wgrad(cin, n, size, sd, dtype):
 @pytest.mark.parametrize("c,n,size,ncls", [(128, 2, (6, 6, 6), 2), (256, 2, (3, 3, 3), 2), (512, 3, (2, 2, 2), 2),
                                            (128, 1, (5, 7, 4), 2), (128, 1, (12, 12, 12), 2),
                                            # n_classes >= 3: bpl*(6+n_classes) > 16 -> several 16-column groups
-                                           (128, 2, (6, 6, 6), 3), (256, 1, (4, 3, 5), 5), (128, 1, (5, 5, 5), 11)])
+                                           (128, 2, (6, 6, 6), 3), (256, 1, (4, 3, 5), 5), (128, 1, (5, 5, 5), 11),
+                                           # batches whose maps hold a 64-voxel box: the tcgen05 weight gradient
+                                           # (the C3 heads at batch 16; C = 64: half-empty channel tile; ragged boxes)
+                                           (256, 16, (3, 3, 3), 2), (256, 16, (6, 6, 6), 2), (512, 16, (3, 3, 3), 2),
+                                           (64, 2, (8, 8, 8), 2), (192, 5, (5, 3, 7), 3)])
 def test_head_backward(c, n, size, ncls):
     ops = _ops()
     bpl = 2
