@@ -101,8 +101,9 @@ struct BnUnitParams {
   float inv_m;
 };
 
-// MODE 0 forward, MODE 1 backward
-template <int MODE>
+// MODE 0 forward, MODE 1 backward.  KEEP: at most 8 rows per thread (the 12^3-sized maps): they are loaded once and
+// stay in registers across both barriers -- phase 3 starts without another trip to L2.
+template <int MODE, bool KEEP>
 __global__ void __launch_bounds__(BU_THREADS, 1) bn_unit_kernel(const BnUnitParams p) {
   __shared__ float red[BU_WARPS][2][8 * 32];      // cross-warp stage of phase 1 (32 KB)
   __shared__ double fin[BU_WARPS][32][2];         // phase 2 lane sums (8 KB)
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) bn_unit_kernel(const BnUnitPara
     }
   }
 
+  uint4 zk[KEEP ? 8 : 1];
   // ---------------- phase 1: column partial sums over this CTA's rows ----------------
   {
     float s0[8], s1[8];
@@ -150,10 +152,36 @@ __global__ void __launch_bounds__(BU_THREADS, 1) bn_unit_kernel(const BnUnitPara
         }
       }
     };
+    if constexpr (KEEP) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long mi = m_begin + r + (long long)i * RP;
+        zk[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (mi < m_end) zk[i] = bu_ld_nc16(p.z + mi * C + c0);
+      }
+      if constexpr (MODE == 1) {
+        // the gradient rows pass through in two batches of four (registers); phase 3 reads them again from L1/L2
+#pragma unroll
+        for (int i0 = 0; i0 < 8; i0 += 4) {
+          uint4 gt[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const long long mi = m_begin + r + (long long)(i0 + i) * RP;
+            gt[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (mi < m_end) gt[i] = bu_ld_nc16(p.g + mi * C + c0);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) add_row(zk[i0 + i], gt[i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) add_row(zk[i], zk[i]);
+      }
+    }
     constexpr int U = (MODE == 0) ? 8 : 4;        // 16-byte loads in flight per thread and operand
     // whole batches of U rows with every load issued before the first use; rows past the end are predicated off
     // and contribute zeros (z = 0 adds nothing to either sum; g = 0 gives dy = 0)
-    for (long long m = m_begin + r; m < m_end; m += (long long)U * RP) {
+    for (long long m = m_begin + r; !KEEP && m < m_end; m += (long long)U * RP) {
       uint4 zu[U], gu[MODE == 1 ? U : 1];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
@@ -211,10 +239,22 @@ __global__ void __launch_bounds__(BU_THREADS, 1) bn_unit_kernel(const BnUnitPara
   // ---------------- phase 2: cross-CTA sums, one warp per channel ----------------
   if (MODE == 0 && blockIdx.x == 0 && tid == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
   for (int c = blockIdx.x * BU_WARPS + warp; c < C; c += (int)G * BU_WARPS) {
+    // every slab value of this lane is requested before the first add (G <= 256: at most 8 per lane and sum); the
+    // adds keep the order b = lane, lane + 32, ...
+    float v0[8], v1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const unsigned b = lane + 32u * i;
+      v0[i] = 0.f; v1[i] = 0.f;
+      if (b < G) {
+        v0[i] = __ldcg(p.slab + (size_t)b * 2 * C + c);
+        v1[i] = __ldcg(p.slab + (size_t)b * 2 * C + C + c);
+      }
+    }
     double ls = 0.0, lq = 0.0;
-    for (unsigned b = lane; b < G; b += 32) {
-      ls += (double)__ldcg(p.slab + (size_t)b * 2 * C + c);
-      lq += (double)__ldcg(p.slab + (size_t)b * 2 * C + C + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (lane + 32u * i < G) { ls += (double)v0[i]; lq += (double)v1[i]; }
     }
     fin[warp][lane][0] = ls;
     fin[warp][lane][1] = lq;
@@ -271,7 +311,14 @@ __global__ void __launch_bounds__(BU_THREADS, 1) bn_unit_kernel(const BnUnitPara
       }
       *reinterpret_cast<uint4*>(p.out + m * C + c0) = bu_pack8(o);
     };
-    for (long long m = m_begin + r; m < m_end; m += 4ll * RP) {
+    if constexpr (KEEP) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long mi = m_begin + r + (long long)i * RP;
+        if (mi < m_end) apply(mi, zk[i]);
+      }
+    }
+    for (long long m = m_begin + r; !KEEP && m < m_end; m += 4ll * RP) {
       uint4 zu[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -310,7 +357,23 @@ __global__ void __launch_bounds__(BU_THREADS, 1) bn_unit_kernel(const BnUnitPara
       *reinterpret_cast<uint4*>(p.out + m * C + c0) = bu_pack8(o);
     };
     // g may be overwritten in place (out == g): every element is read and written by the same thread
-    for (long long m = m_begin + r; m < m_end; m += 4ll * RP) {
+    if constexpr (KEEP) {
+#pragma unroll
+      for (int i0 = 0; i0 < 8; i0 += 4) {
+        uint4 gt[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long mi = m_begin + r + (long long)(i0 + i) * RP;
+          if (mi < m_end) gt[i] = *reinterpret_cast<const uint4*>(p.g + mi * C + c0);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const long long mi = m_begin + r + (long long)(i0 + i) * RP;
+          if (mi < m_end) apply(mi, zk[i0 + i], gt[i]);
+        }
+      }
+    }
+    for (long long m = m_begin + r; !KEEP && m < m_end; m += 4ll * RP) {
       uint4 zu[4], gu[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -584,6 +647,8 @@ int bn_cluster_plan(long long M, int C, long long* rows_per_cta, int* R) {
 // streams cannot each end up half resident waiting for the other.  (No programmatic dependent launch on this one.)
 template <int MODE>
 cudaError_t launch_bn_unit(const BnUnitParams& p, int G, cudaStream_t st) {
+  // forward only: with z AND the per-channel constants of the backward live, keeping rows spills (392 B measured)
+  const bool keep = MODE == 0 && p.rows_per_cta <= 8ll * (BU_THREADS / (p.C / 8));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)G);
   cfg.blockDim = dim3(BU_THREADS);
@@ -594,7 +659,8 @@ cudaError_t launch_bn_unit(const BnUnitParams& p, int G, cudaStream_t st) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, bn_unit_kernel<MODE>, p);
+  return keep ? cudaLaunchKernelEx(&cfg, bn_unit_kernel<MODE, true>, p)
+              : cudaLaunchKernelEx(&cfg, bn_unit_kernel<MODE, false>, p);
 }
 
 template <int MODE, int R>
@@ -635,6 +701,7 @@ int bn_unit_plan(long long M, int C, long long* rows_per_cta) {
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return -1;
   long long G = (M + RP * 4 - 1) / (RP * 4);
   if (G > sms) G = sms;
+  if (G > 256) G = 256;            // phase 2 holds at most 8 slabs per lane
   if (G < 1) G = 1;
   const long long rpc = (M + G - 1) / G;
   *rows_per_cta = rpc;
