@@ -1598,6 +1598,8 @@ int wgrad_tc_launch(const void* dz, const void* x, long long M, int Cin, int Cou
                     cudaStream_t st);
 int head_wgrad_tc_launch(const void* dO16, const void* x, int N, int C, int D, int H, int W, int g, int n_loc, int n_cls,
                          float* dw_loc, float* dw_cls, float* workspace, int64_t workspace_bytes, cudaStream_t st);
+int head_dgrad_tc_launch(const void* dO, const void* w, const void* addend, void* dx, int N, int C, int D, int H, int W,
+                         int groups, cudaStream_t st);
 }
 // SSD3D_WGRAD_TC=0 keeps the mma.sync kernel (A/B measurements, and the shapes the tcgen05 tiling does not take)
 static const bool g_wgrad_tc = [] { const char* e = getenv("SSD3D_WGRAD_TC"); return !(e && e[0] == '0'); }();
@@ -1771,6 +1773,11 @@ extern "C" int ssd3d_head_dgrad(const void* dO, const void* w, const void* adden
   if (C <= 0 || (C % 64) || n_cols <= 0 || n_cols > 256) return SSD3D_ERR_UNSUPPORTED;
   const long long M = (long long)N * D * H * W;
   const int groups = (n_cols + 15) / 16;
+  if (g_wgrad_tc) {
+    const int rc = head_dgrad_tc_launch(dO, w, addend, dx, N, C, D, H, W, groups, static_cast<cudaStream_t>(stream));
+    if (rc == 0) return SSD3D_OK;
+    if (rc < -1) return SSD3D_ERR_ARG;      // -1: no 128-voxel box fits this map -> mma.sync kernel below
+  }
   const size_t smem = (size_t)(27 * 16 * 72 + 2 * 64 * 24) * 2;
   cudaError_t e = cudaFuncSetAttribute(head_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

@@ -327,6 +327,161 @@ __global__ void __launch_bounds__(256) head_wsum_kernel(const float* __restrict_
   else if (r - n_loc < n_cls) dw_cls[((size_t)(r - n_loc) * C + c) * 27 + tap] = acc;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// SSD head data gradient on tcgen05 (transposed 3x3x3 conv, 16 gradient columns per group -> C channels; autograd
+// of ssd3d.py:131-167 w.r.t. the feature map):
+//
+//      dx[u][c] = sum_g sum_tap sum_n dO_g[u - off(tap)][n] * w[16g + n][tap*C + c]      (+ addend[u][c])
+//
+// One UMMA per (group, tap): M = 128 voxels (a 5-D TMA box bw x bh x bd x bn of the map, shifted by the tap, zero
+// filled outside the map = the conv's padding), K = the 16 gradient columns -- a 32-byte row, K-major under
+// SWIZZLE_32B -- and N = up to 128 channels of the weight rows w[16g .. 16g+15][tap*C + c0 ...], which are MN-major
+// (channel contiguous) exactly as TMA delivers them (SWIZZLE_128B, 16 rows = 2 K groups).  27 x groups steps through a
+// ring of 8 KB stages, fp32 accumulator in TMEM, epilogue = + addend, bf16, 32-byte stores to the voxel's row.
+// ------------------------------------------------------------------------------------------------
+constexpr int HD_STAGES = 8;
+constexpr int HD_A_BYTES = 128 * 32;                  // 128 voxels x 16 columns
+constexpr int HD_B_BYTES = 2 * 16 * 128;              // 16 weight rows x (up to) 2 x 64 channels
+constexpr int HD_STAGE_BYTES = HD_A_BYTES + HD_B_BYTES;
+constexpr int HD_SMEM = HD_STAGES * HD_STAGE_BYTES + 1024 + 256;
+
+struct HeadDgradTcParams {
+  int N, D, H, W, C;
+  int NT;                      // channels per tile: 64 or 128
+  int groups;
+  int lw, lh, ld;              // log2 of the box extents bw, bh, bd (bn = 128 >> (lw + lh + ld))
+  int tw, th, td;              // boxes along W, H, D
+  const bf16* addend;          // (M, C) or null
+  bf16* dx;                    // (M, C)
+};
+
+__device__ __forceinline__ uint64_t desc_k_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                 // LBO: unused (K = one 32-byte row)
+  d |= (uint64_t)(256u >> 4) << 32;       // SBO: next group of 8 voxels
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                 // SWIZZLE_32B
+  return d;
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1) head_dgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG,
+                                                                      const __grid_constant__ CUtensorMap tmW,
+                                                                      const HeadDgradTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)HD_STAGES * HD_STAGE_BYTES);
+  uint64_t* empty = full + HD_STAGES;
+  uint64_t* acc_full = empty + HD_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NT = p.NT;
+  const uint32_t tmem_cols = (uint32_t)NT;              // 64 or 128
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < HD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  int t = blockIdx.x;
+  const int w0 = (t % p.tw) << p.lw; t /= p.tw;
+  const int h0 = (t % p.th) << p.lh; t /= p.th;
+  const int d0 = (t % p.td) << p.ld; t /= p.td;
+  const int lb = 7 - p.lw - p.lh - p.ld;               // log2(bn)
+  const int n0 = t << lb;
+  const int c0 = blockIdx.y * NT;
+  const int n_iter = 27 * p.groups;
+  const int w_boxes = NT / 64;
+  const uint32_t stage_tx = HD_A_BYTES + (uint32_t)w_boxes * 2048u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % HD_STAGES;
+        if (it >= HD_STAGES) mbar_wait(&empty[s], ((it / HD_STAGES) - 1) & 1);
+        uint8_t* a = smem + (size_t)s * HD_STAGE_BYTES;
+        uint8_t* b = a + HD_A_BYTES;
+        const int g = it / 27, tap = it - g * 27;
+        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+        mbar_arrive_expect_tx(&full[s], stage_tx);
+        tma_load_5d(a, &tmG, &full[s], 0, w0 - (kw - 1), h0 - (kh - 1), d0 - (kd - 1), g * p.N + n0);
+        for (int j = 0; j < w_boxes; ++j) tma_load_2d(b + j * 2048, &tmW, &full[s], tap * p.C + c0 + 64 * j, g * 16);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, NT) | (1u << 16);      // A K-major, B MN-major
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % HD_STAGES;
+        mbar_wait(&full[s], (it / HD_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a = smem_u32(smem + (size_t)s * HD_STAGE_BYTES);
+        umma_bf16_ss(tmem_base, desc_k_sw32(a), desc_mn(a + HD_A_BYTES, 128, 2048), idesc, it > 0 ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                     // voxel of the box, W fastest
+    const int iw = row & ((1 << p.lw) - 1);
+    const int ih = (row >> p.lw) & ((1 << p.lh) - 1);
+    const int id = (row >> (p.lw + p.lh)) & ((1 << p.ld) - 1);
+    const int in = row >> (p.lw + p.lh + p.ld);
+    const int w = w0 + iw, h = h0 + ih, d = d0 + id, n = n0 + in;
+    const bool valid = w < p.W && h < p.H && d < p.D && n < p.N;
+    const long long m = (((long long)n * p.D + d) * p.H + h) * p.W + w;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NT; c += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (valid) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        bf16* dst = p.dx + m * p.C + c0 + c;
+        if (p.addend) {
+          const uint4 a0 = *reinterpret_cast<const uint4*>(p.addend + m * p.C + c0 + c);
+          const uint4 a1 = *reinterpret_cast<const uint4*>(p.addend + m * p.C + c0 + c + 8);
+          const uint32_t au[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { f[2 * j] += bf16_lo(au[j]); f[2 * j + 1] += bf16_hi(au[j]); }
+        }
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+        o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+        o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+        o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+        *reinterpret_cast<uint4*>(dst) = o0;
+        *reinterpret_cast<uint4*>(dst + 8) = o1;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 }  // namespace
 
 // plan shared with the workspace query: tiles, voxel ranges
@@ -457,6 +612,62 @@ int head_wgrad_tc_launch(const void* dO16, const void* x, int N, int C, int D, i
   if (launch_pdl(head_wsum_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, (const float*)workspace, S,
                  C, g, n_loc, n_cls, dw_loc, dw_cls) != cudaSuccess)
     return -4;
+  return 0;
+}
+
+
+// 128-voxel box for the data gradient (same rule as head_tc_box); log2 extents
+static bool head_dgrad_box(int N, int D, int H, int W, int* lg, long long* cnt) {
+  long long best = -1;
+  for (int lw = 0; lw <= 7; ++lw)
+    for (int lh = 0; lw + lh <= 7; ++lh)
+      for (int ld = 0; lw + lh + ld <= 7; ++ld) {
+        const int bw = 1 << lw, bh = 1 << lh, bd = 1 << ld, bn = 128 >> (lw + lh + ld);
+        if (bw > W || bh > H || bd > D || bn > N) continue;
+        const long long n = (long long)((W + bw - 1) / bw) * ((H + bh - 1) / bh) * ((D + bd - 1) / bd) * ((N + bn - 1) / bn);
+        if (best < 0 || n < best || (n == best && lw > lg[0])) { best = n; lg[0] = lw; lg[1] = lh; lg[2] = ld; }
+      }
+  if (best < 0 || best >= (1ll << 31)) return false;
+  *cnt = best;
+  return true;
+}
+
+// 0: launched, -1: shape not taken (no 128-voxel box / channel count), < -1: error
+int head_dgrad_tc_launch(const void* dO, const void* w, const void* addend, void* dx, int N, int C, int D, int H, int W,
+                         int groups, cudaStream_t st) {
+  if (C <= 0 || (C % 64) || groups <= 0) return -1;
+  int lg[3] = {0, 0, 0};
+  long long boxes;
+  if (!head_dgrad_box(N, D, H, W, lg, &boxes)) return -1;
+  HeadDgradTcParams p{};
+  p.N = N; p.D = D; p.H = H; p.W = W; p.C = C;
+  p.NT = (C % 128 == 0) ? 128 : 64;
+  p.groups = groups;
+  p.lw = lg[0]; p.lh = lg[1]; p.ld = lg[2];
+  p.tw = (W + (1 << p.lw) - 1) >> p.lw; p.th = (H + (1 << p.lh) - 1) >> p.lh; p.td = (D + (1 << p.ld) - 1) >> p.ld;
+  p.addend = static_cast<const bf16*>(addend);
+  p.dx = static_cast<bf16*>(dx);
+  CUtensorMap tmG, tmW;
+  {
+    const uint64_t dims[5] = {16u, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N * groups};
+    const uint64_t strides[4] = {32u, (uint64_t)W * 32, (uint64_t)H * W * 32, (uint64_t)D * H * W * 32};
+    const uint32_t bx[5] = {16u, 1u << p.lw, 1u << p.lh, 1u << p.ld, 128u >> (p.lw + p.lh + p.ld)};
+    if (make_tma_bf16(&tmG, dO, 5, dims, strides, bx, CU_TENSOR_MAP_SWIZZLE_32B)) return -2;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)27 * C, (uint64_t)16 * groups};
+    const uint64_t strides[1] = {(uint64_t)27 * C * 2};
+    const uint32_t bx[2] = {64u, 16u};
+    if (make_tma_bf16(&tmW, w, 2, dims, strides, bx, CU_TENSOR_MAP_SWIZZLE_128B)) return -2;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(head_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HD_SMEM) != cudaSuccess)
+      return -3;
+    attr_set = true;
+  }
+  const dim3 grid((unsigned)boxes, (unsigned)(C / p.NT));
+  if (launch_pdl(head_dgrad_tc_kernel, grid, dim3(WT_THREADS), (size_t)HD_SMEM, st, tmG, tmW, p) != cudaSuccess) return -4;
   return 0;
 }
 
