@@ -29,5 +29,5 @@ demangled = subprocess.run(["c++filt"], input="\n".join(kernels), capture_output
 print("# %s -- %d kernels (cuobjdump -sass, sm_100a)" % (os.path.basename(lib), len(kernels)))
 print("%-70s %7s  %s" % ("kernel", "instr", "  ".join(KEY)))
 for (name, c), dn in zip(kernels.items(), demangled):
-    short = re.sub(r"\(.*", "", dn).replace("ssd3d::", "")[:70]
+    short = re.sub(r"\(.*", "", dn.replace("(anonymous namespace)::", "")).replace("ssd3d::", "")[:70]
     print("%-70s %7d  %s" % (short, c["_total"], "  ".join("%*d" % (len(k), c.get(k, 0)) for k in KEY)))
