@@ -1026,6 +1026,35 @@ __global__ void __launch_bounds__(256) dw_dgrad_kernel(const bf16* __restrict__ 
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   // only taps with (i + 1 - k) divisible by S reach an output: for S = 2 that is k = parity, parity + 2
   // (1 or 2 taps per axis, 3.4 of 27 on average) -- walk exactly those
+  if constexpr (S == 1) {
+    // stride 1: every tap contributes.  One (kd) plane at a time: its nine gradient rows and nine weight vectors are
+    // requested together (zero outside the map) -- with the loads inside the bounds branches the kernel paid one
+    // L2 round trip per tap, 27 in a row (28 us for the 7 MB map of the C3 step's third block)
+#pragma unroll 1
+    for (int kd = 0; kd < 3; ++kd) {
+      const int od = di + 1 - kd;
+      if ((unsigned)od >= (unsigned)Do) continue;
+      const bf16* zrow = dz + ((long long)n * Do + od) * Ho * (long long)Wo * C + c0;
+      uint4 gu[9], wu[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int oh = hi + 1 - t / 3, ow = wi + 1 - t % 3;
+        gu[t] = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)oh < (unsigned)Ho && (unsigned)ow < (unsigned)Wo) gu[t] = ld_nc16(zrow + ((long long)oh * Wo + ow) * C);
+        wu[t] = ld_nc16(w + (kd * 9 + t) * C + c0);
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float gf[8], wf[8];
+        unpack8f(gu[t], gf);
+        unpack8f(wu[t], wf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(gf[j], wf[j], acc[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + gid * 8) = pack8f(acc);
+    return;
+  }
   const int pd = (S == 2) ? ((di + 1) & 1) : 0, ph = (S == 2) ? ((hi + 1) & 1) : 0, pw = (S == 2) ? ((wi + 1) & 1) : 0;
   for (int kd = pd; kd < 3; kd += S) {
     const int td = di + 1 - kd;
@@ -1166,7 +1195,7 @@ __global__ void __launch_bounds__(256) dw_dgrad_s2_kernel(const bf16* __restrict
 // and 8 stores of 16 bytes per 64 gradient elements, and a warp writes whole 128-byte lines (both W parities back
 // to back) where the per-class kernel wrote every line in two far-apart halves.  Weights sit in shared memory as
 // fp32 (two LDS.128 per tap), the products are packed FFMA2.
-__global__ void __launch_bounds__(256) dw_dgrad_s2_block_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) dw_dgrad_s2_block_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ w,
                                                                 bf16* __restrict__ dx, int N, int C, int D, int H, int W,
                                                                 int Do, int Ho, int Wo, int Md, int Mh, int Mw,
                                                                 long long total) {
@@ -1190,19 +1219,22 @@ __global__ void __launch_bounds__(256) dw_dgrad_s2_block_kernel(const bf16* __re
   for (int p = 0; p < 8; ++p)
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[p][q] = 0ull;
+  // all eight gradient vectors of the 2x2x2 block are requested before the first use (zero outside the map: a zero
+  // gradient adds nothing) -- inside the bounds branches they were eight L2 round trips in a row
+  uint4 gu8[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int od = md + (t >> 2), oh = mh + ((t >> 1) & 1), ow = mw + (t & 1);
+    gu8[t] = make_uint4(0u, 0u, 0u, 0u);
+    if (od < Do && oh < Ho && ow < Wo) gu8[t] = ld_nc16(dz + ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * C + c0);
+  }
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
-    const int od = md + a;
-    if (od >= Do) continue;
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-      const int oh = mh + b;
-      if (oh >= Ho) continue;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const int ow = mw + c;
-        if (ow >= Wo) continue;
-        const uint4 u = ld_nc16(dz + ((((long long)n * Do + od) * Ho + oh) * Wo + ow) * C + c0);
+        const uint4 u = gu8[(a * 2 + b) * 2 + c];
         const f32x2_t g[4] = {tr_bf16x2_to_f32x2(u.x), tr_bf16x2_to_f32x2(u.y), tr_bf16x2_to_f32x2(u.z),
                               tr_bf16x2_to_f32x2(u.w)};
 #pragma unroll
