@@ -691,6 +691,306 @@ cudaError_t launch_bn_cluster_r(const BnUnitParams& p, int K, int R, cudaStream_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Larger maps, ONE barrier: 2-D split.  CTA (chunk i, group j) owns a contiguous row chunk x CG = 64 (or 32)
+// channels -- a warp reads whole 128-byte (64-byte) row segments -- and writes its 2*CG column partials to slab
+// [j][i].  The only synchronisation is between the RC CTAs of one channel group (one counter per group): after it
+// EVERY CTA of the group adds the group's RC slabs itself (fp64, fixed order, all loads in flight: RC * 2*CG floats
+// <= 38 KB from L2) and finalizes its CG channels redundantly, so nothing has to be published and waited for a second
+// time; chunk 0 of each group writes the statistics / parameter gradients.  Against bn_unit_kernel this removes one
+// grid barrier and two dependent L2 round trips per launch.  Cooperative launch as above (<= one CTA per SM).
+// ------------------------------------------------------------------------------------------------
+struct BnTileParams {
+  BnUnitParams u;
+  int CG;                 // channels per group: 64 or 32
+  int RC;                 // row chunks (CTAs per group)
+};
+
+template <int MODE, bool KEEP>
+__global__ void __launch_bounds__(BU_THREADS, 1) bn_tile_kernel(const BnTileParams q) {
+  const BnUnitParams& p = q.u;
+  __shared__ float red[BU_WARPS][8][16];          // [warp][cv of the group][s0 x8 | s1 x8]
+  __shared__ double part[4][128];                 // phase 2: four slab lanes per column
+  __shared__ float cst[4][64];                    // forward: scale, shift; backward: ka, kb
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = p.C, CG = q.CG, RC = q.RC;
+  const int CVB = CG >> 3;                        // 16-byte vectors per row of the tile: 8 or 4
+  const int RL = BU_THREADS / CVB;                // row lanes: 64 or 128
+  const int grp = blockIdx.x / RC, chunk = blockIdx.x - grp * RC;
+  const int cv = tid % CVB, r = tid / CVB;
+  const int c0 = grp * CG + (cv << 3);
+  const long long m_begin = (long long)chunk * p.rows_per_cta;
+  const long long m_end = (m_begin + p.rows_per_cta < p.M) ? m_begin + p.rows_per_cta : p.M;
+
+  float sc[8], sh[8], mu[8], is[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = __ldg(p.scale + c0 + j); sh[j] = __ldg(p.shift + c0 + j);
+      mu[j] = __ldg(p.mean + c0 + j);  is[j] = __ldg(p.invstd + c0 + j);
+    }
+  }
+  uint4 zk[KEEP ? 8 : 1];
+  // ---------------- phase 1 ----------------
+  {
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0[j] = 0.f; s1[j] = 0.f; }
+    auto add_row = [&](const uint4& zu, const uint4& gu) {
+      float zf[8];
+      bu_unpack8(zu, zf);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s0[j] += zf[j]; s1[j] = fmaf(zf[j], zf[j], s1[j]); }
+      } else {
+        float gf[8];
+        bu_unpack8(gu, gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pre = __fadd_rn(__fmul_rn(zf[j], sc[j]), sh[j]);
+          const float dy = (pre > 0.f) ? gf[j] : 0.f;
+          const float xh = (zf[j] - mu[j]) * is[j];
+          s0[j] += dy;
+          s1[j] = fmaf(dy, xh, s1[j]);
+        }
+      }
+    };
+    if constexpr (KEEP) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long mi = m_begin + r + (long long)i * RL;
+        zk[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (mi < m_end) zk[i] = bu_ld_nc16(p.z + mi * C + c0);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) add_row(zk[i], zk[i]);
+    }
+    constexpr int U = (MODE == 0) ? 8 : 4;
+    for (long long m = m_begin + r; !KEEP && m < m_end; m += (long long)U * RL) {
+      uint4 zu[U], gu[MODE == 1 ? U : 1];
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const long long mi = m + (long long)i * RL;
+        zu[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (mi < m_end) zu[i] = bu_ld_nc16(p.z + mi * C + c0);
+      }
+      if constexpr (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const long long mi = m + (long long)i * RL;
+          gu[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (mi < m_end) gu[i] = bu_ld_nc16(p.g + mi * C + c0);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        if constexpr (MODE == 1) add_row(zu[i], gu[i]);
+        else add_row(zu[i], zu[i]);
+      }
+    }
+    // lanes with the same cv sit CVB apart
+    for (int off = CVB; off < 32; off <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s0[j] += __shfl_xor_sync(0xffffffffu, s0[j], off);
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+      }
+    }
+    if (lane < CVB) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { red[warp][lane][j] = s0[j]; red[warp][lane][8 + j] = s1[j]; }
+    }
+    __syncthreads();
+    if (tid < 2 * CG) {
+      // column t of the slab row: [s0 of the CG channels | s1 of the CG channels]
+      const int which = tid / CG, ch = tid - which * CG;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < BU_WARPS; ++w) t += red[w][ch >> 3][which * 8 + (ch & 7)];
+      p.slab[((size_t)grp * RC + chunk) * 128 + tid] = t;
+    }
+  }
+  // ---------------- the group's barrier ----------------
+  bu_grid_barrier(p.sync + grp, (unsigned)RC);
+  if (tid == 0) {
+    // last CTA of the group to get here clears the group's two words (all have left the spin: they only leave it
+    // after the counter reached RC, and each adds to the exit word afterwards)
+    if (atomicAdd(p.sync + 256 + grp, 1u) == (unsigned)RC - 1) {
+      p.sync[grp] = 0u;
+      p.sync[256 + grp] = 0u;
+      __threadfence();
+    }
+  }
+  // ---------------- phase 2: the group's totals, in every CTA ----------------
+  {
+    const int col = tid & 127, ln = tid >> 7;                 // 128 columns x 4 slab lanes
+    double acc = 0.0;
+    if (col < 2 * CG) {
+      const float* src = p.slab + (size_t)grp * RC * 128 + col;
+      for (int b0 = ln; b0 < RC; b0 += 32) {                   // 8 slabs of this lane per batch, loads first
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int b = b0 + 4 * i;
+          v[i] = (b < RC) ? __ldcg(src + (size_t)b * 128) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += (double)v[i];
+      }
+    }
+    part[ln][col] = acc;
+    __syncthreads();
+    if (tid < CG) {
+      const double s = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+      const double qq = part[0][CG + tid] + part[1][CG + tid] + part[2][CG + tid] + part[3][CG + tid];
+      const int c = grp * CG + tid;
+      if (MODE == 0) {
+        const double mean = s / (double)p.M;
+        double var = qq / (double)p.M - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float istd = (float)(1.0 / sqrt(var + (double)p.eps));
+        const float ga = p.gamma ? p.gamma[c] : 1.f, be = p.beta ? p.beta[c] : 0.f;
+        const float scl = ga * istd;
+        const float sft = be - (float)mean * scl;
+        cst[0][tid] = scl;
+        cst[1][tid] = sft;
+        if (chunk == 0) {
+          p.scale[c] = scl;
+          p.shift[c] = sft;
+          p.mean[c] = (float)mean;
+          p.invstd[c] = istd;
+          if (p.running_mean && p.running_var) {
+            const double unbiased = (p.M > 1) ? var * (double)p.M / (double)(p.M - 1) : var;
+            p.running_mean[c] = (float)((1.0 - (double)p.momentum) * (double)p.running_mean[c] + (double)p.momentum * mean);
+            p.running_var[c] = (float)((1.0 - (double)p.momentum) * (double)p.running_var[c] + (double)p.momentum * unbiased);
+          }
+          if (c == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+        }
+      } else {
+        const float db = (float)s, dg = (float)qq;
+        if (chunk == 0) { p.dbeta[c] = db; p.dgamma[c] = dg; }
+        const float scj = __ldg(p.scale + c), isj = __ldg(p.invstd + c), muj = __ldg(p.mean + c);
+        const float t = scj * isj * dg * p.inv_m;
+        cst[3][tid] = -t;
+        cst[2][tid] = fmaf(muj, t, -(scj * db * p.inv_m));
+      }
+    }
+    __syncthreads();
+  }
+  if (p.out == nullptr) return;
+  // ---------------- phase 3 ----------------
+  const int cl = cv << 3;                                      // channel within the group
+  if constexpr (MODE == 0) {
+    float a_sc[8], a_sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a_sc[j] = cst[0][cl + j]; a_sh[j] = cst[1][cl + j]; }
+    bool bad = false;
+    auto apply = [&](long long m, const uint4& zu) {
+      float zf[8], o[8];
+      bu_unpack8(zu, zf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = relu_nan(__fadd_rn(__fmul_rn(zf[j], a_sc[j]), a_sh[j]));
+        bad |= (o[j] != o[j]);
+      }
+      *reinterpret_cast<uint4*>(p.out + m * C + c0) = bu_pack8(o);
+    };
+    if constexpr (KEEP) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long mi = m_begin + r + (long long)i * RL;
+        if (mi < m_end) apply(mi, zk[i]);
+      }
+    }
+    for (long long m = m_begin + r; !KEEP && m < m_end; m += 4ll * RL) {
+      uint4 zu[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long mi = m + (long long)i * RL;
+        if (mi < m_end) zu[i] = bu_ld_nc16(p.z + mi * C + c0);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long mi = m + (long long)i * RL;
+        if (mi < m_end) apply(mi, zu[i]);
+      }
+    }
+    if (bad && p.nan_flag) atomicOr(p.nan_flag, SSD3D_NAN_BACKBONE);
+  } else {
+    float ka[8], kb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ka[j] = cst[2][cl + j]; kb[j] = cst[3][cl + j]; }
+    auto apply = [&](long long m, const uint4& zu, const uint4& gu) {
+      float zf[8], gf[8], o[8];
+      bu_unpack8(zu, zf);
+      bu_unpack8(gu, gf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = __fadd_rn(__fmul_rn(zf[j], sc[j]), sh[j]);
+        const float dy = (pre > 0.f) ? gf[j] : 0.f;
+        o[j] = fmaf(zf[j], kb[j], fmaf(sc[j], dy, ka[j]));
+      }
+      *reinterpret_cast<uint4*>(p.out + m * C + c0) = bu_pack8(o);
+    };
+    for (long long m = m_begin + r; m < m_end; m += 4ll * RL) {
+      uint4 zu[4], gu[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long mi = m + (long long)i * RL;
+        if (mi < m_end) {
+          zu[i] = bu_ld_nc16(p.z + mi * C + c0);
+          gu[i] = *reinterpret_cast<const uint4*>(p.g + mi * C + c0);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long mi = m + (long long)i * RL;
+        if (mi < m_end) apply(mi, zu[i], gu[i]);
+      }
+    }
+  }
+}
+
+// tile plan: CG = 64 (32 when C is an odd multiple of 32), RC chunks per group with NG * RC <= SMs
+int bn_tile_plan(long long M, int C, BnTileParams* q) {
+  if (C <= 0 || (C % 32) || M <= 0) return -1;
+  const int CG = (C % 64 == 0) ? 64 : 32;
+  const int NG = C / CG;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return -1;
+  if (NG > sms || NG > 256) return -1;
+  const int RL = BU_THREADS / (CG / 8);
+  long long rc = sms / NG;
+  const long long by_rows = (M + RL * 4 - 1) / (RL * 4);      // at least four rows per row lane
+  if (rc > by_rows) rc = by_rows;
+  if (rc < 1) rc = 1;
+  const long long rpc = (M + rc - 1) / rc;
+  q->u.rows_per_cta = rpc;
+  q->CG = CG;
+  q->RC = (int)((M + rpc - 1) / rpc);
+  return NG * q->RC;
+}
+
+template <int MODE>
+cudaError_t launch_bn_tile(const BnTileParams& q, int G, cudaStream_t st) {
+  const bool keep = MODE == 0 && q.u.rows_per_cta <= 8ll * (BU_THREADS / (q.CG / 8));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)G);
+  cfg.blockDim = dim3(BU_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return keep ? cudaLaunchKernelEx(&cfg, bn_tile_kernel<MODE, true>, q)
+              : cudaLaunchKernelEx(&cfg, bn_tile_kernel<MODE, false>, q);
+}
+
 // grid: every CTA gets at least four rows per row lane; never more CTAs than SMs (all must be resident)
 int bn_unit_plan(long long M, int C, long long* rows_per_cta) {
   const int CV = C / 8;
@@ -714,6 +1014,8 @@ int bn_unit_plan(long long M, int C, long long* rows_per_cta) {
 using namespace ssd3d;
 
 static const bool g_bn_cluster = [] { const char* e = getenv("SSD3D_BN_CLUSTER"); return !(e && e[0] == '0'); }();
+// SSD3D_BN_TILE=0: the two-barrier bn_unit_kernel for the larger maps (A/B measurements)
+static const bool g_bn_tile = [] { const char* e = getenv("SSD3D_BN_TILE"); return !(e && e[0] == '0'); }();
 
 extern "C" int ssd3d_bn_unit_supported(int64_t M, int C) {
   long long rpc;
@@ -723,7 +1025,10 @@ extern "C" int ssd3d_bn_unit_supported(int64_t M, int C) {
   return bn_unit_plan(M, C, &rpc) > 0 ? 1 : 0;
 }
 
-extern "C" int64_t ssd3d_bn_unit_workspace_bytes(int C) { return (int64_t)256 * 2 * C * 4; }
+extern "C" int64_t ssd3d_bn_unit_workspace_bytes(int C) {
+  const int64_t unit = (int64_t)256 * 2 * C * 4, tile = (int64_t)256 * 128 * 4;    // slabs of either kernel
+  return unit > tile ? unit : tile;
+}
 
 extern "C" int ssd3d_bn_unit_fwd(const void* z, int64_t M, int C, const float* gamma, const float* beta, float eps,
                                  float momentum, float* running_mean, float* running_var,
@@ -749,6 +1054,15 @@ extern "C" int ssd3d_bn_unit_fwd(const void* z, int64_t M, int C, const float* g
   if (K > 0) {
     const cudaError_t e = launch_bn_cluster_r<0>(p, K, R, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? SSD3D_OK : (int)e;
+  }
+  if (g_bn_tile) {
+    BnTileParams q{};
+    q.u = p;
+    const int GT = bn_tile_plan(M, C, &q);
+    if (GT > 0 && workspace_bytes >= (int64_t)GT * 128 * 4) {
+      const cudaError_t e = launch_bn_tile<0>(q, GT, static_cast<cudaStream_t>(stream));
+      return e == cudaSuccess ? SSD3D_OK : (int)e;
+    }
   }
   const cudaError_t e = launch_bn_unit<0>(p, G, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SSD3D_OK : (int)e;
@@ -779,6 +1093,15 @@ extern "C" int ssd3d_bn_unit_bwd(const void* z, const void* grad_a, int64_t M, i
   if (K > 0) {
     const cudaError_t e = launch_bn_cluster_r<1>(p, K, R, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? SSD3D_OK : (int)e;
+  }
+  if (g_bn_tile) {
+    BnTileParams q{};
+    q.u = p;
+    const int GT = bn_tile_plan(M, C, &q);
+    if (GT > 0 && workspace_bytes >= (int64_t)GT * 128 * 4) {
+      const cudaError_t e = launch_bn_tile<1>(q, GT, static_cast<cudaStream_t>(stream));
+      return e == cudaSuccess ? SSD3D_OK : (int)e;
+    }
   }
   const cudaError_t e = launch_bn_unit<1>(p, G, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SSD3D_OK : (int)e;

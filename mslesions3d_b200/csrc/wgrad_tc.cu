@@ -1,5 +1,7 @@
-// Pointwise-conv weight gradient on tcgen05 (autograd of nn.Conv3d(kernel_size=1), mobilenet.py:40 under
-// LSSD3D.training_step, ssd3d.py:467-531):
+// Backward-pass contractions of the training step on tcgen05 (three kernels: pointwise weight gradient, SSD head
+// weight gradient, SSD head data gradient), operands straight from TMA in the layouts the channels-last tensors
+// already have.  First: the pointwise-conv weight gradient (autograd of nn.Conv3d(kernel_size=1), mobilenet.py:40
+// under LSSD3D.training_step, ssd3d.py:467-531):
 //
 //      dW[n][k] = sum_m dz[m][n] * x[m][k]          dz (M, Cout) bf16, x (M, Cin) bf16, dW (Cout, Cin) fp32
 //

@@ -691,7 +691,7 @@ def _sync_words(device) -> torch.Tensor:
     key = (str(device), "bn_sync", _WS_SLOT[0])
     cur = _CONST.get(key)
     if cur is None:
-        cur = torch.zeros((16,), dtype=torch.int32, device=device)
+        cur = torch.zeros((512,), dtype=torch.int32, device=device)
         _CONST[key] = cur
     return cur
 
