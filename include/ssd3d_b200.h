@@ -309,10 +309,11 @@ int ssd3d_bn_relu_bwd(const void* z, const void* grad_a, int64_t M, int C, const
                       const float* mean, const float* invstd, float* dgamma, float* dbeta, void* dz, void* workspace,
                       int64_t workspace_bytes, void* stream);
 /* The same two passes as ONE launch each (csrc/bn_unit.cu): column sums, cross-CTA finalize and the elementwise
- * apply are three phases of a grid of at most one CTA per SM, separated by grid-wide barriers.  Arguments as
- * above plus `sync_words`: three device uint32, zero before the first launch, private to the calling stream (the
- * kernel leaves them zero).  ssd3d_bn_unit_supported: 1 if (M, C) can take this path (C/8 a power of two in
- * [4, 512]); workspace: ssd3d_bn_unit_workspace_bytes(C).  Replaces the same reference lines
+ * apply are phases of ONE grid -- thread-block clusters with distributed-shared-memory sums for maps up to 8192 rows,
+ * (row chunk x channel group) tiles with one barrier per channel group above.  Arguments as
+ * above plus `sync_words`: 512 device uint32, zero before the first launch, private to the calling stream (the
+ * kernels leave them zero).  ssd3d_bn_unit_supported: 1 if (M, C) can take this path (C a multiple of 8; above 8192 rows a
+ * multiple of 32, or C/8 a power of two in [4, 512]); workspace: ssd3d_bn_unit_workspace_bytes(C).  Replaces the same reference lines
  * (nn.BatchNorm3d + ReLU in train mode and their autograd backward, mobilenet.py:29-30,44-45). */
 int ssd3d_bn_unit_supported(int64_t M, int C);
 int64_t ssd3d_bn_unit_workspace_bytes(int C);

@@ -1,8 +1,12 @@
-// Train-mode BatchNorm3d + ReLU as ONE launch per direction (mobilenet.py:29-30,44-45 under autograd): the three
-// dependent passes of train.cu -- column partial sums, cross-block finalize, elementwise apply -- run as three
-// phases of one grid whose CTAs are all resident (at most one CTA per SM) and meet at two grid-wide barriers.
-// On the training step's critical chain this removes two launches + their drain/fill per BatchNorm pass
-// (15 units x 2 directions), and the finalize is spread over every warp of the grid instead of a single CTA.
+// Train-mode BatchNorm3d + ReLU as ONE launch per direction (mobilenet.py:29-30,44-45 under autograd) instead of the
+// three dependent passes of train.cu (column partial sums, cross-block finalize, elementwise apply).  Three kernels,
+// picked per shape by ssd3d_bn_unit_fwd / _bwd:
+//   bn_cluster_kernel  maps up to 8192 rows: channel split over thread-block clusters, sums through distributed
+//                      shared memory, no grid-wide barrier at all (below)
+//   bn_tile_kernel     larger maps, channels a multiple of 32: (row chunk x 64-channel group) tiles, ONE barrier per
+//                      channel group, every CTA finalizes its group redundantly (below)
+//   bn_unit_kernel     the general fallback and the first version, described here: all CTAs resident (at most one
+//                      per SM, cooperative launch), three phases separated by two grid-wide barriers
 //
 //   phase 1  CTA b owns rows [b*rows_per_cta, ...): thread = 8 channels x a strided set of rows, fp32 sums,
 //            in-CTA tree (shuffles + shared memory), slab[b][2][C] to the workspace
@@ -14,9 +18,10 @@
 //   phase 3  the CTA walks its own rows again (L2 hits for every map of the network but the first) and writes
 //            a = relu(z*scale+shift)   /   dz = scale*(dy - dbeta/M - xhat*dgamma/M)
 //
-// The barrier words (three u32, zero before the first launch) belong to the caller's stream slot; the last CTA to
-// leave the second barrier zeroes them again, so every launch (and every CUDA-graph replay) finds them clean.
-// Every reduction order is fixed by (M, C, grid): results are bit-reproducible run to run.
+// The barrier words (zero before the first launch; 512 u32: bn_unit uses three, bn_tile two per channel group)
+// belong to the caller's stream slot; the last CTA to leave a barrier zeroes its words again, so every launch (and
+// every CUDA-graph replay) finds them clean.  Every reduction order is fixed by (M, C, grid): results are
+// bit-reproducible run to run.
 #include "common.cuh"
 #include "../../include/ssd3d_b200.h"
 
