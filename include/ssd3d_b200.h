@@ -335,6 +335,15 @@ int ssd3d_pwconv_wgrad(const void* dz, const void* x, int64_t M, int Cin, int Co
 /* stem: dz (N, Do, Ho, Wo, 32) bf16, x (N, Cin, D, H, W) fp32|bf16 -> dw (32, Cin, 3, 3, 3) fp32 */
 int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W, int stride_d,
                      float* dw, void* workspace, int64_t workspace_bytes, void* stream);
+/* stem unit backward without materialising dz (autograd of mobilenet.py:26-31 for the first layer, whose input needs
+ * no gradient): after ssd3d_bn_unit_bwd(..., dz = NULL, ...) has left dgamma / dbeta, the BatchNorm + ReLU backward
+ * is applied to grad_a (N, Do, Ho, Wo, 32) bf16 from the saved raw conv output z while the weight-gradient kernel
+ * loads its rows.  Same result, bit for bit, as ssd3d_bn_unit_bwd + ssd3d_stem_wgrad.  SSD3D_ERR_UNSUPPORTED for
+ * shapes the TMA tile kernel does not take (fewer than 128*148 output voxels, rows TMA cannot address). */
+int ssd3d_stem_wgrad_bn(const void* z, const void* grad_a, const void* x, int x_is_bf16, int N, int Cin, int D, int H,
+                        int W, int stride_d, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, const float* dgamma, const float* dbeta, float* dw, void* workspace,
+                        int64_t workspace_bytes, void* stream);
 /* head: dO (G, N*D*H*W, 16) bf16 gradient rows in G = ceil((n_loc+n_cls)/16) column groups
  * (ssd3d_head_grad_pack), x (N, D, H, W, C) bf16 -> dw_loc (n_loc, C, 3,3,3), dw_cls (n_cls, C, 3,3,3) fp32
  * (ssd3d.py:131-132: any n_classes).  One 16-column contraction pass per group.  C % 64 == 0, n_loc + n_cls <= 256 */

@@ -95,6 +95,8 @@ SIGNATURES = {
     "ssd3d_wgrad_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "ssd3d_pwconv_wgrad": (c_int, [P, P, c_int64, c_int, c_int, P, P, c_int64, P]),
     "ssd3d_stem_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int64, P]),
+    "ssd3d_stem_wgrad_bn": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P,
+                                    c_int64, P]),
     "ssd3d_head_wgrad": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int64, P]),
     "ssd3d_head_grad_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "ssd3d_head_grad_pack": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64, P, P, P, P,

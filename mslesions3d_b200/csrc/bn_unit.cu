@@ -1077,8 +1077,8 @@ extern "C" int ssd3d_bn_unit_bwd(const void* z, const void* grad_a, int64_t M, i
                                  const float* shift, const float* mean, const float* invstd, float* dgamma,
                                  float* dbeta, void* dz, void* workspace, int64_t workspace_bytes, uint32_t* sync_words,
                                  void* stream) {
-  if (!z || !grad_a || !scale || !shift || !mean || !invstd || !dgamma || !dbeta || !dz || !workspace || !sync_words ||
-      M <= 0)
+  // dz == NULL: statistics only (dgamma, dbeta) -- the caller applies the backward elsewhere (ssd3d_stem_wgrad_bn)
+  if (!z || !grad_a || !scale || !shift || !mean || !invstd || !dgamma || !dbeta || !workspace || !sync_words || M <= 0)
     return SSD3D_ERR_ARG;
   BnUnitParams p{};
   int R = 0;

@@ -347,11 +347,28 @@ __device__ __forceinline__ void sw_mma_bf16(float (&d)[4], const uint32_t (&a)[4
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <typename TIn, int CIN>
+// FUSE: the BatchNorm + ReLU backward of the stem unit is applied to the gradient rows as they are loaded -- `dz`
+// then is the gradient w.r.t. the ReLU OUTPUT and `f.z` the saved raw conv output; the rows
+// dz = sc*dy + ka + z*kb (dy = g * [z*sc+sh > 0], the expression of the BatchNorm kernels, rounded to bf16 like the
+// tensor they would have written) exist only in shared memory: the 113 MB gradient of the C3 stem is neither written
+// nor read back.
+struct StemBnFuse {
+  const __nv_bfloat16* z;     // (M, 32) raw conv output
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  const float* dgamma;
+  const float* dbeta;
+  float inv_m;
+};
+
+template <typename TIn, int CIN, bool FUSE>
 __global__ void __launch_bounds__(128, 4) stem_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                  const StemParams p,
                                                                  const __nv_bfloat16* __restrict__ dz,
-                                                                 float* __restrict__ partial) {
+                                                                 float* __restrict__ partial, const StemBnFuse f) {
+  __shared__ float s_bn[FUSE ? 4 : 1][32];      // scale, shift, ka, kb
   constexpr int KREAL = 27 * CIN;
   constexpr int KPAD = (KREAL <= 64) ? 64 : 128;
   constexpr int NREG = KPAD / 2;
@@ -395,6 +412,17 @@ __global__ void __launch_bounds__(128, 4) stem_wgrad_tile_kernel(const __grid_co
   if (tid == 32) {
     if (first < total_tiles) issue_tma(first, 0);
     if (first + (int)gridDim.x < total_tiles) issue_tma(first + gridDim.x, 1);
+  }
+  if constexpr (FUSE) {
+    if (tid < 32) {
+      const float scj = f.scale[tid], isj = f.invstd[tid], muj = f.mean[tid];
+      const float t = scj * isj * f.dgamma[tid] * f.inv_m;
+      s_bn[0][tid] = scj;
+      s_bn[1][tid] = f.shift[tid];
+      s_bn[2][tid] = fmaf(muj, t, -(scj * f.dbeta[tid] * f.inv_m));
+      s_bn[3][tid] = -t;
+    }
+    __syncthreads();
   }
   const int wl = tid % p.TW;
   const int hl = (tid / p.TW) % p.TH;
@@ -465,9 +493,38 @@ __global__ void __launch_bounds__(128, 4) stem_wgrad_tile_kernel(const __grid_co
 #pragma unroll
     for (int q = 0; q < 4; ++q) g4[q] = make_uint4(0u, 0u, 0u, 0u);
     if (wo < p.Wo && ho < p.Ho && dzo < p.Do) {
-      const uint4* src = reinterpret_cast<const uint4*>(dz + ((((long long)t * p.Do + dzo) * p.Ho + ho) * p.Wo + wo) * 32);
+      const long long row = (((long long)t * p.Do + dzo) * p.Ho + ho) * p.Wo + wo;
+      const uint4* src = reinterpret_cast<const uint4*>(dz + row * 32);
 #pragma unroll
       for (int q = 0; q < 4; ++q) g4[q] = __ldg(src + q);
+      if constexpr (FUSE) {
+        const uint4* zsrc = reinterpret_cast<const uint4*>(f.z + row * 32);
+        uint4 z4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) z4[q] = __ldg(zsrc + q);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t zu[4] = {z4[q].x, z4[q].y, z4[q].z, z4[q].w};
+          const uint32_t gu[4] = {g4[q].x, g4[q].y, g4[q].z, g4[q].w};
+          uint32_t ou[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float o2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = q * 8 + h * 2 + e;
+              const float zf = e ? bf16_hi(zu[h]) : bf16_lo(zu[h]);
+              const float gf = e ? bf16_hi(gu[h]) : bf16_lo(gu[h]);
+              const float scc = s_bn[0][c];
+              const float pre = __fadd_rn(__fmul_rn(zf, scc), s_bn[1][c]);
+              const float dy = (pre > 0.f) ? gf : 0.f;
+              o2[e] = fmaf(zf, s_bn[3][c], fmaf(scc, dy, s_bn[2][c]));
+            }
+            ou[h] = pack_bf16x2(o2[0], o2[1]);
+          }
+          g4[q] = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        }
+      }
     }
     __syncthreads();            // the previous tile's fragments have been read; everyone is done with sX[buf]
     if (tid == 32) {
@@ -559,7 +616,7 @@ static int launch_stem_tc(const void* x, const StemParams& p0, CUtensorMapDataTy
 
 template <typename TIn, int CIN>
 static int launch_stem_wgrad(const void* x, const StemParams& p, CUtensorMapDataType dt, const __nv_bfloat16* dz,
-                             float* partial, int max_slabs, int* slabs, cudaStream_t st) {
+                             float* partial, int max_slabs, int* slabs, cudaStream_t st, const StemBnFuse* fuse) {
   constexpr int KPAD = (27 * CIN <= 64) ? 64 : 128;
   CUtensorMap tm;
   {
@@ -577,7 +634,10 @@ static int launch_stem_wgrad(const void* x, const StemParams& p, CUtensorMapData
   }
   const size_t tile_pitch = ((size_t)CIN * p.TDI * p.THI * p.TWI * sizeof(TIn) + 127) & ~(size_t)127;
   const size_t smem = 128 + (size_t)128 * (KPAD + 8) * 2 + 128 * 40 * 2 + 128 + 2 * tile_pitch;
-  cudaError_t e = cudaFuncSetAttribute(stem_wgrad_tile_kernel<TIn, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = fuse ? cudaFuncSetAttribute(stem_wgrad_tile_kernel<TIn, CIN, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(stem_wgrad_tile_kernel<TIn, CIN, false>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * p.N;
   long long per_sm = (smem + 1024) * 4 <= 227 * 1024 ? 4 : ((smem + 1024) * 3 <= 227 * 1024 ? 3 : (smem * 2 <= 220 * 1024 ? 2 : 1));
@@ -585,7 +645,13 @@ static int launch_stem_wgrad(const void* x, const StemParams& p, CUtensorMapData
   if (grid > tiles) grid = tiles;
   if (grid > max_slabs) grid = max_slabs;
   if (grid < 1) return SSD3D_ERR_ARG;
-  SSD3D_LAUNCH_PDL((stem_wgrad_tile_kernel<TIn, CIN>), dim3((unsigned)grid), dim3(128), smem, st, tm, p, dz, partial);
+  if (fuse) {
+    SSD3D_LAUNCH_PDL((stem_wgrad_tile_kernel<TIn, CIN, true>), dim3((unsigned)grid), dim3(128), smem, st, tm, p, dz,
+                     partial, *fuse);
+  } else {
+    SSD3D_LAUNCH_PDL((stem_wgrad_tile_kernel<TIn, CIN, false>), dim3((unsigned)grid), dim3(128), smem, st, tm, p, dz,
+                     partial, StemBnFuse{});
+  }
   *slabs = (int)grid;
   return SSD3D_OK;
 }
@@ -718,14 +784,26 @@ extern "C" int ssd3d_stem_conv_bn_relu(const void* x, int x_is_bf16, const void*
 // Tile-based stem weight gradient (used by ssd3d_stem_wgrad in train.cu): writes `*slabs` partial slabs of
 // (32, *kpad) fp32 to `partial`; SSD3D_ERR_UNSUPPORTED when TMA cannot address the input rows.
 namespace ssd3d {
+// bn (optional, 8 pointers: z, scale, shift, mean, invstd, dgamma, dbeta, &inv_m): fuse the stem unit's BatchNorm + ReLU
+// backward into the gradient load (`dz` is then the gradient w.r.t. the unit's output)
 int stem_wgrad_tiles(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W, int stride_d,
-                     float* partial, int max_slabs, int* slabs, int* kpad, cudaStream_t st) {
+                     float* partial, int max_slabs, int* slabs, int* kpad, cudaStream_t st, const void* const* bn) {
   if (!ssd3d_stem_tc_supported(x_is_bf16, Cin, W)) return SSD3D_ERR_UNSUPPORTED;
   StemParams p{};
   if (const int rc = stem_tiling(p, x_is_bf16, N, D, H, W, stride_d)) return rc;
   *kpad = (27 * Cin <= 64) ? 64 : 128;
   const __nv_bfloat16* g = static_cast<const __nv_bfloat16*>(dz);
-#define STEM_WG(T, DT, C) return launch_stem_wgrad<T, C>(x, p, DT, g, partial, max_slabs, slabs, st)
+  StemBnFuse fz{};
+  const StemBnFuse* fuse = nullptr;
+  if (bn) {
+    fz.z = static_cast<const __nv_bfloat16*>(bn[0]);
+    fz.scale = static_cast<const float*>(bn[1]); fz.shift = static_cast<const float*>(bn[2]);
+    fz.mean = static_cast<const float*>(bn[3]);  fz.invstd = static_cast<const float*>(bn[4]);
+    fz.dgamma = static_cast<const float*>(bn[5]); fz.dbeta = static_cast<const float*>(bn[6]);
+    fz.inv_m = *static_cast<const float*>(bn[7]);
+    fuse = &fz;
+  }
+#define STEM_WG(T, DT, C) return launch_stem_wgrad<T, C>(x, p, DT, g, partial, max_slabs, slabs, st, fuse)
   if (x_is_bf16) {
     switch (Cin) {
       case 1: STEM_WG(__nv_bfloat16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 1);

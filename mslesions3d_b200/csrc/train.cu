@@ -1731,7 +1731,35 @@ extern "C" int ssd3d_head_wgrad(const void* dO, const void* x, int N, int C, int
 
 namespace ssd3d {
 int stem_wgrad_tiles(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W, int stride_d,
-                     float* partial, int max_slabs, int* slabs, int* kpad, cudaStream_t st);   // conv_stem_tc.cu
+                     float* partial, int max_slabs, int* slabs, int* kpad, cudaStream_t st,
+                     const void* const* bn);   // conv_stem_tc.cu
+}
+
+// The stem unit's backward in two launches instead of three: `ssd3d_bn_unit_bwd` with dz = NULL leaves only the
+// statistics (dgamma, dbeta); this entry point then applies the BatchNorm + ReLU backward to the gradient rows while
+// it loads them for the weight gradient (conv_stem_tc.cu): dz of the first layer is never materialised (nothing
+// upstream needs it).  SSD3D_ERR_UNSUPPORTED where the TMA tile kernel does not take the shape.
+extern "C" int ssd3d_stem_wgrad_bn(const void* z, const void* grad_a, const void* x, int x_is_bf16, int N, int Cin, int D,
+                                   int H, int W, int stride_d, const float* scale, const float* shift,
+                                   const float* mean, const float* invstd, const float* dgamma, const float* dbeta,
+                                   float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!z || !grad_a || !x || !scale || !shift || !mean || !invstd || !dgamma || !dbeta || !dw || !workspace)
+    return SSD3D_ERR_ARG;
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin < 1 || Cin > 4 || (stride_d != 1 && stride_d != 2)) return SSD3D_ERR_UNSUPPORTED;
+  const int Do = (D - 1) / stride_d + 1, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long M = (long long)N * Do * Ho * Wo;
+  if (M < 128 * 148) return SSD3D_ERR_UNSUPPORTED;
+  if (workspace_bytes < ssd3d_wgrad_workspace_bytes(M, 32, 27 * Cin)) return SSD3D_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float inv_m = (float)(1.0 / (double)M);
+  const void* bn[8] = {z, scale, shift, mean, invstd, dgamma, dbeta, &inv_m};
+  const int kp = (27 * Cin <= 64) ? 64 : 128;
+  const int max_slabs = (int)std::min<long long>(workspace_bytes / (32ll * kp * 4), 4096);
+  int S = 0, kpad = 0;
+  const int rc = stem_wgrad_tiles(grad_a, x, x_is_bf16, N, Cin, D, H, W, stride_d, static_cast<float*>(workspace),
+                                  max_slabs, &S, &kpad, st, bn);
+  if (rc != SSD3D_OK) return rc;
+  return launch_sum_partials((const float*)workspace, S, 32ll * kpad, 32, 27 * Cin, kpad, 27 * Cin, dw, st);
 }
 
 extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, int N, int Cin, int D, int H, int W,
@@ -1750,7 +1778,7 @@ extern "C" int ssd3d_stem_wgrad(const void* dz, const void* x, int x_is_bf16, in
     const int max_slabs = (int)std::min<long long>(workspace_bytes / (32ll * kp * 4), 4096);
     int S = 0, kpad = 0;
     const int rc = stem_wgrad_tiles(dz, x, x_is_bf16, N, Cin, D, H, W, stride_d, static_cast<float*>(workspace),
-                                    max_slabs, &S, &kpad, st);
+                                    max_slabs, &S, &kpad, st, nullptr);
     if (rc == SSD3D_OK) {
       if (const int rc_s = launch_sum_partials((const float*)workspace, S, 32ll * kpad, 32, 27 * Cin, kpad, 27 * Cin, dw, st)) return rc_s;
       return SSD3D_OK;

@@ -840,6 +840,34 @@ def stem_wgrad(dz: torch.Tensor, x: torch.Tensor, stride_d: int, dw: torch.Tenso
     LAUNCHES[0] += 2
 
 
+def stem_unit_backward(z: torch.Tensor, grad_a: torch.Tensor, st: BNState, dgamma: torch.Tensor, dbeta: torch.Tensor,
+                       x: torch.Tensor, stride_d: int, dw: torch.Tensor) -> bool:
+    """Backward of the stem unit (conv -> BN -> ReLU) in two launches: BatchNorm statistics only (dgamma, dbeta), then the
+    weight-gradient kernel applies the BatchNorm + ReLU backward to the gradient rows as it loads them -- dz is never
+    written.  False (nothing launched) where that path does not take the shape: the caller then runs
+    ``bn_relu_backward`` + ``stem_wgrad``."""
+    n, c, do, ho, wo = z.shape
+    m = n * do * ho * wo
+    _, cin, d, h, w = x.shape
+    lib = _lib.load()
+    if not (_bn_unit_enabled() and lib.ssd3d_bn_unit_supported(m, c)) or m < 128 * 148 or cin > 4:
+        return False
+    if not lib.ssd3d_stem_tc_supported(int(x.dtype == BF16), cin, w):
+        return False
+    ws = _workspace(max(lib.ssd3d_bn_workspace_bytes(c), lib.ssd3d_wgrad_workspace_bytes(m, 32, 27 * cin)), x.device)
+    rc = lib.ssd3d_bn_unit_bwd(z.data_ptr(), grad_a.data_ptr(), m, c, st.scale.data_ptr(), st.shift.data_ptr(),
+                               st.mean.data_ptr(), st.invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), 0,
+                               ws.data_ptr(), ws.numel(), _sync_words(z.device).data_ptr(), _stream())
+    _lib.check(rc, "ssd3d_bn_unit_bwd (statistics only)")
+    rc = lib.ssd3d_stem_wgrad_bn(z.data_ptr(), grad_a.data_ptr(), x.data_ptr(), int(x.dtype == BF16), n, cin, d, h, w,
+                                 stride_d, st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
+                                 st.invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dw.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), _stream())
+    _lib.check(rc, "ssd3d_stem_wgrad_bn")
+    LAUNCHES[0] += 3
+    return True
+
+
 def head_grad_pack(dlocs, dscores, n, d, h, w, bpl, n_classes, prior_offset, dbias_loc, dbias_cls) -> torch.Tensor:
     """-> dO (G, N*D*H*W, 16) bf16 gradient rows of one head in G = ceil(bpl*(6+n_classes)/16) column groups;
     fills the two bias gradients."""

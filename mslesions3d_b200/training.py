@@ -451,10 +451,16 @@ class TrainEngine:
             else:
                 if r is not None:
                     r["g"] = snap(g)
-                dz = ops.bn_relu_backward(u["z"], g, u["st"], grads[p + ".1.weight"], grads[p + ".1.bias"])
-                if r is not None:
-                    r["dz"] = snap(dz)
-                ops.stem_wgrad(dz, u["x"], u["stride"], grads[p + ".0.weight"])
+                # first layer: nothing upstream needs dz, so (outside the tests' recording mode) it is never written --
+                # the weight-gradient kernel applies the BatchNorm + ReLU backward to the rows it loads
+                fused = (r is None and os.environ.get("SSD3D_STEM_BWD_FUSED", "1") != "0" and
+                         ops.stem_unit_backward(u["z"], g, u["st"], grads[p + ".1.weight"], grads[p + ".1.bias"],
+                                                u["x"], u["stride"], grads[p + ".0.weight"]))
+                if not fused:
+                    dz = ops.bn_relu_backward(u["z"], g, u["st"], grads[p + ".1.weight"], grads[p + ".1.bias"])
+                    if r is not None:
+                        r["dz"] = snap(dz)
+                    ops.stem_wgrad(dz, u["x"], u["stride"], grads[p + ".0.weight"])
                 g = None
         if sides is not None:
             for st in sides:

@@ -236,6 +236,33 @@ def test_stem_raw_wgrad(cin, n, size, sd, dtype):
     assert rel_l2(dw, w.grad) < 2e-3, rel_l2(dw, w.grad)
 
 
+@pytest.mark.parametrize("cin,n,size,sd,dtype", [(1, 2, (64, 64, 64), 2, torch.float32), (2, 1, (48, 64, 80), 2, torch.bfloat16),
+                                                 (1, 3, (40, 48, 56), 1, torch.float32)])
+def test_stem_unit_backward_fused_equals_two_step(cin, n, size, sd, dtype):
+    """ssd3d_bn_unit_bwd(dz = NULL) + ssd3d_stem_wgrad_bn (the BatchNorm + ReLU backward applied to the gradient rows
+    inside the weight-gradient kernel, dz never written) against bn_relu_backward + stem_wgrad: bit-identical."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11 * cin + n)
+    x = bf16r(torch.randn((n, cin) + size, generator=g)).to(dtype).cuda()
+    w = bf16r(torch.randn((32, cin, 3, 3, 3), generator=g) * 0.2).cuda()
+    z = ops.stem_conv_raw(x, ops.pack_stem_weight(w), sd)
+    bn = torch.nn.BatchNorm3d(32)
+    with torch.no_grad():
+        bn.weight.copy_(0.5 + torch.rand(32, generator=g))
+        bn.bias.copy_(0.2 * torch.randn(32, generator=g))
+    bn = bn.cuda().train()
+    a, st = ops.bn_train_relu(z, bn, None)
+    ga = to_cl(bf16r(torch.randn(tuple(z.shape), generator=g)))
+    dg1, db1, dw1 = torch.empty(32, device="cuda"), torch.empty(32, device="cuda"), torch.empty_like(w)
+    assert ops.stem_unit_backward(z, ga, st, dg1, db1, x, sd, dw1), "fused path refused a shape it should take"
+    dg2, db2, dw2 = torch.empty(32, device="cuda"), torch.empty(32, device="cuda"), torch.empty_like(w)
+    dz = ops.bn_relu_backward(z, ga.clone(), st, dg2, db2)
+    ops.stem_wgrad(dz, x, sd, dw2)
+    assert torch.equal(dg1, dg2) and torch.equal(db1, db2)
+    assert torch.equal(dw1, dw2), float((dw1 - dw2).abs().max())
+    assert bool(torch.isfinite(dw1).all()) and float(dw1.abs().max()) > 0
+
+
 # ---------------------------------------------------------------------------------------------------
 # SSD heads: gradient rows, bias / weight / data gradients
 # ---------------------------------------------------------------------------------------------------
