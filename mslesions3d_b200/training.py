@@ -543,8 +543,17 @@ class _TrainPlan:
         # steps ahead of the device without rewriting memory an earlier copy still has to read
         self.offsets.copy_(torch.tensor(offs, dtype=torch.int32))
         if total:
-            self.gt_boxes[:total].copy_(torch.cat([b.reshape(-1, 6) for b in gt_boxes]).float(), non_blocking=True)
-            self.gt_labels[:total].copy_(torch.cat([l.reshape(-1) for l in gt_labels]).long(), non_blocking=True)
+            dev = self.gt_boxes.device
+            boxes = [b.reshape(-1, 6) for b in gt_boxes]
+            labels = [l.reshape(-1) for l in gt_labels]
+            if all(b.device == dev and b.dtype == torch.float32 for b in boxes) and \
+                    all(l.device == dev and l.dtype == torch.int64 for l in labels):
+                # device-resident ground truth: concatenate straight into the staging buffers (one launch each)
+                torch.cat(boxes, out=self.gt_boxes[:total])
+                torch.cat(labels, out=self.gt_labels[:total])
+            else:
+                self.gt_boxes[:total].copy_(torch.cat(boxes).float(), non_blocking=True)
+                self.gt_labels[:total].copy_(torch.cat(labels).long(), non_blocking=True)
 
     def _run(self, model, with_optimizer: bool):
         eng = model.train_engine()
