@@ -381,7 +381,7 @@ class TrainEngine:
         # around them, so overlapping buys nothing, and their persistent CTAs (180 registers, ~200 KB of shared
         # memory) would keep the all-resident BatchNorm grids of the main chain (csrc/bn_unit.cu) waiting for SMs.
         # They run in order on the main stream.
-        heavy_bytes = float(os.environ.get("SSD3D_TRAIN_HEAVY_LEAF_MB", "4")) * 2 ** 20
+        heavy_bytes = float(os.environ.get("SSD3D_TRAIN_HEAVY_LEAF_MB", "32")) * 2 ** 20
 
         def leaf(fn, *tensors, nbytes=0):
             if side is None or nbytes >= heavy_bytes:
