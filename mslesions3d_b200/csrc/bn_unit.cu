@@ -1018,6 +1018,19 @@ int bn_unit_plan(long long M, int C, long long* rows_per_cta) {
 
 using namespace ssd3d;
 
+// A launch the driver REFUSES (cooperative grid larger than what can be co-resident on this context -- MPS / green
+// contexts with fewer SMs --, cluster shape not schedulable, ...) has not run anything: clear the error and report
+// "unsupported", so that the caller takes the three-launch passes of train.cu instead of failing.
+static int bn_launch_result(cudaError_t e) {
+  if (e == cudaSuccess) return SSD3D_OK;
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported ||
+      e == cudaErrorInvalidClusterSize || e == cudaErrorInvalidConfiguration) {
+    (void)cudaGetLastError();
+    return SSD3D_ERR_UNSUPPORTED;
+  }
+  return (int)e;
+}
+
 static const bool g_bn_cluster = [] { const char* e = getenv("SSD3D_BN_CLUSTER"); return !(e && e[0] == '0'); }();
 // SSD3D_BN_TILE=0: the two-barrier bn_unit_kernel for the larger maps (A/B measurements)
 static const bool g_bn_tile = [] { const char* e = getenv("SSD3D_BN_TILE"); return !(e && e[0] == '0'); }();
@@ -1058,7 +1071,7 @@ extern "C" int ssd3d_bn_unit_fwd(const void* z, int64_t M, int C, const float* g
   p.scale = scale; p.shift = shift; p.mean = mean; p.invstd = invstd;
   if (K > 0) {
     const cudaError_t e = launch_bn_cluster_r<0>(p, K, R, static_cast<cudaStream_t>(stream));
-    return e == cudaSuccess ? SSD3D_OK : (int)e;
+    return bn_launch_result(e);
   }
   if (g_bn_tile) {
     BnTileParams q{};
@@ -1066,11 +1079,11 @@ extern "C" int ssd3d_bn_unit_fwd(const void* z, int64_t M, int C, const float* g
     const int GT = bn_tile_plan(M, C, &q);
     if (GT > 0 && workspace_bytes >= (int64_t)GT * 128 * 4) {
       const cudaError_t e = launch_bn_tile<0>(q, GT, static_cast<cudaStream_t>(stream));
-      return e == cudaSuccess ? SSD3D_OK : (int)e;
+      return bn_launch_result(e);
     }
   }
   const cudaError_t e = launch_bn_unit<0>(p, G, static_cast<cudaStream_t>(stream));
-  return e == cudaSuccess ? SSD3D_OK : (int)e;
+  return bn_launch_result(e);
 }
 
 extern "C" int ssd3d_bn_unit_bwd(const void* z, const void* grad_a, int64_t M, int C, const float* scale,
@@ -1097,7 +1110,7 @@ extern "C" int ssd3d_bn_unit_bwd(const void* z, const void* grad_a, int64_t M, i
   p.inv_m = (float)(1.0 / (double)M);
   if (K > 0) {
     const cudaError_t e = launch_bn_cluster_r<1>(p, K, R, static_cast<cudaStream_t>(stream));
-    return e == cudaSuccess ? SSD3D_OK : (int)e;
+    return bn_launch_result(e);
   }
   if (g_bn_tile) {
     BnTileParams q{};
@@ -1105,9 +1118,9 @@ extern "C" int ssd3d_bn_unit_bwd(const void* z, const void* grad_a, int64_t M, i
     const int GT = bn_tile_plan(M, C, &q);
     if (GT > 0 && workspace_bytes >= (int64_t)GT * 128 * 4) {
       const cudaError_t e = launch_bn_tile<1>(q, GT, static_cast<cudaStream_t>(stream));
-      return e == cudaSuccess ? SSD3D_OK : (int)e;
+      return bn_launch_result(e);
     }
   }
   const cudaError_t e = launch_bn_unit<1>(p, G, static_cast<cudaStream_t>(stream));
-  return e == cudaSuccess ? SSD3D_OK : (int)e;
+  return bn_launch_result(e);
 }

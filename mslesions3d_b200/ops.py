@@ -780,11 +780,13 @@ def bn_train_relu(z: torch.Tensor, bn: torch.nn.BatchNorm3d, nan_flag: Optional[
             _ptr(bn.running_mean if track else None), _ptr(bn.running_var if track else None), _ptr(nbt),
             st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(), st.invstd.data_ptr(),
             a.data_ptr(), _ptr(nan_flag), ws.data_ptr(), ws.numel())
+    rc = _lib.SSD3D_ERR_UNSUPPORTED
     if _bn_unit_enabled() and lib.ssd3d_bn_unit_supported(m, c):
         rc = lib.ssd3d_bn_unit_fwd(*args, _sync_words(z.device).data_ptr(), _stream())
-        _lib.check(rc, "ssd3d_bn_unit_fwd")
-        LAUNCHES[0] += 1
-    else:
+        if rc != _lib.SSD3D_ERR_UNSUPPORTED:     # unsupported = the driver refused the launch: three-launch path
+            _lib.check(rc, "ssd3d_bn_unit_fwd")
+            LAUNCHES[0] += 1
+    if rc == _lib.SSD3D_ERR_UNSUPPORTED:
         rc = lib.ssd3d_bn_train_fwd(*args, _stream())
         _lib.check(rc, "ssd3d_bn_train_fwd")
         LAUNCHES[0] += 3
@@ -805,11 +807,13 @@ def bn_relu_backward(z: torch.Tensor, grad_a: torch.Tensor, st: BNState, dgamma:
     m = n * d * h * w
     args = (z.data_ptr(), grad_a.data_ptr(), m, c, st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
             st.invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), grad_a.data_ptr(), ws.data_ptr(), ws.numel())
+    rc = _lib.SSD3D_ERR_UNSUPPORTED
     if _bn_unit_enabled() and lib.ssd3d_bn_unit_supported(m, c):
         rc = lib.ssd3d_bn_unit_bwd(*args, _sync_words(z.device).data_ptr(), _stream())
-        _lib.check(rc, "ssd3d_bn_unit_bwd")
-        LAUNCHES[0] += 1
-    else:
+        if rc != _lib.SSD3D_ERR_UNSUPPORTED:
+            _lib.check(rc, "ssd3d_bn_unit_bwd")
+            LAUNCHES[0] += 1
+    if rc == _lib.SSD3D_ERR_UNSUPPORTED:
         rc = lib.ssd3d_bn_relu_bwd(*args, _stream())
         _lib.check(rc, "ssd3d_bn_relu_bwd")
         LAUNCHES[0] += 3
@@ -858,6 +862,8 @@ def stem_unit_backward(z: torch.Tensor, grad_a: torch.Tensor, st: BNState, dgamm
     rc = lib.ssd3d_bn_unit_bwd(z.data_ptr(), grad_a.data_ptr(), m, c, st.scale.data_ptr(), st.shift.data_ptr(),
                                st.mean.data_ptr(), st.invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), 0,
                                ws.data_ptr(), ws.numel(), _sync_words(z.device).data_ptr(), _stream())
+    if rc == _lib.SSD3D_ERR_UNSUPPORTED:         # the driver refused the launch: nothing ran, take the two-step path
+        return False
     _lib.check(rc, "ssd3d_bn_unit_bwd (statistics only)")
     rc = lib.ssd3d_stem_wgrad_bn(z.data_ptr(), grad_a.data_ptr(), x.data_ptr(), int(x.dtype == BF16), n, cin, d, h, w,
                                  stride_d, st.scale.data_ptr(), st.shift.data_ptr(), st.mean.data_ptr(),
