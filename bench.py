@@ -345,6 +345,48 @@ def train_leg(dev, rank, world, steps, warmup, barrier, max_over_ranks):
     return out
 
 
+def train_roofline(dev):
+    """Roofline object of the training step's largest kernel: the BatchNorm + ReLU backward of the stem-sized map
+    (16 x 48^3 x 32 bf16 = 113 MB per tensor; csrc/bn_unit.cu bn_tile_kernel<1>).  Algorithmic bytes per launch: the
+    saved raw conv output z and the incoming gradient read once, dz written once (the kernel reads z and g a second
+    time for the apply phase -- that shows as the distance from the peak).  20 back-to-back launches over three
+    rotating (z, g) pairs (680 MB > L2) between one CUDA event pair.  Never fatal."""
+    from mslesions3d_b200 import ops
+    n, c = TRAIN_BATCH, 32
+    d, h, w = (TRAIN_SIZE[0] + 1) // 2, (TRAIN_SIZE[1] + 1) // 2, (TRAIN_SIZE[2] + 1) // 2
+    peak, peak_src = load_peaks()
+    bn = torch.nn.BatchNorm3d(c).to(dev).train()
+    sets = []
+    gen = torch.Generator(device=dev).manual_seed(3)
+    for _ in range(3):
+        z = torch.randn((n, c, d, h, w), device=dev, generator=gen).to(torch.bfloat16).contiguous(
+            memory_format=torch.channels_last_3d)
+        g = torch.randn((n, c, d, h, w), device=dev, generator=gen).to(torch.bfloat16).contiguous(
+            memory_format=torch.channels_last_3d)
+        _, st = ops.bn_train_relu(z, bn, None)
+        sets.append((z, g, st))
+    dgamma, dbeta = torch.empty(c, device=dev), torch.empty(c, device=dev)
+    for z, g, st in sets:
+        ops.bn_relu_backward(z, g, st, dgamma, dbeta)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 21
+    e0.record()
+    for i in range(launches):
+        z, g, st = sets[i % 3]
+        ops.bn_relu_backward(z, g, st, dgamma, dbeta)
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / launches
+    algo = 3 * n * c * d * h * w * 2
+    achieved = algo / (k_ms * 1e-3) / 1e9
+    return {"kernel": "bn_tile_kernel<1> (train-mode BatchNorm + ReLU backward of the stem map, 16 x 48^3 x 32: column "
+                      "statistics, one barrier per channel group, dz in place)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "algorithmic_bytes_per_launch": algo, "kernel_ms": k_ms, "peak_source": peak_src,
+            "timing": "%d back-to-back launches between one CUDA event pair, three rotating (z, g) pairs = 680 MB" % launches}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -590,6 +632,12 @@ def main():
             if world > 1:
                 raise
             extras["train_error"] = repr(exc)
+        if rank == 0 and "train" in extras:
+            try:
+                extras["train"]["roofline"] = train_roofline(dev)
+            except Exception as exc:      # noqa: BLE001
+                extras["train"]["roofline_error"] = repr(exc)
+            torch.cuda.empty_cache()
 
     clocks = sampler.stop() if rank == 0 else None
 
