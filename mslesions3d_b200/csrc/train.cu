@@ -807,7 +807,7 @@ static int head_wgrad_splits(long long M, int C) {
 template <int LANES>
 __global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restrict__ partial, int S,
                                                            long long slab, int rows, int cols, int src_ld,
-                                                           int dst_ld, float* __restrict__ out) {
+                                                           int dst_ld, int dst_cs, float* __restrict__ out) {
   constexpr int OUTS = 1024 / LANES;
   __shared__ float red[LANES > 1 ? LANES : 1][LANES > 1 ? OUTS : 1];
   pdl_wait();
@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restr
     for (int k = lane; k < S; k += LANES) s += partial[(size_t)k * slab + (size_t)r * src_ld + c];
   }
   if constexpr (LANES == 1) {
-    if (valid) out[(size_t)r * dst_ld + c] = s;
+    if (valid) out[(size_t)r * dst_ld + (size_t)c * dst_cs] = s;
   } else {
     red[lane][ox] = s;
     __syncthreads();
@@ -830,23 +830,25 @@ __global__ void __launch_bounds__(1024) sum_partials_kernel(const float* __restr
       float t = red[0][ox];
 #pragma unroll
       for (int l = 1; l < LANES; ++l) t += red[l][ox];
-      out[(size_t)r * dst_ld + c] = t;
+      out[(size_t)r * dst_ld + (size_t)c * dst_cs] = t;
     }
   }
 }
 
+// dst_cs: stride between the columns of the OUTPUT (1 = plain rows; the depthwise slabs are tap-major [27][C] and land
+// as out[c*27 + tap]: rows = taps with dst_ld = 1, columns = channels with dst_cs = 27)
 static int launch_sum_partials(const float* partial, int S, long long slab, int rows, int cols, int src_ld, int dst_ld,
-                               float* out, cudaStream_t st) {
+                               float* out, cudaStream_t st, int dst_cs = 1) {
   const long long total = (long long)rows * cols;
   if (S <= 3) {
     SSD3D_LAUNCH_PDL(sum_partials_kernel<1>, dim3((unsigned)((total + 1023) / 1024)), dim3(1024), 0, st, partial, S, slab,
-                     rows, cols, src_ld, dst_ld, out);
+                     rows, cols, src_ld, dst_ld, dst_cs, out);
   } else if (S <= 24) {
     SSD3D_LAUNCH_PDL(sum_partials_kernel<4>, dim3((unsigned)((total + 255) / 256)), dim3(1024), 0, st, partial, S, slab,
-                     rows, cols, src_ld, dst_ld, out);
+                     rows, cols, src_ld, dst_ld, dst_cs, out);
   } else {
     SSD3D_LAUNCH_PDL(sum_partials_kernel<32>, dim3((unsigned)((total + 31) / 32)), dim3(1024), 0, st, partial, S, slab,
-                     rows, cols, src_ld, dst_ld, out);
+                     rows, cols, src_ld, dst_ld, dst_cs, out);
   }
   return SSD3D_OK;
 }
@@ -1280,7 +1282,7 @@ __global__ void __launch_bounds__(256, 2) dw_dgrad_s2_block_kernel(const bf16* _
 }
 
 // weight: dw[c][k] = sum_o dz[o][c] * x[S*o + k - 1][c].  thread = (8 channels, kd, voxel lane g): 9 taps x 8
-// channels of accumulators; block partial [C][27] after a fixed-order reduction over the voxel lanes.
+// channels of accumulators; block partial [27][C] (tap-major) after a fixed-order reduction over the voxel lanes.
 template <int S>
 __global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ x,
                                                        int N, int C, int D, int H, int W, int Do, int Ho, int Wo,
@@ -1351,8 +1353,11 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ 
       }
     }
     if (g == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dst[(size_t)(c0 + j) * 27 + kd * 9 + t] = acc[t][j];
+      // tap-major slab [27][C]: the thread's 8 channels are one 32-byte run (the [C][27] layout scattered 72 single
+      // floats per thread, 27 floats apart -- the slab writes, not the loads, were most of this kernel's time)
+      float* d8 = dst + (size_t)(kd * 9 + t) * C + c0;
+      *reinterpret_cast<float4*>(d8) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+      *reinterpret_cast<float4*>(d8 + 4) = make_float4(acc[t][4], acc[t][5], acc[t][6], acc[t][7]);
     }
   }
 }
@@ -1938,7 +1943,7 @@ extern "C" int ssd3d_dwconv3d_wgrad(const void* dz, const void* x, int N, int C,
     SSD3D_LAUNCH_PDL(dw_wgrad_kernel<2>, dim3(B), dim3(threads), 0, st, gp, xp, N, C, D, H, W, Do, Ho, Wo, Mo, vpb, G,
                      partial);
   if (const int rc_s = launch_sum_partials((const float*)partial,
-                   B, (long long)C * 27, C, 27, 27, 27, dw, st)) return rc_s;
+                   B, (long long)C * 27, 27, C, C, 1, dw, st, 27)) return rc_s;
   return SSD3D_OK;
 }
 
